@@ -1,0 +1,368 @@
+"""Lower Python link/source callables to a register bytecode the device evaluates.
+
+The reference evaluates film, conductance, flow, heat, flux and boundary-temperature
+callables as vectorised numpy closures on every right-hand-side call
+(thermca/network.py:773-796; signatures thermca/links.py:39, thermca/source.py:21).
+A Python closure cannot run on the device, so at lowering time each callable is
+called ONCE with symbolic arguments (:class:`Sym`).  Every numpy ufunc, ``where``
+and ``interp`` (the material tables, thermca/materials.py:120-130,359) it applies is
+recorded as one instruction of a straight-line program; the fused network kernel
+(csrc/network.cu) interprets that program per link in IEEE fp64, operation by
+operation in the order Python executed them.
+
+Time-dependent inputs: ``Input.value`` is a shared mutable 0-d array captured when
+the model is built (thermca/input.py:127-146).  When the traced function touches one
+of those arrays (identity match) an ``INPUT k`` leaf is emitted instead of a
+constant, so the value is re-read on every evaluation.
+
+A callable that branches on data in Python (``if v < 2e-4``, e.g.
+thermca/lib/bearing.py:131) or calls unvectorised code cannot be traced; lowering
+raises :class:`UntraceableError` naming it.  There is no host-callback fallback.
+"""
+from __future__ import annotations
+
+import functools
+import numbers
+import types
+import warnings
+
+import numpy as np
+
+# ---- opcodes (keep in sync with csrc/vm.cuh) ---------------------------------
+OPS = [
+    "ARG", "CONST", "INPUT",                      # leaves: a = index
+    "ADD", "SUB", "MUL", "DIV", "POW", "MIN", "MAX",
+    "LT", "LE", "GT", "GE", "EQ", "NE", "AND", "OR",
+    "NEG", "ABS", "SQRT", "EXP", "LOG", "LOG10", "SIN", "COS", "TAN", "TANH",
+    "ARCTAN", "NOT", "SQUARE", "RECIP", "SIGN", "CBRT", "LOG2", "EXP2",
+    "FLOOR", "CEIL", "ISNAN",
+    "WHERE",                                      # a ? b : c
+    "INTERP",                                     # table a, x = b
+    "ARCTAN2", "FMOD",
+]
+OP = {n: i for i, n in enumerate(OPS)}
+MAX_PROGRAM = 1024
+
+
+class UntraceableError(NotImplementedError):
+    pass
+
+
+_BINARY_UFUNC = {
+    np.add: "ADD", np.subtract: "SUB", np.multiply: "MUL", np.true_divide: "DIV",
+    np.power: "POW", np.float_power: "POW", np.minimum: "MIN", np.maximum: "MAX",
+    np.fmin: "MIN", np.fmax: "MAX",
+    np.less: "LT", np.less_equal: "LE", np.greater: "GT", np.greater_equal: "GE",
+    np.equal: "EQ", np.not_equal: "NE", np.logical_and: "AND", np.logical_or: "OR",
+    np.arctan2: "ARCTAN2", np.fmod: "FMOD",
+}
+_UNARY_UFUNC = {
+    np.negative: "NEG", np.absolute: "ABS", np.fabs: "ABS", np.sqrt: "SQRT", np.exp: "EXP",
+    np.log: "LOG", np.log10: "LOG10", np.sin: "SIN", np.cos: "COS", np.tan: "TAN",
+    np.tanh: "TANH", np.arctan: "ARCTAN", np.logical_not: "NOT", np.square: "SQUARE",
+    np.reciprocal: "RECIP", np.sign: "SIGN", np.cbrt: "CBRT", np.log2: "LOG2",
+    np.exp2: "EXP2", np.floor: "FLOOR", np.ceil: "CEIL", np.isnan: "ISNAN",
+}
+
+
+class Program:
+    """Straight-line program; value ``k`` is produced by instruction ``k``."""
+
+    def __init__(self, n_args, inputs, tables):
+        self.n_args = n_args
+        self.code = []            # (op, a, b, c)
+        self.consts = []          # float64 pool
+        self._const_ix = {}
+        self._inputs = inputs     # list of 0-d ndarrays (identity match) -> slot index
+        self._tables = tables     # shared TableRegistry
+        self.result = None
+
+    def emit(self, op, a=0, b=0, c=0):
+        self.code.append((OP[op], int(a), int(b), int(c)))
+        if len(self.code) > MAX_PROGRAM:
+            raise UntraceableError(f"link program longer than {MAX_PROGRAM} instructions")
+        return len(self.code) - 1
+
+    def const(self, value):
+        value = float(value)
+        key = np.float64(value).tobytes()
+        if key not in self._const_ix:
+            self.consts.append(value)
+            self._const_ix[key] = self.emit("CONST", len(self.consts) - 1)
+        return self._const_ix[key]
+
+    def leaf(self, x):
+        """Value index for a non-symbolic operand."""
+        if isinstance(x, Sym):
+            if x.prog is not self:
+                raise UntraceableError("symbol from another trace")
+            return x.ix
+        if isinstance(x, np.ndarray):
+            for k, arr in enumerate(self._inputs):
+                if x is arr or (x.base is not None and x.base is arr):
+                    return self.emit("INPUT", k)
+            if x.size == 1:
+                return self.const(x.reshape(()).item())
+            raise UntraceableError("array-valued parameters (one value per sub-link) are not lowered yet")
+        if isinstance(x, (numbers.Real, np.generic, bool, np.bool_)):
+            return self.const(x)
+        raise UntraceableError(f"operand of type {type(x).__name__} in link function")
+
+    def arrays(self):
+        code = np.asarray(self.code, dtype=np.int32).reshape(-1, 4)
+        return code, np.asarray(self.consts, dtype=np.float64), np.int32(self.result)
+
+
+class TableRegistry:
+    """Piecewise-linear tables shared by all programs (material properties)."""
+
+    def __init__(self):
+        self.tables = []          # list of (xp, fp)
+        self._ix = {}
+
+    def index(self, xp, fp):
+        xp = np.ascontiguousarray(xp, dtype=np.float64).ravel()
+        fp = np.ascontiguousarray(fp, dtype=np.float64).ravel()
+        if xp.size != fp.size or xp.size == 0:
+            raise UntraceableError("interp table with mismatching or empty axes")
+        key = (xp.tobytes(), fp.tobytes())
+        if key not in self._ix:
+            self.tables.append((xp, fp))
+            self._ix[key] = len(self.tables) - 1
+        return self._ix[key]
+
+
+class Sym:
+    """Symbolic fp64 value inside a trace (numpy duck array of shape ``(1,)``)."""
+
+    __array_priority__ = 1000.0
+    shape = (1,)
+    ndim = 1
+    size = 1
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, prog, ix):
+        self.prog = prog
+        self.ix = ix
+
+    # -- python operators ------------------------------------------------------
+    def _bin(self, op, other, swap=False):
+        p = self.prog
+        a, b = (p.leaf(other), self.ix) if swap else (self.ix, p.leaf(other))
+        return Sym(p, p.emit(op, a, b))
+
+    def __add__(self, o): return self._bin("ADD", o)
+    def __radd__(self, o): return self._bin("ADD", o, True)
+    def __sub__(self, o): return self._bin("SUB", o)
+    def __rsub__(self, o): return self._bin("SUB", o, True)
+    def __mul__(self, o): return self._bin("MUL", o)
+    def __rmul__(self, o): return self._bin("MUL", o, True)
+    def __truediv__(self, o): return self._bin("DIV", o)
+    def __rtruediv__(self, o): return self._bin("DIV", o, True)
+    def __pow__(self, o): return self._bin("POW", o)
+    def __rpow__(self, o): return self._bin("POW", o, True)
+    def __lt__(self, o): return self._bin("LT", o)
+    def __le__(self, o): return self._bin("LE", o)
+    def __gt__(self, o): return self._bin("GT", o)
+    def __ge__(self, o): return self._bin("GE", o)
+    def __eq__(self, o): return self._bin("EQ", o)
+    def __ne__(self, o): return self._bin("NE", o)
+    def __and__(self, o): return self._bin("AND", o)
+    def __rand__(self, o): return self._bin("AND", o, True)
+    def __or__(self, o): return self._bin("OR", o)
+    def __ror__(self, o): return self._bin("OR", o, True)
+    def __invert__(self): return Sym(self.prog, self.prog.emit("NOT", self.ix))
+    def __neg__(self): return Sym(self.prog, self.prog.emit("NEG", self.ix))
+    def __pos__(self): return self
+    def __abs__(self): return Sym(self.prog, self.prog.emit("ABS", self.ix))
+    __hash__ = None
+
+    def __bool__(self):
+        raise UntraceableError(
+            "the callable branches on a temperature-dependent value in Python "
+            "(`if`/`and`/`or` on data); use numpy.where so it can run on the device")
+
+    def __len__(self):
+        return 1
+
+    def __iter__(self):
+        raise UntraceableError("the callable iterates over its array argument in Python")
+
+    def __getitem__(self, key):
+        raise UntraceableError("the callable indexes its array argument in Python")
+
+    def __float__(self):
+        raise UntraceableError("the callable converts a temperature-dependent value to float")
+
+    # numpy helpers commonly called as methods
+    def mean(self, *a, **k): return self
+    def ravel(self): return self
+    def copy(self): return self
+
+    # -- numpy protocols ---------------------------------------------------------
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs.get("out") is not None:
+            raise UntraceableError(f"numpy.{ufunc.__name__}.{method} / out= in link function")
+        p = self.prog
+        if ufunc in _BINARY_UFUNC and len(inputs) == 2:
+            return Sym(p, p.emit(_BINARY_UFUNC[ufunc], p.leaf(inputs[0]), p.leaf(inputs[1])))
+        if ufunc in _UNARY_UFUNC and len(inputs) == 1:
+            return Sym(p, p.emit(_UNARY_UFUNC[ufunc], p.leaf(inputs[0])))
+        raise UntraceableError(f"numpy.{ufunc.__name__} is not lowered to the device")
+
+    def __array_function__(self, func, types, args, kwargs):
+        p = self.prog
+        if func is np.where and len(args) == 3:
+            return Sym(p, p.emit("WHERE", p.leaf(args[0]), p.leaf(args[1]), p.leaf(args[2])))
+        if func is np.interp and len(args) == 3 and not kwargs:
+            tid = p._tables.index(args[1], args[2])
+            return Sym(p, p.emit("INTERP", tid, p.leaf(args[0])))
+        if func in (np.mean, np.sum, np.ravel, np.asarray, np.asanyarray, np.atleast_1d) and len(args) == 1:
+            return args[0]      # one symbolic element per link
+        if func is np.clip and len(args) == 3:
+            lo = p.emit("MAX", p.leaf(args[0]), p.leaf(args[1]))
+            return Sym(p, p.emit("MIN", lo, p.leaf(args[2])))
+        raise UntraceableError(f"numpy.{func.__name__} is not lowered to the device")
+
+
+def _substitute(obj, mapping, depth=0):
+    """Copy of ``obj`` with every captured reference to an Input value array (closure
+    cells, default arguments, dict/list/tuple members, nested closures such as the
+    ``kwargs0`` of thermca/_utils/func_tools.py:54-58) replaced by its symbol."""
+    if id(obj) in mapping:
+        return mapping[id(obj)]
+    if depth > 8:
+        return obj
+    if isinstance(obj, types.FunctionType):
+        cells = obj.__closure__ or ()
+        new_cells = [_substitute(c.cell_contents, mapping, depth + 1) for c in cells]
+        defaults = obj.__defaults__
+        new_defaults = tuple(_substitute(d, mapping, depth + 1) for d in defaults) if defaults else defaults
+        changed = any(n is not c.cell_contents for n, c in zip(new_cells, cells)) or (
+            defaults is not None and any(n is not d for n, d in zip(new_defaults, defaults)))
+        if not changed:
+            return obj
+        f = types.FunctionType(obj.__code__, obj.__globals__, obj.__name__, new_defaults,
+                               tuple(types.CellType(n) for n in new_cells))
+        f.__kwdefaults__ = obj.__kwdefaults__
+        f.__qualname__ = obj.__qualname__
+        return f
+    if isinstance(obj, functools.partial):
+        return functools.partial(_substitute(obj.func, mapping, depth + 1),
+                                 *[_substitute(a, mapping, depth + 1) for a in obj.args],
+                                 **{k: _substitute(v, mapping, depth + 1) for k, v in obj.keywords.items()})
+    if isinstance(obj, dict):
+        new = {k: _substitute(v, mapping, depth + 1) for k, v in obj.items()}
+        return new if any(new[k] is not obj[k] for k in obj) else obj
+    if isinstance(obj, (list, tuple)) and len(obj) <= 64:
+        new = [_substitute(v, mapping, depth + 1) for v in obj]
+        return type(obj)(new) if any(n is not o for n, o in zip(new, obj)) else obj
+    return obj
+
+
+def trace(func, n_args, inputs, tables, extra_args=(), input_objs=None, validate=True):
+    """Trace ``func(sym_0 .. sym_{n_args-1}, *extra_args)`` into a :class:`Program`.
+
+    ``inputs`` are the shared 0-d value arrays of the model's ``Input`` elements and
+    ``input_objs`` the elements themselves: while tracing, every reference to such an
+    array is a symbol, so arithmetic done purely on Input values is recorded too."""
+    prog = Program(n_args, inputs, tables)
+    syms = [Sym(prog, prog.emit("ARG", k)) for k in range(n_args)]
+    in_syms = [Sym(prog, prog.emit("INPUT", k)) for k in range(len(inputs))]
+    mapping = {id(arr): s for arr, s in zip(inputs, in_syms)}
+    name = getattr(func, "__qualname__", repr(func))
+    saved = []
+    try:
+        for obj, s in zip(input_objs or (), in_syms):
+            saved.append((obj, obj._value))
+            obj._value = s
+        fsub = _substitute(func, mapping) if mapping else func
+        out = fsub(*syms, *extra_args)
+    except (UntraceableError, TypeError) as e:
+        raise UntraceableError(f"cannot lower callable {name!r} to the device: {e}") from e
+    finally:
+        for obj, v in saved:
+            obj._value = v
+    prog.result = prog.leaf(out)
+    if validate:
+        _validate(func, prog, n_args, inputs, tables, extra_args, name)
+    return prog
+
+
+def _validate(func, prog, n_args, inputs, tables, extra_args, name):
+    """Evaluate the traced program on the host next to the callable itself on a few
+    sample temperatures; a mismatch means the trace missed a dependency."""
+    code, consts, result = prog.arrays()
+    in_vals = [float(np.asarray(a).reshape(-1)[0]) for a in inputs]
+    samples = np.array([[20.0, 35.0, 61.5, 90.0], [25.0, 20.0, 22.25, 40.0]])
+    args = [samples[k % 2].copy() for k in range(n_args)]
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            ref = np.broadcast_to(np.asarray(func(*args, *extra_args), dtype=np.float64), (4,)) \
+                if n_args else np.broadcast_to(np.asarray(func(*extra_args), dtype=np.float64), (4,))
+        except Exception:
+            return          # the callable cannot be probed standalone; keep the trace
+        got = run_program(code, consts, result, args if n_args else [samples[0]], in_vals,
+                          tables.tables)
+    if not np.allclose(got, ref, rtol=1e-12, atol=0.0, equal_nan=True):
+        raise UntraceableError(
+            f"traced program of {name!r} disagrees with the callable ({got} vs {ref}); it "
+            "probably computes with captured state the tracer cannot see")
+
+
+# ---- host interpreter (used by the CPU tests to check the tracer itself) --------
+def run_program(code, consts, result, args, inputs, tables):
+    """Evaluate a program with numpy; ``args`` is a list of equal-length arrays."""
+    n = len(np.atleast_1d(args[0])) if args else 1
+    val = [None] * len(code)
+    f = lambda x: np.broadcast_to(np.asarray(x, dtype=np.float64), (n,))
+    with np.errstate(all="ignore"):
+        for k, (op, a, b, c) in enumerate(code):
+            name = OPS[op]
+            if name == "ARG": v = f(args[a])
+            elif name == "CONST": v = f(consts[a])
+            elif name == "INPUT": v = f(inputs[a])
+            elif name == "ADD": v = val[a] + val[b]
+            elif name == "SUB": v = val[a] - val[b]
+            elif name == "MUL": v = val[a] * val[b]
+            elif name == "DIV": v = val[a] / val[b]
+            elif name == "POW": v = np.power(val[a], val[b])
+            elif name == "MIN": v = np.minimum(val[a], val[b])
+            elif name == "MAX": v = np.maximum(val[a], val[b])
+            elif name == "LT": v = (val[a] < val[b]).astype(np.float64)
+            elif name == "LE": v = (val[a] <= val[b]).astype(np.float64)
+            elif name == "GT": v = (val[a] > val[b]).astype(np.float64)
+            elif name == "GE": v = (val[a] >= val[b]).astype(np.float64)
+            elif name == "EQ": v = (val[a] == val[b]).astype(np.float64)
+            elif name == "NE": v = (val[a] != val[b]).astype(np.float64)
+            elif name == "AND": v = ((val[a] != 0) & (val[b] != 0)).astype(np.float64)
+            elif name == "OR": v = ((val[a] != 0) | (val[b] != 0)).astype(np.float64)
+            elif name == "NEG": v = -val[a]
+            elif name == "ABS": v = np.abs(val[a])
+            elif name == "SQRT": v = np.sqrt(val[a])
+            elif name == "EXP": v = np.exp(val[a])
+            elif name == "LOG": v = np.log(val[a])
+            elif name == "LOG10": v = np.log10(val[a])
+            elif name == "SIN": v = np.sin(val[a])
+            elif name == "COS": v = np.cos(val[a])
+            elif name == "TAN": v = np.tan(val[a])
+            elif name == "TANH": v = np.tanh(val[a])
+            elif name == "ARCTAN": v = np.arctan(val[a])
+            elif name == "NOT": v = (val[a] == 0).astype(np.float64)
+            elif name == "SQUARE": v = val[a] * val[a]
+            elif name == "RECIP": v = 1.0 / val[a]
+            elif name == "SIGN": v = np.sign(val[a])
+            elif name == "CBRT": v = np.cbrt(val[a])
+            elif name == "LOG2": v = np.log2(val[a])
+            elif name == "EXP2": v = np.exp2(val[a])
+            elif name == "FLOOR": v = np.floor(val[a])
+            elif name == "CEIL": v = np.ceil(val[a])
+            elif name == "ISNAN": v = np.isnan(val[a]).astype(np.float64)
+            elif name == "WHERE": v = np.where(val[a] != 0, val[b], val[c])
+            elif name == "INTERP": v = np.interp(val[b], tables[a][0], tables[a][1])
+            elif name == "ARCTAN2": v = np.arctan2(val[a], val[b])
+            elif name == "FMOD": v = np.fmod(val[a], val[b])
+            else: raise ValueError(name)
+            val[k] = v
+    return np.array(val[result], dtype=np.float64)
