@@ -1,0 +1,161 @@
+/* thermca_b200 — C ABI of the B200-native transient solve.
+ *
+ * Drop-in boundary for ONE path of steffenschroe/Thermca: the time integration inside
+ * thermca/solver.py (`transient_solution`, solver.py:61-345; only caller
+ * thermca/network.py:978-980).  The reference is pure Python and has no FFI of its own;
+ * these are the entry points a ctypes binding on the reference side loads (see
+ * INTEGRATION.md).  Every pointer marked `dev` is a DEVICE pointer owned by the caller
+ * (torch tensors on the Python side); the library owns only scratch it allocates
+ * itself.  All functions return 0 on success, <0 on error (`tc_last_error()`).
+ * No function falls back to the CPU.
+ */
+#ifndef THERMCA_B200_H
+#define THERMCA_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tc_solver* tc_handle;
+
+const char* tc_last_error(void);
+int tc_version(void);
+
+/* ---- network level (replaces Network._set_time_dependent_properties, network.py:747-868,
+ *      solve_stationary_nodes / cond_to_differential_equation_representation and the
+ *      network derivative, solver.py:30-58,208-255) ------------------------------------ */
+typedef struct {
+    const int32_t* iarena;      /* dev: all integer tables (index maps, programs, commands) */
+    double* darena;             /* dev: all fp64 tables and the mutable network state */
+    int32_t cmds_off;           /* iarena offset of the command stream (network.cuh) */
+    int32_t prog_dir_off;       /* iarena offset: 4 ints per link program */
+    int32_t tab_dir_off;        /* iarena offset: 2 ints per interpolation table */
+    int32_t N, u, nnz;          /* nodes, unknown nodes, nnz of run_cond */
+    int32_t o_T, o_heat, o_capy, o_vol, o_volcapy, o_condy, o_cond, o_clean, o_calc, o_inputs;
+    int32_t o_indptr, o_indices, o_diag;
+    /* surface-mean jobs (C_surf^T x, C_marg^T x, MOR C_surfs), solver.py:211-220 */
+    int32_t n_mean_jobs, n_mean_blocks;
+    const int32_t* job_of_block;    /* dev */
+    const int32_t* first_block;     /* dev */
+    const int32_t* nblk;            /* dev */
+    const int64_t* ent_start;       /* dev */
+    const int32_t* ent_idx;         /* dev: index into the stacked state */
+    const double* ent_w;            /* dev */
+} tc_net_desc;
+
+/* ---- full-order FE part (replaces FFEIO, thermca/fem/ffe_io.py:8-83 at run time) ------- */
+typedef struct {
+    int32_t n, nslices;
+    int64_t y_off;                  /* offset of the part in the stacked state */
+    const int64_t* slice_ptr;       /* dev: SELL-32 */
+    const int32_t* col;             /* dev */
+    double* val;                    /* dev: mutable (film coefficients live on the diagonal) */
+    const double* mass;             /* dev: M_diag = 1 / M_inv */
+    double* adiag;                  /* dev: dense copy of diag(A) */
+    /* surface loads  b = B[:, nz] flux[nz]  (solver.py:279-281) */
+    int32_t load_nrows;
+    const int32_t* load_row; const int32_t* load_start; const int32_t* load_surf; const double* load_bval;
+    /* films on the diagonal (ffe_io.py:76-82); fd_nrows == 0 when films are constant */
+    int32_t fd_nrows;
+    const int64_t* fd_pos; const int32_t* fd_row; const double* fd_abody;
+    const int32_t* fd_start; const int32_t* fd_film; const double* fd_adata;
+    int32_t films_doff;             /* darena offset of films[F] */
+    int32_t flux_doff;              /* darena offset of surf_flux[S] */
+} tc_ffe_desc;
+
+/* ---- LP part (replaces LPIO at run time, thermca/lpm/lp_io.py:8-80); operator and load
+ *      vector live inside the arenas because the network kernel updates them ------------- */
+typedef struct {
+    int32_t n, nslices;
+    int64_t y_off;
+    int32_t slice_ptr_ioff64;       /* iarena offset (in int32 words, 8-byte aligned) of int64 slice_ptr */
+    int32_t col_ioff;
+    int32_t val_doff;
+    int32_t b_doff;                 /* dense load vector M_inv*(Qs flux + L_film_margs T_link) */
+    int32_t mass_doff;
+} tc_lp_desc;
+
+/* ---- MOR part (replaces MORIO at run time, thermca/fem/mor_io.py:78-92) ------------------ */
+typedef struct {
+    int32_t S, r, F;
+    int64_t y_off;
+    const double* A_body;           /* dev: S*r*r */
+    const double* A_films;          /* dev: F*S*r*r */
+    const double* B_T;              /* dev: S*r */
+    int32_t films_doff, flux_doff;
+} tc_mor_desc;
+
+int tc_create(tc_handle* out, void* cuda_stream);
+int tc_destroy(tc_handle h);
+int tc_set_network(tc_handle h, const tc_net_desc* d);
+int tc_add_ffe_part(tc_handle h, const tc_ffe_desc* d);
+int tc_add_lp_part(tc_handle h, const tc_lp_desc* d);
+int tc_add_mor_part(tc_handle h, const tc_mor_desc* d);
+int tc_finalize(tc_handle h, int64_t n_state);
+
+/* Right-hand side f(t, y) = update_time_derivative (solver.py:193-302). Stateful like the
+ * reference: node temperatures, heat sources and conductances persist between calls. */
+int tc_rhs(tc_handle h, double t, const double* y_dev, double* ydot_dev);
+
+/* ---- explicit adaptive Runge-Kutta == scipy RK45 / RK23 as driven by simple_solve_ivp
+ *      (solver.py:348-390), step control kept on the device -------------------------------- */
+enum { TC_RK45 = 0, TC_RK23 = 1 };
+int tc_set_state(tc_handle h, const double* y_dev);
+int tc_get_state(tc_handle h, double* y_dev);
+/* history ring written on the device after accepted steps (store_results, solver.py:393-424):
+ * hist_io[capacity][n_state - u], hist_net[capacity][1 + 3N + 2 nnz] = time | T | capy | heat | cond | clean */
+int tc_set_history(tc_handle h, double* hist_io_dev, double* hist_net_dev, int32_t capacity, int32_t num_skip);
+int tc_rk_begin(tc_handle h, int32_t method, double t0, double t_end, double rtol, double atol,
+                double max_step, double first_step);
+/* Enqueue up to max_attempts step attempts (one CUDA graph replay each); stops early once the
+ * device reports done. info[8] (host): done, accepted, rejected, status, stored, nfev, t (bits lo/hi) */
+int tc_rk_advance(tc_handle h, int32_t max_attempts, int32_t poll_every);
+int tc_get_info(tc_handle h, int64_t* info8, double* t_now, double* h_next);
+int tc_reset_history(tc_handle h);
+
+/* ---- implicit steps: solve (M + c h K) per FE part with Jacobi-PCG (new numerical method;
+ *      the reference has no implicit scheme) ------------------------------ */
+enum { TC_PCG_COOP = 0, TC_PCG_MULTI = 1 };
+/* one fixed theta step of size h_step: (I + theta h A) d = h f(t + theta h, y); y += d */
+int tc_theta_steps(tc_handle h, int32_t nsteps, double theta, double h_step, double pcg_rtol,
+                   int32_t pcg_maxit, int32_t pcg_mode);
+/* adaptive linearly implicit 2-stage Rosenbrock (ROS2) with embedded first-order estimate */
+int tc_ros2_begin(tc_handle h, double t0, double t_end, double rtol, double atol, double max_step,
+                  double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode);
+int tc_ros2_advance(tc_handle h, int32_t max_attempts, int32_t poll_every);
+int tc_set_time(tc_handle h, double t);
+/* PCG statistics of the implicit path: total iterations, solves, last iteration count */
+int tc_pcg_stats(tc_handle h, int64_t* stats4);
+
+/* ---- stand-alone kernels (parity hooks and micro-benchmarks) ----------------------------- */
+/* y = -A x (mode 0), y = b - A x (mode 1), y = mass*(x + shift*A x) (mode 2) on a SELL-32 operator */
+int tc_sell_spmv(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, const int64_t* slice_ptr,
+                 const int32_t* col, const double* val, const double* x, double* y, const double* b,
+                 const double* mass, double shift, int32_t grid_blocks);
+/* Jacobi-PCG on (M + shift K): solves mass*(I + shift*A) x = mass*rhs; returns iterations in *iters (host) */
+int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, const int64_t* slice_ptr,
+                 const int32_t* col, const double* val, const double* mass, const double* adiag,
+                 const double* rhs, double* x, double shift, double rtol, int32_t maxit, int32_t* iters);
+
+/* ---- batched MOR ensemble (BASELINE config #3): B scenarios in lockstep, FP64 DMMA ------- */
+/* One classical RK4 step of size h for X[S][r][B] with per-scenario films film[F][B](t) =
+ * h0*(1 + 0.5 sin(2 pi t / tau)); operators shared by all scenarios. */
+int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32_t F, int32_t B,
+                       const double* A_body, const double* A_films, const double* B_T,
+                       const int32_t* film_surf, const double* film_h0, const double* film_tau,
+                       const double* t_link, const double* q_surf, double* X, double* work,
+                       double t0, double h, int32_t nsteps, int32_t use_dmma);
+int64_t tc_mor_batch_work_doubles(int32_t S, int32_t r, int32_t F, int32_t B);
+
+/* ---- device-side generator of the synthetic Kuhn cuboid operator (BASELINE configs #2/#5) */
+int tc_synth_cuboid_counts(int32_t nx, int32_t ny, int32_t nz, int64_t* n_rows, int64_t* n_slices,
+                           int64_t* sell_entries);
+int tc_synth_cuboid(void* cuda_stream, int32_t nx, int32_t ny, int32_t nz, double lx, double ly, double lz,
+                    double jitter, double condy, double vol_capy, int64_t row_begin, int64_t row_end,
+                    int64_t* slice_ptr, int32_t* col, double* val, double* mass, double* adiag,
+                    double* q_bottom, double* q_upper);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,173 @@
+"""Parity of the CUDA path against the oracle and the reference-generated golden vectors.
+Everything here goes through the C ABI (thermca_b200/_cabi.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN_MODELS
+
+pytestmark = pytest.mark.gpu
+DEVICE_MODELS = [m for m in GOLDEN_MODELS if m != "tdep_rod"]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _spmv(torch, lib, m, x, mode=0, b=None, mass=None, shift=0.0):
+    from thermca_b200 import _cabi
+    from thermca_b200.device import csr_to_sell
+    s = csr_to_sell(m.indptr, m.indices, m.data)
+    dev = torch.device("cuda")
+    t = {k: torch.from_numpy(np.ascontiguousarray(s[k])).to(dev) for k in ("slice_ptr", "col", "val")}
+    xd = torch.from_numpy(x).to(dev)
+    yd = torch.zeros(m.shape[0], dtype=torch.float64, device=dev)
+    bd = torch.from_numpy(b).to(dev) if b is not None else None
+    md = torch.from_numpy(mass).to(dev) if mass is not None else None
+    p = lambda a: C.c_void_p(a.data_ptr()) if a is not None else C.c_void_p(0)
+    _cabi.check(lib.tc_sell_spmv(C.c_void_p(torch.cuda.current_stream().cuda_stream), mode, m.shape[0],
+                                 s["nslices"], p(t["slice_ptr"]), p(t["col"]), p(t["val"]), p(xd), p(yd), p(bd),
+                                 p(md), float(shift), 0))
+    torch.cuda.synchronize()
+    return yd.cpu().numpy()
+
+
+def test_spmv_bit_exact_vs_scipy(torch_cuda, golden):
+    """Row sums in the reference's entry order, no FMA: identical bits to scipy csr_matvec."""
+    from thermca_b200 import _cabi
+    lib = _cabi.load_library()
+    rng = np.random.default_rng(0)
+    spec, _ = golden("plate_ffe")
+    ab = spec["ffe"][0]["A_body"]
+    mats = [sp.csr_matrix((spec["ffe"][0]["A_data"], ab["indices"], ab["indptr"]), shape=tuple(ab["shape"]))]
+    mats.append(sp.csr_matrix(sp.random(1000, 1000, density=0.02, random_state=1, format="csr")))
+    mats.append(sp.csr_matrix((5, 5)))                       # empty rows
+    ragged = sp.lil_matrix((97, 97))
+    for i in range(97):
+        ragged[i, rng.choice(97, size=1 + (i * 7) % 40, replace=False)] = rng.standard_normal(1 + (i * 7) % 40)
+    mats.append(sp.csr_matrix(ragged))
+    for m in mats:
+        x = rng.standard_normal(m.shape[1])
+        y = _spmv(torch_cuda, lib, m, x, mode=0)
+        assert np.array_equal(y, -(m @ x))
+        b = rng.standard_normal(m.shape[0])
+        y = _spmv(torch_cuda, lib, m, x, mode=1, b=b)
+        assert np.array_equal(y, b - m @ x)
+        mass = rng.uniform(1, 2, m.shape[0])
+        y = _spmv(torch_cuda, lib, m, x, mode=2, mass=mass, shift=0.37)
+        assert np.allclose(y, mass * (x + 0.37 * (m @ x)), rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", DEVICE_MODELS)
+def test_rhs_matches_reference_and_oracle(torch_cuda, golden, name):
+    """f(t, y) on the device == update_time_derivative of the reference (recorded) == oracle."""
+    from thermca_b200.device import DeviceSolver
+    from rhs_oracle import OracleRHS
+    spec, ex = golden(name)
+    dev = DeviceSolver(spec)
+    orc = OracleRHS(spec)
+    t0, y0 = float(ex["sim"]["t0"]), ex["y0"]
+    dev.rhs(t0, y0)
+    orc(t0, y0)
+    R = ex["rhs"]
+    for t, y, fref, href in zip(R["t"], R["y"], R["f"], R["heat"]):
+        f = dev.rhs(t, y)
+        fo = orc(t, y)
+        scale = np.max(np.abs(fref)) + 1e-300
+        assert np.max(np.abs(f - fref)) <= 1e-12 * scale, name
+        assert np.max(np.abs(f - fo)) <= 1e-12 * scale, name
+        st = dev.network_state()
+        assert np.allclose(st["heat_src"], href, rtol=1e-12, atol=1e-12)
+        assert np.allclose(st["T"], orc.net_temp, rtol=1e-12, atol=1e-12)
+        assert np.allclose(st["cond"], orc.cond_data, rtol=1e-9, atol=1e-4)
+    dev.close()
+
+
+@pytest.mark.parametrize("name", DEVICE_MODELS)
+def test_adaptive_rk_matches_reference(torch_cuda, golden, name):
+    """Same accepted-step sequence and temperatures as Network.sim of the reference
+    (1e-9 relative; the step controller runs on the device)."""
+    from thermca_b200.device import DeviceSolver
+    spec, ex = golden(name)
+    sim, ref = ex["sim"], ex["result"]
+    dev = DeviceSolver(spec)
+    out = dev.run_rk(float(sim["t0"]), float(sim["t1"]), float(sim["rel_tol"]), float(sim["abs_tol"]),
+                     str(sim["method"]))
+    dev.close()
+    assert len(out["times"]) == len(ref["times"]), (len(out["times"]), len(ref["times"]))
+    assert np.allclose(out["times"], ref["times"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(out["net_temps"], ref["net_temps"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(out["net_capys"], ref["net_capys"], rtol=1e-9, atol=0, equal_nan=True)
+    if ref["io_temps"].size:
+        assert np.allclose(out["io_temps"][ref["io_snap_idx"]], ref["io_temps"], rtol=1e-9, atol=1e-9)
+    assert out["nfev"] == int(ref["nfev"]) + 1
+
+
+def test_rk_result_skipping_and_zero_span(torch_cuda, golden):
+    from thermca_b200.device import DeviceSolver
+    from rhs_oracle import integrate
+    spec, ex = golden("coffeecup")
+    dev = DeviceSolver(spec)
+    out = dev.run_rk(0.0, 300.0, 1e-5, 1e-6, "RK45", num_skip=3)
+    ref = integrate(spec, [0.0, 300.0], 1e-5, 1e-6, "RK45", num_skip=3)
+    assert np.allclose(out["times"], ref["times"], rtol=1e-9)
+    assert np.allclose(out["net_temps"], ref["net_temps"], rtol=1e-9)
+    dev.close()
+    dev = DeviceSolver(spec)
+    out = dev.run_rk(5.0, 5.0)                 # t1 <= t0: only the initial state (network.py:972-976)
+    assert len(out["times"]) == 1 and out["times"][0] == 5.0
+    dev.close()
+
+
+def _theta_reference(spec, nsteps, h, theta):
+    """CPU restatement of the theta step with a sparse direct solver (oracle side)."""
+    from rhs_oracle import OracleRHS
+    from thermca_b200.lowering import initial_state
+    import scipy.sparse.linalg as spla
+    rhs = OracleRHS(spec)
+    y = initial_state(spec)
+    t = 0.0
+    p = spec["ffe"][0]
+    n = int(p["dof"])
+    for _ in range(nsteps):
+        f = rhs(t + theta * h, y)
+        A = rhs.ffe[0]["A"]
+        z = spla.spsolve((sp.identity(n, format="csc") + theta * h * A.tocsc()), f)
+        y = y + h * z
+        t += h
+    return y
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_theta_pcg_fixed_step(torch_cuda, golden, mode):
+    """Fixed-step theta scheme with Jacobi-PCG == CPU restatement with a direct solver (1e-9)."""
+    from thermca_b200.device import DeviceSolver
+    spec, _ = golden("kuhn_cuboid")
+    dev = DeviceSolver(spec)
+    dev.theta_steps(5, 2.0, theta=0.5, t0=0.0, pcg_rtol=1e-13, pcg_maxit=500, pcg_mode=mode)
+    y = dev.get_state()
+    st = dev.pcg_stats()
+    dev.close()
+    yref = _theta_reference(spec, 5, 2.0, 0.5)
+    assert st["solves"] == 5 and 0 < st["iterations"] < 5 * 500
+    assert np.max(np.abs(y - yref) / np.abs(yref)) < 1e-9
+
+
+def test_ros2_adaptive_matches_rk45(torch_cuda, golden):
+    """Adaptive implicit path agrees with the reference's RK45 trajectory within rtol."""
+    from thermca_b200.device import DeviceSolver
+    spec, ex = golden("plate_ffe")
+    ref = ex["result"]
+    dev = DeviceSolver(spec)
+    out = dev.run_ros2(0.0, float(ex["sim"]["t1"]), rtol=1e-4, atol=1e-6, pcg_rtol=1e-10)
+    dev.close()
+    assert out["times"][-1] == float(ex["sim"]["t1"])
+    Tref, T = ref["net_temps"][-1], out["net_temps"][-1]
+    assert np.allclose(T, Tref, rtol=1e-3, atol=1e-3)
+    io_ref = ref["io_temps"][-1]
+    assert np.allclose(out["io_temps"][-1], io_ref, rtol=1e-3, atol=1e-3)

@@ -1,0 +1,109 @@
+"""Host-side logic: index maps, tracer, SELL layout, spec IO, C ABI exports (no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN_MODELS, ROOT
+from thermca_b200 import _cabi
+from thermca_b200.device import csr_to_sell, csr_diag_positions
+from thermca_b200.lowering import csr_data_idxs, csr_sub_matrix_idxs
+from thermca_b200.spec import save_spec, load_spec
+from thermca_b200.trace import trace, TableRegistry, run_program, UntraceableError
+
+
+@pytest.mark.parametrize("name", GOLDEN_MODELS)
+def test_index_maps_bit_exact(golden, name):
+    """diag / sub-matrix back-maps equal the reference's own (thermca/solver.py:116-122)."""
+    spec, ex = golden(name)
+    for key in ("diag_didx", "uu_didx", "uk_didx"):
+        assert np.array_equal(np.asarray(spec[key], dtype=np.int64), np.asarray(ex["ref_maps"][key], dtype=np.int64))
+
+
+def test_csr_data_idxs_first_match_and_error():
+    m = sp.csr_matrix(np.array([[1.0, 0, 2], [0, 3, 0], [4, 0, 5]]))
+    assert list(csr_data_idxs(m.indptr, m.indices, [0, 2, 1], [2, 0, 1])) == [1, 3, 2]
+    with pytest.raises(IndexError):
+        csr_data_idxs(m.indptr, m.indices, [1], [0])
+    ip, ix, orig = csr_sub_matrix_idxs(m.indptr, m.indices, 0, 2, 1, 3)
+    assert list(ip) == [0, 1, 2] and list(ix) == [1, 0] and list(orig) == [1, 2]
+
+
+def test_sell_layout_roundtrip():
+    rng = np.random.default_rng(1)
+    m = sp.random(70, 70, density=0.1, random_state=3, format="csr") + sp.eye(70, format="csr")
+    m = sp.csr_matrix(m)
+    s = csr_to_sell(m.indptr, m.indices, m.data)
+    assert s["nslices"] == 3 and s["slice_ptr"][-1] == len(s["val"])
+    x = rng.standard_normal(70)
+    y = np.zeros(70)
+    for sl in range(s["nslices"]):
+        base, w = s["slice_ptr"][sl], (s["slice_ptr"][sl + 1] - s["slice_ptr"][sl]) // 32
+        for lane in range(32):
+            r = sl * 32 + lane
+            if r < 70:
+                for k in range(w):
+                    y[r] += s["val"][base + 32 * k + lane] * x[s["col"][base + 32 * k + lane]]
+    assert np.allclose(y, m @ x, rtol=1e-14)
+    assert np.array_equal(s["val"][s["pos"]], m.data)
+    d = csr_diag_positions(m.indptr, m.indices)
+    assert np.allclose(m.data[d], m.diagonal())
+
+
+def test_tracer_where_interp_and_inputs():
+    tabs = TableRegistry()
+    inp = np.array(2.5)
+    xp, fp = np.array([0.0, 10.0, 20.0]), np.array([1.0, 3.0, 2.0])
+
+    def f(a, b, scale=inp):
+        k = np.interp((a + b) / 2.0, xp, fp)
+        return np.where(a > b, k * abs(a - b) ** 0.25, 0.5 * k) * scale
+    p = trace(f, 2, [inp], tabs)
+    code, consts, res = p.arrays()
+    a, b = np.array([5.0, 25.0, -3.0]), np.array([7.0, 1.0, -3.0])
+    got = run_program(code, consts, res, [a, b], [4.0], tabs.tables)
+    inp[...] = 4.0
+    assert np.array_equal(got, f(a, b))
+
+
+def test_tracer_rejects_python_branching():
+    def f(a, b):
+        return a if a > b else b
+    with pytest.raises(UntraceableError):
+        trace(f, 2, [], TableRegistry())
+
+
+def test_spec_roundtrip(tmp_path, golden):
+    spec, ex = golden("plate_mor_var")
+    path = tmp_path / "s.npz"
+    save_spec(path, spec, extra={"a": np.arange(3)})
+    spec2, ex2 = load_spec(path)
+    assert np.array_equal(spec2["rc_indices"], spec["rc_indices"])
+    assert np.array_equal(spec2["mor"][0]["A_films"], spec["mor"][0]["A_films"])
+    assert spec2["ffe"] == [] and spec2["mor"][0]["var_film_rc_idx"] is not None
+    assert np.array_equal(ex2["extra"]["a"], np.arange(3))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """The .so loads and exports every function include/thermca_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "thermca_b200.h")).read()
+    declared = set(re.findall(r"\b(tc_[a-z0-9_]+)\s*\(", header)) - {"tc_solver"}
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    if not os.path.exists(_cabi.LIB_PATH):
+        from thermca_b200.build import build
+        build()
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _cabi.load_library().tc_version() == 100
+
+
+def test_product_path_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "thermca_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "rhs_oracle" not in src and "import oracle" not in src and "from oracle" not in src, fn

@@ -1,0 +1,89 @@
+// Shared device helpers for the thermca_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define TC_WARP 32
+#define TC_SLICE 32          // SELL-C slice height = one warp
+#define TC_MAX_PARTIALS 2048 // upper bound of blocks that publish reduction partials
+
+// ---- error plumbing (host) ---------------------------------------------------------
+extern "C" void tc_set_error(const char* file, int line, const char* msg);
+#define TC_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) {                                             \
+            tc_set_error(__FILE__, __LINE__, cudaGetErrorString(e_));        \
+            return -1;                                                       \
+        }                                                                    \
+    } while (0)
+#define TC_CHECK(cond, msg)                                                  \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            tc_set_error(__FILE__, __LINE__, msg);                           \
+            return -2;                                                       \
+        }                                                                    \
+    } while (0)
+
+// ---- streaming loads that do not allocate in L1 (matrix values / column indices) ----
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// ---- deterministic block reduction (fixed shuffle tree, fixed warp order) -----------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// Sum over the block; result valid in thread 0. `sh` needs >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        r = lane < nw ? sh[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// "Last block done" finaliser: every block stores its partial(s); the block that
+// arrives last sums them in block-index order (deterministic) and calls `fin`.
+// Returns true in ALL threads of the last block.
+__device__ __forceinline__ bool last_block_arrives(unsigned int* counter) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *counter = 0u;   // re-arm for the next launch
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+// Ordered sum of n partials by one block; result valid in thread 0.
+__device__ __forceinline__ double ordered_partial_sum(const volatile double* part, int n, double* sh) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+    return block_sum(v, sh);
+}

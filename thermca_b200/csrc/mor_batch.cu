@@ -1,0 +1,197 @@
+// Batched MOR ensemble step (BASELINE config #3): B load cases of one MOR-reduced FE body
+// advanced in lockstep.  The reference evaluates one scenario at a time in Python
+// (thermca/solver.py:282-299, thermca/fem/mor_io.py:90-92):
+//     A_s = A_body_s + sum_f film_f A_film_{f,s};   xdot_s = -A_s x_s + B_T[s] * flux_s
+// Here the scenario axis is the GEMM N dimension: for every surface s
+//     Z_o (r x B) = W_{o,s} (r x r) . X_s (r x B),  o = 0 (body), 1..F (films)
+// is a true dense contraction done with FP64 tensor-core DMMA (mma.sync m8n8k4 f64;
+// tcgen05 has no f64 kind), and the per-scenario film weighting, the input term and the
+// Runge-Kutta stage update are fused into the epilogue, so A_s is never materialised per
+// scenario (that would be S*r^2*8 B = ~1 MB per scenario and HBM-bound).
+// Layout: X[s][i][b], scenario index fastest.  Classical RK4, fixed step, four launches
+// per step.
+#include "common.cuh"
+#include "../../include/thermca_b200.h"
+
+#define MB_TM 64      // rows per CTA tile
+#define MB_TN 64      // scenarios per CTA tile
+#define MB_TK 16      // k chunk
+#define MB_THREADS 256
+
+struct MorBatch {
+    int S, r, F, B;
+    const double* A_body;   // [S][r][r]
+    const double* A_films;  // [F][S][r][r]
+    const double* B_T;      // [S][r]
+    const int* film_surf;   // [F]
+    const double* film_h0;  // [F][B]
+    const double* film_tau; // [F][B]
+    const double* t_link;   // [F]   link temperature minus reference temperature
+    const double* q_surf;   // [S]   constant flux density per surface
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double film_at(const MorBatch& M, int f, int b, double t) {
+    const double TWO_PI = 6.283185307179586476925;
+    return M.film_h0[(size_t)f * M.B + b] * (1.0 + 0.5 * sin(TWO_PI * t / M.film_tau[(size_t)f * M.B + b]));
+}
+
+// One RK stage:  k = f(t, Xin);  Xout = Xbase + c_out*h*k (if Xout);  Xacc = (first ? Xbase : Xacc) + c_acc*h*k
+template <int NOPS, bool DMMA>
+__global__ void __launch_bounds__(MB_THREADS)
+tc_mor_stage_kernel(MorBatch M, const double* __restrict__ Xin, const double* __restrict__ Xbase,
+                    double* __restrict__ Xout, double* __restrict__ Xacc, double t, double h,
+                    double c_out, double c_acc, int first) {
+    __shared__ double sA[NOPS][MB_TM][MB_TK + 1];
+    __shared__ double sX[MB_TK][MB_TN + 8];
+    const int s = blockIdx.z;
+    const int i0 = blockIdx.y * MB_TM;
+    const int b0 = blockIdx.x * MB_TN;
+    const int r = M.r, B = M.B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 3) * 16;     // warp tile origin (rows)   : 4 x 16
+    const int wn = (warp >> 2) * 32;    // warp tile origin (cols)   : 2 x 32
+    const double* Xs = Xin + (size_t)s * r * B;
+    double acc[NOPS][2][4][2];
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[o][a][c][0] = acc[o][a][c][1] = 0.0;
+
+    for (int k0 = 0; k0 < r; k0 += MB_TK) {
+        // operator chunks: NOPS x (64 x 16), row-major in global (k contiguous)
+        for (int e = tid; e < NOPS * MB_TM * MB_TK; e += MB_THREADS) {
+            const int o = e / (MB_TM * MB_TK);
+            const int rem = e - o * (MB_TM * MB_TK);
+            const int ri = rem / MB_TK, kk = rem - ri * MB_TK;
+            const int gi = i0 + ri, gk = k0 + kk;
+            double v = 0.0;
+            if (gi < r && gk < r) {
+                const double* W = (o == 0) ? M.A_body + (size_t)s * r * r
+                                           : M.A_films + ((size_t)(o - 1) * M.S + s) * r * r;
+                v = W[(size_t)gi * r + gk];
+            }
+            sA[o][ri][kk] = v;
+        }
+        // state chunk: 16 x 64 (scenario contiguous)
+        for (int e = tid; e < MB_TK * MB_TN; e += MB_THREADS) {
+            const int kk = e / MB_TN, bb = e - kk * MB_TN;
+            const int gk = k0 + kk, gb = b0 + bb;
+            sX[kk][bb] = (gk < r && gb < B) ? Xs[(size_t)gk * B + gb] : 0.0;
+        }
+        __syncthreads();
+        if (DMMA) {
+#pragma unroll
+            for (int k4 = 0; k4 < MB_TK; k4 += 4) {
+                double bf[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) bf[c] = sX[k4 + (lane & 3)][wn + 8 * c + (lane >> 2)];
+#pragma unroll
+                for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const double af = sA[o][wm + 8 * a + (lane >> 2)][k4 + (lane & 3)];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) dmma884(acc[o][a][c][0], acc[o][a][c][1], af, bf[c]);
+                    }
+            }
+        } else {
+            // same thread->element ownership as the DMMA C fragment, plain FMA
+#pragma unroll 4
+            for (int kk = 0; kk < MB_TK; ++kk)
+#pragma unroll
+                for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const double af = sA[o][wm + 8 * a + (lane >> 2)][kk];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            acc[o][a][c][0] += af * sX[kk][wn + 8 * c + 2 * (lane & 3)];
+                            acc[o][a][c][1] += af * sX[kk][wn + 8 * c + 2 * (lane & 3) + 1];
+                        }
+                    }
+        }
+        __syncthreads();
+    }
+    // fused epilogue: film weighting, input term, RK stage update
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gi = i0 + wm + 8 * a + (lane >> 2);
+                const int gb = b0 + wn + 8 * c + 2 * (lane & 3) + e;
+                if (gi >= r || gb >= B) continue;
+                double z = acc[0][a][c][e];
+                double flux = M.q_surf[s];
+#pragma unroll
+                for (int f = 0; f < NOPS - 1; ++f) {      // NOPS == F + 1
+                    const double fv = film_at(M, f, gb, t);
+                    z += fv * acc[f + 1][a][c][e];
+                    if (M.film_surf[f] == s) flux += fv * M.t_link[f];
+                }
+                const double kval = -z + M.B_T[(size_t)s * r + gi] * flux;
+                const size_t idx = ((size_t)s * r + gi) * B + gb;
+                const double xb = Xbase[idx];
+                if (Xout) Xout[idx] = xb + c_out * h * kval;
+                Xacc[idx] = (first ? xb : Xacc[idx]) + c_acc * h * kval;
+            }
+}
+
+extern "C" int64_t tc_mor_batch_work_doubles(int32_t S, int32_t r, int32_t F, int32_t B) {
+    (void)F;
+    return 3LL * S * r * B;
+}
+
+template <int NOPS>
+static void launch_stage(bool dmma, dim3 grid, cudaStream_t st, const MorBatch& M, const double* Xin,
+                         const double* Xbase, double* Xout, double* Xacc, double t, double h, double c_out,
+                         double c_acc, int first) {
+    if (dmma)
+        tc_mor_stage_kernel<NOPS, true><<<grid, MB_THREADS, 0, st>>>(M, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
+    else
+        tc_mor_stage_kernel<NOPS, false><<<grid, MB_THREADS, 0, st>>>(M, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
+}
+
+extern "C" int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32_t F, int32_t B,
+                                  const double* A_body, const double* A_films, const double* B_T,
+                                  const int32_t* film_surf, const double* film_h0, const double* film_tau,
+                                  const double* t_link, const double* q_surf, double* X, double* work,
+                                  double t0, double h, int32_t nsteps, int32_t use_dmma) {
+    TC_CHECK(F >= 0 && F <= 3, "batched MOR supports up to 3 film links per body");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    MorBatch M{S, r, F, B, A_body, A_films, B_T, film_surf, film_h0, film_tau, t_link, q_surf};
+    const size_t n = (size_t)S * r * B;
+    double* o1 = work; double* o2 = work + n; double* acc = work + 2 * n;
+    dim3 grid((B + MB_TN - 1) / MB_TN, (r + MB_TM - 1) / MB_TM, S);
+    const bool dm = use_dmma != 0;
+    auto stage = [&](const double* Xin, const double* Xb, double* Xout, double* Xacc, double t, double c_out,
+                     double c_acc, int first) {
+        switch (F) {
+            case 0: launch_stage<1>(dm, grid, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            case 1: launch_stage<2>(dm, grid, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            case 2: launch_stage<3>(dm, grid, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            default: launch_stage<4>(dm, grid, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+        }
+    };
+    double* cur = X;
+    double* nxt = acc;
+    for (int k = 0; k < nsteps; ++k) {
+        const double t = t0 + k * h;
+        stage(cur, cur, o1, nxt, t, 0.5, 1.0 / 6.0, 1);
+        stage(o1, cur, o2, nxt, t + 0.5 * h, 0.5, 1.0 / 3.0, 0);
+        stage(o2, cur, o1, nxt, t + 0.5 * h, 1.0, 1.0 / 3.0, 0);
+        stage(o1, cur, nullptr, nxt, t + h, 0.0, 1.0 / 6.0, 0);
+        double* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (cur != X) TC_CUDA(cudaMemcpyAsync(X, cur, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}

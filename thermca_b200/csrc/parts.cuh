@@ -1,0 +1,218 @@
+// Part-level kernels: the FE / LP state-space operators and their surface coupling.
+//
+// Operator layout in HBM: SELL-32 ("sliced ELLPACK", slice height = one warp).  Slice s
+// holds rows 32s..32s+31 column-major: entry k of local row l sits at
+// slice_ptr[s] + 32*k + l, so a warp reads 256 B of values and 128 B of column
+// indices per k, fully coalesced, and every thread owns one row: the row sum is a
+// sequential, un-fused multiply-add chain in the stored entry order — the same order
+// scipy's csr_matvec uses on the reference's CSR (thermca/solver.py:264,281 via
+// thermca/_utils/sparse.py:10), which makes the product bit-identical to the CPU path.
+// Short rows are padded with (value 0, column = own row).
+#pragma once
+#include "common.cuh"
+
+struct TcSell {
+    int n;                        // rows
+    int nslices;
+    const long long* slice_ptr;   // nslices + 1
+    const int* col;
+    const double* val;
+};
+
+#define TC_SPMV_THREADS 256
+
+enum { SPMV_NEG = 0, SPMV_B = 1, SPMV_SHIFT = 2 };
+
+// MODE SPMV_NEG  : y = -A x                                  (FFE right-hand side, b added on surface rows after)
+// MODE SPMV_B    : y = b - A x                               (LP right-hand side)
+// MODE SPMV_SHIFT: y = mass * (x + shift * A x), partial[blockIdx] = sum x_i y_i
+//                  shift = coef * ctrl[1] (= gamma * h, read on the device)
+// Per-thread body (grid-stride over slices); returns this thread's share of sum x_i y_i.
+// NC_X: gather x through the read-only (non-coherent) path.  Must be false when x is written
+// by other blocks of the SAME launch (persistent PCG kernel): then x is read with ld.global.ca,
+// which the gpu-scope fence of grid.sync() keeps coherent.
+template <bool NC_X>
+__device__ __forceinline__ double tc_ld_x(const double* p) {
+    if (NC_X) return __ldg(p);
+    double v;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int MODE, bool NC_X = true>
+__device__ __forceinline__ double tc_sell_spmv_body(const TcSell& A, const double* x,
+                                                    double* y, const double* __restrict__ b,
+                                                    const double* __restrict__ mass, double shift) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * warps_per_block;
+    double dot = 0.0;
+    for (int s = warp; s < A.nslices; s += nwarps) {
+        const long long base = A.slice_ptr[s];
+        const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+        const double* v = A.val + base + lane;
+        const int* c = A.col + base + lane;
+        double sum = 0.0;
+        int k = 0;
+        for (; k + 4 <= width; k += 4) {
+            const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
+            const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
+            const int c0 = ld_stream_s32(c + 32 * (k + 0)), c1 = ld_stream_s32(c + 32 * (k + 1));
+            const int c2 = ld_stream_s32(c + 32 * (k + 2)), c3 = ld_stream_s32(c + 32 * (k + 3));
+            const double x0 = tc_ld_x<NC_X>(x + c0), x1 = tc_ld_x<NC_X>(x + c1), x2 = tc_ld_x<NC_X>(x + c2), x3 = tc_ld_x<NC_X>(x + c3);
+            sum = __dadd_rn(sum, __dmul_rn(v0, x0));
+            sum = __dadd_rn(sum, __dmul_rn(v1, x1));
+            sum = __dadd_rn(sum, __dmul_rn(v2, x2));
+            sum = __dadd_rn(sum, __dmul_rn(v3, x3));
+        }
+        for (; k < width; ++k) {
+            const double v0 = ld_stream_f64(v + 32 * k);
+            const int c0 = ld_stream_s32(c + 32 * k);
+            sum = __dadd_rn(sum, __dmul_rn(v0, tc_ld_x<NC_X>(x + c0)));
+        }
+        const int row = s * 32 + lane;
+        if (row < A.n) {
+            if (MODE == SPMV_NEG) {
+                y[row] = -sum;
+            } else if (MODE == SPMV_B) {
+                y[row] = __dsub_rn(b[row], sum);
+            } else {
+                const double xr = tc_ld_x<NC_X>(x + row);
+                const double q = mass[row] * (xr + shift * sum);
+                y[row] = q;
+                dot += xr * q;
+            }
+        }
+    }
+    return dot;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_SPMV_THREADS)
+tc_sell_spmv_kernel(TcSell A, const double* __restrict__ x, double* __restrict__ y,
+                    const double* __restrict__ b, const double* __restrict__ mass,
+                    const double* __restrict__ ctrl, double coef, double* __restrict__ partial,
+                    const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    __shared__ double sh[32];
+    double shift = 0.0;
+    if (MODE == SPMV_SHIFT) shift = coef * ctrl[1];
+    const double dot = tc_sell_spmv_body<MODE>(A, x, y, b, mass, shift);
+    if (MODE == SPMV_SHIFT) {
+        const double bs = block_sum(dot, sh);
+        if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+    }
+}
+
+// ---- surface coupling of a full-order FE part ----------------------------------------
+// Unique surface rows with their (surface, B value) lists: row r gets
+//   ydot[r] += sum_{s in list, flux_s != 0} B[r,s] * flux_s        thermca/solver.py:279-281
+struct TcSurfLoad {
+    int nrows;
+    const int* row;        // unique dof index
+    const int* start;      // nrows + 1, into (surf, bval)
+    const int* surf;
+    const double* bval;
+};
+__global__ void tc_ffe_surf_load_kernel(TcSurfLoad L, const double* __restrict__ flux,
+                                        double* __restrict__ ydot, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nrows; i += gridDim.x * blockDim.x) {
+        double bsum = 0.0;
+        for (int k = L.start[i]; k < L.start[i + 1]; ++k) {
+            const double f = flux[L.surf[k]];
+            if (f != 0.0) bsum = __dadd_rn(bsum, __dmul_rn(L.bval[k], f));
+        }
+        const int r = L.row[i];
+        ydot[r] = __dadd_rn(bsum, ydot[r]);
+    }
+}
+
+// Film coefficients folded into the operator diagonal (thermca/fem/ffe_io.py:76-82):
+//   A_ii = A_body_ii + sum_f film_f * a_f,i   in film order, written at the SELL position.
+struct TcFilmDiag {
+    int nrows;
+    const long long* pos;  // position of A_ii in the SELL value array
+    const int* row;        // dof index (for the dense diagonal copy)
+    const double* abody;   // A_body_ii
+    const int* start;      // nrows + 1
+    const int* film;       // film index
+    const double* adata;   // a_f,i
+};
+__global__ void tc_ffe_film_diag_kernel(TcFilmDiag F, const double* __restrict__ films,
+                                        double* __restrict__ val, double* __restrict__ adiag,
+                                        const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F.nrows; i += gridDim.x * blockDim.x) {
+        double v = F.abody[i];
+        for (int k = F.start[i]; k < F.start[i + 1]; ++k)
+            v = __dadd_rn(v, __dmul_rn(films[F.film[k]], F.adata[k]));
+        val[F.pos[i]] = v;
+        if (adiag) adiag[F.row[i]] = v;
+    }
+}
+
+// ---- weighted gathers: surface mean temperatures -------------------------------------
+// Job j = sum_k w[k] * y[idx[k]] over its entry range; split over nblk[j] blocks whose
+// partial sums are combined in block order by the network kernel (C_SURF_MEAN).
+struct TcMeanJobs {
+    int njobs;
+    const int* job_of_block;     // grid size
+    const int* first_block;      // njobs
+    const int* nblk;             // njobs
+    const long long* ent_start;  // njobs + 1
+    const int* idx;              // index into y (absolute, state offset included)
+    const double* w;
+};
+#define TC_MEAN_THREADS 256
+__global__ void __launch_bounds__(TC_MEAN_THREADS)
+tc_surf_mean_kernel(TcMeanJobs J, const double* __restrict__ y, double* __restrict__ partials,
+                    const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    __shared__ double sh[32];
+    const int j = J.job_of_block[blockIdx.x];
+    const int bj = blockIdx.x - J.first_block[j];
+    const long long lo = J.ent_start[j], hi = J.ent_start[j + 1];
+    const long long per = (hi - lo + J.nblk[j] - 1) / J.nblk[j];
+    const long long b0 = lo + per * bj;
+    const long long b1 = b0 + per < hi ? b0 + per : hi;
+    double s = 0.0;
+    for (long long k = b0 + threadIdx.x; k < b1; k += blockDim.x) s += J.w[k] * y[J.idx[k]];
+    const double bs = block_sum(s, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+}
+
+// ---- MOR parts: S independent dense r x r blocks ------------------------------------------
+//   xdot_s = -(A_body_s + sum_f film_f A_film_{f,s}) x_s + B_T[s] * flux_s   thermca/solver.py:282-299
+struct TcMor {
+    int S, r, F;
+    const double* A_body;   // S*r*r
+    const double* A_films;  // F*S*r*r
+    const double* B_T;      // S*r
+};
+__global__ void tc_mor_rhs_kernel(TcMor M, const double* __restrict__ films,
+                                  const double* __restrict__ flux, const double* __restrict__ x,
+                                  double* __restrict__ xdot, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    const int rows = M.S * M.r;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const size_t blk = (size_t)M.S * M.r * M.r;
+    for (int row = warp; row < rows; row += nwarps) {
+        const int s = row / M.r, i = row - s * M.r;
+        const double* ab = M.A_body + ((size_t)s * M.r + i) * M.r;
+        const double* xs = x + (size_t)s * M.r;
+        double acc = 0.0;
+        for (int j = lane; j < M.r; j += 32) {
+            double fsum = 0.0;       // sum(f * A_film) starts from 0 like Python's sum()
+            for (int f = 0; f < M.F; ++f)
+                fsum = __dadd_rn(fsum, __dmul_rn(films[f], M.A_films[f * blk + ((size_t)s * M.r + i) * M.r + j]));
+            const double aij = M.F > 0 ? __dadd_rn(ab[j], fsum) : ab[j];
+            acc += aij * xs[j];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) xdot[row] = __dadd_rn(-acc, __dmul_rn(M.B_T[row], flux[s]));
+    }
+}

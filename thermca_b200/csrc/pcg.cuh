@@ -1,0 +1,186 @@
+// Jacobi-preconditioned conjugate gradients for the implicit step of one FE part.
+//
+// System: mass * (I + shift * A) x = mass * rhs, i.e. (M + shift*K) x = M rhs with
+// A = M^-1 K as the reference stores it (thermca/fem/ffe_io.py:85-117); M + shift*K is
+// symmetric positive definite, diag = mass_i * (1 + shift * A_ii).
+// The reference has no implicit scheme: this is a new method on the
+// reference's operators; its CPU restatement is oracle/theta_oracle.py.
+//
+// Two drivers over the same phases:
+//   * tc_pcg_coop_kernel  - ONE cooperative persistent launch per solve, grid.sync()
+//     between phases, convergence loop on the device (no host round trip);
+//   * tc_pcg_k1/k2/k3     - one launch per phase, used when cooperative launch is not
+//     available and for cross-checking.
+// Dot products: per-block partial (fixed shuffle tree) -> every block sums the G partials
+// in index order, so all blocks see the same scalar and results are run-to-run identical.
+#pragma once
+#include <cooperative_groups.h>
+#include "parts.cuh"
+namespace cg = cooperative_groups;
+
+struct TcPcg {
+    TcSell A;
+    const double* mass;
+    const double* adiag;
+    const double* rhs;      // unscaled right-hand side
+    double* x;              // solution
+    double *r, *p, *q, *dinv;
+    double* partial;        // 4 banks of TC_MAX_PARTIALS
+    double* sc;             // [0],[1] rho (parity), [2] tol2, [3] bnorm2, [4] rr
+    int* isc;               // [0] pcg_done, [1] iterations of this solve, [2] total iterations, [3] solves
+    double rtol;
+    int maxit;
+    const double* ctrl;     // shift = coef * ctrl[1]
+    double coef;
+};
+
+#define TC_PCG_THREADS 256
+
+__device__ __forceinline__ double tc_bank_sum(const double* bank, int G, double* sh) {
+    __shared__ double bcast;
+    const double s = ordered_partial_sum(bank, G, sh);
+    __syncthreads();
+    if (threadIdx.x == 0) bcast = s;
+    __syncthreads();
+    return bcast;
+}
+
+__device__ __forceinline__ void tc_pcg_init_phase(const TcPcg& S, double shift, double* sh) {
+    const int n = S.A.n;
+    double rho = 0.0, bb = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double m = S.mass[i];
+        const double b = m * S.rhs[i];
+        const double d = 1.0 / (m * (1.0 + shift * S.adiag[i]));
+        const double z = d * b;
+        S.r[i] = b; S.x[i] = 0.0; S.dinv[i] = d; S.p[i] = z;
+        rho += b * z; bb += b * b;
+    }
+    const double r0 = block_sum(rho, sh);
+    const double r1 = block_sum(bb, sh);
+    if (threadIdx.x == 0) { S.partial[blockIdx.x] = r0; S.partial[TC_MAX_PARTIALS + blockIdx.x] = r1; }
+}
+
+// x += alpha p ; r -= alpha q ; partial sums of r.(dinv r) and r.r
+__device__ __forceinline__ void tc_pcg_update_phase(const TcPcg& S, double alpha, double* sh) {
+    const int n = S.A.n;
+    double rho = 0.0, rr = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double pi = S.p[i];
+        S.x[i] += alpha * pi;
+        const double ri = S.r[i] - alpha * S.q[i];
+        S.r[i] = ri;
+        rho += ri * (S.dinv[i] * ri);
+        rr += ri * ri;
+    }
+    const double r0 = block_sum(rho, sh);
+    const double r1 = block_sum(rr, sh);
+    if (threadIdx.x == 0) {
+        S.partial[2 * TC_MAX_PARTIALS + blockIdx.x] = r0;
+        S.partial[3 * TC_MAX_PARTIALS + blockIdx.x] = r1;
+    }
+}
+
+__device__ __forceinline__ void tc_pcg_dir_phase(const TcPcg& S, double beta) {
+    const int n = S.A.n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        S.p[i] = S.dinv[i] * S.r[i] + beta * S.p[i];
+}
+
+__global__ void __launch_bounds__(TC_PCG_THREADS)
+tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;       // uniform over the grid
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    const int G = gridDim.x;
+    const double shift = S.coef * S.ctrl[1];
+    tc_pcg_init_phase(S, shift, sh);
+    grid.sync();
+    double rho = tc_bank_sum(S.partial, G, sh);
+    const double bb = tc_bank_sum(S.partial + TC_MAX_PARTIALS, G, sh);
+    const double tol2 = S.rtol * S.rtol * bb;
+    int it = 0;
+    if (bb > 0.0) {
+        for (; it < S.maxit;) {
+            const double dot = tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, S.p, S.q, nullptr, S.mass, shift);
+            const double bs = block_sum(dot, sh);
+            if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
+            grid.sync();
+            const double pq = tc_bank_sum(S.partial, G, sh);
+            const double alpha = rho / pq;
+            tc_pcg_update_phase(S, alpha, sh);
+            grid.sync();
+            const double rho_new = tc_bank_sum(S.partial + 2 * TC_MAX_PARTIALS, G, sh);
+            const double rr = tc_bank_sum(S.partial + 3 * TC_MAX_PARTIALS, G, sh);
+            ++it;
+            if (!(rr > tol2)) break;           // uniform: every block holds the same rr
+            tc_pcg_dir_phase(S, rho_new / rho);
+            rho = rho_new;
+            grid.sync();
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.isc[1] = it; S.isc[2] += it; S.isc[3] += 1;
+    }
+}
+
+// ---- one-launch-per-phase variant ------------------------------------------------------
+__global__ void __launch_bounds__(TC_PCG_THREADS)
+tc_pcg_init_kernel(TcPcg S, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    __shared__ double sh[32];
+    tc_pcg_init_phase(S, S.coef * S.ctrl[1], sh);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { S.isc[0] = 0; S.isc[1] = 0; S.isc[3] += 1; }
+}
+// k1: (first iteration only: finish init scalars) q = P p, partial p.q
+__global__ void __launch_bounds__(TC_PCG_THREADS)
+tc_pcg_k1(TcPcg S, int it, const int* __restrict__ done_flag) {
+    if ((done_flag && *done_flag) || S.isc[0]) return;
+    __shared__ double sh[32];
+    const double dot = tc_sell_spmv_body<SPMV_SHIFT>(S.A, S.p, S.q, nullptr, S.mass, S.coef * S.ctrl[1]);
+    const double bs = block_sum(dot, sh);
+    if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
+    (void)it;
+}
+// pgrid = grid size of the kernel that produced the bank being summed
+__global__ void __launch_bounds__(TC_PCG_THREADS)
+tc_pcg_k2(TcPcg S, int it, int spmv_grid, const int* __restrict__ done_flag) {
+    if ((done_flag && *done_flag) || S.isc[0]) return;
+    __shared__ double sh[32];
+    const double rho = S.sc[it & 1];
+    const double pq = tc_bank_sum(S.partial, spmv_grid, sh);
+    tc_pcg_update_phase(S, rho / pq, sh);
+}
+__global__ void __launch_bounds__(TC_PCG_THREADS)
+tc_pcg_k3(TcPcg S, int it, int upd_grid, const int* __restrict__ done_flag) {
+    if ((done_flag && *done_flag) || S.isc[0]) return;
+    __shared__ double sh[32];
+    const double rho_new = tc_bank_sum(S.partial + 2 * TC_MAX_PARTIALS, upd_grid, sh);
+    const double rr = tc_bank_sum(S.partial + 3 * TC_MAX_PARTIALS, upd_grid, sh);
+    const double rho = S.sc[it & 1];
+    const bool conv = !(rr > S.sc[2]);
+    if (!conv) tc_pcg_dir_phase(S, rho_new / rho);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.sc[(it + 1) & 1] = rho_new;
+        S.sc[4] = rr;
+        S.isc[1] = it + 1; S.isc[2] += 1;
+    }
+    // the done flag must only flip after every block has read isc[0]==0 for this launch:
+    // it is raised by the NEXT launch's prologue instead (tc_pcg_flag_kernel).
+    if (blockIdx.x == 0 && threadIdx.x == 0 && conv) S.sc[5] = 1.0;
+}
+// tiny: stage init scalars / raise the done flag between phases
+__global__ void tc_pcg_scalar_kernel(TcPcg S, int what, int grid_prev, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    __shared__ double sh[32];
+    if (what == 0) {                 // after init: rho, tol2
+        const double rho = tc_bank_sum(S.partial, grid_prev, sh);
+        const double bb = tc_bank_sum(S.partial + TC_MAX_PARTIALS, grid_prev, sh);
+        if (threadIdx.x == 0) {
+            S.sc[0] = rho; S.sc[2] = S.rtol * S.rtol * bb; S.sc[3] = bb; S.sc[5] = 0.0;
+            if (!(bb > 0.0)) S.isc[0] = 1;
+        }
+    } else {                         // after k3: publish convergence
+        if (threadIdx.x == 0 && S.sc[5] != 0.0) S.isc[0] = 1;
+    }
+}

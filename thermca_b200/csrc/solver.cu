@@ -1,0 +1,873 @@
+// Host side of the C ABI (include/thermca_b200.h): solver object, right-hand side
+// pipeline, scipy-equivalent adaptive Runge-Kutta with on-device step control, and the
+// implicit (theta / ROS2) steps on top of the Jacobi-PCG.
+//
+// What it replaces in the reference: the body of thermca/solver.py:transient_solution
+// (solver.py:61-345) including simple_solve_ivp (solver.py:348-390) and, through scipy,
+// RungeKutta._step_impl / rk_step / select_initial_step (scipy/integrate/_ivp/rk.py,
+// common.py — third-party, restated from the installed 1.18.1 sources the reference pins
+// as 1.14.1).
+#include <math.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/thermca_b200.h"
+#include "network.cuh"
+#include "pcg.cuh"
+
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+extern "C" void tc_set_error(const char* file, int line, const char* msg) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s:%d: %s", file, line, msg);
+    g_err = buf;
+}
+extern "C" const char* tc_last_error(void) { return g_err.c_str(); }
+extern "C" int tc_version(void) { return 100; }
+
+// ---- control block layout (device) ------------------------------------------------------
+enum { CT_T = 0, CT_H, CT_HABS, CT_ERR, CT_TEND, CT_RTOL, CT_ATOL, CT_MAXSTEP, CT_TNEW,
+       CT_D0, CT_D1, CT_D2, CT_H0, CT_EXP, CT_INTERVAL, CT_N };
+enum { FL_DONE = 0, FL_ACC, FL_REJ, FL_STATUS, FL_STEP_REJECTED, FL_ACC_THIS, FL_STORED,
+       FL_ACC_LAST, FL_RESULT_STEP, FL_NEXT_COLL, FL_STORE_SLOT, FL_COUNTER, FL_NUM_SKIP,
+       FL_CAPACITY, FL_N };
+
+struct TcLin { int nk; const double* k[7]; double c[7]; };
+
+// out = y + h * sum_j c_j k_j          (scipy rk.py: dy = dot(K[:s].T, a[:s]) * h ; y + dy)
+__global__ void tc_lin_kernel(long long n, const double* y, TcLin L,
+                              const double* __restrict__ ctrl, double* out,
+                              const int* __restrict__ done) {
+    if (done && *done) return;
+    const double h = ctrl[CT_H];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (j < L.nk) acc += L.k[j][i] * L.c[j];
+        out[i] = y[i] + acc * h;
+    }
+}
+
+// partial sums of (a_i/scale_i)^2 [, (b_i/scale_i)^2], scale = atol + |y_i| rtol   (select_initial_step)
+__global__ void tc_norm2_kernel(long long n, const double* __restrict__ y, const double* __restrict__ a,
+                                const double* __restrict__ b, const double* __restrict__ bsub,
+                                const double* __restrict__ ctrl, double* __restrict__ partial,
+                                const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sh[32];
+    const double rtol = ctrl[CT_RTOL], atol = ctrl[CT_ATOL];
+    double s0 = 0.0, s1 = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double sc = atol + fabs(y[i]) * rtol;
+        const double va = a[i] / sc;
+        s0 += va * va;
+        if (b) {
+            const double vb = (bsub ? b[i] - bsub[i] : b[i]) / sc;
+            s1 += vb * vb;
+        }
+    }
+    const double r0 = block_sum(s0, sh);
+    const double r1 = block_sum(s1, sh);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = r0; partial[TC_MAX_PARTIALS + blockIdx.x] = r1; }
+}
+
+// scipy common.py:select_initial_step, first half: h0 from d0, d1
+__global__ void tc_init_h0_kernel(long long n, int G, const double* __restrict__ partial, double* ctrl) {
+    __shared__ double sh[32];
+    const double a = ordered_partial_sum(partial, G, sh);
+    __syncthreads();
+    const double b = ordered_partial_sum(partial + TC_MAX_PARTIALS, G, sh);
+    if (threadIdx.x == 0) {
+        const double d0 = sqrt(a) / sqrt((double)n), d1 = sqrt(b) / sqrt((double)n);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, ctrl[CT_INTERVAL]);
+        ctrl[CT_D0] = d0; ctrl[CT_D1] = d1; ctrl[CT_H0] = h0;
+        ctrl[CT_H] = h0;            // stage time / Euler probe use h0
+    }
+}
+// second half: d2 -> h1 -> h_abs
+__global__ void tc_init_h1_kernel(long long n, int G, const double* __restrict__ partial, double* ctrl,
+                                  double order) {
+    __shared__ double sh[32];
+    const double b = ordered_partial_sum(partial + TC_MAX_PARTIALS, G, sh);
+    if (threadIdx.x == 0) {
+        const double h0 = ctrl[CT_H0], d1 = ctrl[CT_D1];
+        const double d2 = (sqrt(b) / sqrt((double)n)) / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+        else h1 = pow(0.01 / fmax(d1, d2), 1.0 / (order + 1.0));
+        ctrl[CT_D2] = d2;
+        ctrl[CT_HABS] = fmin(fmin(100.0 * h0, h1), fmin(ctrl[CT_INTERVAL], ctrl[CT_MAXSTEP]));
+    }
+}
+
+// scipy rk.py:_step_impl prologue (per attempt)
+__global__ void tc_prepare_kernel(double* ctrl, int* fl) {
+    if (fl[FL_DONE]) return;
+    const double t = ctrl[CT_T];
+    double h_abs = ctrl[CT_HABS];
+    const double min_step = 10.0 * fabs(::nextafter(t, (double)INFINITY) - t);
+    if (fl[FL_ACC_LAST]) {
+        if (h_abs > ctrl[CT_MAXSTEP]) h_abs = ctrl[CT_MAXSTEP];
+        else if (h_abs < min_step) h_abs = min_step;
+        fl[FL_STEP_REJECTED] = 0;
+    }
+    if (h_abs < min_step) { fl[FL_STATUS] = -1; fl[FL_DONE] = 1; return; }
+    double h = h_abs;
+    double t_new = t + h;
+    if (t_new - ctrl[CT_TEND] > 0.0) t_new = ctrl[CT_TEND];
+    h = t_new - t;
+    ctrl[CT_H] = h; ctrl[CT_HABS] = fabs(h); ctrl[CT_TNEW] = t_new;
+}
+
+// error norm + accept / reject + next step size   (scipy rk.py:145-165, common.py:63-65)
+// err_i = h * sum_j E_j K_j[i]; scale = atol + max(|y|,|ynew|) rtol
+__global__ void tc_error_control_kernel(long long n, const double* __restrict__ y,
+                                        const double* __restrict__ ynew, TcLin E, double* ctrl,
+                                        int* fl, double* __restrict__ partial) {
+    if (fl[FL_DONE]) return;
+    __shared__ double sh[32];
+    const double h = ctrl[CT_H], rtol = ctrl[CT_RTOL], atol = ctrl[CT_ATOL];
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (j < E.nk) acc += E.k[j][i] * E.c[j];
+        const double sc = atol + fmax(fabs(y[i]), fabs(ynew[i])) * rtol;
+        const double e = acc * h / sc;
+        s += e * e;
+    }
+    const double bs = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+    if (!last_block_arrives(reinterpret_cast<unsigned int*>(fl + FL_COUNTER))) return;
+    const double tot = ordered_partial_sum(partial, gridDim.x, sh);
+    if (threadIdx.x != 0) return;
+    const double err = sqrt(tot) / sqrt((double)n);
+    ctrl[CT_ERR] = err;
+    double h_abs = ctrl[CT_HABS];
+    const double ex = ctrl[CT_EXP];
+    if (err < 1.0) {
+        double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, ex));
+        if (fl[FL_STEP_REJECTED]) factor = fmin(1.0, factor);
+        h_abs *= factor;
+        ctrl[CT_HABS] = h_abs;
+        ctrl[CT_T] = ctrl[CT_TNEW];
+        fl[FL_ACC] += 1; fl[FL_ACC_THIS] = 1; fl[FL_ACC_LAST] = 1;
+        const double t = ctrl[CT_T], te = ctrl[CT_TEND];
+        // store_results condition (thermca/solver.py:313): skip counter or numpy.isclose(t, t_end)
+        const bool close = fabs(t - te) <= (1e-8 + 1e-5 * fabs(te));
+        if (fl[FL_NEXT_COLL] == fl[FL_RESULT_STEP] || close) {
+            fl[FL_STORE_SLOT] = fl[FL_STORED];
+            fl[FL_STORED] += 1;
+            fl[FL_NEXT_COLL] += fl[FL_NUM_SKIP] + 1;
+        } else {
+            fl[FL_STORE_SLOT] = -1;
+        }
+        fl[FL_RESULT_STEP] += 1;
+        if (t - te >= 0.0) fl[FL_DONE] = 2;    // finished; raised to 1 by the accept kernel
+    } else {
+        h_abs *= fmax(0.2, 0.9 * pow(err, ex));
+        ctrl[CT_HABS] = h_abs;
+        fl[FL_REJ] += 1; fl[FL_STEP_REJECTED] = 1; fl[FL_ACC_THIS] = 0; fl[FL_ACC_LAST] = 0;
+        fl[FL_STORE_SLOT] = -1;
+    }
+}
+
+// on accept: y <- ynew, K0 <- K_last (FSAL), history snapshot
+__global__ void tc_accept_kernel(long long n, long long u, double* __restrict__ y,
+                                 const double* __restrict__ ynew, double* __restrict__ k0,
+                                 const double* __restrict__ klast, const int* __restrict__ fl,
+                                 double* __restrict__ hist_io) {
+    if (fl[FL_DONE] == 1 || !fl[FL_ACC_THIS]) return;
+    const int slot = fl[FL_STORE_SLOT];
+    const long long nio = n - u;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double v = ynew[i];
+        y[i] = v;
+        if (k0) k0[i] = klast[i];
+        if (slot >= 0 && hist_io && i >= u) hist_io[(long long)slot * nio + (i - u)] = v;
+    }
+}
+// network snapshot + flag finalisation (single block)
+__global__ void tc_snapshot_kernel(TcNetParams P, const double* __restrict__ ctrl, int* fl,
+                                   double* __restrict__ hist_net) {
+    if (fl[FL_DONE] == 1) return;
+    if (fl[FL_ACC_THIS]) {
+        const int slot = fl[FL_STORE_SLOT];
+        if (slot >= 0 && hist_net) {
+            const long long w = 1 + 3LL * P.N + 2LL * P.nnz;
+            double* row = hist_net + slot * w;
+            const double* D = P.darena;
+            if (threadIdx.x == 0) row[0] = ctrl[CT_T];
+            for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
+                row[1 + i] = D[P.o_T + i];
+                row[1 + P.N + i] = D[P.o_capy + i];
+                row[1 + 2 * P.N + i] = D[P.o_heat + i];
+            }
+            for (int i = threadIdx.x; i < P.nnz; i += blockDim.x) {
+                row[1 + 3 * P.N + i] = D[P.o_cond + i];
+                row[1 + 3 * P.N + P.nnz + i] = D[P.o_clean + i];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (fl[FL_DONE] == 2) fl[FL_DONE] = 1;
+        else if (fl[FL_ACC_THIS] && fl[FL_STORED] >= fl[FL_CAPACITY]) { fl[FL_STATUS] = 2; fl[FL_DONE] = 1; }
+    }
+}
+
+// generic helpers for the implicit path
+__global__ void tc_copy_kernel(long long n, const double* __restrict__ a, double* __restrict__ out,
+                               const int* __restrict__ done) {
+    if (done && *done) return;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) out[i] = a[i];
+}
+// out = a + s*b
+__global__ void tc_axpby_kernel(long long n, const double* __restrict__ a, double s,
+                                const double* __restrict__ b, double* __restrict__ out,
+                                const int* __restrict__ done) {
+    if (done && *done) return;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) out[i] = a[i] + s * b[i];
+}
+__global__ void tc_advance_time_kernel(double* ctrl, int* fl) {
+    if (fl[FL_DONE]) return;
+    ctrl[CT_T] = ctrl[CT_T] + ctrl[CT_H];
+    fl[FL_ACC] += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+struct FfePart {
+    tc_ffe_desc d;
+    TcSell A;
+    TcSurfLoad load;
+    TcFilmDiag fdiag;
+    double *r, *p, *q, *dinv;          // PCG workspace
+    TcPcg pcg;
+};
+struct LpPart { tc_lp_desc d; TcSell A; const double* b; };
+struct MorPart { tc_mor_desc d; TcMor M; };
+
+struct tc_solver {
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    TcNetParams net{};
+    TcMeanJobs jobs{};
+    int mean_grid = 0;
+    double* mean_partials = nullptr;
+    std::vector<FfePart> ffe;
+    std::vector<LpPart> lp;
+    std::vector<MorPart> mor;
+    long long n_state = 0;
+    bool finalized = false;
+    double* ctrl = nullptr;
+    int* flags = nullptr;
+    double* y = nullptr; double* ynew = nullptr; double* ystage = nullptr;
+    double* K[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* red_partial = nullptr;     // 4 banks
+    double* pcg_sc = nullptr; int* pcg_isc = nullptr;
+    int* pin_flags = nullptr;          // pinned host mirror
+    double* pin_ctrl = nullptr;
+    // history
+    double* hist_io = nullptr; double* hist_net = nullptr; int capacity = 0; int num_skip = 0;
+    // RK
+    int method = TC_RK45; int n_stages = 6;
+    cudaGraphExec_t rk_graph = nullptr;
+    long long nfev = 0;
+    int vec_grid = 148;
+    // implicit
+    double pcg_rtol = 1e-10; int pcg_maxit = 1000; int pcg_mode = TC_PCG_COOP; int coop_grid = 0;
+    double ros_gamma = 1.0 + 0.70710678118654752440;
+};
+
+static int grid_for(long long n, int threads, int cap) {
+    long long g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+extern "C" int tc_create(tc_handle* out, void* cuda_stream) {
+    tc_solver* s = new tc_solver();
+    s->stream = (cudaStream_t)cuda_stream;
+    int dev = 0;
+    TC_CUDA(cudaGetDevice(&dev));
+    TC_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    TC_CUDA(cudaMalloc(&s->ctrl, sizeof(double) * 32));
+    TC_CUDA(cudaMalloc(&s->flags, sizeof(int) * 32));
+    TC_CUDA(cudaMemset(s->ctrl, 0, sizeof(double) * 32));
+    TC_CUDA(cudaMemset(s->flags, 0, sizeof(int) * 32));
+    TC_CUDA(cudaMalloc(&s->red_partial, sizeof(double) * 4 * TC_MAX_PARTIALS));
+    TC_CUDA(cudaMalloc(&s->pcg_sc, sizeof(double) * 16));
+    TC_CUDA(cudaMalloc(&s->pcg_isc, sizeof(int) * 16));
+    TC_CUDA(cudaMemset(s->pcg_sc, 0, sizeof(double) * 16));
+    TC_CUDA(cudaMemset(s->pcg_isc, 0, sizeof(int) * 16));
+    TC_CUDA(cudaMallocHost(&s->pin_flags, sizeof(int) * 32));
+    TC_CUDA(cudaMallocHost(&s->pin_ctrl, sizeof(double) * 32));
+    *out = s;
+    return 0;
+}
+
+extern "C" int tc_destroy(tc_handle s) {
+    if (!s) return 0;
+    if (s->rk_graph) cudaGraphExecDestroy(s->rk_graph);
+    cudaFree(s->ctrl); cudaFree(s->flags); cudaFree(s->red_partial); cudaFree(s->pcg_sc);
+    cudaFree(s->pcg_isc); cudaFree(s->mean_partials);
+    cudaFree(s->y); cudaFree(s->ynew); cudaFree(s->ystage);
+    for (int i = 0; i < 7; ++i) cudaFree(s->K[i]);
+    for (auto& p : s->ffe) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
+    cudaFreeHost(s->pin_flags); cudaFreeHost(s->pin_ctrl);
+    delete s;
+    return 0;
+}
+
+extern "C" int tc_set_network(tc_handle s, const tc_net_desc* d) {
+    TC_CHECK(s && d, "null argument");
+    TcNetParams& P = s->net;
+    P.iarena = d->iarena; P.darena = d->darena;
+    P.cmds = d->iarena + d->cmds_off;
+    P.prog_dir = d->iarena + d->prog_dir_off;
+    P.tab_dir = d->iarena + d->tab_dir_off;
+    P.N = d->N; P.u = d->u; P.nnz = d->nnz;
+    P.o_T = d->o_T; P.o_heat = d->o_heat; P.o_capy = d->o_capy; P.o_vol = d->o_vol;
+    P.o_volcapy = d->o_volcapy; P.o_condy = d->o_condy; P.o_cond = d->o_cond; P.o_clean = d->o_clean;
+    P.o_calc = d->o_calc; P.o_inputs = d->o_inputs;
+    P.o_indptr = d->o_indptr; P.o_indices = d->o_indices; P.o_diag = d->o_diag;
+    s->jobs.njobs = d->n_mean_jobs;
+    s->jobs.job_of_block = d->job_of_block; s->jobs.first_block = d->first_block; s->jobs.nblk = d->nblk;
+    s->jobs.ent_start = (const long long*)d->ent_start; s->jobs.idx = d->ent_idx; s->jobs.w = d->ent_w;
+    s->mean_grid = d->n_mean_blocks;
+    if (s->mean_grid > 0) TC_CUDA(cudaMalloc(&s->mean_partials, sizeof(double) * s->mean_grid));
+    return 0;
+}
+
+extern "C" int tc_add_ffe_part(tc_handle s, const tc_ffe_desc* d) {
+    TC_CHECK(s && d && !s->finalized, "bad state");
+    FfePart p{};
+    p.d = *d;
+    p.A = TcSell{d->n, d->nslices, (const long long*)d->slice_ptr, d->col, d->val};
+    p.load = TcSurfLoad{d->load_nrows, d->load_row, d->load_start, d->load_surf, d->load_bval};
+    p.fdiag = TcFilmDiag{d->fd_nrows, (const long long*)d->fd_pos, d->fd_row, d->fd_abody, d->fd_start,
+                         d->fd_film, d->fd_adata};
+    s->ffe.push_back(p);
+    return 0;
+}
+extern "C" int tc_add_lp_part(tc_handle s, const tc_lp_desc* d) {
+    TC_CHECK(s && d && !s->finalized, "bad state");
+    LpPart p{};
+    p.d = *d;
+    p.A = TcSell{d->n, d->nslices, (const long long*)(s->net.iarena + d->slice_ptr_ioff64),
+                 s->net.iarena + d->col_ioff, s->net.darena + d->val_doff};
+    p.b = s->net.darena + d->b_doff;
+    s->lp.push_back(p);
+    return 0;
+}
+extern "C" int tc_add_mor_part(tc_handle s, const tc_mor_desc* d) {
+    TC_CHECK(s && d && !s->finalized, "bad state");
+    MorPart p{};
+    p.d = *d;
+    p.M = TcMor{d->S, d->r, d->F, d->A_body, d->A_films, d->B_T};
+    s->mor.push_back(p);
+    return 0;
+}
+
+extern "C" int tc_finalize(tc_handle s, int64_t n_state) {
+    TC_CHECK(s && !s->finalized, "bad state");
+    s->n_state = n_state;
+    const size_t bytes = sizeof(double) * (size_t)(n_state > 0 ? n_state : 1);
+    TC_CUDA(cudaMalloc(&s->y, bytes));
+    TC_CUDA(cudaMalloc(&s->ynew, bytes));
+    TC_CUDA(cudaMalloc(&s->ystage, bytes));
+    for (int i = 0; i < 7; ++i) TC_CUDA(cudaMalloc(&s->K[i], bytes));
+    s->vec_grid = grid_for(n_state, 256, s->sm_count * 8);
+    for (auto& p : s->ffe) {
+        const size_t b = sizeof(double) * (size_t)p.d.n;
+        TC_CUDA(cudaMalloc(&p.r, b)); TC_CUDA(cudaMalloc(&p.p, b));
+        TC_CUDA(cudaMalloc(&p.q, b)); TC_CUDA(cudaMalloc(&p.dinv, b));
+    }
+    int occ = 0;
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_pcg_coop_kernel, TC_PCG_THREADS, 0));
+    if (occ > 8) occ = 8;
+    s->coop_grid = occ * s->sm_count;
+    if (s->coop_grid > TC_MAX_PARTIALS) s->coop_grid = TC_MAX_PARTIALS;
+    s->finalized = true;
+    return 0;
+}
+
+// ---- right-hand side pipeline (thermca/solver.py:193-302) ---------------------------------
+static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* out) {
+    cudaStream_t st = s->stream;
+    const int* done = s->flags + FL_DONE;
+    if (s->mean_grid > 0)
+        tc_surf_mean_kernel<<<s->mean_grid, TC_MEAN_THREADS, 0, st>>>(s->jobs, yin, s->mean_partials, done);
+    tc_network_kernel<<<1, TC_NET_THREADS, 0, st>>>(s->net, s->ctrl, c_stage, yin, out, s->mean_partials, done);
+    for (auto& p : s->lp) {
+        const int g = grid_for(p.A.nslices, TC_SPMV_THREADS / 32, s->sm_count * 8);
+        tc_sell_spmv_kernel<SPMV_B><<<g, TC_SPMV_THREADS, 0, st>>>(
+            p.A, yin + p.d.y_off, out + p.d.y_off, p.b, nullptr, s->ctrl, 0.0, nullptr, done);
+    }
+    for (auto& p : s->ffe) {
+        if (p.fdiag.nrows > 0)
+            tc_ffe_film_diag_kernel<<<grid_for(p.fdiag.nrows, 256, s->sm_count * 4), 256, 0, st>>>(
+                p.fdiag, s->net.darena + p.d.films_doff, p.d.val, p.d.adiag, done);
+        const int g = grid_for(p.A.nslices, TC_SPMV_THREADS / 32, s->sm_count * 8);
+        tc_sell_spmv_kernel<SPMV_NEG><<<g, TC_SPMV_THREADS, 0, st>>>(
+            p.A, yin + p.d.y_off, out + p.d.y_off, nullptr, nullptr, s->ctrl, 0.0, nullptr, done);
+        if (p.load.nrows > 0)
+            tc_ffe_surf_load_kernel<<<grid_for(p.load.nrows, 256, s->sm_count * 4), 256, 0, st>>>(
+                p.load, s->net.darena + p.d.flux_doff, out + p.d.y_off, done);
+    }
+    for (auto& p : s->mor) {
+        const int rows = p.M.S * p.M.r;
+        tc_mor_rhs_kernel<<<grid_for(rows, 8, s->sm_count * 4), 256, 0, st>>>(
+            p.M, s->net.darena + p.d.films_doff, s->net.darena + p.d.flux_doff, yin + p.d.y_off,
+            out + p.d.y_off, done);
+    }
+    s->nfev += 1;
+    return 0;
+}
+
+static int set_ctrl(tc_solver* s, int idx, double v) {
+    TC_CUDA(cudaMemcpyAsync(s->ctrl + idx, &v, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int tc_set_time(tc_handle s, double t) { return set_ctrl(s, CT_T, t); }
+
+extern "C" int tc_rhs(tc_handle s, double t, const double* y_dev, double* ydot_dev) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    double c2[2] = {t, 0.0};
+    TC_CUDA(cudaMemcpyAsync(s->ctrl + CT_T, c2, sizeof c2, cudaMemcpyHostToDevice, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    if (enqueue_rhs(s, 0.0, y_dev, ydot_dev)) return -1;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int tc_set_state(tc_handle s, const double* y_dev) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    TC_CUDA(cudaMemcpyAsync(s->y, y_dev, sizeof(double) * s->n_state, cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+extern "C" int tc_get_state(tc_handle s, double* y_dev) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    TC_CUDA(cudaMemcpyAsync(y_dev, s->y, sizeof(double) * s->n_state, cudaMemcpyDeviceToDevice, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+extern "C" int tc_set_history(tc_handle s, double* hist_io, double* hist_net, int32_t capacity, int32_t num_skip) {
+    TC_CHECK(s, "null");
+    s->hist_io = hist_io; s->hist_net = hist_net; s->capacity = capacity; s->num_skip = num_skip;
+    if (s->rk_graph) { cudaGraphExecDestroy(s->rk_graph); s->rk_graph = nullptr; }
+    return 0;
+}
+extern "C" int tc_reset_history(tc_handle s) {
+    int zero = 0;
+    TC_CUDA(cudaMemcpyAsync(s->flags + FL_STORED, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    // a "history full" stop is resumable
+    TC_CUDA(cudaMemcpyAsync(s->pin_flags, s->flags, sizeof(int) * FL_N, cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->pin_flags[FL_STATUS] == 2) {
+        int two[1] = {0};
+        TC_CUDA(cudaMemcpyAsync(s->flags + FL_STATUS, two, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        TC_CUDA(cudaMemcpyAsync(s->flags + FL_DONE, two, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        TC_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return 0;
+}
+
+// ---- Runge-Kutta tableaus (scipy/integrate/_ivp/rk.py: RK23, RK45) ----------------------
+struct Tableau { int n_stages; double C[7]; double A[7][6]; double B[7]; double E[7]; double order; };
+static Tableau tableau(int method) {
+    Tableau T{};
+    if (method == TC_RK45) {
+        T.n_stages = 6; T.order = 4;
+        const double C[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1};
+        const double A[6][5] = {{0, 0, 0, 0, 0},
+                                {1.0 / 5, 0, 0, 0, 0},
+                                {3.0 / 40, 9.0 / 40, 0, 0, 0},
+                                {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+                                {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+                                {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+        const double B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+        const double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+        for (int i = 0; i < 6; ++i) { T.C[i] = C[i]; T.B[i] = B[i]; for (int j = 0; j < 5; ++j) T.A[i][j] = A[i][j]; }
+        for (int i = 0; i < 7; ++i) T.E[i] = E[i];
+    } else {
+        T.n_stages = 3; T.order = 2;
+        const double C[3] = {0, 1.0 / 2, 3.0 / 4};
+        const double A[3][2] = {{0, 0}, {1.0 / 2, 0}, {0, 3.0 / 4}};
+        const double B[3] = {2.0 / 9, 1.0 / 3, 4.0 / 9};
+        const double E[4] = {5.0 / 72, -1.0 / 12, -1.0 / 9, 1.0 / 8};
+        for (int i = 0; i < 3; ++i) { T.C[i] = C[i]; T.B[i] = B[i]; for (int j = 0; j < 2; ++j) T.A[i][j] = A[i][j]; }
+        for (int i = 0; i < 4; ++i) T.E[i] = E[i];
+    }
+    return T;
+}
+
+static int enqueue_rk_attempt(tc_solver* s) {
+    cudaStream_t st = s->stream;
+    const Tableau T = tableau(s->method);
+    const int ns = T.n_stages;
+    const int* done = s->flags + FL_DONE;
+    const long long n = s->n_state;
+    tc_prepare_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
+    for (int sg = 1; sg < ns; ++sg) {
+        TcLin L{};
+        L.nk = sg;
+        for (int j = 0; j < sg; ++j) { L.k[j] = s->K[j]; L.c[j] = T.A[sg][j]; }
+        tc_lin_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->y, L, s->ctrl, s->ystage, done);
+        if (enqueue_rhs(s, T.C[sg], s->ystage, s->K[sg])) return -1;
+    }
+    TcLin Lb{};
+    Lb.nk = ns;
+    for (int j = 0; j < ns; ++j) { Lb.k[j] = s->K[j]; Lb.c[j] = T.B[j]; }
+    tc_lin_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->y, Lb, s->ctrl, s->ynew, done);
+    if (enqueue_rhs(s, 1.0, s->ynew, s->K[ns])) return -1;
+    TcLin Le{};
+    Le.nk = ns + 1;
+    for (int j = 0; j <= ns; ++j) { Le.k[j] = s->K[j]; Le.c[j] = T.E[j]; }
+    tc_error_control_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    tc_accept_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, s->K[0], s->K[ns], s->flags, s->hist_io);
+    tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net);
+    return 0;
+}
+
+static int fetch_flags(tc_solver* s) {
+    TC_CUDA(cudaMemcpyAsync(s->pin_flags, s->flags, sizeof(int) * FL_N, cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaMemcpyAsync(s->pin_ctrl, s->ctrl, sizeof(double) * CT_N, cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int begin_common(tc_solver* s, double t0, double t_end, double rtol, double atol, double max_step,
+                        double exponent) {
+    double c[CT_N];
+    memset(c, 0, sizeof c);
+    c[CT_T] = t0; c[CT_TEND] = t_end; c[CT_RTOL] = rtol; c[CT_ATOL] = atol;
+    c[CT_MAXSTEP] = max_step > 0 ? max_step : INFINITY;
+    c[CT_EXP] = exponent; c[CT_INTERVAL] = fabs(t_end - t0);
+    int f[FL_N];
+    memset(f, 0, sizeof f);
+    f[FL_ACC_LAST] = 1; f[FL_NEXT_COLL] = s->num_skip; f[FL_NUM_SKIP] = s->num_skip;
+    f[FL_CAPACITY] = s->capacity > 0 ? s->capacity : 0x7fffffff; f[FL_STORE_SLOT] = -1;
+    TC_CUDA(cudaMemcpyAsync(s->ctrl, c, sizeof c, cudaMemcpyHostToDevice, s->stream));
+    TC_CUDA(cudaMemcpyAsync(s->flags, f, sizeof f, cudaMemcpyHostToDevice, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    s->nfev = 0;
+    return 0;
+}
+
+// initial snapshot (thermca/solver.py:329-330): rhs at (t0, y0), then store slot 0
+static int store_initial(tc_solver* s) {
+    if (!s->hist_io && !s->hist_net) return 0;
+    int f[3] = {1, 0, 0};   // ACC_THIS = 1, STORED(after) handled below
+    int slot0 = 0, one = 1;
+    TC_CUDA(cudaMemcpyAsync(s->flags + FL_ACC_THIS, f, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    TC_CUDA(cudaMemcpyAsync(s->flags + FL_STORE_SLOT, &slot0, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    TC_CUDA(cudaMemcpyAsync(s->flags + FL_STORED, &one, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    tc_accept_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->n_state, s->net.u, s->ynew, s->y, nullptr, nullptr,
+                                                          s->flags, s->hist_io);
+    tc_snapshot_kernel<<<1, 256, 0, s->stream>>>(s->net, s->ctrl, s->flags, s->hist_net);
+    int zero = 0, m1 = -1;
+    TC_CUDA(cudaMemcpyAsync(s->flags + FL_ACC_THIS, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    TC_CUDA(cudaMemcpyAsync(s->flags + FL_STORE_SLOT, &m1, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int tc_rk_begin(tc_handle s, int32_t method, double t0, double t_end, double rtol, double atol,
+                           double max_step, double first_step) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    TC_CHECK(method == TC_RK45 || method == TC_RK23, "unknown method");
+    if (s->rk_graph && s->method != method) { cudaGraphExecDestroy(s->rk_graph); s->rk_graph = nullptr; }
+    s->method = method;
+    const Tableau T = tableau(method);
+    s->n_stages = T.n_stages;
+    if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / (T.order + 1.0))) return -1;
+    cudaStream_t st = s->stream;
+    const long long n = s->n_state;
+    const int G = s->vec_grid;
+    // transient_solution's own first evaluation + initial snapshot (solver.py:329-330)
+    if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
+    if (store_initial(s)) return -1;
+    if (!(t_end > t0)) {
+        int one = 1;
+        TC_CUDA(cudaMemcpyAsync(s->flags + FL_DONE, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        TC_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+    // scipy RungeKutta.__init__: f = fun(t0, y0); h_abs = select_initial_step(...)
+    if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
+    if (first_step > 0) {
+        if (set_ctrl(s, CT_HABS, first_step)) return -1;
+    } else if (n == 0) {
+        if (set_ctrl(s, CT_HABS, INFINITY)) return -1;
+    } else {
+        tc_norm2_kernel<<<G, 256, 0, st>>>(n, s->y, s->y, s->K[0], nullptr, s->ctrl, s->red_partial, nullptr);
+        tc_init_h0_kernel<<<1, 256, 0, st>>>(n, G, s->red_partial, s->ctrl);
+        TcLin L{};
+        L.nk = 1; L.k[0] = s->K[0]; L.c[0] = 1.0;
+        tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L, s->ctrl, s->ystage, nullptr);   // y1 = y0 + h0 f0
+        if (enqueue_rhs(s, 1.0, s->ystage, s->K[1])) return -1;                        // f1 at t0 + h0
+        tc_norm2_kernel<<<G, 256, 0, st>>>(n, s->y, s->y, s->K[1], s->K[0], s->ctrl, s->red_partial, nullptr);
+        tc_init_h1_kernel<<<1, 256, 0, st>>>(n, G, s->red_partial, s->ctrl, T.order);
+    }
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int tc_rk_advance(tc_handle s, int32_t max_attempts, int32_t poll_every) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    cudaStream_t st = s->stream;
+    if (!s->rk_graph) {
+        cudaGraph_t graph;
+        const long long nfev0 = s->nfev;
+        TC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_rk_attempt(s);
+        TC_CUDA(cudaStreamEndCapture(st, &graph));
+        s->nfev = nfev0;
+        TC_CHECK(rc == 0, "capture failed");
+        TC_CUDA(cudaGraphInstantiate(&s->rk_graph, graph, 0));
+        TC_CUDA(cudaGraphDestroy(graph));
+    }
+    if (poll_every <= 0) poll_every = 16;
+    int launched = 0;
+    while (launched < max_attempts) {
+        int burst = poll_every < max_attempts - launched ? poll_every : max_attempts - launched;
+        // never outrun the history ring: each attempt stores at most one snapshot
+        for (int i = 0; i < burst; ++i) TC_CUDA(cudaGraphLaunch(s->rk_graph, st));
+        launched += burst;
+        s->nfev += (long long)burst * s->n_stages;
+        if (fetch_flags(s)) return -1;
+        if (s->pin_flags[FL_DONE]) break;
+    }
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tc_get_info(tc_handle s, int64_t* info8, double* t_now, double* h_next) {
+    TC_CHECK(s, "null");
+    if (fetch_flags(s)) return -1;
+    info8[0] = s->pin_flags[FL_DONE]; info8[1] = s->pin_flags[FL_ACC]; info8[2] = s->pin_flags[FL_REJ];
+    info8[3] = s->pin_flags[FL_STATUS]; info8[4] = s->pin_flags[FL_STORED]; info8[5] = s->nfev;
+    info8[6] = s->pin_flags[FL_RESULT_STEP]; info8[7] = 0;
+    if (t_now) *t_now = s->pin_ctrl[CT_T];
+    if (h_next) *h_next = s->pin_ctrl[CT_HABS];
+    return 0;
+}
+
+// ---- PCG drivers ---------------------------------------------------------------------------------
+static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int* done) {
+    cudaStream_t st = s ? s->stream : nullptr;
+    if (mode == TC_PCG_COOP) {
+        void* args[] = {(void*)&P, (void*)&done};
+        int g = coop_grid;
+        const int need = grid_for(P.A.nslices, TC_PCG_THREADS / 32, g);
+        if (need < g) g = need;
+        TC_CUDA(cudaLaunchCooperativeKernel((void*)tc_pcg_coop_kernel, dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
+        return 0;
+    }
+    const int gv = grid_for(P.A.n, TC_PCG_THREADS, TC_MAX_PARTIALS);
+    const int gs = grid_for(P.A.nslices, TC_PCG_THREADS / 32, TC_MAX_PARTIALS);
+    tc_pcg_init_kernel<<<gv, TC_PCG_THREADS, 0, st>>>(P, done);
+    tc_pcg_scalar_kernel<<<1, TC_PCG_THREADS, 0, st>>>(P, 0, gv, done);
+    int flag = 0;
+    for (int it = 0; it < P.maxit; ++it) {
+        tc_pcg_k1<<<gs, TC_PCG_THREADS, 0, st>>>(P, it, done);
+        tc_pcg_k2<<<gv, TC_PCG_THREADS, 0, st>>>(P, it, gs, done);
+        tc_pcg_k3<<<gv, TC_PCG_THREADS, 0, st>>>(P, it, gv, done);
+        tc_pcg_scalar_kernel<<<1, TC_PCG_THREADS, 0, st>>>(P, 1, gv, done);
+        if ((it % 8) == 7) {
+            TC_CUDA(cudaMemcpyAsync(&flag, P.isc, sizeof(int), cudaMemcpyDeviceToHost, st));
+            TC_CUDA(cudaStreamSynchronize(st));
+            if (flag) break;
+        }
+    }
+    return 0;
+}
+
+// z = (I + coef*h*A_p)^-1 rhs_p on FE parts, z = rhs elsewhere
+static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, double* z) {
+    cudaStream_t st = s->stream;
+    const int* done = s->flags + FL_DONE;
+    tc_copy_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, rhs, z, done);
+    for (auto& p : s->ffe) {
+        TcPcg& P = p.pcg;
+        P.A = p.A; P.mass = p.d.mass; P.adiag = p.d.adiag;
+        P.rhs = rhs + p.d.y_off; P.x = z + p.d.y_off;
+        P.r = p.r; P.p = p.p; P.q = p.q; P.dinv = p.dinv;
+        P.partial = s->red_partial; P.sc = s->pcg_sc; P.isc = s->pcg_isc;
+        P.rtol = s->pcg_rtol; P.maxit = s->pcg_maxit; P.ctrl = s->ctrl; P.coef = coef;
+        if (launch_pcg(s, P, s->pcg_mode, s->coop_grid, done)) return -1;
+    }
+    return 0;
+}
+
+extern "C" int tc_theta_steps(tc_handle s, int32_t nsteps, double theta, double h_step, double pcg_rtol,
+                              int32_t pcg_maxit, int32_t pcg_mode) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
+    if (set_ctrl(s, CT_H, h_step)) return -1;
+    cudaStream_t st = s->stream;
+    const int* done = s->flags + FL_DONE;
+    for (int k = 0; k < nsteps; ++k) {
+        if (enqueue_rhs(s, theta, s->y, s->K[0])) return -1;                 // f(t + theta h, y)
+        if (enqueue_block_solve(s, theta, s->K[0], s->K[1])) return -1;      // (I + theta h A) z = f
+        TcLin L{};
+        L.nk = 1; L.k[0] = s->K[1]; L.c[0] = 1.0;
+        tc_lin_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, s->y, L, s->ctrl, s->y, done);  // y += h z
+        tc_advance_time_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
+    }
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, double atol, double max_step,
+                             double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
+    if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / 2.0)) return -1;
+    if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
+    if (store_initial(s)) return -1;
+    double h0 = first_step;
+    if (!(h0 > 0)) h0 = 1e-3 * fabs(t_end - t0);
+    if (set_ctrl(s, CT_HABS, h0)) return -1;
+    if (!(t_end > t0)) {
+        int one = 1;
+        TC_CUDA(cudaMemcpyAsync(s->flags + FL_DONE, &one, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        TC_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return 0;
+}
+
+// One ROS2 attempt (Verwer et al. 1999): gamma = 1 + 1/sqrt(2), W-method with J ~ -blockdiag(A_p)
+//   (I + g h A) k1 = f(t, y);  (I + g h A) k2 = f(t + h, y + h k1) - 2 k1
+//   y+ = y + 1.5 h k1 + 0.5 h k2;  err = y+ - (y + h k1) = 0.5 h (k1 + k2)
+static int enqueue_ros2_attempt(tc_solver* s) {
+    cudaStream_t st = s->stream;
+    const int* done = s->flags + FL_DONE;
+    const long long n = s->n_state;
+    const int G = s->vec_grid;
+    tc_prepare_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
+    if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
+    if (enqueue_block_solve(s, s->ros_gamma, s->K[0], s->K[1])) return -1;          // k1
+    TcLin L1{};
+    L1.nk = 1; L1.k[0] = s->K[1]; L1.c[0] = 1.0;
+    tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L1, s->ctrl, s->ystage, done);       // y + h k1
+    if (enqueue_rhs(s, 1.0, s->ystage, s->K[2])) return -1;
+    tc_axpby_kernel<<<G, 256, 0, st>>>(n, s->K[2], -2.0, s->K[1], s->K[3], done);  // f2 - 2 k1
+    if (enqueue_block_solve(s, s->ros_gamma, s->K[3], s->K[4])) return -1;          // k2
+    TcLin L2{};
+    L2.nk = 2; L2.k[0] = s->K[1]; L2.c[0] = 1.5; L2.k[1] = s->K[4]; L2.c[1] = 0.5;
+    tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L2, s->ctrl, s->ynew, done);
+    TcLin Le{};
+    Le.nk = 2; Le.k[0] = s->K[1]; Le.c[0] = 0.5; Le.k[1] = s->K[4]; Le.c[1] = 0.5;
+    tc_error_control_kernel<<<G, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    tc_accept_kernel<<<G, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, nullptr, nullptr, s->flags, s->hist_io);
+    tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net);
+    return 0;
+}
+
+extern "C" int tc_ros2_advance(tc_handle s, int32_t max_attempts, int32_t poll_every) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    if (poll_every <= 0) poll_every = 4;
+    int launched = 0;
+    while (launched < max_attempts) {
+        int burst = poll_every < max_attempts - launched ? poll_every : max_attempts - launched;
+        for (int i = 0; i < burst; ++i)
+            if (enqueue_ros2_attempt(s)) return -1;
+        launched += burst;
+        if (fetch_flags(s)) return -1;
+        if (s->pin_flags[FL_DONE]) break;
+    }
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tc_pcg_stats(tc_handle s, int64_t* stats4) {
+    int isc[4];
+    TC_CUDA(cudaMemcpyAsync(isc, s->pcg_isc, sizeof isc, cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    stats4[0] = isc[2]; stats4[1] = isc[3]; stats4[2] = isc[1]; stats4[3] = s->coop_grid;
+    return 0;
+}
+
+// ---- stand-alone entry points --------------------------------------------------------------------
+extern "C" int tc_sell_spmv(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
+                            const int64_t* slice_ptr, const int32_t* col, const double* val,
+                            const double* x, double* y, const double* b, const double* mass, double shift,
+                            int32_t grid_blocks) {
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    TcSell A{n, nslices, (const long long*)slice_ptr, col, val};
+    int g = grid_blocks > 0 ? grid_blocks : grid_for(nslices, TC_SPMV_THREADS / 32, 148 * 8);
+    static double* one_ctrl = nullptr;      // ctrl[1] = 1 so that shift == coef
+    static double* scratch = nullptr;
+    if (!one_ctrl) {
+        TC_CUDA(cudaMalloc(&one_ctrl, sizeof(double) * 4));
+        const double c[4] = {0.0, 1.0, 0.0, 0.0};
+        TC_CUDA(cudaMemcpy(one_ctrl, c, sizeof c, cudaMemcpyHostToDevice));
+        TC_CUDA(cudaMalloc(&scratch, sizeof(double) * 4 * TC_MAX_PARTIALS));
+    }
+    if (g > TC_MAX_PARTIALS) g = TC_MAX_PARTIALS;
+    if (mode == SPMV_NEG)
+        tc_sell_spmv_kernel<SPMV_NEG><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, nullptr, nullptr, one_ctrl, 0.0, nullptr, nullptr);
+    else if (mode == SPMV_B)
+        tc_sell_spmv_kernel<SPMV_B><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, b, nullptr, one_ctrl, 0.0, nullptr, nullptr);
+    else
+        tc_sell_spmv_kernel<SPMV_SHIFT><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, nullptr, mass, one_ctrl, shift, scratch, nullptr);
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
+                            const int64_t* slice_ptr, const int32_t* col, const double* val,
+                            const double* mass, const double* adiag, const double* rhs, double* x,
+                            double shift, double rtol, int32_t maxit, int32_t* iters) {
+    tc_solver tmp;
+    tmp.stream = (cudaStream_t)cuda_stream;
+    TcPcg P{};
+    P.A = TcSell{n, nslices, (const long long*)slice_ptr, col, val};
+    double* ws = nullptr; double* aux = nullptr; int* isc = nullptr;
+    TC_CUDA(cudaMalloc(&ws, sizeof(double) * 4 * (size_t)n));
+    TC_CUDA(cudaMalloc(&aux, sizeof(double) * (4 * TC_MAX_PARTIALS + 16 + 4)));
+    TC_CUDA(cudaMalloc(&isc, sizeof(int) * 16));
+    TC_CUDA(cudaMemset(isc, 0, sizeof(int) * 16));
+    TC_CUDA(cudaMemset(aux, 0, sizeof(double) * (4 * TC_MAX_PARTIALS + 20)));
+    const double c[4] = {0.0, 1.0, 0.0, 0.0};
+    double* ctrl = aux + 4 * TC_MAX_PARTIALS + 16;
+    TC_CUDA(cudaMemcpy(ctrl, c, sizeof c, cudaMemcpyHostToDevice));
+    P.mass = mass; P.adiag = adiag; P.rhs = rhs; P.x = x;
+    P.r = ws; P.p = ws + n; P.q = ws + 2 * (size_t)n; P.dinv = ws + 3 * (size_t)n;
+    P.partial = aux; P.sc = aux + 4 * TC_MAX_PARTIALS; P.isc = isc;
+    P.rtol = rtol; P.maxit = maxit; P.ctrl = ctrl; P.coef = shift;
+    int dev = 0, sms = 148, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_pcg_coop_kernel, TC_PCG_THREADS, 0));
+    if (occ > 8) occ = 8;
+    int cgp = occ * sms;
+    if (cgp > TC_MAX_PARTIALS) cgp = TC_MAX_PARTIALS;
+    int rc = launch_pcg(&tmp, P, mode, cgp, nullptr);
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize(tmp.stream);
+        if (e != cudaSuccess) { tc_set_error(__FILE__, __LINE__, cudaGetErrorString(e)); rc = -1; }
+    }
+    int h_isc[4] = {0, 0, 0, 0};
+    if (rc == 0) cudaMemcpy(h_isc, isc, sizeof h_isc, cudaMemcpyDeviceToHost);
+    if (iters) *iters = h_isc[1];
+    cudaFree(ws); cudaFree(aux); cudaFree(isc);
+    tmp.pin_flags = nullptr;
+    return rc;
+}
