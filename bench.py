@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""Headline benchmark: DOF*steps/s of the implicit transient step on a synthetic FE cuboid.
+
+A "step" is one implicit theta step (theta = 1/2) of the stacked thermal system: one
+right-hand-side evaluation (surface means -> fused network kernel -> SELL SpMV -> surface
+loads) and one Jacobi-PCG solve of (M + theta*h*K) — north_star items (a)+(b)+(c).
+Workload (BASELINE config #2 scaled to the size the metric is quoted on): one
+tetrahedral FE cuboid, ~10 M DOF, 1 kW on the bottom face, 10 W/m2K film on the other
+faces, operator generated in HBM by csrc/synth.cu.
+
+  python bench.py --gpus 1 --steps 8 --warmup 3             (our arm)
+  python bench.py --impl reference --steps 3 --warmup 1     (CPU reference arm)
+  torchrun ... bench.py --gpus N ...                          (row-partitioned, N > 1)
+
+Prints ONE JSON line (see the driver contract in the repo README / DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+THETA = 0.5
+H_STEP = 1.0            # seconds of simulated time per step
+PCG_RTOL = 1e-8
+FILM, HEAT, T_ENV = 10.0, 1000.0, 20.0
+
+
+def algorithmic_bytes_per_iteration(n_rows, nnz):
+    """Jacobi-PCG iteration on CSR-equivalent storage:
+    SpMV  nnz*(8+4) + rows*(4 indptr + 8 p gather + 8 mass + 8 q write)
+    update x,r (+dots): read x,p,r,q,dinv + write x,r = 56 B/row
+    direction        : read r,dinv,p + write p       = 32 B/row"""
+    return nnz * 12 + n_rows * (28 + 56 + 32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.gpu = gpu_index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.thread.join(timeout=3)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ---- CPU reference arm -------------------------------------------------------------------------
+def cpu_theta_baseline(target_dof, steps, warmup, threads):
+    """The like-for-like CPU port (oracle/theta_oracle.py) of the same step on a bounded
+    sample of the workload: same generator, same physics, smaller mesh."""
+    from thermca_b200.synth import cuboid_spec
+    from thermca_b200.workloads import cuboid_dims
+    from theta_oracle import theta_cg_steps
+    import scipy.sparse as sp
+    nx, ny, nz = cuboid_dims(target_dof)
+    spec = cuboid_spec(nx, ny, nz, jitter=0.15, heat=HEAT, film=FILM, env_temp=T_ENV)
+    p = spec["ffe"][0]
+    n = int(p["dof"])
+    A = sp.csr_matrix((p["A_data"], p["A_body"]["indices"], p["A_body"]["indptr"]), shape=(n, n))
+    mass = 1.0 / p["M_inv"]
+    b = np.zeros(n)
+    flux = [HEAT / p["surf_areas"][0], FILM * T_ENV]
+    for s in range(2):
+        b[p["B_idx"][s]] += p["B_val"][s] * flux[s]
+    y = np.full(n, 20.0)
+    best = None
+    for backend, thr in (("scipy", 1), ("torch", threads)):
+        try:
+            yw, _, _ = theta_cg_steps(A, mass, b, y, warmup, H_STEP, THETA, PCG_RTOL, backend=backend, threads=thr)
+            _, iters, sec = theta_cg_steps(A, mass, b, yw, steps, H_STEP, THETA, PCG_RTOL, backend=backend, threads=thr)
+        except Exception:
+            continue
+        val = n * steps / sec
+        if best is None or val > best["value"]:
+            best = {"value": val, "cores": thr, "backend": backend, "iters_per_step": iters / steps,
+                    "ms_per_step": 1e3 * sec / steps}
+    best.update({"dof": n, "nnz": int(A.nnz), "dims": [nx, ny, nz]})
+    return best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    r = cpu_theta_baseline(args.cpu_dof, args.steps, max(args.warmup, 1), threads)
+    sample = (f"{r['dof']} DOF Kuhn cuboid ({r['dims'][0]}x{r['dims'][1]}x{r['dims'][2]} cells, same generator), "
+              f"{args.steps} theta-PCG steps, {r['backend']} CSR SpMV")
+    line = {
+        "impl": "reference", "metric": "DOF*steps/s (implicit theta-PCG step, full FE cuboid)",
+        "value": r["value"], "unit": "DOF*steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg#2 full FE cuboid, theta=0.5 Jacobi-PCG step (CPU port, bounded sample)",
+                   "dof": r["dof"], "pcg_rtol": PCG_RTOL, "h_step_s": H_STEP,
+                   "iters_per_step": r["iters_per_step"]},
+        "cpu_baseline": {"value": r["value"], "unit": "DOF*steps/s", "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["value"], "unit": "DOF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---- our arm -------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from thermca_b200.device import DeviceSolver
+    from thermca_b200.workloads import cuboid_dims, device_cuboid_spec
+
+    if world > 1:
+        from thermca_b200.dist import run_partitioned_bench
+        line = run_partitioned_bench(args, world, rank, local_rank)
+        if rank == 0:
+            print(json.dumps(line))
+        dist.destroy_process_group()
+        return
+
+    nx, ny, nz = cuboid_dims(args.dof)
+    spec = device_cuboid_spec(nx, ny, nz, heat=HEAT, film=FILM, env_temp=T_ENV)
+    dev = DeviceSolver(spec)
+    n = dev.n_state
+    op = spec["ffe"][0]["sell"]
+    nnz = int(torch.count_nonzero(op["val"]).item())
+
+    def sync():
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    dev.theta_steps(args.warmup, H_STEP, THETA, t0=0.0, pcg_rtol=PCG_RTOL, pcg_mode=args.pcg_mode)
+    sync()
+    dev.timing(True)
+    it0 = dev.pcg_stats()["iterations"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        sync()
+        with torch.cuda.stream(dev.stream):
+            e0.record(dev.stream)
+            dev.theta_steps(args.steps, H_STEP, THETA, pcg_rtol=PCG_RTOL, pcg_mode=args.pcg_mode, sync=False)
+            e1.record(dev.stream)
+        sync()
+    ms = e0.elapsed_time(e1)
+    tm = dev.timing(False)
+    iters = dev.pcg_stats()["iterations"] - it0
+    value = n * args.steps / (ms * 1e-3)
+    peak, peak_kind = measured_peak()
+    pcg_ms_per_launch = tm["pcg_ms"] / max(tm["pcg_launches"], 1)
+    iters_per_solve = iters / max(tm["pcg_launches"], 1)
+    bytes_per_launch = algorithmic_bytes_per_iteration(n, nnz) * iters_per_solve + n * 48   # + init phase
+    achieved = bytes_per_launch / (pcg_ms_per_launch * 1e-3) / 1e9
+    y_dev = dev.get_state()
+
+    # ---- end to end through the host-buffer API: state up, step, state down ---------------------
+    host_y = torch.from_numpy(y_dev).pin_memory()
+    dev_y = torch.empty(n, dtype=torch.float64, device="cuda")
+    e2e_steps = max(2, min(args.steps, 4))
+    sync()
+    t_e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dev_y.copy_(host_y, non_blocking=True)
+        dev.set_state(dev_y)
+        dev.theta_steps(1, H_STEP, THETA, pcg_rtol=PCG_RTOL, pcg_mode=args.pcg_mode)
+        host_y.copy_(dev.get_state_into(dev_y))
+    sync()
+    e2e_sec = time.perf_counter() - t_e0
+    e2e_val = n * e2e_steps / e2e_sec
+
+    cpu = cpu_theta_baseline(args.cpu_dof, 2, 1, os.cpu_count() or 1) if not args.no_cpu else None
+    line = {
+        "metric": "DOF*steps/s (implicit theta-PCG step, full FE cuboid)", "value": value, "unit": "DOF*steps/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg#2 full FE cuboid {nx}x{ny}x{nz} cells = {n} DOF (metric's 10M-DOF size), "
+                               "theta=0.5 Jacobi-PCG step", "dof": n, "nnz": nnz, "pcg_rtol": PCG_RTOL,
+                   "h_step_s": H_STEP, "iters_per_step": iters / args.steps,
+                   "l2": "inputs (1.8 GB operator + 0.5 GB vectors) exceed the 126 MB L2",
+                   "pcg": "cooperative persistent kernel" if args.pcg_mode == 0 else "one launch per phase"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_val, "unit": "DOF*steps/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+                "steps": e2e_steps},
+        "gpu_launches": tm["launches"],
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "tc_pcg_coop_kernel", "peak_kind": peak_kind,
+                     "ms_per_launch": pcg_ms_per_launch, "iters_per_launch": iters_per_solve,
+                     "algorithmic_bytes_per_row_iter": algorithmic_bytes_per_iteration(n, nnz) / n,
+                     "share_of_step": tm["pcg_ms"] / ms},
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {
+            "value": cpu["value"], "unit": "DOF*steps/s", "cores": cpu["cores"], "kind": "port",
+            "sample": f"{cpu['dof']} DOF cuboid (same generator), 2 theta-PCG steps, {cpu['backend']} CSR SpMV, "
+                      f"{cpu['iters_per_step']:.0f} iters/step"}
+    dev.close()
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dof", type=float, default=10.0e6, help="target DOF per GPU")
+    ap.add_argument("--cpu-dof", type=float, default=0.5e6, help="DOF of the bounded CPU sample")
+    ap.add_argument("--pcg-mode", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.dof, args.cpu_dof = int(args.dof), int(args.cpu_dof)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,9 @@ int tc_ros2_begin(tc_handle h, double t0, double t_end, double rtol, double atol
                   double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode);
 int tc_ros2_advance(tc_handle h, int32_t max_attempts, int32_t poll_every);
 int tc_set_time(tc_handle h, double t);
+/* Switch CUDA-event timing of the PCG launches on/off; returns (and clears) the time and launch
+ * counts accumulated since the previous call. */
+int tc_timing(tc_handle h, int32_t enable, double* pcg_ms, int64_t* pcg_launches, int64_t* launches);
 /* PCG statistics of the implicit path: total iterations, solves, last iteration count */
 int tc_pcg_stats(tc_handle h, int64_t* stats4);
 

@@ -1,0 +1,74 @@
+"""CPU ORACLE for the implicit path — TEST / BASELINE INFRASTRUCTURE ONLY.
+
+The reference has no implicit scheme ("parity unpinned" by the
+reference's own tests), so this file restates, on the reference's operators
+(FFEIO.A / M_inv, thermca/fem/ffe_io.py:40-65):
+
+* ``theta_step_direct``  – one theta step with scipy's sparse direct solver (parity target
+  of the device PCG at 1e-9),
+* ``theta_cg_steps``     – the like-for-like CPU port of the device algorithm: Jacobi-PCG
+  on M + theta*h*K, SpMV by scipy ``csr_matvec`` (1 thread, what thermca/_utils/sparse.py:10
+  falls back to) or by torch's CSR kernel on all host threads (stands in for the optional
+  MKL path, thermca/_utils/sparse.py:6-9).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+def theta_step_direct(A, f, y, h, theta):
+    n = A.shape[0]
+    z = spla.spsolve((sp.identity(n, format="csc") + theta * h * A.tocsc()), f)
+    return y + h * z
+
+
+class _TorchCsr:
+    def __init__(self, A, threads):
+        import torch
+        torch.set_num_threads(threads)
+        self.torch = torch
+        self.A = torch.sparse_csr_tensor(torch.from_numpy(A.indptr.astype(np.int64)),
+                                         torch.from_numpy(A.indices.astype(np.int64)),
+                                         torch.from_numpy(A.data), size=A.shape, dtype=torch.float64)
+
+    def __call__(self, x):
+        return (self.A @ self.torch.from_numpy(x)).numpy()
+
+
+def theta_cg_steps(A, mass, b, y, nsteps, h, theta=0.5, rtol=1e-8, maxit=2000, backend="scipy", threads=1):
+    """``nsteps`` theta steps of y' = b - A y with Jacobi-PCG on mass*(I + theta h A).
+    Returns (y, total CG iterations, seconds)."""
+    A = sp.csr_matrix(A)
+    matvec = _TorchCsr(A, threads) if backend == "torch" else (lambda x: A @ x)
+    shift = theta * h
+    adiag = A.diagonal()
+    dinv = 1.0 / (mass * (1.0 + shift * adiag))
+    iters = 0
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        f = b - matvec(y)
+        r = mass * f
+        x = np.zeros_like(y)
+        z = dinv * r
+        p = z.copy()
+        rho = r @ z
+        tol2 = rtol * rtol * (r @ r)
+        for _it in range(maxit):
+            q = mass * (p + shift * matvec(p))
+            alpha = rho / (p @ q)
+            x += alpha * p
+            r -= alpha * q
+            iters += 1
+            rr = r @ r
+            if not rr > tol2:
+                break
+            z = dinv * r
+            rho_new = r @ z
+            p = z + (rho_new / rho) * p
+            rho = rho_new
+        y = y + h * x
+    return y, iters, time.perf_counter() - t0

@@ -281,8 +281,14 @@ struct tc_solver {
     // RK
     int method = TC_RK45; int n_stages = 6;
     cudaGraphExec_t rk_graph = nullptr;
-    long long nfev = 0;
+    long long nfev = 0;            // host-side count of enqueued RHS pipelines (diagnostic)
+    long long nfev_base = 0;       // evaluations outside step attempts (initial snapshot, f0, step probe)
+    int evals_per_attempt = 0;
+    long long launches = 0;        // kernels launched by this solver (host count)
+    std::vector<cudaEvent_t> ev;   // (start, stop) pairs around PCG launches when timing is on
+    bool timing = false;
     int vec_grid = 148;
+    long long attempt_kernels = 0;
     // implicit
     double pcg_rtol = 1e-10; int pcg_maxit = 1000; int pcg_mode = TC_PCG_COOP; int coop_grid = 0;
     double ros_gamma = 1.0 + 0.70710678118654752440;
@@ -432,6 +438,8 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
             out + p.d.y_off, done);
     }
     s->nfev += 1;
+    s->launches += (s->mean_grid > 0 ? 1 : 0) + 1 + (long long)s->lp.size() + (long long)s->mor.size();
+    for (auto& p : s->ffe) s->launches += 1 + (p.fdiag.nrows > 0 ? 1 : 0) + (p.load.nrows > 0 ? 1 : 0);
     return 0;
 }
 
@@ -540,6 +548,7 @@ static int enqueue_rk_attempt(tc_solver* s) {
     tc_error_control_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
     tc_accept_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, s->K[0], s->K[ns], s->flags, s->hist_io);
     tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net);
+    s->launches += ns + 4;   // stage combinations, prepare, error control, accept, snapshot
     return 0;
 }
 
@@ -595,6 +604,8 @@ extern "C" int tc_rk_begin(tc_handle s, int32_t method, double t0, double t_end,
     const Tableau T = tableau(method);
     s->n_stages = T.n_stages;
     if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / (T.order + 1.0))) return -1;
+    s->evals_per_attempt = T.n_stages;
+    s->nfev_base = 1;
     cudaStream_t st = s->stream;
     const long long n = s->n_state;
     const int G = s->vec_grid;
@@ -609,6 +620,7 @@ extern "C" int tc_rk_begin(tc_handle s, int32_t method, double t0, double t_end,
     }
     // scipy RungeKutta.__init__: f = fun(t0, y0); h_abs = select_initial_step(...)
     if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
+    s->nfev_base += 1;
     if (first_step > 0) {
         if (set_ctrl(s, CT_HABS, first_step)) return -1;
     } else if (n == 0) {
@@ -620,6 +632,7 @@ extern "C" int tc_rk_begin(tc_handle s, int32_t method, double t0, double t_end,
         L.nk = 1; L.k[0] = s->K[0]; L.c[0] = 1.0;
         tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L, s->ctrl, s->ystage, nullptr);   // y1 = y0 + h0 f0
         if (enqueue_rhs(s, 1.0, s->ystage, s->K[1])) return -1;                        // f1 at t0 + h0
+        s->nfev_base += 1;
         tc_norm2_kernel<<<G, 256, 0, st>>>(n, s->y, s->y, s->K[1], s->K[0], s->ctrl, s->red_partial, nullptr);
         tc_init_h1_kernel<<<1, 256, 0, st>>>(n, G, s->red_partial, s->ctrl, T.order);
     }
@@ -633,11 +646,13 @@ extern "C" int tc_rk_advance(tc_handle s, int32_t max_attempts, int32_t poll_eve
     cudaStream_t st = s->stream;
     if (!s->rk_graph) {
         cudaGraph_t graph;
-        const long long nfev0 = s->nfev;
+        const long long nfev0 = s->nfev, l0 = s->launches;
         TC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int rc = enqueue_rk_attempt(s);
         TC_CUDA(cudaStreamEndCapture(st, &graph));
         s->nfev = nfev0;
+        s->attempt_kernels = s->launches - l0;
+        s->launches = l0;
         TC_CHECK(rc == 0, "capture failed");
         TC_CUDA(cudaGraphInstantiate(&s->rk_graph, graph, 0));
         TC_CUDA(cudaGraphDestroy(graph));
@@ -650,6 +665,7 @@ extern "C" int tc_rk_advance(tc_handle s, int32_t max_attempts, int32_t poll_eve
         for (int i = 0; i < burst; ++i) TC_CUDA(cudaGraphLaunch(s->rk_graph, st));
         launched += burst;
         s->nfev += (long long)burst * s->n_stages;
+        s->launches += (long long)burst * s->attempt_kernels;
         if (fetch_flags(s)) return -1;
         if (s->pin_flags[FL_DONE]) break;
     }
@@ -661,8 +677,9 @@ extern "C" int tc_get_info(tc_handle s, int64_t* info8, double* t_now, double* h
     TC_CHECK(s, "null");
     if (fetch_flags(s)) return -1;
     info8[0] = s->pin_flags[FL_DONE]; info8[1] = s->pin_flags[FL_ACC]; info8[2] = s->pin_flags[FL_REJ];
-    info8[3] = s->pin_flags[FL_STATUS]; info8[4] = s->pin_flags[FL_STORED]; info8[5] = s->nfev;
-    info8[6] = s->pin_flags[FL_RESULT_STEP]; info8[7] = 0;
+    info8[3] = s->pin_flags[FL_STATUS]; info8[4] = s->pin_flags[FL_STORED];
+    info8[5] = s->nfev_base + (long long)s->evals_per_attempt * (s->pin_flags[FL_ACC] + s->pin_flags[FL_REJ]);
+    info8[6] = s->pin_flags[FL_RESULT_STEP]; info8[7] = s->launches;
     if (t_now) *t_now = s->pin_ctrl[CT_T];
     if (h_next) *h_next = s->pin_ctrl[CT_HABS];
     return 0;
@@ -676,7 +693,14 @@ static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int
         int g = coop_grid;
         const int need = grid_for(P.A.nslices, TC_PCG_THREADS / 32, g);
         if (need < g) g = need;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (s && s->timing) {
+            TC_CUDA(cudaEventCreate(&e0)); TC_CUDA(cudaEventCreate(&e1));
+            TC_CUDA(cudaEventRecord(e0, st));
+        }
         TC_CUDA(cudaLaunchCooperativeKernel((void*)tc_pcg_coop_kernel, dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
+        if (e0) { TC_CUDA(cudaEventRecord(e1, st)); s->ev.push_back(e0); s->ev.push_back(e1); }
+        if (s) s->launches += 1;
         return 0;
     }
     const int gv = grid_for(P.A.n, TC_PCG_THREADS, TC_MAX_PARTIALS);
@@ -729,6 +753,7 @@ extern "C" int tc_theta_steps(tc_handle s, int32_t nsteps, double theta, double 
         L.nk = 1; L.k[0] = s->K[1]; L.c[0] = 1.0;
         tc_lin_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, s->y, L, s->ctrl, s->y, done);  // y += h z
         tc_advance_time_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
+        s->launches += 3;   // block-solve copy, y update, time advance (+ rhs and pcg counted inside)
     }
     TC_CUDA(cudaGetLastError());
     return 0;
@@ -739,6 +764,8 @@ extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, 
     TC_CHECK(s && s->finalized, "solver not finalized");
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
     if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / 2.0)) return -1;
+    s->evals_per_attempt = 2;
+    s->nfev_base = 1;
     if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
     if (store_initial(s)) return -1;
     double h0 = first_step;
@@ -793,6 +820,25 @@ extern "C" int tc_ros2_advance(tc_handle s, int32_t max_attempts, int32_t poll_e
         if (s->pin_flags[FL_DONE]) break;
     }
     TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tc_timing(tc_handle s, int32_t enable, double* pcg_ms, int64_t* pcg_launches, int64_t* launches) {
+    TC_CHECK(s, "null");
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < s->ev.size(); i += 2) {
+        float f = 0.f;
+        TC_CUDA(cudaEventElapsedTime(&f, s->ev[i], s->ev[i + 1]));
+        ms += f;
+        cudaEventDestroy(s->ev[i]); cudaEventDestroy(s->ev[i + 1]);
+    }
+    if (pcg_ms) *pcg_ms = ms;
+    if (pcg_launches) *pcg_launches = (int64_t)(s->ev.size() / 2);
+    if (launches) *launches = s->launches;
+    s->ev.clear();
+    s->timing = enable != 0;
+    s->launches = 0;
     return 0;
 }
 

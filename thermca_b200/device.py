@@ -130,7 +130,9 @@ class DeviceSolver:
         self.lib = _cabi.load_library()
         self.spec = spec
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.stream = torch.cuda.current_stream(self.dev)
+        # a dedicated non-default stream: the RK attempt is replayed as a CUDA graph and the
+        # legacy default stream cannot be captured
+        self.stream = torch.cuda.Stream(self.dev)
         self._keep = []                 # device tensors referenced by raw pointer
         self.N, self.u, self.nnz = int(spec["N"]), int(spec["u"]), int(len(spec["rc_data"]))
         self.lp_off, self.ffe_off, self.mor_off, self.n_state = state_offsets(spec)
@@ -139,6 +141,7 @@ class DeviceSolver:
         self._handle = _cabi.vp()
         _cabi.check(self.lib.tc_create(C.byref(self._handle), C.c_void_p(self.stream.cuda_stream)))
         self._pack()
+        torch.cuda.synchronize(self.dev)        # uploads were issued on torch's current stream
         self.set_state(self.initial_state())
 
     # -- helpers ------------------------------------------------------------------------------
@@ -453,16 +456,25 @@ class DeviceSolver:
         t = self.torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64)).to(self.dev) \
             if not self.torch.is_tensor(y) else y
         self._y_in = t
+        self.torch.cuda.synchronize(self.dev)
         _cabi.check(self.lib.tc_set_state(self._handle, self._p(t)))
         self.stream.synchronize()
 
     def get_state(self):
         out = self.torch.empty(max(self.n_state, 1), dtype=self.torch.float64, device=self.dev)
+        self.torch.cuda.synchronize(self.dev)
         _cabi.check(self.lib.tc_get_state(self._handle, self._p(out)))
         return out[: self.n_state].cpu().numpy()
 
+    def get_state_into(self, out):
+        """Copy the state into a caller-owned device tensor (no host round trip)."""
+        self.torch.cuda.synchronize(self.dev)
+        _cabi.check(self.lib.tc_get_state(self._handle, self._p(out)))
+        return out
+
     def network_state(self):
         """Host copies of the mutable network arrays (T, heat_src, capy, cond, clean_cond)."""
+        self.stream.synchronize()
         d = self.darena.cpu().numpy()
         o, N, nnz = self.off, self.N, self.nnz
         return {"T": d[o["T"]: o["T"] + N].copy(), "heat_src": d[o["heat"]: o["heat"] + N].copy(),
@@ -474,6 +486,7 @@ class DeviceSolver:
         torch = self.torch
         yd = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64)).to(self.dev)
         out = torch.zeros(max(self.n_state, 1), dtype=torch.float64, device=self.dev)
+        torch.cuda.synchronize(self.dev)
         _cabi.check(self.lib.tc_rhs(self._handle, float(t), self._p(yd), self._p(out)))
         return out[: self.n_state].cpu().numpy()
 
@@ -486,6 +499,7 @@ class DeviceSolver:
         self.capacity = cap
         self.hist_io = torch.zeros((cap, max(self.n_io, 1)), dtype=torch.float64, device=self.dev)
         self.hist_net = torch.zeros((cap, w_net), dtype=torch.float64, device=self.dev)
+        torch.cuda.synchronize(self.dev)
         _cabi.check(self.lib.tc_set_history(self._handle, self._p(self.hist_io) if self.n_io else C.c_void_p(0),
                                             self._p(self.hist_net), cap, int(num_skip)))
 
@@ -499,6 +513,7 @@ class DeviceSolver:
 
     def _drain(self, out):
         n = self.info()["stored"]
+        self.stream.synchronize()
         if n:
             net = self.hist_net[:n].cpu().numpy()
             io = self.hist_io[:n, : self.n_io].cpu().numpy() if self.n_io else np.zeros((n, 0))
@@ -578,6 +593,12 @@ class DeviceSolver:
                                             int(pcg_maxit), int(pcg_mode)))
         if sync:
             self.stream.synchronize()
+
+    def timing(self, enable=True):
+        """Toggle CUDA-event timing of PCG launches; returns what accumulated since the last call."""
+        ms, n, launches = _cabi.f64(), _cabi.i64(), _cabi.i64()
+        _cabi.check(self.lib.tc_timing(self._handle, int(bool(enable)), C.byref(ms), C.byref(n), C.byref(launches)))
+        return {"pcg_ms": ms.value, "pcg_launches": int(n.value), "launches": int(launches.value)}
 
     def pcg_stats(self):
         st = (_cabi.i64 * 4)()

@@ -30,16 +30,37 @@ def vertex_index(i, j, k, nx, ny, nz):
     return (j * (nx + 1) + i) * (nz + 1) + k
 
 
-def kuhn_cuboid_mesh(nx, ny, nz, lx, ly, lz):
+def jitter_points(x, y, z, lx, ly, lz, hx, hy, hz, jitter):
+    """Smooth deterministic warp of the interior vertices (same formula as csrc/synth.cu): the
+    normal displacement vanishes on every face, so the cuboid keeps its shape while all 15
+    P1 couplings of the Kuhn split become non-zero (on an orthogonal grid 8 of them cancel
+    exactly and scipy's sparse product drops them)."""
+    pi = 3.14159265358979323846
+    xi, et, ze = x / lx, y / ly, z / lz
+    xo = x + jitter * hx * np.sin(2 * pi * xi) * np.cos(3 * pi * et) * np.cos(2 * pi * ze)
+    yo = y + jitter * hy * np.cos(2 * pi * xi + 0.3) * np.sin(2 * pi * et) * np.cos(pi * ze)
+    zo = z + jitter * hz * np.cos(pi * xi) * np.cos(2 * pi * et + 0.7) * np.sin(2 * pi * ze)
+    return xo, yo, zo
+
+
+def kuhn_cuboid_mesh(nx, ny, nz, lx, ly, lz, jitter=0.0):
     """Returns (points (V,3), tets (6*nx*ny*nz,4), tri_bottom, tri_upper).
 
     ``tri_bottom`` is the z=0 face, ``tri_upper`` the five other faces (the two named
     surfaces of thermca/tests/test_fe_part.py:102-166)."""
-    xs, ys, zs = (np.linspace(0.0, l, n + 1) for l, n in ((lx, nx), (ly, ny), (lz, nz)))
     J, I, K = np.meshgrid(np.arange(ny + 1), np.arange(nx + 1), np.arange(nz + 1), indexing="ij")
     pts = np.empty(((nx + 1) * (ny + 1) * (nz + 1), 3))
     vid = vertex_index(I, J, K, nx, ny, nz).ravel()
-    pts[vid, 0], pts[vid, 1], pts[vid, 2] = xs[I.ravel()], ys[J.ravel()], zs[K.ravel()]
+    Ir, Jr, Kr = I.ravel(), J.ravel(), K.ravel()
+    hx, hy, hz = lx / nx, ly / ny, lz / nz
+    px, py, pz = hx * Ir, hy * Jr, hz * Kr
+    if jitter:
+        px, py, pz = jitter_points(px, py, pz, lx, ly, lz, hx, hy, hz, jitter)
+    # keep the six faces exactly planar
+    px = np.where(Ir == 0, 0.0, np.where(Ir == nx, lx, px))
+    py = np.where(Jr == 0, 0.0, np.where(Jr == ny, ly, py))
+    pz = np.where(Kr == 0, 0.0, np.where(Kr == nz, lz, pz))
+    pts[vid, 0], pts[vid, 1], pts[vid, 2] = px, py, pz
 
     jc, ic, kc = np.meshgrid(np.arange(ny), np.arange(nx), np.arange(nz), indexing="ij")
     ic, jc, kc = ic.ravel(), jc.ravel(), kc.ravel()
@@ -200,9 +221,9 @@ def single_part_network(part, heat_on_surf, film_value, env_temp=20.0):
 
 
 def cuboid_spec(nx, ny, nz, lx=0.5, ly=1.0, lz=0.05, heat=1000.0, film=10.0, env_temp=20.0,
-                init_temp=20.0, dens=8000.0, spec_heat=500.0, condy=50.0):
+                init_temp=20.0, dens=8000.0, spec_heat=500.0, condy=50.0, jitter=0.0):
     """BASELINE config #2 at any size, assembled on the host (use csrc/synth.cu for >2M DOF)."""
-    pts, tets, tb, tu = kuhn_cuboid_mesh(nx, ny, nz, lx, ly, lz)
+    pts, tets, tb, tu = kuhn_cuboid_mesh(nx, ny, nz, lx, ly, lz, jitter)
     Lx, Mx, Qi, Qv, areas = p1_operators(pts, tets, [tb, tu])
     part = ffe_part_spec(Lx, Mx, Qi, Qv, areas, condy, dens * spec_heat, init_temp,
                          films=[film], film_surf_idxs=[1], surf_net_idxs=[1, 2],
