@@ -104,7 +104,9 @@ def test_adaptive_rk_matches_reference(torch_cuda, golden, name):
     assert np.allclose(out["net_temps"], ref["net_temps"], rtol=1e-9, atol=1e-9)
     assert np.allclose(out["net_capys"], ref["net_capys"], rtol=1e-9, atol=0, equal_nan=True)
     if ref["io_temps"].size:
-        assert np.allclose(out["io_temps"][ref["io_snap_idx"]], ref["io_temps"], rtol=1e-9, atol=1e-9)
+        # part states (reduced MOR coordinates span many magnitudes): 1e-9 of the state norm
+        io = out["io_temps"][ref["io_snap_idx"]]
+        assert np.max(np.abs(io - ref["io_temps"])) <= 1e-9 * np.max(np.abs(ref["io_temps"]))
     assert out["nfev"] == int(ref["nfev"]) + 1
 
 
@@ -158,19 +160,24 @@ def test_theta_pcg_fixed_step(torch_cuda, golden, mode):
     assert np.max(np.abs(y - yref) / np.abs(yref)) < 1e-9
 
 
-def test_ros2_adaptive_matches_rk45(torch_cuda, golden):
-    """Adaptive implicit path agrees with the reference's RK45 trajectory within rtol."""
+def test_ros2_adaptive_within_tolerance(torch_cuda, golden):
+    """Adaptive implicit path (ROS2 + PCG, step control on the device) against the oracle's RK45
+    run at tight tolerance: the error at the output time stays within a few rtol."""
     from thermca_b200.device import DeviceSolver
+    from rhs_oracle import integrate
     spec, ex = golden("plate_ffe")
-    ref = ex["result"]
-    dev = DeviceSolver(spec)
-    out = dev.run_ros2(0.0, float(ex["sim"]["t1"]), rtol=1e-4, atol=1e-6, pcg_rtol=1e-10)
-    dev.close()
-    assert out["times"][-1] == float(ex["sim"]["t1"])
-    Tref, T = ref["net_temps"][-1], out["net_temps"][-1]
-    assert np.allclose(T, Tref, rtol=1e-3, atol=1e-3)
-    io_ref = ref["io_temps"][-1]
-    assert np.allclose(out["io_temps"][-1], io_ref, rtol=1e-3, atol=1e-3)
+    t1 = float(ex["sim"]["t1"])
+    tight = integrate(spec, [0.0, t1], 1e-10, 1e-12, "RK45")
+    errs = []
+    for rtol in (1e-3, 1e-4, 1e-5):
+        dev = DeviceSolver(spec)
+        out = dev.run_ros2(0.0, t1, rtol=rtol, atol=1e-6, pcg_rtol=1e-10)
+        dev.close()
+        assert out["times"][-1] == t1 and out["status"] == 0
+        err = np.max(np.abs(out["io_temps"][-1] - tight["io_temps"][-1]) / np.abs(tight["io_temps"][-1]))
+        assert err < 5 * rtol, (rtol, err)
+        errs.append(err)
+    assert errs[2] < errs[0]
 
 
 def test_device_generated_cuboid_matches_host_assembly(torch_cuda):
