@@ -140,6 +140,23 @@ int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, co
                  const int32_t* col, const double* val, const double* mass, const double* adiag,
                  const double* rhs, double* x, double shift, double rtol, int32_t maxit, int32_t* iters);
 
+/* ---- row-partitioned implicit step across GPUs (BASELINE config #5), csrc/dist.cu ------------
+ * One process per GPU; the comm buffer of every rank is exported as a CUDA IPC handle and opened
+ * by its peers; halos and the PCG scalar reductions then move by peer stores inside ONE
+ * cooperative kernel per theta step (no NCCL call on the data path). */
+typedef struct tc_dist tc_dist;
+int tc_dist_create(tc_dist** out, void* cuda_stream, int32_t rank, int32_t world, int64_t n_loc,
+                   int64_t halo, int64_t row_begin);
+int tc_dist_ipc_handle(tc_dist* d, void* handle64);
+int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_n);
+int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
+                         const double* val, const double* mass, const double* adiag, const double* b);
+int tc_dist_set_state(tc_dist* d, const double* y_local_dev);
+int tc_dist_get_state(tc_dist* d, double* y_local_dev);
+int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, double h, double rtol, int32_t maxit);
+int tc_dist_stats(tc_dist* d, int64_t* stats4);
+int tc_dist_destroy(tc_dist* d);
+
 /* ---- batched MOR ensemble (BASELINE config #3): B scenarios in lockstep, FP64 DMMA ------- */
 /* One classical RK4 step of size h for X[S][r][B] with per-scenario films film[F][B](t) =
  * h0*(1 + 0.5 sin(2 pi t / tau)); operators shared by all scenarios. */

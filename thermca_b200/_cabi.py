@@ -68,6 +68,15 @@ EXPORTS = {
     "tc_pcg_stats": (i32, [vp, C.POINTER(i64)]),
     "tc_sell_spmv": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, i32]),
     "tc_pcg_solve": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32, C.POINTER(i32)]),
+    "tc_dist_create": (i32, [C.POINTER(vp), vp, i32, i32, i64, i64, i64]),
+    "tc_dist_ipc_handle": (i32, [vp, vp]),
+    "tc_dist_open_peers": (i32, [vp, vp, C.POINTER(i64)]),
+    "tc_dist_set_operator": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
+    "tc_dist_set_state": (i32, [vp, vp]),
+    "tc_dist_get_state": (i32, [vp, vp]),
+    "tc_dist_theta_steps": (i32, [vp, i32, f64, f64, f64, i32]),
+    "tc_dist_stats": (i32, [vp, C.POINTER(i64)]),
+    "tc_dist_destroy": (i32, [vp]),
     "tc_mor_batch_steps": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  f64, f64, i32, i32]),
     "tc_mor_batch_work_doubles": (i64, [i32, i32, i32, i32]),

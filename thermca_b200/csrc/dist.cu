@@ -1,0 +1,351 @@
+// Row-partitioned implicit step for ONE large FE body across GPUs (BASELINE config #5):
+// fused compute + collective.  Each rank owns a contiguous slab of operator rows and runs
+// ONE cooperative persistent kernel per theta step.  Inside that kernel
+//   * the halo layers of the gathered vector are written straight into the neighbours'
+//     HBM with peer stores over NVLink (no NCCL call, no host round trip),
+//   * the 2-3 scalar reductions of each PCG iteration go through per-rank mailboxes that
+//     every rank writes with peer stores and sums in rank order (bit-identical scalars on
+//     all ranks -> identical convergence decisions, deterministic),
+// so communication overlaps the slab's own SpMV / vector phases block by block.
+// Peer memory is exchanged once at setup as CUDA IPC handles (plumbing via
+// torch.distributed in thermca_b200/dist.py).  The reference has nothing comparable (no
+// multi-process code); per rank the arithmetic is the single-GPU PCG of
+// pcg.cuh on rows [row_begin, row_end).
+#include <cooperative_groups.h>
+#include <string.h>
+#include "../../include/thermca_b200.h"
+#include "parts.cuh"
+namespace cg = cooperative_groups;
+
+#define TC_MAX_WORLD 16
+#define TC_SPIN_LIMIT (6000000000LL)     // ~3 s at 2 GHz: never hang the GPU on a lost peer
+
+struct TcDistK {
+    TcSell A;
+    long long row_begin;
+    int n, H, rank, world;
+    int n_lo, n_hi;                       // local row counts of the neighbours
+    const double *b, *mass, *adiag;
+    double *y_ext, *p_ext;                // [H | n | H]
+    double *x, *r, *q, *dinv;
+    double* partial;                      // 4 banks
+    double* peer_y[2]; double* peer_p[2]; // neighbours' extended vectors (peer memory)
+    int* peer_hflag[2];                   // neighbours' halo flags
+    int* my_hflag;                        // [0] from lower, [1] from upper neighbour
+    double* peer_mb[TC_MAX_WORLD]; int* peer_mbf[TC_MAX_WORLD];
+    double* my_mb; int* my_mbf;           // mb[2][3][MAXW], mbf[2][MAXW]
+    int* state;                           // [0] reduction seq, [1] halo seq, [2] iters last, [3] iters total, [4] error, [5] solves
+    double theta, h, rtol;
+    int maxit;
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until(const int* flag, int seq, int* err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < seq) {
+        if (*((volatile int*)err)) return;
+        if (clock64() - t0 > TC_SPIN_LIMIT) { *((volatile int*)err) = 1; return; }
+    }
+}
+
+__device__ __forceinline__ double bank_sum(const double* bank, int G, double* sh) {
+    __shared__ double bc;
+    const double s = ordered_partial_sum(bank, G, sh);
+    __syncthreads();
+    if (threadIdx.x == 0) bc = s;
+    __syncthreads();
+    return bc;
+}
+
+// my boundary rows -> neighbours' halo regions, then wait for mine
+__device__ void halo_exchange(const TcDistK& S, double* vec, double* const* peer_vec, int hseq,
+                              cg::grid_group& grid) {
+    const int H = S.H, n = S.n;
+    double* lo = peer_vec[0];
+    double* hi = peer_vec[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x) {
+        if (lo) lo[(long long)H + S.n_lo + i] = vec[H + i];
+        if (hi) hi[i] = vec[H + n - H + i];
+    }
+    __threadfence_system();
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (lo) st_release_sys(S.peer_hflag[0] + 1, hseq);
+        if (hi) st_release_sys(S.peer_hflag[1] + 0, hseq);
+    }
+    if (threadIdx.x == 0) {
+        if (lo) spin_until(S.my_hflag + 0, hseq, S.state + 4);
+        if (hi) spin_until(S.my_hflag + 1, hseq, S.state + 4);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// every block holds the same local values; result = sum over ranks in rank order
+__device__ void allreduce3(const TcDistK& S, double* v, int seq) {
+    const int par = seq & 1;
+    if (S.world == 1) return;
+    if (blockIdx.x == 0 && threadIdx.x < S.world) {
+        const int peer = threadIdx.x;
+        volatile double* mb = S.peer_mb[peer];
+        for (int k = 0; k < 3; ++k) mb[(par * 3 + k) * TC_MAX_WORLD + S.rank] = v[k];
+        __threadfence_system();
+        st_release_sys(S.peer_mbf[peer] + par * TC_MAX_WORLD + S.rank, seq);
+    }
+    if (threadIdx.x < S.world) spin_until(S.my_mbf + par * TC_MAX_WORLD + threadIdx.x, seq, S.state + 4);
+    __syncthreads();
+    __threadfence_system();
+    volatile double* mine = S.my_mb;
+    double out[3] = {0.0, 0.0, 0.0};
+    for (int w = 0; w < S.world; ++w)
+        for (int k = 0; k < 3; ++k) out[k] += mine[(par * 3 + k) * TC_MAX_WORLD + w];
+    v[0] = out[0]; v[1] = out[1]; v[2] = out[2];
+    __syncthreads();
+}
+
+#define TC_DIST_THREADS 256
+
+__global__ void __launch_bounds__(TC_DIST_THREADS)
+tc_dist_theta_kernel(TcDistK S) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    const int G = gridDim.x, n = S.n, H = S.H;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    int rseq = S.state[0], hseq = S.state[1];
+    const double shift = S.theta * S.h;
+    // vectors are gathered by GLOBAL column: element of global row g sits at ext[H + g - row_begin]
+    const double* y_g = S.y_ext + H - S.row_begin;
+    const double* p_g = S.p_ext + H - S.row_begin;
+    double* y_loc = S.y_ext + H;
+    double* p_loc = S.p_ext + H;
+
+    // ---- right-hand side f = b - A y (thermca/solver.py:281) on the slab ---------------------
+    halo_exchange(S, S.y_ext, S.peer_y, ++hseq, grid);
+    tc_sell_spmv_body<SPMV_B, false>(S.A, y_g, S.q, S.b, nullptr, 0.0);
+    grid.sync();
+    double rho_l = 0.0, bb_l = 0.0;
+    for (int i = gtid; i < n; i += gsz) {
+        const double m = S.mass[i];
+        const double bsc = m * S.q[i];
+        const double d = 1.0 / (m * (1.0 + shift * S.adiag[i]));
+        const double z = d * bsc;
+        S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; p_loc[i] = z;
+        rho_l += bsc * z; bb_l += bsc * bsc;
+    }
+    {
+        const double r0 = block_sum(rho_l, sh), r1 = block_sum(bb_l, sh);
+        if (threadIdx.x == 0) { S.partial[blockIdx.x] = r0; S.partial[TC_MAX_PARTIALS + blockIdx.x] = r1; }
+    }
+    grid.sync();
+    double red[3];
+    red[0] = bank_sum(S.partial, G, sh);
+    red[1] = bank_sum(S.partial + TC_MAX_PARTIALS, G, sh);
+    red[2] = 0.0;
+    allreduce3(S, red, ++rseq);
+    double rho = red[0];
+    const double tol2 = S.rtol * S.rtol * red[1];
+    int it = 0;
+    if (red[1] > 0.0) {
+        for (; it < S.maxit;) {
+            halo_exchange(S, S.p_ext, S.peer_p, ++hseq, grid);
+            const double dot = tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin);
+            const double bs = block_sum(dot, sh);
+            if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
+            grid.sync();
+            red[0] = bank_sum(S.partial, G, sh); red[1] = 0.0; red[2] = 0.0;
+            allreduce3(S, red, ++rseq);
+            const double alpha = rho / red[0];
+            double rn = 0.0, rr = 0.0;
+            for (int i = gtid; i < n; i += gsz) {
+                S.x[i] += alpha * p_loc[i];
+                const double ri = S.r[i] - alpha * S.q[i];
+                S.r[i] = ri;
+                rn += ri * (S.dinv[i] * ri);
+                rr += ri * ri;
+            }
+            const double r0 = block_sum(rn, sh), r1 = block_sum(rr, sh);
+            if (threadIdx.x == 0) {
+                S.partial[2 * TC_MAX_PARTIALS + blockIdx.x] = r0;
+                S.partial[3 * TC_MAX_PARTIALS + blockIdx.x] = r1;
+            }
+            grid.sync();
+            red[0] = bank_sum(S.partial + 2 * TC_MAX_PARTIALS, G, sh);
+            red[1] = bank_sum(S.partial + 3 * TC_MAX_PARTIALS, G, sh);
+            red[2] = 0.0;
+            allreduce3(S, red, ++rseq);
+            ++it;
+            if (!(red[1] > tol2) || *((volatile int*)(S.state + 4))) break;
+            const double beta = red[0] / rho;
+            for (int i = gtid; i < n; i += gsz) p_loc[i] = S.dinv[i] * S.r[i] + beta * p_loc[i];
+            rho = red[0];
+            grid.sync();
+        }
+    }
+    // ---- y += h * z --------------------------------------------------------------------------
+    for (int i = gtid; i < n; i += gsz) y_loc[i] += S.h * S.x[i];
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.state[0] = rseq; S.state[1] = hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------
+struct tc_dist {
+    cudaStream_t stream;
+    int rank, world;
+    long long n, H, row_begin;
+    char* comm = nullptr;             // my exported buffer
+    size_t comm_bytes = 0;
+    size_t off_y, off_p, off_mb, off_mbf, off_hflag;
+    char* peer[TC_MAX_WORLD];
+    long long peer_n[TC_MAX_WORLD];
+    double *x = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr, *partial = nullptr;
+    int* state = nullptr;
+    TcDistK K;
+    int grid = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t world, int64_t n_loc,
+                              int64_t halo, int64_t row_begin) {
+    TC_CHECK(world >= 1 && world <= TC_MAX_WORLD, "world size");
+    TC_CHECK(halo <= n_loc, "halo wider than the slab");
+    tc_dist* d = new tc_dist();
+    memset(d->peer, 0, sizeof d->peer);
+    d->stream = (cudaStream_t)stream; d->rank = rank; d->world = world;
+    d->n = n_loc; d->H = halo; d->row_begin = row_begin;
+    const size_t ext = (size_t)(n_loc + 2 * halo) * sizeof(double);
+    d->off_y = 0;
+    d->off_p = align_up(ext, 256);
+    d->off_mb = d->off_p + align_up(ext, 256);
+    d->off_mbf = d->off_mb + align_up(sizeof(double) * 2 * 3 * TC_MAX_WORLD, 256);
+    d->off_hflag = d->off_mbf + align_up(sizeof(int) * 2 * TC_MAX_WORLD, 256);
+    d->comm_bytes = d->off_hflag + 256;
+    TC_CUDA(cudaMalloc(&d->comm, d->comm_bytes));
+    TC_CUDA(cudaMemset(d->comm, 0, d->comm_bytes));
+    const size_t nb = sizeof(double) * (size_t)n_loc;
+    TC_CUDA(cudaMalloc(&d->x, nb)); TC_CUDA(cudaMalloc(&d->r, nb));
+    TC_CUDA(cudaMalloc(&d->q, nb)); TC_CUDA(cudaMalloc(&d->dinv, nb));
+    TC_CUDA(cudaMalloc(&d->partial, sizeof(double) * 4 * TC_MAX_PARTIALS));
+    TC_CUDA(cudaMalloc(&d->state, sizeof(int) * 16));
+    TC_CUDA(cudaMemset(d->state, 0, sizeof(int) * 16));
+    d->peer[rank] = d->comm;
+    TC_CUDA(cudaDeviceSynchronize());
+    *out = d;
+    return 0;
+}
+
+extern "C" int tc_dist_ipc_handle(tc_dist* d, void* handle64) {
+    cudaIpcMemHandle_t h;
+    TC_CUDA(cudaIpcGetMemHandle(&h, d->comm));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+// handles: world * 64 bytes; peer_n: local row counts of all ranks
+extern "C" int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_n) {
+    for (int w = 0; w < d->world; ++w) {
+        d->peer_n[w] = peer_n[w];
+        if (w == d->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * w, 64);
+        void* p = nullptr;
+        TC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        d->peer[w] = (char*)p;
+    }
+    return 0;
+}
+
+extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
+                                    const double* val, const double* mass, const double* adiag,
+                                    const double* b) {
+    TcDistK& K = d->K;
+    K.A = TcSell{(int)d->n, nslices, (const long long*)slice_ptr, col, val};
+    K.row_begin = d->row_begin; K.n = (int)d->n; K.H = (int)d->H; K.rank = d->rank; K.world = d->world;
+    K.b = b; K.mass = mass; K.adiag = adiag;
+    K.y_ext = (double*)(d->comm + d->off_y); K.p_ext = (double*)(d->comm + d->off_p);
+    K.x = d->x; K.r = d->r; K.q = d->q; K.dinv = d->dinv; K.partial = d->partial;
+    const int lo = d->rank - 1, hi = d->rank + 1;
+    // peers share my buffer layout except for their own n: offsets depend on n_peer
+    auto ext_bytes = [&](int w) { return align_up((size_t)(d->peer_n[w] + 2 * d->H) * sizeof(double), 256); };
+    auto off_p = [&](int w) { return ext_bytes(w); };
+    auto off_mb = [&](int w) { return 2 * ext_bytes(w); };
+    auto off_mbf = [&](int w) { return off_mb(w) + align_up(sizeof(double) * 2 * 3 * TC_MAX_WORLD, 256); };
+    auto off_hf = [&](int w) { return off_mbf(w) + align_up(sizeof(int) * 2 * TC_MAX_WORLD, 256); };
+    for (int s = 0; s < 2; ++s) { K.peer_y[s] = nullptr; K.peer_p[s] = nullptr; K.peer_hflag[s] = nullptr; }
+    K.n_lo = K.n_hi = 0;
+    if (lo >= 0) {
+        K.peer_y[0] = (double*)(d->peer[lo]); K.peer_p[0] = (double*)(d->peer[lo] + off_p(lo));
+        K.peer_hflag[0] = (int*)(d->peer[lo] + off_hf(lo)); K.n_lo = (int)d->peer_n[lo];
+    }
+    if (hi < d->world) {
+        K.peer_y[1] = (double*)(d->peer[hi]); K.peer_p[1] = (double*)(d->peer[hi] + off_p(hi));
+        K.peer_hflag[1] = (int*)(d->peer[hi] + off_hf(hi)); K.n_hi = (int)d->peer_n[hi];
+    }
+    for (int w = 0; w < TC_MAX_WORLD; ++w) { K.peer_mb[w] = nullptr; K.peer_mbf[w] = nullptr; }
+    for (int w = 0; w < d->world; ++w) {
+        K.peer_mb[w] = (double*)(d->peer[w] + off_mb(w));
+        K.peer_mbf[w] = (int*)(d->peer[w] + off_mbf(w));
+    }
+    K.my_mb = (double*)(d->comm + d->off_mb); K.my_mbf = (int*)(d->comm + d->off_mbf);
+    K.my_hflag = (int*)(d->comm + d->off_hflag);
+    K.state = d->state;
+    int dev = 0, sms = 148, occ = 0;
+    TC_CUDA(cudaGetDevice(&dev));
+    TC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_dist_theta_kernel, TC_DIST_THREADS, 0));
+    if (occ > 8) occ = 8;
+    d->grid = occ * sms;
+    if (d->grid > TC_MAX_PARTIALS) d->grid = TC_MAX_PARTIALS;
+    const int need = (nslices + 7) / 8;
+    if (need < d->grid) d->grid = need > 0 ? need : 1;
+    return 0;
+}
+
+extern "C" int tc_dist_set_state(tc_dist* d, const double* y_local_dev) {
+    TC_CUDA(cudaMemcpyAsync(d->K.y_ext + d->H, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+    TC_CUDA(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+extern "C" int tc_dist_get_state(tc_dist* d, double* y_local_dev) {
+    TC_CUDA(cudaMemcpyAsync(y_local_dev, d->K.y_ext + d->H, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+    TC_CUDA(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+extern "C" int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, double h, double rtol, int32_t maxit) {
+    d->K.theta = theta; d->K.h = h; d->K.rtol = rtol; d->K.maxit = maxit;
+    for (int k = 0; k < nsteps; ++k) {
+        void* args[] = {(void*)&d->K};
+        TC_CUDA(cudaLaunchCooperativeKernel((void*)tc_dist_theta_kernel, dim3(d->grid), dim3(TC_DIST_THREADS), args, 0, d->stream));
+    }
+    return 0;
+}
+
+// stats: iters_last, iters_total, error flag, solves
+extern "C" int tc_dist_stats(tc_dist* d, int64_t* stats4) {
+    int st[16];
+    TC_CUDA(cudaStreamSynchronize(d->stream));
+    TC_CUDA(cudaMemcpy(st, d->state, sizeof st, cudaMemcpyDeviceToHost));
+    stats4[0] = st[2]; stats4[1] = st[3]; stats4[2] = st[4]; stats4[3] = st[5];
+    return 0;
+}
+
+extern "C" int tc_dist_destroy(tc_dist* d) {
+    if (!d) return 0;
+    for (int w = 0; w < d->world; ++w)
+        if (w != d->rank && d->peer[w]) cudaIpcCloseMemHandle(d->peer[w]);
+    cudaFree(d->comm); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
+    cudaFree(d->partial); cudaFree(d->state);
+    delete d;
+    return 0;
+}

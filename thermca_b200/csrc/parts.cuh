@@ -39,10 +39,13 @@ __device__ __forceinline__ double tc_ld_x(const double* p) {
     return v;
 }
 
+// xrow_off: index of local row 0 in the gathered vector (row partition: x is addressed by
+// GLOBAL column, outputs by LOCAL row); 0 on a single GPU.
 template <int MODE, bool NC_X = true>
 __device__ __forceinline__ double tc_sell_spmv_body(const TcSell& A, const double* x,
                                                     double* y, const double* __restrict__ b,
-                                                    const double* __restrict__ mass, double shift) {
+                                                    const double* __restrict__ mass, double shift,
+                                                    long long xrow_off = 0) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -78,7 +81,7 @@ __device__ __forceinline__ double tc_sell_spmv_body(const TcSell& A, const doubl
             } else if (MODE == SPMV_B) {
                 y[row] = __dsub_rn(b[row], sum);
             } else {
-                const double xr = tc_ld_x<NC_X>(x + row);
+                const double xr = tc_ld_x<NC_X>(x + xrow_off + row);
                 const double q = mass[row] * (xr + shift * sum);
                 y[row] = q;
                 dot += xr * q;
@@ -115,7 +118,7 @@ struct TcSurfLoad {
     const int* surf;
     const double* bval;
 };
-__global__ void tc_ffe_surf_load_kernel(TcSurfLoad L, const double* __restrict__ flux,
+static __global__ void tc_ffe_surf_load_kernel(TcSurfLoad L, const double* __restrict__ flux,
                                         double* __restrict__ ydot, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nrows; i += gridDim.x * blockDim.x) {
@@ -140,7 +143,7 @@ struct TcFilmDiag {
     const int* film;       // film index
     const double* adata;   // a_f,i
 };
-__global__ void tc_ffe_film_diag_kernel(TcFilmDiag F, const double* __restrict__ films,
+static __global__ void tc_ffe_film_diag_kernel(TcFilmDiag F, const double* __restrict__ films,
                                         double* __restrict__ val, double* __restrict__ adiag,
                                         const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;
@@ -166,7 +169,7 @@ struct TcMeanJobs {
     const double* w;
 };
 #define TC_MEAN_THREADS 256
-__global__ void __launch_bounds__(TC_MEAN_THREADS)
+static __global__ void __launch_bounds__(TC_MEAN_THREADS)
 tc_surf_mean_kernel(TcMeanJobs J, const double* __restrict__ y, double* __restrict__ partials,
                     const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;
@@ -191,7 +194,7 @@ struct TcMor {
     const double* A_films;  // F*S*r*r
     const double* B_T;      // S*r
 };
-__global__ void tc_mor_rhs_kernel(TcMor M, const double* __restrict__ films,
+static __global__ void tc_mor_rhs_kernel(TcMor M, const double* __restrict__ films,
                                   const double* __restrict__ flux, const double* __restrict__ x,
                                   double* __restrict__ xdot, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;

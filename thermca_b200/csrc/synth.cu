@@ -90,9 +90,15 @@ __global__ void tc_synth_cuboid_kernel(SynthGeo g, const int* __restrict__ order
                                        double* __restrict__ mass, double* __restrict__ adiag,
                                        double* __restrict__ q_bottom, double* __restrict__ q_upper) {
     const long long nloc = g.row_end - g.row_begin;
-    for (long long rl = blockIdx.x * (long long)blockDim.x + threadIdx.x; rl < nloc;
+    const long long npad = ((nloc + 31) / 32) * 32;
+    for (long long rl = blockIdx.x * (long long)blockDim.x + threadIdx.x; rl < npad;
          rl += (long long)gridDim.x * blockDim.x) {
         const long long row = g.row_begin + rl;
+        if (rl >= nloc) {        // padding rows of the last slice: zeros pointing at an owned row
+            const long long pb = (rl >> 5) * (32LL * 15) + (rl & 31);
+            for (int s = 0; s < 15; ++s) { col[pb + 32LL * s] = (int)g.row_begin; val[pb + 32LL * s] = 0.0; }
+            continue;
+        }
         const int k = (int)(row % (g.nz + 1));
         const long long t = row / (g.nz + 1);
         const int i = (int)(t % (g.nx + 1));
@@ -198,7 +204,6 @@ extern "C" int tc_synth_cuboid(void* cuda_stream, int32_t nx, int32_t ny, int32_
                                int64_t row_end, int64_t* slice_ptr, int32_t* col, double* val, double* mass,
                                double* adiag, double* q_bottom, double* q_upper) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    TC_CHECK((row_begin % 32) == 0, "row_begin must be a multiple of the slice height");
     // the 15 admissible neighbour offsets, ordered by linear index offset (ascending column)
     struct Off { long long lin; int dx, dy, dz; };
     Off offs[15];
@@ -230,11 +235,8 @@ extern "C" int tc_synth_cuboid(void* cuda_stream, int32_t nx, int32_t ny, int32_
     SynthGeo g{nx, ny, nz, lx, ly, lz, jitter, condy, vol_capy, row_begin, row_end};
     const long long nloc = row_end - row_begin;
     const long long nsl = (nloc + 31) / 32;
-    // rows past row_end inside the last slice: pad with zeros pointing at row_begin
-    TC_CUDA(cudaMemsetAsync(val, 0, sizeof(double) * nsl * 32 * 15, st));
-    TC_CUDA(cudaMemsetAsync(col, 0, sizeof(int) * nsl * 32 * 15, st));
     tc_fill_slice_ptr_kernel<<<256, 256, 0, st>>>(nsl, (long long*)slice_ptr);
-    long long gb = (nloc + 127) / 128;
+    long long gb = (nsl * 32 + 127) / 128;
     if (gb > 148 * 16) gb = 148 * 16;
     if (gb < 1) gb = 1;
     tc_synth_cuboid_kernel<<<(int)gb, 128, 0, st>>>(g, d_order, d_off, col, val, mass, adiag, q_bottom, q_upper);
