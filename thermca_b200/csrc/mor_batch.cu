@@ -14,8 +14,8 @@
 #include "../../include/thermca_b200.h"
 
 #define MB_TM 64      // rows per CTA tile
-#define MB_TN 64      // scenarios per CTA tile
-#define MB_TK 16      // k chunk
+// scenarios per CTA tile: 16*NC (NC = 8-column DMMA tiles per warp; 4 for <=4 operators, 2 above)
+// k chunk: 16 (8 when more than 4 operators share the 48 KB of static shared memory)
 #define MB_THREADS 256
 
 struct MorBatch {
@@ -41,12 +41,14 @@ __device__ __forceinline__ double film_at(const MorBatch& M, int f, int b, doubl
 }
 
 // One RK stage:  k = f(t, Xin);  Xout = Xbase + c_out*h*k (if Xout);  Xacc = (first ? Xbase : Xacc) + c_acc*h*k
-template <int NOPS, bool DMMA>
+template <int NOPS, int NC, bool DMMA>
 __global__ void __launch_bounds__(MB_THREADS)
 tc_mor_stage_kernel(MorBatch M, const double* __restrict__ Xin, const double* __restrict__ Xbase,
                     double* __restrict__ Xout, double* __restrict__ Xacc, double t, double h,
                     double c_out, double c_acc, int first) {
+    constexpr int MB_TK = NOPS > 4 ? 8 : 16;
     __shared__ double sA[NOPS][MB_TM][MB_TK + 1];
+    constexpr int MB_TN = 16 * NC;
     __shared__ double sX[MB_TK][MB_TN + 8];
     const int s = blockIdx.z;
     const int i0 = blockIdx.y * MB_TM;
@@ -54,15 +56,15 @@ tc_mor_stage_kernel(MorBatch M, const double* __restrict__ Xin, const double* __
     const int r = M.r, B = M.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 16;     // warp tile origin (rows)   : 4 x 16
-    const int wn = (warp >> 2) * 32;    // warp tile origin (cols)   : 2 x 32
+    const int wn = (warp >> 2) * 8 * NC; // warp tile origin (cols)   : 2 x 8*NC
     const double* Xs = Xin + (size_t)s * r * B;
-    double acc[NOPS][2][4][2];
+    double acc[NOPS][2][NC][2];
 #pragma unroll
     for (int o = 0; o < NOPS; ++o)
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[o][a][c][0] = acc[o][a][c][1] = 0.0;
+            for (int c = 0; c < NC; ++c) acc[o][a][c][0] = acc[o][a][c][1] = 0.0;
 
     for (int k0 = 0; k0 < r; k0 += MB_TK) {
         // operator chunks: NOPS x (64 x 16), row-major in global (k contiguous)
@@ -89,16 +91,16 @@ tc_mor_stage_kernel(MorBatch M, const double* __restrict__ Xin, const double* __
         if (DMMA) {
 #pragma unroll
             for (int k4 = 0; k4 < MB_TK; k4 += 4) {
-                double bf[4];
+                double bf[NC];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) bf[c] = sX[k4 + (lane & 3)][wn + 8 * c + (lane >> 2)];
+                for (int c = 0; c < NC; ++c) bf[c] = sX[k4 + (lane & 3)][wn + 8 * c + (lane >> 2)];
 #pragma unroll
                 for (int o = 0; o < NOPS; ++o)
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
                         const double af = sA[o][wm + 8 * a + (lane >> 2)][k4 + (lane & 3)];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) dmma884(acc[o][a][c][0], acc[o][a][c][1], af, bf[c]);
+                        for (int c = 0; c < NC; ++c) dmma884(acc[o][a][c][0], acc[o][a][c][1], af, bf[c]);
                     }
             }
         } else {
@@ -111,7 +113,7 @@ tc_mor_stage_kernel(MorBatch M, const double* __restrict__ Xin, const double* __
                     for (int a = 0; a < 2; ++a) {
                         const double af = sA[o][wm + 8 * a + (lane >> 2)][kk];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < NC; ++c) {
                             acc[o][a][c][0] += af * sX[kk][wn + 8 * c + 2 * (lane & 3)];
                             acc[o][a][c][1] += af * sX[kk][wn + 8 * c + 2 * (lane & 3) + 1];
                         }
@@ -123,7 +125,7 @@ tc_mor_stage_kernel(MorBatch M, const double* __restrict__ Xin, const double* __
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int gi = i0 + wm + 8 * a + (lane >> 2);
@@ -150,14 +152,15 @@ extern "C" int64_t tc_mor_batch_work_doubles(int32_t S, int32_t r, int32_t F, in
     return 3LL * S * r * B;
 }
 
-template <int NOPS>
-static void launch_stage(bool dmma, dim3 grid, cudaStream_t st, const MorBatch& M, const double* Xin,
+template <int NOPS, int NC>
+static void launch_stage(bool dmma, int S, int r, int B, cudaStream_t st, const MorBatch& M, const double* Xin,
                          const double* Xbase, double* Xout, double* Xacc, double t, double h, double c_out,
                          double c_acc, int first) {
+    dim3 grid((B + 16 * NC - 1) / (16 * NC), (r + MB_TM - 1) / MB_TM, S);
     if (dmma)
-        tc_mor_stage_kernel<NOPS, true><<<grid, MB_THREADS, 0, st>>>(M, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
+        tc_mor_stage_kernel<NOPS, NC, true><<<grid, MB_THREADS, 0, st>>>(M, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
     else
-        tc_mor_stage_kernel<NOPS, false><<<grid, MB_THREADS, 0, st>>>(M, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
+        tc_mor_stage_kernel<NOPS, NC, false><<<grid, MB_THREADS, 0, st>>>(M, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
 }
 
 extern "C" int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32_t F, int32_t B,
@@ -165,20 +168,21 @@ extern "C" int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32
                                   const int32_t* film_surf, const double* film_h0, const double* film_tau,
                                   const double* t_link, const double* q_surf, double* X, double* work,
                                   double t0, double h, int32_t nsteps, int32_t use_dmma) {
-    TC_CHECK(F >= 0 && F <= 3, "batched MOR supports up to 3 film links per body");
+    TC_CHECK(F >= 0 && F <= 5, "batched MOR supports up to 5 film links per body");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     MorBatch M{S, r, F, B, A_body, A_films, B_T, film_surf, film_h0, film_tau, t_link, q_surf};
     const size_t n = (size_t)S * r * B;
     double* o1 = work; double* o2 = work + n; double* acc = work + 2 * n;
-    dim3 grid((B + MB_TN - 1) / MB_TN, (r + MB_TM - 1) / MB_TM, S);
     const bool dm = use_dmma != 0;
     auto stage = [&](const double* Xin, const double* Xb, double* Xout, double* Xacc, double t, double c_out,
                      double c_acc, int first) {
         switch (F) {
-            case 0: launch_stage<1>(dm, grid, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
-            case 1: launch_stage<2>(dm, grid, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
-            case 2: launch_stage<3>(dm, grid, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
-            default: launch_stage<4>(dm, grid, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            case 0: launch_stage<1, 4>(dm, S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            case 1: launch_stage<2, 4>(dm, S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            case 2: launch_stage<3, 4>(dm, S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            case 3: launch_stage<4, 4>(dm, S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            case 4: launch_stage<5, 2>(dm, S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            default: launch_stage<6, 2>(dm, S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
         }
     };
     double* cur = X;

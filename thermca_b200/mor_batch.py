@@ -1,0 +1,65 @@
+"""Batched MOR ensemble (BASELINE config #3): B load cases of one MOR body in lockstep.
+
+Host wrapper of ``tc_mor_batch_steps`` (csrc/mor_batch.cu).  Per scenario b the kernel
+computes exactly what the reference computes for one MOR part per right-hand side
+(thermca/solver.py:282-299 with A = A_body + sum_f film_f A_films[f], mor_io.py:90-92),
+with the film coefficients of scenario b following
+``film_f,b(t) = h0_f,b * (1 + 0.5 sin(2 pi t / tau_f,b))`` (SURVEY.md §8d cfg#3).
+Scenario slices shard over GPUs without communication.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+
+
+class MorEnsemble:
+    def __init__(self, A_body, A_films, B_T, film_surf, film_h0, film_tau, t_link, q_surf, x0, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("thermca_b200 needs a CUDA device; there is no CPU fallback")
+        self.torch = torch
+        self.lib = _cabi.load_library()
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        A_body = np.ascontiguousarray(A_body, dtype=np.float64)
+        self.S, self.r = A_body.shape[0], A_body.shape[1]
+        A_films = np.ascontiguousarray(A_films, dtype=np.float64).reshape(-1, self.S, self.r, self.r)
+        self.F = A_films.shape[0]
+        film_h0 = np.ascontiguousarray(film_h0, dtype=np.float64).reshape(self.F, -1)
+        self.B = film_h0.shape[1] if self.F else int(np.asarray(x0).shape[-1])
+        up = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.dev)
+        self.t = {
+            "A_body": up(A_body), "A_films": up(A_films if self.F else np.zeros(1)), "B_T": up(B_T),
+            "film_surf": up(film_surf if self.F else [0], np.int32), "film_h0": up(film_h0 if self.F else np.zeros(1)),
+            "film_tau": up(np.reshape(film_tau, (self.F, -1)) if self.F else np.ones(1)),
+            "t_link": up(t_link if self.F else np.zeros(1)), "q_surf": up(q_surf),
+        }
+        x0 = np.asarray(x0, dtype=np.float64)
+        if x0.ndim == 2:                      # (S, r) -> broadcast over scenarios
+            x0 = np.repeat(x0[:, :, None], self.B, axis=2)
+        self.X = up(x0.reshape(self.S, self.r, self.B))
+        nwork = int(self.lib.tc_mor_batch_work_doubles(self.S, self.r, self.F, self.B))
+        self.work = torch.empty(nwork, dtype=torch.float64, device=self.dev)
+        self.time = 0.0
+        torch.cuda.synchronize(self.dev)
+
+    def steps(self, nsteps, h, use_dmma=True, stream=None):
+        torch = self.torch
+        st = torch.cuda.current_stream(self.dev) if stream is None else stream
+        p = lambda a: C.c_void_p(a.data_ptr())
+        t = self.t
+        _cabi.check(self.lib.tc_mor_batch_steps(
+            C.c_void_p(st.cuda_stream), self.S, self.r, self.F, self.B, p(t["A_body"]), p(t["A_films"]), p(t["B_T"]),
+            p(t["film_surf"]), p(t["film_h0"]), p(t["film_tau"]), p(t["t_link"]), p(t["q_surf"]), p(self.X),
+            p(self.work), float(self.time), float(h), int(nsteps), int(bool(use_dmma))))
+        self.time += nsteps * h
+
+    def state(self):
+        self.torch.cuda.synchronize(self.dev)
+        return self.X.cpu().numpy()
+
+    def flops_per_step(self):
+        return 4 * 2.0 * (1 + self.F) * self.r * self.r * self.S * self.B
