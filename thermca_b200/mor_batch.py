@@ -28,8 +28,8 @@ class MorEnsemble:
         self.S, self.r = A_body.shape[0], A_body.shape[1]
         A_films = np.ascontiguousarray(A_films, dtype=np.float64).reshape(-1, self.S, self.r, self.r)
         self.F = A_films.shape[0]
-        film_h0 = np.ascontiguousarray(film_h0, dtype=np.float64).reshape(self.F, -1)
-        self.B = film_h0.shape[1] if self.F else int(np.asarray(x0).shape[-1])
+        self.B = int(np.asarray(film_h0).reshape(self.F, -1).shape[1]) if self.F else int(np.asarray(x0).shape[-1])
+        film_h0 = np.ascontiguousarray(film_h0, dtype=np.float64).reshape(self.F, self.B)
         up = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.dev)
         self.t = {
             "A_body": up(A_body), "A_films": up(A_films if self.F else np.zeros(1)), "B_T": up(B_T),
