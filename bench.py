@@ -249,6 +249,80 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+# ---- secondary metric: batched MOR ensemble (BASELINE config #3) ---------------------------------
+def run_mor(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from thermca_b200.mor_batch import MorEnsemble
+    S, r, F, B = 3, 200, 2, 4096                      # per GPU; scenario slices shard without communication
+    rng = np.random.default_rng(0)                    # SURVEY.md cfg#3: h0 ~ U[5,50], tau ~ U[60,600] s
+
+    def spd(scale):
+        Q = rng.standard_normal((r, r)) / np.sqrt(r)
+        return (Q @ Q.T + 0.1 * np.eye(r)) * scale
+    A_body = np.array([spd(1e-2) for _ in range(S)])
+    A_films = np.array([[spd(1e-5) for _ in range(S)] for _ in range(F)])
+    B_T = rng.standard_normal((S, r)) * 1e-3
+    rng_b = np.random.default_rng(1000 + rank)
+    h0, tau = rng_b.uniform(5, 50, (F, B)), rng_b.uniform(60, 600, (F, B))
+    ens = MorEnsemble(A_body, A_films, B_T, np.array([0, 1], dtype=np.int32), h0, tau, np.array([-5.0, 3.0]),
+                      np.array([100.0, 0.0, 0.0]), np.zeros((S, r)))
+    h = 0.5
+    # FP64 tensor-core ceiling measured here with a plain library DGEMM (not in MEASURED_PEAKS.json)
+    a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        torch.matmul(a, a)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); g0.record()
+    for _ in range(5):
+        torch.matmul(a, a)
+    g1.record(); torch.cuda.synchronize()
+    dgemm_tflops = 5 * 2 * 4096 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12
+    del a
+    res = {}
+    for dmma in (True, False):
+        ens.steps(args.warmup * 4, h, use_dmma=dmma)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0.record()
+            ens.steps(args.steps * 4, h, use_dmma=dmma)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        res[dmma] = (float(ms.item()), clocks.summary())
+    nsteps = args.steps * 4
+    ms, clk = res[True]
+    tflops = ens.flops_per_step() * nsteps / (ms * 1e-3) / 1e12
+    line = {
+        "metric": "scenarios*steps/s (batched MOR ensemble, RK4 step)", "value": B * world * nsteps / (ms * 1e-3),
+        "unit": "scenarios*steps/s", "n_gpus": world, "steps": nsteps, "warmup": args.warmup * 4,
+        "ms_per_step": ms / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"cfg#3 MOR ensemble S={S} r={r} F={F} B={B}/GPU, time-varying films, RK4 h={h}s",
+                   "l2": "operators (8.6 MB) are L2-resident by design; state 3x19.7 MB/GPU streams"},
+        "clocks": clk, "gpu_launches": nsteps * 4,
+        "roofline": {"bound": "tensor", "achieved": tflops, "peak": dgemm_tflops, "unit": "TFLOP/s",
+                     "frac": tflops / dgemm_tflops, "traffic": None, "kernel": "tc_mor_stage_kernel<3,4,true>",
+                     "peak_kind": "torch.matmul fp64 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
+                     "fma_variant_ms_per_step": res[False][0] / nsteps},
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,10 +333,13 @@ def main():
     ap.add_argument("--cpu-dof", type=float, default=0.5e6, help="DOF of the bounded CPU sample")
     ap.add_argument("--pcg-mode", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="fe", choices=["fe", "mor"])
     args = ap.parse_args()
     args.dof, args.cpu_dof = int(args.dof), int(args.cpu_dof)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "mor":
+        run_mor(args)
     else:
         run_ours(args)
 

@@ -278,6 +278,8 @@ def integrate(spec, time_span, rel_tol=1e-3, abs_tol=1e-6, method="RK45", num_sk
     u = rhs.u
     rhs(t0, y0)
     times, net_temps, io_temps = [t0], [rhs.net_temp.copy()], [y0[u:].copy()]
+    extra = {"net_capys": [rhs.capy.copy()], "net_heat_srcs": [rhs.heat_src.copy()],
+             "cond_data": [rhs.cond_data.copy()], "clean_data": [rhs.clean_data.copy()]}
     nfev = 1
     nsteps = 0
     if tf > t0:
@@ -296,9 +298,13 @@ def integrate(spec, time_span, rel_tol=1e-3, abs_tol=1e-6, method="RK45", num_sk
                 times.append(solver.t)
                 net_temps.append(rhs.net_temp.copy())
                 io_temps.append(solver.y[u:].copy())
+                extra["net_capys"].append(rhs.capy.copy()); extra["net_heat_srcs"].append(rhs.heat_src.copy())
+                extra["cond_data"].append(rhs.cond_data.copy()); extra["clean_data"].append(rhs.clean_data.copy())
                 next_coll += num_skip + 1
             result_step += 1
             nsteps += 1
         nfev += solver.nfev
-    return {"times": np.array(times), "net_temps": np.array(net_temps),
-            "io_temps": np.array(io_temps), "nfev": nfev, "nsteps": nsteps}
+    out = {"times": np.array(times), "net_temps": np.array(net_temps),
+           "io_temps": np.array(io_temps), "nfev": nfev, "nsteps": nsteps}
+    out.update({k: np.array(v) for k, v in extra.items()})
+    return out

@@ -1,0 +1,107 @@
+"""Host-side logic of the row partition on CPU: world_size 2 over gloo (no GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from thermca_b200.dist import slab_partition, local_spmv_with_halo
+from thermca_b200.synth import cuboid_spec
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, nx, ny, nz, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    spec = cuboid_spec(nx, ny, nz, jitter=0.15)
+    p = spec["ffe"][0]
+    n = int(p["dof"])
+    A = sp.csr_matrix((p["A_data"], p["A_body"]["indices"], p["A_body"]["indptr"]), shape=(n, n))
+    mass = 1.0 / p["M_inv"]
+    bounds, halo = slab_partition(nx, ny, nz, world)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    A_loc = A[r0:r1]
+    # every column this slab touches lies inside [r0 - halo, r1 + halo)
+    cols = A_loc.indices
+    assert cols.min() >= max(r0 - halo, 0) and cols.max() < min(r1 + halo, n)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(n)
+    x_loc = x[r0:r1].copy()
+
+    def exchange(v_loc):
+        lo = hi = None
+        reqs = []
+        if rank > 0:
+            lo = torch.empty(halo, dtype=torch.float64)
+            reqs += [dist.isend(torch.from_numpy(v_loc[:halo].copy()), rank - 1), dist.irecv(lo, rank - 1)]
+        if rank < world - 1:
+            hi = torch.empty(halo, dtype=torch.float64)
+            reqs += [dist.isend(torch.from_numpy(v_loc[-halo:].copy()), rank + 1), dist.irecv(hi, rank + 1)]
+        for r in reqs:
+            r.wait()
+        return (None if lo is None else lo.numpy()), (None if hi is None else hi.numpy())
+
+    lo, hi = exchange(x_loc)
+    y_loc = local_spmv_with_halo(A_loc, x_loc, r0, halo, lo, hi, n)
+    assert np.array_equal(y_loc, (A @ x)[r0:r1])
+
+    # distributed Jacobi-PCG on (M + s K) with one allreduce per dot product == serial CG
+    shift = 0.5
+    b = mass[r0:r1] * rng.standard_normal(n)[r0:r1]
+    dinv = 1.0 / (mass[r0:r1] * (1.0 + shift * A.diagonal()[r0:r1]))
+    xs = np.zeros(r1 - r0); r = b.copy(); z = dinv * r; pvec = z.copy()
+
+    def gsum(v):
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t)
+        return float(t.item())
+    rho = gsum(r @ z)
+    for _ in range(25):
+        lo, hi = exchange(pvec)
+        q = mass[r0:r1] * (pvec + shift * local_spmv_with_halo(A_loc, pvec, r0, halo, lo, hi, n))
+        alpha = rho / gsum(pvec @ q)
+        xs += alpha * pvec; r -= alpha * q
+        z = dinv * r
+        rho_new = gsum(r @ z)
+        pvec = z + (rho_new / rho) * pvec
+        rho = rho_new
+    res = gsum(r @ r) ** 0.5
+    np.save(os.path.join(out_dir, f"x{rank}.npy"), xs)
+    np.save(os.path.join(out_dir, f"b{rank}.npy"), b)
+    assert res < 1e-8 * gsum(b @ b) ** 0.5
+    dist.destroy_process_group()
+
+
+def test_slab_partition_layers():
+    bounds, halo = slab_partition(4, 9, 3, 2)
+    layer = 5 * 4
+    assert list(bounds) == [0, 5 * layer, 10 * layer] and halo == layer + 4 + 1
+    bounds, _ = slab_partition(4, 10, 3, 4)
+    assert list(np.diff(bounds) // layer) == [3, 3, 3, 2]
+    with pytest.raises(ValueError):
+        slab_partition(4, 2, 3, 4)
+
+
+def test_partitioned_spmv_and_pcg_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, 5, 9, 3, str(tmp_path)), nprocs=2, join=True)
+    # assembled solution solves the global system
+    spec = cuboid_spec(5, 9, 3, jitter=0.15)
+    p = spec["ffe"][0]
+    n = int(p["dof"])
+    A = sp.csr_matrix((p["A_data"], p["A_body"]["indices"], p["A_body"]["indptr"]), shape=(n, n))
+    mass = 1.0 / p["M_inv"]
+    x = np.concatenate([np.load(tmp_path / "x0.npy"), np.load(tmp_path / "x1.npy")])
+    b = np.concatenate([np.load(tmp_path / "b0.npy"), np.load(tmp_path / "b1.npy")])
+    assert np.linalg.norm(mass * (x + 0.5 * (A @ x)) - b) < 1e-8 * np.linalg.norm(b)
