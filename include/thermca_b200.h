@@ -61,6 +61,12 @@ typedef struct {
     const int32_t* fd_start; const int32_t* fd_film; const double* fd_adata;
     int32_t films_doff;             /* darena offset of films[F] */
     int32_t flux_doff;              /* darena offset of surf_flux[S] */
+    /* temperature dependent body (fe_system.py:185-193): when tdep != 0 the SELL arrays above hold
+     * Lx_base (geometry only), `mass` holds Mx_diag and the product is formed edge by edge */
+    int32_t tdep, condy_tab, volcapy_tab;
+    int32_t ts_nrows;
+    const int32_t* ts_row; const int32_t* ts_start; const int32_t* ts_surf; const double* ts_qval;
+    const int32_t* ts_fstart; const int32_t* ts_film; const double* ts_adata;
 } tc_ffe_desc;
 
 /* ---- LP part (replaces LPIO at run time, thermca/lpm/lp_io.py:8-80); operator and load

@@ -9,7 +9,7 @@ import scipy.sparse as sp
 from conftest import GOLDEN_MODELS
 
 pytestmark = pytest.mark.gpu
-DEVICE_MODELS = [m for m in GOLDEN_MODELS if m != "tdep_rod"]
+DEVICE_MODELS = list(GOLDEN_MODELS)
 
 
 @pytest.fixture(scope="module")

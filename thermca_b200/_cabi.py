@@ -29,7 +29,10 @@ class FfeDesc(C.Structure):
                 ("mass", vp), ("adiag", vp),
                 ("load_nrows", i32), ("load_row", vp), ("load_start", vp), ("load_surf", vp), ("load_bval", vp),
                 ("fd_nrows", i32), ("fd_pos", vp), ("fd_row", vp), ("fd_abody", vp), ("fd_start", vp),
-                ("fd_film", vp), ("fd_adata", vp), ("films_doff", i32), ("flux_doff", i32)]
+                ("fd_film", vp), ("fd_adata", vp), ("films_doff", i32), ("flux_doff", i32),
+                ("tdep", i32), ("condy_tab", i32), ("volcapy_tab", i32), ("ts_nrows", i32),
+                ("ts_row", vp), ("ts_start", vp), ("ts_surf", vp), ("ts_qval", vp),
+                ("ts_fstart", vp), ("ts_film", vp), ("ts_adata", vp)]
 
 
 class LpDesc(C.Structure):

@@ -156,6 +156,94 @@ static __global__ void tc_ffe_film_diag_kernel(TcFilmDiag F, const double* __res
     }
 }
 
+// ---- temperature dependent FE bodies (FESystem.update_material_properties,
+//      thermca/fem/fe_system.py:185-193 + FFEIO.update_material_properties ffe_io.py:67-74) ----
+// The reference rebuilds the operator on every right-hand side: L_ij = k((T_i+T_j)/2) Lx_ij
+// (diagonal = -row sum), M_i = c(T_i) Mx_i, A = M^-1 L: three full matrix passes.  Here the
+// same numbers are formed edge by edge inside the product, nothing is rebuilt or stored:
+//   ydot_i = -(1/M_i) * [ sum_{j!=i} k_ij Lx_ij T_j - (sum_{j!=i} k_ij Lx_ij) T_i ]
+// Lx_base is stored SELL-32 with its stored diagonal entry (value 0) skipped.
+__device__ __forceinline__ double tc_tab(const int* __restrict__ dir, const double* __restrict__ arena, int t, double x) {
+    const int off = dir[2 * t], n = dir[2 * t + 1];
+    const double* xp = arena + off;
+    const double* fp = xp + n;
+    if (isnan(x)) return x;
+    if (n == 1) return fp[0];
+    if (x <= xp[0]) return fp[0];
+    if (x >= xp[n - 1]) return fp[n - 1];
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= xp[mid]) lo = mid; else hi = mid;
+    }
+    const double slope = __ddiv_rn(__dsub_rn(fp[lo + 1], fp[lo]), __dsub_rn(xp[lo + 1], xp[lo]));
+    return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xp[lo])), fp[lo]);
+}
+
+struct TcTdep {
+    TcSell Lx;                 // Lx_base (geometry only)
+    const double* Mx;          // lumped geometric mass
+    const int* tab_dir;        // table directory (iarena)
+    const double* arena;       // darena
+    int condy_tab, volcapy_tab;
+};
+static __global__ void __launch_bounds__(TC_SPMV_THREADS)
+tc_ffe_tdep_spmv_kernel(TcTdep P, const double* __restrict__ x, double* __restrict__ y,
+                        const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * warps_per_block;
+    for (int s = warp; s < P.Lx.nslices; s += nwarps) {
+        const long long base = P.Lx.slice_ptr[s];
+        const int width = (int)((P.Lx.slice_ptr[s + 1] - base) >> 5);
+        const int row = s * 32 + lane;
+        const bool live = row < P.Lx.n;
+        const double xi = live ? x[row] : 0.0;
+        const double minv = live ? __ddiv_rn(1.0, __dmul_rn(tc_tab(P.tab_dir, P.arena, P.volcapy_tab, xi), P.Mx[row])) : 0.0;
+        double acc = 0.0, offsum = 0.0;
+        for (int k = 0; k < width; ++k) {
+            const double lx = ld_stream_f64(P.Lx.val + base + 32 * k + lane);
+            const int c = ld_stream_s32(P.Lx.col + base + 32 * k + lane);
+            if (c == row || !live) continue;
+            const double xc = __ldg(x + c);
+            const double kij = __dmul_rn(tc_tab(P.tab_dir, P.arena, P.condy_tab, __ddiv_rn(__dadd_rn(xi, xc), 2.0)), lx);
+            offsum = __dadd_rn(offsum, kij);
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(minv, kij), xc));
+        }
+        if (live) {
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(minv, -offsum), xi));
+            y[row] = -acc;
+        }
+    }
+}
+// surface rows of a temperature dependent part: load with the current 1/M_i and the film
+// diagonal (A_films keep the construction-time M_inv, as in the reference)
+struct TcTdepSurf {
+    int nrows;
+    const int* row; const int* start; const int* surf; const double* qval;      // Qs entries
+    const int* fstart; const int* film; const double* adata;                     // film diagonal lists
+};
+static __global__ void tc_ffe_tdep_surf_kernel(TcTdepSurf L, TcTdep P, const double* __restrict__ flux,
+                                               const double* __restrict__ films, const double* __restrict__ x,
+                                               double* __restrict__ ydot, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nrows; i += gridDim.x * blockDim.x) {
+        const int r = L.row[i];
+        const double xi = x[r];
+        const double minv = __ddiv_rn(1.0, __dmul_rn(tc_tab(P.tab_dir, P.arena, P.volcapy_tab, xi), P.Mx[r]));
+        double bsum = 0.0;
+        for (int k = L.start[i]; k < L.start[i + 1]; ++k) {
+            const double f = flux[L.surf[k]];
+            if (f != 0.0) bsum = __dadd_rn(bsum, __dmul_rn(__dmul_rn(minv, L.qval[k]), f));
+        }
+        double fd = 0.0;
+        for (int k = L.fstart[i]; k < L.fstart[i + 1]; ++k) fd = __dadd_rn(fd, __dmul_rn(films[L.film[k]], L.adata[k]));
+        ydot[r] = __dadd_rn(bsum, __dsub_rn(ydot[r], __dmul_rn(fd, xi)));
+    }
+}
+
 // ---- weighted gathers: surface mean temperatures -------------------------------------
 // Job j = sum_k w[k] * y[idx[k]] over its entry range; split over nblk[j] blocks whose
 // partial sums are combined in block order by the network kernel (C_SURF_MEAN).

@@ -421,6 +421,19 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
             p.A, yin + p.d.y_off, out + p.d.y_off, p.b, nullptr, s->ctrl, 0.0, nullptr, done);
     }
     for (auto& p : s->ffe) {
+        if (p.d.tdep) {
+            TcTdep T{p.A, p.d.mass, s->net.tab_dir, s->net.darena, p.d.condy_tab, p.d.volcapy_tab};
+            const int g = grid_for(p.A.nslices, TC_SPMV_THREADS / 32, s->sm_count * 8);
+            tc_ffe_tdep_spmv_kernel<<<g, TC_SPMV_THREADS, 0, st>>>(T, yin + p.d.y_off, out + p.d.y_off, done);
+            if (p.d.ts_nrows > 0) {
+                TcTdepSurf L{p.d.ts_nrows, p.d.ts_row, p.d.ts_start, p.d.ts_surf, p.d.ts_qval, p.d.ts_fstart,
+                             p.d.ts_film, p.d.ts_adata};
+                tc_ffe_tdep_surf_kernel<<<grid_for(p.d.ts_nrows, 256, s->sm_count * 4), 256, 0, st>>>(
+                    L, T, s->net.darena + p.d.flux_doff, s->net.darena + p.d.films_doff, yin + p.d.y_off,
+                    out + p.d.y_off, done);
+            }
+            continue;
+        }
         if (p.fdiag.nrows > 0)
             tc_ffe_film_diag_kernel<<<grid_for(p.fdiag.nrows, 256, s->sm_count * 4), 256, 0, st>>>(
                 p.fdiag, s->net.darena + p.d.films_doff, p.d.val, p.d.adiag, done);
@@ -439,7 +452,8 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
     }
     s->nfev += 1;
     s->launches += (s->mean_grid > 0 ? 1 : 0) + 1 + (long long)s->lp.size() + (long long)s->mor.size();
-    for (auto& p : s->ffe) s->launches += 1 + (p.fdiag.nrows > 0 ? 1 : 0) + (p.load.nrows > 0 ? 1 : 0);
+    for (auto& p : s->ffe)
+        s->launches += p.d.tdep ? 1 + (p.d.ts_nrows > 0 ? 1 : 0) : 1 + (p.fdiag.nrows > 0 ? 1 : 0) + (p.load.nrows > 0 ? 1 : 0);
     return 0;
 }
 
@@ -728,6 +742,7 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
     const int* done = s->flags + FL_DONE;
     tc_copy_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, rhs, z, done);
     for (auto& p : s->ffe) {
+        if (p.d.tdep) continue;      // operator depends on T: treated explicitly (copy above)
         TcPcg& P = p.pcg;
         P.A = p.A; P.mass = p.d.mass; P.adiag = p.d.adiag;
         P.rhs = rhs + p.d.y_off; P.x = z + p.d.y_off;

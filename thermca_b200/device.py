@@ -289,10 +289,6 @@ class DeviceSolver:
         ffe_dev = []
         for k, p in enumerate(s["ffe"]):
             F, S = len(p["films"]), int(p["S"])
-            if p["tdep"] is not None:
-                raise NotImplementedError(
-                    "temperature dependent FEPart bodies (FESystem.update_material_properties) are not "
-                    "on the device yet")
             ffe_dev.append({"films": A.add_d(p["films"] if F else np.zeros(1)), "flux": A.add_d(np.zeros(S)),
                             "areas": A.add_d(p["surf_areas"]), "surf_net": A.add_i(p["surf_net_idxs"]),
                             "film_surf": A.add_i(p["film_surf_idxs"] if F else [0]),
@@ -391,7 +387,56 @@ class DeviceSolver:
             _cabi.check(self.lib.tc_add_mor_part(self._handle, C.byref(md)))
         _cabi.check(self.lib.tc_finalize(self._handle, self.n_state))
 
+    def _add_ffe_tdep(self, k, p, d):
+        """Temperature dependent body: ship Lx_base (geometry) + tables; the operator is formed edge
+        by edge in the kernel (thermca/fem/fe_system.py:185-193)."""
+        td = p["tdep"]
+        n = int(p["dof"])
+        row = np.asarray(td["row"], dtype=np.int64)
+        indptr = np.concatenate([[0], np.cumsum(np.bincount(row, minlength=n))])
+        sell = csr_to_sell(indptr, td["col"], td["Lx_base_data"])
+        t_sp, t_col, t_val = self._up(sell["slice_ptr"]), self._up(sell["col"]), self._up(sell["val"])
+        t_mx = self._up(np.asarray(td["Mx_diag"], dtype=np.float64))
+        t_zero = self._up(np.zeros(n))
+        self.ffe_sell.append({"slice_ptr": t_sp, "col": t_col, "val": t_val, "mass": t_mx, "adiag": t_zero,
+                              "n": n, "nslices": sell["nslices"]})
+        # per surface/film row: Qs entries and film-diagonal entries
+        q_rows = np.concatenate([np.asarray(ix, dtype=np.int64) for ix in td["Qs_idx"]])
+        q_surf = np.concatenate([np.full(len(ix), sidx, dtype=np.int32) for sidx, ix in enumerate(td["Qs_idx"])])
+        q_val = np.concatenate([np.asarray(v, dtype=np.float64) for v in td["Qs_val"]])
+        ab_indptr = np.asarray(p["A_body"]["indptr"], dtype=np.int64)
+        if len(p["films"]):
+            f_cpos = np.concatenate([np.asarray(ix, dtype=np.int64) for ix in p["film_didx"]])
+            f_rows = np.searchsorted(ab_indptr, f_cpos, side="right") - 1
+            f_film = np.concatenate([np.full(len(ix), f, dtype=np.int32) for f, ix in enumerate(p["film_didx"])])
+            f_adata = np.concatenate([np.asarray(a, dtype=np.float64) for a in p["film_adata"]])
+        else:
+            f_rows, f_film, f_adata = np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0)
+        rows = np.unique(np.concatenate([q_rows, f_rows]))
+        oq = np.lexsort((q_surf, q_rows))
+        of = np.lexsort((f_film, f_rows))
+        q_start = np.searchsorted(q_rows[oq], np.append(rows, rows[-1] + 1 if len(rows) else 0)).astype(np.int32)
+        f_start = np.searchsorted(f_rows[of], np.append(rows, rows[-1] + 1 if len(rows) else 0)).astype(np.int32)
+        fd = _cabi.FfeDesc()
+        fd.n, fd.nslices, fd.y_off = n, sell["nslices"], self.ffe_off[k]
+        fd.slice_ptr, fd.col, fd.val = self._p(t_sp), self._p(t_col), self._p(t_val)
+        fd.mass, fd.adiag = self._p(t_mx), self._p(t_zero)
+        fd.load_nrows, fd.fd_nrows = 0, 0
+        fd.films_doff, fd.flux_doff = d["films"], d["flux"]
+        fd.tdep, fd.condy_tab, fd.volcapy_tab = 1, int(td["condy_tab"]), int(td["vol_capy_tab"])
+        fd.ts_nrows = len(rows)
+        fd.ts_row = self._p(self._up(rows.astype(np.int32)))
+        fd.ts_start = self._p(self._up(q_start))
+        fd.ts_surf = self._p(self._up(q_surf[oq].astype(np.int32) if len(oq) else np.zeros(1, np.int32)))
+        fd.ts_qval = self._p(self._up(q_val[oq] if len(oq) else np.zeros(1)))
+        fd.ts_fstart = self._p(self._up(f_start))
+        fd.ts_film = self._p(self._up(f_film[of].astype(np.int32) if len(of) else np.zeros(1, np.int32)))
+        fd.ts_adata = self._p(self._up(f_adata[of] if len(of) else np.zeros(1)))
+        _cabi.check(self.lib.tc_add_ffe_part(self._handle, C.byref(fd)))
+
     def _add_ffe(self, k, p, d):
+        if p.get("tdep") is not None:
+            return self._add_ffe_tdep(k, p, d)
         ab = p["A_body"]
         n = int(p["dof"])
         if "sell" in p:                  # operator already resident on the device (csrc/synth.cu)
@@ -449,6 +494,7 @@ class DeviceSolver:
         else:
             fd.fd_nrows = 0
         fd.films_doff, fd.flux_doff = d["films"], d["flux"]
+        fd.tdep, fd.ts_nrows = 0, 0
         _cabi.check(self.lib.tc_add_ffe_part(self._handle, C.byref(fd)))
 
     # -- state ---------------------------------------------------------------------------------------
