@@ -171,6 +171,44 @@ def tdep_rod():
     return Network(model), dict(time_span=[0.01, 0.3], method="RK45")
 
 
+def assembly():
+    """Small instance of BASELINE config #4: FE bodies (one temperature dependent, one MOR), two
+    linked LP blocks, temperature dependent fluid nodes with flow links, a stationary node,
+    nonlinear films, an Input driven heat loss (pattern of docs/examples/bearing.ipynb)."""
+    mesh = Mesh.read(PLATE_MSH, file_format="gmsh")
+    with Model() as model:
+        frame = FEPart(mesh, solids.steel, init_temp=22.0, temp_dependent=True, lump_cond_meth=None,
+                       name="frame")
+        table = FEPart(mesh, test_steel, init_temp=21.0, mor_dof=8, lump_cond_meth=None, name="table")
+        blk1 = lp_parts.block(matl=solids.steel, init_temp=23.0, width=0.2, hgt=0.1, depth=0.1,
+                              width_div=4, hgt_div=2, depth_div=2, name="blk1")
+        blk2 = lp_parts.block(matl=solids.al, init_temp=20.0, width=0.1, hgt=0.1, depth=0.1,
+                              width_div=2, hgt_div=2, depth_div=2, name="blk2")
+        env = BoundNode(temp=20.0, name="env")
+        inlet = BoundNode(temp=30.0, name="inlet")
+        oil1 = MatlNode(vol=2e-4, matl=fluids.water, init_temp=25.0, name="oil1")
+        oil2 = MatlNode(vol=3e-4, matl=fluids.water, init_temp=24.0, name="oil2")
+        oil1.temp_dependent = True
+        oil2.temp_dependent = True
+        FlowLink(oil1, inlet, vol_flow=1.0e-5)
+        FlowLink(oil2, oil1, vol_flow=lambda t_dest, t_src, fluid: 1.0e-5 * (1.0 + 0.01 * (t_src - 20.0)),
+                 matl=fluids.water)
+        FilmLink(frame.surf.top, oil1, forced_conv.plate(vel=0.5, length=0.5), matl=fluids.water)
+        FilmLink(table.surf.top, oil2, 200.0)
+        FilmLink(blk1.surf.top, frame.surf.bottom, 500.0)
+        FilmLink(blk1.surf.right, blk2.surf.left, film=lambda t0, t1, matl: 300.0 + 0.5 * (t0 + t1))
+        FilmLink(blk2.surf.right, env, combd_film.conv_radn_room(), matl=fluids.air)
+        FilmLink(frame.surf.left, env, free_conv.vert_surf(surf_hgt=0.05), matl=fluids.air)
+        FilmLink(table.surf.left, env, radiation.therm_radn(res_emis=0.7))
+        hub = StatNode(name="hub")
+        CondLink(hub, oil2, 4.0)
+        CondLink(hub, env, 1.5)
+        speed = Input([[0, 100.0], [20, 250.0], [40, 150.0]], name="speed")
+        HeatSource(table.surf.bottom, heat=lambda temp: 0.5 * speed.value * (1.0 - 0.002 * (temp - 20.0)))
+        HeatSource(hub, 12.0)
+    return Network(model), dict(time_span=[0.0, 45.0], method="RK45", rel_tol=1e-4)
+
+
 MODELS = {
     "getting_started": getting_started,
     "coffeecup": coffeecup,
@@ -181,4 +219,5 @@ MODELS = {
     "plate_mor_var": plate_mor_var,
     "kuhn_cuboid": kuhn_cuboid,
     "tdep_rod": tdep_rod,
+    "assembly": assembly,
 }
