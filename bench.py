@@ -157,13 +157,19 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    force_dist = os.environ.get("TC_FORCE_DIST") == "1"      # developer switch: partitioned path at world 1
+    if world > 1 or force_dist:
+        if force_dist and world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from thermca_b200.device import DeviceSolver
     from thermca_b200.workloads import cuboid_dims, device_cuboid_spec
 
-    if world > 1:
+    if world > 1 or force_dist:
         from thermca_b200.dist import run_partitioned_bench
         line = run_partitioned_bench(args, world, rank, local_rank)
         if rank == 0:

@@ -34,7 +34,7 @@ struct TcDistK {
     int* my_hflag;                        // [0] from lower, [1] from upper neighbour
     double* peer_mb[TC_MAX_WORLD]; int* peer_mbf[TC_MAX_WORLD];
     double* my_mb; int* my_mbf;           // mb[2][3][MAXW], mbf[2][MAXW]
-    int* state;                           // [0] reduction seq, [1] halo seq, [2] iters last, [3] iters total, [4] error, [5] solves
+    int* state;                           // [0] reduction seq, [1] halo seq, [2] iters last, [3] iters total, [4] error, [5] solves, [6] halo post counter
     double theta, h, rtol;
     int maxit;
 };
@@ -64,26 +64,40 @@ __device__ __forceinline__ double bank_sum(const double* bank, int G, double* sh
     return bc;
 }
 
-// my boundary rows -> neighbours' halo regions, then wait for mine
-__device__ void halo_exchange(const TcDistK& S, double* vec, double* const* peer_vec, int hseq,
-                              cg::grid_group& grid) {
-    const int H = S.H, n = S.n;
+#define TC_HALO_BLOCKS 8      // blocks that push the halo layers (112 KB per side on the 10M slab)
+
+// Post my boundary rows into the neighbours' halo regions.  Only the first TC_HALO_BLOCKS blocks
+// take part; the last of them to finish raises the neighbours' flags.  No grid-wide barrier.
+__device__ void halo_post(const TcDistK& S, const double* vec, double* const* peer_vec, int hseq) {
     double* lo = peer_vec[0];
     double* hi = peer_vec[1];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x) {
+    if (!lo && !hi) return;
+    const int nb = min((int)gridDim.x, TC_HALO_BLOCKS);
+    if ((int)blockIdx.x >= nb) return;
+    const int H = S.H, n = S.n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += nb * blockDim.x) {
         if (lo) lo[(long long)H + S.n_lo + i] = vec[H + i];
         if (hi) hi[i] = vec[H + n - H + i];
     }
     __threadfence_system();
-    grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (lo) st_release_sys(S.peer_hflag[0] + 1, hseq);
-        if (hi) st_release_sys(S.peer_hflag[1] + 0, hseq);
-    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        if (lo) spin_until(S.my_hflag + 0, hseq, S.state + 4);
-        if (hi) spin_until(S.my_hflag + 1, hseq, S.state + 4);
-        __threadfence_system();
+        const int done = atomicAdd(S.state + 6, 1);
+        if (done == nb - 1) {
+            S.state[6] = 0;
+            __threadfence_system();
+            if (lo) st_release_sys(S.peer_hflag[0] + 1, hseq);
+            if (hi) st_release_sys(S.peer_hflag[1] + 0, hseq);
+        }
+    }
+}
+// Wait until both neighbours have posted halo `hseq` (called before the boundary slices only).
+__device__ void halo_wait(const TcDistK& S, int hseq) {
+    if (!S.peer_y[0] && !S.peer_y[1]) return;
+    if (threadIdx.x == 0) {
+        if (S.peer_y[0]) spin_until(S.my_hflag + 0, hseq, S.state + 4);
+        if (S.peer_y[1]) spin_until(S.my_hflag + 1, hseq, S.state + 4);
+        __threadfence_system();       // acquire + drop stale L1 lines of the halo region
     }
     __syncthreads();
 }
@@ -96,12 +110,10 @@ __device__ void allreduce3(const TcDistK& S, double* v, int seq) {
         const int peer = threadIdx.x;
         volatile double* mb = S.peer_mb[peer];
         for (int k = 0; k < 3; ++k) mb[(par * 3 + k) * TC_MAX_WORLD + S.rank] = v[k];
-        __threadfence_system();
-        st_release_sys(S.peer_mbf[peer] + par * TC_MAX_WORLD + S.rank, seq);
+        st_release_sys(S.peer_mbf[peer] + par * TC_MAX_WORLD + S.rank, seq);   // orders the stores above
     }
     if (threadIdx.x < S.world) spin_until(S.my_mbf + par * TC_MAX_WORLD + threadIdx.x, seq, S.state + 4);
     __syncthreads();
-    __threadfence_system();
     volatile double* mine = S.my_mb;
     double out[3] = {0.0, 0.0, 0.0};
     for (int w = 0; w < S.world; ++w)
@@ -127,8 +139,15 @@ tc_dist_theta_kernel(TcDistK S) {
     double* p_loc = S.p_ext + H;
 
     // ---- right-hand side f = b - A y (thermca/solver.py:281) on the slab ---------------------
-    halo_exchange(S, S.y_ext, S.peer_y, ++hseq, grid);
-    tc_sell_spmv_body<SPMV_B, false>(S.A, y_g, S.q, S.b, nullptr, 0.0);
+    // slices whose rows reach into a neighbour's rows: done last, after the halo has landed
+    const int nsl = S.A.nslices;
+    const int nb_lo = S.peer_y[0] ? min(nsl, (H + 31) / 32) : 0;
+    const int nb_hi = S.peer_y[1] ? min(nsl - nb_lo, (H + 31) / 32 + 1) : 0;
+    halo_post(S, S.y_ext, S.peer_y, ++hseq);
+    tc_sell_spmv_body<SPMV_B, false>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, nb_lo, nsl - nb_hi);
+    halo_wait(S, hseq);
+    tc_sell_spmv_body<SPMV_B, false>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, 0, nb_lo);
+    tc_sell_spmv_body<SPMV_B, false>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, nsl - nb_hi, nsl);
     grid.sync();
     double rho_l = 0.0, bb_l = 0.0;
     for (int i = gtid; i < n; i += gsz) {
@@ -154,8 +173,13 @@ tc_dist_theta_kernel(TcDistK S) {
     int it = 0;
     if (red[1] > 0.0) {
         for (; it < S.maxit;) {
-            halo_exchange(S, S.p_ext, S.peer_p, ++hseq, grid);
-            const double dot = tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin);
+            halo_post(S, S.p_ext, S.peer_p, ++hseq);
+            double dot = tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
+                                                              nb_lo, nsl - nb_hi);
+            halo_wait(S, hseq);
+            dot += tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin, 0, nb_lo);
+            dot += tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
+                                                        nsl - nb_hi, nsl);
             const double bs = block_sum(dot, sh);
             if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
             grid.sync();

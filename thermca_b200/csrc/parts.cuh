@@ -45,13 +45,14 @@ template <int MODE, bool NC_X = true>
 __device__ __forceinline__ double tc_sell_spmv_body(const TcSell& A, const double* x,
                                                     double* y, const double* __restrict__ b,
                                                     const double* __restrict__ mass, double shift,
-                                                    long long xrow_off = 0) {
+                                                    long long xrow_off = 0, int s_begin = 0, int s_end = -1) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * warps_per_block;
     double dot = 0.0;
-    for (int s = warp; s < A.nslices; s += nwarps) {
+    if (s_end < 0) s_end = A.nslices;
+    for (int s = s_begin + warp; s < s_end; s += nwarps) {
         const long long base = A.slice_ptr[s];
         const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
         const double* v = A.val + base + lane;
