@@ -161,6 +161,7 @@ int tc_dist_set_state(tc_dist* d, const double* y_local_dev);
 int tc_dist_get_state(tc_dist* d, double* y_local_dev);
 int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, double h, double rtol, int32_t maxit);
 int tc_dist_stats(tc_dist* d, int64_t* stats4);
+int tc_dist_profile(tc_dist* d, uint64_t* out32);   /* per-phase wall time (ns) of block 0 / last block */
 int tc_dist_destroy(tc_dist* d);
 
 /* ---- batched MOR ensemble (BASELINE config #3): B scenarios in lockstep, FP64 DMMA ------- */

@@ -79,6 +79,7 @@ EXPORTS = {
     "tc_dist_get_state": (i32, [vp, vp]),
     "tc_dist_theta_steps": (i32, [vp, i32, f64, f64, f64, i32]),
     "tc_dist_stats": (i32, [vp, C.POINTER(i64)]),
+    "tc_dist_profile": (i32, [vp, C.POINTER(C.c_uint64)]),
     "tc_dist_destroy": (i32, [vp]),
     "tc_mor_batch_steps": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  f64, f64, i32, i32]),

@@ -37,6 +37,7 @@ struct TcDistK {
     int* state;                           // [0] reduction seq, [1] halo seq, [2] iters last, [3] iters total, [4] error, [5] solves, [6] halo post counter
     double theta, h, rtol;
     int maxit;
+    unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
 };
 
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
@@ -124,6 +125,17 @@ __device__ void allreduce3(const TcDistK& S, double* v, int seq) {
 
 #define TC_DIST_THREADS 256
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// phase profiler: thread 0 of block 0 and of the last block accumulate wall time per phase
+#define PROF_INIT() const int prof_row = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1); \
+    unsigned long long prof_t = (prof_row >= 0 && threadIdx.x == 0) ? gtime() : 0ULL
+#define PROF(k) do { if (prof_row >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
+    S.prof[prof_row * 16 + (k)] += t_ - prof_t; prof_t = t_; } } while (0)
+
 __global__ void __launch_bounds__(TC_DIST_THREADS)
 tc_dist_theta_kernel(TcDistK S) {
     cg::grid_group grid = cg::this_grid();
@@ -131,6 +143,7 @@ tc_dist_theta_kernel(TcDistK S) {
     const int G = gridDim.x, n = S.n, H = S.H;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     int rseq = S.state[0], hseq = S.state[1];
+    PROF_INIT();
     const double shift = S.theta * S.h;
     // vectors are gathered by GLOBAL column: element of global row g sits at ext[H + g - row_begin]
     const double* y_g = S.y_ext + H - S.row_begin;
@@ -173,18 +186,25 @@ tc_dist_theta_kernel(TcDistK S) {
     int it = 0;
     if (red[1] > 0.0) {
         for (; it < S.maxit;) {
+            PROF(0);
             halo_post(S, S.p_ext, S.peer_p, ++hseq);
+            PROF(1);
             double dot = tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
                                                               nb_lo, nsl - nb_hi);
+            PROF(2);
             halo_wait(S, hseq);
+            PROF(3);
             dot += tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin, 0, nb_lo);
             dot += tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
                                                         nsl - nb_hi, nsl);
             const double bs = block_sum(dot, sh);
             if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
+            PROF(4);
             grid.sync();
+            PROF(5);
             red[0] = bank_sum(S.partial, G, sh); red[1] = 0.0; red[2] = 0.0;
             allreduce3(S, red, ++rseq);
+            PROF(6);
             const double alpha = rho / red[0];
             double rn = 0.0, rr = 0.0;
             for (int i = gtid; i < n; i += gsz) {
@@ -199,17 +219,22 @@ tc_dist_theta_kernel(TcDistK S) {
                 S.partial[2 * TC_MAX_PARTIALS + blockIdx.x] = r0;
                 S.partial[3 * TC_MAX_PARTIALS + blockIdx.x] = r1;
             }
+            PROF(7);
             grid.sync();
+            PROF(8);
             red[0] = bank_sum(S.partial + 2 * TC_MAX_PARTIALS, G, sh);
             red[1] = bank_sum(S.partial + 3 * TC_MAX_PARTIALS, G, sh);
             red[2] = 0.0;
             allreduce3(S, red, ++rseq);
+            PROF(9);
             ++it;
             if (!(red[1] > tol2) || *((volatile int*)(S.state + 4))) break;
             const double beta = red[0] / rho;
             for (int i = gtid; i < n; i += gsz) p_loc[i] = S.dinv[i] * S.r[i] + beta * p_loc[i];
             rho = red[0];
+            PROF(10);
             grid.sync();
+            PROF(11);
         }
     }
     // ---- y += h * z --------------------------------------------------------------------------
@@ -232,6 +257,7 @@ struct tc_dist {
     long long peer_n[TC_MAX_WORLD];
     double *x = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr, *partial = nullptr;
     int* state = nullptr;
+    unsigned long long* prof = nullptr;
     TcDistK K;
     int grid = 0;
 };
@@ -261,6 +287,8 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     TC_CUDA(cudaMalloc(&d->partial, sizeof(double) * 4 * TC_MAX_PARTIALS));
     TC_CUDA(cudaMalloc(&d->state, sizeof(int) * 16));
     TC_CUDA(cudaMemset(d->state, 0, sizeof(int) * 16));
+    TC_CUDA(cudaMalloc(&d->prof, sizeof(unsigned long long) * 32));
+    TC_CUDA(cudaMemset(d->prof, 0, sizeof(unsigned long long) * 32));
     d->peer[rank] = d->comm;
     TC_CUDA(cudaDeviceSynchronize());
     *out = d;
@@ -323,6 +351,7 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     K.my_mb = (double*)(d->comm + d->off_mb); K.my_mbf = (int*)(d->comm + d->off_mbf);
     K.my_hflag = (int*)(d->comm + d->off_hflag);
     K.state = d->state;
+    K.prof = d->prof;
     int dev = 0, sms = 148, occ = 0;
     TC_CUDA(cudaGetDevice(&dev));
     TC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -364,12 +393,20 @@ extern "C" int tc_dist_stats(tc_dist* d, int64_t* stats4) {
     return 0;
 }
 
+// phase profile: 32 accumulated nanosecond counters (block 0: [0..15], last block: [16..31]); cleared on read
+extern "C" int tc_dist_profile(tc_dist* d, uint64_t* out32) {
+    TC_CUDA(cudaStreamSynchronize(d->stream));
+    TC_CUDA(cudaMemcpy(out32, d->prof, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemset(d->prof, 0, sizeof(unsigned long long) * 32));
+    return 0;
+}
+
 extern "C" int tc_dist_destroy(tc_dist* d) {
     if (!d) return 0;
     for (int w = 0; w < d->world; ++w)
         if (w != d->rank && d->peer[w]) cudaIpcCloseMemHandle(d->peer[w]);
     cudaFree(d->comm); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
-    cudaFree(d->partial); cudaFree(d->state);
+    cudaFree(d->partial); cudaFree(d->state); cudaFree(d->prof);
     delete d;
     return 0;
 }

@@ -122,6 +122,17 @@ class DistCuboid:
         _cabi.check(self.lib.tc_dist_stats(self._h, st))
         return {"iters_last": int(st[0]), "iters_total": int(st[1]), "error": int(st[2]), "solves": int(st[3])}
 
+    PHASES = ["dir->post", "halo post", "spmv interior", "halo wait", "spmv boundary+dot", "grid.sync", "allreduce pq",
+              "update x,r", "grid.sync", "allreduce rho", "direction", "grid.sync"]
+
+    def profile(self):
+        """Accumulated per-phase wall time (ms) seen by block 0 and by the last block; cleared on read."""
+        from . import _cabi
+        buf = (C.c_uint64 * 32)()
+        _cabi.check(self.lib.tc_dist_profile(self._h, buf))
+        return {"block0": {n: buf[i] / 1e6 for i, n in enumerate(self.PHASES)},
+                "last": {n: buf[16 + i] / 1e6 for i, n in enumerate(self.PHASES)}}
+
     def close(self):
         if self._h:
             self.dist.barrier()
@@ -140,6 +151,7 @@ def run_partitioned_bench(args, world, rank, local_rank):
     dc = DistCuboid(nx, ny_tot, nz, ly=1.0 * world, heat=B.HEAT * world, film=B.FILM, env_temp=B.T_ENV)
     dc.theta_steps(args.warmup, B.H_STEP, B.THETA, B.PCG_RTOL)
     it0 = dc.stats()["iters_total"]
+    dc.profile()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with B.ClockSampler(local_rank) as clocks:
         torch.cuda.synchronize()
@@ -155,6 +167,7 @@ def run_partitioned_bench(args, world, rank, local_rank):
     ms = float(ms.item())
     st = dc.stats()
     iters = st["iters_total"] - it0
+    prof = dc.profile()
     err = torch.tensor([st["error"]], dtype=torch.int64, device="cuda")
     dist.all_reduce(err, op=dist.ReduceOp.MAX)
     nnz = torch.tensor([dc.nnz], dtype=torch.int64, device="cuda")
@@ -187,7 +200,8 @@ def run_partitioned_bench(args, world, rank, local_rank):
                                f"{world} slabs, theta=0.5 Jacobi-PCG step, halo+reductions by peer stores in-kernel",
                    "dof": n_tot, "dof_per_gpu": dc.n, "nnz": int(nnz.item()), "pcg_rtol": B.PCG_RTOL,
                    "h_step_s": B.H_STEP, "iters_per_step": iters / args.steps, "halo_rows": dc.halo,
-                   "l2": "per-GPU inputs exceed the 126 MB L2", "comm_error": int(err.item())},
+                   "l2": "per-GPU inputs exceed the 126 MB L2", "comm_error": int(err.item()),
+                   "phase_ms_rank0": prof},
         "clocks": clocks.summary(),
         "e2e": {"value": n_tot * e2e_steps / float(e2e.item()), "unit": "DOF*steps/s",
                 "h2d_bytes_per_step": n_tot * 8, "d2h_bytes_per_step": n_tot * 8, "steps": e2e_steps},
