@@ -23,7 +23,7 @@ namespace cg = cooperative_groups;
 struct TcDistK {
     TcSell A;
     long long row_begin;
-    int n, H, rank, world;
+    int n, H, HP, rank, world;            // HP: halo slot rounded up to 16 doubles (128-byte aligned local part)
     int n_lo, n_hi;                       // local row counts of the neighbours
     const double *b, *mass, *adiag;
     double *y_ext, *p_ext;                // [H | n | H]
@@ -76,9 +76,10 @@ __device__ void halo_post(const TcDistK& S, const double* vec, double* const* pe
     const int nb = min((int)gridDim.x, TC_HALO_BLOCKS);
     if ((int)blockIdx.x >= nb) return;
     const int H = S.H, n = S.n;
+    const int HP = S.HP;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += nb * blockDim.x) {
-        if (lo) lo[(long long)H + S.n_lo + i] = vec[H + i];
-        if (hi) hi[i] = vec[H + n - H + i];
+        if (lo) lo[(long long)HP + S.n_lo + i] = vec[HP + i];               // -> their upper halo
+        if (hi) hi[HP - H + i] = vec[HP + n - H + i];                       // -> their lower halo
     }
     __threadfence_system();
     __syncthreads();
@@ -146,10 +147,13 @@ tc_dist_theta_kernel(TcDistK S) {
     PROF_INIT();
     const double shift = S.theta * S.h;
     // vectors are gathered by GLOBAL column: element of global row g sits at ext[H + g - row_begin]
-    const double* y_g = S.y_ext + H - S.row_begin;
-    const double* p_g = S.p_ext + H - S.row_begin;
-    double* y_loc = S.y_ext + H;
-    double* p_loc = S.p_ext + H;
+    const int HP = S.HP;
+    const double* y_g = S.y_ext + HP - S.row_begin;
+    const double* p_g = S.p_ext + HP - S.row_begin;
+    double* y_loc = S.y_ext + HP;
+    double* p_loc = S.p_ext + HP;
+    double* const p_lo = S.peer_p[0];      // neighbours' p_ext (peer memory) or null
+    double* const p_hi = S.peer_p[1];
 
     // ---- right-hand side f = b - A y (thermca/solver.py:281) on the slab ---------------------
     // slices whose rows reach into a neighbour's rows: done last, after the halo has landed
@@ -170,6 +174,11 @@ tc_dist_theta_kernel(TcDistK S) {
         const double z = d * bsc;
         S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; p_loc[i] = z;
         rho_l += bsc * z; bb_l += bsc * bsc;
+        // boundary rows go straight into the neighbours' halo slots (peer stores over NVLink)
+        bool remote = false;
+        if (p_lo && i < H) { p_lo[(long long)HP + S.n_lo + i] = z; remote = true; }
+        if (p_hi && i >= n - H) { p_hi[HP - H + (i - (n - H))] = z; remote = true; }
+        if (remote) __threadfence_system();
     }
     {
         const double r0 = block_sum(rho_l, sh), r1 = block_sum(bb_l, sh);
@@ -187,7 +196,11 @@ tc_dist_theta_kernel(TcDistK S) {
     if (red[1] > 0.0) {
         for (; it < S.maxit;) {
             PROF(0);
-            halo_post(S, S.p_ext, S.peer_p, ++hseq);
+            ++hseq;
+            if (blockIdx.x == 0 && threadIdx.x == 0) {      // halo stores were fenced before the last grid.sync
+                if (p_lo) st_release_sys(S.peer_hflag[0] + 1, hseq);
+                if (p_hi) st_release_sys(S.peer_hflag[1] + 0, hseq);
+            }
             PROF(1);
             double dot = tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
                                                               nb_lo, nsl - nb_hi);
@@ -230,7 +243,14 @@ tc_dist_theta_kernel(TcDistK S) {
             ++it;
             if (!(red[1] > tol2) || *((volatile int*)(S.state + 4))) break;
             const double beta = red[0] / rho;
-            for (int i = gtid; i < n; i += gsz) p_loc[i] = S.dinv[i] * S.r[i] + beta * p_loc[i];
+            for (int i = gtid; i < n; i += gsz) {
+                const double pn = S.dinv[i] * S.r[i] + beta * p_loc[i];
+                p_loc[i] = pn;
+                bool remote = false;
+                if (p_lo && i < H) { p_lo[(long long)HP + S.n_lo + i] = pn; remote = true; }
+                if (p_hi && i >= n - H) { p_hi[HP - H + (i - (n - H))] = pn; remote = true; }
+                if (remote) __threadfence_system();
+            }
             rho = red[0];
             PROF(10);
             grid.sync();
@@ -249,7 +269,7 @@ tc_dist_theta_kernel(TcDistK S) {
 struct tc_dist {
     cudaStream_t stream;
     int rank, world;
-    long long n, H, row_begin;
+    long long n, H, HP, row_begin;
     char* comm = nullptr;             // my exported buffer
     size_t comm_bytes = 0;
     size_t off_y, off_p, off_mb, off_mbf, off_hflag;
@@ -272,7 +292,8 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     memset(d->peer, 0, sizeof d->peer);
     d->stream = (cudaStream_t)stream; d->rank = rank; d->world = world;
     d->n = n_loc; d->H = halo; d->row_begin = row_begin;
-    const size_t ext = (size_t)(n_loc + 2 * halo) * sizeof(double);
+    d->HP = (halo + 15) / 16 * 16;
+    const size_t ext = (size_t)(n_loc + 2 * d->HP) * sizeof(double);
     d->off_y = 0;
     d->off_p = align_up(ext, 256);
     d->off_mb = d->off_p + align_up(ext, 256);
@@ -322,13 +343,13 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
                                     const double* b) {
     TcDistK& K = d->K;
     K.A = TcSell{(int)d->n, nslices, (const long long*)slice_ptr, col, val};
-    K.row_begin = d->row_begin; K.n = (int)d->n; K.H = (int)d->H; K.rank = d->rank; K.world = d->world;
+    K.row_begin = d->row_begin; K.n = (int)d->n; K.H = (int)d->H; K.HP = (int)d->HP; K.rank = d->rank; K.world = d->world;
     K.b = b; K.mass = mass; K.adiag = adiag;
     K.y_ext = (double*)(d->comm + d->off_y); K.p_ext = (double*)(d->comm + d->off_p);
     K.x = d->x; K.r = d->r; K.q = d->q; K.dinv = d->dinv; K.partial = d->partial;
     const int lo = d->rank - 1, hi = d->rank + 1;
     // peers share my buffer layout except for their own n: offsets depend on n_peer
-    auto ext_bytes = [&](int w) { return align_up((size_t)(d->peer_n[w] + 2 * d->H) * sizeof(double), 256); };
+    auto ext_bytes = [&](int w) { return align_up((size_t)(d->peer_n[w] + 2 * d->HP) * sizeof(double), 256); };
     auto off_p = [&](int w) { return ext_bytes(w); };
     auto off_mb = [&](int w) { return 2 * ext_bytes(w); };
     auto off_mbf = [&](int w) { return off_mb(w) + align_up(sizeof(double) * 2 * 3 * TC_MAX_WORLD, 256); };
@@ -365,12 +386,12 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
 }
 
 extern "C" int tc_dist_set_state(tc_dist* d, const double* y_local_dev) {
-    TC_CUDA(cudaMemcpyAsync(d->K.y_ext + d->H, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+    TC_CUDA(cudaMemcpyAsync(d->K.y_ext + d->HP, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     TC_CUDA(cudaStreamSynchronize(d->stream));
     return 0;
 }
 extern "C" int tc_dist_get_state(tc_dist* d, double* y_local_dev) {
-    TC_CUDA(cudaMemcpyAsync(y_local_dev, d->K.y_ext + d->H, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+    TC_CUDA(cudaMemcpyAsync(y_local_dev, d->K.y_ext + d->HP, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     TC_CUDA(cudaStreamSynchronize(d->stream));
     return 0;
 }
