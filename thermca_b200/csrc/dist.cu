@@ -94,12 +94,15 @@ __device__ void halo_post(const TcDistK& S, const double* vec, double* const* pe
     }
 }
 // Wait until both neighbours have posted halo `hseq` (called before the boundary slices only).
-__device__ void halo_wait(const TcDistK& S, int hseq) {
+// Only blocks that own boundary slices wait; they read the gathered vector through L2
+// (ld.global.cg), so no L1 invalidation is needed and the interior pass of co-resident blocks
+// keeps its cached lines.
+__device__ void halo_wait(const TcDistK& S, int hseq, int nb_max) {
     if (!S.peer_y[0] && !S.peer_y[1]) return;
+    if ((int)(blockIdx.x * (blockDim.x >> 5)) >= nb_max) return;      // this block has no boundary slice
     if (threadIdx.x == 0) {
         if (S.peer_y[0]) spin_until(S.my_hflag + 0, hseq, S.state + 4);
         if (S.peer_y[1]) spin_until(S.my_hflag + 1, hseq, S.state + 4);
-        __threadfence_system();       // acquire + drop stale L1 lines of the halo region
     }
     __syncthreads();
 }
@@ -161,10 +164,11 @@ tc_dist_theta_kernel(TcDistK S) {
     const int nb_lo = S.peer_y[0] ? min(nsl, (H + 31) / 32) : 0;
     const int nb_hi = S.peer_y[1] ? min(nsl - nb_lo, (H + 31) / 32 + 1) : 0;
     halo_post(S, S.y_ext, S.peer_y, ++hseq);
-    tc_sell_spmv_body<SPMV_B, false>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, nb_lo, nsl - nb_hi);
-    halo_wait(S, hseq);
-    tc_sell_spmv_body<SPMV_B, false>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, 0, nb_lo);
-    tc_sell_spmv_body<SPMV_B, false>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, nsl - nb_hi, nsl);
+    const int nb_max = max(nb_lo, nb_hi);
+    tc_sell_spmv_body<SPMV_B, 0>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, nb_lo, nsl - nb_hi);
+    halo_wait(S, hseq, nb_max);
+    tc_sell_spmv_body<SPMV_B, 2>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, 0, nb_lo);
+    tc_sell_spmv_body<SPMV_B, 2>(S.A, y_g, S.q, S.b, nullptr, 0.0, 0, nsl - nb_hi, nsl);
     grid.sync();
     double rho_l = 0.0, bb_l = 0.0;
     for (int i = gtid; i < n; i += gsz) {
@@ -202,14 +206,14 @@ tc_dist_theta_kernel(TcDistK S) {
                 if (p_hi) st_release_sys(S.peer_hflag[1] + 0, hseq);
             }
             PROF(1);
-            double dot = tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
-                                                              nb_lo, nsl - nb_hi);
+            double dot = tc_sell_spmv_body<SPMV_SHIFT, 0>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
+                                                          nb_lo, nsl - nb_hi);
             PROF(2);
-            halo_wait(S, hseq);
+            halo_wait(S, hseq, nb_max);
             PROF(3);
-            dot += tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin, 0, nb_lo);
-            dot += tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
-                                                        nsl - nb_hi, nsl);
+            dot += tc_sell_spmv_body<SPMV_SHIFT, 2>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin, 0, nb_lo);
+            dot += tc_sell_spmv_body<SPMV_SHIFT, 2>(S.A, p_g, S.q, nullptr, S.mass, shift, S.row_begin,
+                                                    nsl - nb_hi, nsl);
             const double bs = block_sum(dot, sh);
             if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
             PROF(4);

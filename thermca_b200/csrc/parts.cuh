@@ -31,17 +31,20 @@ enum { SPMV_NEG = 0, SPMV_B = 1, SPMV_SHIFT = 2 };
 // NC_X: gather x through the read-only (non-coherent) path.  Must be false when x is written
 // by other blocks of the SAME launch (persistent PCG kernel): then x is read with ld.global.ca,
 // which the gpu-scope fence of grid.sync() keeps coherent.
-template <bool NC_X>
+// NC_X = 1: read-only path; 0: ld.global.ca; 2: ld.global.cg (L2 only: data another GPU may have
+// just written through NVLink, no L1 invalidation needed).
+template <int NC_X>
 __device__ __forceinline__ double tc_ld_x(const double* p) {
-    if (NC_X) return __ldg(p);
+    if (NC_X == 1) return __ldg(p);
     double v;
-    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    if (NC_X == 2) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    else asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
 
 // xrow_off: index of local row 0 in the gathered vector (row partition: x is addressed by
 // GLOBAL column, outputs by LOCAL row); 0 on a single GPU.
-template <int MODE, bool NC_X = true>
+template <int MODE, int NC_X = 1>
 __device__ __forceinline__ double tc_sell_spmv_body(const TcSell& A, const double* x,
                                                     double* y, const double* __restrict__ b,
                                                     const double* __restrict__ mass, double shift,

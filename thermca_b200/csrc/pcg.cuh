@@ -102,7 +102,7 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     int it = 0;
     if (bb > 0.0) {
         for (; it < S.maxit;) {
-            const double dot = tc_sell_spmv_body<SPMV_SHIFT, false>(S.A, S.p, S.q, nullptr, S.mass, shift);
+            const double dot = tc_sell_spmv_body<SPMV_SHIFT, 0>(S.A, S.p, S.q, nullptr, S.mass, shift);
             const double bs = block_sum(dot, sh);
             if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
             grid.sync();
