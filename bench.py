@@ -202,6 +202,7 @@ def run_ours(args):
         sync()
     ms = e0.elapsed_time(e1)
     tm = dev.timing(False)
+    phase = dev.pcg_profile()
     iters = dev.pcg_stats()["iterations"] - it0
     value = n * args.steps / (ms * 1e-3)
     peak, peak_kind = measured_peak()
@@ -244,7 +245,7 @@ def run_ours(args):
                      "traffic": None, "kernel": "tc_pcg_coop_kernel", "peak_kind": peak_kind,
                      "ms_per_launch": pcg_ms_per_launch, "iters_per_launch": iters_per_solve,
                      "algorithmic_bytes_per_row_iter": algorithmic_bytes_per_iteration(n, nnz) / n,
-                     "share_of_step": tm["pcg_ms"] / ms},
+                     "share_of_step": tm["pcg_ms"] / ms, "phase_ms_block0": phase},
     }
     if cpu is not None:
         line["cpu_baseline"] = {

@@ -133,6 +133,7 @@ int tc_set_time(tc_handle h, double t);
 /* Switch CUDA-event timing of the PCG launches on/off; returns (and clears) the time and launch
  * counts accumulated since the previous call. */
 int tc_timing(tc_handle h, int32_t enable, double* pcg_ms, int64_t* pcg_launches, int64_t* launches);
+int tc_pcg_profile(tc_handle h, uint64_t* out16);   /* per-phase ns of block 0 while timing is on */
 /* PCG statistics of the implicit path: total iterations, solves, last iteration count */
 int tc_pcg_stats(tc_handle h, int64_t* stats4);
 

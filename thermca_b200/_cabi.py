@@ -68,6 +68,7 @@ EXPORTS = {
     "tc_ros2_advance": (i32, [vp, i32, i32]),
     "tc_set_time": (i32, [vp, f64]),
     "tc_timing": (i32, [vp, i32, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
+    "tc_pcg_profile": (i32, [vp, C.POINTER(C.c_uint64)]),
     "tc_pcg_stats": (i32, [vp, C.POINTER(i64)]),
     "tc_sell_spmv": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, i32]),
     "tc_pcg_solve": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32, C.POINTER(i32)]),

@@ -12,6 +12,7 @@
 // multi-process code); per rank the arithmetic is the single-GPU PCG of
 // pcg.cuh on rows [row_begin, row_end).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/thermca_b200.h"
 #include "parts.cuh"
@@ -140,7 +141,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define PROF(k) do { if (prof_row >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
     S.prof[prof_row * 16 + (k)] += t_ - prof_t; prof_t = t_; } } while (0)
 
-__global__ void __launch_bounds__(TC_DIST_THREADS)
+template <int MB>
+__global__ void __launch_bounds__(TC_DIST_THREADS, MB)
 tc_dist_theta_kernel(TcDistK S) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
@@ -270,6 +272,19 @@ tc_dist_theta_kernel(TcDistK S) {
 }
 
 // ---- host ------------------------------------------------------------------------------------
+static void* dist_fn() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TC_PCG_OCC");
+        v = e ? atoi(e) : 6;
+    }
+    switch (v) {
+        case 5: return (void*)tc_dist_theta_kernel<5>;
+        case 8: return (void*)tc_dist_theta_kernel<8>;
+        default: return (void*)tc_dist_theta_kernel<6>;
+    }
+}
+
 struct tc_dist {
     cudaStream_t stream;
     int rank, world;
@@ -350,6 +365,12 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     K.row_begin = d->row_begin; K.n = (int)d->n; K.H = (int)d->H; K.HP = (int)d->HP; K.rank = d->rank; K.world = d->world;
     K.b = b; K.mass = mass; K.adiag = adiag;
     K.y_ext = (double*)(d->comm + d->off_y); K.p_ext = (double*)(d->comm + d->off_p);
+    if (getenv("TC_DIST_EXP") && d->world == 1) {      // experiment: vectors outside the IPC-exported allocation
+        double* alt = nullptr;
+        TC_CUDA(cudaMalloc(&alt, 2 * align_up((size_t)(d->n + 2 * d->HP) * sizeof(double), 256)));
+        TC_CUDA(cudaMemset(alt, 0, 2 * align_up((size_t)(d->n + 2 * d->HP) * sizeof(double), 256)));
+        K.y_ext = alt; K.p_ext = (double*)((char*)alt + align_up((size_t)(d->n + 2 * d->HP) * sizeof(double), 256));
+    }
     K.x = d->x; K.r = d->r; K.q = d->q; K.dinv = d->dinv; K.partial = d->partial;
     const int lo = d->rank - 1, hi = d->rank + 1;
     // peers share my buffer layout except for their own n: offsets depend on n_peer
@@ -380,7 +401,7 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     int dev = 0, sms = 148, occ = 0;
     TC_CUDA(cudaGetDevice(&dev));
     TC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_dist_theta_kernel, TC_DIST_THREADS, 0));
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)dist_fn(), TC_DIST_THREADS, 0));
     if (occ > 8) occ = 8;
     d->grid = occ * sms;
     if (d->grid > TC_MAX_PARTIALS) d->grid = TC_MAX_PARTIALS;
@@ -404,7 +425,7 @@ extern "C" int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, dou
     d->K.theta = theta; d->K.h = h; d->K.rtol = rtol; d->K.maxit = maxit;
     for (int k = 0; k < nsteps; ++k) {
         void* args[] = {(void*)&d->K};
-        TC_CUDA(cudaLaunchCooperativeKernel((void*)tc_dist_theta_kernel, dim3(d->grid), dim3(TC_DIST_THREADS), args, 0, d->stream));
+        TC_CUDA(cudaLaunchCooperativeKernel(dist_fn(), dim3(d->grid), dim3(TC_DIST_THREADS), args, 0, d->stream));
     }
     return 0;
 }
@@ -414,7 +435,7 @@ extern "C" int tc_dist_stats(tc_dist* d, int64_t* stats4) {
     int st[16];
     TC_CUDA(cudaStreamSynchronize(d->stream));
     TC_CUDA(cudaMemcpy(st, d->state, sizeof st, cudaMemcpyDeviceToHost));
-    stats4[0] = st[2]; stats4[1] = st[3]; stats4[2] = st[4]; stats4[3] = st[5];
+    stats4[0] = st[2]; stats4[1] = st[3]; stats4[2] = st[4]; stats4[3] = st[5] + 1000000LL * d->grid;
     return 0;
 }
 

@@ -32,6 +32,7 @@ struct TcPcg {
     int maxit;
     const double* ctrl;     // shift = coef * ctrl[1]
     double coef;
+    unsigned long long* prof;   // optional [16] phase times (ns) of block 0
 };
 
 #define TC_PCG_THREADS 256
@@ -87,13 +88,25 @@ __device__ __forceinline__ void tc_pcg_dir_phase(const TcPcg& S, double beta) {
         S.p[i] = S.dinv[i] * S.r[i] + beta * S.p[i];
 }
 
-__global__ void __launch_bounds__(TC_PCG_THREADS)
+__device__ __forceinline__ unsigned long long tc_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define PCG_PROF(k) do { if (S.prof && blockIdx.x == 0 && threadIdx.x == 0) { const unsigned long long t_ = tc_gtime(); \
+    S.prof[(k)] += t_ - prof_t; prof_t = t_; } } while (0)
+
+// MB = resident blocks per SM the register allocation is tuned for (occupancy matters: the kernel
+// is latency/bandwidth bound; measured on B200, see profiles/).
+template <int MB>
+__global__ void __launch_bounds__(TC_PCG_THREADS, MB)
 tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;       // uniform over the grid
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
     const int G = gridDim.x;
     const double shift = S.coef * S.ctrl[1];
+    unsigned long long prof_t = (S.prof && blockIdx.x == 0 && threadIdx.x == 0) ? tc_gtime() : 0ULL;
     tc_pcg_init_phase(S, shift, sh);
     grid.sync();
     double rho = tc_bank_sum(S.partial, G, sh);
@@ -102,21 +115,30 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     int it = 0;
     if (bb > 0.0) {
         for (; it < S.maxit;) {
+            PCG_PROF(0);
             const double dot = tc_sell_spmv_body<SPMV_SHIFT, 0>(S.A, S.p, S.q, nullptr, S.mass, shift);
+            PCG_PROF(1);
             const double bs = block_sum(dot, sh);
             if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
             grid.sync();
+            PCG_PROF(2);
             const double pq = tc_bank_sum(S.partial, G, sh);
             const double alpha = rho / pq;
+            PCG_PROF(3);
             tc_pcg_update_phase(S, alpha, sh);
+            PCG_PROF(4);
             grid.sync();
+            PCG_PROF(5);
             const double rho_new = tc_bank_sum(S.partial + 2 * TC_MAX_PARTIALS, G, sh);
             const double rr = tc_bank_sum(S.partial + 3 * TC_MAX_PARTIALS, G, sh);
             ++it;
+            PCG_PROF(6);
             if (!(rr > tol2)) break;           // uniform: every block holds the same rr
             tc_pcg_dir_phase(S, rho_new / rho);
             rho = rho_new;
+            PCG_PROF(7);
             grid.sync();
+            PCG_PROF(8);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {

@@ -8,6 +8,7 @@
 // common.py — third-party, restated from the installed 1.18.1 sources the reference pins
 // as 1.14.1).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -24,6 +25,9 @@ extern "C" void tc_set_error(const char* file, int line, const char* msg) {
 }
 extern "C" const char* tc_last_error(void) { return g_err.c_str(); }
 extern "C" int tc_version(void) { return 100; }
+
+#define TC_PCG_DEFAULT_OCC 6
+static int pcg_coop_grid(int sm_count);
 
 // ---- control block layout (device) ------------------------------------------------------
 enum { CT_T = 0, CT_H, CT_HABS, CT_ERR, CT_TEND, CT_RTOL, CT_ATOL, CT_MAXSTEP, CT_TNEW,
@@ -273,7 +277,7 @@ struct tc_solver {
     double* y = nullptr; double* ynew = nullptr; double* ystage = nullptr;
     double* K[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* red_partial = nullptr;     // 4 banks
-    double* pcg_sc = nullptr; int* pcg_isc = nullptr;
+    double* pcg_sc = nullptr; int* pcg_isc = nullptr; unsigned long long* pcg_prof = nullptr;
     int* pin_flags = nullptr;          // pinned host mirror
     double* pin_ctrl = nullptr;
     // history
@@ -316,6 +320,8 @@ extern "C" int tc_create(tc_handle* out, void* cuda_stream) {
     TC_CUDA(cudaMalloc(&s->pcg_isc, sizeof(int) * 16));
     TC_CUDA(cudaMemset(s->pcg_sc, 0, sizeof(double) * 16));
     TC_CUDA(cudaMemset(s->pcg_isc, 0, sizeof(int) * 16));
+    TC_CUDA(cudaMalloc(&s->pcg_prof, sizeof(unsigned long long) * 16));
+    TC_CUDA(cudaMemset(s->pcg_prof, 0, sizeof(unsigned long long) * 16));
     TC_CUDA(cudaMallocHost(&s->pin_flags, sizeof(int) * 32));
     TC_CUDA(cudaMallocHost(&s->pin_ctrl, sizeof(double) * 32));
     *out = s;
@@ -399,11 +405,7 @@ extern "C" int tc_finalize(tc_handle s, int64_t n_state) {
         TC_CUDA(cudaMalloc(&p.r, b)); TC_CUDA(cudaMalloc(&p.p, b));
         TC_CUDA(cudaMalloc(&p.q, b)); TC_CUDA(cudaMalloc(&p.dinv, b));
     }
-    int occ = 0;
-    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_pcg_coop_kernel, TC_PCG_THREADS, 0));
-    if (occ > 8) occ = 8;
-    s->coop_grid = occ * s->sm_count;
-    if (s->coop_grid > TC_MAX_PARTIALS) s->coop_grid = TC_MAX_PARTIALS;
+    s->coop_grid = pcg_coop_grid(s->sm_count);
     s->finalized = true;
     return 0;
 }
@@ -700,6 +702,32 @@ extern "C" int tc_get_info(tc_handle s, int64_t* info8, double* t_now, double* h
 }
 
 // ---- PCG drivers ---------------------------------------------------------------------------------
+static int pcg_occ_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TC_PCG_OCC");
+        v = e ? atoi(e) : TC_PCG_DEFAULT_OCC;
+        if (v != 5 && v != 6 && v != 8) v = TC_PCG_DEFAULT_OCC;
+    }
+    return v;
+}
+static void* pcg_coop_fn() {
+    switch (pcg_occ_variant()) {
+        case 5: return (void*)tc_pcg_coop_kernel<5>;
+        case 8: return (void*)tc_pcg_coop_kernel<8>;
+        default: return (void*)tc_pcg_coop_kernel<6>;
+    }
+}
+static int pcg_coop_grid(int sm_count) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pcg_coop_fn(), TC_PCG_THREADS, 0);
+    if (occ > 8) occ = 8;
+    if (occ < 1) occ = 1;
+    int g = occ * sm_count;
+    if (g > TC_MAX_PARTIALS) g = TC_MAX_PARTIALS;
+    return g;
+}
+
 static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int* done) {
     cudaStream_t st = s ? s->stream : nullptr;
     if (mode == TC_PCG_COOP) {
@@ -712,7 +740,7 @@ static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int
             TC_CUDA(cudaEventCreate(&e0)); TC_CUDA(cudaEventCreate(&e1));
             TC_CUDA(cudaEventRecord(e0, st));
         }
-        TC_CUDA(cudaLaunchCooperativeKernel((void*)tc_pcg_coop_kernel, dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
+        TC_CUDA(cudaLaunchCooperativeKernel(pcg_coop_fn(), dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
         if (e0) { TC_CUDA(cudaEventRecord(e1, st)); s->ev.push_back(e0); s->ev.push_back(e1); }
         if (s) s->launches += 1;
         return 0;
@@ -749,6 +777,7 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         P.r = p.r; P.p = p.p; P.q = p.q; P.dinv = p.dinv;
         P.partial = s->red_partial; P.sc = s->pcg_sc; P.isc = s->pcg_isc;
         P.rtol = s->pcg_rtol; P.maxit = s->pcg_maxit; P.ctrl = s->ctrl; P.coef = coef;
+        P.prof = s->timing ? s->pcg_prof : nullptr;
         if (launch_pcg(s, P, s->pcg_mode, s->coop_grid, done)) return -1;
     }
     return 0;
@@ -857,6 +886,15 @@ extern "C" int tc_timing(tc_handle s, int32_t enable, double* pcg_ms, int64_t* p
     return 0;
 }
 
+// phase profile of the cooperative PCG kernel (block 0, ns; recorded while timing is on; cleared on read):
+// spmv, sync, pq sum, update, sync, rho sums, direction, sync
+extern "C" int tc_pcg_profile(tc_handle s, uint64_t* out16) {
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    TC_CUDA(cudaMemcpy(out16, s->pcg_prof, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemset(s->pcg_prof, 0, sizeof(unsigned long long) * 16));
+    return 0;
+}
+
 extern "C" int tc_pcg_stats(tc_handle s, int64_t* stats4) {
     int isc[4];
     TC_CUDA(cudaMemcpyAsync(isc, s->pcg_isc, sizeof isc, cudaMemcpyDeviceToHost, s->stream));
@@ -912,14 +950,11 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     P.mass = mass; P.adiag = adiag; P.rhs = rhs; P.x = x;
     P.r = ws; P.p = ws + n; P.q = ws + 2 * (size_t)n; P.dinv = ws + 3 * (size_t)n;
     P.partial = aux; P.sc = aux + 4 * TC_MAX_PARTIALS; P.isc = isc;
-    P.rtol = rtol; P.maxit = maxit; P.ctrl = ctrl; P.coef = shift;
-    int dev = 0, sms = 148, occ = 0;
+    P.rtol = rtol; P.maxit = maxit; P.ctrl = ctrl; P.coef = shift; P.prof = nullptr;
+    int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_pcg_coop_kernel, TC_PCG_THREADS, 0));
-    if (occ > 8) occ = 8;
-    int cgp = occ * sms;
-    if (cgp > TC_MAX_PARTIALS) cgp = TC_MAX_PARTIALS;
+    const int cgp = pcg_coop_grid(sms);
     int rc = launch_pcg(&tmp, P, mode, cgp, nullptr);
     if (rc == 0) {
         cudaError_t e = cudaStreamSynchronize(tmp.stream);

@@ -646,6 +646,12 @@ class DeviceSolver:
         _cabi.check(self.lib.tc_timing(self._handle, int(bool(enable)), C.byref(ms), C.byref(n), C.byref(launches)))
         return {"pcg_ms": ms.value, "pcg_launches": int(n.value), "launches": int(launches.value)}
 
+    def pcg_profile(self):
+        names = ["loop top", "spmv", "dot+sync", "pq sum", "update x,r", "sync", "rho sums", "direction", "sync "]
+        buf = (C.c_uint64 * 16)()
+        _cabi.check(self.lib.tc_pcg_profile(self._handle, buf))
+        return {n: buf[i] / 1e6 for i, n in enumerate(names)}
+
     def pcg_stats(self):
         st = (_cabi.i64 * 4)()
         _cabi.check(self.lib.tc_pcg_stats(self._handle, st))

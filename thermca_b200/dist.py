@@ -120,7 +120,8 @@ class DistCuboid:
         from . import _cabi
         st = (_cabi.i64 * 4)()
         _cabi.check(self.lib.tc_dist_stats(self._h, st))
-        return {"iters_last": int(st[0]), "iters_total": int(st[1]), "error": int(st[2]), "solves": int(st[3])}
+        return {"iters_last": int(st[0]), "iters_total": int(st[1]), "error": int(st[2]),
+                "solves": int(st[3]) % 1000000, "grid": int(st[3]) // 1000000}
 
     PHASES = ["dir->post", "halo post", "spmv interior", "halo wait", "spmv boundary+dot", "grid.sync", "allreduce pq",
               "update x,r", "grid.sync", "allreduce rho", "direction", "grid.sync"]
@@ -201,7 +202,7 @@ def run_partitioned_bench(args, world, rank, local_rank):
                    "dof": n_tot, "dof_per_gpu": dc.n, "nnz": int(nnz.item()), "pcg_rtol": B.PCG_RTOL,
                    "h_step_s": B.H_STEP, "iters_per_step": iters / args.steps, "halo_rows": dc.halo,
                    "l2": "per-GPU inputs exceed the 126 MB L2", "comm_error": int(err.item()),
-                   "phase_ms_rank0": prof},
+                   "phase_ms_rank0": prof, "grid": st["grid"]},
         "clocks": clocks.summary(),
         "e2e": {"value": n_tot * e2e_steps / float(e2e.item()), "unit": "DOF*steps/s",
                 "h2d_bytes_per_step": n_tot * 8, "d2h_bytes_per_step": n_tot * 8, "steps": e2e_steps},
