@@ -276,12 +276,12 @@ static void* dist_fn() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("TC_PCG_OCC");
-        v = e ? atoi(e) : 6;
+        v = e ? atoi(e) : 8;
     }
     switch (v) {
         case 5: return (void*)tc_dist_theta_kernel<5>;
-        case 8: return (void*)tc_dist_theta_kernel<8>;
-        default: return (void*)tc_dist_theta_kernel<6>;
+        case 6: return (void*)tc_dist_theta_kernel<6>;
+        default: return (void*)tc_dist_theta_kernel<8>;
     }
 }
 

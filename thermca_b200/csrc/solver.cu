@@ -26,7 +26,7 @@ extern "C" void tc_set_error(const char* file, int line, const char* msg) {
 extern "C" const char* tc_last_error(void) { return g_err.c_str(); }
 extern "C" int tc_version(void) { return 100; }
 
-#define TC_PCG_DEFAULT_OCC 6
+#define TC_PCG_DEFAULT_OCC 8
 static int pcg_coop_grid(int sm_count);
 
 // ---- control block layout (device) ------------------------------------------------------
@@ -714,8 +714,8 @@ static int pcg_occ_variant() {
 static void* pcg_coop_fn() {
     switch (pcg_occ_variant()) {
         case 5: return (void*)tc_pcg_coop_kernel<5>;
-        case 8: return (void*)tc_pcg_coop_kernel<8>;
-        default: return (void*)tc_pcg_coop_kernel<6>;
+        case 6: return (void*)tc_pcg_coop_kernel<6>;
+        default: return (void*)tc_pcg_coop_kernel<8>;
     }
 }
 static int pcg_coop_grid(int sm_count) {
