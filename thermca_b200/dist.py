@@ -123,8 +123,8 @@ class DistCuboid:
         return {"iters_last": int(st[0]), "iters_total": int(st[1]), "error": int(st[2]),
                 "solves": int(st[3]) % 1000000, "grid": int(st[3]) // 1000000}
 
-    PHASES = ["dir->post", "halo post", "spmv interior", "halo wait", "spmv boundary+dot", "grid.sync", "allreduce pq",
-              "update x,r", "grid.sync", "allreduce rho", "direction", "grid.sync"]
+    PHASES = ["rhs+init", "halo flag", "spmv", "-", "dot", "sync1", "allreduce pq",
+              "update x,r", "sync2", "allreduce rho", "direction", "sync3"]
 
     def profile(self):
         """Accumulated per-phase wall time (ms) seen by block 0 and by the last block; cleared on read."""
