@@ -147,6 +147,138 @@ tc_mor_stage_kernel(MorBatch M, const double* __restrict__ Xin, const double* __
             }
 }
 
+
+// ---- pipelined variant: cp.async (LDGSTS) double buffering, conflict-free padded tiles, 2 CTAs/SM ----
+// Same math and epilogue as tc_mor_stage_kernel<.., true>; the k-chunks of the operator tiles and of
+// the state tile are prefetched one chunk ahead so the DMMA pipe is not stalled on L2 latency.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+#define MP_TK 16
+#define MP_LDA (MP_TK + 4)     // 20 doubles: rows 16-byte aligned, A-fragment reads conflict free
+#define MP_TN 64
+#define MP_LDX (MP_TN + 4)     // 68 doubles
+
+template <int NOPS>
+__global__ void __launch_bounds__(MB_THREADS, (NOPS <= 3 ? 2 : 1))
+tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ Xin, const double* __restrict__ Xbase,
+                         double* __restrict__ Xout, double* __restrict__ Xacc, double t, double h,
+                         double c_out, double c_acc, int first) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int A_STAGE = NOPS * MB_TM * MP_LDA;
+    constexpr int X_STAGE = MP_TK * MP_LDX;
+    double* sA0 = smem;                         // [2][NOPS][64][20]
+    double* sX0 = smem + 2 * A_STAGE;           // [2][16][68]
+    const int s = blockIdx.z;
+    const int i0 = blockIdx.y * MB_TM;
+    const int b0 = blockIdx.x * MP_TN;
+    const int r = M.r, B = M.B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 3) * 16;
+    const int wn = (warp >> 2) * 32;
+    const double* Xs = Xin + (size_t)s * r * B;
+    double acc[NOPS][2][4][2];
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[o][a][c][0] = acc[o][a][c][1] = 0.0;
+
+    auto load_chunk = [&](int stage, int k0) {
+        double* sA = sA0 + stage * A_STAGE;
+        double* sX = sX0 + stage * X_STAGE;
+        // operators: NOPS x 64 rows x 8 pairs (16 bytes each)
+        for (int e = tid; e < NOPS * MB_TM * (MP_TK / 2); e += MB_THREADS) {
+            const int o = e / (MB_TM * (MP_TK / 2));
+            const int rem = e - o * (MB_TM * (MP_TK / 2));
+            const int ri = rem / (MP_TK / 2), kp = rem - ri * (MP_TK / 2);
+            const int gi = i0 + ri, gk = k0 + 2 * kp;
+            const double* W = (o == 0) ? M.A_body + (size_t)s * r * r : M.A_films + ((size_t)(o - 1) * M.S + s) * r * r;
+            const bool ok = gi < r && gk < r;          // r is even: a pair is either inside or outside
+            cp_async16(sA + (o * MB_TM + ri) * MP_LDA + 2 * kp, ok ? (const void*)(W + (size_t)gi * r + gk) : (const void*)W,
+                       ok ? 16 : 0);
+        }
+        // state: 16 rows x 32 pairs
+        for (int e = tid; e < MP_TK * (MP_TN / 2); e += MB_THREADS) {
+            const int kk = e / (MP_TN / 2), bp = e - kk * (MP_TN / 2);
+            const int gk = k0 + kk, gb = b0 + 2 * bp;
+            const bool ok = gk < r && gb < B;
+            cp_async16(sX + kk * MP_LDX + 2 * bp, ok ? (const void*)(Xs + (size_t)gk * B + gb) : (const void*)Xs, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+
+    const int nchunks = (r + MP_TK - 1) / MP_TK;
+    load_chunk(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int st = ch & 1;
+        if (ch + 1 < nchunks) { load_chunk(st ^ 1, (ch + 1) * MP_TK); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const double* sA = sA0 + st * A_STAGE;
+        const double* sX = sX0 + st * X_STAGE;
+#pragma unroll
+        for (int k4 = 0; k4 < MP_TK; k4 += 4) {
+            double bf[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bf[c] = sX[(k4 + (lane & 3)) * MP_LDX + wn + 8 * c + (lane >> 2)];
+#pragma unroll
+            for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const double af = sA[(o * MB_TM + wm + 8 * a + (lane >> 2)) * MP_LDA + k4 + (lane & 3)];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dmma884(acc[o][a][c][0], acc[o][a][c][1], af, bf[c]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gi = i0 + wm + 8 * a + (lane >> 2);
+                const int gb = b0 + wn + 8 * c + 2 * (lane & 3) + e;
+                if (gi >= r || gb >= B) continue;
+                double z = acc[0][a][c][e];
+                double flux = M.q_surf[s];
+#pragma unroll
+                for (int f = 0; f < NOPS - 1; ++f) {
+                    const double fv = film_at(M, f, gb, t);
+                    z += fv * acc[f + 1][a][c][e];
+                    if (M.film_surf[f] == s) flux += fv * M.t_link[f];
+                }
+                const double kval = -z + M.B_T[(size_t)s * r + gi] * flux;
+                const size_t idx = ((size_t)s * r + gi) * B + gb;
+                const double xb = Xbase[idx];
+                if (Xout) Xout[idx] = xb + c_out * h * kval;
+                Xacc[idx] = (first ? xb : Xacc[idx]) + c_acc * h * kval;
+            }
+}
+
+template <int NOPS>
+static int launch_stage_pipe(int S, int r, int B, cudaStream_t st, const MorBatch& M, const double* Xin,
+                             const double* Xbase, double* Xout, double* Xacc, double t, double h, double c_out,
+                             double c_acc, int first) {
+    const size_t smem = sizeof(double) * 2 * (NOPS * MB_TM * MP_LDA + MP_TK * MP_LDX);
+    static bool configured = false;
+    if (!configured) {
+        TC_CUDA(cudaFuncSetAttribute(tc_mor_stage_pipe_kernel<NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((B + MP_TN - 1) / MP_TN, (r + MB_TM - 1) / MB_TM, S);
+    tc_mor_stage_pipe_kernel<NOPS><<<grid, MB_THREADS, smem, st>>>(M, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
+    return 0;
+}
+
 extern "C" int64_t tc_mor_batch_work_doubles(int32_t S, int32_t r, int32_t F, int32_t B) {
     (void)F;
     return 3LL * S * r * B;
@@ -174,8 +306,18 @@ extern "C" int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32
     const size_t n = (size_t)S * r * B;
     double* o1 = work; double* o2 = work + n; double* acc = work + 2 * n;
     const bool dm = use_dmma != 0;
+    const bool pipe = use_dmma == 2 && F <= 3 && (r % 2) == 0 && (B % 2) == 0;
     auto stage = [&](const double* Xin, const double* Xb, double* Xout, double* Xacc, double t, double c_out,
                      double c_acc, int first) {
+        if (pipe) {
+            switch (F) {
+                case 0: launch_stage_pipe<1>(S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+                case 1: launch_stage_pipe<2>(S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+                case 2: launch_stage_pipe<3>(S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+                default: launch_stage_pipe<4>(S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+            }
+            return;
+        }
         switch (F) {
             case 0: launch_stage<1, 4>(dm, S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
             case 1: launch_stage<2, 4>(dm, S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;

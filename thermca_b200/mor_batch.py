@@ -46,7 +46,8 @@ class MorEnsemble:
         self.time = 0.0
         torch.cuda.synchronize(self.dev)
 
-    def steps(self, nsteps, h, use_dmma=True, stream=None):
+    def steps(self, nsteps, h, use_dmma=2, stream=None):
+        """use_dmma: 2 = pipelined DMMA kernel (default), 1 = simple DMMA kernel, 0 = FMA cross-check."""
         torch = self.torch
         st = torch.cuda.current_stream(self.dev) if stream is None else stream
         p = lambda a: C.c_void_p(a.data_ptr())
@@ -54,7 +55,7 @@ class MorEnsemble:
         _cabi.check(self.lib.tc_mor_batch_steps(
             C.c_void_p(st.cuda_stream), self.S, self.r, self.F, self.B, p(t["A_body"]), p(t["A_films"]), p(t["B_T"]),
             p(t["film_surf"]), p(t["film_h0"]), p(t["film_tau"]), p(t["t_link"]), p(t["q_surf"]), p(self.X),
-            p(self.work), float(self.time), float(h), int(nsteps), int(bool(use_dmma))))
+            p(self.work), float(self.time), float(h), int(nsteps), int(use_dmma) if use_dmma in (0, 1, 2) else 1))
         self.time += nsteps * h
 
     def state(self):
