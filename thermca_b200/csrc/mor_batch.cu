@@ -214,6 +214,7 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ Xin, const doubl
         cp_async_commit();
     };
 
+    const bool live[2] = {i0 + wm < r, i0 + wm + 8 < r};      // warp-uniform
     const int nchunks = (r + MP_TK - 1) / MP_TK;
     load_chunk(0, 0);
     for (int ch = 0; ch < nchunks; ++ch) {
@@ -232,6 +233,7 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ Xin, const doubl
             for (int o = 0; o < NOPS; ++o)
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
+                    if (!live[a]) continue;          // 8-row strip entirely past r (ragged last row tile)
                     const double af = sA[(o * MB_TM + wm + 8 * a + (lane >> 2)) * MP_LDA + k4 + (lane & 3)];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) dmma884(acc[o][a][c][0], acc[o][a][c][1], af, bf[c]);
