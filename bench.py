@@ -227,6 +227,25 @@ def run_ours(args):
     e2e_sec = time.perf_counter() - t_e0
     e2e_val = n * e2e_steps / e2e_sec
 
+    # extra: the reference's own scheme (explicit adaptive RK45, step control on the device) on the
+    # same operator, 40 accepted/rejected attempts from the initial state
+    dev.set_state(dev.initial_state())
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev._alloc_history(10 ** 9)                    # no snapshots inside the timed attempts
+    from thermca_b200 import _cabi as _cb
+    _cb.check(dev.lib.tc_rk_begin(dev._handle, 0, 0.0, 1.0e9, 1e-3, 1e-6, 0.0, 0.0))
+    _cb.check(dev.lib.tc_rk_advance(dev._handle, 8, 8))
+    sync()
+    r0.record(dev.stream)
+    _cb.check(dev.lib.tc_rk_advance(dev._handle, 40, 40))
+    r1.record(dev.stream)
+    sync()
+    rk_ms = r0.elapsed_time(r1) / 40
+    rk_info = dev.info()
+    rk45 = {"ms_per_attempt": rk_ms, "dof_attempts_per_s": n / (rk_ms * 1e-3), "rhs_per_attempt": 6,
+            "accepted": rk_info["accepted"], "rejected": rk_info["rejected"], "t_reached_s": rk_info["t"],
+            "algorithmic_gbs": (6 * (nnz * 12 + n * 20) + n * 8 * 44) / (rk_ms * 1e-3) / 1e9}
+
     cpu = cpu_theta_baseline(args.cpu_dof, 2, 1, os.cpu_count() or 1) if not args.no_cpu else None
     line = {
         "metric": "DOF*steps/s (implicit theta-PCG step, full FE cuboid)", "value": value, "unit": "DOF*steps/s",
@@ -241,6 +260,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "DOF*steps/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
                 "steps": e2e_steps},
         "gpu_launches": tm["launches"],
+        "rk45_explicit": rk45,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "tc_pcg_coop_kernel", "peak_kind": peak_kind,
                      "ms_per_launch": pcg_ms_per_launch, "iters_per_launch": iters_per_solve,
