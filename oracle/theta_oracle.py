@@ -39,10 +39,36 @@ class _TorchCsr:
         return (self.A @ self.torch.from_numpy(x)).numpy()
 
 
+def _c_omp_steps(A, mass, b, y, nsteps, h, theta, rtol, maxit, threads):
+    """oracle/c/theta_cg_omp.c through ctypes (all host threads)."""
+    import ctypes as C
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from build_c import build
+    lib = C.CDLL(build())
+    lib.theta_cg_steps.restype = C.c_int64
+    n = A.shape[0]
+    ip, ix = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    a = np.ascontiguousarray(A.data)
+    adiag = np.ascontiguousarray(A.diagonal())
+    mass = np.ascontiguousarray(mass); b = np.ascontiguousarray(b)
+    yo = np.array(y, dtype=np.float64)
+    work = np.empty(6 * n)
+    ptr = lambda v: v.ctypes.data_as(C.c_void_p)
+    t0 = time.perf_counter()
+    iters = lib.theta_cg_steps(C.c_int64(n), ptr(ip), ptr(ix), ptr(a), ptr(mass), ptr(adiag), ptr(b), ptr(yo),
+                               C.c_int32(nsteps), C.c_double(h), C.c_double(theta), C.c_double(rtol),
+                               C.c_int32(maxit), ptr(work), C.c_int32(threads))
+    return yo, int(iters), time.perf_counter() - t0
+
+
 def theta_cg_steps(A, mass, b, y, nsteps, h, theta=0.5, rtol=1e-8, maxit=2000, backend="scipy", threads=1):
     """``nsteps`` theta steps of y' = b - A y with Jacobi-PCG on mass*(I + theta h A).
     Returns (y, total CG iterations, seconds)."""
     A = sp.csr_matrix(A)
+    if backend == "c_omp":
+        return _c_omp_steps(A, mass, b, y, nsteps, h, theta, rtol, maxit, threads)
     matvec = _TorchCsr(A, threads) if backend == "torch" else (lambda x: A @ x)
     shift = theta * h
     adiag = A.diagonal()

@@ -65,3 +65,27 @@ def test_cutting_disc_reference_run(golden):
     res, probe = ex["result"], ex["probe"]
     outer = res["net_temps"][:, int(probe["outer"])]
     assert outer[0] == 20.0 and outer[-1] > 80.0 and np.all(np.diff(outer) > -1e-9)
+
+
+def test_theta_oracle_backends_agree():
+    """numpy / C-OpenMP ports of the implicit step agree with the direct-solver restatement."""
+    import scipy.sparse as sp
+    from thermca_b200.synth import cuboid_spec
+    from theta_oracle import theta_cg_steps, theta_step_direct
+    spec = cuboid_spec(5, 7, 3, jitter=0.15)
+    p = spec["ffe"][0]
+    n = int(p["dof"])
+    A = sp.csr_matrix((p["A_data"], p["A_body"]["indices"], p["A_body"]["indptr"]), shape=(n, n))
+    mass = 1.0 / p["M_inv"]
+    b = np.zeros(n)
+    for s, fl in enumerate([1000.0 / p["surf_areas"][0], 200.0]):
+        b[p["B_idx"][s]] += p["B_val"][s] * fl
+    y0 = np.full(n, 20.0)
+    y_np, it_np, _ = theta_cg_steps(A, mass, b, y0, 3, 2.0, rtol=1e-13)
+    y_c, it_c, _ = theta_cg_steps(A, mass, b, y0, 3, 2.0, rtol=1e-13, backend="c_omp", threads=2)
+    y_d = y0.copy()
+    for _ in range(3):
+        y_d = theta_step_direct(A, b - A @ y_d, y_d, 2.0, 0.5)
+    assert it_np == it_c
+    assert np.allclose(y_np, y_c, rtol=1e-13)
+    assert np.allclose(y_np, y_d, rtol=1e-10)
