@@ -29,6 +29,7 @@ struct TcDistK {
     const double *b, *mass, *adiag;
     double *y_ext, *p_ext;                // [H | n | H]
     double *x, *r, *q, *dinv;
+    double *pdir, *sdir;                  // single-reduction CG only: search direction p and s = P p
     double* partial;                      // 4 banks
     double* peer_y[2]; double* peer_p[2]; // neighbours' extended vectors (peer memory)
     int* peer_hflag[2];                   // neighbours' halo flags
@@ -329,12 +330,148 @@ tc_dist_theta_kernel(TcDistK S) {
     }
 }
 
+
+// ---- single-reduction variant (Chronopoulos & Gear 1989) ----------------------------------------
+// Classic PCG needs two global reductions per iteration (p.Pp, then r.z); across GPUs each one is a
+// NVLink round trip plus the skew between ranks.  With s = P p kept by recurrence,
+//   u = D^-1 r,  w = P u,  gamma = r.u,  delta = w.u           (ONE reduction: gamma, delta, r.r)
+//   beta = gamma/gamma_old,  alpha = gamma / (delta - beta*gamma/alpha_old)
+//   p = u + beta p,  s = w + beta s,  x += alpha p,  r -= alpha s
+// one allreduce and two grid barriers per iteration remain (classic: two and three), for about the same
+// HBM traffic.  The gathered vector (with halo) is u; it is pushed to the neighbours from the vector phase.
+template <int MB>
+__global__ void __launch_bounds__(TC_DIST_THREADS, MB)
+tc_dist_theta_cgcg_kernel(TcDistK S) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    const int G = gridDim.x, n = S.n, H = S.H;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    int rseq = S.state[0], hseq = S.state[1];
+    PROF_INIT();
+    const double shift = S.theta * S.h;
+    const int HP = S.HP;
+    const double* y_g = S.y_ext + HP - S.row_begin;
+    const double* u_g = S.p_ext + HP - S.row_begin;
+    double* y_loc = S.y_ext + HP;
+    double* u_loc = S.p_ext + HP;
+    double* const u_lo = S.peer_p[0];
+    double* const u_hi = S.peer_p[1];
+    double* w = S.q;
+    const int nsl = S.A.nslices;
+    const int nb_lo = S.peer_y[0] ? min(nsl, (H + 31) / 32) : 0;
+    const int nb_hi = S.peer_y[1] ? min(nsl - nb_lo, (H + 31) / 32 + 1) : 0;
+
+    halo_post(S, S.y_ext, S.peer_y, ++hseq);
+    slab_spmv<SPMV_B>(S, y_g, S.q, S.b, 0.0, nb_lo, nb_hi, hseq);
+    grid.sync();
+    double g_l = 0.0, bb_l = 0.0;
+    for (int i = gtid; i < n; i += gsz) {
+        const double m = S.mass[i];
+        const double bsc = m * S.q[i];
+        const double d = 1.0 / (m * (1.0 + shift * S.adiag[i]));
+        const double u = d * bsc;
+        S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; u_loc[i] = u; S.pdir[i] = 0.0; S.sdir[i] = 0.0;
+        g_l += bsc * u; bb_l += bsc * bsc;
+        bool remote = false;
+        if (u_lo && i < H) { u_lo[(long long)HP + S.n_lo + i] = u; remote = true; }
+        if (u_hi && i >= n - H) { u_hi[HP - H + (i - (n - H))] = u; remote = true; }
+        if (remote) __threadfence_system();
+    }
+    {
+        const double r0 = block_sum(g_l, sh), r1 = block_sum(bb_l, sh);
+        if (threadIdx.x == 0) { S.partial[blockIdx.x] = r0; S.partial[3 * TC_MAX_PARTIALS + blockIdx.x] = r1; }
+    }
+    grid.sync();
+    // partial banks: gamma -> bank rp (0/1), r.r -> bank 3+rp (3/4), delta -> bank 2.  gamma / r.r
+    // alternate by iteration parity: a fast block may already publish iteration i+1 while a slow one
+    // is still summing iteration i.
+    int rp = 0;
+    double red[3];
+    double gamma = 0.0, alpha = 0.0, beta = 0.0, tol2 = 0.0;
+    int it = 0;
+    bool first = true;
+    for (;;) {
+        PROF(0);
+        // ---- w = P u (halo of u was fenced before the barrier above) -------------------------
+        ++hseq;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (u_lo) st_release_sys(S.peer_hflag[0] + 1, hseq);
+            if (u_hi) st_release_sys(S.peer_hflag[1] + 0, hseq);
+        }
+        const double dot = slab_spmv<SPMV_SHIFT>(S, u_g, w, nullptr, shift, nb_lo, nb_hi, hseq);
+        PROF(2);
+        const double bs = block_sum(dot, sh);
+        if (threadIdx.x == 0) S.partial[2 * TC_MAX_PARTIALS + blockIdx.x] = bs;
+        PROF(4);
+        grid.sync();
+        PROF(5);
+        red[0] = bank_sum(S.partial + rp * TC_MAX_PARTIALS, G, sh);          // gamma = r.u
+        red[1] = bank_sum(S.partial + 2 * TC_MAX_PARTIALS, G, sh);           // delta = w.u
+        red[2] = bank_sum(S.partial + (3 + rp) * TC_MAX_PARTIALS, G, sh);    // r.r
+        allreduce3(S, red, ++rseq);
+        PROF(6);
+        if (first) {
+            tol2 = S.rtol * S.rtol * red[2];
+            if (!(red[2] > 0.0)) break;
+            beta = 0.0; alpha = red[0] / red[1];
+            first = false;
+        } else {
+            if (!(red[2] > tol2) || it >= S.maxit || *((volatile int*)(S.state + 4))) break;
+            beta = red[0] / gamma;
+            alpha = red[0] / (red[1] - beta * red[0] / alpha);
+        }
+        gamma = red[0];
+        // ---- vector phase -----------------------------------------------------------------------
+        double gn = 0.0, rr = 0.0;
+        for (int i = gtid; i < n; i += gsz) {
+            const double pn = u_loc[i] + beta * S.pdir[i];
+            const double sn = w[i] + beta * S.sdir[i];
+            S.pdir[i] = pn; S.sdir[i] = sn;
+            S.x[i] += alpha * pn;
+            const double ri = S.r[i] - alpha * sn;
+            S.r[i] = ri;
+            const double un = S.dinv[i] * ri;
+            u_loc[i] = un;
+            gn += ri * un; rr += ri * ri;
+            bool remote = false;
+            if (u_lo && i < H) { u_lo[(long long)HP + S.n_lo + i] = un; remote = true; }
+            if (u_hi && i >= n - H) { u_hi[HP - H + (i - (n - H))] = un; remote = true; }
+            if (remote) __threadfence_system();
+        }
+        const double r0 = block_sum(gn, sh), r1 = block_sum(rr, sh);
+        rp ^= 1;
+        if (threadIdx.x == 0) {
+            S.partial[rp * TC_MAX_PARTIALS + blockIdx.x] = r0;
+            S.partial[(3 + rp) * TC_MAX_PARTIALS + blockIdx.x] = r1;
+        }
+        ++it;
+        PROF(7);
+        grid.sync();
+        PROF(8);
+    }
+    for (int i = gtid; i < n; i += gsz) y_loc[i] += S.h * S.x[i];
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.state[0] = rseq; S.state[1] = hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
+    }
+}
+
 // ---- host ------------------------------------------------------------------------------------
 static void* dist_fn() {
     static int v = -1;
+    static int classic = -1;
     if (v < 0) {
         const char* e = getenv("TC_PCG_OCC");
         v = e ? atoi(e) : 8;
+        const char* a = getenv("TC_DIST_CG");                 // "classic" selects two-reduction PCG
+        classic = (a && a[0] == 'c' && a[1] == 'l') ? 1 : 0;
+    }
+    if (!classic) {
+        switch (v) {
+            case 5: return (void*)tc_dist_theta_cgcg_kernel<5>;
+            case 6: return (void*)tc_dist_theta_cgcg_kernel<6>;
+            default: return (void*)tc_dist_theta_cgcg_kernel<8>;
+        }
     }
     switch (v) {
         case 5: return (void*)tc_dist_theta_kernel<5>;
@@ -353,6 +490,7 @@ struct tc_dist {
     char* peer[TC_MAX_WORLD];
     long long peer_n[TC_MAX_WORLD];
     double *x = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr, *partial = nullptr;
+    double *pdir = nullptr, *sdir = nullptr;
     int* state = nullptr;
     unsigned long long* prof = nullptr;
     TcDistK K;
@@ -382,7 +520,8 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     const size_t nb = sizeof(double) * (size_t)n_loc;
     TC_CUDA(cudaMalloc(&d->x, nb)); TC_CUDA(cudaMalloc(&d->r, nb));
     TC_CUDA(cudaMalloc(&d->q, nb)); TC_CUDA(cudaMalloc(&d->dinv, nb));
-    TC_CUDA(cudaMalloc(&d->partial, sizeof(double) * 4 * TC_MAX_PARTIALS));
+    TC_CUDA(cudaMalloc(&d->pdir, nb)); TC_CUDA(cudaMalloc(&d->sdir, nb));
+    TC_CUDA(cudaMalloc(&d->partial, sizeof(double) * 6 * TC_MAX_PARTIALS));
     TC_CUDA(cudaMalloc(&d->state, sizeof(int) * 16));
     TC_CUDA(cudaMemset(d->state, 0, sizeof(int) * 16));
     TC_CUDA(cudaMalloc(&d->prof, sizeof(unsigned long long) * 32));
@@ -430,6 +569,7 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
         K.y_ext = alt; K.p_ext = (double*)((char*)alt + align_up((size_t)(d->n + 2 * d->HP) * sizeof(double), 256));
     }
     K.x = d->x; K.r = d->r; K.q = d->q; K.dinv = d->dinv; K.partial = d->partial;
+    K.pdir = d->pdir; K.sdir = d->sdir;
     const int lo = d->rank - 1, hi = d->rank + 1;
     // peers share my buffer layout except for their own n: offsets depend on n_peer
     auto ext_bytes = [&](int w) { return align_up((size_t)(d->peer_n[w] + 2 * d->HP) * sizeof(double), 256); };
@@ -510,6 +650,7 @@ extern "C" int tc_dist_destroy(tc_dist* d) {
     for (int w = 0; w < d->world; ++w)
         if (w != d->rank && d->peer[w]) cudaIpcCloseMemHandle(d->peer[w]);
     cudaFree(d->comm); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
+    cudaFree(d->pdir); cudaFree(d->sdir);
     cudaFree(d->partial); cudaFree(d->state); cudaFree(d->prof);
     delete d;
     return 0;
