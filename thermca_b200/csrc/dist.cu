@@ -463,8 +463,11 @@ static void* dist_fn() {
     if (v < 0) {
         const char* e = getenv("TC_PCG_OCC");
         v = e ? atoi(e) : 8;
-        const char* a = getenv("TC_DIST_CG");                 // "classic" selects two-reduction PCG
-        classic = (a && a[0] == 'c' && a[1] == 'l') ? 1 : 0;
+        // measured on 2 and 8 B200 (profiles/README.md): the single-reduction variant saves ~40 % of the
+        // reduction wait but its fused vector phase streams 12 arrays and runs ~25 % slower, net -3..-8 %;
+        // two-reduction PCG stays the default, TC_DIST_CG=cgcg selects the other one
+        const char* a = getenv("TC_DIST_CG");
+        classic = (a && a[0] == 'c' && a[1] == 'g') ? 0 : 1;
     }
     if (!classic) {
         switch (v) {
