@@ -105,3 +105,22 @@ def test_unknown_method_and_untraceable_callable(dropin):
         CondLink(a, b, cond=1.0)
     with pytest.raises(ValueError):
         Network(model2).sim([0, 1.0], method="NOPE", progress_bar=False)
+
+
+def test_linear_diag_search_is_result_identical(dropin):
+    import scipy.sparse as sp
+    from thermca._utils.sparse import coo_diag_data_idxs
+    from thermca_b200.solver import linear_coo_diag_data_idxs
+    rng = np.random.default_rng(0)
+    m = sp.random(60, 60, density=0.1, random_state=2, format="csr") + sp.eye(60, format="csr")
+    m = sp.csr_matrix(m)
+    m[7, 7] = 0.0
+    m.eliminate_zeros()                       # a row without a stored diagonal
+    coo = m.tocoo()
+    a = coo_diag_data_idxs(m.shape, m.data.shape, coo.row, coo.col)
+    b = linear_coo_diag_data_idxs(m.shape, m.data.shape, coo.row, coo.col)
+    assert np.array_equal(np.asarray(a), b)
+    # and a model builds through the patched constructors
+    import ref_models
+    net, kw = ref_models.kuhn_cuboid()
+    assert net._ffe_ios[0].fe_sys.dof == 364

@@ -94,15 +94,43 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
 
 
 _original = None
+_original_diag = {}
 
 
-def install():
-    """Route ``Network.sim`` through the device solver (thermca/network.py:978)."""
+def linear_coo_diag_data_idxs(shape, data_shape, row, col):
+    """Result-identical, O(nnz) replacement of ``thermca._utils.sparse.coo_diag_data_idxs``
+    (thermca/_utils/sparse.py:13-22 is O(rows*nnz): 43 min at 1 M DOF).  First
+    stored diagonal entry per row, rows in ascending order, rows without a diagonal skipped."""
+    row = np.asarray(row)
+    col = np.asarray(col)
+    hit = np.nonzero(row == col)[0]
+    if hit.size == 0:
+        return np.array([], dtype=np.int64)
+    r = row[hit]
+    order = np.lexsort((hit, r))
+    r, hit = r[order], hit[order]
+    first = np.concatenate([[True], r[1:] != r[:-1]])
+    return hit[first].astype(np.int64)
+
+
+def install(fix_quadratic_build=True):
+    """Route ``Network.sim`` through the device solver (thermca/network.py:978).
+
+    ``fix_quadratic_build`` also swaps the quadratic diagonal search used by ``FESystem.__init__`` /
+    ``LPSystem.__init__`` (thermca/fem/fe_system.py:138-140, thermca/lpm/lp_system.py:58-60) for the
+    linear-time equivalent, so that 10^5..10^6-DOF ``FEPart`` models can be built at all."""
     global _original
     import thermca.solver as ref_solver
     if _original is None:
         _original = ref_solver.transient_solution
     ref_solver.transient_solution = transient_solution
+    if fix_quadratic_build:
+        import thermca.fem.fe_system as fes
+        import thermca.lpm.lp_system as lps
+        for mod in (fes, lps):
+            if mod not in _original_diag:
+                _original_diag[mod] = mod.coo_diag_data_idxs
+            mod.coo_diag_data_idxs = linear_coo_diag_data_idxs
     return _original
 
 
@@ -112,3 +140,6 @@ def uninstall():
         import thermca.solver as ref_solver
         ref_solver.transient_solution = _original
         _original = None
+    for mod, fn in list(_original_diag.items()):
+        mod.coo_diag_data_idxs = fn
+        del _original_diag[mod]
