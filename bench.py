@@ -183,7 +183,7 @@ def run_ours(args):
 
     nx, ny, nz = cuboid_dims(args.dof)
     spec = device_cuboid_spec(nx, ny, nz, heat=HEAT, film=FILM, env_temp=T_ENV)
-    dev = DeviceSolver(spec)
+    dev = DeviceSolver(spec, use_col16=os.environ.get("TC_COL16", "1") != "0")
     n = dev.n_state
     op = spec["ffe"][0]["sell"]
     nnz = int(torch.count_nonzero(op["val"]).item())

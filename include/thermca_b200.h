@@ -49,6 +49,7 @@ typedef struct {
     int64_t y_off;                  /* offset of the part in the stacked state */
     const int64_t* slice_ptr;       /* dev: SELL-32 */
     const int32_t* col;             /* dev */
+    const int16_t* col16;           /* dev, optional: col - row when the band fits 16 bits (else NULL) */
     double* val;                    /* dev: mutable (film coefficients live on the diagonal) */
     const double* mass;             /* dev: M_diag = 1 / M_inv */
     double* adiag;                  /* dev: dense copy of diag(A) */
@@ -140,8 +141,8 @@ int tc_pcg_stats(tc_handle h, int64_t* stats4);
 /* ---- stand-alone kernels (parity hooks and micro-benchmarks) ----------------------------- */
 /* y = -A x (mode 0), y = b - A x (mode 1), y = mass*(x + shift*A x) (mode 2) on a SELL-32 operator */
 int tc_sell_spmv(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, const int64_t* slice_ptr,
-                 const int32_t* col, const double* val, const double* x, double* y, const double* b,
-                 const double* mass, double shift, int32_t grid_blocks);
+                 const int32_t* col, const int16_t* col16, const double* val, const double* x, double* y,
+                 const double* b, const double* mass, double shift, int32_t grid_blocks);
 /* Jacobi-PCG on (M + shift K): solves mass*(I + shift*A) x = mass*rhs; returns iterations in *iters (host) */
 int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, const int64_t* slice_ptr,
                  const int32_t* col, const double* val, const double* mass, const double* adiag,
@@ -157,7 +158,8 @@ int tc_dist_create(tc_dist** out, void* cuda_stream, int32_t rank, int32_t world
 int tc_dist_ipc_handle(tc_dist* d, void* handle64);
 int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_n);
 int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
-                         const double* val, const double* mass, const double* adiag, const double* b);
+                         const int16_t* col16, const double* val, const double* mass, const double* adiag,
+                         const double* b);
 int tc_dist_set_state(tc_dist* d, const double* y_local_dev);
 int tc_dist_get_state(tc_dist* d, double* y_local_dev);
 int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, double h, double rtol, int32_t maxit);
@@ -180,7 +182,7 @@ int tc_synth_cuboid_counts(int32_t nx, int32_t ny, int32_t nz, int64_t* n_rows, 
                            int64_t* sell_entries);
 int tc_synth_cuboid(void* cuda_stream, int32_t nx, int32_t ny, int32_t nz, double lx, double ly, double lz,
                     double jitter, double condy, double vol_capy, int64_t row_begin, int64_t row_end,
-                    int64_t* slice_ptr, int32_t* col, double* val, double* mass, double* adiag,
+                    int64_t* slice_ptr, int32_t* col, int16_t* col16, double* val, double* mass, double* adiag,
                     double* q_bottom, double* q_upper);
 
 #ifdef __cplusplus

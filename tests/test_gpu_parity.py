@@ -19,7 +19,7 @@ def torch_cuda():
     return torch
 
 
-def _spmv(torch, lib, m, x, mode=0, b=None, mass=None, shift=0.0):
+def _spmv(torch, lib, m, x, mode=0, b=None, mass=None, shift=0.0, col16=False):
     from thermca_b200 import _cabi
     from thermca_b200.device import csr_to_sell
     s = csr_to_sell(m.indptr, m.indices, m.data)
@@ -30,9 +30,12 @@ def _spmv(torch, lib, m, x, mode=0, b=None, mass=None, shift=0.0):
     bd = torch.from_numpy(b).to(dev) if b is not None else None
     md = torch.from_numpy(mass).to(dev) if mass is not None else None
     p = lambda a: C.c_void_p(a.data_ptr()) if a is not None else C.c_void_p(0)
+    c16 = None
+    if col16 and s["col16"] is not None:
+        c16 = torch.from_numpy(s["col16"]).to(dev)
     _cabi.check(lib.tc_sell_spmv(C.c_void_p(torch.cuda.current_stream().cuda_stream), mode, m.shape[0],
-                                 s["nslices"], p(t["slice_ptr"]), p(t["col"]), p(t["val"]), p(xd), p(yd), p(bd),
-                                 p(md), float(shift), 0))
+                                 s["nslices"], p(t["slice_ptr"]), p(t["col"]), p(c16), p(t["val"]), p(xd), p(yd),
+                                 p(bd), p(md), float(shift), 0))
     torch.cuda.synchronize()
     return yd.cpu().numpy()
 
@@ -54,6 +57,8 @@ def test_spmv_bit_exact_vs_scipy(torch_cuda, golden):
     for m in mats:
         x = rng.standard_normal(m.shape[1])
         y = _spmv(torch_cuda, lib, m, x, mode=0)
+        assert np.array_equal(y, -(m @ x))
+        y = _spmv(torch_cuda, lib, m, x, mode=0, col16=True)          # 16-bit relative columns: same bits
         assert np.array_equal(y, -(m @ x))
         b = rng.standard_normal(m.shape[0])
         y = _spmv(torch_cuda, lib, m, x, mode=1, b=b)

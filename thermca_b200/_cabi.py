@@ -25,7 +25,7 @@ class NetDesc(C.Structure):
 
 
 class FfeDesc(C.Structure):
-    _fields_ = [("n", i32), ("nslices", i32), ("y_off", i64), ("slice_ptr", vp), ("col", vp), ("val", vp),
+    _fields_ = [("n", i32), ("nslices", i32), ("y_off", i64), ("slice_ptr", vp), ("col", vp), ("col16", vp), ("val", vp),
                 ("mass", vp), ("adiag", vp),
                 ("load_nrows", i32), ("load_row", vp), ("load_start", vp), ("load_surf", vp), ("load_bval", vp),
                 ("fd_nrows", i32), ("fd_pos", vp), ("fd_row", vp), ("fd_abody", vp), ("fd_start", vp),
@@ -70,12 +70,12 @@ EXPORTS = {
     "tc_timing": (i32, [vp, i32, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
     "tc_pcg_profile": (i32, [vp, C.POINTER(C.c_uint64)]),
     "tc_pcg_stats": (i32, [vp, C.POINTER(i64)]),
-    "tc_sell_spmv": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, i32]),
+    "tc_sell_spmv": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32]),
     "tc_pcg_solve": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32, C.POINTER(i32)]),
     "tc_dist_create": (i32, [C.POINTER(vp), vp, i32, i32, i64, i64, i64]),
     "tc_dist_ipc_handle": (i32, [vp, vp]),
     "tc_dist_open_peers": (i32, [vp, vp, C.POINTER(i64)]),
-    "tc_dist_set_operator": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
+    "tc_dist_set_operator": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
     "tc_dist_set_state": (i32, [vp, vp]),
     "tc_dist_get_state": (i32, [vp, vp]),
     "tc_dist_theta_steps": (i32, [vp, i32, f64, f64, f64, i32]),
@@ -86,7 +86,7 @@ EXPORTS = {
                                  f64, f64, i32, i32]),
     "tc_mor_batch_work_doubles": (i64, [i32, i32, i32, i32]),
     "tc_synth_cuboid_counts": (i32, [i32, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
-    "tc_synth_cuboid": (i32, [vp, i32, i32, i32, f64, f64, f64, f64, f64, f64, i64, i64, vp, vp, vp, vp,
+    "tc_synth_cuboid": (i32, [vp, i32, i32, i32, f64, f64, f64, f64, f64, f64, i64, i64, vp, vp, vp, vp, vp,
                               vp, vp, vp]),
 }
 

@@ -32,6 +32,11 @@ __device__ __forceinline__ double ld_stream_f64(const double* p) {
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ int ld_stream_s16(const short* p) {
+    short v;
+    asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=h"(v) : "l"(p));
+    return (int)v;
+}
 __device__ __forceinline__ int ld_stream_s32(const int* p) {
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));

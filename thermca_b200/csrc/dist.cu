@@ -163,8 +163,31 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xg, 
         const long long base = A.slice_ptr[s];
         const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
         const double* v = A.val + base + lane;
-        const int* c = A.col + base + lane;
         double sum = 0.0;
+        if (A.col16) {
+            const short* c = A.col16 + base + lane;
+            const double* xr0 = xg + (S.row_begin + s * 32 + lane);
+            if (!boundary) {
+                int k = 0;
+                for (; k + 4 <= width; k += 4) {
+                    const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
+                    const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
+                    const int c0 = ld_stream_s16(c + 32 * (k + 0)), c1 = ld_stream_s16(c + 32 * (k + 1));
+                    const int c2 = ld_stream_s16(c + 32 * (k + 2)), c3 = ld_stream_s16(c + 32 * (k + 3));
+                    const double x0 = tc_ld_x<0>(xr0 + c0), x1 = tc_ld_x<0>(xr0 + c1), x2 = tc_ld_x<0>(xr0 + c2), x3 = tc_ld_x<0>(xr0 + c3);
+                    sum = __dadd_rn(sum, __dmul_rn(v0, x0));
+                    sum = __dadd_rn(sum, __dmul_rn(v1, x1));
+                    sum = __dadd_rn(sum, __dmul_rn(v2, x2));
+                    sum = __dadd_rn(sum, __dmul_rn(v3, x3));
+                }
+                for (; k < width; ++k)
+                    sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xr0 + ld_stream_s16(c + 32 * k))));
+            } else {
+                for (int k = 0; k < width; ++k)
+                    sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<2>(xr0 + ld_stream_s16(c + 32 * k))));
+            }
+        } else {
+        const int* c = A.col + base + lane;
         if (!boundary) {
             int k = 0;
             for (; k + 4 <= width; k += 4) {
@@ -183,6 +206,7 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xg, 
         } else {
             for (int k = 0; k < width; ++k)
                 sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<2>(xg + ld_stream_s32(c + 32 * k))));
+        }
         }
         const int row = s * 32 + lane;
         if (row < A.n) {
@@ -558,10 +582,10 @@ extern "C" int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t
 }
 
 extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
-                                    const double* val, const double* mass, const double* adiag,
-                                    const double* b) {
+                                    const int16_t* col16, const double* val, const double* mass,
+                                    const double* adiag, const double* b) {
     TcDistK& K = d->K;
-    K.A = TcSell{(int)d->n, nslices, (const long long*)slice_ptr, col, val};
+    K.A = TcSell{(int)d->n, nslices, (const long long*)slice_ptr, col, val, (const short*)col16};
     K.row_begin = d->row_begin; K.n = (int)d->n; K.H = (int)d->H; K.HP = (int)d->HP; K.rank = d->rank; K.world = d->world;
     K.b = b; K.mass = mass; K.adiag = adiag;
     K.y_ext = (double*)(d->comm + d->off_y); K.p_ext = (double*)(d->comm + d->off_p);

@@ -365,7 +365,7 @@ extern "C" int tc_add_ffe_part(tc_handle s, const tc_ffe_desc* d) {
     TC_CHECK(s && d && !s->finalized, "bad state");
     FfePart p{};
     p.d = *d;
-    p.A = TcSell{d->n, d->nslices, (const long long*)d->slice_ptr, d->col, d->val};
+    p.A = TcSell{d->n, d->nslices, (const long long*)d->slice_ptr, d->col, d->val, (const short*)d->col16};
     p.load = TcSurfLoad{d->load_nrows, d->load_row, d->load_start, d->load_surf, d->load_bval};
     p.fdiag = TcFilmDiag{d->fd_nrows, (const long long*)d->fd_pos, d->fd_row, d->fd_abody, d->fd_start,
                          d->fd_film, d->fd_adata};
@@ -377,7 +377,7 @@ extern "C" int tc_add_lp_part(tc_handle s, const tc_lp_desc* d) {
     LpPart p{};
     p.d = *d;
     p.A = TcSell{d->n, d->nslices, (const long long*)(s->net.iarena + d->slice_ptr_ioff64),
-                 s->net.iarena + d->col_ioff, s->net.darena + d->val_doff};
+                 s->net.iarena + d->col_ioff, s->net.darena + d->val_doff, nullptr};
     p.b = s->net.darena + d->b_doff;
     s->lp.push_back(p);
     return 0;
@@ -905,11 +905,11 @@ extern "C" int tc_pcg_stats(tc_handle s, int64_t* stats4) {
 
 // ---- stand-alone entry points --------------------------------------------------------------------
 extern "C" int tc_sell_spmv(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
-                            const int64_t* slice_ptr, const int32_t* col, const double* val,
+                            const int64_t* slice_ptr, const int32_t* col, const int16_t* col16, const double* val,
                             const double* x, double* y, const double* b, const double* mass, double shift,
                             int32_t grid_blocks) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    TcSell A{n, nslices, (const long long*)slice_ptr, col, val};
+    TcSell A{n, nslices, (const long long*)slice_ptr, col, val, (const short*)col16};
     int g = grid_blocks > 0 ? grid_blocks : grid_for(nslices, TC_SPMV_THREADS / 32, 148 * 8);
     static double* one_ctrl = nullptr;      // ctrl[1] = 1 so that shift == coef
     static double* scratch = nullptr;
@@ -937,7 +937,7 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     tc_solver tmp;
     tmp.stream = (cudaStream_t)cuda_stream;
     TcPcg P{};
-    P.A = TcSell{n, nslices, (const long long*)slice_ptr, col, val};
+    P.A = TcSell{n, nslices, (const long long*)slice_ptr, col, val, nullptr};
     double* ws = nullptr; double* aux = nullptr; int* isc = nullptr;
     TC_CUDA(cudaMalloc(&ws, sizeof(double) * 4 * (size_t)n));
     TC_CUDA(cudaMalloc(&aux, sizeof(double) * (4 * TC_MAX_PARTIALS + 16 + 4)));

@@ -86,7 +86,7 @@ __device__ double face_load(const SynthGeo& g, int axis, int fixed, int i, int j
 
 __global__ void tc_synth_cuboid_kernel(SynthGeo g, const int* __restrict__ order27,
                                        const long long* __restrict__ off15,
-                                       int* __restrict__ col, double* __restrict__ val,
+                                       int* __restrict__ col, short* __restrict__ col16, double* __restrict__ val,
                                        double* __restrict__ mass, double* __restrict__ adiag,
                                        double* __restrict__ q_bottom, double* __restrict__ q_upper) {
     const long long nloc = g.row_end - g.row_begin;
@@ -96,7 +96,10 @@ __global__ void tc_synth_cuboid_kernel(SynthGeo g, const int* __restrict__ order
         const long long row = g.row_begin + rl;
         if (rl >= nloc) {        // padding rows of the last slice: zeros pointing at an owned row
             const long long pb = (rl >> 5) * (32LL * 15) + (rl & 31);
-            for (int s = 0; s < 15; ++s) { col[pb + 32LL * s] = (int)g.row_begin; val[pb + 32LL * s] = 0.0; }
+            for (int s = 0; s < 15; ++s) {          // point at the last owned row (keeps col - row small)
+                col[pb + 32LL * s] = (int)(g.row_end - 1); val[pb + 32LL * s] = 0.0;
+                if (col16) col16[pb + 32LL * s] = (short)(g.row_end - 1 - row);
+            }
             continue;
         }
         const int k = (int)(row % (g.nz + 1));
@@ -169,6 +172,7 @@ __global__ void tc_synth_cuboid_kernel(SynthGeo g, const int* __restrict__ order
                                 k + dz >= 0 && k + dz <= g.nz;
             const double a = inside ? minv * (g.condy * acc[s]) : 0.0;
             col[base + 32LL * s] = inside ? (int)c : (int)row;
+            if (col16) col16[base + 32LL * s] = inside ? (short)off15[s] : (short)0;
             val[base + 32LL * s] = a;
             if (dx == 0 && dy == 0 && dz == 0) adiag[rl] = a;
         }
@@ -201,8 +205,8 @@ extern "C" int tc_synth_cuboid_counts(int32_t nx, int32_t ny, int32_t nz, int64_
 
 extern "C" int tc_synth_cuboid(void* cuda_stream, int32_t nx, int32_t ny, int32_t nz, double lx, double ly,
                                double lz, double jitter, double condy, double vol_capy, int64_t row_begin,
-                               int64_t row_end, int64_t* slice_ptr, int32_t* col, double* val, double* mass,
-                               double* adiag, double* q_bottom, double* q_upper) {
+                               int64_t row_end, int64_t* slice_ptr, int32_t* col, int16_t* col16, double* val,
+                               double* mass, double* adiag, double* q_bottom, double* q_upper) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // the 15 admissible neighbour offsets, ordered by linear index offset (ascending column)
     struct Off { long long lin; int dx, dy, dz; };
@@ -239,7 +243,10 @@ extern "C" int tc_synth_cuboid(void* cuda_stream, int32_t nx, int32_t ny, int32_
     long long gb = (nsl * 32 + 127) / 128;
     if (gb > 148 * 16) gb = 148 * 16;
     if (gb < 1) gb = 1;
-    tc_synth_cuboid_kernel<<<(int)gb, 128, 0, st>>>(g, d_order, d_off, col, val, mass, adiag, q_bottom, q_upper);
+    // the band of the Kuhn cuboid is one y-layer: relative columns fit 16 bits iff that is < 2^15
+    const long long band = (long long)(nx + 1) * (nz + 1) + (nz + 1) + 1;
+    if (band >= 32768) col16 = nullptr;
+    tc_synth_cuboid_kernel<<<(int)gb, 128, 0, st>>>(g, d_order, d_off, col, (short*)col16, val, mass, adiag, q_bottom, q_upper);
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_order); cudaFree(d_off);

@@ -61,7 +61,17 @@ def csr_to_sell(indptr, indices, data, n=None):
         col[:] = own
     col[pos] = np.asarray(indices, dtype=np.int32)
     val[pos] = np.asarray(data, dtype=np.float64)
-    return {"slice_ptr": slice_ptr, "col": col, "val": val, "pos": pos, "n": n, "nslices": nsl}
+    # compressed columns: col - row, when the band fits 16 bits (padding of rows past n points at row n-1)
+    col16 = None
+    if total:
+        own_all = sl_of * 32 + lane
+        ref_col = col.astype(np.int64)
+        ref_col[own_all >= n] = n - 1
+        rel = ref_col - own_all
+        if rel.min() >= -32768 and rel.max() <= 32767:
+            col16 = rel.astype(np.int16)
+            col = ref_col.astype(np.int32)
+    return {"slice_ptr": slice_ptr, "col": col, "col16": col16, "val": val, "pos": pos, "n": n, "nslices": nsl}
 
 
 def csr_diag_positions(indptr, indices):
@@ -124,7 +134,7 @@ class _Arena:
 class DeviceSolver:
     """Owns the device copy of one lowered network and the native solver handle."""
 
-    def __init__(self, spec, device=None, history_bytes=1 << 30):
+    def __init__(self, spec, device=None, history_bytes=1 << 30, use_col16=True):
         torch = _torch()
         self.torch = torch
         self.lib = _cabi.load_library()
@@ -138,6 +148,7 @@ class DeviceSolver:
         self.lp_off, self.ffe_off, self.mor_off, self.n_state = state_offsets(spec)
         self.n_io = self.n_state - self.u
         self.history_bytes = history_bytes
+        self.use_col16 = use_col16            # 16-bit relative column indices when the band allows
         self._handle = _cabi.vp()
         _cabi.check(self.lib.tc_create(C.byref(self._handle), C.c_void_p(self.stream.cuda_stream)))
         self._pack()
@@ -420,6 +431,7 @@ class DeviceSolver:
         fd = _cabi.FfeDesc()
         fd.n, fd.nslices, fd.y_off = n, sell["nslices"], self.ffe_off[k]
         fd.slice_ptr, fd.col, fd.val = self._p(t_sp), self._p(t_col), self._p(t_val)
+        fd.col16 = self._p(None)
         fd.mass, fd.adiag = self._p(t_mx), self._p(t_zero)
         fd.load_nrows, fd.fd_nrows = 0, 0
         fd.films_doff, fd.flux_doff = d["films"], d["flux"]
@@ -442,6 +454,7 @@ class DeviceSolver:
         if "sell" in p:                  # operator already resident on the device (csrc/synth.cu)
             sell = p["sell"]
             t_sp, t_col, t_val = sell["slice_ptr"], sell["col"], sell["val"]
+            t_col16 = sell.get("col16")
             t_mass, t_adiag = sell["mass"], sell["adiag"]
             nslices = int(sell["nslices"])
             pos = None
@@ -449,6 +462,7 @@ class DeviceSolver:
         else:
             sell = csr_to_sell(ab["indptr"], ab["indices"], p["A_data"])
             t_sp, t_col, t_val = self._up(sell["slice_ptr"]), self._up(sell["col"]), self._up(sell["val"])
+            t_col16 = self._up(sell["col16"]) if sell["col16"] is not None else None
             t_mass = self._up(1.0 / np.asarray(p["M_inv"], dtype=np.float64))
             dpos = csr_diag_positions(ab["indptr"], ab["indices"])
             t_adiag = self._up(np.asarray(p["A_data"], dtype=np.float64)[dpos])
@@ -464,6 +478,9 @@ class DeviceSolver:
         fd = _cabi.FfeDesc()
         fd.n, fd.nslices, fd.y_off = n, nslices, self.ffe_off[k]
         fd.slice_ptr, fd.col, fd.val = self._p(t_sp), self._p(t_col), self._p(t_val)
+        fd.col16 = self._p(t_col16 if self.use_col16 else None)
+        if t_col16 is not None:
+            self._keep.append(t_col16)
         fd.mass, fd.adiag = self._p(t_mass), self._p(t_adiag)
         if len(rows):
             urow, start, (surf_s, bval_s) = _group_lists(rows, surf, [surf, bval])

@@ -94,7 +94,9 @@ class DistCuboid:
         self._handles = C.create_string_buffer(handles, len(handles))
         _cabi.check(self.lib.tc_dist_open_peers(self._h, self._handles, peer_n))
         p = lambda t: C.c_void_p(t.data_ptr())
+        c16 = op.get("col16") if os.environ.get("TC_COL16", "1") != "0" else None
         _cabi.check(self.lib.tc_dist_set_operator(self._h, op["nslices"], p(op["slice_ptr"]), p(op["col"]),
+                                                  p(c16) if c16 is not None else C.c_void_p(0),
                                                   p(op["val"]), p(op["mass"]), p(op["adiag"]), p(self.b)))
         self.set_state(torch.full((self.n,), float(init_temp), dtype=torch.float64, device=self.dev))
         dist.barrier()

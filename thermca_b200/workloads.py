@@ -36,6 +36,7 @@ def device_cuboid_operator(nx, ny, nz, lx=0.5, ly=1.0, lz=0.05, jitter=0.15, con
     t = {
         "slice_ptr": torch.empty(nsl + 1, dtype=torch.int64, device=dev),
         "col": torch.empty(nsl * 32 * 15, dtype=torch.int32, device=dev),
+        "col16": torch.empty(nsl * 32 * 15, dtype=torch.int16, device=dev),
         "val": torch.empty(nsl * 32 * 15, dtype=torch.float64, device=dev),
         "mass": torch.empty(nloc, dtype=torch.float64, device=dev),
         "adiag": torch.empty(nloc, dtype=torch.float64, device=dev),
@@ -46,8 +47,10 @@ def device_cuboid_operator(nx, ny, nz, lx=0.5, ly=1.0, lz=0.05, jitter=0.15, con
     p = lambda a: C.c_void_p(a.data_ptr())
     _cabi.check(lib.tc_synth_cuboid(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), nx, ny, nz,
                                     lx, ly, lz, jitter, condy, vol_capy, row_begin, row_end,
-                                    p(t["slice_ptr"]), p(t["col"]), p(t["val"]), p(t["mass"]), p(t["adiag"]),
-                                    p(t["q_bottom"]), p(t["q_upper"])))
+                                    p(t["slice_ptr"]), p(t["col"]), p(t["col16"]), p(t["val"]), p(t["mass"]),
+                                    p(t["adiag"]), p(t["q_bottom"]), p(t["q_upper"])))
+    if (nx + 1) * (nz + 1) + (nz + 1) + 1 >= 32768:
+        t["col16"] = None                       # band too wide for 16-bit relative columns
     t.update({"n": nloc, "nslices": nsl, "n_global": n, "row_begin": row_begin})
     return t
 
