@@ -218,3 +218,74 @@ def test_device_generated_cuboid_runs_like_host_spec(torch_cuda):
     assert len(ra["times"]) == len(rb["times"])
     assert np.allclose(ra["io_temps"][-1], rb["io_temps"][-1], rtol=1e-10)
     a.close(); b.close()
+
+
+def test_history_ring_drains_and_options(torch_cuda, golden):
+    """Many stored steps through a tiny device history ring (forced drains), plus the scipy
+    options the reference forwards (max_step, first_step; thermca/solver.py:362)."""
+    from thermca_b200.device import DeviceSolver
+    from rhs_oracle import integrate
+    spec, ex = golden("coffeecup")
+    ref = ex["result"]
+    dev = DeviceSolver(spec, history_bytes=12 * 8 * (dev_row := 1 + 3 * int(spec["N"]) + 2 * len(spec["rc_data"]) + 7))
+    out = dev.run_rk(0.0, 1200.0, 1e-5, 1e-6, "RK45", attempts_per_poll=4)
+    dev.close()
+    assert dev.capacity < 20 < len(out["times"])
+    assert np.allclose(out["times"], ref["times"], rtol=1e-9)
+    assert np.allclose(out["net_temps"], ref["net_temps"], rtol=1e-9)
+    dev = DeviceSolver(spec)
+    out = dev.run_rk(0.0, 200.0, 1e-4, 1e-6, "RK23", max_step=7.5, first_step=0.25)
+    dev.close()
+    orc = integrate(spec, [0.0, 200.0], 1e-4, 1e-6, "RK23", max_step=7.5, first_step=0.25)
+    assert len(out["times"]) == len(orc["times"]) and np.max(np.diff(out["times"])) <= 7.5 + 1e-12
+    assert np.allclose(out["times"], orc["times"], rtol=1e-9)
+    assert np.allclose(out["net_temps"], orc["net_temps"], rtol=1e-9)
+
+
+def test_large_cuboid_properties(torch_cuda):
+    """Full-size properties on a 1 M-DOF device-generated operator (no oracle run at this size):
+    (1) the theta-PCG solution satisfies the linear system to the requested tolerance (residual
+    recomputed with the bit-exact SpMV kernel), (2) energy balance: d/dt sum(M T) equals the net
+    heat input, (3) linearity of the SpMV."""
+    import torch
+    from thermca_b200 import _cabi
+    from thermca_b200.device import DeviceSolver
+    from thermca_b200.workloads import cuboid_dims, device_cuboid_spec
+    lib = _cabi.load_library()
+    nx, ny, nz = cuboid_dims(1.0e6)
+    spec = device_cuboid_spec(nx, ny, nz)
+    op = spec["ffe"][0]["sell"]
+    dev = DeviceSolver(spec)
+    n = dev.n_state
+    y0 = torch.full((n,), 20.0, dtype=torch.float64, device="cuda")
+    f0 = torch.from_numpy(dev.rhs(0.0, y0.cpu().numpy())).cuda()
+    # (2) at uniform T = T_env the film exchanges nothing: sum(M f) == heat input (1 kW)
+    power = float((op["mass"] * f0).sum())
+    assert abs(power - 1000.0) < 1e-6 * 1000.0
+    # (1) one theta step: (I + theta h A) z = f0, y1 = y0 + h z
+    h, theta = 1.0, 0.5
+    dev.theta_steps(1, h, theta, t0=0.0, pcg_rtol=1e-10)
+    y1 = torch.from_numpy(dev.get_state()).cuda()
+    z = (y1 - y0) / h
+    Az = torch.zeros_like(z)
+    p = lambda a: C.c_void_p(a.data_ptr()) if a is not None else C.c_void_p(0)
+    _cabi.check(lib.tc_sell_spmv(C.c_void_p(torch.cuda.current_stream().cuda_stream), 0, n, op["nslices"],
+                                 p(op["slice_ptr"]), p(op["col"]), p(None), p(op["val"]), p(z), p(Az), p(None), p(None),
+                                 0.0, 0))
+    torch.cuda.synchronize()
+    resid = op["mass"] * (z - theta * h * Az - f0)           # Az holds -A z
+    rel = float(resid.norm() / (op["mass"] * f0).norm())
+    assert rel < 5e-10, rel
+    # (3) linearity: A(2x + y) == 2 A x + A y up to rounding
+    x1 = torch.rand(n, dtype=torch.float64, device="cuda")
+    x2 = torch.rand(n, dtype=torch.float64, device="cuda")
+    outs = []
+    for v in (x1, x2, 2 * x1 + x2):
+        o = torch.zeros_like(v)
+        _cabi.check(lib.tc_sell_spmv(C.c_void_p(torch.cuda.current_stream().cuda_stream), 0, n, op["nslices"],
+                                     p(op["slice_ptr"]), p(op["col"]), p(op["col16"]), p(op["val"]), p(v), p(o), p(None),
+                                     p(None), 0.0, 0))
+        torch.cuda.synchronize()
+        outs.append(o)
+    assert float((outs[2] - 2 * outs[0] - outs[1]).abs().max()) < 1e-9 * float(outs[2].abs().max())
+    dev.close()
