@@ -221,3 +221,23 @@ MODELS = {
     "tdep_rod": tdep_rod,
     "assembly": assembly,
 }
+
+
+def lp_tdep():
+    """Temperature dependent LP body (pattern of thermca/tests/test_lp_part.py:601-665, shorter rod)."""
+    with Asm() as rod_asm:
+        cyl_rod = Cyl(lgth=1.0, lgth_div=24, name="cyl")
+        Surf(name="begin", faces=[cyl_rod.face.base])
+        Surf(name="end", faces=[cyl_rod.face.end])
+    matl = Solid(condy=np.array([[0.0, 5.0], [0.1, 0.5]]), dens=np.array([[0.0, 5.0], [1.0, 0.8]]), spec_heat=2.0)
+    with Model() as model:
+        rod = LPPart(asm=rod_asm, matl=matl, init_temp=1.0, temp_dependent=True, name="rod")
+        stat = StatNode()
+        FilmLink(rod.surf.begin, stat, film=1e32)
+        HeatSource(stat, heat=1.0 * rod.surf.begin.area())
+        bound = BoundNode(temp=0.0)
+        FilmLink(rod.surf.end, bound, film=free_conv.vert_surf(surf_hgt=0.3, factor=50.0), matl=fluids.air)
+    return Network(model), dict(time_span=[0.01, 3.0], method="RK45")
+
+
+MODELS["lp_tdep"] = lp_tdep

@@ -76,7 +76,9 @@ class OracleRHS:
                               shape=tuple(p["A_body"]["shape"]))
             self.lp.append({"A": A, "films": np.array(p["films"]),
                             "L_film_margs": np.array(p["L_film_margs"]),
-                            "L_film_margs_sum": np.array(p["L_film_margs"]).sum(axis=0)})
+                            "L_film_margs_sum": np.array(p["L_film_margs"]).sum(axis=0),
+                            "M_inv": np.array(p["M_inv"]), "L_data": np.array(p["L_data"]),
+                            "A_body_data": np.array(p["A_body"]["data"])})
 
     # -- helpers -------------------------------------------------------------------
     def _prog(self, k, args):
@@ -102,7 +104,7 @@ class OracleRHS:
         L = np.zeros((dof, F))
         for i in range(F):
             film_conds = p["face_areas"][i] * st["films"][i]
-            marg_conds = -p["L_data"][p["smx_didx"][i]]
+            marg_conds = -st["L_data"][p["smx_didx"][i]]
             np.add.at(L[:, i], p["marg_idxs"][i], film_conds * marg_conds / (film_conds + marg_conds))
         return L
 
@@ -110,8 +112,8 @@ class OracleRHS:
         # thermca/lpm/lp_io.py:68-80
         st["L_film_margs"] = self._lp_series(p, st)
         st["L_film_margs_sum"] = st["L_film_margs"].sum(axis=0)
-        diag = p["M_inv"] * st["L_film_margs"].sum(axis=1)
-        data = np.array(p["A_body"]["data"])
+        diag = st["M_inv"] * st["L_film_margs"].sum(axis=1)
+        data = np.array(st["A_body_data"])
         data[p["A_diag_didx"]] += diag
         st["A"].data = data
 
@@ -172,6 +174,24 @@ class OracleRHS:
             # scipy's csr product drops exact zeros and leaves indices unsorted, exactly as in
             # the reference's own sparse_dot(M_inv, L) (thermca/fem/ffe_io.py:73)
             st["A_body_data"] = (Minv @ L).data
+        # LP body material updates (thermca/lpm/lp_system.py:106-118, lp_io.py:59-66)
+        for k, (p, st) in enumerate(zip(s["lp"], self.lp)):
+            td = p.get("tdep")
+            if td is None:
+                continue
+            dof = int(p["dof"])
+            x = y[self.lp_off[k]: self.lp_off[k] + dof]
+            T_all = np.empty(int(td["n_rows"]))
+            T_all[:dof] = x
+            for marg, surf in zip(td["marg_all"], td["surf_all"]):
+                T_all[surf] = x[marg]
+            cond_temp = (T_all[td["row"]] + T_all[td["col"]]) / 2.0
+            L = sp.csr_matrix((self._interp(td["condy_tab"], cond_temp) * td["Lx_base_data"],
+                               (td["row"], td["col"])), shape=(int(td["n_rows"]), dof))
+            L.data[td["diag_didx"]] = -np.asarray(L[:dof].sum(axis=1)).ravel()
+            st["L_data"] = L.data
+            st["M_inv"] = 1.0 / (self._interp(td["vol_capy_tab"], x) * td["Mx_diag"])
+            st["A_body_data"] = (sp.diags(st["M_inv"], format="csr") @ L[:dof]).data
         for p, st in zip(s["lp"], self.lp):
             if int(p["var"]):
                 self._lp_update_state(p, st)
@@ -248,7 +268,7 @@ class OracleRHS:
             surf_flux = self.heat_src[p["surf_net_idxs"]] / p["surf_areas"]
             flow = (p["Qs"] @ surf_flux).ravel()
             flow += (st["L_film_margs"] @ T[p["link_elem_net_idxs"]]).ravel()
-            out.append(p["M_inv"] * flow - st["A"] @ x)
+            out.append(st["M_inv"] * flow - st["A"] @ x)
         for k, (p, st) in enumerate(zip(s["ffe"], self.ffe)):
             x = y[self.ffe_off[k]: self.ffe_off[k] + int(p["dof"])]
             surf_flux = self.heat_src[p["surf_net_idxs"]] / p["surf_areas"]

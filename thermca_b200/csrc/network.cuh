@@ -20,7 +20,7 @@
 enum TcCmd {
     C_END = 0, C_SET_TU, C_SURF_MEAN, C_INPUTS, C_MATL_GROUP, C_CAPY, C_FLOW_CONST, C_FLOW_FUNC,
     C_FILM_FUNC, C_HEAT_FUNC, C_FLUX_FUNC, C_BOUND_FUNC, C_PART_FILMS, C_LP_UPDATE, C_LP2LP,
-    C_LP_LEAK, C_STAT, C_DIAG, C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D
+    C_LP_LEAK, C_STAT, C_DIAG, C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D, C_LP_TDEP
 };
 
 struct TcNetParams {
@@ -272,6 +272,45 @@ tc_network_kernel(TcNetParams P, const double* __restrict__ ctrl, double c_stage
                 flow = __dadd_rn(flow, fl2);
                 D[a[3] + i] = __dmul_rn(D[a[9] + i], flow);
             }
+        } break;
+        case C_LP_TDEP: {
+            // Temperature dependent LP body (LPSystem.update_material_properties, lpm/lp_system.py:106-118,
+            // LPIO.update_material_properties lp_io.py:59-66).
+            // a: dof, n_rows, nnzL, y_off, Lx_doff, row_ioff, col_ioff, Ldata_doff, Lindptr_ioff, diag_ioff,
+            //    Mx_doff, minv_doff, mass_doff, condy_tab, vc_tab, tall_doff, nsurf, surfdir_ioff
+            //    (nsurf x {marg_ioff, surfidx_ioff, count}), n_ab, fromL_ioff, abrow_ioff, sellpos_ioff,
+            //    val_doff, abody_diag_doff
+            const int dof = a[0], n_rows = a[1], nnzL = a[2];
+            const double* x = y + a[3];
+            double* Tall = D + a[15];
+            for (int i = tid; i < dof; i += nt) Tall[i] = x[i];
+            for (int s = 0; s < a[16]; ++s) {
+                const int* q = I + a[17] + 3 * s;
+                const int *mg = I + q[0], *sf = I + q[1];
+                for (int j = tid; j < q[2]; j += nt) Tall[sf[j]] = x[mg[j]];
+            }
+            __syncthreads();
+            const int *row = I + a[5], *col = I + a[6];
+            double* Ld = D + a[7];
+            for (int k = tid; k < nnzL; k += nt) {
+                const double ct = __ddiv_rn(__dadd_rn(Tall[row[k]], Tall[col[k]]), 2.0);
+                Ld[k] = __dmul_rn(tc_interp(tb, a[13], ct), D[a[4] + k]);
+            }
+            __syncthreads();
+            const int *lip = I + a[8], *dg = I + a[9];
+            for (int i = tid; i < dof; i += nt) {
+                double sum = 0.0;
+                for (int k = lip[i]; k < lip[i + 1]; ++k) sum = __dadd_rn(sum, Ld[k]);
+                Ld[dg[i]] = -sum;
+                const double md = __dmul_rn(tc_interp(tb, a[14], x[i]), D[a[10] + i]);
+                D[a[12] + i] = md;
+                D[a[11] + i] = __ddiv_rn(1.0, md);
+            }
+            __syncthreads();
+            const int *fl = I + a[19], *abr = I + a[20], *sp = I + a[21];
+            for (int k = tid; k < a[18]; k += nt) D[a[22] + sp[k]] = __dmul_rn(D[a[11] + abr[k]], Ld[fl[k]]);
+            for (int i = tid; i < dof; i += nt) D[a[23] + i] = __dmul_rn(D[a[11] + i], Ld[dg[i]]);
+            (void)n_rows;
         } break;
         case C_COPY_D: {                // n, src_doff, dst_doff
             for (int i = tid; i < a[0]; i += nt) D[a[2] + i] = D[a[1] + i];

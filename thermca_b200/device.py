@@ -18,7 +18,7 @@ from .spec import state_offsets
 # command opcodes, keep in sync with csrc/network.cuh
 (C_END, C_SET_TU, C_SURF_MEAN, C_INPUTS, C_MATL_GROUP, C_CAPY, C_FLOW_CONST, C_FLOW_FUNC, C_FILM_FUNC,
  C_HEAT_FUNC, C_FLUX_FUNC, C_BOUND_FUNC, C_PART_FILMS, C_LP_UPDATE, C_LP2LP, C_LP_LEAK, C_STAT, C_DIAG,
- C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D) = range(22)
+ C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D, C_LP_TDEP) = range(23)
 
 MEAN_ENTRIES_PER_BLOCK = 4096
 MEAN_MAX_BLOCKS_PER_JOB = 64
@@ -296,6 +296,18 @@ class DeviceSolver:
                 face_dir += [A.add_d(p["face_areas"][f]), A.add_i(p["smx_didx"][f]), A.add_i(p["marg_idxs"][f]),
                              len(p["face_areas"][f])]
             d["face_dir"] = A.add_i(face_dir if face_dir else [0, 0, 0, 0])
+            td = p.get("tdep")
+            if td is not None:
+                surfdir = []
+                for marg, surf in zip(td["marg_all"], td["surf_all"]):
+                    surfdir += [A.add_i(marg), A.add_i(surf), len(marg)]
+                d["tdep_args"] = [
+                    dof, int(td["n_rows"]), len(td["Lx_base_data"]), self.lp_off[k], A.add_d(td["Lx_base_data"]),
+                    A.add_i(td["row"]), A.add_i(td["col"]), d["Ldata"], A.add_i(td["L_indptr"]), A.add_i(td["diag_didx"]),
+                    A.add_d(td["Mx_diag"]), d["minv"], d["mass"], int(td["condy_tab"]), int(td["vol_capy_tab"]),
+                    A.add_d(np.zeros(int(td["n_rows"]))), len(td["marg_all"]), A.add_i(surfdir if surfdir else [0, 0, 0]),
+                    len(td["abody_from_L"]), A.add_i(td["abody_from_L"]), A.add_i(td["abody_rows"]),
+                    A.add_i(sell["pos"]), d["val"], d["abody_diag"]]
             lp_dev.append(d)
         ffe_dev = []
         for k, p in enumerate(s["ffe"]):
@@ -323,6 +335,9 @@ class DeviceSolver:
             cmd(C_LP_UPDATE, d["dof"], d["F"], d["films"], d["lfm"], d["lsum"], d["Ldata"], d["face_dir"],
                 d["minv"], d["abody_diag"], d["val"], d["diagpos"])
 
+        for p, d in zip(s["lp"], lp_dev):
+            if "tdep_args" in d:
+                cmd(C_LP_TDEP, *d["tdep_args"])
         for p, d in zip(s["lp"], lp_dev):
             if int(p["var"]):
                 lp_update(d)

@@ -225,7 +225,28 @@ def _lower_lp(lo, net, k, io):
     p["leak_fwd"] = _i64(net._var_lp_run_cond_fwd_idxs[j]) if j >= 0 else None
     p["leak_bwd"] = _i64(net._var_lp_run_cond_bwd_idxs[j]) if j >= 0 else None
     if _find(net._var_body_lp_ios, io) >= 0:
-        raise NotImplementedError("temperature dependent LPPart bodies are not lowered yet")
+        # LPSystem.update_material_properties (thermca/lpm/lp_system.py:106-118)
+        matl = sysm.matl
+        coo = sysm.Lx_base_coo
+        L = sp.csr_matrix(sysm.L)
+        lookup = {}
+        for r in range(L.shape[0]):
+            for k in range(L.indptr[r], L.indptr[r + 1]):
+                lookup.setdefault((r, int(L.indices[k])), k)
+        ab = sp.csr_matrix(io.A_body)
+        ab_rows = np.repeat(np.arange(ab.shape[0]), np.diff(ab.indptr))
+        from_L = np.array([lookup[(int(r), int(c))] for r, c in zip(ab_rows, ab.indices)], dtype=np.int64)
+        p["tdep"] = {
+            "Lx_base_data": _f64(sysm.Lx_base.data), "row": _i64(coo.row), "col": _i64(coo.col),
+            "L_indptr": _i64(L.indptr), "n_rows": np.int64(L.shape[0]),
+            "diag_didx": _i64(sysm.L_diag_data_idxs), "Mx_diag": _f64(sysm.Mx_diag),
+            "condy_tab": lo.table(matl._condy[0], matl._condy[1]),
+            "vol_capy_tab": lo.table(matl._vol_capy_temp, matl._vol_capy),
+            "marg_all": [_i64(m) for m in sysm.marg_dof_idxs], "surf_all": [_i64(x) for x in sysm.surf_dof_idxs],
+            "abody_from_L": from_L, "abody_rows": _i64(ab_rows),
+        }
+    else:
+        p["tdep"] = None
     return p
 
 
