@@ -80,6 +80,7 @@ typedef struct {
     int32_t val_doff;
     int32_t b_doff;                 /* dense load vector M_inv*(Qs flux + L_film_margs T_link) */
     int32_t mass_doff;
+    int32_t adiag_doff;             /* dense diag(A), kept current by the network kernel */
 } tc_lp_desc;
 
 /* ---- MOR part (replaces MORIO at run time, thermca/fem/mor_io.py:78-92) ------------------ */

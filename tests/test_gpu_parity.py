@@ -289,3 +289,18 @@ def test_large_cuboid_properties(torch_cuda):
         outs.append(o)
     assert float((outs[2] - 2 * outs[0] - outs[1]).abs().max()) < 1e-9 * float(outs[2].abs().max())
     dev.close()
+
+
+def test_ros2_with_implicit_lp_part(torch_cuda, golden):
+    """ROS2 on the coffee cup (LP part solved implicitly by PCG, network node explicit) against the
+    oracle's RK45 at tight tolerance."""
+    from thermca_b200.device import DeviceSolver
+    from rhs_oracle import integrate
+    spec, ex = golden("coffeecup")
+    tight = integrate(spec, [0.0, 600.0], 1e-9, 1e-10, "RK45")
+    dev = DeviceSolver(spec)
+    out = dev.run_ros2(0.0, 600.0, rtol=1e-5, atol=1e-7, pcg_rtol=1e-12)
+    dev.close()
+    assert out["status"] == 0 and out["times"][-1] == 600.0 and out["pcg"]["solves"] > 0
+    assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=2e-4)
+    assert np.allclose(out["io_temps"][-1], tight["io_temps"][-1], rtol=2e-4)

@@ -37,7 +37,7 @@ class FfeDesc(C.Structure):
 
 class LpDesc(C.Structure):
     _fields_ = [("n", i32), ("nslices", i32), ("y_off", i64), ("slice_ptr_ioff64", i32), ("col_ioff", i32),
-                ("val_doff", i32), ("b_doff", i32), ("mass_doff", i32)]
+                ("val_doff", i32), ("b_doff", i32), ("mass_doff", i32), ("adiag_doff", i32)]
 
 
 class MorDesc(C.Structure):

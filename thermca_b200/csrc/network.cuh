@@ -161,7 +161,8 @@ tc_network_kernel(TcNetParams P, const double* __restrict__ ctrl, double c_stage
         case C_LP_UPDATE: {
             // dof, F, films_doff, lfm_doff (dof*F row-major), lsum_doff (F), Ldata_doff,
             // face_dir ioff (F x {areas_doff, smx_ioff, marg_ioff, count}), minv_doff,
-            // abody_diag_doff (dof), sellval_doff, diagpos_ioff (position of A_ii in SELL values)
+            // abody_diag_doff (dof), sellval_doff, diagpos_ioff (position of A_ii in SELL values),
+            // adiag_doff (dense copy of the updated diagonal, used by the implicit solves)
             const int dof = a[0], F = a[1];
             double* lfm = D + a[3];
             for (int i = tid; i < dof * F; i += nt) lfm[i] = 0.0;
@@ -192,7 +193,9 @@ tc_network_kernel(TcNetParams P, const double* __restrict__ ctrl, double c_stage
             for (int i = tid; i < dof; i += nt) {
                 double rs = 0.0;
                 for (int f = 0; f < F; ++f) rs = __dadd_rn(rs, lfm[i * F + f]);
-                D[a[9] + dpos[i]] = __dadd_rn(D[a[8] + i], __dmul_rn(D[a[7] + i], rs));
+                const double dv = __dadd_rn(D[a[8] + i], __dmul_rn(D[a[7] + i], rs));
+                D[a[9] + dpos[i]] = dv;
+                D[a[11] + i] = dv;
             }
         } break;
         case C_LP2LP: {                 // films0_doff+f0, lsum1_doff+f1, area0_doff ; films1.., lsum0.., area1..

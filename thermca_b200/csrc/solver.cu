@@ -257,7 +257,7 @@ struct FfePart {
     double *r, *p, *q, *dinv;          // PCG workspace
     TcPcg pcg;
 };
-struct LpPart { tc_lp_desc d; TcSell A; const double* b; };
+struct LpPart { tc_lp_desc d; TcSell A; const double* b; double *r, *p, *q, *dinv; TcPcg pcg; };
 struct MorPart { tc_mor_desc d; TcMor M; };
 
 struct tc_solver {
@@ -336,6 +336,7 @@ extern "C" int tc_destroy(tc_handle s) {
     cudaFree(s->y); cudaFree(s->ynew); cudaFree(s->ystage);
     for (int i = 0; i < 7; ++i) cudaFree(s->K[i]);
     for (auto& p : s->ffe) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
+    for (auto& p : s->lp) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
     cudaFreeHost(s->pin_flags); cudaFreeHost(s->pin_ctrl);
     delete s;
     return 0;
@@ -401,6 +402,11 @@ extern "C" int tc_finalize(tc_handle s, int64_t n_state) {
     for (int i = 0; i < 7; ++i) TC_CUDA(cudaMalloc(&s->K[i], bytes));
     s->vec_grid = grid_for(n_state, 256, s->sm_count * 8);
     for (auto& p : s->ffe) {
+        const size_t b = sizeof(double) * (size_t)p.d.n;
+        TC_CUDA(cudaMalloc(&p.r, b)); TC_CUDA(cudaMalloc(&p.p, b));
+        TC_CUDA(cudaMalloc(&p.q, b)); TC_CUDA(cudaMalloc(&p.dinv, b));
+    }
+    for (auto& p : s->lp) {
         const size_t b = sizeof(double) * (size_t)p.d.n;
         TC_CUDA(cudaMalloc(&p.r, b)); TC_CUDA(cudaMalloc(&p.p, b));
         TC_CUDA(cudaMalloc(&p.q, b)); TC_CUDA(cudaMalloc(&p.dinv, b));
@@ -771,6 +777,17 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
     cudaStream_t st = s->stream;
     const int* done = s->flags + FL_DONE;
     tc_copy_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, rhs, z, done);
+    // LP parts: same SPD structure (M A = L_body + film/margin diagonal, thermca/lpm/lp_io.py:106-128)
+    for (auto& p : s->lp) {
+        TcPcg& P = p.pcg;
+        P.A = p.A; P.mass = s->net.darena + p.d.mass_doff; P.adiag = s->net.darena + p.d.adiag_doff;
+        P.rhs = rhs + p.d.y_off; P.x = z + p.d.y_off;
+        P.r = p.r; P.p = p.p; P.q = p.q; P.dinv = p.dinv;
+        P.partial = s->red_partial; P.sc = s->pcg_sc; P.isc = s->pcg_isc;
+        P.rtol = s->pcg_rtol; P.maxit = s->pcg_maxit; P.ctrl = s->ctrl; P.coef = coef;
+        P.prof = nullptr;
+        if (launch_pcg(s, P, s->pcg_mode, s->coop_grid, done)) return -1;
+    }
     for (auto& p : s->ffe) {
         if (p.d.tdep) continue;      // operator depends on T: treated explicitly (copy above)
         TcPcg& P = p.pcg;

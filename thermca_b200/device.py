@@ -287,6 +287,7 @@ class DeviceSolver:
                 "val": A.add_d(sell["val"]), "diagpos": A.add_i(sell["pos"][dpos_csr]),
                 "slice_ptr": A.add_i64(sell["slice_ptr"]), "col": A.add_i(sell["col"]),
                 "b": A.add_d(np.zeros(dof)), "mass": A.add_d(1.0 / np.asarray(p["M_inv"])),
+                "adiag": A.add_d(np.asarray(p["A_data"])[dpos_csr]),
                 "qs": A.add_d(np.asarray(p["Qs"]).reshape(dof, S)), "areas": A.add_d(p["surf_areas"]),
                 "surf_net": A.add_i(p["surf_net_idxs"]), "link": A.add_i(p["link_elem_net_idxs"] if F else [0]),
                 "dock": A.add_d(p["dock_areas"] if F else np.zeros(1)), "dof": dof, "F": F, "S": S,
@@ -333,7 +334,7 @@ class DeviceSolver:
 
         def lp_update(d):
             cmd(C_LP_UPDATE, d["dof"], d["F"], d["films"], d["lfm"], d["lsum"], d["Ldata"], d["face_dir"],
-                d["minv"], d["abody_diag"], d["val"], d["diagpos"])
+                d["minv"], d["abody_diag"], d["val"], d["diagpos"], d["adiag"])
 
         for p, d in zip(s["lp"], lp_dev):
             if "tdep_args" in d:
@@ -397,7 +398,7 @@ class DeviceSolver:
             ld = _cabi.LpDesc()
             ld.n, ld.nslices, ld.y_off = d["dof"], d["sell"]["nslices"], self.lp_off[k]
             ld.slice_ptr_ioff64, ld.col_ioff, ld.val_doff = d["slice_ptr"], d["col"], d["val"]
-            ld.b_doff, ld.mass_doff = d["b"], d["mass"]
+            ld.b_doff, ld.mass_doff, ld.adiag_doff = d["b"], d["mass"], d["adiag"]
             _cabi.check(self.lib.tc_add_lp_part(self._handle, C.byref(ld)))
         self.ffe_sell = []
         for k, (p, d) in enumerate(zip(s["ffe"], ffe_dev)):
