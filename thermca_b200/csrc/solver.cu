@@ -738,6 +738,9 @@ static int pcg_coop_grid(int sm_count) {
 
 static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int* done) {
     cudaStream_t st = s ? s->stream : nullptr;
+    // CG terminates in at most n steps in exact arithmetic: never spin on a tolerance below the
+    // attainable residual of a tiny system
+    if ((long long)P.maxit > 2LL * P.A.n + 50) P.maxit = 2 * P.A.n + 50;
     if (mode == TC_PCG_COOP) {
         void* args[] = {(void*)&P, (void*)&done};
         int g = coop_grid;
