@@ -44,43 +44,57 @@ def algorithmic_bytes_per_iteration(n_rows, nnz):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (one persistent
+    `nvidia-smi -lms 100` process; started before the warm-up steps, stopped after the timed region)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
         self.gpu = gpu_index
-        self.thread = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for nm, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(nm)
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.proc = None
+        self.lines = []
 
     def __enter__(self):
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+            time.sleep(0.25)          # first sample before the load starts
+        except Exception:
+            self.proc = None
         return self
 
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
     def __exit__(self, *a):
-        self._stop.set()
-        self.thread.join(timeout=3)
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
 
     def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        sm, mx, reasons = [], None, set()
+        for line in self.lines:
+            f = [x.strip() for x in line.strip().split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                for nm, v in zip(self.NAMES, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
 
 
 def measured_peak():
@@ -212,12 +226,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------
-    dev.theta_steps(args.warmup, H_STEP, THETA, t0=0.0, pcg_rtol=PCG_RTOL, pcg_mode=args.pcg_mode)
-    sync()
-    dev.timing(True)
-    it0 = dev.pcg_stats()["iterations"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        dev.theta_steps(args.warmup, H_STEP, THETA, t0=0.0, pcg_rtol=PCG_RTOL, pcg_mode=args.pcg_mode)
+        sync()
+        dev.timing(True)
+        it0 = dev.pcg_stats()["iterations"]
         sync()
         with torch.cuda.stream(dev.stream):
             e0.record(dev.stream)

@@ -152,11 +152,11 @@ def run_partitioned_bench(args, world, rank, local_rank):
     nx, ny, nz = cuboid_dims(args.dof)
     ny_tot = (ny + 1) * world - 1                     # the same number of y-layers per rank
     dc = DistCuboid(nx, ny_tot, nz, ly=1.0 * world, heat=B.HEAT * world, film=B.FILM, env_temp=B.T_ENV)
-    dc.theta_steps(args.warmup, B.H_STEP, B.THETA, B.PCG_RTOL)
-    it0 = dc.stats()["iters_total"]
-    dc.profile()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with B.ClockSampler(local_rank) as clocks:
+        dc.theta_steps(args.warmup, B.H_STEP, B.THETA, B.PCG_RTOL)
+        it0 = dc.stats()["iters_total"]
+        dc.profile()
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
