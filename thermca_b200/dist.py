@@ -191,6 +191,14 @@ def run_partitioned_bench(args, world, rank, local_rank):
     torch.cuda.synchronize(); dist.barrier()
     e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    # per-rank busy / wait split (block 0 of every rank): exposes systematic skew between GPUs
+    pl = prof["last"]
+    mine = torch.tensor([pl["spmv"] + pl["update x,r"] + pl["direction"] + pl["dot"],
+                         pl["allreduce pq"] + pl["allreduce rho"] + pl["sync1"] + pl["sync2"] + pl["sync3"]],
+                        dtype=torch.float64, device="cuda")
+    allp = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(allp, mine)
+    per_rank = [[round(float(v[0]), 1), round(float(v[1]), 1)] for v in allp]
     peak, peak_kind = B.measured_peak()
     bytes_step = B.algorithmic_bytes_per_iteration(dc.n, dc.nnz) * (iters / args.steps) + dc.n * (12 * 15 + 80)
     achieved = bytes_step / (ms / args.steps * 1e-3) / 1e9
@@ -204,7 +212,8 @@ def run_partitioned_bench(args, world, rank, local_rank):
                    "dof": n_tot, "dof_per_gpu": dc.n, "nnz": int(nnz.item()), "pcg_rtol": B.PCG_RTOL,
                    "h_step_s": B.H_STEP, "iters_per_step": iters / args.steps, "halo_rows": dc.halo,
                    "l2": "per-GPU inputs exceed the 126 MB L2", "comm_error": int(err.item()),
-                   "phase_ms_rank0": prof, "grid": st["grid"]},
+                   "phase_ms_rank0": prof, "grid": st["grid"],
+                   "busy_wait_ms_per_rank": per_rank},
         "clocks": clocks.summary(),
         "e2e": {"value": n_tot * e2e_steps / float(e2e.item()), "unit": "DOF*steps/s",
                 "h2d_bytes_per_step": n_tot * 8, "d2h_bytes_per_step": n_tot * 8, "steps": e2e_steps},
