@@ -40,6 +40,7 @@ struct TcDistK {
     double theta, h, rtol;
     int maxit;
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
+    double* lres;                         // [2][4] locally published reduction results
 };
 
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
@@ -109,23 +110,50 @@ __device__ void halo_wait(const TcDistK& S, int hseq, int nb_max) {
     __syncthreads();
 }
 
-// every block holds the same local values; result = sum over ranks in rank order
+// every block holds the same local values; result = sum over ranks in rank order.
+// Only block 0 talks to the peers (8 remote stores + 8 pollers on the NVLink-written mailbox); it then
+// publishes the sum in a local slot that the other ~1200 blocks poll, so the mailbox lines are not
+// hammered by ten thousand system-scope loads while the peers' stores are in flight.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ void allreduce3(const TcDistK& S, double* v, int seq) {
     const int par = seq & 1;
     if (S.world == 1) return;
-    if (blockIdx.x == 0 && threadIdx.x < S.world) {
-        const int peer = threadIdx.x;
-        volatile double* mb = S.peer_mb[peer];
-        for (int k = 0; k < 3; ++k) mb[(par * 3 + k) * TC_MAX_WORLD + S.rank] = v[k];
-        st_release_sys(S.peer_mbf[peer] + par * TC_MAX_WORLD + S.rank, seq);   // orders the stores above
+    volatile double* res = S.lres + par * 4;      // local result slot [2][4]
+    int* lflag = S.state + 8 + par;               // local flags
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < S.world) {
+            const int peer = threadIdx.x;
+            volatile double* mb = S.peer_mb[peer];
+            for (int k = 0; k < 3; ++k) mb[(par * 3 + k) * TC_MAX_WORLD + S.rank] = v[k];
+            st_release_sys(S.peer_mbf[peer] + par * TC_MAX_WORLD + S.rank, seq);   // orders the stores above
+            spin_until(S.my_mbf + par * TC_MAX_WORLD + threadIdx.x, seq, S.state + 4);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            volatile double* mine = S.my_mb;
+            double out[3] = {0.0, 0.0, 0.0};
+            for (int w = 0; w < S.world; ++w)
+                for (int k = 0; k < 3; ++k) out[k] += mine[(par * 3 + k) * TC_MAX_WORLD + w];
+            res[0] = out[0]; res[1] = out[1]; res[2] = out[2];
+            st_release_gpu(lflag, seq);
+        }
     }
-    if (threadIdx.x < S.world) spin_until(S.my_mbf + par * TC_MAX_WORLD + threadIdx.x, seq, S.state + 4);
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(lflag) < seq) {
+            if (*((volatile int*)(S.state + 4))) break;
+            if (clock64() - t0 > TC_SPIN_LIMIT) { *((volatile int*)(S.state + 4)) = 1; break; }
+        }
+    }
     __syncthreads();
-    volatile double* mine = S.my_mb;
-    double out[3] = {0.0, 0.0, 0.0};
-    for (int w = 0; w < S.world; ++w)
-        for (int k = 0; k < 3; ++k) out[k] += mine[(par * 3 + k) * TC_MAX_WORLD + w];
-    v[0] = out[0]; v[1] = out[1]; v[2] = out[2];
+    v[0] = res[0]; v[1] = res[1]; v[2] = res[2];
     __syncthreads();
 }
 
@@ -520,6 +548,7 @@ struct tc_dist {
     double *pdir = nullptr, *sdir = nullptr;
     int* state = nullptr;
     unsigned long long* prof = nullptr;
+    double* lres = nullptr;
     TcDistK K;
     int grid = 0;
 };
@@ -551,6 +580,8 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     TC_CUDA(cudaMalloc(&d->partial, sizeof(double) * 6 * TC_MAX_PARTIALS));
     TC_CUDA(cudaMalloc(&d->state, sizeof(int) * 16));
     TC_CUDA(cudaMemset(d->state, 0, sizeof(int) * 16));
+    TC_CUDA(cudaMalloc(&d->lres, sizeof(double) * 8));
+    TC_CUDA(cudaMemset(d->lres, 0, sizeof(double) * 8));
     TC_CUDA(cudaMalloc(&d->prof, sizeof(unsigned long long) * 32));
     TC_CUDA(cudaMemset(d->prof, 0, sizeof(unsigned long long) * 32));
     d->peer[rank] = d->comm;
@@ -623,6 +654,7 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     K.my_hflag = (int*)(d->comm + d->off_hflag);
     K.state = d->state;
     K.prof = d->prof;
+    K.lres = d->lres;
     int dev = 0, sms = 148, occ = 0;
     TC_CUDA(cudaGetDevice(&dev));
     TC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -678,7 +710,7 @@ extern "C" int tc_dist_destroy(tc_dist* d) {
         if (w != d->rank && d->peer[w]) cudaIpcCloseMemHandle(d->peer[w]);
     cudaFree(d->comm); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
     cudaFree(d->pdir); cudaFree(d->sdir);
-    cudaFree(d->partial); cudaFree(d->state); cudaFree(d->prof);
+    cudaFree(d->partial); cudaFree(d->state); cudaFree(d->prof); cudaFree(d->lres);
     delete d;
     return 0;
 }
