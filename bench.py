@@ -97,6 +97,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(n, iters_per_launch):
+    """DRAM bytes per PCG launch from the committed ncu capture (profiles/r01_pcg_traffic.json), scaled to this
+    run's iteration count; None when the capture was taken on a different problem size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_pcg_traffic.json")) as f:
+            t = json.load(f)
+        if abs(t["dof"] - n) > 0.02 * n:
+            return None
+        return t["dram_bytes_per_row_iter"] * n * iters_per_launch
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -300,7 +313,8 @@ def run_ours(args):
         "gpu_launches": tm["launches"],
         "rk45_explicit": rk45,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "tc_pcg_coop_kernel", "peak_kind": peak_kind,
+                     "traffic": measured_traffic(n, iters_per_solve), "kernel": "tc_pcg_coop_kernel",
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "peak_kind": peak_kind,
                      "ms_per_launch": pcg_ms_per_launch, "iters_per_launch": iters_per_solve,
                      "algorithmic_bytes_per_row_iter": algorithmic_bytes_per_iteration(n, nnz) / n,
                      "share_of_step": tm["pcg_ms"] / ms, "phase_ms_block0": phase},
