@@ -164,9 +164,20 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #define MP_TN 64
 #define MP_LDX (MP_TN + 4)     // 68 doubles
 
+// film coefficients of every scenario at the stage time, evaluated once per stage (F*B values)
+// instead of once per output element inside the GEMM epilogue
+__global__ void tc_mor_films_kernel(MorBatch M, double t, double* __restrict__ fv) {
+    const int n = M.F * M.B;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int f = i / M.B;
+        fv[i] = film_at(M, f, i - f * M.B, t);
+    }
+}
+
 template <int NOPS>
 __global__ void __launch_bounds__(MB_THREADS, (NOPS <= 3 ? 2 : 1))
-tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ Xin, const double* __restrict__ Xbase,
+tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double* __restrict__ Xin,
+                         const double* __restrict__ Xbase,
                          double* __restrict__ Xout, double* __restrict__ Xacc, double t, double h,
                          double c_out, double c_acc, int first) {
     extern __shared__ __align__(16) double smem[];
@@ -174,9 +185,13 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ Xin, const doubl
     constexpr int X_STAGE = MP_TK * MP_LDX;
     double* sA0 = smem;                         // [2][NOPS][64][20]
     double* sX0 = smem + 2 * A_STAGE;           // [2][16][68]
-    const int s = blockIdx.z;
-    const int i0 = blockIdx.y * MB_TM;
-    const int b0 = blockIdx.x * MP_TN;
+    // CTA order: scenario tile fastest, then surface, row tile slowest, so the cheap ragged last row tiles
+    // (r % 64 rows) are scheduled last and fill the tail of the final wave
+    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int rest = lin / gridDim.x;
+    const int s = rest % gridDim.z;
+    const int i0 = (rest / gridDim.z) * MB_TM;
+    const int b0 = (lin - rest * gridDim.x) * MP_TN;
     const int r = M.r, B = M.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 16;
@@ -190,26 +205,37 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ Xin, const doubl
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[o][a][c][0] = acc[o][a][c][1] = 0.0;
 
+    // every thread owns the same copy slots in every chunk (MB_THREADS = 256 = 32 rows x 8 pairs):
+    // operator slot q -> operator q/2, row (tid>>3) + 32*(q&1), pair tid&7; state slot q -> k-row (tid>>5) + 8q
+    static_assert(MB_THREADS == 256 && MB_TM == 64 && MP_TK == 16 && MP_TN == 64, "copy slot mapping");
+    const int a_ri = tid >> 3, a_kp = tid & 7;
+    const bool a_in[2] = {i0 + a_ri < r, i0 + a_ri + 32 < r};
+    const size_t a_off = (size_t)(i0 + a_ri) * r + 2 * a_kp;
+    const int a_dst = a_ri * MP_LDA + 2 * a_kp;
+    const double* Wb = M.A_body + (size_t)s * r * r;
+    const double* Wf = M.A_films + (size_t)s * r * r;
+    const size_t w_stride = (size_t)M.S * r * r;
+    const int x_kk = tid >> 5, x_bp = tid & 31;
+    const bool x_in = b0 + 2 * x_bp < B;
+    const size_t x_off = (size_t)x_kk * B + b0 + 2 * x_bp;
+    const int x_dst = x_kk * MP_LDX + 2 * x_bp;
     auto load_chunk = [&](int stage, int k0) {
         double* sA = sA0 + stage * A_STAGE;
         double* sX = sX0 + stage * X_STAGE;
-        // operators: NOPS x 64 rows x 8 pairs (16 bytes each)
-        for (int e = tid; e < NOPS * MB_TM * (MP_TK / 2); e += MB_THREADS) {
-            const int o = e / (MB_TM * (MP_TK / 2));
-            const int rem = e - o * (MB_TM * (MP_TK / 2));
-            const int ri = rem / (MP_TK / 2), kp = rem - ri * (MP_TK / 2);
-            const int gi = i0 + ri, gk = k0 + 2 * kp;
-            const double* W = (o == 0) ? M.A_body + (size_t)s * r * r : M.A_films + ((size_t)(o - 1) * M.S + s) * r * r;
-            const bool ok = gi < r && gk < r;          // r is even: a pair is either inside or outside
-            cp_async16(sA + (o * MB_TM + ri) * MP_LDA + 2 * kp, ok ? (const void*)(W + (size_t)gi * r + gk) : (const void*)W,
-                       ok ? 16 : 0);
+        const bool k_in = k0 + 2 * a_kp < r;            // r is even: a pair is either inside or outside
+#pragma unroll
+        for (int q = 0; q < 2 * NOPS; ++q) {
+            const int o = q >> 1, half = q & 1;
+            const double* W = o == 0 ? Wb : Wf + (size_t)(o - 1) * w_stride;
+            const bool ok = k_in && a_in[half];
+            cp_async16(sA + a_dst + (o * MB_TM + 32 * half) * MP_LDA,
+                       ok ? (const void*)(W + a_off + (size_t)(32 * half) * r + k0) : (const void*)Wb, ok ? 16 : 0);
         }
-        // state: 16 rows x 32 pairs
-        for (int e = tid; e < MP_TK * (MP_TN / 2); e += MB_THREADS) {
-            const int kk = e / (MP_TN / 2), bp = e - kk * (MP_TN / 2);
-            const int gk = k0 + kk, gb = b0 + 2 * bp;
-            const bool ok = gk < r && gb < B;
-            cp_async16(sX + kk * MP_LDX + 2 * bp, ok ? (const void*)(Xs + (size_t)gk * B + gb) : (const void*)Xs, ok ? 16 : 0);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const bool ok = x_in && k0 + x_kk + 8 * q < r;
+            cp_async16(sX + x_dst + 8 * q * MP_LDX,
+                       ok ? (const void*)(Xs + x_off + (size_t)(k0 + 8 * q) * B) : (const void*)Xs, ok ? 16 : 0);
         }
         cp_async_commit();
     };
@@ -241,33 +267,57 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ Xin, const doubl
         }
         __syncthreads();
     }
+    // fused epilogue.  Film weights and input flux belong to a scenario column, B_T to a row: both are
+    // formed once per thread; a thread owns column pairs (B is even), so state traffic moves as double2.
+    const double q_s = M.q_surf[s];
+    double tl[NOPS > 1 ? NOPS - 1 : 1];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int f = 0; f < NOPS - 1; ++f) tl[f] = M.film_surf[f] == s ? M.t_link[f] : 0.0;
+    double bt[2];
+    bool rok[2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+    for (int a = 0; a < 2; ++a) {
+        const int gi = i0 + wm + 8 * a + (lane >> 2);
+        rok[a] = gi < r;
+        bt[a] = rok[a] ? M.B_T[(size_t)s * r + gi] : 0.0;
+    }
+    const double ho = c_out * h, ha = c_acc * h;
+    const size_t row0 = ((size_t)s * r + i0 + wm + (lane >> 2)) * B;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int gb = b0 + wn + 8 * c + 2 * (lane & 3);
+        if (gb >= B) continue;
+        double fvv[NOPS > 1 ? NOPS - 1 : 1][2];
+        double flux[2] = {q_s, q_s};
+#pragma unroll
+        for (int f = 0; f < NOPS - 1; ++f) {
+            const double2 v = *reinterpret_cast<const double2*>(fv + (size_t)f * B + gb);
+            fvv[f][0] = v.x; fvv[f][1] = v.y;
+            if (M.film_surf[f] == s) { flux[0] += v.x * tl[f]; flux[1] += v.y * tl[f]; }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            if (!rok[a]) continue;
+            const size_t idx = row0 + (size_t)(8 * a) * B + gb;
+            double kv[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int gi = i0 + wm + 8 * a + (lane >> 2);
-                const int gb = b0 + wn + 8 * c + 2 * (lane & 3) + e;
-                if (gi >= r || gb >= B) continue;
                 double z = acc[0][a][c][e];
-                double flux = M.q_surf[s];
 #pragma unroll
-                for (int f = 0; f < NOPS - 1; ++f) {
-                    const double fv = film_at(M, f, gb, t);
-                    z += fv * acc[f + 1][a][c][e];
-                    if (M.film_surf[f] == s) flux += fv * M.t_link[f];
-                }
-                const double kval = -z + M.B_T[(size_t)s * r + gi] * flux;
-                const size_t idx = ((size_t)s * r + gi) * B + gb;
-                const double xb = Xbase[idx];
-                if (Xout) Xout[idx] = xb + c_out * h * kval;
-                Xacc[idx] = (first ? xb : Xacc[idx]) + c_acc * h * kval;
+                for (int f = 0; f < NOPS - 1; ++f) z += fvv[f][e] * acc[f + 1][a][c][e];
+                kv[e] = -z + bt[a] * flux[e];
             }
+            const double2 xb = *reinterpret_cast<const double2*>(Xbase + idx);
+            if (Xout) *reinterpret_cast<double2*>(Xout + idx) = make_double2(xb.x + ho * kv[0], xb.y + ho * kv[1]);
+            double2 xa = xb;
+            if (!first) xa = *reinterpret_cast<const double2*>(Xacc + idx);
+            *reinterpret_cast<double2*>(Xacc + idx) = make_double2(xa.x + ha * kv[0], xa.y + ha * kv[1]);
+        }
+    }
 }
 
 template <int NOPS>
-static int launch_stage_pipe(int S, int r, int B, cudaStream_t st, const MorBatch& M, const double* Xin,
+static int launch_stage_pipe(int S, int r, int B, cudaStream_t st, const MorBatch& M, double* fv, const double* Xin,
                              const double* Xbase, double* Xout, double* Xacc, double t, double h, double c_out,
                              double c_acc, int first) {
     const size_t smem = sizeof(double) * 2 * (NOPS * MB_TM * MP_LDA + MP_TK * MP_LDX);
@@ -277,13 +327,13 @@ static int launch_stage_pipe(int S, int r, int B, cudaStream_t st, const MorBatc
         configured = true;
     }
     dim3 grid((B + MP_TN - 1) / MP_TN, (r + MB_TM - 1) / MB_TM, S);
-    tc_mor_stage_pipe_kernel<NOPS><<<grid, MB_THREADS, smem, st>>>(M, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
+    if (M.F > 0) tc_mor_films_kernel<<<(M.F * B + 255) / 256, 256, 0, st>>>(M, t, fv);
+    tc_mor_stage_pipe_kernel<NOPS><<<grid, MB_THREADS, smem, st>>>(M, fv, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
     return 0;
 }
 
 extern "C" int64_t tc_mor_batch_work_doubles(int32_t S, int32_t r, int32_t F, int32_t B) {
-    (void)F;
-    return 3LL * S * r * B;
+    return 3LL * S * r * B + (int64_t)(F > 0 ? F : 1) * B;
 }
 
 template <int NOPS, int NC>
@@ -307,16 +357,17 @@ extern "C" int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32
     MorBatch M{S, r, F, B, A_body, A_films, B_T, film_surf, film_h0, film_tau, t_link, q_surf};
     const size_t n = (size_t)S * r * B;
     double* o1 = work; double* o2 = work + n; double* acc = work + 2 * n;
+    double* fvtab = work + 3 * n;              // [F][B] film values of the current stage
     const bool dm = use_dmma != 0;
     const bool pipe = use_dmma == 2 && F <= 3 && (r % 2) == 0 && (B % 2) == 0;
     auto stage = [&](const double* Xin, const double* Xb, double* Xout, double* Xacc, double t, double c_out,
                      double c_acc, int first) {
         if (pipe) {
             switch (F) {
-                case 0: launch_stage_pipe<1>(S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
-                case 1: launch_stage_pipe<2>(S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
-                case 2: launch_stage_pipe<3>(S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
-                default: launch_stage_pipe<4>(S, r, B, st, M, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+                case 0: launch_stage_pipe<1>(S, r, B, st, M, fvtab, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+                case 1: launch_stage_pipe<2>(S, r, B, st, M, fvtab, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+                case 2: launch_stage_pipe<3>(S, r, B, st, M, fvtab, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
+                default: launch_stage_pipe<4>(S, r, B, st, M, fvtab, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
             }
             return;
         }
