@@ -159,6 +159,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+struct TcTrue { static constexpr bool value = true; };
+struct TcFalse { static constexpr bool value = false; };
+
 #define MP_TK 16
 #define MP_LDA (MP_TK + 4)     // 20 doubles: rows 16-byte aligned, A-fragment reads conflict free
 #define MP_TN 64
@@ -241,15 +244,11 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
     };
 
     const bool live[2] = {i0 + wm < r, i0 + wm + 8 < r};      // warp-uniform
+    const bool full_tile = i0 + MB_TM <= r;                     // CTA-uniform
     const int nchunks = (r + MP_TK - 1) / MP_TK;
-    load_chunk(0, 0);
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int st = ch & 1;
-        if (ch + 1 < nchunks) { load_chunk(st ^ 1, (ch + 1) * MP_TK); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
-        const double* sA = sA0 + st * A_STAGE;
-        const double* sX = sX0 + st * X_STAGE;
+    // the DMMAs of one k-chunk; RAGGED (last row tile only) skips 8-row strips that lie past r, the
+    // full tiles run without predicates
+    auto mma_chunk = [&](const double* sA, const double* sX, auto ragged) {
 #pragma unroll
         for (int k4 = 0; k4 < MP_TK; k4 += 4) {
             double bf[4];
@@ -259,59 +258,96 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
             for (int o = 0; o < NOPS; ++o)
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
-                    if (!live[a]) continue;          // 8-row strip entirely past r (ragged last row tile)
+                    if (decltype(ragged)::value && !live[a]) continue;
                     const double af = sA[(o * MB_TM + wm + 8 * a + (lane >> 2)) * MP_LDA + k4 + (lane & 3)];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) dmma884(acc[o][a][c][0], acc[o][a][c][1], af, bf[c]);
                 }
         }
+    };
+    load_chunk(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int st = ch & 1;
+        if (ch + 1 < nchunks) { load_chunk(st ^ 1, (ch + 1) * MP_TK); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const double* sA = sA0 + st * A_STAGE;
+        const double* sX = sX0 + st * X_STAGE;
+        if (full_tile) mma_chunk(sA, sX, TcFalse{});
+        else if (live[0]) mma_chunk(sA, sX, TcTrue{});
         __syncthreads();
     }
-    // fused epilogue.  Film weights and input flux belong to a scenario column, B_T to a row: both are
-    // formed once per thread; a thread owns column pairs (B is even), so state traffic moves as double2.
-    const double q_s = M.q_surf[s];
-    double tl[NOPS > 1 ? NOPS - 1 : 1];
-#pragma unroll
-    for (int f = 0; f < NOPS - 1; ++f) tl[f] = M.film_surf[f] == s ? M.t_link[f] : 0.0;
-    double bt[2];
-    bool rok[2];
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int gi = i0 + wm + 8 * a + (lane >> 2);
-        rok[a] = gi < r;
-        bt[a] = rok[a] ? M.B_T[(size_t)s * r + gi] : 0.0;
-    }
-    const double ho = c_out * h, ha = c_acc * h;
-    const size_t row0 = ((size_t)s * r + i0 + wm + (lane >> 2)) * B;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int gb = b0 + wn + 8 * c + 2 * (lane & 3);
-        if (gb >= B) continue;
-        double fvv[NOPS > 1 ? NOPS - 1 : 1][2];
-        double flux[2] = {q_s, q_s};
-#pragma unroll
-        for (int f = 0; f < NOPS - 1; ++f) {
-            const double2 v = *reinterpret_cast<const double2*>(fv + (size_t)f * B + gb);
-            fvv[f][0] = v.x; fvv[f][1] = v.y;
-            if (M.film_surf[f] == s) { flux[0] += v.x * tl[f]; flux[1] += v.y * tl[f]; }
-        }
+
+    // fused epilogue, pass 1: k = -(Z_0 + sum_f film_f Z_f) + B_T * flux per accumulator element, staged
+    // through the (now free) shared memory so that pass 2 can move the state in whole 512-byte rows with
+    // all its loads in flight at once (the accumulators no longer occupy the registers then).
+    constexpr int LDK = MP_TN + 8;                  // 72: double2 stores of a quarter warp hit distinct banks
+    static_assert(MB_TM * LDK <= 2 * (NOPS * MB_TM * MP_LDA + MP_TK * MP_LDX), "stage tile fits the pipeline buffers");
+    double* sK = smem;
+    {
+        const double q_s = M.q_surf[s];
+        double bt[2];
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-            if (!rok[a]) continue;
-            const size_t idx = row0 + (size_t)(8 * a) * B + gb;
-            double kv[2];
+            const int gi = i0 + wm + 8 * a + (lane >> 2);
+            bt[a] = gi < r ? M.B_T[(size_t)s * r + gi] : 0.0;
+        }
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                double z = acc[0][a][c][e];
+        for (int c = 0; c < 4; ++c) {
+            const int cl = wn + 8 * c + 2 * (lane & 3);
+            const int gb = b0 + cl;
+            double fvv[NOPS > 1 ? NOPS - 1 : 1][2];
+            double flux[2] = {q_s, q_s};
 #pragma unroll
-                for (int f = 0; f < NOPS - 1; ++f) z += fvv[f][e] * acc[f + 1][a][c][e];
-                kv[e] = -z + bt[a] * flux[e];
+            for (int f = 0; f < NOPS - 1; ++f) {
+                double2 v = make_double2(0.0, 0.0);
+                if (gb < B) v = *reinterpret_cast<const double2*>(fv + (size_t)f * B + gb);
+                fvv[f][0] = v.x; fvv[f][1] = v.y;
+                if (M.film_surf[f] == s) { const double tl = M.t_link[f]; flux[0] += v.x * tl; flux[1] += v.y * tl; }
             }
-            const double2 xb = *reinterpret_cast<const double2*>(Xbase + idx);
-            if (Xout) *reinterpret_cast<double2*>(Xout + idx) = make_double2(xb.x + ho * kv[0], xb.y + ho * kv[1]);
-            double2 xa = xb;
-            if (!first) xa = *reinterpret_cast<const double2*>(Xacc + idx);
-            *reinterpret_cast<double2*>(Xacc + idx) = make_double2(xa.x + ha * kv[0], xa.y + ha * kv[1]);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                double kv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double z = acc[0][a][c][e];
+#pragma unroll
+                    for (int f = 0; f < NOPS - 1; ++f) z += fvv[f][e] * acc[f + 1][a][c][e];
+                    kv[e] = -z + bt[a] * flux[e];
+                }
+                *reinterpret_cast<double2*>(sK + (wm + 8 * a + (lane >> 2)) * LDK + cl) = make_double2(kv[0], kv[1]);
+            }
+        }
+    }
+    __syncthreads();
+    // pass 2: RK stage update; thread -> rows (tid>>5) + 8j, column pair tid&31
+    {
+        const double ho = c_out * h, ha = c_acc * h;
+        const int cl = 2 * (tid & 31);
+        const int gb = b0 + cl;
+        const int r0 = tid >> 5;
+        if (gb < B) {
+            double2 xb[8], xa[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int gi = i0 + r0 + 8 * j;
+                if (gi < r) {
+                    const size_t idx = ((size_t)s * r + gi) * B + gb;
+                    xb[j] = *reinterpret_cast<const double2*>(Xbase + idx);
+                    if (!first) xa[j] = *reinterpret_cast<const double2*>(Xacc + idx);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int gi = i0 + r0 + 8 * j;
+                if (gi < r) {
+                    const size_t idx = ((size_t)s * r + gi) * B + gb;
+                    const double2 kv = *reinterpret_cast<const double2*>(sK + (r0 + 8 * j) * LDK + cl);
+                    if (Xout) *reinterpret_cast<double2*>(Xout + idx) = make_double2(xb[j].x + ho * kv.x, xb[j].y + ho * kv.y);
+                    const double2 base = first ? xb[j] : xa[j];
+                    *reinterpret_cast<double2*>(Xacc + idx) = make_double2(base.x + ha * kv.x, base.y + ha * kv.y);
+                }
+            }
         }
     }
 }
