@@ -390,7 +390,7 @@ def run_mor(args):
         "data": "synthetic",
         "config": {"workload": f"cfg#3 MOR ensemble S={S} r={r} F={F} B={B}/GPU, time-varying films, RK4 h={h}s",
                    "l2": "operators (8.6 MB) are L2-resident by design; state 3x19.7 MB/GPU streams"},
-        "clocks": clk, "gpu_launches": nsteps * 8,     # 4 stages x (film table + DMMA stage kernel)
+        "clocks": clk, "gpu_launches": nsteps * 5,     # film table + 4 DMMA stage kernels
         "roofline": {"bound": "tensor", "achieved": tflops, "peak": dgemm_tflops, "unit": "TFLOP/s",
                      "frac": tflops / dgemm_tflops, "traffic": None, "kernel": "tc_mor_stage_pipe_kernel<3>",
                      "peak_kind": "torch.matmul fp64 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",

@@ -44,7 +44,8 @@ def _random_case(S, r, F, B, seed):
     return A_body, A_films, B_T, film_surf, h0, tau, t_link, q_surf, X0
 
 
-@pytest.mark.parametrize("S,r,F,B", [(3, 40, 2, 96), (2, 200, 1, 130), (1, 17, 0, 64), (2, 64, 3, 64), (2, 33, 5, 50)])
+@pytest.mark.parametrize("S,r,F,B", [(3, 40, 2, 96), (2, 200, 1, 130), (1, 17, 0, 64), (2, 64, 3, 64), (2, 33, 5, 50),
+                                     (3, 200, 2, 192), (2, 198, 2, 70), (1, 136, 0, 66), (2, 150, 3, 64), (1, 128, 2, 64)])
 @pytest.mark.parametrize("dmma", [2, 1, 0])
 def test_mor_batch_matches_numpy(S, r, F, B, dmma):
     from thermca_b200.mor_batch import MorEnsemble

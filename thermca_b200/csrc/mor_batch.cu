@@ -167,14 +167,28 @@ struct TcFalse { static constexpr bool value = false; };
 #define MP_TN 64
 #define MP_LDX (MP_TN + 4)     // 68 doubles
 
-// film coefficients of every scenario at the stage time, evaluated once per stage (F*B values)
-// instead of once per output element inside the GEMM epilogue
-__global__ void tc_mor_films_kernel(MorBatch M, double t, double* __restrict__ fv) {
-    const int n = M.F * M.B;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int f = i / M.B;
-        fv[i] = film_at(M, f, i - f * M.B, t);
+// film coefficients of every scenario at the three stage times t, t+h/2, t+h of one RK4 step, evaluated once
+// per step (3*F*B values) instead of once per output element inside the GEMM epilogue
+__global__ void tc_mor_films_kernel(MorBatch M, double t, double h, double* __restrict__ fv) {
+    const int fb = M.F * M.B;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * fb; i += gridDim.x * blockDim.x) {
+        const int k = i / fb, j = i - k * fb;
+        const int f = j / M.B;
+        fv[i] = film_at(M, f, j - f * M.B, t + 0.5 * h * k);
     }
+}
+
+// dynamic shared memory of the pipelined kernel: two stages of (NOPS x 72 x 20 operator + 16 x 68 state)
+// doubles, reused as the 72 x 72 staging tile of the epilogue
+__host__ __device__ constexpr int mor_pipe_smem_doubles(int nops) {
+    return 2 * (nops * (MB_TM + 8) * MP_LDA + MP_TK * MP_LDX) > (MB_TM + 8) * (MP_TN + 8)
+               ? 2 * (nops * (MB_TM + 8) * MP_LDA + MP_TK * MP_LDX) : (MB_TM + 8) * (MP_TN + 8);
+}
+
+// a remainder of 1..8 rows past the last full 64-row tile is folded into that tile
+__host__ __device__ __forceinline__ bool mor_fold_rows(int r) {
+    const int rem = r % MB_TM;
+    return r > MB_TM && rem > 0 && rem <= 8;
 }
 
 template <int NOPS>
@@ -184,23 +198,29 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
                          double* __restrict__ Xout, double* __restrict__ Xacc, double t, double h,
                          double c_out, double c_acc, int first) {
     extern __shared__ __align__(16) double smem[];
-    constexpr int A_STAGE = NOPS * MB_TM * MP_LDA;
+    constexpr int TMX = MB_TM + 8;              // rows per operator buffer: tile + one folded 8-row strip
+    constexpr int A_STAGE = NOPS * TMX * MP_LDA;
     constexpr int X_STAGE = MP_TK * MP_LDX;
-    double* sA0 = smem;                         // [2][NOPS][64][20]
+    double* sA0 = smem;                         // [2][NOPS][72][20]
     double* sX0 = smem + 2 * A_STAGE;           // [2][16][68]
     // CTA order: scenario tile fastest, then surface, row tile slowest, so the cheap ragged last row tiles
     // (r % 64 rows) are scheduled last and fill the tail of the final wave
     const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     const int rest = lin / gridDim.x;
     const int s = rest % gridDim.z;
-    const int i0 = (rest / gridDim.z) * MB_TM;
+    const int ty = rest / gridDim.z;
+    const int i0 = ty * MB_TM;
     const int b0 = (lin - rest * gridDim.x) * MP_TN;
     const int r = M.r, B = M.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 16;
     const int wn = (warp >> 2) * 32;
+    // A remainder of at most 8 rows (r = 200: 3 x 64 + 8) is folded into the last full tile: every warp takes
+    // one extra 8x8 block of that strip (columns wn + 8*(warp&3)), so no latency-bound sliver tile exists.
+    const bool ext = mor_fold_rows(r) && ty == (int)gridDim.y - 1;      // CTA-uniform
     const double* Xs = Xin + (size_t)s * r * B;
     double acc[NOPS][2][4][2];
+    double accx[NOPS][2];
 #pragma unroll
     for (int o = 0; o < NOPS; ++o)
 #pragma unroll
@@ -209,7 +229,8 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
             for (int c = 0; c < 4; ++c) acc[o][a][c][0] = acc[o][a][c][1] = 0.0;
 
     // every thread owns the same copy slots in every chunk (MB_THREADS = 256 = 32 rows x 8 pairs):
-    // operator slot q -> operator q/2, row (tid>>3) + 32*(q&1), pair tid&7; state slot q -> k-row (tid>>5) + 8q
+    // operator slot q -> operator q/2, row (tid>>3) + 32*(q&1), pair tid&7; state slot q -> k-row (tid>>5) + 8q;
+    // folded strip: thread -> operator tid>>6, row 64 + ((tid>>3)&7), pair tid&7
     static_assert(MB_THREADS == 256 && MB_TM == 64 && MP_TK == 16 && MP_TN == 64, "copy slot mapping");
     const int a_ri = tid >> 3, a_kp = tid & 7;
     const bool a_in[2] = {i0 + a_ri < r, i0 + a_ri + 32 < r};
@@ -231,8 +252,15 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
             const int o = q >> 1, half = q & 1;
             const double* W = o == 0 ? Wb : Wf + (size_t)(o - 1) * w_stride;
             const bool ok = k_in && a_in[half];
-            cp_async16(sA + a_dst + (o * MB_TM + 32 * half) * MP_LDA,
+            cp_async16(sA + a_dst + (o * TMX + 32 * half) * MP_LDA,
                        ok ? (const void*)(W + a_off + (size_t)(32 * half) * r + k0) : (const void*)Wb, ok ? 16 : 0);
+        }
+        if (ext && tid < NOPS * 64) {
+            const int e_o = tid >> 6, e_ri = (tid >> 3) & 7;
+            const double* W = e_o == 0 ? Wb : Wf + (size_t)(e_o - 1) * w_stride;
+            const bool ok = k_in && i0 + MB_TM + e_ri < r;
+            cp_async16(sA + (e_o * TMX + MB_TM + e_ri) * MP_LDA + 2 * a_kp,
+                       ok ? (const void*)(W + (size_t)(i0 + MB_TM + e_ri) * r + 2 * a_kp + k0) : (const void*)Wb, ok ? 16 : 0);
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -246,43 +274,62 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
     const bool live[2] = {i0 + wm < r, i0 + wm + 8 < r};      // warp-uniform
     const bool full_tile = i0 + MB_TM <= r;                     // CTA-uniform
     const int nchunks = (r + MP_TK - 1) / MP_TK;
-    // the DMMAs of one k-chunk; RAGGED (last row tile only) skips 8-row strips that lie past r, the
-    // full tiles run without predicates
-    auto mma_chunk = [&](const double* sA, const double* sX, auto ragged) {
+    const int cx = warp & 3;                                    // column block of the folded strip
+    // The k loop.  RAGGED (a last row tile that could not be folded) skips 8-row strips that lie past r; EXTRA
+    // adds the folded strip; plain full tiles run without predicates.  One barrier per chunk: once every warp
+    // has passed it, chunk ch is visible AND everybody is done with chunk ch-1, whose buffer the prefetch of
+    // chunk ch+1 may therefore overwrite.
+    auto k_loop = [&](auto ragged, auto extra) {
+        load_chunk(0, 0);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int st = ch & 1;
+            cp_async_wait<0>();
+            __syncthreads();
+            if (ch + 1 < nchunks) load_chunk(st ^ 1, (ch + 1) * MP_TK);
+            const double* sA = sA0 + st * A_STAGE;
+            const double* sX = sX0 + st * X_STAGE;
+            if (decltype(ragged)::value && !live[0]) continue;
 #pragma unroll
-        for (int k4 = 0; k4 < MP_TK; k4 += 4) {
-            double bf[4];
+            for (int k4 = 0; k4 < MP_TK; k4 += 4) {
+                double bf[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) bf[c] = sX[(k4 + (lane & 3)) * MP_LDX + wn + 8 * c + (lane >> 2)];
+                for (int c = 0; c < 4; ++c) bf[c] = sX[(k4 + (lane & 3)) * MP_LDX + wn + 8 * c + (lane >> 2)];
 #pragma unroll
-            for (int o = 0; o < NOPS; ++o)
+                for (int o = 0; o < NOPS; ++o)
 #pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    if (decltype(ragged)::value && !live[a]) continue;
-                    const double af = sA[(o * MB_TM + wm + 8 * a + (lane >> 2)) * MP_LDA + k4 + (lane & 3)];
+                    for (int a = 0; a < 2; ++a) {
+                        if (decltype(ragged)::value && !live[a]) continue;
+                        const double af = sA[(o * TMX + wm + 8 * a + (lane >> 2)) * MP_LDA + k4 + (lane & 3)];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) dmma884(acc[o][a][c][0], acc[o][a][c][1], af, bf[c]);
+                        for (int c = 0; c < 4; ++c) dmma884(acc[o][a][c][0], acc[o][a][c][1], af, bf[c]);
+                    }
+                if (decltype(extra)::value) {
+                    const double bx = sX[(k4 + (lane & 3)) * MP_LDX + wn + 8 * cx + (lane >> 2)];
+#pragma unroll
+                    for (int o = 0; o < NOPS; ++o) {
+                        const double af = sA[(o * TMX + MB_TM + (lane >> 2)) * MP_LDA + k4 + (lane & 3)];
+                        dmma884(accx[o][0], accx[o][1], af, bx);
+                    }
                 }
+            }
         }
+        __syncthreads();
     };
-    load_chunk(0, 0);
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int st = ch & 1;
-        if (ch + 1 < nchunks) { load_chunk(st ^ 1, (ch + 1) * MP_TK); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
-        const double* sA = sA0 + st * A_STAGE;
-        const double* sX = sX0 + st * X_STAGE;
-        if (full_tile) mma_chunk(sA, sX, TcFalse{});
-        else if (live[0]) mma_chunk(sA, sX, TcTrue{});
-        __syncthreads();
+    if (ext) {
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o) accx[o][0] = accx[o][1] = 0.0;
+        k_loop(TcFalse{}, TcTrue{});
+    } else if (full_tile) {
+        k_loop(TcFalse{}, TcFalse{});
+    } else {
+        k_loop(TcTrue{}, TcFalse{});
     }
 
     // fused epilogue, pass 1: k = -(Z_0 + sum_f film_f Z_f) + B_T * flux per accumulator element, staged
     // through the (now free) shared memory so that pass 2 can move the state in whole 512-byte rows with
     // all its loads in flight at once (the accumulators no longer occupy the registers then).
     constexpr int LDK = MP_TN + 8;                  // 72: double2 stores of a quarter warp hit distinct banks
-    static_assert(MB_TM * LDK <= 2 * (NOPS * MB_TM * MP_LDA + MP_TK * MP_LDX), "stage tile fits the pipeline buffers");
+    static_assert(TMX * LDK <= mor_pipe_smem_doubles(NOPS), "stage tile fits the pipeline buffers");
     double* sK = smem;
     {
         const double q_s = M.q_surf[s];
@@ -317,30 +364,44 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
                 }
                 *reinterpret_cast<double2*>(sK + (wm + 8 * a + (lane >> 2)) * LDK + cl) = make_double2(kv[0], kv[1]);
             }
+            if (ext && c == cx) {                    // folded strip: row 64 + lane/4 of the tile
+                const int gi = i0 + MB_TM + (lane >> 2);
+                const double btx = gi < r ? M.B_T[(size_t)s * r + gi] : 0.0;
+                double kv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double z = accx[0][e];
+#pragma unroll
+                    for (int f = 0; f < NOPS - 1; ++f) z += fvv[f][e] * accx[f + 1][e];
+                    kv[e] = -z + btx * flux[e];
+                }
+                *reinterpret_cast<double2*>(sK + (MB_TM + (lane >> 2)) * LDK + cl) = make_double2(kv[0], kv[1]);
+            }
         }
     }
     __syncthreads();
-    // pass 2: RK stage update; thread -> rows (tid>>5) + 8j, column pair tid&31
+    // pass 2: RK stage update; thread -> rows (tid>>5) + 8j (j = 8: the folded strip), column pair tid&31
     {
         const double ho = c_out * h, ha = c_acc * h;
         const int cl = 2 * (tid & 31);
         const int gb = b0 + cl;
         const int r0 = tid >> 5;
+        const int row_end = min(r, i0 + (ext ? TMX : MB_TM));
         if (gb < B) {
-            double2 xb[8], xa[8];
+            double2 xb[9], xa[9];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 9; ++j) {
                 const int gi = i0 + r0 + 8 * j;
-                if (gi < r) {
+                if (gi < row_end) {
                     const size_t idx = ((size_t)s * r + gi) * B + gb;
                     xb[j] = *reinterpret_cast<const double2*>(Xbase + idx);
                     if (!first) xa[j] = *reinterpret_cast<const double2*>(Xacc + idx);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 9; ++j) {
                 const int gi = i0 + r0 + 8 * j;
-                if (gi < r) {
+                if (gi < row_end) {
                     const size_t idx = ((size_t)s * r + gi) * B + gb;
                     const double2 kv = *reinterpret_cast<const double2*>(sK + (r0 + 8 * j) * LDK + cl);
                     if (Xout) *reinterpret_cast<double2*>(Xout + idx) = make_double2(xb[j].x + ho * kv.x, xb[j].y + ho * kv.y);
@@ -356,20 +417,19 @@ template <int NOPS>
 static int launch_stage_pipe(int S, int r, int B, cudaStream_t st, const MorBatch& M, double* fv, const double* Xin,
                              const double* Xbase, double* Xout, double* Xacc, double t, double h, double c_out,
                              double c_acc, int first) {
-    const size_t smem = sizeof(double) * 2 * (NOPS * MB_TM * MP_LDA + MP_TK * MP_LDX);
+    const size_t smem = sizeof(double) * mor_pipe_smem_doubles(NOPS);
     static bool configured = false;
     if (!configured) {
         TC_CUDA(cudaFuncSetAttribute(tc_mor_stage_pipe_kernel<NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((B + MP_TN - 1) / MP_TN, (r + MB_TM - 1) / MB_TM, S);
-    if (M.F > 0) tc_mor_films_kernel<<<(M.F * B + 255) / 256, 256, 0, st>>>(M, t, fv);
+    dim3 grid((B + MP_TN - 1) / MP_TN, mor_fold_rows(r) ? r / MB_TM : (r + MB_TM - 1) / MB_TM, S);
     tc_mor_stage_pipe_kernel<NOPS><<<grid, MB_THREADS, smem, st>>>(M, fv, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
     return 0;
 }
 
 extern "C" int64_t tc_mor_batch_work_doubles(int32_t S, int32_t r, int32_t F, int32_t B) {
-    return 3LL * S * r * B + (int64_t)(F > 0 ? F : 1) * B;
+    return 3LL * S * r * B + 3LL * (F > 0 ? F : 1) * B;
 }
 
 template <int NOPS, int NC>
@@ -393,12 +453,14 @@ extern "C" int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32
     MorBatch M{S, r, F, B, A_body, A_films, B_T, film_surf, film_h0, film_tau, t_link, q_surf};
     const size_t n = (size_t)S * r * B;
     double* o1 = work; double* o2 = work + n; double* acc = work + 2 * n;
-    double* fvtab = work + 3 * n;              // [F][B] film values of the current stage
+    double* fv3 = work + 3 * n;                // [3][F][B] film values at t, t+h/2, t+h of the current step
     const bool dm = use_dmma != 0;
     const bool pipe = use_dmma == 2 && F <= 3 && (r % 2) == 0 && (B % 2) == 0;
-    auto stage = [&](const double* Xin, const double* Xb, double* Xout, double* Xacc, double t, double c_out,
+    // tk: index of the stage time among (t, t+h/2, t+h)
+    auto stage = [&](const double* Xin, const double* Xb, double* Xout, double* Xacc, double t, int tk, double c_out,
                      double c_acc, int first) {
         if (pipe) {
+            double* fvtab = fv3 + (size_t)tk * F * B;
             switch (F) {
                 case 0: launch_stage_pipe<1>(S, r, B, st, M, fvtab, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
                 case 1: launch_stage_pipe<2>(S, r, B, st, M, fvtab, Xin, Xb, Xout, Xacc, t, h, c_out, c_acc, first); break;
@@ -420,10 +482,11 @@ extern "C" int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32
     double* nxt = acc;
     for (int k = 0; k < nsteps; ++k) {
         const double t = t0 + k * h;
-        stage(cur, cur, o1, nxt, t, 0.5, 1.0 / 6.0, 1);
-        stage(o1, cur, o2, nxt, t + 0.5 * h, 0.5, 1.0 / 3.0, 0);
-        stage(o2, cur, o1, nxt, t + 0.5 * h, 1.0, 1.0 / 3.0, 0);
-        stage(o1, cur, nullptr, nxt, t + h, 0.0, 1.0 / 6.0, 0);
+        if (pipe && F > 0) tc_mor_films_kernel<<<(3 * F * B + 255) / 256, 256, 0, st>>>(M, t, h, fv3);
+        stage(cur, cur, o1, nxt, t, 0, 0.5, 1.0 / 6.0, 1);
+        stage(o1, cur, o2, nxt, t + 0.5 * h, 1, 0.5, 1.0 / 3.0, 0);
+        stage(o2, cur, o1, nxt, t + 0.5 * h, 1, 1.0, 1.0 / 3.0, 0);
+        stage(o1, cur, nullptr, nxt, t + h, 2, 0.0, 1.0 / 6.0, 0);
         double* tmp = cur; cur = nxt; nxt = tmp;
     }
     if (cur != X) TC_CUDA(cudaMemcpyAsync(X, cur, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
