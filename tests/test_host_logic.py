@@ -107,3 +107,29 @@ def test_product_path_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "rhs_oracle" not in src and "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_stationary_install_swaps_spsolve_and_fails_loudly_without_gpu():
+    """thermca_b200.stationary routes the reference's steady-state solves (fe_system.py:467-469,
+    lp_system.py:250) through the device PCG; without a CUDA device it must raise, not fall back."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import refenv
+    if not refenv.available():
+        pytest.skip("reference tree not present")
+    refenv.activate()
+    import thermca.fem.fe_system as fes
+    import thermca.lpm.lp_system as lps
+    from thermca_b200 import stationary
+    orig = (fes.spsolve, lps.spsolve)
+    stationary.install()
+    try:
+        assert fes.spsolve is stationary.spd_solve and lps.spsolve is stationary.spd_solve
+        import torch
+        if not torch.cuda.is_available():
+            import scipy.sparse as sp
+            with pytest.raises(RuntimeError):
+                fes.spsolve(sp.identity(3, format="csr"), np.ones(3))
+    finally:
+        stationary.uninstall()
+    assert (fes.spsolve, lps.spsolve) == orig
