@@ -186,6 +186,19 @@ int tc_synth_cuboid(void* cuda_stream, int32_t nx, int32_t ny, int32_t nz, doubl
                     int64_t* slice_ptr, int32_t* col, int16_t* col16, double* val, double* mass, double* adiag,
                     double* q_bottom, double* q_upper);
 
+/* ---- P1 operator build on the device (csrc/assembly.cu) --------------------------------------
+ * Replaces the scikit-fem assembly behind FESystem.fem_matrices_from_skfem (thermca/fem/fe_system.py:322-400)
+ * for linear tetrahedra: per element (key, value) contributions, an in-order segment sum after the caller has
+ * sorted the keys, and the SELL-32 layout of A = scale * row_scale * L the solver kernels read. */
+int tc_p1_tet_contributions(void* cuda_stream, int64_t n_points, int64_t n_tets, const double* points,
+                            const int32_t* tets, int64_t* keys, double* vals, int32_t* mkeys, double* mvals);
+int tc_p1_tri_loads(void* cuda_stream, int64_t n_tris, const double* points, const int32_t* tris, int32_t* keys,
+                    double* vals);
+int tc_segment_sum(void* cuda_stream, int64_t nseg, const int64_t* start, const double* vals, double* out);
+int tc_csr_to_sell(void* cuda_stream, int32_t n, int32_t nslices, const int64_t* indptr, const int32_t* indices,
+                   const double* data, const double* row_scale, double scale, const int64_t* slice_ptr,
+                   int32_t* col, int16_t* col16, double* val, double* diag_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,3 +133,26 @@ def test_stationary_install_swaps_spsolve_and_fails_loudly_without_gpu():
     finally:
         stationary.uninstall()
     assert (fes.spsolve, lps.spsolve) == orig
+
+
+def test_assembly_install_swaps_fem_matrices():
+    """thermca_b200.assembly.install() routes FESystem's operator build (fe_system.py:114-125) to the device."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import refenv
+    if not refenv.available():
+        pytest.skip("reference tree not present")
+    refenv.activate()
+    import thermca.fem.fe_system as fes
+    from thermca_b200 import assembly
+    orig = fes.FESystem.__dict__["fem_matrices_from_skfem"]
+    assembly.install()
+    try:
+        assert fes.FESystem.fem_matrices_from_skfem is assembly.fem_matrices_device
+        import torch
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError):
+                assembly.p1_assemble_device(np.zeros((4, 3)), np.array([[0, 1, 2, 3]]), [])
+    finally:
+        assembly.uninstall()
+    assert fes.FESystem.__dict__["fem_matrices_from_skfem"] is orig

@@ -88,6 +88,10 @@ EXPORTS = {
     "tc_synth_cuboid_counts": (i32, [i32, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "tc_synth_cuboid": (i32, [vp, i32, i32, i32, f64, f64, f64, f64, f64, f64, i64, i64, vp, vp, vp, vp, vp,
                               vp, vp, vp]),
+    "tc_p1_tet_contributions": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, vp]),
+    "tc_p1_tri_loads": (i32, [vp, i64, vp, vp, vp, vp]),
+    "tc_segment_sum": (i32, [vp, i64, vp, vp, vp]),
+    "tc_csr_to_sell": (i32, [vp, i32, i32, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -105,3 +105,43 @@ def sell_to_csr_host(op):
     keep = ~((val == 0.0) & (col == rows))
     m = sp.csr_matrix((val[keep], (rows[keep], col[keep])), shape=(n, op["n_global"]))
     return m
+
+
+def device_mesh_spec(points, tets, tris_heat, tris_film, heat=1000.0, film=10.0, env_temp=20.0, init_temp=20.0,
+                     condy=50.0, vol_capy=8000.0 * 500.0, device=None):
+    """The BASELINE config #2 network (heat on surface 0, constant film on surface 1 to a BoundNode) on an
+    ARBITRARY tetrahedral mesh, with the operator assembled on the device (thermca_b200/assembly.py)."""
+    import torch
+    from .assembly import device_fe_operator
+    op = device_fe_operator(points, tets, [tris_heat, tris_film], condy, vol_capy, device=device)
+    n = op["n"]
+    csr = op.pop("csr")
+    mass = op["mass"]
+    Qi = [ix.cpu().numpy().astype(np.int64) for ix in op["Qs_idx"]]
+    Qv = [v.cpu().numpy() for v in op["Qs_val"]]
+    minv_h = [(1.0 / mass[ix]).cpu().numpy() for ix in op["Qs_idx"]]
+    # film of surface 1 folded into the stored diagonal (thermca/fem/ffe_io.py:57-60)
+    rows = op["Qs_idx"][1]
+    add = film * torch.from_numpy(minv_h[1] * Qv[1]).to(mass.device)
+    indptr, indices = csr["indptr"], csr["indices"]
+    lens = indptr[1:] - indptr[:-1]
+    row_of = torch.repeat_interleave(torch.arange(n, device=mass.device, dtype=torch.int64), lens)
+    dpos = torch.nonzero(indices.to(torch.int64) == row_of).ravel()          # one stored diagonal per row
+    if int(dpos.numel()) != n:
+        raise ValueError("mesh has a vertex that belongs to no tetrahedron")
+    k_diag = dpos[rows] - indptr[rows]
+    pos = op["slice_ptr"][rows >> 5] + 32 * k_diag + (rows & 31)
+    op["val"][pos] += add
+    op["adiag"][rows] += add
+    areas = op["surf_areas"]
+    part = {
+        "dof": np.int64(n), "init_temp": np.float64(init_temp),
+        "A_body": None, "A_data": None, "M_inv": None, "sell": op,
+        "B_idx": Qi, "B_val": [m * q for m, q in zip(minv_h, Qv)],
+        "C_idx": Qi, "C_val": c_surf_columns(Qv),
+        "surf_areas": areas, "S": np.int64(2), "films": np.array([film]),
+        "film_surf_idxs": np.array([1], dtype=np.int64), "surf_net_idxs": np.array([1, 2], dtype=np.int64),
+        "link_elem_net_idxs": np.array([0], dtype=np.int64), "film_didx": [], "film_adata": [],
+        "dock_areas": areas[[1]], "var_film_rc_idx": None, "tdep": None,
+    }
+    return single_part_network(part, heat, film, env_temp)
