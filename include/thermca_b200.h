@@ -199,6 +199,17 @@ int tc_csr_to_sell(void* cuda_stream, int32_t n, int32_t nslices, const int64_t*
                    const double* data, const double* row_scale, double scale, const int64_t* slice_ptr,
                    int32_t* col, int16_t* col16, double* val, double* diag_out);
 
+/* ---- orthogonalisation kernels of the inverse-Krylov MOR basis build (csrc/krylov.cu) ------------
+ * Replace the modified Gram-Schmidt loop of arnoldi_iteration (thermca/fem/mor_io.py:203-217): v is
+ * orthogonalised against the first k columns of the column-major Q (column j at Q + j*ld) by `passes`
+ * rounds of classical Gram-Schmidt; |v|^2 afterwards goes to nrm2_out[0] (device memory), the summed
+ * projection coefficients to h_out[0..k) if not NULL.  work: tc_krylov_work_doubles(k_max) doubles. */
+int64_t tc_krylov_work_doubles(int32_t k_max);
+int tc_krylov_orthogonalize(void* cuda_stream, int64_t n, int32_t k, const double* Q, int64_t ld, double* v,
+                            int32_t passes, double* work, double* h_out, double* nrm2_out);
+/* out = v / sqrt(nrm2[0]) */
+int tc_krylov_normalize(void* cuda_stream, int64_t n, const double* v, const double* nrm2, double* out);
+
 #ifdef __cplusplus
 }
 #endif

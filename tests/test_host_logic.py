@@ -156,3 +156,25 @@ def test_assembly_install_swaps_fem_matrices():
     finally:
         assembly.uninstall()
     assert fes.FESystem.__dict__["fem_matrices_from_skfem"] is orig
+
+
+def test_mor_basis_install_keeps_disk_cache_key():
+    """thermca_b200.mor_basis.install() swaps mor_io.transform for a device build under the SAME cache name
+    (thermca/_utils/func_tools.py:79-80: '<func.__name__>_<hash(args)>.pickle')."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import refenv
+    if not refenv.available():
+        pytest.skip("reference tree not present")
+    refenv.activate()
+    import thermca.fem.mor_io as mio
+    from thermca_b200 import mor_basis
+    orig = mio.transform
+    mor_basis.install()
+    try:
+        assert mio.transform is not orig
+        assert mio.transform.__name__ == "transform" == orig.__name__
+        assert mio.transform.__wrapped__.__name__ == "transform"
+    finally:
+        mor_basis.uninstall()
+    assert mio.transform is orig

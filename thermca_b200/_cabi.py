@@ -92,6 +92,9 @@ EXPORTS = {
     "tc_p1_tri_loads": (i32, [vp, i64, vp, vp, vp, vp]),
     "tc_segment_sum": (i32, [vp, i64, vp, vp, vp]),
     "tc_csr_to_sell": (i32, [vp, i32, i32, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]),
+    "tc_krylov_work_doubles": (i64, [i32]),
+    "tc_krylov_orthogonalize": (i32, [vp, i64, i32, vp, i64, vp, i32, vp, vp, vp]),
+    "tc_krylov_normalize": (i32, [vp, i64, vp, vp, vp]),
 }
 
 _lib = None
