@@ -144,6 +144,12 @@ int tc_pcg_stats(tc_handle h, int64_t* stats4);
 int tc_sell_spmv(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, const int64_t* slice_ptr,
                  const int32_t* col, const int16_t* col16, const double* val, const double* x, double* y,
                  const double* b, const double* mass, double shift, int32_t grid_blocks);
+/* One traced link program (thermca_b200/trace.py: int32[4] per instruction) evaluated for m argument pairs:
+ * what one call of a film / conductance closure `f(T0, T1, matl)` (thermca/network.py:781-785) returns.
+ * tab_dir[2t] = offset of table t in tab_arena, tab_dir[2t+1] = its length (x values, then y values). */
+int tc_vm_eval(void* cuda_stream, const int32_t* code, int32_t n_instr, int32_t result, const double* consts,
+               const int32_t* tab_dir, const double* tab_arena, const double* inputs, const double* a0,
+               const double* a1, int32_t m, double* out);
 /* Jacobi-PCG on (M + shift K): solves mass*(I + shift*A) x = mass*rhs; returns iterations in *iters (host) */
 int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, const int64_t* slice_ptr,
                  const int32_t* col, const double* val, const double* mass, const double* adiag,

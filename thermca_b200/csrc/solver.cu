@@ -926,6 +926,31 @@ extern "C" int tc_pcg_stats(tc_handle s, int64_t* stats4) {
 }
 
 // ---- stand-alone entry points --------------------------------------------------------------------
+// One traced link program evaluated for m argument pairs (parity hook for the interpreter of vm.cuh)
+__global__ void tc_vm_eval_kernel(const int* __restrict__ code, int n_instr, int result, const double* __restrict__ consts,
+                                  const int* __restrict__ tab_dir, const double* __restrict__ tab_arena,
+                                  const double* __restrict__ inputs, const double* __restrict__ a0,
+                                  const double* __restrict__ a1, int m, double* __restrict__ out) {
+    __shared__ int dir[4];
+    if (threadIdx.x == 0) { dir[0] = 0; dir[1] = n_instr; dir[2] = 0; dir[3] = result; }
+    __syncthreads();
+    double reg[TC_VM_MAX];
+    TcTables tb{tab_dir, tab_arena};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+        out[i] = tc_vm_run(code, consts, dir, 0, tb, inputs, a0[i], a1 ? a1[i] : 0.0, reg);
+}
+
+extern "C" int tc_vm_eval(void* cuda_stream, const int32_t* code, int32_t n_instr, int32_t result, const double* consts,
+                          const int32_t* tab_dir, const double* tab_arena, const double* inputs,
+                          const double* a0, const double* a1, int32_t m, double* out) {
+    TC_CHECK(n_instr > 0 && n_instr <= TC_VM_MAX && result >= 0 && result < n_instr, "program length out of range");
+    if (m <= 0) return 0;
+    tc_vm_eval_kernel<<<(m + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(code, n_instr, result, consts, tab_dir, tab_arena,
+                                                                           inputs, a0, a1, m, out);
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int tc_sell_spmv(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
                             const int64_t* slice_ptr, const int32_t* col, const int16_t* col16, const double* val,
                             const double* x, double* y, const double* b, const double* mass, double shift,
