@@ -241,3 +241,23 @@ def lp_tdep():
 
 
 MODELS["lp_tdep"] = lp_tdep
+
+
+def steel_sheet():
+    """The LPPart steel sheet of the ``Result`` doctest (thermca/resultdata.py:81-131): its printed
+    temperature table is a known answer of the reference for an LP transient."""
+    steel = Solid(dens=8000.0, spec_heat=500.0, condy=50.0)
+    with Asm() as cuboid:
+        block = Cube(width=0.5, hgt=1.0, depth=0.05, hgt_div=10)
+        face = block.face
+        Surf(name="upper", faces=[face.left, face.right, face.front, face.back, face.top])
+        Surf(name="btm", faces=[face.btm])
+    with Model() as model:
+        sheet = LPPart(asm=cuboid, matl=steel, name="sheet")
+        env = BoundNode(temp=20.0, posn=(-0.3, 0.5, 0.025), name="env")
+        FilmLink(sheet.surf.upper, env, film=10.0)
+        HeatSource(sheet.surf.btm, heat=1000.0, name="src")
+    return Network(model), dict(time_span=[0.0, 36000.0], method="RK45")
+
+
+MODELS["steel_sheet"] = steel_sheet

@@ -90,6 +90,20 @@ def test_link_results_and_part_views_through_dropin(dropin):
     assert np.allclose(res[part.surf.top].temp([10.0, t_end]), ref[part2.surf.top].temp([10.0, t_end]), rtol=1e-10)
 
 
+def test_result_doctest_table_through_dropin(dropin):
+    """The printed table of the ``Result`` doctest (thermca/resultdata.py:125-131): LPPart steel sheet,
+    spatially interpolated temperatures from the reference's own post-processing on our collector."""
+    from numpy import geomspace
+    import ref_models
+    net, kw = ref_models.steel_sheet()
+    res = net.sim(tuple(kw["time_span"]), progress_bar=False)
+    sheet = net._lp_parts[0] if hasattr(net, "_lp_parts") else [e for e in net.model.elems if e.name == "sheet"][0]
+    frame = res[sheet].temp_frame(time=geomspace(0.1, 36000.0, num=5), lctn=[(0.0, 0.0, 0.0), (0.0, 1.0, 0.0)])
+    table = np.array([[0.010217, 0.000268], [0.249103, 0.006545], [5.769231, 0.157884], [83.300245, 3.310066],
+                      [253.019457, 45.451702]])
+    assert np.allclose(frame.to_numpy(), table, rtol=0, atol=5.1e-7)       # the digits the doctest prints
+
+
 def test_unknown_method_and_untraceable_callable(dropin):
     from thermca import Model, Node, BoundNode, CondLink, Network
     from thermca_b200.trace import UntraceableError
