@@ -113,6 +113,11 @@ int tc_get_state(tc_handle h, double* y_dev);
 /* history ring written on the device after accepted steps (store_results, solver.py:393-424):
  * hist_io[capacity][n_state - u], hist_net[capacity][1 + 3N + 2 nnz] = time | T | capy | heat | cond | clean */
 int tc_set_history(tc_handle h, double* hist_io_dev, double* hist_net_dev, int32_t capacity, int32_t num_skip);
+/* Probe mode of the history (results at scale): with n_probe > 0 a row of hist_io holds only the listed part
+ * DOFs, hist_io[capacity][n_probe] (indices into the part block of the state, i.e. the io_temp layout of
+ * solver.py:315-316), instead of the full part state the reference copies per stored step; n_probe = 0
+ * restores full rows.  Call before tc_set_history. */
+int tc_set_probes(tc_handle h, const int64_t* probe_idx_dev, int32_t n_probe);
 int tc_rk_begin(tc_handle h, int32_t method, double t0, double t_end, double rtol, double atol,
                 double max_step, double first_step);
 /* Enqueue up to max_attempts step attempts (one CUDA graph replay each); stops early once the

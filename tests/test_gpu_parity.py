@@ -304,3 +304,28 @@ def test_ros2_with_implicit_lp_part(torch_cuda, golden):
     assert out["status"] == 0 and out["times"][-1] == 300.0 and out["pcg"]["solves"] > 0
     assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=2e-4)
     assert np.allclose(out["io_temps"][-1], tight["io_temps"][-1], rtol=2e-4)
+
+
+def test_probe_history_matches_full_history(torch_cuda, golden):
+    """Results at scale: the probe ring stores the selected part DOFs of every accepted step; values and step
+    sequence equal the full-history run, the final field is fetched once."""
+    from thermca_b200.device import DeviceSolver
+    from thermca_b200.solver import simulate
+    spec, ex = golden("plate_ffe_var")
+    sim = ex["sim"]
+    args = (float(sim["t0"]), float(sim["t1"]), float(sim["rel_tol"]), float(sim["abs_tol"]), str(sim["method"]))
+    dev = DeviceSolver(spec)
+    full = dev.run_rk(*args)
+    dev.close()
+    probes = np.array([0, 7, 511, 934, 3])
+    res = simulate(spec, args[:2], args[2], args[3], args[4], probe_dofs=probes)
+    assert res["probes"] and res["probe_temps"].shape == (len(full["times"]), len(probes))
+    assert np.array_equal(res["times"], full["times"])
+    assert np.array_equal(res["net_temps"], full["net_temps"])
+    assert np.array_equal(res["probe_temps"], full["io_temps"][:, probes])
+    assert np.array_equal(res["final_io_temps"], full["io_temps"][-1])
+    # implicit path and thinning
+    res2 = simulate(spec, (0.0, 60.0), 1e-4, 1e-6, "ROS2_PCG", num_res_skip=2, probe_dofs=probes[:2])
+    assert res2["probe_temps"].shape[1] == 2 and len(res2["times"]) == res2["probe_temps"].shape[0]
+    with pytest.raises(IndexError):
+        simulate(spec, (0.0, 1.0), probe_dofs=[10 ** 6])

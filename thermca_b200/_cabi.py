@@ -59,6 +59,7 @@ EXPORTS = {
     "tc_set_state": (i32, [vp, vp]),
     "tc_get_state": (i32, [vp, vp]),
     "tc_set_history": (i32, [vp, vp, vp, i32, i32]),
+    "tc_set_probes": (i32, [vp, vp, i32]),
     "tc_rk_begin": (i32, [vp, i32, f64, f64, f64, f64, f64, f64]),
     "tc_rk_advance": (i32, [vp, i32, i32]),
     "tc_get_info": (i32, [vp, C.POINTER(i64), C.POINTER(f64), C.POINTER(f64)]),

@@ -186,17 +186,24 @@ __global__ void tc_error_control_kernel(long long n, const double* __restrict__ 
 __global__ void tc_accept_kernel(long long n, long long u, double* __restrict__ y,
                                  const double* __restrict__ ynew, double* __restrict__ k0,
                                  const double* __restrict__ klast, const int* __restrict__ fl,
-                                 double* __restrict__ hist_io) {
+                                 double* __restrict__ hist_io, const long long* __restrict__ probe_idx,
+                                 int n_probe) {
     if (fl[FL_DONE] == 1 || !fl[FL_ACC_THIS]) return;
     const int slot = fl[FL_STORE_SLOT];
     const long long nio = n - u;
+    const bool full_rows = probe_idx == nullptr;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         const double v = ynew[i];
         y[i] = v;
         if (k0) k0[i] = klast[i];
-        if (slot >= 0 && hist_io && i >= u) hist_io[(long long)slot * nio + (i - u)] = v;
+        if (full_rows && slot >= 0 && hist_io && i >= u) hist_io[(long long)slot * nio + (i - u)] = v;
     }
+    // probe mode: a history row holds only the selected part DOFs (indices into the part block of the state)
+    if (!full_rows && slot >= 0 && hist_io)
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_probe;
+             i += (long long)gridDim.x * blockDim.x)
+            hist_io[(long long)slot * n_probe + i] = ynew[u + probe_idx[i]];
 }
 // network snapshot + flag finalisation (single block)
 __global__ void tc_snapshot_kernel(TcNetParams P, const double* __restrict__ ctrl, int* fl,
@@ -282,6 +289,7 @@ struct tc_solver {
     double* pin_ctrl = nullptr;
     // history
     double* hist_io = nullptr; double* hist_net = nullptr; int capacity = 0; int num_skip = 0;
+    const long long* probe_idx = nullptr; int n_probe = 0;     // probe mode of the history (tc_set_probes)
     // RK
     int method = TC_RK45; int n_stages = 6;
     cudaGraphExec_t rk_graph = nullptr;
@@ -497,6 +505,14 @@ extern "C" int tc_get_state(tc_handle s, double* y_dev) {
     TC_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
+extern "C" int tc_set_probes(tc_handle s, const int64_t* probe_idx_dev, int32_t n_probe) {
+    TC_CHECK(s, "null handle");
+    TC_CHECK(n_probe >= 0, "negative probe count");
+    s->probe_idx = n_probe > 0 ? (const long long*)probe_idx_dev : nullptr;
+    s->n_probe = n_probe > 0 ? n_probe : 0;
+    return 0;
+}
+
 extern "C" int tc_set_history(tc_handle s, double* hist_io, double* hist_net, int32_t capacity, int32_t num_skip) {
     TC_CHECK(s, "null");
     s->hist_io = hist_io; s->hist_net = hist_net; s->capacity = capacity; s->num_skip = num_skip;
@@ -570,7 +586,7 @@ static int enqueue_rk_attempt(tc_solver* s) {
     Le.nk = ns + 1;
     for (int j = 0; j <= ns; ++j) { Le.k[j] = s->K[j]; Le.c[j] = T.E[j]; }
     tc_error_control_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
-    tc_accept_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, s->K[0], s->K[ns], s->flags, s->hist_io);
+    tc_accept_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, s->K[0], s->K[ns], s->flags, s->hist_io, s->probe_idx, s->n_probe);
     tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net);
     s->launches += ns + 4;   // stage combinations, prepare, error control, accept, snapshot
     return 0;
@@ -610,7 +626,7 @@ static int store_initial(tc_solver* s) {
     TC_CUDA(cudaMemcpyAsync(s->flags + FL_STORE_SLOT, &slot0, sizeof(int), cudaMemcpyHostToDevice, s->stream));
     TC_CUDA(cudaMemcpyAsync(s->flags + FL_STORED, &one, sizeof(int), cudaMemcpyHostToDevice, s->stream));
     tc_accept_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->n_state, s->net.u, s->ynew, s->y, nullptr, nullptr,
-                                                          s->flags, s->hist_io);
+                                                          s->flags, s->hist_io, s->probe_idx, s->n_probe);
     tc_snapshot_kernel<<<1, 256, 0, s->stream>>>(s->net, s->ctrl, s->flags, s->hist_net);
     int zero = 0, m1 = -1;
     TC_CUDA(cudaMemcpyAsync(s->flags + FL_ACC_THIS, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
@@ -868,7 +884,8 @@ static int enqueue_ros2_attempt(tc_solver* s) {
     TcLin Le{};
     Le.nk = 2; Le.k[0] = s->K[1]; Le.c[0] = 0.5; Le.k[1] = s->K[4]; Le.c[1] = 0.5;
     tc_error_control_kernel<<<G, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
-    tc_accept_kernel<<<G, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, nullptr, nullptr, s->flags, s->hist_io);
+    tc_accept_kernel<<<G, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, nullptr, nullptr, s->flags, s->hist_io, s->probe_idx,
+                                        s->n_probe);
     tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net);
     return 0;
 }

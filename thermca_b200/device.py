@@ -570,16 +570,33 @@ class DeviceSolver:
         return out[: self.n_state].cpu().numpy()
 
     # -- history ring --------------------------------------------------------------------------------------
+    def set_probes(self, probe_dofs):
+        """Results at scale: store only the listed part DOFs (indices into the part block of
+        the state, the ``io_temp`` layout of thermca/solver.py:315-316) per accepted step instead of the full part
+        state; network temperatures (which include every surface mean) are always stored.  ``None`` restores full
+        rows.  The full field stays on the device and is fetched on demand with ``get_state()``."""
+        if probe_dofs is None:
+            self._probe_idx = None
+            _cabi.check(self.lib.tc_set_probes(self._handle, C.c_void_p(0), 0))
+            return
+        idx = np.ascontiguousarray(probe_dofs, dtype=np.int64).ravel()
+        if idx.size and (idx.min() < 0 or idx.max() >= self.n_io):
+            raise IndexError("probe DOF outside the part block of the state")
+        self._probe_idx = self._up(idx) if idx.size else None
+        self._n_probe = int(idx.size)
+        _cabi.check(self.lib.tc_set_probes(self._handle, self._p(self._probe_idx), int(idx.size)))
+
     def _alloc_history(self, num_skip):
         torch = self.torch
         w_net = 1 + 3 * self.N + 2 * self.nnz
-        per = 8 * (self.n_io + w_net)
+        self._io_width = self._n_probe if getattr(self, "_probe_idx", None) is not None else self.n_io
+        per = 8 * (self._io_width + w_net)
         cap = int(max(8, min(8192, self.history_bytes // max(per, 1))))
         self.capacity = cap
-        self.hist_io = torch.zeros((cap, max(self.n_io, 1)), dtype=torch.float64, device=self.dev)
+        self.hist_io = torch.zeros((cap, max(self._io_width, 1)), dtype=torch.float64, device=self.dev)
         self.hist_net = torch.zeros((cap, w_net), dtype=torch.float64, device=self.dev)
         torch.cuda.synchronize(self.dev)
-        _cabi.check(self.lib.tc_set_history(self._handle, self._p(self.hist_io) if self.n_io else C.c_void_p(0),
+        _cabi.check(self.lib.tc_set_history(self._handle, self._p(self.hist_io) if self._io_width else C.c_void_p(0),
                                             self._p(self.hist_net), cap, int(num_skip)))
 
     def info(self):
@@ -595,7 +612,7 @@ class DeviceSolver:
         self.stream.synchronize()
         if n:
             net = self.hist_net[:n].cpu().numpy()
-            io = self.hist_io[:n, : self.n_io].cpu().numpy() if self.n_io else np.zeros((n, 0))
+            io = self.hist_io[:n, : self._io_width].cpu().numpy() if self._io_width else np.zeros((n, 0))
             out["net"].append(net)
             out["io"].append(io)
         _cabi.check(self.lib.tc_reset_history(self._handle))
@@ -603,11 +620,11 @@ class DeviceSolver:
     def _collect(self, out):
         N, nnz = self.N, self.nnz
         net = np.vstack(out["net"]) if out["net"] else np.zeros((0, 1 + 3 * N + 2 * nnz))
-        io = np.vstack(out["io"]) if out["io"] else np.zeros((0, self.n_io))
+        io = np.vstack(out["io"]) if out["io"] else np.zeros((0, self._io_width))
         return {"times": net[:, 0].copy(), "net_temps": net[:, 1:1 + N].copy(),
                 "net_capys": net[:, 1 + N:1 + 2 * N].copy(), "net_heat_srcs": net[:, 1 + 2 * N:1 + 3 * N].copy(),
                 "cond_data": net[:, 1 + 3 * N:1 + 3 * N + nnz].copy(), "clean_data": net[:, 1 + 3 * N + nnz:].copy(),
-                "io_temps": io}
+                "io_temps": io, "probes": getattr(self, "_probe_idx", None) is not None}
 
     # -- integrators -----------------------------------------------------------------------------------------
     def run_rk(self, t0, t1, rtol=1e-3, atol=1e-6, method="RK45", num_skip=0, max_step=np.inf,

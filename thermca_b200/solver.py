@@ -93,6 +93,39 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
     return coll
 
 
+def simulate(net, time_span, rel_tol=1e-3, abs_tol=1e-6, method="RK45", num_res_skip=0, probe_dofs=(), **options):
+    """Results at scale: the same solve as ``Network.sim`` without the per-step copies that
+    dominate the reference at 10^6..10^7 DOF (``store_results``, thermca/solver.py:393-424: all part DOFs, a dense
+    N x N conductance matrix and a DOK per stored step; ``ResultData.from_collector``, resultdata.py:694-779).
+
+    Per accepted step the device ring keeps the network vector (node temperatures incl. every surface mean,
+    capacities, heat sources, conductance data) and the part DOFs listed in ``probe_dofs`` (indices into the part
+    block of the state = the reference's ``io_temp`` layout).  The full field is downloaded once, at the end.
+    Returns a dict: ``times, net_temps, net_capys, net_heat_srcs, cond_data, clean_data`` (CSR data order of
+    ``net.run_cond``), ``probe_temps`` (steps x probes) and ``final_io_temps``."""
+    t0, t1 = float(time_span[0]), float(time_span[1])
+    if not isinstance(method, str):
+        method = getattr(method, "__name__", str(method))
+    spec = lower_network(net) if not isinstance(net, dict) else net
+    dev = DeviceSolver(spec)
+    try:
+        dev.set_probes(np.asarray(probe_dofs, dtype=np.int64))
+        if method in ("RK45", "RK23"):
+            res = dev.run_rk(t0, t1, rel_tol, abs_tol, method, num_res_skip, max_step=options.get("max_step", np.inf),
+                             first_step=options.get("first_step"))
+        elif method in IMPLICIT_METHODS:
+            res = dev.run_ros2(t0, t1, rel_tol, abs_tol, num_res_skip, max_step=options.get("max_step", np.inf),
+                               first_step=options.get("first_step"), pcg_rtol=options.get("pcg_rtol", 1e-8))
+        else:
+            raise ValueError(f"unknown integration method {method!r}")
+        u = int(spec["u"])
+        res["final_io_temps"] = dev.get_state()[u:]
+    finally:
+        dev.close()
+    res["probe_temps"] = res.pop("io_temps")
+    return res
+
+
 _original = None
 _original_diag = {}
 
