@@ -1,0 +1,23 @@
+"""The fused peer-memory theta/PCG kernel of csrc/dist.cu on ONE GPU (world size 1: no neighbours, the mailbox
+reduction degenerates to the local sum) must reproduce the single-GPU solver.  The multi-rank run of the same
+script is `torchrun --nproc-per-node N scripts/dist_check.py` (N = 2, 8 verified; see profiles/README.md)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dist_kernel_world1_matches_single_gpu_solver():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dist_check.py")], env=env, capture_output=True,
+                       text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "dist_check ok" in r.stdout
