@@ -41,6 +41,7 @@ typedef struct {
     const int64_t* ent_start;       /* dev */
     const int32_t* ent_idx;         /* dev: index into the stacked state */
     const double* ent_w;            /* dev */
+    int32_t n_iarena, n_darena;     /* arena lengths in words (the network kernel warms its L1 with them) */
 } tc_net_desc;
 
 /* ---- full-order FE part (replaces FFEIO, thermca/fem/ffe_io.py:8-83 at run time) ------- */

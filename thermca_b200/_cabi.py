@@ -21,7 +21,7 @@ class NetDesc(C.Structure):
                [(n, i32) for n in ("o_T", "o_heat", "o_capy", "o_vol", "o_volcapy", "o_condy", "o_cond",
                                    "o_clean", "o_calc", "o_inputs", "o_indptr", "o_indices", "o_diag")] + \
                [("n_mean_jobs", i32), ("n_mean_blocks", i32), ("job_of_block", vp), ("first_block", vp),
-                ("nblk", vp), ("ent_start", vp), ("ent_idx", vp), ("ent_w", vp)]
+                ("nblk", vp), ("ent_start", vp), ("ent_idx", vp), ("ent_w", vp), ("n_iarena", i32), ("n_darena", i32)]
 
 
 class FfeDesc(C.Structure):

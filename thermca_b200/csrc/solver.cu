@@ -357,6 +357,7 @@ extern "C" int tc_set_network(tc_handle s, const tc_net_desc* d) {
     P.cmds = d->iarena + d->cmds_off;
     P.prog_dir = d->iarena + d->prog_dir_off;
     P.tab_dir = d->iarena + d->tab_dir_off;
+    P.n_iarena = d->n_iarena; P.n_darena = d->n_darena;
     P.N = d->N; P.u = d->u; P.nnz = d->nnz;
     P.o_T = d->o_T; P.o_heat = d->o_heat; P.o_capy = d->o_capy; P.o_vol = d->o_vol;
     P.o_volcapy = d->o_volcapy; P.o_condy = d->o_condy; P.o_cond = d->o_cond; P.o_clean = d->o_clean;
@@ -951,10 +952,10 @@ __global__ void tc_vm_eval_kernel(const int* __restrict__ code, int n_instr, int
     __shared__ int dir[4];
     if (threadIdx.x == 0) { dir[0] = 0; dir[1] = n_instr; dir[2] = 0; dir[3] = result; }
     __syncthreads();
-    double reg[TC_VM_MAX];
+    extern __shared__ double sreg[];            // [n_instr][blockDim]
     TcTables tb{tab_dir, tab_arena};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
-        out[i] = tc_vm_run(code, consts, dir, 0, tb, inputs, a0[i], a1 ? a1[i] : 0.0, reg);
+        out[i] = tc_vm_run(code, consts, dir, 0, tb, inputs, a0[i], a1 ? a1[i] : 0.0, sreg + threadIdx.x, blockDim.x);
 }
 
 extern "C" int tc_vm_eval(void* cuda_stream, const int32_t* code, int32_t n_instr, int32_t result, const double* consts,
@@ -962,7 +963,14 @@ extern "C" int tc_vm_eval(void* cuda_stream, const int32_t* code, int32_t n_inst
                           const double* a0, const double* a1, int32_t m, double* out) {
     TC_CHECK(n_instr > 0 && n_instr <= TC_VM_MAX && result >= 0 && result < n_instr, "program length out of range");
     if (m <= 0) return 0;
-    tc_vm_eval_kernel<<<(m + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(code, n_instr, result, consts, tab_dir, tab_arena,
+    const size_t smem = sizeof(double) * 64 * (size_t)n_instr;
+    static bool configured = false;
+    if (!configured) {
+        TC_CUDA(cudaFuncSetAttribute(tc_vm_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 400));
+        configured = true;
+    }
+    TC_CHECK(n_instr <= 400, "program too long for the stand-alone evaluator");
+    tc_vm_eval_kernel<<<(m + 63) / 64, 64, smem, (cudaStream_t)cuda_stream>>>(code, n_instr, result, consts, tab_dir, tab_arena,
                                                                            inputs, a0, a1, m, out);
     TC_CUDA(cudaGetLastError());
     return 0;

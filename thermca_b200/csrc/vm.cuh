@@ -49,20 +49,35 @@ __device__ __forceinline__ double tc_interp(const TcTables& tb, int t, double x)
 __device__ double tc_vm_run(const int* __restrict__ iarena, const double* __restrict__ darena,
                             const int* __restrict__ prog_dir, int prog, const TcTables& tb,
                             const double* __restrict__ inputs, double a0, double a1,
-                            double* __restrict__ reg) {
+                            double* __restrict__ regs, int stride = 1) {
+    // value k lives at regs[k * stride]: stride 1 for a private array, blockDim for a shared-memory file
+    struct RegFile {
+        double* p; int s;
+        __device__ __forceinline__ double& operator[](int k) const { return p[k * s]; }
+    } reg{regs, stride};
     const int4* code = reinterpret_cast<const int4*>(iarena + prog_dir[4 * prog]);
     const int n = prog_dir[4 * prog + 1];
     const double* consts = darena + prog_dir[4 * prog + 2];
+    // The interpreter is a chain of dependent latencies (fetch -> dispatch -> operands -> op), so the next
+    // instruction word is fetched before the current one is dispatched, and the frequent cheap operations
+    // (leaves, + - *) are decided with two compares instead of the jump table of the general switch.
+    int4 nxt = code[0];
     for (int k = 0; k < n; ++k) {
-        const int4 ins = code[k];
+        const int4 ins = nxt;
+        if (k + 1 < n) nxt = code[k + 1];
         double v;
+        if (ins.x <= OP_MUL && ins.x != OP_INPUT) {
+            if (ins.x >= OP_ADD) {
+                const double a = reg[ins.y], b = reg[ins.z];
+                v = ins.x == OP_ADD ? __dadd_rn(a, b) : (ins.x == OP_SUB ? __dsub_rn(a, b) : __dmul_rn(a, b));
+            } else {
+                v = ins.x == OP_CONST ? consts[ins.y] : (ins.y == 0 ? a0 : a1);
+            }
+            reg[k] = v;
+            continue;
+        }
         switch (ins.x) {
-            case OP_ARG: v = ins.y == 0 ? a0 : a1; break;
-            case OP_CONST: v = consts[ins.y]; break;
             case OP_INPUT: v = inputs[ins.y]; break;
-            case OP_ADD: v = __dadd_rn(reg[ins.y], reg[ins.z]); break;
-            case OP_SUB: v = __dsub_rn(reg[ins.y], reg[ins.z]); break;
-            case OP_MUL: v = __dmul_rn(reg[ins.y], reg[ins.z]); break;
             case OP_DIV: v = __ddiv_rn(reg[ins.y], reg[ins.z]); break;
             case OP_POW: v = pow(reg[ins.y], reg[ins.z]); break;
             case OP_MIN: { double a = reg[ins.y], b = reg[ins.z]; v = (isnan(a) || isnan(b)) ? (a + b) : fmin(a, b); } break;

@@ -18,7 +18,7 @@ from .spec import state_offsets
 # command opcodes, keep in sync with csrc/network.cuh
 (C_END, C_SET_TU, C_SURF_MEAN, C_INPUTS, C_MATL_GROUP, C_CAPY, C_FLOW_CONST, C_FLOW_FUNC, C_FILM_FUNC,
  C_HEAT_FUNC, C_FLUX_FUNC, C_BOUND_FUNC, C_PART_FILMS, C_LP_UPDATE, C_LP2LP, C_LP_LEAK, C_STAT, C_DIAG,
- C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D, C_LP_TDEP) = range(23)
+ C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D, C_LP_TDEP, C_FUNCS) = range(24)
 
 MEAN_ENTRIES_PER_BLOCK = 4096
 MEAN_MAX_BLOCKS_PER_JOB = 64
@@ -258,18 +258,27 @@ class DeviceSolver:
         if len(fc["didx"]):
             cmd(C_FLOW_CONST, len(fc["didx"]), A.add_i(fc["didx"]), A.add_i(fc["i0"]), A.add_i(fc["i1"]),
                 A.add_d(fc["vol_flow"]))
+        # closures: one command; groups evaluated concurrently (a warp each), applied in the reference's order
+        groups = []
+        n_res = 0
+        def group(kind, prog, n, *offs):
+            nonlocal n_res
+            groups.append([kind, int(prog), int(n), n_res] + [int(o) for o in offs] + [0] * (6 - len(offs)))
+            n_res += int(n)
         for g in s["flow_funcs"]:
-            cmd(C_FLOW_FUNC, int(g["prog"]), len(g["didx"]), A.add_i(g["didx"]), A.add_i(g["i0"]), A.add_i(g["i1"]))
+            group(0, g["prog"], len(g["didx"]), A.add_i(g["didx"]), A.add_i(g["i0"]), A.add_i(g["i1"]))
         for g in s["film_funcs"]:
-            cmd(C_FILM_FUNC, int(g["prog"]), len(g["fwd"]), A.add_i(g["fwd"]), A.add_i(g["bwd"]),
-                A.add_i(g["i0"]), A.add_i(g["i1"]), A.add_d(g["areas"]))
+            group(1, g["prog"], len(g["fwd"]), A.add_i(g["fwd"]), A.add_i(g["bwd"]), A.add_i(g["i0"]), A.add_i(g["i1"]),
+                  A.add_d(g["areas"]))
         for g in s["heat_funcs"]:
             idxs = np.asarray(g["idxs"]).reshape(len(g["counts"]), -1)
-            cmd(C_HEAT_FUNC, int(g["prog"]), idxs.shape[0], idxs.shape[1], A.add_i(idxs), A.add_d(g["counts"]))
+            group(2, g["prog"], idxs.shape[0], idxs.shape[1], A.add_i(idxs), A.add_d(g["counts"]))
         for g in s["flux_funcs"]:
-            cmd(C_FLUX_FUNC, int(g["prog"]), len(g["idxs"]), A.add_i(g["idxs"]), A.add_d(g["areas"]))
+            group(3, g["prog"], len(g["idxs"]), A.add_i(g["idxs"]), A.add_d(g["areas"]))
         for g in s["bound_funcs"]:
-            cmd(C_BOUND_FUNC, int(g["prog"]), len(g["idxs"]), A.add_i(g["idxs"]))
+            group(4, g["prog"], len(g["idxs"]), A.add_i(g["idxs"]))
+        if groups:
+            cmd(C_FUNCS, len(groups), A.add_d(np.zeros(max(n_res, 1))), *[w for g in groups for w in g])
 
         # ---- per-part arena data ------------------------------------------------------------------
         lp_dev = []
@@ -392,6 +401,7 @@ class DeviceSolver:
         nd.n_mean_jobs, nd.n_mean_blocks = len(jobs), len(job_of_block)
         nd.job_of_block, nd.first_block, nd.nblk = self._p(t_job), self._p(t_first), self._p(t_nblk)
         nd.ent_start, nd.ent_idx, nd.ent_w = self._p(t_estart), self._p(t_eidx), self._p(t_ew)
+        nd.n_iarena, nd.n_darena = int(self.iarena.numel()), int(self.darena.numel())
         _cabi.check(self.lib.tc_set_network(self._handle, C.byref(nd)))
 
         for k, d in enumerate(lp_dev):
