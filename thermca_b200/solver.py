@@ -75,7 +75,7 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
         coll.net_clean_conds.append(np.asmatrix(clean))
         coll.net_posns.append(net.posn.copy())
         if res["io_temps"].shape[1] > 0:
-            coll.io_temps.append(res["io_temps"][k].copy())
+            coll.io_temps.append(res["io_temps"][k])     # row view; from_collector stacks them (resultdata.py:720)
         if net._lp_ios:
             coll.lp_M_diagss.append([io.lp_sys.M_diag.copy() for io in net._lp_ios])
             coll.lp_Lss.append([io.lp_sys.L.copy() for io in net._lp_ios])
