@@ -86,3 +86,31 @@ def test_mor_batch_reproduces_reference_rhs_per_scenario(golden):
     X = ens.state()
     assert np.max(np.abs(X[:, :, 0].ravel() - y)) <= 1e-10 * np.max(np.abs(y))
     assert np.array_equal(X[:, :, 0], X[:, :, B - 1])
+
+
+def test_ensemble_on_reference_operators_matches_reference_run(golden):
+    """Every scenario of an ensemble built from the reference's MORIO operators (golden plate_mor) with the
+    golden's constant films reproduces the surface temperatures of the reference's own Network.sim run."""
+    from thermca_b200.mor_batch import MorEnsemble
+    spec, ex = golden("plate_mor")
+    part = spec["mor"][0]
+    ref = ex["result"]
+    F, B = int(part["F"]), 64
+    films = np.asarray(part["films"], dtype=np.float64)
+    h0 = np.repeat(films[:, None], B, axis=1)
+    tau = np.full((F, B), 1e300)                               # sin(2 pi t / tau) = 0: constant films
+    link_T = np.asarray(spec["init_temp"])[np.asarray(part["link_elem_net_idxs"])]
+    heat = np.asarray(spec["heat_src"])[np.asarray(part["surf_net_idxs"])]
+    ens = MorEnsemble.from_part(part, link_T, heat, h0, tau)
+    t_end = float(ref["times"][-1])
+    ens.steps(int(round(t_end / 0.25)), 0.25)
+    Ts = ens.surface_temps()                                   # (S, B)
+    want = ref["net_temps"][-1][np.asarray(part["surf_net_idxs"])]
+    assert np.abs(Ts - Ts[:, :1]).max() == 0.0                 # identical scenarios -> identical columns
+    # the reference run is adaptive RK45 at rtol 1e-3; RK4 with h = 0.25 s is far more accurate
+    assert np.allclose(Ts[:, 0] - 20.0, want - 20.0, rtol=2e-3, atol=1e-3)
+    # and against a tight CPU integration of the same lowered network
+    from rhs_oracle import integrate
+    tight = integrate(spec, [0.0, t_end], 1e-10, 1e-12, "RK45")
+    want_t = tight["net_temps"][-1][np.asarray(part["surf_net_idxs"])]
+    assert np.allclose(Ts[:, 0], want_t, rtol=1e-8, atol=1e-8)

@@ -46,6 +46,28 @@ class MorEnsemble:
         self.time = 0.0
         torch.cuda.synchronize(self.dev)
 
+    @classmethod
+    def from_part(cls, part, link_temps, surf_heat, film_h0, film_tau, device=None):
+        """Ensemble over ONE MOR part of a lowered network (``spec["mor"][k]``, i.e. the reference's
+        ``MORIO`` operators): ``link_temps[f]`` = temperature of the node behind film f, ``surf_heat[s]`` = heat
+        flow into surface s (W), ``film_h0 / film_tau`` (F x B) = the per-scenario film laws.  The input term
+        follows thermca/solver.py:282-292: flux_s = heat_s / area_s + sum_f film_f (T_link,f - T_ref)."""
+        S, r = int(part["S"]), int(part["r"])
+        q_surf = np.asarray(surf_heat, dtype=np.float64) / np.asarray(part["surf_areas"], dtype=np.float64)
+        t_link = np.asarray(link_temps, dtype=np.float64) - float(part["ref_temp"])
+        ens = cls(part["A_body"], part["A_films"], part["B_T"], np.asarray(part["film_surf_idxs"], dtype=np.int32),
+                  film_h0, film_tau, t_link, q_surf, np.asarray(part["x0"], dtype=np.float64).reshape(S, r),
+                  device=device)
+        ens.C_surfs = np.asarray(part["C_surfs"], dtype=np.float64)
+        ens.ref_temp = float(part["ref_temp"])
+        return ens
+
+    def surface_temps(self):
+        """Mean surface temperatures (S x B) of every scenario: sum_s C_surfs[s]^T x_s + T_ref
+        (thermca/solver.py:216-220)."""
+        X = self.state()                                       # (S, r, B)
+        return np.einsum("srq,srb->qb", self.C_surfs, X) + self.ref_temp
+
     def steps(self, nsteps, h, use_dmma=2, stream=None):
         """use_dmma: 2 = pipelined DMMA kernel (default), 1 = simple DMMA kernel, 0 = FMA cross-check."""
         torch = self.torch
