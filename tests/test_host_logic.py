@@ -178,3 +178,26 @@ def test_mor_basis_install_keeps_disk_cache_key():
     finally:
         mor_basis.uninstall()
     assert mio.transform is orig
+
+
+def test_package_level_install_and_uninstall():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import refenv
+    if not refenv.available():
+        pytest.skip("reference tree not present")
+    refenv.activate()
+    import thermca.solver as rs
+    import thermca.fem.fe_system as fes
+    import thermca.fem.mor_io as mio
+    import thermca_b200
+    before = (rs.transient_solution, fes.spsolve, fes.FESystem.__dict__["fem_matrices_from_skfem"], mio.transform)
+    thermca_b200.install()
+    try:
+        assert rs.transient_solution is thermca_b200.solver.transient_solution
+        assert fes.spsolve is thermca_b200.stationary.spd_solve
+        assert fes.FESystem.fem_matrices_from_skfem is thermca_b200.assembly.fem_matrices_device
+        assert mio.transform is not before[3]
+    finally:
+        thermca_b200.uninstall()
+    assert (rs.transient_solution, fes.spsolve, fes.FESystem.__dict__["fem_matrices_from_skfem"], mio.transform) == before
