@@ -69,6 +69,11 @@ typedef struct {
     int32_t ts_nrows;
     const int32_t* ts_row; const int32_t* ts_start; const int32_t* ts_surf; const double* ts_qval;
     const int32_t* ts_fstart; const int32_t* ts_film; const double* ts_adata;
+    /* tdep only: operator frozen at the initial temperatures, A0 = M0^-1 (L0 + film diagonal) in SELL-32 with
+     * its mass M0 and diagonal.  It is the Jacobian approximation of the W-method (tc_ros2_*); NULL = the part
+     * is stepped explicitly inside the implicit scheme */
+    int32_t j_nslices;
+    const int64_t* j_slice_ptr; const int32_t* j_col; const double* j_val; const double* j_mass; const double* j_adiag;
 } tc_ffe_desc;
 
 /* ---- LP part (replaces LPIO at run time, thermca/lpm/lp_io.py:8-80); operator and load

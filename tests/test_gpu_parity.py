@@ -329,3 +329,28 @@ def test_probe_history_matches_full_history(torch_cuda, golden):
     assert res2["probe_temps"].shape[1] == 2 and len(res2["times"]) == res2["probe_temps"].shape[0]
     with pytest.raises(IndexError):
         simulate(spec, (0.0, 1.0), probe_dofs=[10 ** 6])
+
+
+@pytest.mark.parametrize("name", ["tdep_rod", "assembly"])
+def test_ros2_temperature_dependent_body(torch_cuda, golden, name):
+    """Temperature dependent FE bodies inside the implicit scheme: the W-method solves them with the operator
+    frozen at the initial temperatures (the right-hand side uses the exact k(T), c(T)); result against the
+    oracle's RK45 at tight tolerance."""
+    from thermca_b200.device import DeviceSolver
+    from rhs_oracle import integrate
+    spec, ex = golden(name)
+    t0, t1 = float(ex["sim"]["t0"]), float(ex["sim"]["t1"])
+    tight = integrate(spec, [t0, t1], 1e-9, 1e-11, "RK45")
+    dev = DeviceSolver(spec)
+    out = dev.run_ros2(t0, t1, rtol=1e-5, atol=1e-8, pcg_rtol=1e-10)
+    dev.close()
+    assert out["status"] == 0 and out["times"][-1] == t1
+    # LP and FE blocks (physical temperatures); reduced MOR coordinates are judged through the network temperatures
+    from thermca_b200.spec import state_offsets
+    _, _, mor_off, n_state = state_offsets(spec)
+    end = (mor_off[0] if len(mor_off) else n_state) - int(spec["u"])
+    got, want = out["io_temps"][-1][:end], tight["io_temps"][-1][:end]
+    assert np.abs(got - want).max() < 2e-5 * np.abs(want).max()
+    assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=2e-4, atol=1e-6)
+    print(name, "ROS2 accepted", out["accepted"], "rejected", out["rejected"], "pcg", out["pcg"], "RK45 tight steps",
+          tight["nsteps"])

@@ -32,7 +32,8 @@ class FfeDesc(C.Structure):
                 ("fd_film", vp), ("fd_adata", vp), ("films_doff", i32), ("flux_doff", i32),
                 ("tdep", i32), ("condy_tab", i32), ("volcapy_tab", i32), ("ts_nrows", i32),
                 ("ts_row", vp), ("ts_start", vp), ("ts_surf", vp), ("ts_qval", vp),
-                ("ts_fstart", vp), ("ts_film", vp), ("ts_adata", vp)]
+                ("ts_fstart", vp), ("ts_film", vp), ("ts_adata", vp),
+                ("j_nslices", i32), ("j_slice_ptr", vp), ("j_col", vp), ("j_val", vp), ("j_mass", vp), ("j_adiag", vp)]
 
 
 class LpDesc(C.Structure):

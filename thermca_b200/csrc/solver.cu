@@ -259,6 +259,7 @@ __global__ void tc_advance_time_kernel(double* ctrl, int* fl) {
 struct FfePart {
     tc_ffe_desc d;
     TcSell A;
+    TcSell J;                          // tdep: frozen operator used as the W-method Jacobian (n == 0: none)
     TcSurfLoad load;
     TcFilmDiag fdiag;
     double *r, *p, *q, *dinv;          // PCG workspace
@@ -376,6 +377,8 @@ extern "C" int tc_add_ffe_part(tc_handle s, const tc_ffe_desc* d) {
     FfePart p{};
     p.d = *d;
     p.A = TcSell{d->n, d->nslices, (const long long*)d->slice_ptr, d->col, d->val, (const short*)d->col16};
+    if (d->tdep && d->j_val)
+        p.J = TcSell{d->n, d->j_nslices, (const long long*)d->j_slice_ptr, d->j_col, d->j_val, nullptr};
     p.load = TcSurfLoad{d->load_nrows, d->load_row, d->load_start, d->load_surf, d->load_bval};
     p.fdiag = TcFilmDiag{d->fd_nrows, (const long long*)d->fd_pos, d->fd_row, d->fd_abody, d->fd_start,
                          d->fd_film, d->fd_adata};
@@ -793,7 +796,9 @@ static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int
 }
 
 // z = (I + coef*h*A_p)^-1 rhs_p on FE parts, z = rhs elsewhere
-static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, double* z) {
+// w_method: the caller tolerates an inexact Jacobian (ROS2), so temperature dependent bodies are solved with
+// their operator frozen at the initial temperatures; otherwise they are left explicit
+static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, double* z, bool w_method = false) {
     cudaStream_t st = s->stream;
     const int* done = s->flags + FL_DONE;
     tc_copy_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, rhs, z, done);
@@ -809,9 +814,10 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         if (launch_pcg(s, P, s->pcg_mode, s->coop_grid, done)) return -1;
     }
     for (auto& p : s->ffe) {
-        if (p.d.tdep) continue;      // operator depends on T: treated explicitly (copy above)
+        const bool frozen = p.d.tdep != 0;
+        if (frozen && !(w_method && p.J.n > 0)) continue;      // operator depends on T: explicit (copy above)
         TcPcg& P = p.pcg;
-        P.A = p.A; P.mass = p.d.mass; P.adiag = p.d.adiag;
+        P.A = frozen ? p.J : p.A; P.mass = frozen ? p.d.j_mass : p.d.mass; P.adiag = frozen ? p.d.j_adiag : p.d.adiag;
         P.rhs = rhs + p.d.y_off; P.x = z + p.d.y_off;
         P.r = p.r; P.p = p.p; P.q = p.q; P.dinv = p.dinv;
         P.partial = s->red_partial; P.sc = s->pcg_sc; P.isc = s->pcg_isc;
@@ -872,13 +878,13 @@ static int enqueue_ros2_attempt(tc_solver* s) {
     const int G = s->vec_grid;
     tc_prepare_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
     if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
-    if (enqueue_block_solve(s, s->ros_gamma, s->K[0], s->K[1])) return -1;          // k1
+    if (enqueue_block_solve(s, s->ros_gamma, s->K[0], s->K[1], true)) return -1;    // k1
     TcLin L1{};
     L1.nk = 1; L1.k[0] = s->K[1]; L1.c[0] = 1.0;
     tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L1, s->ctrl, s->ystage, done);       // y + h k1
     if (enqueue_rhs(s, 1.0, s->ystage, s->K[2])) return -1;
     tc_axpby_kernel<<<G, 256, 0, st>>>(n, s->K[2], -2.0, s->K[1], s->K[3], done);  // f2 - 2 k1
-    if (enqueue_block_solve(s, s->ros_gamma, s->K[3], s->K[4])) return -1;          // k2
+    if (enqueue_block_solve(s, s->ros_gamma, s->K[3], s->K[4], true)) return -1;    // k2
     TcLin L2{};
     L2.nk = 2; L2.k[0] = s->K[1]; L2.c[0] = 1.5; L2.k[1] = s->K[4]; L2.c[1] = 0.5;
     tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L2, s->ctrl, s->ynew, done);

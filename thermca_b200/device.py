@@ -470,6 +470,16 @@ class DeviceSolver:
         fd.ts_fstart = self._p(self._up(f_start))
         fd.ts_film = self._p(self._up(f_film[of].astype(np.int32) if len(of) else np.zeros(1, np.int32)))
         fd.ts_adata = self._p(self._up(f_adata[of] if len(of) else np.zeros(1)))
+        # Jacobian approximation of the implicit W-method: the operator as the reference built it at the initial
+        # temperatures (FFEIO.A incl. the initial film diagonal, fem/ffe_io.py:24-65), frozen
+        ab = p["A_body"]
+        jsell = csr_to_sell(ab["indptr"], ab["indices"], p["A_data"])
+        dpos = csr_diag_positions(ab["indptr"], ab["indices"])
+        fd.j_nslices = jsell["nslices"]
+        fd.j_slice_ptr, fd.j_col = self._p(self._up(jsell["slice_ptr"])), self._p(self._up(jsell["col"]))
+        fd.j_val = self._p(self._up(jsell["val"]))
+        fd.j_mass = self._p(self._up(1.0 / np.asarray(p["M_inv"], dtype=np.float64)))
+        fd.j_adiag = self._p(self._up(np.asarray(p["A_data"], dtype=np.float64)[dpos]))
         _cabi.check(self.lib.tc_add_ffe_part(self._handle, C.byref(fd)))
 
     def _add_ffe(self, k, p, d):
