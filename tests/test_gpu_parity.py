@@ -354,3 +354,25 @@ def test_ros2_temperature_dependent_body(torch_cuda, golden, name):
     assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=2e-4, atol=1e-6)
     print(name, "ROS2 accepted", out["accepted"], "rejected", out["rejected"], "pcg", out["pcg"], "RK45 tight steps",
           tight["nsteps"])
+
+
+def test_ros2_stiff_network_node_is_implicit(torch_cuda, golden):
+    """A lumped node with a tiny capacity (time constant ~2 ms against a 20 s simulation) must not restrict the
+    implicit scheme: the unknown network nodes are part of the W-method's block solve."""
+    import copy
+    from thermca_b200.device import DeviceSolver
+    from rhs_oracle import integrate
+    spec, ex = golden("plate_ffe_var")
+    spec = copy.deepcopy(spec)
+    assert int(spec["u"]) == 1
+    spec["capy"] = np.array(spec["capy"], dtype=np.float64)
+    spec["capy"][0] = 0.01                                    # was 2e3 J/K; conductances of ~5 W/K stay
+    t1 = 20.0
+    tight = integrate(spec, [0.0, t1], 1e-8, 1e-10, "RK45")
+    dev = DeviceSolver(spec)
+    out = dev.run_ros2(0.0, t1, rtol=1e-4, atol=1e-7, pcg_rtol=1e-10)
+    dev.close()
+    assert out["status"] == 0 and out["times"][-1] == t1
+    assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=5e-4, atol=1e-4)
+    assert out["accepted"] + out["rejected"] < tight["nsteps"] / 10, (out["accepted"], tight["nsteps"])
+    print("stiff node: ROS2 steps", out["accepted"], "+", out["rejected"], "explicit RK45 steps", tight["nsteps"])

@@ -291,6 +291,7 @@ struct tc_solver {
     // history
     double* hist_io = nullptr; double* hist_net = nullptr; int capacity = 0; int num_skip = 0;
     const long long* probe_idx = nullptr; int n_probe = 0;     // probe mode of the history (tc_set_probes)
+    double* net_vec = nullptr;                                 // 4*u doubles: CG vectors of the network block solve
     // RK
     int method = TC_RK45; int n_stages = 6;
     cudaGraphExec_t rk_graph = nullptr;
@@ -344,6 +345,7 @@ extern "C" int tc_destroy(tc_handle s) {
     cudaFree(s->pcg_isc); cudaFree(s->mean_partials);
     cudaFree(s->y); cudaFree(s->ynew); cudaFree(s->ystage);
     for (int i = 0; i < 7; ++i) cudaFree(s->K[i]);
+    cudaFree(s->net_vec);
     for (auto& p : s->ffe) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
     for (auto& p : s->lp) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
     cudaFreeHost(s->pin_flags); cudaFreeHost(s->pin_ctrl);
@@ -423,6 +425,7 @@ extern "C" int tc_finalize(tc_handle s, int64_t n_state) {
         TC_CUDA(cudaMalloc(&p.r, b)); TC_CUDA(cudaMalloc(&p.p, b));
         TC_CUDA(cudaMalloc(&p.q, b)); TC_CUDA(cudaMalloc(&p.dinv, b));
     }
+    if (s->net.u > 0) TC_CUDA(cudaMalloc(&s->net_vec, sizeof(double) * 4 * (size_t)s->net.u));
     s->coop_grid = pcg_coop_grid(s->sm_count);
     s->finalized = true;
     return 0;
@@ -796,12 +799,85 @@ static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int
 }
 
 // z = (I + coef*h*A_p)^-1 rhs_p on FE parts, z = rhs elsewhere
+// Unknown network nodes inside the W-method: z_u = (I + s C_uu^-1 L_uu)^-1 rhs_u, i.e. (C + s L_uu) z = C rhs with
+// the conductance matrix in the differential-equation form of the latest right-hand side (calc, rows < u:
+// diagonal = sum of the row's conductances, off-diagonal = -G; thermca/solver.py:45-58,252-255).  C + s L_uu is
+// symmetric positive definite; u <= ~10^3, so one CTA runs Jacobi-CG over the CSR rows (columns >= u are the
+// coupling to bound nodes and part surfaces, which stays explicit).  vec: 4*u doubles of scratch.
+__global__ void __launch_bounds__(256)
+tc_net_block_solve_kernel(TcNetParams P, const double* __restrict__ ctrl, double coef,
+                          const double* __restrict__ rhs, double* __restrict__ z, double* __restrict__ vec,
+                          double rtol, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sh[32];
+    __shared__ double bc[2];
+    const int u = P.u, tid = threadIdx.x, nt = blockDim.x;
+    const int* indptr = P.iarena + P.o_indptr;
+    const int* indices = P.iarena + P.o_indices;
+    const double* calc = P.darena + P.o_calc;
+    const double* capy = P.darena + P.o_capy;
+    const int* dg = P.iarena + P.o_diag;
+    const double sft = coef * ctrl[1];
+    double *r = vec, *p = vec + u, *q = vec + 2 * u, *dinv = vec + 3 * u;
+    double rho_l = 0.0, bb_l = 0.0;
+    for (int i = tid; i < u; i += nt) {
+        const double b = capy[i] * rhs[i];
+        const double d = 1.0 / (capy[i] + sft * calc[dg[i]]);
+        r[i] = b; z[i] = 0.0; dinv[i] = d; p[i] = d * b;
+        rho_l += b * d * b; bb_l += b * b;
+    }
+    auto bsum = [&](double v, int slot) {
+        const double t = block_sum(v, sh);
+        if (tid == 0) bc[slot] = t;
+        __syncthreads();
+        const double out = bc[slot];
+        __syncthreads();
+        return out;
+    };
+    double rho = bsum(rho_l, 0);
+    const double bb = bsum(bb_l, 1);
+    if (!(bb > 0.0)) return;
+    const double tol2 = rtol * rtol * bb;
+    const int maxit = 2 * u + 20;
+    for (int it = 0; it < maxit; ++it) {
+        double pq_l = 0.0;
+        for (int i = tid; i < u; i += nt) {
+            double acc = 0.0;
+            for (int j = indptr[i]; j < indptr[i + 1]; ++j) {
+                const int c = indices[j];
+                if (c < u) acc += calc[j] * p[c];
+            }
+            const double qi = capy[i] * p[i] + sft * acc;
+            q[i] = qi;
+            pq_l += p[i] * qi;
+        }
+        const double pq = bsum(pq_l, 0);
+        const double alpha = rho / pq;
+        double rn_l = 0.0, rr_l = 0.0;
+        for (int i = tid; i < u; i += nt) {
+            z[i] += alpha * p[i];
+            const double ri = r[i] - alpha * q[i];
+            r[i] = ri;
+            rn_l += ri * dinv[i] * ri; rr_l += ri * ri;
+        }
+        const double rho_new = bsum(rn_l, 0);
+        const double rr = bsum(rr_l, 1);
+        if (!(rr > tol2)) break;
+        const double beta = rho_new / rho;
+        rho = rho_new;
+        for (int i = tid; i < u; i += nt) p[i] = dinv[i] * r[i] + beta * p[i];
+        __syncthreads();
+    }
+}
+
 // w_method: the caller tolerates an inexact Jacobian (ROS2), so temperature dependent bodies are solved with
 // their operator frozen at the initial temperatures; otherwise they are left explicit
 static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, double* z, bool w_method = false) {
     cudaStream_t st = s->stream;
     const int* done = s->flags + FL_DONE;
     tc_copy_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, rhs, z, done);
+    if (w_method && s->net.u > 0 && s->net_vec)
+        tc_net_block_solve_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, coef, rhs, z, s->net_vec, 1e-12, done);
     // LP parts: same SPD structure (M A = L_body + film/margin diagonal, thermca/lpm/lp_io.py:106-128)
     for (auto& p : s->lp) {
         TcPcg& P = p.pcg;

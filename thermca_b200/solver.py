@@ -8,8 +8,8 @@ the same side effects on the ``Network`` the reference's post-processing relies 
 Methods
 * ``'RK45'`` / ``'RK23'`` — scipy's adaptive explicit Runge-Kutta pairs restated on the
   device (step controller included); these are what the reference runs by default.
-* ``'ROS2_PCG'`` — adaptive linearly implicit 2-stage Rosenbrock method, FE parts solved by
-  Jacobi-PCG (new method; the reference has no implicit scheme).  ``'LSODA'`` requests
+* ``'ROS2_PCG'`` — adaptive linearly implicit 2-stage Rosenbrock-W method; FE and LP parts solved by
+  Jacobi-PCG, unknown network nodes by a small CG (new method; the reference has no implicit scheme).  ``'LSODA'`` requests
   are served by it as well (LSODA's dense Jacobian is unusable beyond ~30k DOF); results
   agree within the requested tolerances at output times.
 """
