@@ -376,3 +376,21 @@ def test_ros2_stiff_network_node_is_implicit(torch_cuda, golden):
     assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=5e-4, atol=1e-4)
     assert out["accepted"] + out["rejected"] < tight["nsteps"] / 10, (out["accepted"], tight["nsteps"])
     print("stiff node: ROS2 steps", out["accepted"], "+", out["rejected"], "explicit RK45 steps", tight["nsteps"])
+
+
+@pytest.mark.parametrize("name", ["plate_mor", "plate_mor_var"])
+def test_ros2_with_implicit_mor_blocks(torch_cuda, golden, name):
+    """MOR bodies inside the implicit scheme (dense r x r CG per surface, films of the latest right-hand side)."""
+    from thermca_b200.device import DeviceSolver
+    from rhs_oracle import integrate
+    spec, ex = golden(name)
+    t1 = float(ex["sim"]["t1"])
+    tight = integrate(spec, [0.0, t1], 1e-9, 1e-11, "RK45")
+    dev = DeviceSolver(spec)
+    out = dev.run_ros2(0.0, t1, rtol=1e-5, atol=1e-8, pcg_rtol=1e-10)
+    dev.close()
+    assert out["status"] == 0 and out["times"][-1] == t1
+    assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=2e-4, atol=1e-6)
+    scale = np.abs(tight["io_temps"][-1]).max()
+    assert np.abs(out["io_temps"][-1] - tight["io_temps"][-1]).max() < 1e-3 * scale
+    print(name, "ROS2 accepted", out["accepted"], "rejected", out["rejected"])

@@ -870,6 +870,102 @@ tc_net_block_solve_kernel(TcNetParams P, const double* __restrict__ ctrl, double
     }
 }
 
+// MOR blocks inside the W-method: (I + s A_q) z_q = rhs_q for every surface q of a reduced body, with
+// A_q = A_body[q] + sum_f film_f A_films[f][q] (r x r, symmetric positive definite; thermca/fem/mor_io.py:90-92) applied on
+// the fly.  One CTA per surface runs Jacobi-CG with its vectors in shared memory (5 r doubles).
+__global__ void __launch_bounds__(256)
+tc_mor_block_solve_kernel(TcMor M, const double* __restrict__ films, const double* __restrict__ ctrl, double coef,
+                          const double* __restrict__ rhs, double* __restrict__ z, double rtol,
+                          const int* __restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ double smv[];
+    __shared__ double sh[32];
+    __shared__ double bc[2];
+    const int r = M.r, q_s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const size_t blk = (size_t)M.S * r * r;
+    const double* ab = M.A_body + (size_t)q_s * r * r;
+    const double* af = M.A_films + (size_t)q_s * r * r;
+    const double* b = rhs + (size_t)q_s * r;
+    double* x = z + (size_t)q_s * r;
+    double *rv = smv, *p = smv + r, *q = smv + 2 * r, *dinv = smv + 3 * r, *xs = smv + 4 * r;
+    const double sft = coef * ctrl[1];
+    auto a_at = [&](int i, int j) {
+        double v = ab[(size_t)i * r + j];
+        for (int f = 0; f < M.F; ++f) v += films[f] * af[f * blk + (size_t)i * r + j];
+        return v;
+    };
+    auto bsum = [&](double v, int slot) {
+        const double t = block_sum(v, sh);
+        if (tid == 0) bc[slot] = t;
+        __syncthreads();
+        const double out = bc[slot];
+        __syncthreads();
+        return out;
+    };
+    // A W-method may use any Jacobian approximation, also none: when the step is well inside the explicit
+    // stability region of this block (Gershgorin bound of s*A below 1/2) the copy made by the caller (z = rhs)
+    // stands and the block is explicit for this attempt - measured: fewer steps than damping non-stiff modes.
+    {
+        double g_l = 0.0;
+        for (int i = warp; i < r; i += nw) {
+            double acc = 0.0;
+            for (int j = lane; j < r; j += 32) acc += fabs(a_at(i, j));
+            acc = warp_sum(acc);
+            if (lane == 0) g_l = fmax(g_l, acc);
+        }
+        g_l = warp_max(g_l);            // lane 0 of every warp holds its maximum; reduce over warps
+        __syncthreads();
+        if (lane == 0) sh[warp] = g_l;
+        __syncthreads();
+        double g = 0.0;
+        for (int w = 0; w < nw; ++w) g = fmax(g, sh[w]);
+        __syncthreads();
+        if (sft * g < 0.5) return;      // uniform over the CTA
+    }
+    double rho_l = 0.0, bb_l = 0.0;
+    for (int i = tid; i < r; i += nt) {
+        const double bi = b[i];
+        const double d = 1.0 / (1.0 + sft * a_at(i, i));
+        rv[i] = bi; xs[i] = 0.0; dinv[i] = d; p[i] = d * bi;
+        rho_l += bi * d * bi; bb_l += bi * bi;
+    }
+    double rho = bsum(rho_l, 0);
+    const double bb = bsum(bb_l, 1);
+    if (bb > 0.0) {
+        const double tol2 = rtol * rtol * bb;
+        const int maxit = 2 * r + 20;
+        for (int it = 0; it < maxit; ++it) {
+            for (int i = warp; i < r; i += nw) {            // q = p + s A p, one warp per row
+                double acc = 0.0;
+                for (int j = lane; j < r; j += 32) acc += a_at(i, j) * p[j];
+                acc = warp_sum(acc);
+                if (lane == 0) q[i] = p[i] + sft * acc;
+            }
+            __syncthreads();
+            double pq_l = 0.0;
+            for (int i = tid; i < r; i += nt) pq_l += p[i] * q[i];
+            const double alpha = rho / bsum(pq_l, 0);
+            double rn_l = 0.0, rr_l = 0.0;
+            for (int i = tid; i < r; i += nt) {
+                xs[i] += alpha * p[i];
+                const double ri = rv[i] - alpha * q[i];
+                rv[i] = ri;
+                rn_l += ri * dinv[i] * ri; rr_l += ri * ri;
+            }
+            const double rho_new = bsum(rn_l, 0);
+            const double rr = bsum(rr_l, 1);
+            if (!(rr > tol2)) break;
+            const double beta = rho_new / rho;
+            rho = rho_new;
+            for (int i = tid; i < r; i += nt) p[i] = dinv[i] * rv[i] + beta * p[i];
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < r; i += nt) x[i] = xs[i];
+}
+
 // w_method: the caller tolerates an inexact Jacobian (ROS2), so temperature dependent bodies are solved with
 // their operator frozen at the initial temperatures; otherwise they are left explicit
 static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, double* z, bool w_method = false) {
@@ -878,6 +974,12 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
     tc_copy_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, rhs, z, done);
     if (w_method && s->net.u > 0 && s->net_vec)
         tc_net_block_solve_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, coef, rhs, z, s->net_vec, 1e-12, done);
+    if (w_method)
+        for (auto& p : s->mor) {
+            if (p.M.r > 1024) continue;                      // vectors would not fit the default shared memory: explicit
+            tc_mor_block_solve_kernel<<<p.M.S, 256, sizeof(double) * 5 * p.M.r, st>>>(
+                p.M, s->net.darena + p.d.films_doff, s->ctrl, coef, rhs + p.d.y_off, z + p.d.y_off, 1e-12, done);
+        }
     // LP parts: same SPD structure (M A = L_body + film/margin diagonal, thermca/lpm/lp_io.py:106-128)
     for (auto& p : s->lp) {
         TcPcg& P = p.pcg;
