@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 import refenv  # noqa: E402
 
 refenv.activate()
-from thermca import free_conv, forced_conv, radiation, combd_film, evaporation, fluids, TRANSVERSE  # noqa: E402
+from thermca import free_conv, forced_conv, radiation, combd_film, evaporation, bearing, fluids, TRANSVERSE  # noqa: E402
 
 from thermca_b200.trace import trace, TableRegistry, UntraceableError  # noqa: E402
 
@@ -58,6 +58,10 @@ CASES = [
     ("combd_film.conv_radn_room_at_room_temps", combd_film.conv_radn_room_at_room_temps(), air, None),
     ("combd_film.conv_radn_room", combd_film.conv_radn_room(), air, None),
     ("evaporation.free_forc_water_to_air", evaporation.free_forc_water_to_air(), air, None),
+    # Python control flow on data (traced path by path and joined with WHERE):
+    ("free_conv.vert_cyl_gap", free_conv.vert_cyl_gap(), None, None),              # per-element if/elif loop :317-323
+    ("bearing.heat_loss", bearing.heat_loss(), "heat", None),                      # `if v < 2e-4` bearing.py:131
+    ("bearing.heat_loss[slow, oil bath]", bearing.heat_loss(rot_freq=0.02, lube_type="oil bath"), "heat", None),
 ]
 
 
@@ -70,14 +74,17 @@ def main():
     k = 0
     names = []
     for name, func, matl, kat in CASES:
+        heat = isinstance(matl, str) and matl == "heat"          # heat functions take the mean temperature only
         try:
-            prog = trace(func, 2, [], tables, extra_args=(matl,))
+            prog = trace(func, 1, [], tables) if heat else trace(func, 2, [], tables, extra_args=(matl,))
         except UntraceableError as e:
             print("untraceable:", name, e)
             continue
         with np.errstate(all="ignore"):
-            # array call, as the solver issues it (thermca/network.py:781-785: one vector per link group)
-            expect = np.asarray(func(t0.copy(), t1.copy(), matl), dtype=np.float64) * np.ones_like(t0)
+            if heat:      # network.py:788-790 calls f(mean(T[idx])) with a scalar
+                expect = np.array([float(func(a)) for a in t0])
+            else:         # array call, as the solver issues it (network.py:781-785: one vector per link group)
+                expect = np.asarray(func(t0.copy(), t1.copy(), matl), dtype=np.float64) * np.ones_like(t0)
         if kat is not None:
             assert float(func(36, 22, matl)) == kat, (name, kat)       # the notebook's printed digits (scalar call)
             assert abs(expect[0] - kat) <= 4e-16 * kat                 # numpy's array pow may differ in the last bit

@@ -110,7 +110,12 @@ def test_unknown_method_and_untraceable_callable(dropin):
     with Model() as model:
         a = Node(capy=1.0, init_temp=0.0)
         b = BoundNode(temp=1.0)
-        CondLink(a, b, cond=lambda t0, t1, matl: 2.0 if t0 > t1 else 1.0)      # branches on data
+        def halving(t0, t1, matl):                   # trip count depends on data: no finite set of paths
+            x = abs(t0 - t1) + 2.0
+            while x > 1.0:
+                x = x / 2.0
+            return x
+        CondLink(a, b, cond=halving)
     with pytest.raises(UntraceableError):
         Network(model).sim([0, 1.0], progress_bar=False)
     with Model() as model2:

@@ -69,11 +69,46 @@ def test_tracer_where_interp_and_inputs():
     assert np.array_equal(got, f(a, b))
 
 
-def test_tracer_rejects_python_branching():
+def test_tracer_follows_python_branches_and_rejects_data_dependent_loops():
+    """`if` on data (thermca/lib/bearing.py:131, free_conv.py:317-323) is traced path by path and joined with
+    WHERE; a loop whose trip count depends on data has no finite set of paths and is rejected."""
+    tabs = TableRegistry()
+
     def f(a, b):
-        return a if a > b else b
+        if a > b:
+            out = a * 2.0
+        elif a > 0.0 and b < -1.0:
+            out = b - a
+        else:
+            out = np.sqrt(abs(a))
+        return out + 1.0
+    p = trace(f, 2, [], tabs)
+    code, consts, res = p.arrays()
+    a, b = np.array([3.0, -1.0, 0.5, 2.0, -4.0]), np.array([1.0, 2.0, -3.0, 2.0, -2.0])
+    got = run_program(code, consts, res, [a, b], [], tabs.tables)
+    want = np.array([f(x, y) for x, y in zip(a, b)])
+    assert np.array_equal(got, want)
+
+    def buf(a, b):                       # numpy.empty_like + per-element assignment (free_conv.vert_cyl_gap)
+        n = a - b
+        c = np.empty_like(n)
+        for i in range(len(n)):
+            if n[i] < 0.2:
+                c[i] = 0.48
+            else:
+                c[i] = 0.93
+        return c * n
+    p = trace(buf, 2, [], tabs)
+    code, consts, res = p.arrays()
+    assert np.array_equal(run_program(code, consts, res, [a, b], [], tabs.tables), buf(a.copy(), b.copy()))
+
+    def loop(a, b):
+        x = a - b
+        while x > 1.0:
+            x = x / 2.0
+        return x
     with pytest.raises(UntraceableError):
-        trace(f, 2, [], TableRegistry())
+        trace(loop, 2, [], tabs)
 
 
 def test_spec_roundtrip(tmp_path, golden):

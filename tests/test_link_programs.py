@@ -25,7 +25,7 @@ def _load():
 def test_host_interpreter_reproduces_reference_closures_bit_exactly():
     from thermca_b200.trace import run_program
     progs, tables, t0, t1 = _load()
-    assert len(progs) == 25
+    assert len(progs) == 28
     for name, code, consts, result, expect in progs:
         got = run_program([tuple(r) for r in code], list(consts), result, [t0, t1], [], tables)
         assert np.array_equal(got, expect, equal_nan=True), name

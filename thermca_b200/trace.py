@@ -76,6 +76,7 @@ class Program:
         self._inputs = inputs     # list of 0-d ndarrays (identity match) -> slot index
         self._tables = tables     # shared TableRegistry
         self.result = None
+        self._decide = None       # set by trace(): resolves `if <Sym>` while exploring execution paths
 
     def emit(self, op, a=0, b=0, c=0):
         self.code.append((OP[op], int(a), int(b), int(c)))
@@ -93,6 +94,8 @@ class Program:
 
     def leaf(self, x):
         """Value index for a non-symbolic operand."""
+        if type(x).__name__ == "SymBuffer":
+            x = x._sym()
         if isinstance(x, Sym):
             if x.prog is not self:
                 raise UntraceableError("symbol from another trace")
@@ -178,18 +181,24 @@ class Sym:
     __hash__ = None
 
     def __bool__(self):
-        raise UntraceableError(
-            "the callable branches on a temperature-dependent value in Python "
-            "(`if`/`and`/`or` on data); use numpy.where so it can run on the device")
+        # Python control flow on data (`if v < 2e-4:` in thermca/lib/bearing.py:131): the tracer runs the callable
+        # once per execution path and joins the paths with WHERE (see trace()).
+        if self.prog._decide is None:
+            raise UntraceableError(
+                "the callable branches on a temperature-dependent value in Python "
+                "(`if`/`and`/`or` on data); use numpy.where so it can run on the device")
+        return self.prog._decide(self)
 
     def __len__(self):
         return 1
 
     def __iter__(self):
-        raise UntraceableError("the callable iterates over its array argument in Python")
+        return iter((self,))
 
     def __getitem__(self, key):
-        raise UntraceableError("the callable indexes its array argument in Python")
+        if key in (0, -1, (0,), Ellipsis) or key == slice(None):
+            return self             # one symbolic element per link
+        raise UntraceableError("the callable indexes its array argument beyond the single link element")
 
     def __float__(self):
         raise UntraceableError("the callable converts a temperature-dependent value to float")
@@ -219,10 +228,69 @@ class Sym:
             return Sym(p, p.emit("INTERP", tid, p.leaf(args[0])))
         if func in (np.mean, np.sum, np.ravel, np.asarray, np.asanyarray, np.atleast_1d) and len(args) == 1:
             return args[0]      # one symbolic element per link
+        if func in (np.empty_like, np.zeros_like, np.ones_like) and len(args) == 1:
+            return SymBuffer(p, None if func is np.empty_like else (0.0 if func is np.zeros_like else 1.0))
         if func is np.clip and len(args) == 3:
             lo = p.emit("MAX", p.leaf(args[0]), p.leaf(args[1]))
             return Sym(p, p.emit("MIN", lo, p.leaf(args[2])))
         raise UntraceableError(f"numpy.{func.__name__} is not lowered to the device")
+
+
+class SymBuffer:
+    """Result of ``numpy.empty_like(sym)`` / ``zeros_like`` inside a trace: a one-element array the callable fills by
+    item assignment (thermca/lib/free_conv.py:312-323) and then uses in arithmetic."""
+
+    __array_priority__ = 1001.0
+    shape = (1,)
+    ndim = 1
+    size = 1
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, prog, value=None):
+        self.prog = prog
+        self.value = value
+
+    def __len__(self):
+        return 1
+
+    def __setitem__(self, key, value):
+        if key not in (0, -1, (0,), Ellipsis) and key != slice(None):
+            raise UntraceableError("item assignment beyond the single link element")
+        self.value = value
+
+    def _sym(self):
+        if self.value is None:
+            raise UntraceableError("array element used before it was assigned")
+        v = self.value
+        return v if isinstance(v, Sym) else Sym(self.prog, self.prog.leaf(v))
+
+    def __getitem__(self, key):
+        return self._sym()[key]
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        inputs = tuple(i._sym() if isinstance(i, SymBuffer) else i for i in inputs)
+        return self._sym().__array_ufunc__(ufunc, method, *inputs, **kwargs)
+
+    def __array_function__(self, func, types, args, kwargs):
+        args = tuple(a._sym() if isinstance(a, SymBuffer) else a for a in args)
+        return self._sym().__array_function__(func, types, args, kwargs)
+
+
+def _buffer_op(name, swap=False):
+    def op(self, other):
+        other = other._sym() if isinstance(other, SymBuffer) else other
+        return self._sym()._bin(name, other, swap)
+    return op
+
+
+for _n, _op in (("add", "ADD"), ("sub", "SUB"), ("mul", "MUL"), ("truediv", "DIV"), ("pow", "POW"), ("lt", "LT"),
+                ("le", "LE"), ("gt", "GT"), ("ge", "GE")):
+    setattr(SymBuffer, f"__{_n}__", _buffer_op(_op))
+    if _n in ("add", "sub", "mul", "truediv", "pow"):
+        setattr(SymBuffer, f"__r{_n}__", _buffer_op(_op, True))
+
+
+MAX_PATHS = 32
 
 
 def _substitute(obj, mapping, depth=0):
@@ -277,13 +345,39 @@ def trace(func, n_args, inputs, tables, extra_args=(), input_objs=None, validate
             saved.append((obj, obj._value))
             obj._value = s
         fsub = _substitute(func, mapping) if mapping else func
-        out = fsub(*syms, *extra_args)
+        # Python `if` on symbolic data: run the callable once per execution path (decisions beyond the forced
+        # prefix default to True) and join the alternatives with WHERE, innermost decision first.  Both sides of
+        # a WHERE are evaluated on the device, exactly like numpy.where evaluates both of its arguments.
+        n_paths = [0]
+
+        def explore(forced):
+            n_paths[0] += 1
+            if n_paths[0] > MAX_PATHS:
+                raise UntraceableError(f"more than {MAX_PATHS} execution paths (data-dependent loop?)")
+            taken, opened = [], []
+
+            def decide(sym):
+                k = len(taken)
+                if k < len(forced):
+                    taken.append(forced[k])
+                else:
+                    opened.append(sym.ix)
+                    taken.append(True)
+                return taken[-1]
+            prog._decide = decide
+            res = prog.leaf(fsub(*syms, *extra_args))
+            for j in reversed(range(len(opened))):
+                alt = explore(taken[:len(forced) + j] + [False])
+                res = prog.emit("WHERE", opened[j], res, alt)
+            return res
+        result = explore([])
     except (UntraceableError, TypeError) as e:
         raise UntraceableError(f"cannot lower callable {name!r} to the device: {e}") from e
     finally:
+        prog._decide = None
         for obj, v in saved:
             obj._value = v
-    prog.result = prog.leaf(out)
+    prog.result = result
     if validate:
         _validate(func, prog, n_args, inputs, tables, extra_args, name)
     return prog
