@@ -396,10 +396,41 @@ def run_mor(args):
                      "peak_kind": "torch.matmul fp64 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
                      "simple_dmma_ms_per_step": res[1][0] / nsteps, "fma_variant_ms_per_step": res[0][0] / nsteps},
     }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = mor_cpu_baseline(A_body, A_films, B_T, h0, tau, h)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def mor_cpu_baseline(A_body, A_films, B_T, h0, tau, h, n_scen=48, n_steps=4):
+    """What the reference does for this workload, one scenario at a time (thermca/solver.py:282-299 with
+    mor_io.py:90-92): A = A_body + sum_f film_f A_films per right-hand side, then S small GEMVs; RK4, numpy, 1 core."""
+    S, r = A_body.shape[:2]
+    F = A_films.shape[0]
+    film_surf = np.array([0, 1])
+    t_link = np.array([-5.0, 3.0])
+    q_surf = np.array([100.0, 0.0, 0.0])
+
+    def rhs(t, x, b):
+        films = h0[:, b] * (1.0 + 0.5 * np.sin(2.0 * np.pi * t / tau[:, b]))
+        A = A_body + sum(f * Af for f, Af in zip(films, A_films))            # (S, r, r), rebuilt per call
+        flux = q_surf.copy()
+        np.add.at(flux, film_surf, films * t_link)
+        return np.array([-a @ xs for a, xs in zip(A, x)]) + B_T * flux[:, None]
+    t0 = time.perf_counter()
+    for b in range(n_scen):
+        x = np.zeros((S, r))
+        t = 0.0
+        for _ in range(n_steps):
+            k1 = rhs(t, x, b); k2 = rhs(t + 0.5 * h, x + 0.5 * h * k1, b)
+            k3 = rhs(t + 0.5 * h, x + 0.5 * h * k2, b); k4 = rhs(t + h, x + h * k3, b)
+            x = x + h / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+            t += h
+    dt = time.perf_counter() - t0
+    return {"value": n_scen * n_steps / dt, "unit": "scenarios*steps/s", "cores": 1, "kind": "port",
+            "sample": f"{n_scen} scenarios x {n_steps} RK4 steps, numpy, one scenario at a time as the reference runs them"}
 
 
 def main():
