@@ -11,7 +11,7 @@ Thermca installation to the device; ``uninstall()`` restores the reference's own
 __version__ = "0.1.0"
 
 __all__ = ["solver", "device", "lowering", "trace", "spec", "synth", "workloads", "dist", "mor_batch", "build",
-           "stationary", "assembly", "mor_basis", "install", "uninstall"]
+           "stationary", "assembly", "mor_basis", "linsolve", "install", "uninstall"]
 
 
 def install(transient=True, stationary=True, assembly=True, mor_basis=True):

@@ -21,58 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from .device import csr_to_sell
-
-_EPS = 2.0 ** -80
-
-
-def _p(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
-
-
-class _DeviceOperator:
-    """SELL-32 copy of a scipy CSR matrix with the two things the basis build needs: products and SPD solves."""
-
-    def __init__(self, A, dev):
-        import scipy.sparse as sp
-        import torch
-        self.torch, self.dev = torch, dev
-        self.lib = _cabi.load_library()
-        A = sp.csr_matrix(A)
-        A.sort_indices()
-        self.n = A.shape[0]
-        s = csr_to_sell(A.indptr, A.indices, A.data)
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        self.nslices = s["nslices"]
-        self.slice_ptr, self.col, self.val = up(s["slice_ptr"]), up(s["col"]), up(s["val"])
-        self.diag = up(A.diagonal())
-        self.mass = torch.full((self.n,), _EPS, dtype=torch.float64, device=dev)
-        self.iterations = 0
-        self.solves = 0
-
-    def _stream(self):
-        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
-
-    def matvec_into(self, x, y):
-        """y = A x"""
-        _cabi.check(self.lib.tc_sell_spmv(self._stream(), 0, self.n, self.nslices, _p(self.slice_ptr), _p(self.col),
-                                          _p(None), _p(self.val), _p(x), _p(y), _p(None), _p(None), 0.0, 0))
-        y.neg_()
-        return y
-
-    def solve(self, b, rtol):
-        """x = A^-1 b by Jacobi-PCG (A symmetric positive definite); b, x device vectors."""
-        torch = self.torch
-        x = torch.zeros(self.n, dtype=torch.float64, device=self.dev)
-        rhs = b / _EPS
-        iters = C.c_int32(0)
-        torch.cuda.synchronize(self.dev)
-        _cabi.check(self.lib.tc_pcg_solve(self._stream(), 0, self.n, self.nslices, _p(self.slice_ptr), _p(self.col),
-                                          _p(self.val), _p(self.mass), _p(self.diag), _p(rhs), _p(x), 1.0 / _EPS,
-                                          float(rtol), min(20 * self.n + 1000, 100000), C.byref(iters)))
-        self.iterations += int(iters.value)
-        self.solves += 1
-        return x
+from .linsolve import DeviceOperator, _p
 
 
 def _arnoldi_device(op, b, dim, pcg_rtol, work, h2):
@@ -105,8 +54,8 @@ def transform_device(M_is, A_body, A_film, A, B, C, dim, pcg_rtol=1e-13, device=
     C_out = np.asarray(C, dtype=np.float64)
     n, S = B.shape
     dim = int(dim)
-    opA = _DeviceOperator(A, dev)
-    opBody = _DeviceOperator(A_body, dev)
+    opA = DeviceOperator(A, dev)
+    opBody = DeviceOperator(A_body, dev)
     mis = torch.from_numpy(np.ascontiguousarray(M_is.diagonal())).to(dev)
     film_diag = [torch.from_numpy(np.ascontiguousarray(Af.diagonal())).to(dev) for Af in A_film] if A_film is not None else []
     Bd = torch.from_numpy(np.ascontiguousarray(B.T)).to(dev)            # (S, n)

@@ -16,14 +16,9 @@ relative perturbation of 1e-24, far below the solver tolerance.
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 
-from . import _cabi
-from .device import csr_to_sell
-
-_EPS = 2.0 ** -80
+from .linsolve import DeviceOperator
 
 
 class NotConvergedError(RuntimeError):
@@ -40,7 +35,6 @@ def spd_solve(A, b, rtol=1e-12, maxit=None, device=None, return_info=False):
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("thermca_b200.stationary needs a CUDA device (no CPU fallback)")
-    lib = _cabi.load_library()
     A = sp.csr_matrix(A)
     n = A.shape[0]
     if A.shape[0] != A.shape[1]:
@@ -54,34 +48,21 @@ def spd_solve(A, b, rtol=1e-12, maxit=None, device=None, return_info=False):
                          "boundary condition set has no unique equilibrium")
     if not b.any():
         return (np.zeros(n), {"iterations": 0, "relres": 0.0}) if return_info else np.zeros(n)
-    A.sort_indices()
-    s = csr_to_sell(A.indptr, A.indices, A.data)
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    t_ptr, t_col, t_val = up(s["slice_ptr"]), up(s["col"]), up(s["val"])
-    t_diag, t_b = up(diag), up(b)
-    t_mass = torch.full((n,), _EPS, dtype=torch.float64, device=dev)
-    t_rhs = t_b / _EPS                                   # mass * rhs == b exactly
-    t_x = torch.zeros(n, dtype=torch.float64, device=dev)
-    t_r = torch.empty(n, dtype=torch.float64, device=dev)
-    p = lambda a: C.c_void_p(a.data_ptr()) if a is not None else C.c_void_p(0)
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    iters = C.c_int32(0)
-    maxit = int(maxit) if maxit is not None else 20 * n + 1000     # capped at 2n+50 by the library
-    torch.cuda.synchronize(dev)
-    _cabi.check(lib.tc_pcg_solve(stream, 0, n, s["nslices"], p(t_ptr), p(t_col), p(t_val), p(t_mass), p(t_diag),
-                                 p(t_rhs), p(t_x), 1.0 / _EPS, float(rtol), maxit, C.byref(iters)))
+    op = DeviceOperator(A, dev)
+    t_b = torch.from_numpy(b).to(dev)
+    t_x = op.solve(t_b, rtol, maxit)
     # independent residual check: r = b - A x
-    _cabi.check(lib.tc_sell_spmv(stream, 1, n, s["nslices"], p(t_ptr), p(t_col), p(None), p(t_val), p(t_x), p(t_r),
-                                 p(t_b), p(None), 0.0, 0))
+    t_r = op.residual_into(t_x, t_b, torch.empty(n, dtype=torch.float64, device=dev))
     torch.cuda.synchronize(dev)
     relres = float(torch.linalg.vector_norm(t_r) / torch.linalg.vector_norm(t_b))
+    iters = op.last_iterations
     if not np.isfinite(relres) or relres > 100.0 * rtol:
-        raise NotConvergedError(f"device PCG stopped after {iters.value} iterations at relative residual {relres:.3e} "
+        raise NotConvergedError(f"device PCG stopped after {iters} iterations at relative residual {relres:.3e} "
                                 f"(requested {rtol:.1e}); is the matrix symmetric positive definite?")
     x = t_x.cpu().numpy()
     if return_info:
-        return x, {"iterations": int(iters.value), "relres": relres}
+        return x, {"iterations": int(iters), "relres": relres}
     return x
 
 
