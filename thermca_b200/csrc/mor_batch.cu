@@ -198,6 +198,7 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
                          double* __restrict__ Xout, double* __restrict__ Xacc, double t, double h,
                          double c_out, double c_acc, int first) {
     extern __shared__ __align__(16) double smem[];
+    asm volatile("griddepcontrol.launch_dependents;");      // the next stage's CTAs may fill the tail of this grid
     constexpr int TMX = MB_TM + 8;              // rows per operator buffer: tile + one folded 8-row strip
     constexpr int A_STAGE = NOPS * TMX * MP_LDA;
     constexpr int X_STAGE = MP_TK * MP_LDX;
@@ -243,9 +244,8 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
     const bool x_in = b0 + 2 * x_bp < B;
     const size_t x_off = (size_t)x_kk * B + b0 + 2 * x_bp;
     const int x_dst = x_kk * MP_LDX + 2 * x_bp;
-    auto load_chunk = [&](int stage, int k0) {
+    auto load_ops = [&](int stage, int k0) {
         double* sA = sA0 + stage * A_STAGE;
-        double* sX = sX0 + stage * X_STAGE;
         const bool k_in = k0 + 2 * a_kp < r;            // r is even: a pair is either inside or outside
 #pragma unroll
         for (int q = 0; q < 2 * NOPS; ++q) {
@@ -262,6 +262,9 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
             cp_async16(sA + (e_o * TMX + MB_TM + e_ri) * MP_LDA + 2 * a_kp,
                        ok ? (const void*)(W + (size_t)(i0 + MB_TM + e_ri) * r + 2 * a_kp + k0) : (const void*)Wb, ok ? 16 : 0);
         }
+    };
+    auto load_state = [&](int stage, int k0) {
+        double* sX = sX0 + stage * X_STAGE;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const bool ok = x_in && k0 + x_kk + 8 * q < r;
@@ -270,6 +273,7 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
         }
         cp_async_commit();
     };
+    auto load_chunk = [&](int stage, int k0) { load_ops(stage, k0); load_state(stage, k0); };
 
     const bool live[2] = {i0 + wm < r, i0 + wm + 8 < r};      // warp-uniform
     const bool full_tile = i0 + MB_TM <= r;                     // CTA-uniform
@@ -280,7 +284,12 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
     // has passed it, chunk ch is visible AND everybody is done with chunk ch-1, whose buffer the prefetch of
     // chunk ch+1 may therefore overwrite.
     auto k_loop = [&](auto ragged, auto extra) {
-        load_chunk(0, 0);
+        // Programmatic dependent launch: this grid may have been scheduled while the previous stage kernel was
+        // still draining.  The operators do not depend on it, so their first chunk is already in flight when the
+        // grid dependency (previous stage complete and flushed) is awaited; everything after reads the state.
+        load_ops(0, 0);
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        load_state(0, 0);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int st = ch & 1;
             cp_async_wait<0>();
@@ -424,7 +433,15 @@ static int launch_stage_pipe(int S, int r, int B, cudaStream_t st, const MorBatc
         configured = true;
     }
     dim3 grid((B + MP_TN - 1) / MP_TN, mor_fold_rows(r) ? r / MB_TM : (r + MB_TM - 1) / MB_TM, S);
-    tc_mor_stage_pipe_kernel<NOPS><<<grid, MB_THREADS, smem, st>>>(M, fv, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc, first);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(MB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const double* fvc = fv;
+    TC_CUDA(cudaLaunchKernelEx(&cfg, tc_mor_stage_pipe_kernel<NOPS>, M, fvc, Xin, Xbase, Xout, Xacc, t, h, c_out, c_acc,
+                               first));
     return 0;
 }
 
