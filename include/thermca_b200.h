@@ -216,6 +216,16 @@ int tc_csr_to_sell(void* cuda_stream, int32_t n, int32_t nslices, const int64_t*
                    const double* data, const double* row_scale, double scale, const int64_t* slice_ptr,
                    int32_t* col, int16_t* col16, double* val, double* diag_out);
 
+/* ---- Jacobi-PCG for K <= 8 right-hand sides sharing one matrix sweep per iteration (csrc/pcg_multi.cu) ----
+ * A X = B, A symmetric positive definite in SELL-32 with diagonal `diag`; B, X: [n][K] with the K values of a
+ * row contiguous; iters_dev[K]: device array of iteration counts (maxit = not converged).
+ * work: tc_pcg_multi_work_doubles(n, K) doubles.  Replaces the per-surface solves of
+ * arnoldi_iteration (thermca/fem/mor_io.py:206) when several surfaces advance together. */
+int64_t tc_pcg_multi_work_doubles(int64_t n, int32_t K);
+int tc_pcg_solve_multi(void* cuda_stream, int32_t n, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
+                       const double* val, const double* diag, int32_t K, const double* B, double* X, double* work,
+                       double rtol, int32_t maxit, int32_t* iters_dev);
+
 /* ---- orthogonalisation kernels of the inverse-Krylov MOR basis build (csrc/krylov.cu) ------------
  * Replace the modified Gram-Schmidt loop of arnoldi_iteration (thermca/fem/mor_io.py:203-217): v is
  * orthogonalised against the first k columns of the column-major Q (column j at Q + j*ld) by `passes`

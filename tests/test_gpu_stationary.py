@@ -60,3 +60,29 @@ def test_large_poisson_like_system():
     x, info = spd_solve(K, b, rtol=1e-10, return_info=True)
     assert np.linalg.norm(K @ x - b) / np.linalg.norm(b) < 1e-9
     assert info["iterations"] < 2000
+
+
+def test_multi_rhs_pcg_matches_single_solves():
+    """csrc/pcg_multi.cu: K right-hand sides with one matrix sweep per iteration == K separate solves."""
+    import torch
+    from thermca_b200.linsolve import DeviceOperator
+    n1 = 24
+    e = np.ones(n1)
+    T = sp.diags([-e[:-1], 2.2 * e, -e[:-1]], [-1, 0, 1])
+    I = sp.identity(n1)
+    K3 = (sp.kron(sp.kron(T, I), I) + sp.kron(sp.kron(I, T), I) + sp.kron(sp.kron(I, I), T)).tocsr()
+    rng = np.random.default_rng(5)
+    dev = torch.device("cuda")
+    op = DeviceOperator(K3, dev)
+    for K in (1, 2, 5, 8):
+        B = rng.standard_normal((K, K3.shape[0]))
+        B[K - 1] *= 1e-3                                       # different scales converge at different iterations
+        if K > 2:
+            B[1] = 0.0                                         # a zero right-hand side stays zero
+        Bd = torch.from_numpy(B).to(dev)
+        X = op.solve_multi(Bd, 1e-11).cpu().numpy()
+        for k in range(K):
+            xs = op.solve(Bd[k], 1e-11).cpu().numpy()
+            nb = np.linalg.norm(B[k])
+            assert np.linalg.norm(K3 @ X[k] - B[k]) <= 1e-10 * max(nb, 1e-300) + (0 if nb else 0)
+            assert np.abs(X[k] - xs).max() <= 1e-9 * max(np.abs(xs).max(), 1e-300) + (0.0 if nb else 1e-300)

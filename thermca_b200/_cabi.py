@@ -95,6 +95,8 @@ EXPORTS = {
     "tc_p1_tri_loads": (i32, [vp, i64, vp, vp, vp, vp]),
     "tc_segment_sum": (i32, [vp, i64, vp, vp, vp]),
     "tc_csr_to_sell": (i32, [vp, i32, i32, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]),
+    "tc_pcg_multi_work_doubles": (i64, [i64, i32]),
+    "tc_pcg_solve_multi": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, f64, i32, vp]),
     "tc_krylov_work_doubles": (i64, [i32]),
     "tc_krylov_orthogonalize": (i32, [vp, i64, i32, vp, i64, vp, i32, vp, vp, vp]),
     "tc_krylov_normalize": (i32, [vp, i64, vp, vp, vp]),

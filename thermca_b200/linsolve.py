@@ -67,6 +67,29 @@ class DeviceOperator:
         self.solves += 1
         return x
 
+    def solve_multi(self, B, rtol, maxit=None):
+        """X = A^-1 B for up to 8 right-hand sides (rows of the (K, n) tensor B) with one matrix sweep per PCG
+        iteration (csrc/pcg_multi.cu).  Returns the (K, n) solutions."""
+        torch = self.torch
+        K = int(B.shape[0])
+        if K == 1:
+            return self.solve(B[0], rtol, maxit)[None, :]
+        Bi = B.T.contiguous()                                  # [n][K]: the K values of a row contiguous
+        Xi = torch.empty_like(Bi)
+        nwork = int(self.lib.tc_pcg_multi_work_doubles(self.n, K))
+        if getattr(self, "_mwork", None) is None or self._mwork.numel() < nwork:
+            self._mwork = torch.empty(nwork, dtype=torch.float64, device=self.dev)
+        iters = torch.zeros(8, dtype=torch.int32, device=self.dev)
+        _cabi.check(self.lib.tc_pcg_solve_multi(self._stream(), self.n, self.nslices, _p(self.slice_ptr), _p(self.col),
+                                                _p(self.val), _p(self.diag), K, _p(Bi), _p(Xi), _p(self._mwork),
+                                                float(rtol), int(maxit) if maxit else min(20 * self.n + 1000, 100000),
+                                                _p(iters)))
+        it = iters[:K].cpu().numpy()
+        self.last_iterations = int(it.max())
+        self.iterations += int(it.max())                       # matrix sweeps
+        self.solves += K
+        return Xi.T.contiguous()
+
     def residual_into(self, x, b, r):
         """r = b - A x (separate SpMV launch; used to re-check a solve independently of the PCG recurrence)"""
         _cabi.check(self.lib.tc_sell_spmv(self._stream(), 1, self.n, self.nslices, _p(self.slice_ptr), _p(self.col),

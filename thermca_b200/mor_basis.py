@@ -24,23 +24,35 @@ from . import _cabi
 from .linsolve import DeviceOperator, _p
 
 
-def _arnoldi_device(op, b, dim, pcg_rtol, work, h2):
-    """Orthonormal basis (dim columns, column-major: tensor (dim, n)) of the Krylov space of A^-1 started at b
-    (thermca/fem/mor_io.py:176-218).  Columns after a breakdown (|v| <= 1e-12) stay zero, as in the reference."""
+def _arnoldi_device(op, Bs, dim, pcg_rtol, work, h2):
+    """Orthonormal bases (one per row of ``Bs``; each ``dim`` columns, column-major: tensor (dim, n)) of the Krylov
+    spaces of A^-1 started at those vectors (thermca/fem/mor_io.py:176-218).  The k-th solves of all bases run
+    together (one matrix sweep per PCG iteration, csrc/pcg_multi.cu).  Columns after a breakdown (|v| <= 1e-12)
+    stay zero, as in the reference."""
     torch = op.torch
     lib, n = op.lib, op.n
     stream = op._stream()
-    Q = torch.zeros((dim, n), dtype=torch.float64, device=op.dev)
-    v = b.clone()
-    _cabi.check(lib.tc_krylov_orthogonalize(stream, n, 0, _p(Q), n, _p(v), 1, _p(work), _p(None), _p(h2)))
-    _cabi.check(lib.tc_krylov_normalize(stream, n, _p(v), _p(h2), _p(Q[0])))
+    S = int(Bs.shape[0])
+    Qs = [torch.zeros((dim, n), dtype=torch.float64, device=op.dev) for _ in range(S)]
+    alive = [True] * S
+    for s in range(S):
+        v = Bs[s].clone()
+        _cabi.check(lib.tc_krylov_orthogonalize(stream, n, 0, _p(Qs[s]), n, _p(v), 1, _p(work), _p(None), _p(h2)))
+        _cabi.check(lib.tc_krylov_normalize(stream, n, _p(v), _p(h2), _p(Qs[s][0])))
     for k in range(dim - 1):
-        v = op.solve(Q[k], pcg_rtol)
-        _cabi.check(lib.tc_krylov_orthogonalize(stream, n, k + 1, _p(Q), n, _p(v), 2, _p(work), _p(None), _p(h2)))
-        if float(h2.item()) ** 0.5 <= 1e-12:
-            break
-        _cabi.check(lib.tc_krylov_normalize(stream, n, _p(v), _p(h2), _p(Q[k + 1])))
-    return Q
+        idx = [s for s in range(S) if alive[s]]
+        for lo in range(0, len(idx), 8):
+            grp = idx[lo: lo + 8]
+            V = op.solve_multi(torch.stack([Qs[s][k] for s in grp]), pcg_rtol)
+            for j, s in enumerate(grp):
+                v = V[j].contiguous()
+                _cabi.check(lib.tc_krylov_orthogonalize(stream, n, k + 1, _p(Qs[s]), n, _p(v), 2, _p(work), _p(None),
+                                                        _p(h2)))
+                if float(h2.item()) ** 0.5 <= 1e-12:
+                    alive[s] = False
+                    continue
+                _cabi.check(lib.tc_krylov_normalize(stream, n, _p(v), _p(h2), _p(Qs[s][k + 1])))
+    return Qs
 
 
 def transform_device(M_is, A_body, A_film, A, B, C, dim, pcg_rtol=1e-13, device=None, return_info=False):
@@ -69,8 +81,9 @@ def transform_device(M_is, A_body, A_film, A, B, C, dim, pcg_rtol=1e-13, device=
     Crs = np.empty((S, dim, S))
     VT1 = np.empty((S, n, dim))
     VT0 = np.empty((S, dim, n))
+    Qs = _arnoldi_device(opA, Bd, dim, pcg_rtol, work, h2)             # per surface (dim, n): row j = basis vector j
     for s in range(S):
-        Q = _arnoldi_device(opA, Bd[s], dim, pcg_rtol, work, h2)        # (dim, n): row j = basis vector j
+        Q = Qs[s]
         for j in range(dim):
             opBody.matvec_into(Q[j], Y[j])
         Ar_body[s] = torch.matmul(Q, Y.T).cpu().numpy()                 # V^T A_body V
