@@ -184,6 +184,11 @@ __host__ __device__ constexpr int mor_pipe_smem_doubles(int nops) {
     return 2 * (nops * (MB_TM + 8) * MP_LDA + MP_TK * MP_LDX) > (MB_TM + 8) * (MP_TN + 8)
                ? 2 * (nops * (MB_TM + 8) * MP_LDA + MP_TK * MP_LDX) : (MB_TM + 8) * (MP_TN + 8);
 }
+// + the epilogue's small operands, fetched with the first chunk: film values of the tile's scenario columns
+// [F][64] and the B_T rows of the tile [72]
+__host__ __device__ constexpr int mor_pipe_smem_total(int nops) {
+    return mor_pipe_smem_doubles(nops) + (nops > 1 ? nops - 1 : 1) * MP_TN + MB_TM + 8;
+}
 
 // a remainder of 1..8 rows past the last full 64-row tile is folded into that tile
 __host__ __device__ __forceinline__ bool mor_fold_rows(int r) {
@@ -204,6 +209,8 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
     constexpr int X_STAGE = MP_TK * MP_LDX;
     double* sA0 = smem;                         // [2][NOPS][72][20]
     double* sX0 = smem + 2 * A_STAGE;           // [2][16][68]
+    double* sF = smem + mor_pipe_smem_doubles(NOPS);                         // [NOPS-1][64] film values of the columns
+    double* sBT = sF + (NOPS > 1 ? NOPS - 1 : 1) * MP_TN;                    // [72] B_T rows of the tile
     // CTA order: scenario tile fastest, then surface, row tile slowest, so the cheap ragged last row tiles
     // (r % 64 rows) are scheduled last and fill the tail of the final wave
     const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
@@ -289,6 +296,16 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
         // grid dependency (previous stage complete and flushed) is awaited; everything after reads the state.
         load_ops(0, 0);
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        // the epilogue's small operands ride along with the first chunk (their L2 latency is off the tail)
+        if (tid < (NOPS - 1) * 32) {
+            const int f = tid >> 5, cp2 = 2 * (tid & 31);
+            const bool ok = b0 + cp2 < B;
+            cp_async16(sF + f * MP_TN + cp2, ok ? (const void*)(fv + (size_t)f * B + b0 + cp2) : (const void*)Xs, ok ? 16 : 0);
+        } else if (tid >= 128 && tid < 128 + TMX / 2) {
+            const int rp = 2 * (tid - 128);
+            const bool ok = i0 + rp < r;
+            cp_async16(sBT + rp, ok ? (const void*)(M.B_T + (size_t)s * r + i0 + rp) : (const void*)Xs, ok ? 16 : 0);
+        }
         load_state(0, 0);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int st = ch & 1;
@@ -344,20 +361,15 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
         const double q_s = M.q_surf[s];
         double bt[2];
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int gi = i0 + wm + 8 * a + (lane >> 2);
-            bt[a] = gi < r ? M.B_T[(size_t)s * r + gi] : 0.0;
-        }
+        for (int a = 0; a < 2; ++a) bt[a] = sBT[wm + 8 * a + (lane >> 2)];          // zero-filled past r
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int cl = wn + 8 * c + 2 * (lane & 3);
-            const int gb = b0 + cl;
             double fvv[NOPS > 1 ? NOPS - 1 : 1][2];
             double flux[2] = {q_s, q_s};
 #pragma unroll
             for (int f = 0; f < NOPS - 1; ++f) {
-                double2 v = make_double2(0.0, 0.0);
-                if (gb < B) v = *reinterpret_cast<const double2*>(fv + (size_t)f * B + gb);
+                const double2 v = *reinterpret_cast<const double2*>(sF + f * MP_TN + cl);  // zero-filled past B
                 fvv[f][0] = v.x; fvv[f][1] = v.y;
                 if (M.film_surf[f] == s) { const double tl = M.t_link[f]; flux[0] += v.x * tl; flux[1] += v.y * tl; }
             }
@@ -374,8 +386,7 @@ tc_mor_stage_pipe_kernel(MorBatch M, const double* __restrict__ fv, const double
                 *reinterpret_cast<double2*>(sK + (wm + 8 * a + (lane >> 2)) * LDK + cl) = make_double2(kv[0], kv[1]);
             }
             if (ext && c == cx) {                    // folded strip: row 64 + lane/4 of the tile
-                const int gi = i0 + MB_TM + (lane >> 2);
-                const double btx = gi < r ? M.B_T[(size_t)s * r + gi] : 0.0;
+                const double btx = sBT[MB_TM + (lane >> 2)];
                 double kv[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -426,7 +437,7 @@ template <int NOPS>
 static int launch_stage_pipe(int S, int r, int B, cudaStream_t st, const MorBatch& M, double* fv, const double* Xin,
                              const double* Xbase, double* Xout, double* Xacc, double t, double h, double c_out,
                              double c_acc, int first) {
-    const size_t smem = sizeof(double) * mor_pipe_smem_doubles(NOPS);
+    const size_t smem = sizeof(double) * mor_pipe_smem_total(NOPS);
     static bool configured = false;
     if (!configured) {
         TC_CUDA(cudaFuncSetAttribute(tc_mor_stage_pipe_kernel<NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
