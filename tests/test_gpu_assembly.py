@@ -126,3 +126,21 @@ def test_device_mesh_spec_runs_and_matches_host_spec():
     yh = dev.get_state()
     dev.close()
     assert np.abs(yd - yh).max() < 1e-8
+
+
+def test_fem_matrices_drop_in_returns_the_reference_tuple():
+    """`fem_matrices_device(body_mesh, surf_meshes)` = the tuple FESystem.__init__ unpacks (fe_system.py:114-125),
+    compared element by element with what the reference's own function returned for plate.msh."""
+    from types import SimpleNamespace
+    from thermca_b200.assembly import fem_matrices_device
+    pts, tets, tris, ref = _mesh("plate")
+    body = SimpleNamespace(points=pts, cell_blocks=[tets])
+    surfs = SimpleNamespace(cell_blocks=tris, block_names=ref["names"])
+    Mx, Lx, Qs, v2d, d2v, dof, sdofs, areas = fem_matrices_device(body, surfs)
+    assert dof == len(pts) and np.array_equal(v2d, np.arange(dof)) and np.array_equal(d2v, np.arange(dof))
+    assert sp.issparse(Lx) and Lx.format == "csr" and Lx.shape == (dof, dof)
+    assert np.abs((Lx - ref["Lx"]).data).max() <= 1e-13 * np.abs(ref["Lx"].data).max()
+    assert np.allclose(Mx, ref["Mx"], rtol=1e-13, atol=0)
+    assert Qs.shape == ref["Qs"].shape and np.allclose(Qs, ref["Qs"], rtol=1e-13, atol=0)
+    assert all(np.array_equal(a, b) for a, b in zip(sdofs, ref["sdofs"]))
+    assert np.allclose(areas, ref["areas"], rtol=1e-13)
