@@ -1,6 +1,7 @@
 """Parity of the CUDA path against the oracle and the reference-generated golden vectors.
 Everything here goes through the C ABI (thermca_b200/_cabi.py)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -301,9 +302,22 @@ def test_ros2_with_implicit_lp_part(torch_cuda, golden):
     dev = DeviceSolver(spec)
     out = dev.run_ros2(0.0, 300.0, rtol=1e-5, atol=1e-7, pcg_rtol=1e-10)
     dev.close()
-    assert out["status"] == 0 and out["times"][-1] == 300.0 and out["pcg"]["solves"] > 0
+    assert out["status"] == 0 and out["times"][-1] == 300.0
     assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=2e-4)
     assert np.allclose(out["io_temps"][-1], tight["io_temps"][-1], rtol=2e-4)
+    # below the stability bound the W-method keeps the block explicit (TC_W_EXPLICIT_BOUND in csrc/solver.cu); with
+    # the bound at 0 every attempt solves the LP part by PCG - same accuracy requirement
+    os.environ["TC_W_EXPLICIT_BOUND"] = "0"
+    try:
+        dev = DeviceSolver(spec)
+        imp = dev.run_ros2(0.0, 300.0, rtol=1e-5, atol=1e-7, pcg_rtol=1e-10)
+        dev.close()
+    finally:
+        del os.environ["TC_W_EXPLICIT_BOUND"]
+    assert imp["status"] == 0 and imp["pcg"]["solves"] > 0 and out["pcg"]["solves"] == 0
+    assert np.allclose(imp["net_temps"][-1], tight["net_temps"][-1], rtol=2e-4)
+    assert np.allclose(imp["io_temps"][-1], tight["io_temps"][-1], rtol=2e-4)
+    print("coffee cup ROS2 steps: gated", out["accepted"], "always implicit", imp["accepted"])
 
 
 def test_probe_history_matches_full_history(torch_cuda, golden):
@@ -394,3 +408,26 @@ def test_ros2_with_implicit_mor_blocks(torch_cuda, golden, name):
     scale = np.abs(tight["io_temps"][-1]).max()
     assert np.abs(out["io_temps"][-1] - tight["io_temps"][-1]).max() < 1e-3 * scale
     print(name, "ROS2 accepted", out["accepted"], "rejected", out["rejected"])
+
+
+@pytest.mark.parametrize("name,t1", [("getting_started", 5.0), ("plate_ffe_var", 20.0), ("kuhn_cuboid", 5.0), ("lp_tdep", 3.0),
+                                     ("steel_sheet", 2000.0), ("cutting_disc", 2.0)])
+def test_ros2_agrees_with_tight_rk45_on_every_model_family(torch_cuda, golden, name, t1):
+    """The LSODA substitute on the remaining goldens (network-only, LP, temperature dependent LP, FE with
+    closures / Inputs / stationary nodes): node temperatures and part states against a tight explicit run."""
+    from thermca_b200.device import DeviceSolver
+    from rhs_oracle import integrate
+    spec, ex = golden(name)
+    t0 = float(ex["sim"]["t0"])
+    tight = integrate(spec, [t0, t1], 1e-8, 1e-10, "RK45")
+    # lp_tdep: conductivity varies 5x over the 3 K this body spans, so the frozen-operator Jacobian is off by O(1);
+    # in the implicit regime the W-method is then second order with a large constant - judged at 1e-6 instead
+    rtol = 1e-6 if name == "lp_tdep" else 1e-5
+    dev = DeviceSolver(spec)
+    out = dev.run_ros2(t0, t1, rtol=rtol, atol=1e-3 * rtol, pcg_rtol=1e-10)
+    dev.close()
+    assert out["status"] == 0 and out["times"][-1] == t1
+    assert np.allclose(out["net_temps"][-1], tight["net_temps"][-1], rtol=5e-4, atol=1e-5)
+    if tight["io_temps"].shape[1]:
+        scale = np.abs(tight["io_temps"][-1]).max()
+        assert np.abs(out["io_temps"][-1] - tight["io_temps"][-1]).max() < 5e-4 * scale

@@ -33,6 +33,7 @@ struct TcPcg {
     const double* ctrl;     // shift = coef * ctrl[1]
     double coef;
     unsigned long long* prof;   // optional [16] phase times (ns) of block 0
+    const int* skip;            // optional: non-zero -> leave x untouched (block is explicit this attempt)
 };
 
 #define TC_PCG_THREADS 256
@@ -102,6 +103,7 @@ template <int MB>
 __global__ void __launch_bounds__(TC_PCG_THREADS, MB)
 tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;       // uniform over the grid
+    if (S.skip && *S.skip) return;             // uniform over the grid
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
     const int G = gridDim.x;

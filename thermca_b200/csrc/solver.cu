@@ -256,6 +256,11 @@ __global__ void tc_advance_time_kernel(double* ctrl, int* fl) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Blocks stay explicit inside the W-method while gamma*h times the Gershgorin bound G of their operator is below
+// this value: h*rho(A) <= h*G < 2/1.707 = 1.17, inside the stability interval [-2, 0] of the explicit limit of ROS2
+// (Heun's method) with a margin of 40 %.
+#define TC_W_EXPLICIT_BOUND 2.0
+
 struct FfePart {
     tc_ffe_desc d;
     TcSell A;
@@ -292,6 +297,8 @@ struct tc_solver {
     double* hist_io = nullptr; double* hist_net = nullptr; int capacity = 0; int num_skip = 0;
     const long long* probe_idx = nullptr; int n_probe = 0;     // probe mode of the history (tc_set_probes)
     double* net_vec = nullptr;                                 // 4*u doubles: CG vectors of the network block solve
+    int* gate_flags = nullptr; double* gate_partial = nullptr; unsigned int* gate_counter = nullptr;   // stiffness gates
+    double w_bound = TC_W_EXPLICIT_BOUND;                      // env TC_W_EXPLICIT_BOUND overrides (0: always implicit)
     // RK
     int method = TC_RK45; int n_stages = 6;
     cudaGraphExec_t rk_graph = nullptr;
@@ -345,7 +352,7 @@ extern "C" int tc_destroy(tc_handle s) {
     cudaFree(s->pcg_isc); cudaFree(s->mean_partials);
     cudaFree(s->y); cudaFree(s->ynew); cudaFree(s->ystage);
     for (int i = 0; i < 7; ++i) cudaFree(s->K[i]);
-    cudaFree(s->net_vec);
+    cudaFree(s->net_vec); cudaFree(s->gate_flags); cudaFree(s->gate_partial); cudaFree(s->gate_counter);
     for (auto& p : s->ffe) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
     for (auto& p : s->lp) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
     cudaFreeHost(s->pin_flags); cudaFreeHost(s->pin_ctrl);
@@ -426,6 +433,14 @@ extern "C" int tc_finalize(tc_handle s, int64_t n_state) {
         TC_CUDA(cudaMalloc(&p.q, b)); TC_CUDA(cudaMalloc(&p.dinv, b));
     }
     if (s->net.u > 0) TC_CUDA(cudaMalloc(&s->net_vec, sizeof(double) * 4 * (size_t)s->net.u));
+    {
+        const size_t nparts = s->ffe.size() + s->lp.size() + 1;
+        TC_CUDA(cudaMalloc(&s->gate_flags, sizeof(int) * nparts));
+        TC_CUDA(cudaMemset(s->gate_flags, 0, sizeof(int) * nparts));
+        TC_CUDA(cudaMalloc(&s->gate_partial, sizeof(double) * 256));
+        TC_CUDA(cudaMalloc(&s->gate_counter, sizeof(unsigned int)));
+        TC_CUDA(cudaMemset(s->gate_counter, 0, sizeof(unsigned int)));
+    }
     s->coop_grid = pcg_coop_grid(s->sm_count);
     s->finalized = true;
     return 0;
@@ -875,7 +890,7 @@ tc_net_block_solve_kernel(TcNetParams P, const double* __restrict__ ctrl, double
 // the fly.  One CTA per surface runs Jacobi-CG with its vectors in shared memory (5 r doubles).
 __global__ void __launch_bounds__(256)
 tc_mor_block_solve_kernel(TcMor M, const double* __restrict__ films, const double* __restrict__ ctrl, double coef,
-                          const double* __restrict__ rhs, double* __restrict__ z, double rtol,
+                          double bound, const double* __restrict__ rhs, double* __restrict__ z, double rtol,
                           const int* __restrict__ done) {
     if (done && *done) return;
     extern __shared__ double smv[];
@@ -904,7 +919,7 @@ tc_mor_block_solve_kernel(TcMor M, const double* __restrict__ films, const doubl
         return out;
     };
     // A W-method may use any Jacobian approximation, also none: when the step is well inside the explicit
-    // stability region of this block (Gershgorin bound of s*A below 1/2) the copy made by the caller (z = rhs)
+    // stability region of this block (Gershgorin bound of s*A below TC_W_EXPLICIT_BOUND) the copy made by the caller (z = rhs)
     // stands and the block is explicit for this attempt - measured: fewer steps than damping non-stiff modes.
     {
         double g_l = 0.0;
@@ -921,7 +936,7 @@ tc_mor_block_solve_kernel(TcMor M, const double* __restrict__ films, const doubl
         double g = 0.0;
         for (int w = 0; w < nw; ++w) g = fmax(g, sh[w]);
         __syncthreads();
-        if (sft * g < 0.5) return;      // uniform over the CTA
+        if (sft * g < bound) return;      // uniform over the CTA
     }
     double rho_l = 0.0, bb_l = 0.0;
     for (int i = tid; i < r; i += nt) {
@@ -966,19 +981,51 @@ tc_mor_block_solve_kernel(TcMor M, const double* __restrict__ films, const doubl
     for (int i = tid; i < r; i += nt) x[i] = xs[i];
 }
 
+// Stiffness gate of one PCG block inside the W-method: with A = M^-1 K diagonally dominant, 2 max_i A_ii bounds
+// its spectral radius.  While s * 2 max A_ii < TC_W_EXPLICIT_BOUND the step is inside the explicit stability region and the
+// block is left explicit for this attempt (z = rhs, the copy the caller made): damping non-stiff modes with an
+// inexact Jacobian only costs accuracy (measured on the temperature dependent LP golden: error 7e-3 -> 1e-6 at
+// the same tolerance).  This is what LSODA's Adams/BDF switch does for the reference.
+__global__ void __launch_bounds__(256)
+tc_pcg_gate_kernel(long long n, const double* __restrict__ adiag, const double* __restrict__ ctrl, double coef,
+                   double bound, double* __restrict__ partial, unsigned int* __restrict__ counter,
+                   int* __restrict__ skip, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sh[32];
+    double m = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmax(m, adiag[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+        partial[blockIdx.x] = m;
+    }
+    if (last_block_arrives(counter)) {
+        if (threadIdx.x == 0) {
+            double g = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) g = fmax(g, ((volatile double*)partial)[b]);
+            *skip = (coef * ctrl[1] * 2.0 * g < bound) ? 1 : 0;
+        }
+    }
+}
+
 // w_method: the caller tolerates an inexact Jacobian (ROS2), so temperature dependent bodies are solved with
 // their operator frozen at the initial temperatures; otherwise they are left explicit
 static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, double* z, bool w_method = false) {
     cudaStream_t st = s->stream;
     const int* done = s->flags + FL_DONE;
     tc_copy_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, rhs, z, done);
+    int gate_ix = 0;
     if (w_method && s->net.u > 0 && s->net_vec)
         tc_net_block_solve_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, coef, rhs, z, s->net_vec, 1e-12, done);
     if (w_method)
         for (auto& p : s->mor) {
             if (p.M.r > 1024) continue;                      // vectors would not fit the default shared memory: explicit
             tc_mor_block_solve_kernel<<<p.M.S, 256, sizeof(double) * 5 * p.M.r, st>>>(
-                p.M, s->net.darena + p.d.films_doff, s->ctrl, coef, rhs + p.d.y_off, z + p.d.y_off, 1e-12, done);
+                p.M, s->net.darena + p.d.films_doff, s->ctrl, coef, s->w_bound, rhs + p.d.y_off, z + p.d.y_off, 1e-12,
+                done);
         }
     // LP parts: same SPD structure (M A = L_body + film/margin diagonal, thermca/lpm/lp_io.py:106-128)
     for (auto& p : s->lp) {
@@ -989,6 +1036,13 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         P.partial = s->red_partial; P.sc = s->pcg_sc; P.isc = s->pcg_isc;
         P.rtol = s->pcg_rtol; P.maxit = s->pcg_maxit; P.ctrl = s->ctrl; P.coef = coef;
         P.prof = nullptr;
+        P.skip = nullptr;
+        if (w_method && s->pcg_mode == TC_PCG_COOP) {
+            int* flag = s->gate_flags + gate_ix++;
+            tc_pcg_gate_kernel<<<grid_for(p.d.n, 256, 256), 256, 0, st>>>(p.d.n, P.adiag, s->ctrl, coef, s->w_bound,
+                                                                          s->gate_partial, s->gate_counter, flag, done);
+            P.skip = flag;
+        }
         if (launch_pcg(s, P, s->pcg_mode, s->coop_grid, done)) return -1;
     }
     for (auto& p : s->ffe) {
@@ -1001,6 +1055,13 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         P.partial = s->red_partial; P.sc = s->pcg_sc; P.isc = s->pcg_isc;
         P.rtol = s->pcg_rtol; P.maxit = s->pcg_maxit; P.ctrl = s->ctrl; P.coef = coef;
         P.prof = s->timing ? s->pcg_prof : nullptr;
+        P.skip = nullptr;
+        if (w_method && s->pcg_mode == TC_PCG_COOP) {
+            int* flag = s->gate_flags + gate_ix++;
+            tc_pcg_gate_kernel<<<grid_for(p.d.n, 256, 256), 256, 0, st>>>(p.d.n, P.adiag, s->ctrl, coef, s->w_bound,
+                                                                          s->gate_partial, s->gate_counter, flag, done);
+            P.skip = flag;
+        }
         if (launch_pcg(s, P, s->pcg_mode, s->coop_grid, done)) return -1;
     }
     return 0;
@@ -1030,6 +1091,7 @@ extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, 
                              double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
+    if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);
     if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / 2.0)) return -1;
     s->evals_per_attempt = 2;
     s->nfev_base = 1;
