@@ -23,8 +23,10 @@ class _OracleDevice:
     def __init__(self, spec):
         self.spec = spec
 
-    def run_rk(self, t0, t1, rtol, atol, method, num_skip, max_step=np.inf, first_step=None):
+    def run_rk(self, t0, t1, rtol, atol, method, num_skip, max_step=np.inf, first_step=None, progress=None):
         from rhs_oracle import integrate
+        if progress is not None:                       # the device driver reports after every burst of attempts
+            progress({"t": 0.5 * (t0 + t1)})
         opts = {}
         if np.isfinite(max_step):
             opts["max_step"] = max_step
@@ -60,6 +62,7 @@ def test_sim_through_dropin_matches_reference(dropin):
     from thermca import Network
     net, kw = ref_models.coffeecup()
     res_new = net.sim(kw["time_span"], rel_tol=kw["rel_tol"], progress_bar=False)
+    assert net._solve_step_time == kw["time_span"][1] and net.time == kw["time_span"][1]   # progress attributes kept up
     dropin.uninstall()
     net2, _ = ref_models.coffeecup()
     res_ref = net2.sim(kw["time_span"], rel_tol=kw["rel_tol"], progress_bar=False)

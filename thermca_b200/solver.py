@@ -32,16 +32,27 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
         method = getattr(method, "__name__", str(method))
     spec = lower_network(net)
     dev = DeviceSolver(spec)
+
+    # the progress thread of Network.sim reads these two attributes every 2 s (network.py:960-985, solver.py:321-325)
+    import time as _time
+    last = [t0, _time.perf_counter()]
+
+    def progress(info):
+        now = _time.perf_counter()
+        if now > last[1]:
+            net._solve_step_speed = (info["t"] - last[0]) / (now - last[1])
+        net._solve_step_time = info["t"]
+        last[0], last[1] = info["t"], now
     try:
         if method in ("RK45", "RK23"):
             res = dev.run_rk(t0, t1, rel_tol, abs_tol, method, num_skip,
                              max_step=options.get("max_step", np.inf),
-                             first_step=options.get("first_step"))
+                             first_step=options.get("first_step"), progress=progress)
         elif method in IMPLICIT_METHODS:
             res = dev.run_ros2(t0, t1, rel_tol, abs_tol, num_skip,
                                max_step=options.get("max_step", np.inf),
                                first_step=options.get("first_step"),
-                               pcg_rtol=options.get("pcg_rtol", 1e-8))
+                               pcg_rtol=options.get("pcg_rtol", 1e-8), progress=progress)
         else:
             raise ValueError(f"unknown integration method {method!r}")
         final_net = dev.network_state()
@@ -83,7 +94,6 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
     # side effects the reference leaves behind (SURVEY.md §8b "what it must write")
     net.time = float(res["times"][-1]) if len(res["times"]) else t0
     net._solve_step_time = net.time
-    net._solve_step_speed = 0.0
     net.capy[:] = final_net["capy"]
     net.heat_src[:] = final_net["heat_src"]
     net.run_cond.data[:] = final_net["cond"]
