@@ -120,49 +120,8 @@ tc_network_kernel(TcNetParams P, const double* __restrict__ ctrl, double c_stage
             for (int i = tid; i < a[0]; i += nt)
                 cond[dx[i]] = __ddiv_rn(__dmul_rn(vf[i], __dadd_rn(volcapy[i0[i]], volcapy[i1[i]])), 2.0);
         } break;
-        case C_FLOW_FUNC: {             // prog, n, didx, i0, i1
-            const int *dx = I + a[2], *i0 = I + a[3], *i1 = I + a[4];
-            for (int i = tid; i < a[1]; i += nt) {
-                const double f = tc_vm_run(I, D, P.prog_dir, a[0], tb, inputs, T[i0[i]], T[i1[i]], reg);
-                cond[dx[i]] = __ddiv_rn(__dmul_rn(f, __dadd_rn(volcapy[i0[i]], volcapy[i1[i]])), 2.0);
-            }
-        } break;
-        case C_FILM_FUNC: {             // prog, n, fwd, bwd, i0, i1, areas_doff
-            const int *fw = I + a[2], *bw = I + a[3], *i0 = I + a[4], *i1 = I + a[5];
-            const double* ar = D + a[6];
-            for (int i = tid; i < a[1]; i += nt) {
-                const double f = tc_vm_run(I, D, P.prog_dir, a[0], tb, inputs, T[i0[i]], T[i1[i]], reg);
-                const double cv = __dmul_rn(f, ar[i]);
-                clean[fw[i]] = cv; clean[bw[i]] = cv;
-                cond[fw[i]] = cv; cond[bw[i]] = cv;
-            }
-        } break;
-        case C_HEAT_FUNC: {             // prog, K, m, idxs_off (K*m), counts_doff
-            const int* idx = I + a[3];
-            const double* cnt = D + a[4];
-            const int m = a[2];
-            for (int k = tid; k < a[1]; k += nt) {
-                double s = 0.0;
-                for (int j = 0; j < m; ++j) s += T[idx[k * m + j]];
-                const double mean = __ddiv_rn(s, (double)m);
-                const double f = tc_vm_run(I, D, P.prog_dir, a[0], tb, inputs, mean, 0.0, reg);
-                const double q = __ddiv_rn(f, cnt[k]);
-                for (int j = 0; j < m; ++j) heat[idx[k * m + j]] = q;
-            }
-        } break;
-        case C_FLUX_FUNC: {             // prog, n, idx, areas_doff
-            const int* idx = I + a[2];
-            const double* ar = D + a[3];
-            for (int i = tid; i < a[1]; i += nt) {
-                const double f = tc_vm_run(I, D, P.prog_dir, a[0], tb, inputs, T[idx[i]], 0.0, reg);
-                heat[idx[i]] = __dmul_rn(f, ar[i]);
-            }
-        } break;
-        case C_BOUND_FUNC: {            // prog, n, idx
-            const int* idx = I + a[2];
-            for (int i = tid; i < a[1]; i += nt)
-                T[idx[i]] = tc_vm_run(I, D, P.prog_dir, a[0], tb, inputs, 0.0, 0.0, reg);
-        } break;
+        // C_FLOW_FUNC .. C_BOUND_FUNC: superseded by C_FUNCS (all closure groups in one command); the enum values stay
+        // reserved so that the command numbering of thermca_b200/device.py does not shift
         case C_FUNCS: {
             // All closure groups of one right-hand side at once.  The closures read only node temperatures,
             // Inputs and material tables (network.py:773-796 calls them before any bound temperature is
