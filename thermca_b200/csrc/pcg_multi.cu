@@ -32,6 +32,7 @@ struct TcPcgMulti {
 };
 
 // every block sums the G partials of K quantities in block order; result in out[k] for all threads
+template <int KT>
 __device__ __forceinline__ void pm_bank_sums(const double* bank, int G, int K, double* sh, double* bc, double* out) {
     for (int k = 0; k < K; ++k) {
         const double s = ordered_partial_sum(bank + (size_t)k * TC_MAX_PARTIALS, G, sh);
@@ -39,16 +40,19 @@ __device__ __forceinline__ void pm_bank_sums(const double* bank, int G, int K, d
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < PM_KMAX; ++k) out[k] = k < K ? bc[k] : 0.0;      // static indices: `out` stays in registers
+    for (int k = 0; k < KT; ++k) out[k] = bc[k];      // static indices: `out` stays in registers
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(PM_THREADS, 2)
+// KT = number of right-hand sides (compile time: exact unrolling, registers and occupancy scale with it)
+template <int KT>
+__global__ void __launch_bounds__(PM_THREADS, (KT <= 2 ? 6 : (KT <= 4 ? 4 : 2)))
 tc_pcg_multi_kernel(TcPcgMulti S) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
-    __shared__ double bc[PM_KMAX];
-    const int G = gridDim.x, K = S.K, n = S.n;
+    __shared__ double bc[KT];
+    const int G = gridDim.x, n = S.n;
+    constexpr int K = KT;
     const int tid = threadIdx.x, lane = tid & 31;
     const long long gtid = blockIdx.x * (long long)PM_THREADS + tid, gthreads = (long long)G * PM_THREADS;
     double* bank0 = S.partial;
@@ -56,13 +60,13 @@ tc_pcg_multi_kernel(TcPcgMulti S) {
     double* bank2 = S.partial + 2 * (size_t)PM_KMAX * TC_MAX_PARTIALS;
 
     // init: x = 0, r = b, p = r / diag; rho = r.z, bb = b.b
-    double acc0[PM_KMAX], acc1[PM_KMAX];
+    double acc0[KT], acc1[KT];
 #pragma unroll
-    for (int k = 0; k < PM_KMAX; ++k) acc0[k] = acc1[k] = 0.0;
+    for (int k = 0; k < KT; ++k) acc0[k] = acc1[k] = 0.0;
     for (long long i = gtid; i < n; i += gthreads) {
         const double d = 1.0 / S.diag[i];
 #pragma unroll
-        for (int k = 0; k < PM_KMAX; ++k)
+        for (int k = 0; k < KT; ++k)
             if (k < K) {
                 const double bv = S.b[i * K + k];
                 S.x[i * K + k] = 0.0; S.r[i * K + k] = bv; S.p[i * K + k] = d * bv;
@@ -70,20 +74,20 @@ tc_pcg_multi_kernel(TcPcgMulti S) {
             }
     }
 #pragma unroll
-    for (int k = 0; k < PM_KMAX; ++k)
+    for (int k = 0; k < KT; ++k)
         if (k < K) {                                   // uniform over the grid
             const double s0 = block_sum(acc0[k], sh);
             const double s1 = block_sum(acc1[k], sh);
             if (tid == 0) { bank0[(size_t)k * TC_MAX_PARTIALS + blockIdx.x] = s0; bank1[(size_t)k * TC_MAX_PARTIALS + blockIdx.x] = s1; }
         }
     grid.sync();
-    double rho[PM_KMAX], tol2[PM_KMAX];
-    bool active[PM_KMAX];
-    pm_bank_sums(bank0, G, K, sh, bc, rho);
-    pm_bank_sums(bank1, G, K, sh, bc, tol2);
+    double rho[KT], tol2[KT];
+    bool active[KT];
+    pm_bank_sums<KT>(bank0, G, K, sh, bc, rho);
+    pm_bank_sums<KT>(bank1, G, K, sh, bc, tol2);
     int n_active = 0;
 #pragma unroll
-    for (int k = 0; k < PM_KMAX; ++k) {
+    for (int k = 0; k < KT; ++k) {
         if (k < K) { active[k] = tol2[k] > 0.0; tol2[k] *= S.rtol * S.rtol; n_active += active[k]; }
         else active[k] = false;
     }
@@ -93,38 +97,38 @@ tc_pcg_multi_kernel(TcPcgMulti S) {
     while (n_active > 0 && it < S.maxit) {
         // q = A p (one warp per 32-row slice), partial p.q
 #pragma unroll
-        for (int k = 0; k < PM_KMAX; ++k) acc0[k] = 0.0;
+        for (int k = 0; k < KT; ++k) acc0[k] = 0.0;
         for (int sl = blockIdx.x * warps + (tid >> 5); sl < S.nslices; sl += G * warps) {
             const long long base = S.slice_ptr[sl];
             const int width = (int)((S.slice_ptr[sl + 1] - base) >> 5);
             const long long row = (long long)sl * 32 + lane;
-            double sum[PM_KMAX];
+            double sum[KT];
 #pragma unroll
-            for (int k = 0; k < PM_KMAX; ++k) sum[k] = 0.0;
+            for (int k = 0; k < KT; ++k) sum[k] = 0.0;
             for (int j = 0; j < width; ++j) {
                 const double v = ld_stream_f64(S.val + base + 32LL * j + lane);
                 const long long c = ld_stream_s32(S.col + base + 32LL * j + lane);
 #pragma unroll
-                for (int k = 0; k < PM_KMAX; ++k)
+                for (int k = 0; k < KT; ++k)
                     if (k < K) sum[k] += v * S.p[c * K + k];
             }
             if (row < n) {
 #pragma unroll
-                for (int k = 0; k < PM_KMAX; ++k)
+                for (int k = 0; k < KT; ++k)
                     if (k < K) { S.q[row * K + k] = sum[k]; acc0[k] += S.p[row * K + k] * sum[k]; }
             }
         }
 #pragma unroll
-        for (int k = 0; k < PM_KMAX; ++k)
+        for (int k = 0; k < KT; ++k)
             if (k < K) {
                 const double s0 = block_sum(acc0[k], sh);
                 if (tid == 0) bank0[(size_t)k * TC_MAX_PARTIALS + blockIdx.x] = s0;
             }
         grid.sync();
-        double alpha[PM_KMAX];
-        pm_bank_sums(bank0, G, K, sh, bc, alpha);
+        double alpha[KT];
+        pm_bank_sums<KT>(bank0, G, K, sh, bc, alpha);
 #pragma unroll
-        for (int k = 0; k < PM_KMAX; ++k) {
+        for (int k = 0; k < KT; ++k) {
             alpha[k] = (k < K && active[k]) ? rho[k] / alpha[k] : 0.0;
             acc0[k] = acc1[k] = 0.0;
         }
@@ -132,7 +136,7 @@ tc_pcg_multi_kernel(TcPcgMulti S) {
         for (long long i = gtid; i < n; i += gthreads) {
             const double d = 1.0 / S.diag[i];
 #pragma unroll
-            for (int k = 0; k < PM_KMAX; ++k)
+            for (int k = 0; k < KT; ++k)
                 if (k < K) {
                     const size_t e = (size_t)i * K + k;
                     S.x[e] += alpha[k] * S.p[e];
@@ -142,20 +146,20 @@ tc_pcg_multi_kernel(TcPcgMulti S) {
                 }
         }
 #pragma unroll
-        for (int k = 0; k < PM_KMAX; ++k)
+        for (int k = 0; k < KT; ++k)
             if (k < K) {
                 const double s0 = block_sum(acc0[k], sh);
                 const double s1 = block_sum(acc1[k], sh);
                 if (tid == 0) { bank1[(size_t)k * TC_MAX_PARTIALS + blockIdx.x] = s0; bank2[(size_t)k * TC_MAX_PARTIALS + blockIdx.x] = s1; }
             }
         grid.sync();
-        double rho_new[PM_KMAX], rr[PM_KMAX], beta[PM_KMAX];
-        pm_bank_sums(bank1, G, K, sh, bc, rho_new);
-        pm_bank_sums(bank2, G, K, sh, bc, rr);
+        double rho_new[KT], rr[KT], beta[KT];
+        pm_bank_sums<KT>(bank1, G, K, sh, bc, rho_new);
+        pm_bank_sums<KT>(bank2, G, K, sh, bc, rr);
         ++it;
         n_active = 0;
 #pragma unroll
-        for (int k = 0; k < PM_KMAX; ++k) {
+        for (int k = 0; k < KT; ++k) {
             beta[k] = 0.0;
             if (k < K && active[k]) {
                 if (!(rr[k] > tol2[k])) {
@@ -172,7 +176,7 @@ tc_pcg_multi_kernel(TcPcgMulti S) {
         for (long long i = gtid; i < n; i += gthreads) {
             const double d = 1.0 / S.diag[i];
 #pragma unroll
-            for (int k = 0; k < PM_KMAX; ++k)
+            for (int k = 0; k < KT; ++k)
                 if (k < K && active[k]) {
                     const size_t e = (size_t)i * K + k;
                     S.p[e] = d * S.r[e] + beta[k] * S.p[e];
@@ -182,7 +186,7 @@ tc_pcg_multi_kernel(TcPcgMulti S) {
     }
     if (blockIdx.x == 0 && tid == 0) {
 #pragma unroll
-        for (int k = 0; k < PM_KMAX; ++k)
+        for (int k = 0; k < KT; ++k)
             if (k < K && active[k]) S.iters[k] = S.maxit;
     }
 }
@@ -211,7 +215,18 @@ extern "C" int tc_pcg_solve_multi(void* cuda_stream, int32_t n, int32_t nslices,
     int dev = 0, sms = 148, per_sm = 0;
     TC_CUDA(cudaGetDevice(&dev));
     TC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc_pcg_multi_kernel, PM_THREADS, 0));
+    const void* fn = nullptr;
+    switch (K) {
+        case 1: fn = (const void*)tc_pcg_multi_kernel<1>; break;
+        case 2: fn = (const void*)tc_pcg_multi_kernel<2>; break;
+        case 3: fn = (const void*)tc_pcg_multi_kernel<3>; break;
+        case 4: fn = (const void*)tc_pcg_multi_kernel<4>; break;
+        case 5: fn = (const void*)tc_pcg_multi_kernel<5>; break;
+        case 6: fn = (const void*)tc_pcg_multi_kernel<6>; break;
+        case 7: fn = (const void*)tc_pcg_multi_kernel<7>; break;
+        default: fn = (const void*)tc_pcg_multi_kernel<8>; break;
+    }
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PM_THREADS, 0));
     TC_CHECK(per_sm > 0, "kernel does not fit an SM");
     int g = sms * per_sm;
     const int need = (nslices + PM_THREADS / 32 - 1) / (PM_THREADS / 32);
@@ -219,7 +234,6 @@ extern "C" int tc_pcg_solve_multi(void* cuda_stream, int32_t n, int32_t nslices,
     if (g > TC_MAX_PARTIALS) g = TC_MAX_PARTIALS;
     if (g < 1) g = 1;
     void* args[] = {(void*)&S};
-    TC_CUDA(cudaLaunchCooperativeKernel((void*)tc_pcg_multi_kernel, dim3(g), dim3(PM_THREADS), args, 0,
-                                        (cudaStream_t)cuda_stream));
+    TC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(g), dim3(PM_THREADS), args, 0, (cudaStream_t)cuda_stream));
     return 0;
 }

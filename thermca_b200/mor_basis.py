@@ -41,8 +41,11 @@ def _arnoldi_device(op, Bs, dim, pcg_rtol, work, h2):
         _cabi.check(lib.tc_krylov_normalize(stream, n, _p(v), _p(h2), _p(Qs[s][0])))
     for k in range(dim - 1):
         idx = [s for s in range(S) if alive[s]]
-        for lo in range(0, len(idx), 8):
-            grp = idx[lo: lo + 8]
+        # measured on B200 (scripts/pcg_multi_bandwidth.py): up to 6 right-hand sides per launch cost ~45 us per
+        # right-hand side and sweep at 1 M DOF, 8 cost 64 us (register-limited occupancy) -> groups of <= 6, else <= 4
+        step = len(idx) if len(idx) <= 6 else 4
+        for lo in range(0, len(idx), max(step, 1)):
+            grp = idx[lo: lo + step]
             V = op.solve_multi(torch.stack([Qs[s][k] for s in grp]), pcg_rtol)
             for j, s in enumerate(grp):
                 v = V[j].contiguous()
