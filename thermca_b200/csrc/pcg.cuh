@@ -38,6 +38,49 @@ struct TcPcg {
 
 #define TC_PCG_THREADS 256
 
+// Two banks at once (rho and r.r after the update phase): the loads of both are in flight together and the two
+// block reductions share their barriers.  Same per-thread and per-block summation order as tc_bank_sum.
+__device__ __forceinline__ void tc_bank_sum2(const double* bank_a, const double* bank_b, int G, double* sh,
+                                             double& out_a, double& out_b) {
+    __shared__ double sh_b[32];
+    __shared__ double bcast2[2];
+    double va = 0.0, vb = 0.0;
+    for (int i0 = threadIdx.x; i0 < G; i0 += 4 * blockDim.x) {
+        double ba[4], bb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * blockDim.x;
+            ba[k] = i < G ? __ldcg(bank_a + i) : 0.0;
+            bb[k] = i < G ? __ldcg(bank_b + i) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k * (int)blockDim.x < G) { va += ba[k]; vb += bb[k]; }
+    }
+    va = warp_sum(va); vb = warp_sum(vb);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sh[w] = va; sh_b[w] = vb; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        double ra = lane < nw ? sh[lane] : 0.0, rb = lane < nw ? sh_b[lane] : 0.0;
+        ra = warp_sum(ra); rb = warp_sum(rb);
+        if (lane == 0) { bcast2[0] = ra; bcast2[1] = rb; }
+    }
+    __syncthreads();
+    out_a = bcast2[0]; out_b = bcast2[1];
+    __syncthreads();
+}
+
+__device__ __forceinline__ double tc_bank_sum_seq(const double* bank, int G, double* sh) {
+    __shared__ double bcast_s;
+    const double s = ordered_partial_sum_seq(bank, G, sh);
+    __syncthreads();
+    if (threadIdx.x == 0) bcast_s = s;
+    __syncthreads();
+    return bcast_s;
+}
 __device__ __forceinline__ double tc_bank_sum(const double* bank, int G, double* sh) {
     __shared__ double bcast;
     const double s = ordered_partial_sum(bank, G, sh);
@@ -99,7 +142,9 @@ __device__ __forceinline__ unsigned long long tc_gtime() {
 
 // MB = resident blocks per SM the register allocation is tuned for (occupancy matters: the kernel
 // is latency/bandwidth bound; measured on B200, see profiles/).
-template <int MB>
+// SMALL: instantiation for systems below ~4 M rows, where the reductions are a visible share of an iteration:
+// batched partial loads and the fused two-bank sum (identical summation order, identical results).
+template <int MB, bool SMALL = false>
 __global__ void __launch_bounds__(TC_PCG_THREADS, MB)
 tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;       // uniform over the grid
@@ -111,8 +156,8 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     unsigned long long prof_t = (S.prof && blockIdx.x == 0 && threadIdx.x == 0) ? tc_gtime() : 0ULL;
     tc_pcg_init_phase(S, shift, sh);
     grid.sync();
-    double rho = tc_bank_sum(S.partial, G, sh);
-    const double bb = tc_bank_sum(S.partial + TC_MAX_PARTIALS, G, sh);
+    double rho = tc_bank_sum_seq(S.partial, G, sh);
+    const double bb = tc_bank_sum_seq(S.partial + TC_MAX_PARTIALS, G, sh);
     const double tol2 = S.rtol * S.rtol * bb;
     int it = 0;
     if (bb > 0.0) {
@@ -124,15 +169,20 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
             if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
             grid.sync();
             PCG_PROF(2);
-            const double pq = tc_bank_sum(S.partial, G, sh);
+            const double pq = SMALL ? tc_bank_sum(S.partial, G, sh) : tc_bank_sum_seq(S.partial, G, sh);
             const double alpha = rho / pq;
             PCG_PROF(3);
             tc_pcg_update_phase(S, alpha, sh);
             PCG_PROF(4);
             grid.sync();
             PCG_PROF(5);
-            const double rho_new = tc_bank_sum(S.partial + 2 * TC_MAX_PARTIALS, G, sh);
-            const double rr = tc_bank_sum(S.partial + 3 * TC_MAX_PARTIALS, G, sh);
+            double rho_new, rr;
+            if (SMALL) {
+                tc_bank_sum2(S.partial + 2 * TC_MAX_PARTIALS, S.partial + 3 * TC_MAX_PARTIALS, G, sh, rho_new, rr);
+            } else {
+                rho_new = tc_bank_sum_seq(S.partial + 2 * TC_MAX_PARTIALS, G, sh);
+                rr = tc_bank_sum_seq(S.partial + 3 * TC_MAX_PARTIALS, G, sh);
+            }
             ++it;
             PCG_PROF(6);
             if (!(rr > tol2)) break;           // uniform: every block holds the same rr

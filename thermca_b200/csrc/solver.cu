@@ -757,11 +757,13 @@ static int pcg_occ_variant() {
     }
     return v;
 }
-static void* pcg_coop_fn() {
+#define TC_PCG_SMALL_ROWS 4000000
+static void* pcg_coop_fn(long long n_rows = -1) {
+    const bool small_sys = n_rows >= 0 && n_rows < TC_PCG_SMALL_ROWS;
     switch (pcg_occ_variant()) {
         case 5: return (void*)tc_pcg_coop_kernel<5>;
         case 6: return (void*)tc_pcg_coop_kernel<6>;
-        default: return (void*)tc_pcg_coop_kernel<8>;
+        default: return small_sys ? (void*)tc_pcg_coop_kernel<8, true> : (void*)tc_pcg_coop_kernel<8>;
     }
 }
 static int pcg_coop_grid(int sm_count) {
@@ -789,7 +791,7 @@ static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int
             TC_CUDA(cudaEventCreate(&e0)); TC_CUDA(cudaEventCreate(&e1));
             TC_CUDA(cudaEventRecord(e0, st));
         }
-        TC_CUDA(cudaLaunchCooperativeKernel(pcg_coop_fn(), dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
+        TC_CUDA(cudaLaunchCooperativeKernel(pcg_coop_fn(P.A.n), dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
         if (e0) { TC_CUDA(cudaEventRecord(e1, st)); s->ev.push_back(e0); s->ev.push_back(e1); }
         if (s) s->launches += 1;
         return 0;
