@@ -431,3 +431,31 @@ def test_ros2_agrees_with_tight_rk45_on_every_model_family(torch_cuda, golden, n
     if tight["io_temps"].shape[1]:
         scale = np.abs(tight["io_temps"][-1]).max()
         assert np.abs(out["io_temps"][-1] - tight["io_temps"][-1]).max() < 5e-4 * scale
+
+
+@pytest.mark.parametrize("name,t1,bound", [("coffeecup", 100.0, 2.0), ("coffeecup", 100.0, 0.0), ("plate_ffe", 30.0, 0.0),
+                                           ("plate_mor", 100.0, 0.0), ("assembly", 30.0, 2.0), ("assembly", 30.0, 0.0),
+                                           ("plate_ffe_var", 20.0, 0.0), ("tdep_rod", 0.5, 2.0), ("lp_tdep", 0.5, 0.0)])
+def test_ros2_matches_cpu_restatement(torch_cuda, golden, name, t1, bound):
+    """The adaptive ROS2 W-method on the device against its CPU restatement (oracle/ros2_oracle.py: same stages, block
+    structure, explicit/implicit switch and controller, direct solves instead of PCG): identical accept/reject
+    sequence, temperatures to solver tolerance.  bound = 0 forces every block onto its implicit branch."""
+    from thermca_b200.device import DeviceSolver
+    from ros2_oracle import ros2_integrate
+    spec, ex = golden(name)
+    t0 = float(ex["sim"]["t0"])
+    ref = ros2_integrate(spec, t0, t1, 1e-4, 1e-7, bound=bound)
+    os.environ["TC_W_EXPLICIT_BOUND"] = repr(bound)
+    try:
+        dev = DeviceSolver(spec)
+        out = dev.run_ros2(t0, t1, rtol=1e-4, atol=1e-7, pcg_rtol=1e-13, pcg_maxit=5000)
+        dev.close()
+    finally:
+        del os.environ["TC_W_EXPLICIT_BOUND"]
+    assert (out["accepted"], out["rejected"]) == (ref["accepted"], ref["rejected"])
+    assert np.allclose(out["times"], ref["times"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(out["net_temps"], ref["net_temps"], rtol=1e-7, atol=1e-9)
+    if ref["io_temps"].shape[1]:
+        assert np.abs(out["io_temps"] - ref["io_temps"]).max() <= 1e-7 * np.abs(ref["io_temps"]).max()
+    if bound == 0.0 and (spec["lp"] or spec["ffe"]):
+        assert out["pcg"]["solves"] > 0

@@ -207,7 +207,7 @@ __global__ void tc_accept_kernel(long long n, long long u, double* __restrict__ 
 }
 // network snapshot + flag finalisation (single block)
 __global__ void tc_snapshot_kernel(TcNetParams P, const double* __restrict__ ctrl, int* fl,
-                                   double* __restrict__ hist_net) {
+                                   double* __restrict__ hist_net, const double* __restrict__ y = nullptr) {
     if (fl[FL_DONE] == 1) return;
     if (fl[FL_ACC_THIS]) {
         const int slot = fl[FL_STORE_SLOT];
@@ -217,7 +217,8 @@ __global__ void tc_snapshot_kernel(TcNetParams P, const double* __restrict__ ctr
             const double* D = P.darena;
             if (threadIdx.x == 0) row[0] = ctrl[CT_T];
             for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
-                row[1 + i] = D[P.o_T + i];
+                // unknown nodes: the accepted state itself (temp_u[:] = solve_temp[:u], thermca/solver.py:314)
+                row[1 + i] = (y && i < P.u) ? y[i] : D[P.o_T + i];
                 row[1 + P.N + i] = D[P.o_capy + i];
                 row[1 + 2 * P.N + i] = D[P.o_heat + i];
             }
@@ -1098,6 +1099,7 @@ extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, 
     s->evals_per_attempt = 2;
     s->nfev_base = 1;
     if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
+    tc_copy_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->n_state, s->K[0], s->K[5], nullptr);   // "previous f(t+h, y+)"
     if (store_initial(s)) return -1;
     double h0 = first_step;
     if (!(h0 > 0)) h0 = 1e-3 * fabs(t_end - t0);
@@ -1113,13 +1115,22 @@ extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, 
 // One ROS2 attempt (Verwer et al. 1999): gamma = 1 + 1/sqrt(2), W-method with J ~ -blockdiag(A_p)
 //   (I + g h A) k1 = f(t, y);  (I + g h A) k2 = f(t + h, y + h k1) - 2 k1
 //   y+ = y + 1.5 h k1 + 0.5 h k2;  err = y+ - (y + h k1) = 0.5 h (k1 + k2)
+// f(t, y) of an attempt is the f(t + h, y+) the previous accepted attempt evaluated last (kept in K[5]); after a
+// rejection y is unchanged and K[0] still holds it
+__global__ void tc_ros2_reuse_kernel(long long n, const double* __restrict__ fend, double* __restrict__ f1,
+                                     const int* __restrict__ fl) {
+    if (fl[FL_DONE] == 1 || !fl[FL_ACC_LAST]) return;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        f1[i] = fend[i];
+}
+
 static int enqueue_ros2_attempt(tc_solver* s) {
     cudaStream_t st = s->stream;
     const int* done = s->flags + FL_DONE;
     const long long n = s->n_state;
     const int G = s->vec_grid;
+    tc_ros2_reuse_kernel<<<G, 256, 0, st>>>(n, s->K[5], s->K[0], s->flags);        // before prepare clears nothing it needs
     tc_prepare_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
-    if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
     if (enqueue_block_solve(s, s->ros_gamma, s->K[0], s->K[1], true)) return -1;    // k1
     TcLin L1{};
     L1.nk = 1; L1.k[0] = s->K[1]; L1.c[0] = 1.0;
@@ -1130,12 +1141,15 @@ static int enqueue_ros2_attempt(tc_solver* s) {
     TcLin L2{};
     L2.nk = 2; L2.k[0] = s->K[1]; L2.c[0] = 1.5; L2.k[1] = s->K[4]; L2.c[1] = 0.5;
     tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L2, s->ctrl, s->ynew, done);
+    // f(t + h, y+): next attempt's f(t, y) if this one is accepted, and the network state the snapshot stores
+    // (surface means, conductances, sources at the new state - as after the FSAL stage of the explicit pairs)
+    if (enqueue_rhs(s, 1.0, s->ynew, s->K[5])) return -1;
     TcLin Le{};
     Le.nk = 2; Le.k[0] = s->K[1]; Le.c[0] = 0.5; Le.k[1] = s->K[4]; Le.c[1] = 0.5;
     tc_error_control_kernel<<<G, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
     tc_accept_kernel<<<G, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, nullptr, nullptr, s->flags, s->hist_io, s->probe_idx,
                                         s->n_probe);
-    tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net);
+    tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net, s->y);
     return 0;
 }
 
