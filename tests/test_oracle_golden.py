@@ -89,3 +89,19 @@ def test_theta_oracle_backends_agree():
     assert it_np == it_c
     assert np.allclose(y_np, y_c, rtol=1e-13)
     assert np.allclose(y_np, y_d, rtol=1e-10)
+
+
+def test_ros2_restatement_converges_to_the_explicit_solution(golden):
+    """oracle/ros2_oracle.py (the CPU restatement the device's implicit path is checked against): second-order
+    convergence towards a tight RK45 run of the same lowered network, on both branches of the block switch."""
+    from ros2_oracle import ros2_integrate
+    from rhs_oracle import integrate
+    spec, ex = golden("plate_ffe_var")
+    tight = integrate(spec, [0.0, 20.0], 1e-10, 1e-12, "RK45")
+    for bound in (2.0, 0.0):
+        errs = []
+        for rtol in (1e-3, 1e-5):
+            out = ros2_integrate(spec, 0.0, 20.0, rtol, rtol * 1e-3, bound=bound)
+            errs.append(np.abs(out["net_temps"][-1] - tight["net_temps"][-1]).max())
+            assert bound != 0.0 or out["solves"] > 0
+        assert errs[1] < 2e-4 and errs[1] < errs[0]
