@@ -138,7 +138,12 @@ enum { TC_PCG_COOP = 0, TC_PCG_MULTI = 1 };
 /* one fixed theta step of size h_step: (I + theta h A) d = h f(t + theta h, y); y += d */
 int tc_theta_steps(tc_handle h, int32_t nsteps, double theta, double h_step, double pcg_rtol,
                    int32_t pcg_maxit, int32_t pcg_mode);
-/* adaptive linearly implicit 2-stage Rosenbrock (ROS2) with embedded first-order estimate */
+/* Adaptive linearly implicit 2-stage Rosenbrock-W method (ROS2, gamma = 1 + 1/sqrt 2) with embedded first-order
+ * estimate and the RK step controller; serves the reference's `method='LSODA'` requests (thermca/solver.py:359-365).
+ * Block Jacobian: FE / LP parts by Jacobi-PCG (temperature dependent FE bodies with their operator frozen at the
+ * initial temperatures), unknown network nodes and MOR blocks by small CG solves; every block is left explicit for
+ * an attempt while gamma*h*(Gershgorin bound of its operator) < 2 (env TC_W_EXPLICIT_BOUND overrides).  CPU
+ * restatement: oracle/ros2_oracle.py. */
 int tc_ros2_begin(tc_handle h, double t0, double t_end, double rtol, double atol, double max_step,
                   double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode);
 int tc_ros2_advance(tc_handle h, int32_t max_attempts, int32_t poll_every);
