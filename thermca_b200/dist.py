@@ -10,7 +10,6 @@ the single-GPU path on rows [row_begin, row_end).
 from __future__ import annotations
 
 import ctypes as C
-import json
 import os
 
 import numpy as np
