@@ -86,14 +86,6 @@ __device__ __forceinline__ bool last_block_arrives(unsigned int* counter) {
     if (is_last) __threadfence();
     return is_last;
 }
-// Ordered sum of n partials by one block with one load in flight at a time (volatile); kept for the large-system
-// instantiation of the PCG kernel, whose code generation is better with it (A/B on the same B200, 10.35 M DOF:
-// 411.4 vs 409.0 M DOF*steps/s), while the batched form below wins below ~4 M DOF (1.06 M: 699 -> 734 M).
-__device__ __forceinline__ double ordered_partial_sum_seq(const volatile double* part, int n, double* sh) {
-    double v = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
-    return block_sum(v, sh);
-}
 // Ordered sum of n partials by one block; result valid in thread 0.  The partials were written by other blocks
 // and made visible by a grid barrier / last-block fence, so they are read from L2 (ld.global.cg); four loads are
 // in flight at a time (a chain of dependent volatile loads cost ~0.6 us each), the additions keep the index order.

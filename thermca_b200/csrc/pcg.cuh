@@ -7,15 +7,17 @@
 // reference's operators; its CPU restatement is oracle/theta_oracle.py.
 //
 // Two drivers over the same phases:
-//   * tc_pcg_coop_kernel  - ONE cooperative persistent launch per solve, grid.sync()
-//     between phases, convergence loop on the device (no host round trip);
+//   * tc_pcg_coop_kernel  - ONE cooperative persistent launch per solve, reduce-barriers
+//     (gridbar.cuh) between phases, convergence loop on the device (no host round trip);
 //   * tc_pcg_k1/k2/k3     - one launch per phase, used when cooperative launch is not
 //     available and for cross-checking.
-// Dot products: per-block partial (fixed shuffle tree) -> every block sums the G partials
-// in index order, so all blocks see the same scalar and results are run-to-run identical.
+// Dot products: per-block partial (fixed shuffle tree) -> the last block to reach the barrier sums
+// the G partials in index order and publishes the total, so all blocks see the same scalar and
+// results are run-to-run identical.
 #pragma once
 #include <cooperative_groups.h>
 #include "parts.cuh"
+#include "gridbar.cuh"
 namespace cg = cooperative_groups;
 
 struct TcPcg {
@@ -27,60 +29,19 @@ struct TcPcg {
     double *r, *p, *q, *dinv;
     double* partial;        // 4 banks of TC_MAX_PARTIALS
     double* sc;             // [0],[1] rho (parity), [2] tol2, [3] bnorm2, [4] rr
-    int* isc;               // [0] pcg_done, [1] iterations of this solve, [2] total iterations, [3] solves
+    int* isc;               // [0] pcg_done, [1] iterations of this solve, [2] total iterations, [3] solves,
+                            // [4] status of the last failed solve (1 iteration limit, 2 breakdown), [5] failed solves
     double rtol;
     int maxit;
     const double* ctrl;     // shift = coef * ctrl[1]
     double coef;
     unsigned long long* prof;   // optional [16] phase times (ns) of block 0
     const int* skip;            // optional: non-zero -> leave x untouched (block is explicit this attempt)
+    TcGridBar bar;              // reduce-barrier state of the cooperative kernel (gridbar.cuh)
 };
 
 #define TC_PCG_THREADS 256
 
-// Two banks at once (rho and r.r after the update phase): the loads of both are in flight together and the two
-// block reductions share their barriers.  Same per-thread and per-block summation order as tc_bank_sum.
-__device__ __forceinline__ void tc_bank_sum2(const double* bank_a, const double* bank_b, int G, double* sh,
-                                             double& out_a, double& out_b) {
-    __shared__ double sh_b[32];
-    __shared__ double bcast2[2];
-    double va = 0.0, vb = 0.0;
-    for (int i0 = threadIdx.x; i0 < G; i0 += 4 * blockDim.x) {
-        double ba[4], bb[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = i0 + k * blockDim.x;
-            ba[k] = i < G ? __ldcg(bank_a + i) : 0.0;
-            bb[k] = i < G ? __ldcg(bank_b + i) : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (i0 + k * (int)blockDim.x < G) { va += ba[k]; vb += bb[k]; }
-    }
-    va = warp_sum(va); vb = warp_sum(vb);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) { sh[w] = va; sh_b[w] = vb; }
-    __syncthreads();
-    if (w == 0) {
-        const int nw = (blockDim.x + 31) >> 5;
-        double ra = lane < nw ? sh[lane] : 0.0, rb = lane < nw ? sh_b[lane] : 0.0;
-        ra = warp_sum(ra); rb = warp_sum(rb);
-        if (lane == 0) { bcast2[0] = ra; bcast2[1] = rb; }
-    }
-    __syncthreads();
-    out_a = bcast2[0]; out_b = bcast2[1];
-    __syncthreads();
-}
-
-__device__ __forceinline__ double tc_bank_sum_seq(const double* bank, int G, double* sh) {
-    __shared__ double bcast_s;
-    const double s = ordered_partial_sum_seq(bank, G, sh);
-    __syncthreads();
-    if (threadIdx.x == 0) bcast_s = s;
-    __syncthreads();
-    return bcast_s;
-}
 __device__ __forceinline__ double tc_bank_sum(const double* bank, int G, double* sh) {
     __shared__ double bcast;
     const double s = ordered_partial_sum(bank, G, sh);
@@ -142,59 +103,82 @@ __device__ __forceinline__ unsigned long long tc_gtime() {
 
 // MB = resident blocks per SM the register allocation is tuned for (occupancy matters: the kernel
 // is latency/bandwidth bound; measured on B200, see profiles/).
-// SMALL: instantiation for systems below ~4 M rows, where the reductions are a visible share of an iteration:
-// batched partial loads and the fused two-bank sum (identical summation order, identical results).
-template <int MB, bool SMALL = false>
+// Every reduction is folded into its grid barrier (gridbar.cuh): three barriers per iteration, the first two
+// carry p.q and (r.z, r.r).  Summation order is fixed (block partial tree, then block-index order), so all
+// blocks hold bit-identical scalars and runs are reproducible.
+// Status (isc[4]): 0 converged, 1 iteration limit reached with r.r above the tolerance, 2 breakdown
+// (non-finite or non-positive p.q / r.r) — surfaced by tc_pcg_stats, checked by the host drivers.
+template <int MB>
 __global__ void __launch_bounds__(TC_PCG_THREADS, MB)
 tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;       // uniform over the grid
     if (S.skip && *S.skip) return;             // uniform over the grid
-    cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
-    const int G = gridDim.x;
+    unsigned int gen = *((volatile unsigned int*)(S.bar.ctr + 32));
     const double shift = S.coef * S.ctrl[1];
     unsigned long long prof_t = (S.prof && blockIdx.x == 0 && threadIdx.x == 0) ? tc_gtime() : 0ULL;
-    tc_pcg_init_phase(S, shift, sh);
-    grid.sync();
-    double rho = tc_bank_sum_seq(S.partial, G, sh);
-    const double bb = tc_bank_sum_seq(S.partial + TC_MAX_PARTIALS, G, sh);
+    double red[2];
+    {
+        const int n = S.A.n;
+        double rho = 0.0, bb = 0.0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const double m = S.mass[i];
+            const double b = m * S.rhs[i];
+            const double d = 1.0 / (m * (1.0 + shift * S.adiag[i]));
+            const double z = d * b;
+            S.r[i] = b; S.x[i] = 0.0; S.dinv[i] = d; S.p[i] = z;
+            rho += b * z; bb += b * b;
+        }
+        red[0] = block_sum(rho, sh);
+        red[1] = block_sum(bb, sh);
+    }
+    tc_grid_reduce<2>(S.bar, gen, red, sh);
+    double rho = red[0];
+    const double bb = red[1];
     const double tol2 = S.rtol * S.rtol * bb;
-    int it = 0;
+    int it = 0, status = 0;
     if (bb > 0.0) {
+        status = 1;
         for (; it < S.maxit;) {
             PCG_PROF(0);
             const double dot = tc_sell_spmv_body<SPMV_SHIFT, 0>(S.A, S.p, S.q, nullptr, S.mass, shift);
             PCG_PROF(1);
-            const double bs = block_sum(dot, sh);
-            if (threadIdx.x == 0) S.partial[blockIdx.x] = bs;
-            grid.sync();
+            red[0] = block_sum(dot, sh);
+            tc_grid_reduce<1>(S.bar, gen, red, sh);
             PCG_PROF(2);
-            const double pq = SMALL ? tc_bank_sum(S.partial, G, sh) : tc_bank_sum_seq(S.partial, G, sh);
+            const double pq = red[0];
+            if (!(pq > 0.0) || !isfinite(pq)) { status = 2; break; }     // uniform: every block holds the same pq
             const double alpha = rho / pq;
-            PCG_PROF(3);
-            tc_pcg_update_phase(S, alpha, sh);
-            PCG_PROF(4);
-            grid.sync();
-            PCG_PROF(5);
-            double rho_new, rr;
-            if (SMALL) {
-                tc_bank_sum2(S.partial + 2 * TC_MAX_PARTIALS, S.partial + 3 * TC_MAX_PARTIALS, G, sh, rho_new, rr);
-            } else {
-                rho_new = tc_bank_sum_seq(S.partial + 2 * TC_MAX_PARTIALS, G, sh);
-                rr = tc_bank_sum_seq(S.partial + 3 * TC_MAX_PARTIALS, G, sh);
+            {
+                const int n = S.A.n;
+                double rn = 0.0, rr = 0.0;
+                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+                    const double pi = S.p[i];
+                    S.x[i] += alpha * pi;
+                    const double ri = S.r[i] - alpha * S.q[i];
+                    S.r[i] = ri;
+                    rn += ri * (S.dinv[i] * ri);
+                    rr += ri * ri;
+                }
+                red[0] = block_sum(rn, sh);
+                red[1] = block_sum(rr, sh);
             }
+            PCG_PROF(3);
+            tc_grid_reduce<2>(S.bar, gen, red, sh);
+            PCG_PROF(4);
+            const double rho_new = red[0], rr = red[1];
             ++it;
-            PCG_PROF(6);
-            if (!(rr > tol2)) break;           // uniform: every block holds the same rr
+            if (!(rr > tol2)) { status = isfinite(rr) ? 0 : 2; break; }   // uniform
             tc_pcg_dir_phase(S, rho_new / rho);
             rho = rho_new;
-            PCG_PROF(7);
-            grid.sync();
-            PCG_PROF(8);
+            PCG_PROF(5);
+            tc_grid_barrier(S.bar, gen, sh);
+            PCG_PROF(6);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         S.isc[1] = it; S.isc[2] += it; S.isc[3] += 1;
+        if (status) { S.isc[4] = status; S.isc[5] += 1; }
     }
 }
 

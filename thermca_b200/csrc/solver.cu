@@ -292,6 +292,7 @@ struct tc_solver {
     double* K[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* red_partial = nullptr;     // 4 banks
     double* pcg_sc = nullptr; int* pcg_isc = nullptr; unsigned long long* pcg_prof = nullptr;
+    TcGridBar bar{};                   // reduce-barrier state of the cooperative PCG kernel (gridbar.cuh)
     int* pin_flags = nullptr;          // pinned host mirror
     double* pin_ctrl = nullptr;
     // history
@@ -340,6 +341,11 @@ extern "C" int tc_create(tc_handle* out, void* cuda_stream) {
     TC_CUDA(cudaMemset(s->pcg_isc, 0, sizeof(int) * 16));
     TC_CUDA(cudaMalloc(&s->pcg_prof, sizeof(unsigned long long) * 16));
     TC_CUDA(cudaMemset(s->pcg_prof, 0, sizeof(unsigned long long) * 16));
+    TC_CUDA(cudaMalloc(&s->bar.ctr, sizeof(unsigned int) * 64));
+    TC_CUDA(cudaMemset(s->bar.ctr, 0, sizeof(unsigned int) * 64));
+    TC_CUDA(cudaMalloc(&s->bar.part, sizeof(double) * TC_BAR_MAXK * TC_MAX_PARTIALS));
+    TC_CUDA(cudaMalloc(&s->bar.res, sizeof(double) * 2 * TC_BAR_MAXK));
+    TC_CUDA(cudaMemset(s->bar.res, 0, sizeof(double) * 2 * TC_BAR_MAXK));
     TC_CUDA(cudaMallocHost(&s->pin_flags, sizeof(int) * 32));
     TC_CUDA(cudaMallocHost(&s->pin_ctrl, sizeof(double) * 32));
     *out = s;
@@ -350,7 +356,8 @@ extern "C" int tc_destroy(tc_handle s) {
     if (!s) return 0;
     if (s->rk_graph) cudaGraphExecDestroy(s->rk_graph);
     cudaFree(s->ctrl); cudaFree(s->flags); cudaFree(s->red_partial); cudaFree(s->pcg_sc);
-    cudaFree(s->pcg_isc); cudaFree(s->mean_partials);
+    cudaFree(s->pcg_isc); cudaFree(s->pcg_prof); cudaFree(s->mean_partials);
+    cudaFree(s->bar.ctr); cudaFree(s->bar.part); cudaFree(s->bar.res);
     cudaFree(s->y); cudaFree(s->ynew); cudaFree(s->ystage);
     for (int i = 0; i < 7; ++i) cudaFree(s->K[i]);
     cudaFree(s->net_vec); cudaFree(s->gate_flags); cudaFree(s->gate_partial); cudaFree(s->gate_counter);
@@ -758,13 +765,11 @@ static int pcg_occ_variant() {
     }
     return v;
 }
-#define TC_PCG_SMALL_ROWS 4000000
-static void* pcg_coop_fn(long long n_rows = -1) {
-    const bool small_sys = n_rows >= 0 && n_rows < TC_PCG_SMALL_ROWS;
+static void* pcg_coop_fn() {
     switch (pcg_occ_variant()) {
         case 5: return (void*)tc_pcg_coop_kernel<5>;
         case 6: return (void*)tc_pcg_coop_kernel<6>;
-        default: return small_sys ? (void*)tc_pcg_coop_kernel<8, true> : (void*)tc_pcg_coop_kernel<8>;
+        default: return (void*)tc_pcg_coop_kernel<8>;
     }
 }
 static int pcg_coop_grid(int sm_count) {
@@ -792,7 +797,7 @@ static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int
             TC_CUDA(cudaEventCreate(&e0)); TC_CUDA(cudaEventCreate(&e1));
             TC_CUDA(cudaEventRecord(e0, st));
         }
-        TC_CUDA(cudaLaunchCooperativeKernel(pcg_coop_fn(P.A.n), dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
+        TC_CUDA(cudaLaunchCooperativeKernel(pcg_coop_fn(), dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
         if (e0) { TC_CUDA(cudaEventRecord(e1, st)); s->ev.push_back(e0); s->ev.push_back(e1); }
         if (s) s->launches += 1;
         return 0;
@@ -1040,6 +1045,7 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         P.rtol = s->pcg_rtol; P.maxit = s->pcg_maxit; P.ctrl = s->ctrl; P.coef = coef;
         P.prof = nullptr;
         P.skip = nullptr;
+        P.bar = s->bar;
         if (w_method && s->pcg_mode == TC_PCG_COOP) {
             int* flag = s->gate_flags + gate_ix++;
             tc_pcg_gate_kernel<<<grid_for(p.d.n, 256, 256), 256, 0, st>>>(p.d.n, P.adiag, s->ctrl, coef, s->w_bound,
@@ -1059,6 +1065,7 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         P.rtol = s->pcg_rtol; P.maxit = s->pcg_maxit; P.ctrl = s->ctrl; P.coef = coef;
         P.prof = s->timing ? s->pcg_prof : nullptr;
         P.skip = nullptr;
+        P.bar = s->bar;
         if (w_method && s->pcg_mode == TC_PCG_COOP) {
             int* flag = s->gate_flags + gate_ix++;
             tc_pcg_gate_kernel<<<grid_for(p.d.n, 256, 256), 256, 0, st>>>(p.d.n, P.adiag, s->ctrl, coef, s->w_bound,
@@ -1205,6 +1212,17 @@ extern "C" int tc_pcg_stats(tc_handle s, int64_t* stats4) {
     return 0;
 }
 
+// status2: [0] status of the last failed PCG solve (0 none, 1 iteration limit reached above the tolerance,
+// 2 breakdown: non-finite or non-positive curvature), [1] number of failed solves; cleared on read
+extern "C" int tc_pcg_status(tc_handle s, int64_t* status2) {
+    int isc[8];
+    TC_CUDA(cudaMemcpyAsync(isc, s->pcg_isc, sizeof isc, cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    status2[0] = isc[4]; status2[1] = isc[5];
+    TC_CUDA(cudaMemsetAsync(s->pcg_isc + 4, 0, 2 * sizeof(int), s->stream));
+    return 0;
+}
+
 // ---- stand-alone entry points --------------------------------------------------------------------
 // One traced link program evaluated for m argument pairs (parity hook for the interpreter of vm.cuh)
 __global__ void tc_vm_eval_kernel(const int* __restrict__ code, int n_instr, int result, const double* __restrict__ consts,
@@ -1272,6 +1290,41 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     tmp.stream = (cudaStream_t)cuda_stream;
     TcPcg P{};
     P.A = TcSell{n, nslices, (const long long*)slice_ptr, col, val, nullptr};
+    // one scratch allocation: 4 vectors | partial banks + scalars + ctrl | barrier banks + totals | ints
+    const size_t n_aux = 4 * TC_MAX_PARTIALS + 20, n_bar = TC_BAR_MAXK * TC_MAX_PARTIALS + 2 * TC_BAR_MAXK;
+    const size_t n_dbl = 4 * (size_t)n + n_aux + n_bar;
+    char* blob = nullptr;
+    TC_CUDA(cudaMalloc(&blob, sizeof(double) * n_dbl + sizeof(int) * (16 + 64)));
+    TC_CUDA(cudaMemsetAsync(blob + sizeof(double) * 4 * (size_t)n, 0,
+                            sizeof(double) * (n_aux + n_bar) + sizeof(int) * (16 + 64), tmp.stream));
+    double* ws = (double*)blob;
+    double* aux = ws + 4 * (size_t)n;
+    P.bar.part = aux + n_aux; P.bar.res = P.bar.part + TC_BAR_MAXK * TC_MAX_PARTIALS;
+    int* isc = (int*)(blob + sizeof(double) * n_dbl);
+    P.bar.ctr = (unsigned int*)(isc + 16);
+    const double c[4] = {0.0, 1.0, 0.0, 0.0};
+        TC_CUDA(cudaMemcpy(one_ctrl, c, sizeof c, cudaMemcpyHostToDevice));
+        TC_CUDA(cudaMalloc(&scratch, sizeof(double) * 4 * TC_MAX_PARTIALS));
+    }
+    if (g > TC_MAX_PARTIALS) g = TC_MAX_PARTIALS;
+    if (mode == SPMV_NEG)
+        tc_sell_spmv_kernel<SPMV_NEG><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, nullptr, nullptr, one_ctrl, 0.0, nullptr, nullptr);
+    else if (mode == SPMV_B)
+        tc_sell_spmv_kernel<SPMV_B><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, b, nullptr, one_ctrl, 0.0, nullptr, nullptr);
+    else
+        tc_sell_spmv_kernel<SPMV_SHIFT><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, nullptr, mass, one_ctrl, shift, scratch, nullptr);
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
+                            const int64_t* slice_ptr, const int32_t* col, const double* val,
+                            const double* mass, const double* adiag, const double* rhs, double* x,
+                            double shift, double rtol, int32_t maxit, int32_t* iters) {
+    tc_solver tmp;
+    tmp.stream = (cudaStream_t)cuda_stream;
+    TcPcg P{};
+    P.A = TcSell{n, nslices, (const long long*)slice_ptr, col, val, nullptr};
     double* ws = nullptr; double* aux = nullptr; int* isc = nullptr;
     TC_CUDA(cudaMalloc(&ws, sizeof(double) * 4 * (size_t)n));
     TC_CUDA(cudaMalloc(&aux, sizeof(double) * (4 * TC_MAX_PARTIALS + 16 + 4)));
@@ -1280,7 +1333,8 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     TC_CUDA(cudaMemset(aux, 0, sizeof(double) * (4 * TC_MAX_PARTIALS + 20)));
     const double c[4] = {0.0, 1.0, 0.0, 0.0};
     double* ctrl = aux + 4 * TC_MAX_PARTIALS + 16;
-    TC_CUDA(cudaMemcpy(ctrl, c, sizeof c, cudaMemcpyHostToDevice));
+    TC_CUDA(cudaMemcpyAsync(ctrl, c, sizeof c, cudaMemcpyHostToDevice, tmp.stream));
+    TC_CUDA(cudaStreamSynchronize(tmp.stream));
     P.mass = mass; P.adiag = adiag; P.rhs = rhs; P.x = x;
     P.r = ws; P.p = ws + n; P.q = ws + 2 * (size_t)n; P.dinv = ws + 3 * (size_t)n;
     P.partial = aux; P.sc = aux + 4 * TC_MAX_PARTIALS; P.isc = isc;
@@ -1297,7 +1351,7 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     int h_isc[4] = {0, 0, 0, 0};
     if (rc == 0) cudaMemcpy(h_isc, isc, sizeof h_isc, cudaMemcpyDeviceToHost);
     if (iters) *iters = h_isc[1];
-    cudaFree(ws); cudaFree(aux); cudaFree(isc);
+    cudaFree(blob);
     tmp.pin_flags = nullptr;
     return rc;
 }
