@@ -116,6 +116,7 @@ int tc_rhs(tc_handle h, double t, const double* y_dev, double* ydot_dev);
 enum { TC_RK45 = 0, TC_RK23 = 1 };
 int tc_set_state(tc_handle h, const double* y_dev);
 int tc_get_state(tc_handle h, double* y_dev);
+int tc_get_state_async(tc_handle h, double* y_dev);   /* enqueue only (tc_set_state never blocks either) */
 /* history ring written on the device after accepted steps (store_results, solver.py:393-424):
  * hist_io[capacity][n_state - u], hist_net[capacity][1 + 3N + 2 nnz] = time | T | capy | heat | cond | clean */
 int tc_set_history(tc_handle h, double* hist_io_dev, double* hist_net_dev, int32_t capacity, int32_t num_skip);
@@ -154,6 +155,10 @@ int tc_timing(tc_handle h, int32_t enable, double* pcg_ms, int64_t* pcg_launches
 int tc_pcg_profile(tc_handle h, uint64_t* out16);   /* per-phase ns of block 0 while timing is on */
 /* PCG statistics of the implicit path: total iterations, solves, last iteration count */
 int tc_pcg_stats(tc_handle h, int64_t* stats4);
+/* status2[0]: status of the last FAILED PCG solve since the previous call (0 none, 1 iteration limit reached with
+ * the residual above the tolerance, 2 breakdown: non-finite / non-positive curvature); status2[1]: number of
+ * failed solves.  Cleared on read.  The host drivers raise on it (there is no silent degradation). */
+int tc_pcg_status(tc_handle h, int64_t* status2);
 
 /* ---- stand-alone kernels (parity hooks and micro-benchmarks) ----------------------------- */
 /* y = -A x (mode 0), y = b - A x (mode 1), y = mass*(x + shift*A x) (mode 2) on a SELL-32 operator */
@@ -173,21 +178,40 @@ int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, co
 
 /* ---- row-partitioned implicit step across GPUs (BASELINE config #5), csrc/dist.cu ------------
  * One process per GPU; the comm buffer of every rank is exported as a CUDA IPC handle and opened
- * by its peers; halos and the PCG scalar reductions then move by peer stores inside ONE
- * cooperative kernel per theta step (no NCCL call on the data path). */
+ * by its peers; ghost values and the PCG scalar reductions then move by peer stores inside ONE
+ * cooperative kernel per theta step (no NCCL call on the data path).  The reference has no
+ * multi-process code; per rank this is thermca/solver.py:265-281 (right-hand side
+ * of a full-order FE part) plus the implicit solve on the local rows.
+ * Vectors are "extended": [n_loc local rows | n_ghost ghost slots]; operator columns index that vector.
+ * Calls return 0, or a negative code with tc_last_error(): -3 = a wait on a peer timed out
+ * (TC_DIST_TIMEOUT_S seconds, default 20), -4 = PCG iteration limit / breakdown. */
 typedef struct tc_dist tc_dist;
-int tc_dist_create(tc_dist** out, void* cuda_stream, int32_t rank, int32_t world, int64_t n_loc,
-                   int64_t halo, int64_t row_begin);
+int tc_dist_create(tc_dist** out, void* cuda_stream, int32_t rank, int32_t world, int64_t n_loc, int64_t n_ghost);
 int tc_dist_ipc_handle(tc_dist* d, void* handle64);
-int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_n);
+/* handles: world x 64 bytes; peer_ext[w] = n_loc + n_ghost of rank w */
+int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_ext);
+/* halo plan (host arrays, copied): entry e sends local row send_row[e] to slot send_dst[e] of the extended
+ * vectors of rank send_peer[e]; nbr = ranks this rank trades ghosts with */
+int tc_dist_set_halo(tc_dist* d, int64_t n_send, const int32_t* send_row, const int32_t* send_peer,
+                     const int64_t* send_dst, int32_t n_nbr, const int32_t* nbr);
+/* SELL-32 operator of the local rows (device pointers, kept by reference); col16 (optional) = column - row of
+ * the interior slices; order (required when n_bnd > 0) = slice order with the n_bnd boundary slices last */
 int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
                          const int16_t* col16, const double* val, const double* mass, const double* adiag,
-                         const double* b);
+                         const double* b, int32_t n_bnd, const int32_t* order);
+int tc_dist_set_load(tc_dist* d, const double* b_local_dev);     /* swap the load vector (time-varying loads) */
 int tc_dist_set_state(tc_dist* d, const double* y_local_dev);
-int tc_dist_get_state(tc_dist* d, double* y_local_dev);
+int tc_dist_get_state(tc_dist* d, double* y_local_dev);          /* fails (-3/-4) if a step since the last reset failed */
+int tc_dist_copy_state_async(tc_dist* d, double* y_local_dev, int32_t dir);   /* enqueue only: 0 set, 1 get */
 int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, double h, double rtol, int32_t maxit);
-int tc_dist_stats(tc_dist* d, int64_t* stats4);
+int tc_dist_check(tc_dist* d);                                   /* synchronises; 0, -3 or -4 */
+int tc_dist_reset_error(tc_dist* d);
+/* iters_last, iters_total, comm error flag, solves + 1e6 * grid, failed solves */
+int tc_dist_stats(tc_dist* d, int64_t* stats5);
 int tc_dist_profile(tc_dist* d, uint64_t* out32);   /* per-phase wall time (ns) of block 0 / last block */
+/* teardown: tc_dist_close_peers on every rank, a host barrier, then tc_dist_destroy (CUDA IPC rule: the
+ * exporter must not free while an importer has the buffer mapped) */
+int tc_dist_close_peers(tc_dist* d);
 int tc_dist_destroy(tc_dist* d);
 
 /* ---- batched MOR ensemble (BASELINE config #3): B scenarios in lockstep, FP64 DMMA ------- */

@@ -1,43 +1,86 @@
-"""Multi-GPU check (torchrun, N >= 2): the fused peer-memory theta/PCG path on row slabs must
-reproduce the single-GPU path on the same global mesh."""
-import os, sys
+"""Multi-GPU check (torchrun, N >= 1): the fused peer-memory theta/PCG path on row blocks must reproduce the
+single-GPU path on the same global problem.  Two bodies:
+  * the synthetic Kuhn cuboid in y-slabs (rank +-1 neighbours),
+  * the same operator as a "real" body handed over as a host CSR in a scrambled DOF order: reverse
+    Cuthill-McKee reordering, even row blocks, general neighbour sets (DistBody.from_csr).
+Prints one line per rank and `dist_check ok`; `--json PATH` writes the numbers (kept under profiles/)."""
+import json
+import os
+import sys
+
 import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
 
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
-    from thermca_b200.dist import DistCuboid
+    from thermca_b200.dist import DistBody, DistCuboid
     from thermca_b200.device import DeviceSolver
-    from thermca_b200.workloads import device_cuboid_spec
+    from thermca_b200.workloads import device_cuboid_spec, sell_to_csr_host
+    steps, rtol = 4, 1e-12
     nx, ny, nz = 20, 16 * world - 1, 6
+    # ---- (a) cuboid slabs ------------------------------------------------------------------------
     dc = DistCuboid(nx, ny, nz)
-    dc.theta_steps(4, 1.0, 0.5, rtol=1e-12)
+    dc.theta_steps(steps, 1.0, 0.5, rtol=rtol, sync=True)
     st = dc.stats()
     y_loc = dc.get_state().cpu().numpy()
-    ok = True
-    # single-GPU reference of the same global problem on every rank (small)
-    ref = DeviceSolver(device_cuboid_spec(nx, ny, nz))
-    ref.theta_steps(4, 1.0, 0.5, t0=0.0, pcg_rtol=1e-12)
-    y_ref = ref.get_state()[dc.row_begin: dc.row_begin + dc.n]
+    spec = device_cuboid_spec(nx, ny, nz)
+    ref = DeviceSolver(spec)
+    ref.theta_steps(steps, 1.0, 0.5, t0=0.0, pcg_rtol=rtol)
+    y_full = ref.get_state()
     pst = ref.pcg_stats()
+    y_ref = y_full[dc.row_begin: dc.row_begin + dc.n]
+    err_a = float(np.max(np.abs(y_loc - y_ref) / np.abs(y_ref)))
+    e_d, n_d = dc.global_sums()
+    ok = err_a < 1e-9 and st["error"] == 0 and st["failed_solves"] == 0 and st["iters_total"] == pst["iterations"]
+    print(f"[cuboid] rank {rank}/{world}: rows [{dc.row_begin},{dc.row_begin + dc.n}) ghosts {dc.n_ghost} "
+          f"boundary slices {dc.n_bnd} neighbours {list(dc.plan[3])} iters {st['iters_total']} (single GPU "
+          f"{pst['iterations']}) max rel err {err_a:.3e}", flush=True)
+    # ---- (b) a body handed over as host CSR in a scrambled order -----------------------------------
+    op = spec["ffe"][0]["sell"]
+    A = sell_to_csr_host(op).tocsr()
+    n = A.shape[0]
+    mass = op["mass"].cpu().numpy()
+    part = spec["ffe"][0]
+    b = np.zeros(n)
+    flux = [1000.0 / part["surf_areas"][0], 10.0 * 20.0]
+    for s in range(2):
+        np.add.at(b, part["B_idx"][s], part["B_val"][s] * flux[s])
+    scr = np.random.default_rng(3).permutation(n)                    # the caller's DOF order
+    A_s = A[scr][:, scr].tocsr()
+    body = DistBody.from_csr(A_s, mass[scr], b[scr], init_temp=20.0)
+    body.theta_steps(steps, 1.0, 0.5, rtol=rtol, sync=True)
+    y_body = body.gather_state().cpu().numpy()                       # caller's order
+    err_b = float(np.max(np.abs(y_body - y_full[scr]) / np.abs(y_full[scr])))
+    stb = body.stats()
+    ok = ok and err_b < 1e-9 and stb["error"] == 0 and stb["failed_solves"] == 0
+    print(f"[csr body] rank {rank}/{world}: rows {body.n} ghosts {body.n_ghost} boundary slices {body.n_bnd} "
+          f"neighbours {list(body.plan[3])} iters {stb['iters_total']} max rel err {err_b:.3e}", flush=True)
     ref.close()
-    err = np.max(np.abs(y_loc - y_ref) / np.abs(y_ref))
-    print(f"rank {rank}/{world}: rows [{dc.row_begin},{dc.row_begin + dc.n}) halo {dc.halo} iters {st} ref {pst} "
-          f"max rel err {err:.3e} range [{y_loc.min():.6f},{y_loc.max():.6f}]", flush=True)
-    ok = ok and err < 1e-9 and st["error"] == 0
+    body.close()
     dc.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
+    errs = torch.tensor([err_a, err_b], dtype=torch.float64, device="cuda")
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     dist.destroy_process_group()
+    if rank == 0 and "--json" in sys.argv:
+        with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
+            json.dump({"world": world, "steps": steps, "pcg_rtol": rtol, "cuboid_cells": [nx, ny, nz],
+                       "max_rel_err_cuboid_slabs": float(errs[0]), "max_rel_err_csr_body_rcm": float(errs[1]),
+                       "iters_dist": st["iters_total"], "iters_single_gpu": pst["iterations"],
+                       "energy_sum_M_y": e_d, "ok": not bool(flag.item())}, f)
     if flag.item():
         sys.exit(1)
     if rank == 0:
         print("dist_check ok")
+
 
 if __name__ == "__main__":
     main()

@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from thermca_b200.dist import slab_partition, local_spmv_with_halo
+from thermca_b200.dist import (slab_partition, local_spmv_with_halo, even_row_bounds, ghost_columns, remap_columns,
+                               send_plan, emulate_push, csr_rows_to_sell)
 from thermca_b200.synth import cuboid_spec
 
 
@@ -105,3 +106,76 @@ def test_partitioned_spmv_and_pcg_world2(tmp_path):
     x = np.concatenate([np.load(tmp_path / "x0.npy"), np.load(tmp_path / "x1.npy")])
     b = np.concatenate([np.load(tmp_path / "b0.npy"), np.load(tmp_path / "b1.npy")])
     assert np.linalg.norm(mass * (x + 0.5 * (A @ x)) - b) < 1e-8 * np.linalg.norm(b)
+
+
+def _sell_matvec(slice_ptr, col, val, x_ext, n_rows):
+    """What csrc/dist.cu:slab_spmv computes for the local rows, on the host."""
+    y = np.zeros(n_rows)
+    for s_ in range(len(slice_ptr) - 1):
+        w = (slice_ptr[s_ + 1] - slice_ptr[s_]) // 32
+        for lane in range(32):
+            r = 32 * s_ + lane
+            if r < n_rows:
+                acc = 0.0
+                for k in range(w):
+                    p_ = slice_ptr[s_] + 32 * k + lane
+                    acc += val[p_] * x_ext[col[p_]]
+                y[r] = acc
+    return y
+
+
+def _worker_general(rank, world, port, out_dir):
+    """General partition: scrambled DOF order -> RCM -> even row blocks -> ghost lists, column remap, send plan,
+    emulated push: the partitioned product and a distributed PCG equal the serial ones."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    spec = cuboid_spec(4, 11, 3, jitter=0.15)
+    p = spec["ffe"][0]
+    n = int(p["dof"])
+    A0 = sp.csr_matrix((p["A_data"], p["A_body"]["indices"], p["A_body"]["indptr"]), shape=(n, n))
+    scr = np.random.default_rng(11).permutation(n)
+    A = A0[scr][:, scr].tocsr()
+    mass = (1.0 / p["M_inv"])[scr]
+    perm = np.asarray(reverse_cuthill_mckee(A, symmetric_mode=True), dtype=np.int64)
+    Ap = A[perm][:, perm].tocsr(); Ap.sort_indices()
+    mass_p = mass[perm]
+    bounds = even_row_bounds(n, world)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    rows = Ap[r0:r1]
+    slice_ptr, col_g, val = csr_rows_to_sell(rows.indptr, rows.indices, rows.data, r1 - r0, pad_col_offset=r0)
+    ghosts = ghost_columns(col_g, r0, r1)
+    col = remap_columns(col_g, r0, r1, ghosts)
+    assert col.min() >= 0 and col.max() < (r1 - r0) + len(ghosts)
+    all_ghosts = [None] * world
+    dist.all_gather_object(all_ghosts, ghosts)
+    plan = send_plan(all_ghosts, bounds, rank)
+    # every ghost slot is written exactly once
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(n)
+    ext = emulate_push(x[r0:r1], len(ghosts), plan, rank, world, dist.all_gather_object)
+    assert not np.isnan(ext).any()
+    assert np.array_equal(ext[r1 - r0:], x[ghosts])
+    y_loc = _sell_matvec(slice_ptr, col, val, ext, r1 - r0)
+    assert np.allclose(y_loc, (Ap @ x)[r0:r1], rtol=1e-13, atol=1e-13)
+    # neighbours are symmetric here
+    nb = [None] * world
+    dist.all_gather_object(nb, list(plan[3]))
+    for w in plan[3]:
+        assert rank in nb[int(w)]
+    np.save(os.path.join(out_dir, f"nbr{rank}.npy"), plan[3])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_general_partition_ghost_plan(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_worker_general, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(len(np.load(tmp_path / f"nbr{r}.npy")) >= 1 for r in range(world))
+
+
+def test_even_row_bounds():
+    b = even_row_bounds(1000, 3)
+    assert b[0] == 0 and b[-1] == 1000 and all(v % 32 == 0 for v in b[:-1])
+    with pytest.raises(ValueError):
+        even_row_bounds(40, 4)

@@ -1,6 +1,8 @@
-"""The fused peer-memory theta/PCG kernel of csrc/dist.cu on ONE GPU (world size 1: no neighbours, the mailbox
-reduction degenerates to the local sum) must reproduce the single-GPU solver.  The multi-rank run of the same
-script is `torchrun --nproc-per-node N scripts/dist_check.py` (N = 2, 8 verified; see profiles/README.md)."""
+"""The fused peer-memory theta/PCG kernel of csrc/dist.cu on ONE GPU (world size 1: no neighbours, the in-barrier
+all-reduce degenerates to the local sum) must reproduce the single-GPU solver, for the slab cuboid and for a body
+handed over as a scrambled host CSR (RCM reordering).  The multi-rank run of the same script is
+`torchrun --nproc-per-node N scripts/dist_check.py --json profiles/r02_dist_check_nN.json` (outputs kept under
+profiles/)."""
 import os
 import socket
 import subprocess

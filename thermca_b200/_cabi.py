@@ -59,6 +59,7 @@ EXPORTS = {
     "tc_rhs": (i32, [vp, f64, vp, vp]),
     "tc_set_state": (i32, [vp, vp]),
     "tc_get_state": (i32, [vp, vp]),
+    "tc_get_state_async": (i32, [vp, vp]),
     "tc_set_history": (i32, [vp, vp, vp, i32, i32]),
     "tc_set_probes": (i32, [vp, vp, i32]),
     "tc_rk_begin": (i32, [vp, i32, f64, f64, f64, f64, f64, f64]),
@@ -71,19 +72,26 @@ EXPORTS = {
     "tc_set_time": (i32, [vp, f64]),
     "tc_timing": (i32, [vp, i32, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
     "tc_pcg_profile": (i32, [vp, C.POINTER(C.c_uint64)]),
+    "tc_pcg_status": (i32, [vp, C.POINTER(i64)]),
     "tc_pcg_stats": (i32, [vp, C.POINTER(i64)]),
     "tc_sell_spmv": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32]),
     "tc_vm_eval": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "tc_pcg_solve": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32, C.POINTER(i32)]),
-    "tc_dist_create": (i32, [C.POINTER(vp), vp, i32, i32, i64, i64, i64]),
+    "tc_dist_create": (i32, [C.POINTER(vp), vp, i32, i32, i64, i64]),
     "tc_dist_ipc_handle": (i32, [vp, vp]),
     "tc_dist_open_peers": (i32, [vp, vp, C.POINTER(i64)]),
-    "tc_dist_set_operator": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "tc_dist_set_halo": (i32, [vp, i64, vp, vp, vp, i32, vp]),
+    "tc_dist_set_operator": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+    "tc_dist_set_load": (i32, [vp, vp]),
     "tc_dist_set_state": (i32, [vp, vp]),
     "tc_dist_get_state": (i32, [vp, vp]),
+    "tc_dist_copy_state_async": (i32, [vp, vp, i32]),
     "tc_dist_theta_steps": (i32, [vp, i32, f64, f64, f64, i32]),
+    "tc_dist_check": (i32, [vp]),
+    "tc_dist_reset_error": (i32, [vp]),
     "tc_dist_stats": (i32, [vp, C.POINTER(i64)]),
     "tc_dist_profile": (i32, [vp, C.POINTER(C.c_uint64)]),
+    "tc_dist_close_peers": (i32, [vp]),
     "tc_dist_destroy": (i32, [vp]),
     "tc_mor_batch_steps": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  f64, f64, i32, i32]),

@@ -51,6 +51,7 @@ __device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int&
     __shared__ int s_last;
     __shared__ double s_tot[TC_BAR_MAXK > 0 ? TC_BAR_MAXK : 1];
     const int G = gridDim.x;
+    __syncthreads();                                       // every thread's earlier stores are ordered before thread 0's fence
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) B.part[k * TC_MAX_PARTIALS + blockIdx.x] = v[k];

@@ -535,6 +535,12 @@ extern "C" int tc_get_state(tc_handle s, double* y_dev) {
     TC_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
+// enqueue-only variant for pipelined host<->device streaming (no synchronisation; ordered on the solver stream)
+extern "C" int tc_get_state_async(tc_handle s, double* y_dev) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    TC_CUDA(cudaMemcpyAsync(y_dev, s->y, sizeof(double) * s->n_state, cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
 extern "C" int tc_set_probes(tc_handle s, const int64_t* probe_idx_dev, int32_t n_probe) {
     TC_CHECK(s, "null handle");
     TC_CHECK(n_probe >= 0, "negative probe count");
@@ -1302,35 +1308,6 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     P.bar.part = aux + n_aux; P.bar.res = P.bar.part + TC_BAR_MAXK * TC_MAX_PARTIALS;
     int* isc = (int*)(blob + sizeof(double) * n_dbl);
     P.bar.ctr = (unsigned int*)(isc + 16);
-    const double c[4] = {0.0, 1.0, 0.0, 0.0};
-        TC_CUDA(cudaMemcpy(one_ctrl, c, sizeof c, cudaMemcpyHostToDevice));
-        TC_CUDA(cudaMalloc(&scratch, sizeof(double) * 4 * TC_MAX_PARTIALS));
-    }
-    if (g > TC_MAX_PARTIALS) g = TC_MAX_PARTIALS;
-    if (mode == SPMV_NEG)
-        tc_sell_spmv_kernel<SPMV_NEG><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, nullptr, nullptr, one_ctrl, 0.0, nullptr, nullptr);
-    else if (mode == SPMV_B)
-        tc_sell_spmv_kernel<SPMV_B><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, b, nullptr, one_ctrl, 0.0, nullptr, nullptr);
-    else
-        tc_sell_spmv_kernel<SPMV_SHIFT><<<g, TC_SPMV_THREADS, 0, st>>>(A, x, y, nullptr, mass, one_ctrl, shift, scratch, nullptr);
-    TC_CUDA(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
-                            const int64_t* slice_ptr, const int32_t* col, const double* val,
-                            const double* mass, const double* adiag, const double* rhs, double* x,
-                            double shift, double rtol, int32_t maxit, int32_t* iters) {
-    tc_solver tmp;
-    tmp.stream = (cudaStream_t)cuda_stream;
-    TcPcg P{};
-    P.A = TcSell{n, nslices, (const long long*)slice_ptr, col, val, nullptr};
-    double* ws = nullptr; double* aux = nullptr; int* isc = nullptr;
-    TC_CUDA(cudaMalloc(&ws, sizeof(double) * 4 * (size_t)n));
-    TC_CUDA(cudaMalloc(&aux, sizeof(double) * (4 * TC_MAX_PARTIALS + 16 + 4)));
-    TC_CUDA(cudaMalloc(&isc, sizeof(int) * 16));
-    TC_CUDA(cudaMemset(isc, 0, sizeof(int) * 16));
-    TC_CUDA(cudaMemset(aux, 0, sizeof(double) * (4 * TC_MAX_PARTIALS + 20)));
     const double c[4] = {0.0, 1.0, 0.0, 0.0};
     double* ctrl = aux + 4 * TC_MAX_PARTIALS + 16;
     TC_CUDA(cudaMemcpyAsync(ctrl, c, sizeof c, cudaMemcpyHostToDevice, tmp.stream));

@@ -699,6 +699,13 @@ class DeviceSolver:
                     "pcg": self.pcg_stats()})
         if info["status"] == -1:
             raise Exception("Solver failed" + "Required step size is less than spacing between numbers.")
+        bad = self.pcg_status()
+        res["pcg_failed_solves"] = bad["failed_solves"]
+        if bad["failed_solves"]:
+            # a W-method tolerates inexact stage solves (the error estimator sees them), but never silently
+            import warnings
+            warnings.warn(f"{bad['failed_solves']} PCG stage solves ended without reaching pcg_rtol "
+                          f"({bad['reason']}); raise pcg_maxit or loosen pcg_rtol", RuntimeWarning)
         return res
 
     def theta_steps(self, nsteps, h, theta=0.5, t0=None, pcg_rtol=1e-10, pcg_maxit=2000, pcg_mode=0, sync=True):
@@ -709,6 +716,55 @@ class DeviceSolver:
                                             int(pcg_maxit), int(pcg_mode)))
         if sync:
             self.stream.synchronize()
+            bad = self.pcg_status()
+            if bad["failed_solves"]:       # fixed steps have no error estimator behind them: a bad solve is an error
+                raise RuntimeError(f"PCG did not converge in {bad['failed_solves']} of {nsteps} theta steps "
+                                   f"({bad['reason']}, pcg_maxit={pcg_maxit}, pcg_rtol={pcg_rtol})")
+
+    def theta_stream(self, host_in, host_out, h, theta=0.5, pcg_rtol=1e-8, pcg_maxit=2000, pcg_mode=0):
+        """Host-buffer throughput API: one theta step for every pinned host state in ``host_in`` (list of 1-D float64
+        tensors), results into the pinned tensors ``host_out``.  Double buffered: the upload of job j+1 and the
+        download of job j-1 run on their own streams while job j is being stepped.  Returns when all results are
+        in host memory."""
+        torch = self.torch
+        n = self.n_state
+        st_in, st_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        if not hasattr(self, "_stage"):
+            self._stage = [[torch.empty(n, dtype=torch.float64, device=self.dev) for _ in range(2)] for _ in range(2)]
+        ins, outs = self._stage
+        up = [torch.cuda.Event() for _ in host_in]
+        done = [torch.cuda.Event() for _ in host_in]
+        down = [torch.cuda.Event() for _ in host_in]
+        torch.cuda.synchronize(self.dev)
+        for j, (hi, ho) in enumerate(zip(host_in, host_out)):
+            with torch.cuda.stream(st_in):
+                if j >= 2:
+                    st_in.wait_event(done[j - 2])                 # staging slot free again
+                ins[j & 1].copy_(hi, non_blocking=True)
+                up[j].record(st_in)
+            self.stream.wait_event(up[j])
+            if j >= 2:
+                self.stream.wait_event(down[j - 2])               # result slot drained
+            _cabi.check(self.lib.tc_set_state(self._handle, self._p(ins[j & 1])))
+            _cabi.check(self.lib.tc_theta_steps(self._handle, 1, float(theta), float(h), float(pcg_rtol),
+                                                int(pcg_maxit), int(pcg_mode)))
+            _cabi.check(self.lib.tc_get_state_async(self._handle, self._p(outs[j & 1])))
+            done[j].record(self.stream)
+            with torch.cuda.stream(st_out):
+                st_out.wait_event(done[j])
+                ho.copy_(outs[j & 1], non_blocking=True)
+                down[j].record(st_out)
+        torch.cuda.synchronize(self.dev)
+        bad = self.pcg_status()
+        if bad["failed_solves"]:
+            raise RuntimeError(f"PCG did not converge in {bad['failed_solves']} streamed steps ({bad['reason']})")
+
+    def pcg_status(self):
+        """Failed PCG solves since the last call (csrc/pcg.cuh status flag); cleared on read."""
+        st = (_cabi.i64 * 2)()
+        _cabi.check(self.lib.tc_pcg_status(self._handle, st))
+        reason = {0: "none", 1: "iteration limit", 2: "breakdown (non-finite or non-positive curvature)"}.get(int(st[0]), "?")
+        return {"status": int(st[0]), "failed_solves": int(st[1]), "reason": reason}
 
     def timing(self, enable=True):
         """Toggle CUDA-event timing of PCG launches; returns what accumulated since the last call."""
@@ -717,7 +773,8 @@ class DeviceSolver:
         return {"pcg_ms": ms.value, "pcg_launches": int(n.value), "launches": int(launches.value)}
 
     def pcg_profile(self):
-        names = ["loop top", "spmv", "dot+sync", "pq sum", "update x,r", "sync", "rho sums", "direction", "sync "]
+        names = ["loop top", "spmv", "dot + reduce-barrier (p.q)", "update x,r", "reduce-barrier (r.z, r.r)",
+                 "direction", "barrier"]
         buf = (C.c_uint64 * 16)()
         _cabi.check(self.lib.tc_pcg_profile(self._handle, buf))
         return {n: buf[i] / 1e6 for i, n in enumerate(names)}

@@ -1,11 +1,16 @@
-"""Multi-GPU plumbing: slab partition of one large FE body, IPC exchange of peer buffers and
+"""Multi-GPU plumbing: row partition of one large FE body, halo plan, IPC exchange of peer buffers and
 the driver of the fused peer-memory theta/PCG kernel (csrc/dist.cu).
 
 One process per GPU (torchrun).  ``torch.distributed`` is used only for setup (all-gather of
-CUDA IPC handles and sizes), barriers and the max-over-ranks timing; the data path — halo
-layers and the PCG scalar reductions — moves by peer stores over NVLink inside the kernel.
+CUDA IPC handles, sizes and ghost lists), barriers and the max-over-ranks timing; the data path — ghost
+values and the PCG scalar reductions — moves by peer stores over NVLink inside the kernel.
 The reference has no multi-process code; per rank the arithmetic is
-the single-GPU path on rows [row_begin, row_end).
+the single-GPU path (thermca/solver.py:265-281 + the implicit solve) on the local rows.
+
+Layout: every rank owns the contiguous global rows [bounds[rank], bounds[rank+1]) of a (bandwidth
+reducing) ordering.  Vectors are *extended*: ``[n_loc local | n_ghost ghosts]``, ghosts = the sorted
+global columns outside the own range that the local rows reference.  Operator columns are remapped to
+that vector; slices that reference a ghost are *boundary slices* and are processed last.
 """
 from __future__ import annotations
 
@@ -15,6 +20,7 @@ import os
 import numpy as np
 
 
+# ---- host logic (numpy; covered by the world-size-2 gloo tests) ---------------------------------
 def slab_partition(nx, ny, nz, world):
     """Contiguous row slabs cut between y-layers of the Kuhn cuboid (rows are ordered with y
     slowest, thermca_b200/synth.py:vertex_index).  Returns (bounds[world+1], halo_rows): a row of
@@ -31,9 +37,72 @@ def slab_partition(nx, ny, nz, world):
     return bounds.astype(np.int64), int(halo)
 
 
+def even_row_bounds(n, world, multiple=32):
+    """Contiguous row blocks of (almost) equal size, cut at multiples of the SELL slice height."""
+    per = -(-n // world)
+    per = -(-per // multiple) * multiple
+    bounds = np.minimum(np.arange(world + 1, dtype=np.int64) * per, n)
+    if np.any(np.diff(bounds) <= 0):
+        raise ValueError("more ranks than row blocks")
+    return bounds
+
+
+def ghost_columns(cols_global, r0, r1):
+    """Sorted unique global columns outside [r0, r1) among ``cols_global`` (1-D integer array)."""
+    c = np.asarray(cols_global)
+    out = c[(c < r0) | (c >= r1)]
+    return np.unique(out).astype(np.int64)
+
+
+def remap_columns(cols_global, r0, r1, ghosts):
+    """Global column -> index into the extended vector [local | ghosts]."""
+    c = np.asarray(cols_global).astype(np.int64)
+    inside = (c >= r0) & (c < r1)
+    loc = np.where(inside, c - r0, (r1 - r0) + np.searchsorted(ghosts, c))
+    return loc
+
+
+def send_plan(all_ghosts, bounds, rank):
+    """What this rank must push: ``all_ghosts[w]`` = sorted ghost columns of rank w.  Returns
+    (send_row int32, send_peer int32, send_dst int64, neighbours int32): entry e sends local row
+    send_row[e] into slot send_dst[e] of rank send_peer[e]'s extended vectors."""
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    rows, peers, dsts, nbrs = [], [], [], set()
+    for w, g in enumerate(all_ghosts):
+        if w == rank:
+            continue
+        g = np.asarray(g, dtype=np.int64)
+        hit = np.nonzero((g >= r0) & (g < r1))[0]
+        if hit.size:
+            n_w = int(bounds[w + 1] - bounds[w])
+            rows.append(g[hit] - r0)
+            peers.append(np.full(hit.size, w))
+            dsts.append(n_w + hit)
+            nbrs.add(w)
+    # the ranks that own my ghosts are neighbours as well (symmetric for a symmetric pattern; kept general)
+    mine = np.asarray(all_ghosts[rank], dtype=np.int64)
+    if mine.size:
+        owners = np.searchsorted(bounds, mine, side="right") - 1
+        nbrs.update(int(o) for o in np.unique(owners))
+    cat = lambda v, dt: np.concatenate(v).astype(dt) if v else np.zeros(0, dtype=dt)
+    return cat(rows, np.int32), cat(peers, np.int32), cat(dsts, np.int64), np.array(sorted(nbrs), dtype=np.int32)
+
+
+def emulate_push(x_local, n_ghost, plan, rank, world, all_gather_object):
+    """Host restatement of the in-kernel ghost exchange (used by the gloo tests): returns the extended vector."""
+    send_row, send_peer, send_dst, _ = plan
+    out = [None] * world
+    all_gather_object(out, (send_peer, send_dst, np.asarray(x_local)[send_row]))
+    ext = np.concatenate([np.asarray(x_local, dtype=np.float64), np.full(n_ghost, np.nan)])
+    for w, (peer, dst, val) in enumerate(out):
+        sel = peer == rank
+        ext[dst[sel]] = val[sel]
+    return ext
+
+
 def local_spmv_with_halo(A_rows, x_local, row_begin, halo, recv_lo, recv_hi, n_global):
-    """Host restatement of the slab product used by the gloo tests: ``A_rows`` holds the rows of
-    this rank with GLOBAL columns; the gathered vector is [lower halo | local | upper halo]."""
+    """Host restatement of a slab product with +-1 neighbours: ``A_rows`` holds the rows of this rank with
+    GLOBAL columns; the gathered vector is [lower halo | local | upper halo]."""
     n_loc = len(x_local)
     ext = np.zeros(n_global)
     ext[row_begin: row_begin + n_loc] = x_local
@@ -44,25 +113,295 @@ def local_spmv_with_halo(A_rows, x_local, row_begin, halo, recv_lo, recv_hi, n_g
     return A_rows @ ext
 
 
-class DistCuboid:
-    """BASELINE config #5: the synthetic FE cuboid row-partitioned over ``world`` GPUs."""
+def csr_rows_to_sell(indptr, indices, data, n_rows, pad_col_offset=0):
+    """SELL-32 arrays (slice_ptr int64, col int64, val f64) of CSR rows; short rows are padded with
+    (0, own row + pad_col_offset) as csrc/parts.cuh expects.  Row i of the CSR is local row i; columns are
+    kept as given (pass the global row offset as ``pad_col_offset`` when they are global)."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    lens = np.diff(indptr)
+    nsl = (n_rows + 31) // 32
+    lens_p = np.zeros(nsl * 32, dtype=np.int64)
+    lens_p[:n_rows] = lens
+    width = lens_p.reshape(nsl, 32).max(axis=1)
+    slice_ptr = np.concatenate([[0], np.cumsum(width * 32)]).astype(np.int64)
+    total = int(slice_ptr[-1])
+    pos = np.arange(total, dtype=np.int64)
+    sl = np.searchsorted(slice_ptr, pos, side="right") - 1
+    lane = (pos - slice_ptr[sl]) & 31
+    col = np.minimum(32 * sl + lane, n_rows - 1) + pad_col_offset          # padding: own row
+    val = np.zeros(total, dtype=np.float64)
+    rows = np.repeat(np.arange(n_rows, dtype=np.int64), lens)
+    k = np.arange(int(indptr[-1]), dtype=np.int64) - np.repeat(indptr[:-1], lens)
+    p = slice_ptr[rows >> 5] + 32 * k + (rows & 31)
+    col[p] = np.asarray(indices, dtype=np.int64)
+    val[p] = np.asarray(data, dtype=np.float64)
+    return slice_ptr, col, val
+
+
+# ---- device side ------------------------------------------------------------------------------------
+class DistBody:
+    """One FE body row-partitioned over the ranks of the default process group.
+
+    ``op`` describes the LOCAL rows [row_begin, row_begin + n) on the device: ``slice_ptr`` (int64), ``col``
+    (int32, GLOBAL columns), ``val``, optional ``col16`` (column - row), ``mass``, ``adiag`` (diagonal of
+    A = M^-1 K incl. films), ``nslices``.  ``b``: load vector of the local rows (device)."""
+
+    def __init__(self, op, b, bounds, init_temp=20.0):
+        import torch
+        import torch.distributed as dist
+        from . import _cabi
+        self.torch, self.dist, self.lib = torch, dist, _cabi.load_library()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.bounds = np.asarray(bounds, dtype=np.int64)
+        r0, r1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        self.row_begin, self.n, self.n_global = r0, r1 - r0, int(self.bounds[-1])
+        assert int(op["n"]) == self.n
+        self.op, self.b = op, b
+        nsl = int(op["nslices"])
+        col = op["col"]
+        # ---- ghosts, column remap, boundary slices (on the device: 10^8 entries at 10 M rows) ----------
+        outside = (col < r0) | (col >= r1)
+        ghosts = torch.unique(col[outside]).to(torch.int64)                 # sorted
+        self.n_ghost = int(ghosts.numel())
+        widths = (op["slice_ptr"][1:] - op["slice_ptr"][:-1])
+        slice_of = torch.repeat_interleave(torch.arange(nsl, device=self.dev), widths)
+        bnd_mask = torch.zeros(nsl, dtype=torch.bool, device=self.dev)
+        if self.n_ghost:
+            bnd_mask[slice_of[outside]] = True
+        col_loc = col.to(torch.int64) - r0
+        if self.n_ghost:
+            col_loc[outside] = self.n + torch.searchsorted(ghosts, col[outside].to(torch.int64))
+        self.col_loc = col_loc.to(torch.int32)
+        op["col"] = self.col_loc                 # the global columns are not needed any more (0.6 GB at 10 M rows)
+        del col_loc, slice_of, outside, col
+        ids = torch.arange(nsl, device=self.dev, dtype=torch.int32)
+        self.order = torch.cat([ids[~bnd_mask], ids[bnd_mask]]).contiguous()
+        self.n_bnd = int(bnd_mask.sum().item())
+        self.stream = torch.cuda.Stream(self.dev)
+        self.nnz = int(torch.count_nonzero(op["val"]).item())
+        # ---- halo plan (setup-time collectives) --------------------------------------------------------
+        all_ghosts = [None] * self.world
+        dist.all_gather_object(all_ghosts, ghosts.cpu().numpy())
+        self.plan = send_plan(all_ghosts, self.bounds, self.rank)
+        ext = [int(self.bounds[w + 1] - self.bounds[w]) + len(all_ghosts[w]) for w in range(self.world)]
+        torch.cuda.synchronize(self.dev)
+        self._h = _cabi.vp()
+        _cabi.check(self.lib.tc_dist_create(C.byref(self._h), C.c_void_p(self.stream.cuda_stream), self.rank,
+                                            self.world, self.n, self.n_ghost))
+        hbuf = (C.c_ubyte * 64)()
+        _cabi.check(self.lib.tc_dist_ipc_handle(self._h, hbuf))
+        allh = [None] * self.world
+        dist.all_gather_object(allh, bytes(hbuf))
+        handles = b"".join(allh)
+        self._handles = C.create_string_buffer(handles, len(handles))
+        _cabi.check(self.lib.tc_dist_open_peers(self._h, self._handles, (_cabi.i64 * self.world)(*ext)))
+        sr, sp_, sd, nb = self.plan
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._plan_keep = [np.ascontiguousarray(a) for a in (sr, sp_, sd, nb)]
+        sr, sp_, sd, nb = self._plan_keep
+        _cabi.check(self.lib.tc_dist_set_halo(self._h, len(sr), ptr(sr), ptr(sp_), ptr(sd), len(nb), ptr(nb)))
+        p = lambda t: C.c_void_p(t.data_ptr())
+        c16 = op.get("col16") if os.environ.get("TC_COL16", "1") != "0" else None
+        _cabi.check(self.lib.tc_dist_set_operator(self._h, nsl, p(op["slice_ptr"]), p(self.col_loc),
+                                                  p(c16) if c16 is not None else C.c_void_p(0),
+                                                  p(op["val"]), p(op["mass"]), p(op["adiag"]), p(self.b),
+                                                  self.n_bnd, p(self.order)))
+        self.set_state(torch.full((self.n,), float(init_temp), dtype=torch.float64, device=self.dev))
+        dist.barrier()
+
+    # ---- construction from a replicated host operator (a real, lowered FE body) -------------------------
+    @classmethod
+    def from_csr(cls, A, mass, b, init_temp=20.0, reorder=True):
+        """Partition the body whose operator ``A = M^-1 K`` (scipy CSR, replicated on every rank, e.g.
+        ``FFEIO.A`` of a lowered part, thermca/fem/ffe_io.py:40-65), lumped mass and load vector are given on the
+        host.  ``reorder``: reverse Cuthill-McKee (scipy) so that contiguous row blocks have few ghosts; the
+        user-visible DOF order is kept (``gather_state`` / ``set_global_state`` permute back)."""
+        import scipy.sparse as sp
+        import torch
+        import torch.distributed as dist
+        A = sp.csr_matrix(A)
+        n = A.shape[0]
+        if reorder:
+            from scipy.sparse.csgraph import reverse_cuthill_mckee
+            perm = np.asarray(reverse_cuthill_mckee(sp.csr_matrix((np.ones_like(A.data), A.indices, A.indptr),
+                                                                   shape=A.shape), symmetric_mode=True), dtype=np.int64)
+        else:
+            perm = np.arange(n, dtype=np.int64)
+        inv = np.empty(n, dtype=np.int64)
+        inv[perm] = np.arange(n)
+        Ap = A[perm][:, perm].tocsr()
+        Ap.sort_indices()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        bounds = even_row_bounds(n, world)
+        r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+        rows = Ap[r0:r1]
+        slice_ptr, col, val = csr_rows_to_sell(rows.indptr, rows.indices, rows.data, r1 - r0, pad_col_offset=r0)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nsl = len(slice_ptr) - 1
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+        mass_p = np.asarray(mass, dtype=np.float64)[perm]
+        # 16-bit relative columns when the band allows it (interior slices only use them)
+        pos = np.arange(col.size, dtype=np.int64)
+        sl = np.searchsorted(slice_ptr, pos, side="right") - 1
+        row_g = r0 + 32 * sl + ((pos - slice_ptr[sl]) & 31)
+        rel = col - np.minimum(row_g, r1 - 1)
+        inside = (col >= r0) & (col < r1)
+        c16 = None
+        if np.all(np.abs(rel[inside]) < 32768):
+            c16 = t(np.where(inside, rel, 0), torch.int16)
+        op = {"n": r1 - r0, "nslices": nsl, "slice_ptr": t(slice_ptr, torch.int64), "col": t(col, torch.int32),
+              "val": t(val, torch.float64), "mass": t(mass_p[r0:r1], torch.float64),
+              "adiag": t(Ap.diagonal()[r0:r1], torch.float64), "col16": c16}
+        body = cls(op, t(np.asarray(b, dtype=np.float64)[perm][r0:r1], torch.float64), bounds,
+                   init_temp=init_temp)
+        body.perm, body.inv_perm = perm, inv
+        return body
+
+    # ---- state ------------------------------------------------------------------------------------------
+    def set_state(self, y):
+        from . import _cabi
+        self.torch.cuda.synchronize(self.dev)
+        self._y_keep = y
+        _cabi.check(self.lib.tc_dist_set_state(self._h, C.c_void_p(y.data_ptr())))
+
+    def get_state(self, out=None):
+        from . import _cabi
+        if out is None:
+            out = self.torch.empty(self.n, dtype=self.torch.float64, device=self.dev)
+        self.torch.cuda.synchronize(self.dev)
+        _cabi.check(self.lib.tc_dist_get_state(self._h, C.c_void_p(out.data_ptr())))
+        return out
+
+    def set_load(self, b):
+        """Swap the load vector of the local rows (kept by reference)."""
+        from . import _cabi
+        self.b = b
+        _cabi.check(self.lib.tc_dist_set_load(self._h, C.c_void_p(b.data_ptr())))
+
+    def gather_state(self):
+        """Global state in the caller's DOF order on every rank (setup / result path, NCCL all-gather)."""
+        torch, dist = self.torch, self.dist
+        mine = self.get_state()
+        sizes = [int(self.bounds[w + 1] - self.bounds[w]) for w in range(self.world)]
+        parts = [torch.empty(s, dtype=torch.float64, device=self.dev) for s in sizes]
+        dist.all_gather(parts, mine)
+        y = torch.cat(parts)
+        inv = getattr(self, "inv_perm", None)
+        return y if inv is None else y[torch.from_numpy(inv).to(self.dev)]
+
+    def set_global_state(self, y_global):
+        perm = getattr(self, "perm", None)
+        y = self.torch.as_tensor(y_global, dtype=self.torch.float64, device=self.dev)
+        if perm is not None:
+            y = y[self.torch.from_numpy(perm).to(self.dev)]
+        self.set_state(y[self.row_begin: self.row_begin + self.n].contiguous())
+
+    # ---- stepping ---------------------------------------------------------------------------------------
+    def theta_steps(self, nsteps, h, theta=0.5, rtol=1e-8, maxit=2000, sync=False):
+        from . import _cabi
+        _cabi.check(self.lib.tc_dist_theta_steps(self._h, int(nsteps), float(theta), float(h), float(rtol), int(maxit)))
+        if sync:
+            self.check()
+
+    def theta_stream(self, host_in, host_out, h, theta=0.5, rtol=1e-8, maxit=2000):
+        """Host-buffer throughput API (per rank: the local rows): one theta step for every pinned host state in
+        ``host_in``, results into the pinned ``host_out``; uploads / downloads are double buffered against the steps
+        (see DeviceSolver.theta_stream)."""
+        from . import _cabi
+        torch = self.torch
+        st_in, st_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        if not hasattr(self, "_stage"):
+            self._stage = [[torch.empty(self.n, dtype=torch.float64, device=self.dev) for _ in range(2)] for _ in range(2)]
+        ins, outs = self._stage
+        up = [torch.cuda.Event() for _ in host_in]
+        done = [torch.cuda.Event() for _ in host_in]
+        down = [torch.cuda.Event() for _ in host_in]
+        torch.cuda.synchronize(self.dev)
+        for j, (hi, ho) in enumerate(zip(host_in, host_out)):
+            with torch.cuda.stream(st_in):
+                if j >= 2:
+                    st_in.wait_event(done[j - 2])
+                ins[j & 1].copy_(hi, non_blocking=True)
+                up[j].record(st_in)
+            self.stream.wait_event(up[j])
+            if j >= 2:
+                self.stream.wait_event(down[j - 2])
+            _cabi.check(self.lib.tc_dist_copy_state_async(self._h, C.c_void_p(ins[j & 1].data_ptr()), 0))
+            _cabi.check(self.lib.tc_dist_theta_steps(self._h, 1, float(theta), float(h), float(rtol), int(maxit)))
+            _cabi.check(self.lib.tc_dist_copy_state_async(self._h, C.c_void_p(outs[j & 1].data_ptr()), 1))
+            done[j].record(self.stream)
+            with torch.cuda.stream(st_out):
+                st_out.wait_event(done[j])
+                ho.copy_(outs[j & 1], non_blocking=True)
+                down[j].record(st_out)
+        torch.cuda.synchronize(self.dev)
+        self.check()
+
+    def check(self):
+        """Synchronise and raise on EVERY rank if any rank saw a communication timeout or a failed solve."""
+        torch, dist = self.torch, self.dist
+        rc = int(self.lib.tc_dist_check(self._h))
+        msg = self.lib.tc_last_error().decode() if rc else ""
+        flag = torch.tensor([rc], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        worst = int(flag.item())
+        if worst:
+            raise RuntimeError(f"row-partitioned step failed (worst code {worst} over ranks; this rank: {rc} {msg})")
+
+    def reset_error(self):
+        from . import _cabi
+        _cabi.check(self.lib.tc_dist_reset_error(self._h))
+
+    def stats(self):
+        from . import _cabi
+        st = (_cabi.i64 * 5)()
+        _cabi.check(self.lib.tc_dist_stats(self._h, st))
+        return {"iters_last": int(st[0]), "iters_total": int(st[1]), "error": int(st[2]),
+                "solves": int(st[3]) % 1000000, "grid": int(st[3]) // 1000000, "failed_solves": int(st[4])}
+
+    PHASES = ["loop top", "spmv", "dot", "reduce-barrier p.q (+allreduce)", "update x,r",
+              "reduce-barrier r.z,r.r (+allreduce)", "direction + halo push", "barrier"]
+
+    def profile(self):
+        """Accumulated per-phase wall time (ms) seen by block 0 and by the last block; cleared on read."""
+        from . import _cabi
+        buf = (C.c_uint64 * 32)()
+        _cabi.check(self.lib.tc_dist_profile(self._h, buf))
+        return {"block0": {n: buf[i] / 1e6 for i, n in enumerate(self.PHASES)},
+                "last": {n: buf[16 + i] / 1e6 for i, n in enumerate(self.PHASES)}}
+
+    def global_sums(self, y=None):
+        """(sum_i M_i y_i, sum_i y_i^2) over all ranks: thermal energy / capacity-weighted mean and the 2-norm."""
+        torch, dist = self.torch, self.dist
+        y = self.get_state() if y is None else y
+        v = torch.stack([(self.op["mass"] * y).sum(), (y * y).sum()])
+        dist.all_reduce(v)
+        return float(v[0].item()), float(v[1].item())
+
+    def close(self):
+        if self._h:
+            self.lib.tc_dist_close_peers(self._h)     # drain + unmap the peers' buffers
+            self.dist.barrier()                        # nobody still maps my buffer
+            self.lib.tc_dist_destroy(self._h)
+            self._h = None
+
+
+class DistCuboid(DistBody):
+    """BASELINE config #5: the synthetic FE cuboid row-partitioned over ``world`` GPUs (slabs along y)."""
 
     def __init__(self, nx, ny, nz, lx=0.5, ly=1.0, lz=0.05, heat=1000.0, film=10.0, env_temp=20.0,
                  init_temp=20.0, jitter=0.15, condy=50.0, vol_capy=8000.0 * 500.0):
         import torch
         import torch.distributed as dist
-        from . import _cabi
         from .workloads import device_cuboid_operator
-        self.torch, self.dist, self.lib = torch, dist, _cabi.load_library()
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.dev = torch.device("cuda", torch.cuda.current_device())
-        bounds, halo = slab_partition(nx, ny, nz, self.world)
-        self.bounds, self.halo = bounds, halo
-        r0, r1 = int(bounds[self.rank]), int(bounds[self.rank + 1])
-        self.row_begin, self.n = r0, r1 - r0
-        self.n_global = int(bounds[-1])
-        op = device_cuboid_operator(nx, ny, nz, lx, ly, lz, jitter, condy, vol_capy, r0, r1, self.dev)
-        self.op = op
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        bounds, halo = slab_partition(nx, ny, nz, world)
+        self.halo = halo
+        self.dims = (nx, ny, nz)
+        r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+        op = device_cuboid_operator(nx, ny, nz, lx, ly, lz, jitter, condy, vol_capy, r0, r1, dev)
         # surface areas are global sums of the local load columns
         areas = torch.stack([op["q_bottom"].sum(), op["q_upper"].sum()])
         dist.all_reduce(areas)
@@ -75,150 +414,5 @@ class DistCuboid:
         op["val"][pos] += add
         op["adiag"][rows] += add
         # load vector b = M^-1 (Qs flux), flux = [heat/area_bottom, film*T_env]  (solver.py:267-281)
-        self.b = minv * (op["q_bottom"] * (heat / self.areas[0]) + op["q_upper"] * (film * env_temp))
-        self.stream = torch.cuda.Stream(self.dev)
-        self.nnz = int(torch.count_nonzero(op["val"]).item())
-        torch.cuda.synchronize(self.dev)
-        self._h = _cabi.vp()
-        _cabi.check(self.lib.tc_dist_create(C.byref(self._h), C.c_void_p(self.stream.cuda_stream), self.rank,
-                                            self.world, self.n, halo, r0))
-        # exchange IPC handles and slab sizes (setup only)
-        hbuf = (C.c_ubyte * 64)()
-        _cabi.check(self.lib.tc_dist_ipc_handle(self._h, hbuf))
-        mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=self.dev)
-        allh = [torch.empty(64, dtype=torch.uint8, device=self.dev) for _ in range(self.world)]
-        dist.all_gather(allh, mine)
-        handles = bytes(torch.cat(allh).cpu().numpy().tobytes())
-        peer_n = (_cabi.i64 * self.world)(*[int(bounds[w + 1] - bounds[w]) for w in range(self.world)])
-        self._handles = C.create_string_buffer(handles, len(handles))
-        _cabi.check(self.lib.tc_dist_open_peers(self._h, self._handles, peer_n))
-        p = lambda t: C.c_void_p(t.data_ptr())
-        c16 = op.get("col16") if os.environ.get("TC_COL16", "1") != "0" else None
-        _cabi.check(self.lib.tc_dist_set_operator(self._h, op["nslices"], p(op["slice_ptr"]), p(op["col"]),
-                                                  p(c16) if c16 is not None else C.c_void_p(0),
-                                                  p(op["val"]), p(op["mass"]), p(op["adiag"]), p(self.b)))
-        self.set_state(torch.full((self.n,), float(init_temp), dtype=torch.float64, device=self.dev))
-        dist.barrier()
-
-    def set_state(self, y):
-        self.torch.cuda.synchronize(self.dev)
-        self._y_keep = y
-        from . import _cabi
-        _cabi.check(self.lib.tc_dist_set_state(self._h, C.c_void_p(y.data_ptr())))
-
-    def get_state(self):
-        from . import _cabi
-        out = self.torch.empty(self.n, dtype=self.torch.float64, device=self.dev)
-        self.torch.cuda.synchronize(self.dev)
-        _cabi.check(self.lib.tc_dist_get_state(self._h, C.c_void_p(out.data_ptr())))
-        return out
-
-    def theta_steps(self, nsteps, h, theta=0.5, rtol=1e-8, maxit=2000):
-        from . import _cabi
-        _cabi.check(self.lib.tc_dist_theta_steps(self._h, int(nsteps), float(theta), float(h), float(rtol), int(maxit)))
-
-    def stats(self):
-        from . import _cabi
-        st = (_cabi.i64 * 4)()
-        _cabi.check(self.lib.tc_dist_stats(self._h, st))
-        return {"iters_last": int(st[0]), "iters_total": int(st[1]), "error": int(st[2]),
-                "solves": int(st[3]) % 1000000, "grid": int(st[3]) // 1000000}
-
-    PHASES = ["rhs+init", "halo flag", "spmv", "-", "dot", "sync1", "allreduce pq",
-              "update x,r", "sync2", "allreduce rho", "direction", "sync3"]
-
-    def profile(self):
-        """Accumulated per-phase wall time (ms) seen by block 0 and by the last block; cleared on read."""
-        from . import _cabi
-        buf = (C.c_uint64 * 32)()
-        _cabi.check(self.lib.tc_dist_profile(self._h, buf))
-        return {"block0": {n: buf[i] / 1e6 for i, n in enumerate(self.PHASES)},
-                "last": {n: buf[16 + i] / 1e6 for i, n in enumerate(self.PHASES)}}
-
-    def close(self):
-        if self._h:
-            self.dist.barrier()
-            self.lib.tc_dist_destroy(self._h)
-            self._h = None
-
-
-def run_partitioned_bench(args, world, rank, local_rank):
-    """bench.py leg for N > 1: weak scaling, args.dof rows per GPU, slabs along y."""
-    import torch
-    import torch.distributed as dist
-    from .workloads import cuboid_dims
-    import bench as B
-    nx, ny, nz = cuboid_dims(args.dof)
-    ny_tot = (ny + 1) * world - 1                     # the same number of y-layers per rank
-    dc = DistCuboid(nx, ny_tot, nz, ly=1.0 * world, heat=B.HEAT * world, film=B.FILM, env_temp=B.T_ENV)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with B.ClockSampler(local_rank) as clocks:
-        dc.theta_steps(args.warmup, B.H_STEP, B.THETA, B.PCG_RTOL)
-        it0 = dc.stats()["iters_total"]
-        dc.profile()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0.record(dc.stream)
-        dc.theta_steps(args.steps, B.H_STEP, B.THETA, B.PCG_RTOL)
-        e1.record(dc.stream)
-        torch.cuda.synchronize()
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    st = dc.stats()
-    iters = st["iters_total"] - it0
-    prof = dc.profile()
-    err = torch.tensor([st["error"]], dtype=torch.int64, device="cuda")
-    dist.all_reduce(err, op=dist.ReduceOp.MAX)
-    nnz = torch.tensor([dc.nnz], dtype=torch.int64, device="cuda")
-    dist.all_reduce(nnz)
-    n_tot = dc.n_global
-    # e2e: state of every slab up from pinned host memory, one step, state down
-    host_y = dc.get_state().cpu().pin_memory()
-    dev_y = torch.empty(dc.n, dtype=torch.float64, device="cuda")
-    e2e_steps = 2
-    torch.cuda.synchronize(); dist.barrier()
-    import time
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        dev_y.copy_(host_y, non_blocking=True)
-        dc.set_state(dev_y)
-        dc.theta_steps(1, B.H_STEP, B.THETA, B.PCG_RTOL)
-        host_y.copy_(dc.get_state())
-    torch.cuda.synchronize(); dist.barrier()
-    e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-    # per-rank busy / wait split (block 0 of every rank): exposes systematic skew between GPUs
-    pl = prof["last"]
-    mine = torch.tensor([pl["spmv"] + pl["update x,r"] + pl["direction"] + pl["dot"],
-                         pl["allreduce pq"] + pl["allreduce rho"] + pl["sync1"] + pl["sync2"] + pl["sync3"]],
-                        dtype=torch.float64, device="cuda")
-    allp = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
-    dist.all_gather(allp, mine)
-    per_rank = [[round(float(v[0]), 1), round(float(v[1]), 1)] for v in allp]
-    peak, peak_kind = B.measured_peak()
-    bytes_step = B.algorithmic_bytes_per_iteration(dc.n, dc.nnz) * (iters / args.steps) + dc.n * (12 * 15 + 80)
-    achieved = bytes_step / (ms / args.steps * 1e-3) / 1e9
-    line = {
-        "metric": "DOF*steps/s (implicit theta-PCG step, full FE cuboid)", "value": n_tot * args.steps / (ms * 1e-3),
-        "unit": "DOF*steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg#5 row-partitioned FE cuboid {nx}x{ny_tot}x{nz} cells = {n_tot} DOF, "
-                               f"{world} slabs, theta=0.5 Jacobi-PCG step, halo+reductions by peer stores in-kernel",
-                   "dof": n_tot, "dof_per_gpu": dc.n, "nnz": int(nnz.item()), "pcg_rtol": B.PCG_RTOL,
-                   "h_step_s": B.H_STEP, "iters_per_step": iters / args.steps, "halo_rows": dc.halo,
-                   "l2": "per-GPU inputs exceed the 126 MB L2", "comm_error": int(err.item()),
-                   "phase_ms_rank0": prof, "grid": st["grid"],
-                   "busy_wait_ms_per_rank": per_rank},
-        "clocks": clocks.summary(),
-        "e2e": {"value": n_tot * e2e_steps / float(e2e.item()), "unit": "DOF*steps/s",
-                "h2d_bytes_per_step": n_tot * 8, "d2h_bytes_per_step": n_tot * 8, "steps": e2e_steps},
-        "gpu_launches": args.steps * world,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "tc_dist_theta_kernel (per GPU)", "peak_kind": peak_kind},
-    }
-    dc.close()
-    return line
+        b = minv * (op["q_bottom"] * (heat / self.areas[0]) + op["q_upper"] * (film * env_temp))
+        super().__init__(op, b, bounds, init_temp=init_temp)

@@ -84,5 +84,12 @@ class MorEnsemble:
         self.torch.cuda.synchronize(self.dev)
         return self.X.cpu().numpy()
 
+    def launches_per_step(self):
+        """Kernels per RK4 step of the default path: film table + four stage kernels."""
+        return 5
+
+    def kernel_name(self):
+        return "tc_mor_stage_pipe_kernel<3>"
+
     def flops_per_step(self):
         return 4 * 2.0 * (1 + self.F) * self.r * self.r * self.S * self.B
