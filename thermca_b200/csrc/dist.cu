@@ -57,21 +57,26 @@ struct TcDistK {
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
 };
 
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
     int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// bounded wait; on timeout (or when another thread of this rank already gave up) raises the error flag
+// bounded wait; on timeout (or when another thread of this rank already gave up) raises the error flag.
+// Relaxed polls + ONE acquire fence at the end: an acquire load per poll would invalidate this SM's L1 on every
+// iteration while co-resident warps are still gathering through it.
 __device__ __forceinline__ void spin_until(const int* flag, int seq, int* err, long long limit) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(flag) < seq) {
-        if (*((volatile int*)err)) return;
-        if (clock64() - t0 > limit) { *((volatile int*)err) = 1; __threadfence(); return; }
+    if (ld_relaxed_sys(flag) < seq) {
+        const long long t0 = clock64();
+        while (ld_relaxed_sys(flag) < seq) {
+            if (*((volatile int*)err)) return;
+            if (clock64() - t0 > limit) { *((volatile int*)err) = 1; __threadfence(); return; }
+        }
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
 
 // All-reduce of the local totals, run by the last block to reach the grid barrier (gridbar.cuh hook).
@@ -221,7 +226,7 @@ tc_dist_theta_kernel(TcDistK S) {
     __shared__ double sh[32];
     const int n = S.n;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    unsigned int gen = *((volatile unsigned int*)(S.bar.ctr + 32));
+    unsigned int gen = tc_bar_generation(S.bar);
     int rseq = S.state[0], hseq = S.state[1];
     PROF_INIT();
     const double shift = S.theta * S.h;
@@ -374,8 +379,8 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     TC_CUDA(cudaMemset(d->state, 0, sizeof(int) * 16));
     TC_CUDA(cudaMalloc(&d->prof, sizeof(unsigned long long) * 32));
     TC_CUDA(cudaMemset(d->prof, 0, sizeof(unsigned long long) * 32));
-    TC_CUDA(cudaMalloc(&d->K.bar.ctr, sizeof(unsigned int) * 64));
-    TC_CUDA(cudaMemset(d->K.bar.ctr, 0, sizeof(unsigned int) * 64));
+    TC_CUDA(cudaMalloc(&d->K.bar.ctr, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
+    TC_CUDA(cudaMemset(d->K.bar.ctr, 0, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
     TC_CUDA(cudaMalloc(&d->K.bar.part, sizeof(double) * TC_BAR_MAXK * TC_MAX_PARTIALS));
     TC_CUDA(cudaMalloc(&d->K.bar.res, sizeof(double) * 2 * TC_BAR_MAXK));
     TC_CUDA(cudaMemset(d->K.bar.res, 0, sizeof(double) * 2 * TC_BAR_MAXK));

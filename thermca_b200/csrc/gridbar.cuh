@@ -18,23 +18,39 @@
 #define TC_BAR_MAXK 4
 
 struct TcGridBar {
-    unsigned int* ctr;      // [0] arrival count, [32] generation (separate 128-byte lines); zero-initialised
+    unsigned int* ctr;      // [0] arrival count; generation flags at [32 * (1 + j)], j < TC_BAR_FLAGS (one 128-byte line
+                            // each: the pollers are spread over several L2 lines); zero-initialised, TC_BAR_CTR_WORDS words
     double* part;           // TC_BAR_MAXK banks of TC_MAX_PARTIALS
     double* res;            // [2][TC_BAR_MAXK] totals, parity = generation & 1
 };
+#define TC_BAR_FLAGS 32                                   // blocks poll flag (blockIdx % TC_BAR_FLAGS)
+#define TC_BAR_CTR_WORDS (32 * (1 + TC_BAR_FLAGS))
 
-__device__ __forceinline__ unsigned int tc_ld_acquire_gpu_u32(const unsigned int* p) {
+// Fences: fence.acq_rel.gpu (MEMBAR.ALL.GPU + L1 invalidate) is enough on both sides of the flag; CUDA's
+// __threadfence() is the sequentially consistent fence.sc.gpu (measured ~2x the cost).  The wait loop polls with a
+// relaxed (volatile) load: an acquire load per poll would invalidate the SM's L1 on every iteration and evict the
+// gather lines of co-resident blocks that are still working.
+__device__ __forceinline__ void tc_fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned int tc_ld_relaxed_gpu_u32(const unsigned int* p) {
     unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void tc_st_relaxed_gpu_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// release-only forms: MEMBAR.ALL.GPU + the access, WITHOUT the L1 invalidation an acq_rel fence carries (checked in
+// SASS) — the arriving block must not wipe the L1 lines of co-resident blocks that are still in the phase
+__device__ __forceinline__ unsigned int tc_atom_add_release_gpu(unsigned int* p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
 }
 __device__ __forceinline__ void tc_st_release_gpu_u32(unsigned int* p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned int tc_atom_add_acqrel_gpu(unsigned int* p, unsigned int v) {
-    unsigned int old;
-    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
+__device__ __forceinline__ unsigned int tc_bar_generation(const TcGridBar& B) {
+    return tc_ld_relaxed_gpu_u32(B.ctr + 32);
 }
 
 struct TcNoExchange {
@@ -43,7 +59,7 @@ struct TcNoExchange {
 
 // v[k]: this block's contribution, valid in thread 0.  On return every thread of every block holds the
 // grid totals in v[k].  `gen` is the caller's running generation counter (same value in all blocks; the
-// kernel reads it once from ctr[32] at entry).  sh: >= 32 doubles of shared scratch.
+// kernel reads it once with tc_bar_generation at entry).  sh: >= 32 doubles of shared scratch.
 // xchg(tot, K): called by ALL threads of the last block with the local totals in shared memory `tot`;
 // may replace them (multi-GPU sum).  Must contain its own __syncthreads() pairs if it uses several threads.
 template <int K, class X>
@@ -55,13 +71,14 @@ __device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int&
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) B.part[k * TC_MAX_PARTIALS + blockIdx.x] = v[k];
-        __threadfence();                                   // partials + everything this block wrote before
-        const unsigned int old = tc_atom_add_acqrel_gpu(B.ctr, 1u);
-        s_last = (old == (unsigned int)(G - 1));
+        // release: partials + everything this block wrote before (cumulative over the __syncthreads above)
+        const unsigned int old = tc_atom_add_release_gpu(B.ctr, 1u);
+        const int last = (old == (unsigned int)(G - 1));
+        if (last) tc_fence_acq_rel_gpu();                  // acquire: everything the other blocks released
+        s_last = last;
     }
     __syncthreads();
     if (s_last) {
-        __threadfence();                                    // acquire side for every thread of the last block
         if (K > 0) {
             double acc[K > 0 ? K : 1];
 #pragma unroll
@@ -94,13 +111,15 @@ __device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int&
             double* res = B.res + (gen & 1u) * TC_BAR_MAXK;
 #pragma unroll
             for (int k = 0; k < K; ++k) res[k] = s_tot[k];
-            B.ctr[0] = 0u;                                  // re-arm: nobody arrives again before the release below
-            __threadfence();
-            tc_st_release_gpu_u32(B.ctr + 32, gen + 1u);
+            tc_st_relaxed_gpu_u32(B.ctr, 0u);               // re-arm: nobody arrives again before the release below
         }
+        __syncthreads();
+        if (threadIdx.x < TC_BAR_FLAGS)                     // release (cumulative over thread 0's stores) + flag
+            tc_st_release_gpu_u32(B.ctr + 32 * (1 + threadIdx.x), gen + 1u);
     } else if (threadIdx.x == 0) {
-        while (tc_ld_acquire_gpu_u32(B.ctr + 32) == gen) { }
-        __threadfence();                                    // gpu-scope fence: stale L1 lines of this SM are dropped
+        const unsigned int* flag = B.ctr + 32 * (1 + (blockIdx.x % TC_BAR_FLAGS));
+        while (tc_ld_relaxed_gpu_u32(flag) == gen) { }
+        tc_fence_acq_rel_gpu();                             // acquire + stale L1 lines of this SM are dropped
     }
     __syncthreads();
     if (K > 0) {

@@ -114,7 +114,7 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;       // uniform over the grid
     if (S.skip && *S.skip) return;             // uniform over the grid
     __shared__ double sh[32];
-    unsigned int gen = *((volatile unsigned int*)(S.bar.ctr + 32));
+    unsigned int gen = tc_bar_generation(S.bar);
     const double shift = S.coef * S.ctrl[1];
     unsigned long long prof_t = (S.prof && blockIdx.x == 0 && threadIdx.x == 0) ? tc_gtime() : 0ULL;
     double red[2];

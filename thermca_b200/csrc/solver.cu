@@ -341,8 +341,8 @@ extern "C" int tc_create(tc_handle* out, void* cuda_stream) {
     TC_CUDA(cudaMemset(s->pcg_isc, 0, sizeof(int) * 16));
     TC_CUDA(cudaMalloc(&s->pcg_prof, sizeof(unsigned long long) * 16));
     TC_CUDA(cudaMemset(s->pcg_prof, 0, sizeof(unsigned long long) * 16));
-    TC_CUDA(cudaMalloc(&s->bar.ctr, sizeof(unsigned int) * 64));
-    TC_CUDA(cudaMemset(s->bar.ctr, 0, sizeof(unsigned int) * 64));
+    TC_CUDA(cudaMalloc(&s->bar.ctr, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
+    TC_CUDA(cudaMemset(s->bar.ctr, 0, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
     TC_CUDA(cudaMalloc(&s->bar.part, sizeof(double) * TC_BAR_MAXK * TC_MAX_PARTIALS));
     TC_CUDA(cudaMalloc(&s->bar.res, sizeof(double) * 2 * TC_BAR_MAXK));
     TC_CUDA(cudaMemset(s->bar.res, 0, sizeof(double) * 2 * TC_BAR_MAXK));
@@ -1300,9 +1300,9 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     const size_t n_aux = 4 * TC_MAX_PARTIALS + 20, n_bar = TC_BAR_MAXK * TC_MAX_PARTIALS + 2 * TC_BAR_MAXK;
     const size_t n_dbl = 4 * (size_t)n + n_aux + n_bar;
     char* blob = nullptr;
-    TC_CUDA(cudaMalloc(&blob, sizeof(double) * n_dbl + sizeof(int) * (16 + 64)));
+    TC_CUDA(cudaMalloc(&blob, sizeof(double) * n_dbl + sizeof(int) * (16 + TC_BAR_CTR_WORDS)));
     TC_CUDA(cudaMemsetAsync(blob + sizeof(double) * 4 * (size_t)n, 0,
-                            sizeof(double) * (n_aux + n_bar) + sizeof(int) * (16 + 64), tmp.stream));
+                            sizeof(double) * (n_aux + n_bar) + sizeof(int) * (16 + TC_BAR_CTR_WORDS), tmp.stream));
     double* ws = (double*)blob;
     double* aux = ws + 4 * (size_t)n;
     P.bar.part = aux + n_aux; P.bar.res = P.bar.part + TC_BAR_MAXK * TC_MAX_PARTIALS;

@@ -67,6 +67,10 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
                        for i, io in enumerate(net._mor_ios)])
     coll = _ResultCollector(io_temp_dt=np.dtype([("lp", lp_dt), ("ffe", ffe_dt), ("mor", mor_dt)]))
 
+    _check_material_limits(net, res)
+    lp_offs = np.concatenate([[0], np.cumsum([io.lp_sys.dof for io in net._lp_ios])]).astype(int)
+    tdep_lp = [(i, io) for i, io in enumerate(net._lp_ios) if io in getattr(net, "_var_body_lp_ios", [])]
+
     rc = net.run_cond
     coo = rc.tocoo()
     rows, cols = coo.row, coo.col            # CSR order == data order
@@ -88,6 +92,13 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
         if res["io_temps"].shape[1] > 0:
             coll.io_temps.append(res["io_temps"][k])     # row view; from_collector stacks them (resultdata.py:720)
         if net._lp_ios:
+            # temperature dependent LP bodies: the reference stores the capacity / conductance matrices of the last
+            # right-hand side of the step, i.e. at the accepted state (thermca/solver.py:419-424 after
+            # network.py:820-822); the device rebuilds them inside the network kernel, so the host copies the
+            # post-processing reads are refreshed here with the reference's own routine (thermca/lpm/lp_io.py:59-66)
+            for i, io in tdep_lp:
+                with _quiet():
+                    io.update_material_properties(np.asarray(res["io_temps"][k][lp_offs[i]: lp_offs[i + 1]]))
             coll.lp_M_diagss.append([io.lp_sys.M_diag.copy() for io in net._lp_ios])
             coll.lp_Lss.append([io.lp_sys.L.copy() for io in net._lp_ios])
 
@@ -101,6 +112,45 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
     if res.get("status", 0) == -1:
         raise Exception("Solver failed" + "Required step size is less than spacing between numbers.")
     return coll
+
+
+class _quiet:
+    """Suppress the per-call limit warnings of the reference while refreshing stored matrices (the check over all
+    stored states is done once by ``_check_material_limits``)."""
+
+    def __enter__(self):
+        import warnings
+        self._cm = warnings.catch_warnings()
+        self._cm.__enter__()
+        warnings.simplefilter("ignore")
+
+    def __exit__(self, *a):
+        return self._cm.__exit__(*a)
+
+
+def _check_material_limits(net, res):
+    """``Material.check_limits`` (thermca/materials.py:155-169) over ALL stored states at once — the reference calls it
+    on every right-hand side for temperature dependent nodes (network.py:763), FE bodies (fem/fe_system.py:187) and LP
+    bodies (lpm/lp_system.py:107) and notes "better check all result temps at once"; the device evaluates the tables
+    clamped like numpy.interp, the warning is raised here from the stored temperatures."""
+    temps = np.asarray(res["net_temps"])
+    if temps.size:
+        for matl, idx in getattr(net, "_all_temp_dependent_matl_idxs", {}).items():
+            matl.check_limits(temps[:, idx])
+    io = np.asarray(res["io_temps"])
+    if io.ndim != 2 or io.shape[1] == 0:
+        return
+    off = 0
+    for lp_io in net._lp_ios:
+        n = lp_io.lp_sys.dof
+        if lp_io in getattr(net, "_var_body_lp_ios", []):
+            lp_io.lp_sys.matl.check_limits(io[:, off: off + n])
+        off += n
+    for ffe_io in net._ffe_ios:
+        n = ffe_io.fe_sys.dof
+        if ffe_io in getattr(net, "_var_body_ffe_ios", []):
+            ffe_io.fe_sys.matl.check_limits(io[:, off: off + n])
+        off += n
 
 
 def simulate(net, time_span, rel_tol=1e-3, abs_tol=1e-6, method="RK45", num_res_skip=0, probe_dofs=(), **options):
