@@ -176,6 +176,11 @@ int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, co
                  const int32_t* col, const double* val, const double* mass, const double* adiag,
                  const double* rhs, double* x, double shift, double rtol, int32_t maxit, int32_t* iters);
 
+/* micro-benchmark: ns per grid barrier of an empty persistent kernel; mode 0 = reduce-barrier (csrc/gridbar.cuh)
+ * carrying K in {0,1,2} values, 1 = cooperative_groups grid.sync() */
+int tc_bar_bench(void* cuda_stream, int32_t blocks, int32_t threads, int32_t iters, int32_t K, int32_t mode,
+                 double* ns_per_barrier);
+
 /* ---- row-partitioned implicit step across GPUs (BASELINE config #5), csrc/dist.cu ------------
  * One process per GPU; the comm buffer of every rank is exported as a CUDA IPC handle and opened
  * by its peers; ghost values and the PCG scalar reductions then move by peer stores inside ONE

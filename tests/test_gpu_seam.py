@@ -81,6 +81,13 @@ def test_network_sim_on_device_matches_reference_solver(seam, name):
     fin = np.isfinite(b)
     assert np.array_equal(np.isfinite(a), fin)
     assert np.allclose(a[fin], b[fin], rtol=1e-7, atol=1e-4)
+    # per-step LP capacity / conductance matrices the post-processing reads (temperature dependent LP bodies: lp_tdep)
+    assert len(d.lp_M_diagss) == len(r.lp_M_diagss)
+    for md, mr, ld, lr in zip(d.lp_M_diagss, r.lp_M_diagss, d.lp_Lss, r.lp_Lss):
+        for a_, b_ in zip(md, mr):
+            assert np.allclose(a_, b_, rtol=1e-9, atol=0.0)
+        for a_, b_ in zip(ld, lr):
+            assert np.allclose(a_.data, b_.data, rtol=1e-8, atol=1e-12 * np.max(np.abs(b_.data)))
     # what the reference leaves on the Network after the solve
     assert net.time == pytest.approx(net_ref.time, rel=1e-12)
     assert np.allclose(net.capy, net_ref.capy, rtol=1e-9)

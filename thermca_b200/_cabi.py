@@ -77,6 +77,7 @@ EXPORTS = {
     "tc_sell_spmv": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32]),
     "tc_vm_eval": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "tc_pcg_solve": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32, C.POINTER(i32)]),
+    "tc_bar_bench": (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(f64)]),
     "tc_dist_create": (i32, [C.POINTER(vp), vp, i32, i32, i64, i64]),
     "tc_dist_ipc_handle": (i32, [vp, vp]),
     "tc_dist_open_peers": (i32, [vp, vp, C.POINTER(i64)]),

@@ -22,7 +22,7 @@ from .spec import state_offsets
 
 MEAN_ENTRIES_PER_BLOCK = 4096
 MEAN_MAX_BLOCKS_PER_JOB = 64
-VM_MAX = 512
+from .trace import MAX_PROGRAM as VM_MAX      # one limit: tracer, packer and csrc/vm.cuh (TC_VM_MAX)
 
 
 def _torch():

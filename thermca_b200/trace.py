@@ -41,7 +41,7 @@ OPS = [
     "ARCTAN2", "FMOD",
 ]
 OP = {n: i for i, n in enumerate(OPS)}
-MAX_PROGRAM = 1024
+MAX_PROGRAM = 512        # == TC_VM_MAX of csrc/vm.cuh (thermca_b200.device.VM_MAX is this constant)
 
 
 class UntraceableError(NotImplementedError):
@@ -384,25 +384,51 @@ def trace(func, n_args, inputs, tables, extra_args=(), input_objs=None, validate
 
 
 def _validate(func, prog, n_args, inputs, tables, extra_args, name):
-    """Evaluate the traced program on the host next to the callable itself on a few
-    sample temperatures; a mismatch means the trace missed a dependency."""
+    """Evaluate the traced program on the host next to the callable itself; a mismatch means the trace missed a
+    dependency, and a callable that cannot be probed is REJECTED (no silent pass).
+
+    Probes: the 4 fixed temperature pairs of round 1 plus 8 seeded random ones, each at two settings of the model's
+    ``Input`` values (as found, and scaled by 1.37 + 0.11 k) — the value arrays are shared with the ``Input``
+    elements, so writing them in place is what ``Input._set_time`` does at run time (thermca/input.py:127-146).
+    The callable is called sample by sample with 1-element arrays (so scalar ``if`` statements have a truth value
+    as they do at run time, thermca/lib/bearing.py:131, and element loops over ``empty_like`` buffers work,
+    free_conv.py:312-323).  What this cannot see: mutable state other than ``Input.value`` that the
+    callable captured (a list it appends to, a global it reads) is frozen at its trace-time value."""
     code, consts, result = prog.arrays()
-    in_vals = [float(np.asarray(a).reshape(-1)[0]) for a in inputs]
-    samples = np.array([[20.0, 35.0, 61.5, 90.0], [25.0, 20.0, 22.25, 40.0]])
+    rng = np.random.default_rng(20251020)
+    t0 = np.concatenate([[20.0, 35.0, 61.5, 90.0], rng.uniform(5.0, 150.0, 8)])
+    t1 = np.concatenate([[25.0, 20.0, 22.25, 40.0], rng.uniform(5.0, 150.0, 8)])
+    samples = [t0, t1]
+    m = len(t0)
     args = [samples[k % 2].copy() for k in range(n_args)]
-    with np.errstate(all="ignore"), warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        try:
-            ref = np.broadcast_to(np.asarray(func(*args, *extra_args), dtype=np.float64), (4,)) \
-                if n_args else np.broadcast_to(np.asarray(func(*extra_args), dtype=np.float64), (4,))
-        except Exception:
-            return          # the callable cannot be probed standalone; keep the trace
-        got = run_program(code, consts, result, args if n_args else [samples[0]], in_vals,
-                          tables.tables)
-    if not np.allclose(got, ref, rtol=1e-12, atol=0.0, equal_nan=True):
-        raise UntraceableError(
-            f"traced program of {name!r} disagrees with the callable ({got} vs {ref}); it "
-            "probably computes with captured state the tracer cannot see")
+    saved = [np.array(a, copy=True) for a in inputs]
+    try:
+        for setting in range(2 if inputs else 1):
+            if setting:
+                for k, a in enumerate(inputs):
+                    np.asarray(a)[...] = saved[k] * (1.37 + 0.11 * k) + 0.5 * (saved[k] == 0)
+            in_vals = [float(np.asarray(a).reshape(-1)[0]) for a in inputs]
+            ref = np.empty(m)
+            with np.errstate(all="ignore"), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for j in range(m):
+                    try:
+                        call = [np.array([a[j]]) for a in args]          # 1-element arrays: numpy semantics (nan, not
+                        # complex, for a negative base), len() works, and a scalar `if` still has a truth value
+                        ref[j] = float(np.asarray(func(*call, *extra_args), dtype=np.float64).reshape(-1)[0])
+                    except Exception as e:
+                        raise UntraceableError(
+                            f"callable {name!r} cannot be evaluated standalone for validation ({type(e).__name__}: {e}); "
+                            "its trace is not trusted") from e
+                got = run_program(code, consts, result, args if n_args else [samples[0]], in_vals, tables.tables)
+            if not np.allclose(got, ref, rtol=1e-12, atol=0.0, equal_nan=True):
+                bad = int(np.argmax(~np.isclose(got, ref, rtol=1e-12, atol=0.0, equal_nan=True)))
+                raise UntraceableError(
+                    f"traced program of {name!r} disagrees with the callable (sample {bad}: {got[bad]} vs {ref[bad]}, "
+                    f"Input setting {setting}); it probably computes with captured state the tracer cannot see")
+    finally:
+        for a, v in zip(inputs, saved):
+            np.asarray(a)[...] = v
 
 
 # ---- host interpreter (used by the CPU tests to check the tracer itself) --------
