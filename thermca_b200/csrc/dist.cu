@@ -220,8 +220,8 @@ __device__ __forceinline__ void init_row(const TcDistK& S, int i, double shift, 
     d = __ddiv_rn(1.0, __dmul_rn(m, __fma_rn(shift, S.adiag[i], 1.0)));
 }
 
-template <int MB>
-__global__ void __launch_bounds__(TC_DIST_THREADS, MB)
+template <int MB, int THREADS = TC_DIST_THREADS>
+__global__ void __launch_bounds__(THREADS, MB)
 tc_dist_theta_kernel(TcDistK S) {
     __shared__ double sh[32];
     const int n = S.n;
@@ -321,12 +321,23 @@ tc_dist_theta_kernel(TcDistK S) {
 }
 
 // ---- host ------------------------------------------------------------------------------------
+static int dist_threads() {
+    static int t = -1;
+    if (t < 0) {
+        const char* e = getenv("TC_PCG_THREADS");
+        t = e ? atoi(e) : TC_DIST_THREADS;
+        if (t != 256 && t != 512 && t != 1024) t = TC_DIST_THREADS;
+    }
+    return t;
+}
 static void* dist_fn() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("TC_PCG_OCC");
         v = e ? atoi(e) : 8;
     }
+    if (dist_threads() == 1024) return (void*)tc_dist_theta_kernel<2, 1024>;
+    if (dist_threads() == 512) return (void*)tc_dist_theta_kernel<4, 512>;
     switch (v) {
         case 5: return (void*)tc_dist_theta_kernel<5>;
         case 6: return (void*)tc_dist_theta_kernel<6>;
@@ -485,12 +496,12 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     double secs = to ? atof(to) : 20.0;
     if (!(secs > 0.0)) secs = 20.0;
     K.spin_limit = (long long)(secs * 1e3 * (double)khz);
-    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)dist_fn(), TC_DIST_THREADS, 0));
-    if (occ > 8) occ = 8;
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)dist_fn(), dist_threads(), 0));
+    if (occ > 2048 / dist_threads()) occ = 2048 / dist_threads();
     if (occ < 1) occ = 1;
     d->grid = occ * sms;
     if (d->grid > TC_MAX_PARTIALS) d->grid = TC_MAX_PARTIALS;
-    const int need = (nslices + 7) / 8;
+    const int need = (nslices + dist_threads() / 32 - 1) / (dist_threads() / 32);
     if (need < d->grid) d->grid = need > 0 ? need : 1;
     return 0;
 }
@@ -551,7 +562,7 @@ extern "C" int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, dou
     d->K.theta = theta; d->K.h = h; d->K.rtol = rtol; d->K.maxit = maxit;
     for (int k = 0; k < nsteps; ++k) {
         void* args[] = {(void*)&d->K};
-        TC_CUDA(cudaLaunchCooperativeKernel(dist_fn(), dim3(d->grid), dim3(TC_DIST_THREADS), args, 0, d->stream));
+        TC_CUDA(cudaLaunchCooperativeKernel(dist_fn(), dim3(d->grid), dim3(dist_threads()), args, 0, d->stream));
     }
     return 0;
 }

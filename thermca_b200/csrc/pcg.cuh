@@ -108,8 +108,8 @@ __device__ __forceinline__ unsigned long long tc_gtime() {
 // blocks hold bit-identical scalars and runs are reproducible.
 // Status (isc[4]): 0 converged, 1 iteration limit reached with r.r above the tolerance, 2 breakdown
 // (non-finite or non-positive p.q / r.r) — surfaced by tc_pcg_stats, checked by the host drivers.
-template <int MB>
-__global__ void __launch_bounds__(TC_PCG_THREADS, MB)
+template <int MB, int THREADS = TC_PCG_THREADS>
+__global__ void __launch_bounds__(THREADS, MB)
 tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;       // uniform over the grid
     if (S.skip && *S.skip) return;             // uniform over the grid

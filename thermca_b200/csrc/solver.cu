@@ -27,6 +27,7 @@ extern "C" const char* tc_last_error(void) { return g_err.c_str(); }
 extern "C" int tc_version(void) { return 100; }
 
 #define TC_PCG_DEFAULT_OCC 8
+#define TC_PCG_COOP_THREADS_DEFAULT 256
 static int pcg_coop_grid(int sm_count);
 
 // ---- control block layout (device) ------------------------------------------------------
@@ -771,7 +772,21 @@ static int pcg_occ_variant() {
     }
     return v;
 }
+// block shape of the cooperative kernel: 256 threads x 8 blocks/SM by default; TC_PCG_THREADS = 512 / 1024 selects
+// 4 / 2 blocks per SM (same warps per SM, fewer participants per grid barrier: profiles/README.md, barrier bench)
+static int pcg_coop_threads() {
+    static int t = -1;
+    if (t < 0) {
+        const char* e = getenv("TC_PCG_THREADS");
+        t = e ? atoi(e) : TC_PCG_COOP_THREADS_DEFAULT;
+        if (t != 256 && t != 512 && t != 1024) t = TC_PCG_COOP_THREADS_DEFAULT;
+    }
+    return t;
+}
 static void* pcg_coop_fn() {
+    const int t = pcg_coop_threads();
+    if (t == 1024) return (void*)tc_pcg_coop_kernel<2, 1024>;
+    if (t == 512) return (void*)tc_pcg_coop_kernel<4, 512>;
     switch (pcg_occ_variant()) {
         case 5: return (void*)tc_pcg_coop_kernel<5>;
         case 6: return (void*)tc_pcg_coop_kernel<6>;
@@ -780,8 +795,9 @@ static void* pcg_coop_fn() {
 }
 static int pcg_coop_grid(int sm_count) {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pcg_coop_fn(), TC_PCG_THREADS, 0);
-    if (occ > 8) occ = 8;
+    const int t = pcg_coop_threads();
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pcg_coop_fn(), t, 0);
+    if (occ > 2048 / t) occ = 2048 / t;
     if (occ < 1) occ = 1;
     int g = occ * sm_count;
     if (g > TC_MAX_PARTIALS) g = TC_MAX_PARTIALS;
@@ -796,14 +812,15 @@ static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int
     if (mode == TC_PCG_COOP) {
         void* args[] = {(void*)&P, (void*)&done};
         int g = coop_grid;
-        const int need = grid_for(P.A.nslices, TC_PCG_THREADS / 32, g);
+        const int cthreads = pcg_coop_threads();
+        const int need = grid_for(P.A.nslices, cthreads / 32, g);
         if (need < g) g = need;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (s && s->timing) {
             TC_CUDA(cudaEventCreate(&e0)); TC_CUDA(cudaEventCreate(&e1));
             TC_CUDA(cudaEventRecord(e0, st));
         }
-        TC_CUDA(cudaLaunchCooperativeKernel(pcg_coop_fn(), dim3(g), dim3(TC_PCG_THREADS), args, 0, st));
+        TC_CUDA(cudaLaunchCooperativeKernel(pcg_coop_fn(), dim3(g), dim3(cthreads), args, 0, st));
         if (e0) { TC_CUDA(cudaEventRecord(e1, st)); s->ev.push_back(e0); s->ev.push_back(e1); }
         if (s) s->launches += 1;
         return 0;
