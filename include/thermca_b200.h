@@ -177,7 +177,7 @@ int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, co
                  const double* rhs, double* x, double shift, double rtol, int32_t maxit, int32_t* iters);
 
 /* micro-benchmark: ns per grid barrier of an empty persistent kernel; mode 0 = reduce-barrier (csrc/gridbar.cuh)
- * carrying K in {0,1,2} values, 1 = cooperative_groups grid.sync() */
+ * carrying K in {0,1,2} values, 1 = cooperative_groups grid.sync(), 2 = last-arriver variant (K in {1,2}) */
 int tc_bar_bench(void* cuda_stream, int32_t blocks, int32_t threads, int32_t iters, int32_t K, int32_t mode,
                  double* ns_per_barrier);
 

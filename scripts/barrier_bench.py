@@ -8,7 +8,8 @@ st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 out = []
 for threads, bps in ((256, 8), (256, 4), (512, 4), (512, 2), (1024, 2), (1024, 1), (256, 1)):
     row = {"threads": threads, "blocks_per_sm": bps}
-    for name, K, mode in (("grid.sync", 0, 1), ("barrier", 0, 0), ("reduce1", 1, 0), ("reduce2", 2, 0)):
+    for name, K, mode in (("grid.sync", 0, 1), ("barrier", 0, 0), ("reduce1", 1, 0), ("reduce2", 2, 0),
+                          ("last1", 1, 2), ("last2", 2, 2)):
         ns = C.c_double()
         _cabi.check(lib.tc_bar_bench(st, 148 * bps, threads, 2000, K, mode, C.byref(ns)))
         row[name] = round(ns.value, 1)

@@ -8,8 +8,7 @@ namespace cg = cooperative_groups;
 
 template <int K, int MODE>
 __global__ void tc_bar_bench_kernel(TcGridBar B, int iters, double* sink) {
-    __shared__ double sh[32];
-    unsigned int gen = tc_bar_generation(B);
+    unsigned int gen = 0u, tgen = tc_bar_generation(B);
     double v[K > 0 ? K : 1];
     double acc = 0.0;
     cg::grid_group grid = cg::this_grid();
@@ -17,13 +16,15 @@ __global__ void tc_bar_bench_kernel(TcGridBar B, int iters, double* sink) {
         if (MODE == 1) { grid.sync(); continue; }
 #pragma unroll
         for (int k = 0; k < (K > 0 ? K : 1); ++k) v[k] = 1.0 + k;
-        tc_grid_reduce<K>(B, gen, v, sh);
+        if (MODE == 2) tc_grid_reduce_last<(K > 0 ? K : 1)>(B, tgen, v, [](double*, int) {});
+        else tc_grid_reduce<K>(B, gen, v);
         acc += v[0];
     }
     if (sink && blockIdx.x == 0 && threadIdx.x == 0) sink[0] = acc;
 }
 
-// ns per barrier; mode 0 = reduce-barrier with K values (0, 1, 2), 1 = cooperative_groups grid.sync()
+// ns per barrier; mode 0 = reduce-barrier with K values (0, 1, 2), 1 = cooperative_groups grid.sync(),
+// 2 = last-arriver variant (K = 1, 2) with an empty exchange hook
 extern "C" int tc_bar_bench(void* cuda_stream, int32_t blocks, int32_t threads, int32_t iters, int32_t K, int32_t mode,
                             double* ns_per_barrier) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -31,10 +32,11 @@ extern "C" int tc_bar_bench(void* cuda_stream, int32_t blocks, int32_t threads, 
     TcGridBar B{};
     TC_CUDA(cudaMalloc(&B.ctr, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
     TC_CUDA(cudaMemset(B.ctr, 0, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
-    TC_CUDA(cudaMalloc(&B.part, sizeof(double) * TC_BAR_MAXK * TC_MAX_PARTIALS));
+    TC_CUDA(cudaMalloc(&B.part, sizeof(double) * TC_BAR_PART_DOUBLES));
     TC_CUDA(cudaMalloc(&B.res, sizeof(double) * 2 * TC_BAR_MAXK + 8));
     double* sink = B.res + 2 * TC_BAR_MAXK;
     void* fn = mode == 1 ? (void*)tc_bar_bench_kernel<0, 1>
+               : mode == 2 ? (K <= 1 ? (void*)tc_bar_bench_kernel<1, 2> : (void*)tc_bar_bench_kernel<2, 2>)
                : K == 0 ? (void*)tc_bar_bench_kernel<0, 0> : K == 1 ? (void*)tc_bar_bench_kernel<1, 0>
                                                                     : (void*)tc_bar_bench_kernel<2, 0>;
     cudaEvent_t e0, e1;

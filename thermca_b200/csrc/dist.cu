@@ -226,7 +226,7 @@ tc_dist_theta_kernel(TcDistK S) {
     __shared__ double sh[32];
     const int n = S.n;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    unsigned int gen = tc_bar_generation(S.bar);
+    unsigned int gen = 0u, tgen = tc_bar_generation(S.bar);
     int rseq = S.state[0], hseq = S.state[1];
     PROF_INIT();
     const double shift = S.theta * S.h;
@@ -237,11 +237,11 @@ tc_dist_theta_kernel(TcDistK S) {
     if (S.n_nbr > 0) {
         for (long long e = gtid; e < S.n_send; e += gsz) S.peer_y[S.send_peer[e]][S.send_dst[e]] = y_loc[S.send_row[e]];
         __threadfence_system();
-        tc_grid_barrier(S.bar, gen, sh);
+        tc_grid_barrier(S.bar, gen);
         raise_halo_flags(S, ++hseq);
     }
     slab_spmv<SPMV_B>(S, S.y_ext, S.q, S.b, 0.0, hseq);
-    tc_grid_barrier(S.bar, gen, sh);
+    tc_grid_barrier(S.bar, gen);
     double red[TC_DIST_K];
     {
         double* p0 = S.p_ext[0];
@@ -262,7 +262,7 @@ tc_dist_theta_kernel(TcDistK S) {
         if (S.n_send > 0) __threadfence_system();
         red[0] = block_sum(rho_l, sh); red[1] = block_sum(bb_l, sh); red[2] = 0.0;
     }
-    tc_grid_reduce<2>(S.bar, gen, red, sh, TcDistExchange{S, ++rseq});
+    tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
     double rho = red[0];
     const double bb = red[1];
     const double tol2 = S.rtol * S.rtol * bb;
@@ -277,7 +277,7 @@ tc_dist_theta_kernel(TcDistK S) {
             PROF(1);
             red[0] = block_sum(dot, sh);
             PROF(2);
-            tc_grid_reduce<1>(S.bar, gen, red, sh, TcDistExchange{S, ++rseq});
+            tc_grid_reduce_last<1>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
             PROF(3);
             const double pq = red[0];
             if (!(pq > 0.0) || !isfinite(pq)) { status = 2; break; }       // uniform over the grid AND over the ranks
@@ -292,7 +292,7 @@ tc_dist_theta_kernel(TcDistK S) {
             }
             red[0] = block_sum(rn, sh); red[1] = block_sum(rr, sh);
             PROF(4);
-            tc_grid_reduce<2>(S.bar, gen, red, sh, TcDistExchange{S, ++rseq});
+            tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
             PROF(5);
             ++it;
             if (!(red[1] > tol2)) { status = isfinite(red[1]) ? 0 : 2; break; }
@@ -307,7 +307,7 @@ tc_dist_theta_kernel(TcDistK S) {
             rho = red[0];
             pb ^= 1;
             PROF(6);
-            tc_grid_barrier(S.bar, gen, sh);
+            tc_grid_barrier(S.bar, gen);
             PROF(7);
         }
     }
@@ -392,7 +392,7 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     TC_CUDA(cudaMemset(d->prof, 0, sizeof(unsigned long long) * 32));
     TC_CUDA(cudaMalloc(&d->K.bar.ctr, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
     TC_CUDA(cudaMemset(d->K.bar.ctr, 0, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
-    TC_CUDA(cudaMalloc(&d->K.bar.part, sizeof(double) * TC_BAR_MAXK * TC_MAX_PARTIALS));
+    TC_CUDA(cudaMalloc(&d->K.bar.part, sizeof(double) * TC_BAR_PART_DOUBLES));
     TC_CUDA(cudaMalloc(&d->K.bar.res, sizeof(double) * 2 * TC_BAR_MAXK));
     TC_CUDA(cudaMemset(d->K.bar.res, 0, sizeof(double) * 2 * TC_BAR_MAXK));
     d->peer[rank] = d->comm;

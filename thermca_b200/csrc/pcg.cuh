@@ -114,7 +114,7 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     if (done_flag && *done_flag) return;       // uniform over the grid
     if (S.skip && *S.skip) return;             // uniform over the grid
     __shared__ double sh[32];
-    unsigned int gen = tc_bar_generation(S.bar);
+    unsigned int gen = 0u;
     const double shift = S.coef * S.ctrl[1];
     unsigned long long prof_t = (S.prof && blockIdx.x == 0 && threadIdx.x == 0) ? tc_gtime() : 0ULL;
     double red[2];
@@ -132,7 +132,7 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
         red[0] = block_sum(rho, sh);
         red[1] = block_sum(bb, sh);
     }
-    tc_grid_reduce<2>(S.bar, gen, red, sh);
+    tc_grid_reduce<2>(S.bar, gen, red);
     double rho = red[0];
     const double bb = red[1];
     const double tol2 = S.rtol * S.rtol * bb;
@@ -144,7 +144,7 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
             const double dot = tc_sell_spmv_body<SPMV_SHIFT, 0>(S.A, S.p, S.q, nullptr, S.mass, shift);
             PCG_PROF(1);
             red[0] = block_sum(dot, sh);
-            tc_grid_reduce<1>(S.bar, gen, red, sh);
+            tc_grid_reduce<1>(S.bar, gen, red);
             PCG_PROF(2);
             const double pq = red[0];
             if (!(pq > 0.0) || !isfinite(pq)) { status = 2; break; }     // uniform: every block holds the same pq
@@ -164,7 +164,7 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
                 red[1] = block_sum(rr, sh);
             }
             PCG_PROF(3);
-            tc_grid_reduce<2>(S.bar, gen, red, sh);
+            tc_grid_reduce<2>(S.bar, gen, red);
             PCG_PROF(4);
             const double rho_new = red[0], rr = red[1];
             ++it;
@@ -172,7 +172,7 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
             tc_pcg_dir_phase(S, rho_new / rho);
             rho = rho_new;
             PCG_PROF(5);
-            tc_grid_barrier(S.bar, gen, sh);
+            tc_grid_barrier(S.bar, gen);
             PCG_PROF(6);
         }
     }

@@ -344,7 +344,7 @@ extern "C" int tc_create(tc_handle* out, void* cuda_stream) {
     TC_CUDA(cudaMemset(s->pcg_prof, 0, sizeof(unsigned long long) * 16));
     TC_CUDA(cudaMalloc(&s->bar.ctr, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
     TC_CUDA(cudaMemset(s->bar.ctr, 0, sizeof(unsigned int) * TC_BAR_CTR_WORDS));
-    TC_CUDA(cudaMalloc(&s->bar.part, sizeof(double) * TC_BAR_MAXK * TC_MAX_PARTIALS));
+    TC_CUDA(cudaMalloc(&s->bar.part, sizeof(double) * TC_BAR_PART_DOUBLES));
     TC_CUDA(cudaMalloc(&s->bar.res, sizeof(double) * 2 * TC_BAR_MAXK));
     TC_CUDA(cudaMemset(s->bar.res, 0, sizeof(double) * 2 * TC_BAR_MAXK));
     TC_CUDA(cudaMallocHost(&s->pin_flags, sizeof(int) * 32));
@@ -1314,7 +1314,7 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     TcPcg P{};
     P.A = TcSell{n, nslices, (const long long*)slice_ptr, col, val, nullptr};
     // one scratch allocation: 4 vectors | partial banks + scalars + ctrl | barrier banks + totals | ints
-    const size_t n_aux = 4 * TC_MAX_PARTIALS + 20, n_bar = TC_BAR_MAXK * TC_MAX_PARTIALS + 2 * TC_BAR_MAXK;
+    const size_t n_aux = 4 * TC_MAX_PARTIALS + 20, n_bar = TC_BAR_PART_DOUBLES + 2 * TC_BAR_MAXK;
     const size_t n_dbl = 4 * (size_t)n + n_aux + n_bar;
     char* blob = nullptr;
     TC_CUDA(cudaMalloc(&blob, sizeof(double) * n_dbl + sizeof(int) * (16 + TC_BAR_CTR_WORDS)));
@@ -1322,7 +1322,7 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
                             sizeof(double) * (n_aux + n_bar) + sizeof(int) * (16 + TC_BAR_CTR_WORDS), tmp.stream));
     double* ws = (double*)blob;
     double* aux = ws + 4 * (size_t)n;
-    P.bar.part = aux + n_aux; P.bar.res = P.bar.part + TC_BAR_MAXK * TC_MAX_PARTIALS;
+    P.bar.part = aux + n_aux; P.bar.res = P.bar.part + TC_BAR_PART_DOUBLES;
     int* isc = (int*)(blob + sizeof(double) * n_dbl);
     P.bar.ctr = (unsigned int*)(isc + 16);
     const double c[4] = {0.0, 1.0, 0.0, 0.0};
