@@ -187,16 +187,17 @@ int tc_bar_bench(void* cuda_stream, int32_t blocks, int32_t threads, int32_t ite
  * cooperative kernel per theta step (no NCCL call on the data path).  The reference has no
  * multi-process code; per rank this is thermca/solver.py:265-281 (right-hand side
  * of a full-order FE part) plus the implicit solve on the local rows.
- * Vectors are "extended": [n_loc local rows | n_ghost ghost slots]; operator columns index that vector.
+ * Operator columns: < n_loc = local row, >= n_loc = ghost slot + n_loc.  Ghost values and reduction mailboxes are
+ * "LL" encoded in the exported buffer (every 8-byte granule carries a sequence tag): no flags, no system fences.
  * Calls return 0, or a negative code with tc_last_error(): -3 = a wait on a peer timed out
  * (TC_DIST_TIMEOUT_S seconds, default 20), -4 = PCG iteration limit / breakdown. */
 typedef struct tc_dist tc_dist;
 int tc_dist_create(tc_dist** out, void* cuda_stream, int32_t rank, int32_t world, int64_t n_loc, int64_t n_ghost);
 int tc_dist_ipc_handle(tc_dist* d, void* handle64);
-/* handles: world x 64 bytes; peer_ext[w] = n_loc + n_ghost of rank w */
-int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_ext);
-/* halo plan (host arrays, copied): entry e sends local row send_row[e] to slot send_dst[e] of the extended
- * vectors of rank send_peer[e]; nbr = ranks this rank trades ghosts with */
+/* handles: world x 64 bytes; peer_ghost[w] = ghost count of rank w */
+int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_ghost);
+/* halo plan (host arrays, copied): entry e sends local row send_row[e] to ghost slot send_dst[e] of rank
+ * send_peer[e]; nbr = ranks this rank trades ghosts with */
 int tc_dist_set_halo(tc_dist* d, int64_t n_send, const int32_t* send_row, const int32_t* send_peer,
                      const int64_t* send_dst, int32_t n_nbr, const int32_t* nbr);
 /* SELL-32 operator of the local rows (device pointers, kept by reference); col16 (optional) = column - row of

@@ -4,15 +4,16 @@
 //   * ghost values of the gathered vector are written straight into the peers' HBM with peer
 //     stores over NVLink (no NCCL call, no host round trip), driven by send lists, so any
 //     partition works (contiguous slabs of a banded ordering give rank +-1 neighbours, a general
-//     partition any neighbour set);
+//     partition any neighbour set); every value carries its own sequence tag ("LL" encoding), so
+//     there are no halo flags and no system-scope fences on the critical path;
 //   * every PCG reduction is folded into a grid barrier (gridbar.cuh) whose last-arriving block
 //     also trades the local sums with all peers through per-rank mailboxes and adds them in rank
 //     order: one barrier == one global all-reduce, bit-identical scalars on all ranks ->
 //     identical convergence decisions, deterministic results;
 //   * the search direction is double buffered, so the rows a peer needs are recomputed from
 //     stable inputs by the pushing threads (no intra-phase race, no extra barrier) and the push
-//     overlaps the vector phase; the product runs interior slices first and waits for the
-//     neighbours' flags only before the few boundary slices.
+//     overlaps the vector phase; the product runs interior slices first and touches ghosts only
+//     in the few boundary slices at the end of every warp's share.
 // Peer memory is exchanged once at setup as CUDA IPC handles (plumbing via torch.distributed in
 // thermca_b200/dist.py).  The reference has nothing comparable (no multi-process code, SURVEY.md
 // fact 1); per rank the arithmetic is the single-GPU PCG of pcg.cuh on the local rows.
@@ -30,24 +31,30 @@
 
 #define TC_MAX_WORLD 16
 #define TC_DIST_K 3                     // values per all-reduce
+#define TC_MB_SLOT 8                    // u64 granules per (parity, sender) mailbox slot (2 per value, padded to 64 B)
 
+typedef unsigned long long u64;
+
+// Everything that crosses NVLink is "LL" encoded (the scheme of NCCL's low-latency protocol): a double travels as two
+// 8-byte granules {32 data bits | 32-bit sequence tag}.  8-byte stores are single-copy atomic, so a reader that finds
+// the expected tag in a granule also has its data: no flag, no system-scope fence on the sender (a MEMBAR.SYS would
+// wait for the remote acknowledgements, i.e. a full NVLink round trip on the critical path), and every ghost value is
+// usable the moment it lands.  Tags are monotonic sequence numbers (halo: hseq, reductions: rseq).
 struct TcDistK {
-    TcSell A;                             // local rows; col16 relative to the row (interior slices), col = index
-                                          // into the extended vector [n local | n_ghost ghosts] (boundary slices)
+    TcSell A;                             // local rows; col16 relative to the row (interior slices), col (boundary
+                                          // slices): < n local row, >= n ghost slot (col - n)
     int n, n_ghost, rank, world;
     int n_bnd;                            // boundary slices (reference at least one ghost column)
     const int* order;                     // nslices: interior slices first, boundary slices last
     const double *b, *mass, *adiag;
-    double *y_ext, *p_ext[2];             // [n | n_ghost] each, inside the exported buffer
+    double *y, *p[2];                     // local vectors (n each); the search direction is double buffered
     double *x, *r, *q, *dinv;
-    long long n_send;                     // halo send list: local row -> (peer, slot in the peer's extended vector)
+    u64 *y_gl, *p_gl[2];                  // my ghost values, LL encoded: 2 granules per ghost slot (exported memory)
+    long long n_send;                     // halo send list: local row -> (peer, ghost slot of the peer)
     const int* send_row; const int* send_peer; const long long* send_dst;
-    double* peer_y[TC_MAX_WORLD]; double* peer_p[2][TC_MAX_WORLD];
-    int* peer_hflag[TC_MAX_WORLD];        // peers' halo flag arrays (I write entry [rank])
-    int n_nbr; int nbr[TC_MAX_WORLD];     // ranks I trade ghosts with
-    int* my_hflag;                        // [TC_MAX_WORLD], entry w written by rank w
-    double* peer_mb[TC_MAX_WORLD]; int* peer_mbf[TC_MAX_WORLD];
-    double* my_mb; int* my_mbf;           // mb[2][TC_DIST_K][MAXW], mbf[2][MAXW]
+    u64* peer_y_gl[TC_MAX_WORLD]; u64* peer_p_gl[2][TC_MAX_WORLD];
+    int n_nbr;                            // ranks I trade ghosts with (only its being non-zero matters to the kernel)
+    u64* peer_mb[TC_MAX_WORLD]; u64* my_mb;      // mailboxes [2 parities][TC_MAX_WORLD senders][TC_MB_SLOT]
     TcGridBar bar;
     int* state;                           // [0] reduction seq, [1] halo seq, [2] iters last, [3] iters total,
                                           // [4] comm error, [5] solves, [7] status of the last failed solve, [8] failed solves
@@ -57,53 +64,62 @@ struct TcDistK {
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
 };
 
-__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
-    int v;
-    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ u64 ld_relaxed_sys_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(u64* p, u64 v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// bounded wait; on timeout (or when another thread of this rank already gave up) raises the error flag.
-// Relaxed polls + ONE acquire fence at the end: an acquire load per poll would invalidate this SM's L1 on every
-// iteration while co-resident warps are still gathering through it.
-__device__ __forceinline__ void spin_until(const int* flag, int seq, int* err, long long limit) {
-    if (ld_relaxed_sys(flag) < seq) {
-        const long long t0 = clock64();
-        while (ld_relaxed_sys(flag) < seq) {
-            if (*((volatile int*)err)) return;
-            if (clock64() - t0 > limit) { *((volatile int*)err) = 1; __threadfence(); return; }
-        }
+__device__ __forceinline__ void ll_store(u64* g, double v, unsigned int tag) {
+    const u64 bits = (u64)__double_as_longlong(v);
+    st_relaxed_sys_u64(g, ((u64)tag << 32) | (bits & 0xffffffffULL));
+    st_relaxed_sys_u64(g + 1, ((u64)tag << 32) | (bits >> 32));
+}
+// bounded wait for one granule; on timeout (or when another thread of this rank already gave up) raises the error flag
+__device__ __forceinline__ u64 ll_wait(const u64* g, unsigned int tag, int* err, long long limit) {
+    u64 v = ld_relaxed_sys_u64(g);
+    if ((unsigned int)(v >> 32) == tag) return v;
+    const long long t0 = clock64();
+    for (;;) {
+        v = ld_relaxed_sys_u64(g);
+        if ((unsigned int)(v >> 32) == tag) return v;
+        if (*((volatile int*)err)) return v;
+        if (clock64() - t0 > limit) { *((volatile int*)err) = 1; __threadfence(); return v; }
     }
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+__device__ __forceinline__ double ll_load(const u64* g, unsigned int tag, int* err, long long limit) {
+    const u64 lo = ll_wait(g, tag, err, limit), hi = ll_wait(g + 1, tag, err, limit);
+    return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffULL)));
 }
 
-// All-reduce of the local totals, run by the last block to reach the grid barrier (gridbar.cuh hook).
-// Thread w < world writes my values into peer w's mailbox (parity double buffered, sequence tagged) and
-// waits for peer w's values in mine; thread 0 then adds the world's values in rank order.
+// All-reduce of the local totals, run by the last block to reach the grid barrier (gridbar.cuh hook): thread w < world
+// writes my values into rank w's mailbox and waits for rank w's values in mine; thread 0 adds them in rank order, so
+// every rank gets bit-identical totals.  A rank whose error flag is up contributes NaN: every rank then leaves the
+// iteration in this very reduction.
 struct TcDistExchange {
     const TcDistK& S;
     int seq;
     __device__ __forceinline__ void operator()(double* tot, int K) const {
         if (S.world == 1) return;
+        __shared__ double s_in[TC_MAX_WORLD][TC_DIST_K];
         const int par = seq & 1;
         int* err = S.state + 4;
-        if (threadIdx.x < S.world) {
+        if ((int)threadIdx.x < S.world) {
             const int peer = threadIdx.x;
             const bool bad = *((volatile int*)err) != 0;
-            volatile double* mb = S.peer_mb[peer];
-            for (int k = 0; k < K; ++k) mb[(par * TC_DIST_K + k) * TC_MAX_WORLD + S.rank] = bad ? nan("") : tot[k];
-            st_release_sys(S.peer_mbf[peer] + par * TC_MAX_WORLD + S.rank, seq);     // orders the stores above
-            spin_until(S.my_mbf + par * TC_MAX_WORLD + peer, seq, err, S.spin_limit);
+            u64* out = S.peer_mb[peer] + ((size_t)par * TC_MAX_WORLD + S.rank) * TC_MB_SLOT;
+            for (int k = 0; k < K; ++k) ll_store(out + 2 * k, bad ? nan("") : tot[k], (unsigned int)seq);
+            const u64* in = S.my_mb + ((size_t)par * TC_MAX_WORLD + peer) * TC_MB_SLOT;
+            for (int k = 0; k < K; ++k) s_in[peer][k] = ll_load(in + 2 * k, (unsigned int)seq, err, S.spin_limit);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             const bool bad = *((volatile int*)err) != 0;
-            volatile double* mine = S.my_mb;
             for (int k = 0; k < K; ++k) {
                 double s = 0.0;
-                for (int w = 0; w < S.world; ++w) s += mine[(par * TC_DIST_K + k) * TC_MAX_WORLD + w];
+                for (int w = 0; w < S.world; ++w) s += s_in[w][k];
                 tot[k] = bad ? nan("") : s;
             }
         }
@@ -111,44 +127,39 @@ struct TcDistExchange {
     }
 };
 
-#define TC_DIST_THREADS 256
+#define TC_DIST_THREADS 1024
 
-// Local rows times the extended vector, interior slices first (16-bit relative or 32-bit local columns, gathered
-// through L1) and the boundary slices LAST in every warp's grid-stride sequence: a warp waits for the neighbours'
-// halo flags only when it reaches its first boundary slice (by then the interior part has hidden the NVLink
-// latency) and reads the gathered vector of boundary slices through L2 (ld.global.cg: ghosts were written by
-// another GPU, the local L1 may hold stale lines).
+// Local rows times [local vector | ghosts], interior slices first (16-bit relative or 32-bit local columns) and the
+// boundary slices LAST in every warp's grid-stride sequence, so the ghost values have had the whole interior pass to
+// cross NVLink; a ghost that is still missing is waited for individually (LL tag), there is no halo flag.
 template <int MODE>
-__device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xe, double* y, const double* b,
-                                            double shift, int hseq) {
+__device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, const u64* xg, double* y,
+                                            const double* b, double shift, unsigned int hseq) {
     const TcSell& A = S.A;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * warps_per_block;
-    const int nsl = A.nslices, n_int = nsl - S.n_bnd;
-    bool waited = false;
+    const int nsl = A.nslices, n_int = nsl - S.n_bnd, n = S.n;
     double dot = 0.0;
     for (int idx = warp; idx < nsl; idx += nwarps) {
         const bool boundary = idx >= n_int;
         const int s = S.order ? S.order[idx] : idx;
-        if (boundary && !waited) {
-            if (lane == 0)
-                for (int k = 0; k < S.n_nbr; ++k) spin_until(S.my_hflag + S.nbr[k], hseq, S.state + 4, S.spin_limit);
-            __syncwarp();
-            waited = true;
-        }
         const long long base = A.slice_ptr[s];
         const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
         const double* v = A.val + base + lane;
         double sum = 0.0;
         if (boundary) {
             const int* c = A.col + base + lane;
-            for (int k = 0; k < width; ++k)
-                sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<2>(xe + ld_stream_s32(c + 32 * k))));
+            for (int k = 0; k < width; ++k) {
+                const int cc = ld_stream_s32(c + 32 * k);
+                const double xv = cc < n ? tc_ld_x<0>(xl + cc)
+                                         : ll_load(xg + 2 * (size_t)(cc - n), hseq, S.state + 4, S.spin_limit);
+                sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), xv));
+            }
         } else if (A.col16) {
             const short* c = A.col16 + base + lane;
-            const double* xr0 = xe + (s * 32 + lane);
+            const double* xr0 = xl + (s * 32 + lane);
             int k = 0;
             for (; k + 4 <= width; k += 4) {
                 const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
@@ -171,21 +182,21 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xe, 
                 const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
                 const int c0 = ld_stream_s32(c + 32 * (k + 0)), c1 = ld_stream_s32(c + 32 * (k + 1));
                 const int c2 = ld_stream_s32(c + 32 * (k + 2)), c3 = ld_stream_s32(c + 32 * (k + 3));
-                const double x0 = tc_ld_x<0>(xe + c0), x1 = tc_ld_x<0>(xe + c1), x2 = tc_ld_x<0>(xe + c2), x3 = tc_ld_x<0>(xe + c3);
+                const double x0 = tc_ld_x<0>(xl + c0), x1 = tc_ld_x<0>(xl + c1), x2 = tc_ld_x<0>(xl + c2), x3 = tc_ld_x<0>(xl + c3);
                 sum = __dadd_rn(sum, __dmul_rn(v0, x0));
                 sum = __dadd_rn(sum, __dmul_rn(v1, x1));
                 sum = __dadd_rn(sum, __dmul_rn(v2, x2));
                 sum = __dadd_rn(sum, __dmul_rn(v3, x3));
             }
             for (; k < width; ++k)
-                sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xe + ld_stream_s32(c + 32 * k))));
+                sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xl + ld_stream_s32(c + 32 * k))));
         }
         const int row = s * 32 + lane;
         if (row < A.n) {
             if (MODE == SPMV_B) {
                 y[row] = __dsub_rn(b[row], sum);
             } else {
-                const double xr = tc_ld_x<0>(xe + row);
+                const double xr = tc_ld_x<0>(xl + row);
                 const double q = S.mass[row] * (xr + shift * sum);
                 y[row] = q;
                 dot += xr * q;
@@ -206,12 +217,6 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define PROF(k) do { if (prof_row >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
     S.prof[prof_row * 16 + (k)] += t_ - prof_t; prof_t = t_; } } while (0)
 
-// after a barrier that ordered this rank's ghost pushes: tell every neighbour that halo `hseq` has landed
-__device__ __forceinline__ void raise_halo_flags(const TcDistK& S, int hseq) {
-    if (blockIdx.x == 0 && (int)threadIdx.x < S.n_nbr)
-        st_release_sys(S.peer_hflag[S.nbr[threadIdx.x]] + S.rank, hseq);
-}
-
 // scaled right-hand side and Jacobi factor of one row (explicit roundings: the owner's loop and the halo push
 // must produce the same bits)
 __device__ __forceinline__ void init_row(const TcDistK& S, int i, double shift, double& bsc, double& d) {
@@ -227,25 +232,29 @@ tc_dist_theta_kernel(TcDistK S) {
     const int n = S.n;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     unsigned int gen = 0u, tgen = tc_bar_generation(S.bar);
-    int rseq = S.state[0], hseq = S.state[1];
+    int rseq = S.state[0];
+    unsigned int hseq = (unsigned int)S.state[1];
     PROF_INIT();
     const double shift = S.theta * S.h;
-    double* y_loc = S.y_ext;
     int pb = 0;
 
     // ---- right-hand side f = b - A y (thermca/solver.py:281) on the local rows -----------------
-    if (S.n_nbr > 0) {
-        for (long long e = gtid; e < S.n_send; e += gsz) S.peer_y[S.send_peer[e]][S.send_dst[e]] = y_loc[S.send_row[e]];
-        __threadfence_system();
-        tc_grid_barrier(S.bar, gen);
-        raise_halo_flags(S, ++hseq);
-    }
-    slab_spmv<SPMV_B>(S, S.y_ext, S.q, S.b, 0.0, hseq);
+    ++hseq;
+    for (long long e = gtid; e < S.n_send; e += gsz)
+        ll_store(S.peer_y_gl[S.send_peer[e]] + 2 * S.send_dst[e], S.y[S.send_row[e]], hseq);
+    slab_spmv<SPMV_B>(S, S.y, S.y_gl, S.q, S.b, 0.0, hseq);
     tc_grid_barrier(S.bar, gen);
     double red[TC_DIST_K];
+    ++hseq;
     {
-        double* p0 = S.p_ext[0];
+        double* p0 = S.p[0];
         double rho_l = 0.0, bb_l = 0.0;
+        // rows a peer needs first: recomputed from the same stable inputs (bit-identical), pushed over NVLink
+        for (long long e = gtid; e < S.n_send; e += gsz) {
+            double bsc, d;
+            init_row(S, S.send_row[e], shift, bsc, d);
+            ll_store(S.peer_p_gl[0][S.send_peer[e]] + 2 * S.send_dst[e], __dmul_rn(d, bsc), hseq);
+        }
         for (int i = gtid; i < n; i += gsz) {
             double bsc, d;
             init_row(S, i, shift, bsc, d);
@@ -253,13 +262,6 @@ tc_dist_theta_kernel(TcDistK S) {
             S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; p0[i] = z;
             rho_l += bsc * z; bb_l += bsc * bsc;
         }
-        // rows a peer needs: recomputed from the same stable inputs (bit-identical), pushed over NVLink
-        for (long long e = gtid; e < S.n_send; e += gsz) {
-            double bsc, d;
-            init_row(S, S.send_row[e], shift, bsc, d);
-            S.peer_p[0][S.send_peer[e]][S.send_dst[e]] = __dmul_rn(d, bsc);
-        }
-        if (S.n_send > 0) __threadfence_system();
         red[0] = block_sum(rho_l, sh); red[1] = block_sum(bb_l, sh); red[2] = 0.0;
     }
     tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
@@ -271,9 +273,8 @@ tc_dist_theta_kernel(TcDistK S) {
         status = 1;
         for (; it < S.maxit;) {
             PROF(0);
-            raise_halo_flags(S, ++hseq);          // ghost pushes of p[pb] were fenced before the last barrier
-            const double* pe = S.p_ext[pb];
-            const double dot = slab_spmv<SPMV_SHIFT>(S, pe, S.q, nullptr, shift, hseq);
+            const double* pe = S.p[pb];
+            const double dot = slab_spmv<SPMV_SHIFT>(S, pe, S.p_gl[pb], S.q, nullptr, shift, hseq);
             PROF(1);
             red[0] = block_sum(dot, sh);
             PROF(2);
@@ -297,13 +298,15 @@ tc_dist_theta_kernel(TcDistK S) {
             ++it;
             if (!(red[1] > tol2)) { status = isfinite(red[1]) ? 0 : 2; break; }
             const double beta = red[0] / rho;
-            double* pn = S.p_ext[pb ^ 1];
-            for (int i = gtid; i < n; i += gsz) pn[i] = __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i]));
+            double* pn = S.p[pb ^ 1];
+            ++hseq;
+            // ghost rows first, so they are in flight while the local rows are updated
             for (long long e = gtid; e < S.n_send; e += gsz) {
                 const int i = S.send_row[e];
-                S.peer_p[pb ^ 1][S.send_peer[e]][S.send_dst[e]] = __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i]));
+                ll_store(S.peer_p_gl[pb ^ 1][S.send_peer[e]] + 2 * S.send_dst[e],
+                         __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i])), hseq);
             }
-            if (S.n_send > 0) __threadfence_system();
+            for (int i = gtid; i < n; i += gsz) pn[i] = __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i]));
             rho = red[0];
             pb ^= 1;
             PROF(6);
@@ -313,9 +316,9 @@ tc_dist_theta_kernel(TcDistK S) {
     }
     // ---- y += h * z (not committed after a communication failure / breakdown) ------------------
     if (status != 2)
-        for (int i = gtid; i < n; i += gsz) y_loc[i] += S.h * S.x[i];
+        for (int i = gtid; i < n; i += gsz) S.y[i] += S.h * S.x[i];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        S.state[0] = rseq; S.state[1] = hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
+        S.state[0] = rseq; S.state[1] = (int)hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
         if (status) { S.state[7] = status; S.state[8] += 1; }
     }
 }
@@ -331,28 +334,21 @@ static int dist_threads() {
     return t;
 }
 static void* dist_fn() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("TC_PCG_OCC");
-        v = e ? atoi(e) : 8;
-    }
-    if (dist_threads() == 1024) return (void*)tc_dist_theta_kernel<2, 1024>;
+    // 2 blocks x 1024 threads per SM by default (fewer barrier participants, profiles/README.md); TC_PCG_THREADS=512/256
     if (dist_threads() == 512) return (void*)tc_dist_theta_kernel<4, 512>;
-    switch (v) {
-        case 5: return (void*)tc_dist_theta_kernel<5>;
-        case 6: return (void*)tc_dist_theta_kernel<6>;
-        default: return (void*)tc_dist_theta_kernel<8>;
-    }
+    if (dist_threads() == 256) return (void*)tc_dist_theta_kernel<8, 256>;
+    return (void*)tc_dist_theta_kernel<2, 1024>;
 }
 
 struct tc_dist {
     cudaStream_t stream;
     int rank, world;
     long long n, n_ghost;
-    char* comm = nullptr;             // my exported buffer
+    char* comm = nullptr;             // my exported buffer: LL ghost arrays + mailboxes
     size_t comm_bytes = 0;
     char* peer[TC_MAX_WORLD];
-    long long peer_ext[TC_MAX_WORLD]; // n + n_ghost of every rank (fixes the layout of its buffer)
+    long long peer_ghost[TC_MAX_WORLD];   // ghost count of every rank (fixes the layout of its buffer)
+    double *y = nullptr, *p0 = nullptr, *p1 = nullptr;
     double *x = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr;
     int* state = nullptr;
     unsigned long long* prof = nullptr;
@@ -363,12 +359,11 @@ struct tc_dist {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-// layout of a rank's exported buffer: [y_ext | p_ext0 | p_ext1 | mailbox | mailbox flags | halo flags]
-static size_t ext_bytes(long long ext) { return align_up((size_t)ext * sizeof(double), 256); }
-static size_t off_p(long long ext, int k) { return (size_t)(1 + k) * ext_bytes(ext); }
-static size_t off_mb(long long ext) { return 3 * ext_bytes(ext); }
-static size_t off_mbf(long long ext) { return off_mb(ext) + align_up(sizeof(double) * 2 * TC_DIST_K * TC_MAX_WORLD, 256); }
-static size_t off_hf(long long ext) { return off_mbf(ext) + align_up(sizeof(int) * 2 * TC_MAX_WORLD, 256); }
+// layout of a rank's exported buffer: [y ghosts | p ghosts 0 | p ghosts 1 | mailboxes], ghosts LL encoded (16 B each)
+static size_t gl_bytes(long long n_ghost) { return align_up((size_t)(n_ghost > 0 ? n_ghost : 1) * 2 * sizeof(u64), 256); }
+static size_t off_gl(long long n_ghost, int k) { return (size_t)k * gl_bytes(n_ghost); }
+static size_t off_mb(long long n_ghost) { return 3 * gl_bytes(n_ghost); }
+static size_t mb_bytes() { return align_up(sizeof(u64) * 2 * TC_MAX_WORLD * TC_MB_SLOT, 256); }
 
 extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t world, int64_t n_loc,
                               int64_t n_ghost) {
@@ -379,11 +374,11 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     memset(&d->K, 0, sizeof d->K);
     d->stream = (cudaStream_t)stream; d->rank = rank; d->world = world;
     d->n = n_loc; d->n_ghost = n_ghost;
-    const long long ext = n_loc + n_ghost;
-    d->comm_bytes = off_hf(ext) + align_up(sizeof(int) * TC_MAX_WORLD, 256);
+    d->comm_bytes = off_mb(n_ghost) + mb_bytes();
     TC_CUDA(cudaMalloc(&d->comm, d->comm_bytes));
-    TC_CUDA(cudaMemset(d->comm, 0, d->comm_bytes));
+    TC_CUDA(cudaMemset(d->comm, 0, d->comm_bytes));          // tag 0 everywhere: sequence numbers start at 1
     const size_t nb = sizeof(double) * (size_t)n_loc;
+    TC_CUDA(cudaMalloc(&d->y, nb)); TC_CUDA(cudaMalloc(&d->p0, nb)); TC_CUDA(cudaMalloc(&d->p1, nb));
     TC_CUDA(cudaMalloc(&d->x, nb)); TC_CUDA(cudaMalloc(&d->r, nb));
     TC_CUDA(cudaMalloc(&d->q, nb)); TC_CUDA(cudaMalloc(&d->dinv, nb));
     TC_CUDA(cudaMalloc(&d->state, sizeof(int) * 16));
@@ -396,7 +391,7 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     TC_CUDA(cudaMalloc(&d->K.bar.res, sizeof(double) * 2 * TC_BAR_MAXK));
     TC_CUDA(cudaMemset(d->K.bar.res, 0, sizeof(double) * 2 * TC_BAR_MAXK));
     d->peer[rank] = d->comm;
-    d->peer_ext[rank] = ext;
+    d->peer_ghost[rank] = n_ghost;
     TC_CUDA(cudaDeviceSynchronize());
     *out = d;
     return 0;
@@ -410,10 +405,10 @@ extern "C" int tc_dist_ipc_handle(tc_dist* d, void* handle64) {
     return 0;
 }
 
-// handles: world * 64 bytes; peer_ext: n + n_ghost of all ranks
-extern "C" int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_ext) {
+// handles: world * 64 bytes; peer_ghost: ghost count of all ranks
+extern "C" int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_ghost) {
     for (int w = 0; w < d->world; ++w) {
-        d->peer_ext[w] = peer_ext[w];
+        d->peer_ghost[w] = peer_ghost[w];
         if (w == d->rank) continue;
         cudaIpcMemHandle_t h;
         memcpy(&h, (const char*)handles + 64 * w, 64);
@@ -425,15 +420,16 @@ extern "C" int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t
     return 0;
 }
 
-// Halo plan: send list (local row -> peer, slot in the peer's extended vector) and the neighbour set.
+// Halo plan: send list (local row -> peer, ghost slot of that peer) and the number of neighbour ranks.
 // All arrays are HOST pointers; they are copied.
 extern "C" int tc_dist_set_halo(tc_dist* d, int64_t n_send, const int32_t* send_row, const int32_t* send_peer,
                                 const int64_t* send_dst, int32_t n_nbr, const int32_t* nbr) {
     TC_CHECK(n_nbr >= 0 && n_nbr < TC_MAX_WORLD, "neighbour count");
+    (void)nbr;
     for (int64_t e = 0; e < n_send; ++e) {
         const int w = send_peer[e];
         TC_CHECK(w >= 0 && w < d->world && w != d->rank && d->peer[w], "send list names a peer that is not open");
-        TC_CHECK(send_row[e] >= 0 && send_row[e] < d->n && send_dst[e] >= 0 && send_dst[e] < d->peer_ext[w],
+        TC_CHECK(send_row[e] >= 0 && send_row[e] < d->n && send_dst[e] >= 0 && send_dst[e] < d->peer_ghost[w],
                  "send list entry out of range");
     }
     cudaFree(d->send_row); cudaFree(d->send_peer); cudaFree(d->send_dst);
@@ -449,16 +445,12 @@ extern "C" int tc_dist_set_halo(tc_dist* d, int64_t n_send, const int32_t* send_
     TcDistK& K = d->K;
     K.n_send = n_send; K.send_row = d->send_row; K.send_peer = d->send_peer; K.send_dst = d->send_dst;
     K.n_nbr = n_nbr;
-    for (int k = 0; k < n_nbr; ++k) {
-        TC_CHECK(nbr[k] >= 0 && nbr[k] < d->world && nbr[k] != d->rank, "neighbour rank");
-        K.nbr[k] = nbr[k];
-    }
     return 0;
 }
 
-// Operator of the local rows (device pointers, kept by reference).  col: index into the extended vector
-// [n local | n_ghost]; col16 (optional): column - row for the interior slices; order (optional): slice
-// permutation with the n_bnd boundary slices last.
+// Operator of the local rows (device pointers, kept by reference).  col: < n_loc local row, >= n_loc ghost slot + n_loc
+// (read in boundary slices, and in all slices when col16 is absent); col16 (optional): column - row for the interior
+// slices; order (required when n_bnd > 0): slice permutation with the n_bnd boundary slices last.
 extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
                                     const int16_t* col16, const double* val, const double* mass,
                                     const double* adiag, const double* b, int32_t n_bnd, const int32_t* order) {
@@ -468,24 +460,21 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     K.n = (int)d->n; K.n_ghost = (int)d->n_ghost; K.rank = d->rank; K.world = d->world;
     K.n_bnd = n_bnd; K.order = order;
     K.b = b; K.mass = mass; K.adiag = adiag;
-    const long long ext = d->n + d->n_ghost;
-    K.y_ext = (double*)d->comm;
-    K.p_ext[0] = (double*)(d->comm + off_p(ext, 0)); K.p_ext[1] = (double*)(d->comm + off_p(ext, 1));
+    K.y = d->y; K.p[0] = d->p0; K.p[1] = d->p1;
     K.x = d->x; K.r = d->r; K.q = d->q; K.dinv = d->dinv;
+    K.y_gl = (u64*)(d->comm + off_gl(d->n_ghost, 0));
+    K.p_gl[0] = (u64*)(d->comm + off_gl(d->n_ghost, 1)); K.p_gl[1] = (u64*)(d->comm + off_gl(d->n_ghost, 2));
+    K.my_mb = (u64*)(d->comm + off_mb(d->n_ghost));
     for (int w = 0; w < TC_MAX_WORLD; ++w) {
-        K.peer_y[w] = nullptr; K.peer_p[0][w] = nullptr; K.peer_p[1][w] = nullptr;
-        K.peer_hflag[w] = nullptr; K.peer_mb[w] = nullptr; K.peer_mbf[w] = nullptr;
+        K.peer_y_gl[w] = nullptr; K.peer_p_gl[0][w] = nullptr; K.peer_p_gl[1][w] = nullptr; K.peer_mb[w] = nullptr;
     }
     for (int w = 0; w < d->world; ++w) {
         if (!d->peer[w]) continue;
-        const long long e = d->peer_ext[w];
-        K.peer_y[w] = (double*)d->peer[w];
-        K.peer_p[0][w] = (double*)(d->peer[w] + off_p(e, 0)); K.peer_p[1][w] = (double*)(d->peer[w] + off_p(e, 1));
-        K.peer_mb[w] = (double*)(d->peer[w] + off_mb(e)); K.peer_mbf[w] = (int*)(d->peer[w] + off_mbf(e));
-        K.peer_hflag[w] = (int*)(d->peer[w] + off_hf(e));
+        const long long g = d->peer_ghost[w];
+        K.peer_y_gl[w] = (u64*)(d->peer[w] + off_gl(g, 0));
+        K.peer_p_gl[0][w] = (u64*)(d->peer[w] + off_gl(g, 1)); K.peer_p_gl[1][w] = (u64*)(d->peer[w] + off_gl(g, 2));
+        K.peer_mb[w] = (u64*)(d->peer[w] + off_mb(g));
     }
-    K.my_mb = (double*)(d->comm + off_mb(ext)); K.my_mbf = (int*)(d->comm + off_mbf(ext));
-    K.my_hflag = (int*)(d->comm + off_hf(ext));
     K.state = d->state;
     K.prof = d->prof;
     int dev = 0, sms = 148, occ = 0, khz = 1965000;
@@ -534,20 +523,20 @@ extern "C" int tc_dist_reset_error(tc_dist* d) {
 }
 
 extern "C" int tc_dist_set_state(tc_dist* d, const double* y_local_dev) {
-    TC_CUDA(cudaMemcpyAsync(d->K.y_ext, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+    TC_CUDA(cudaMemcpyAsync(d->y, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     TC_CUDA(cudaStreamSynchronize(d->stream));
     return 0;
 }
 extern "C" int tc_dist_get_state(tc_dist* d, double* y_local_dev) {
-    TC_CUDA(cudaMemcpyAsync(y_local_dev, d->K.y_ext, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+    TC_CUDA(cudaMemcpyAsync(y_local_dev, d->y, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     return tc_dist_check(d);
 }
 // enqueue-only copies for pipelined host<->device streaming: dir 0 = set (caller -> state), 1 = get
 extern "C" int tc_dist_copy_state_async(tc_dist* d, double* y_local_dev, int32_t dir) {
     if (dir == 0)
-        TC_CUDA(cudaMemcpyAsync(d->K.y_ext, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+        TC_CUDA(cudaMemcpyAsync(d->y, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     else
-        TC_CUDA(cudaMemcpyAsync(y_local_dev, d->K.y_ext, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+        TC_CUDA(cudaMemcpyAsync(y_local_dev, d->y, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     return 0;
 }
 // load vector of the local rows (device pointer, kept by reference): time-varying boundary data
@@ -597,7 +586,7 @@ extern "C" int tc_dist_close_peers(tc_dist* d) {
 extern "C" int tc_dist_destroy(tc_dist* d) {
     if (!d) return 0;
     tc_dist_close_peers(d);
-    cudaFree(d->comm); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
+    cudaFree(d->comm); cudaFree(d->y); cudaFree(d->p0); cudaFree(d->p1); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
     cudaFree(d->state); cudaFree(d->prof);
     cudaFree(d->K.bar.ctr); cudaFree(d->K.bar.part); cudaFree(d->K.bar.res);
     cudaFree(d->send_row); cudaFree(d->send_peer); cudaFree(d->send_dst);

@@ -27,7 +27,7 @@ extern "C" const char* tc_last_error(void) { return g_err.c_str(); }
 extern "C" int tc_version(void) { return 100; }
 
 #define TC_PCG_DEFAULT_OCC 8
-#define TC_PCG_COOP_THREADS_DEFAULT 256
+#define TC_PCG_COOP_THREADS_DEFAULT 1024      // 2 blocks of 1024 threads per SM (measured: profiles/README.md)
 static int pcg_coop_grid(int sm_count);
 
 // ---- control block layout (device) ------------------------------------------------------
@@ -772,8 +772,9 @@ static int pcg_occ_variant() {
     }
     return v;
 }
-// block shape of the cooperative kernel: 256 threads x 8 blocks/SM by default; TC_PCG_THREADS = 512 / 1024 selects
-// 4 / 2 blocks per SM (same warps per SM, fewer participants per grid barrier: profiles/README.md, barrier bench)
+// block shape of the cooperative kernel: 1024 threads x 2 blocks/SM by default; TC_PCG_THREADS = 512 / 256 selects
+// 4 / 8 blocks per SM (same warps per SM; fewer participants per grid barrier are cheaper: 1 M DOF 716 -> 820 M
+// DOF*steps/s, 10 M DOF 412 -> 419, profiles/README.md)
 static int pcg_coop_threads() {
     static int t = -1;
     if (t < 0) {

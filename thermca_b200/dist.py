@@ -65,7 +65,7 @@ def remap_columns(cols_global, r0, r1, ghosts):
 def send_plan(all_ghosts, bounds, rank):
     """What this rank must push: ``all_ghosts[w]`` = sorted ghost columns of rank w.  Returns
     (send_row int32, send_peer int32, send_dst int64, neighbours int32): entry e sends local row
-    send_row[e] into slot send_dst[e] of rank send_peer[e]'s extended vectors."""
+    send_row[e] into ghost slot send_dst[e] of rank send_peer[e]."""
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
     rows, peers, dsts, nbrs = [], [], [], set()
     for w, g in enumerate(all_ghosts):
@@ -74,10 +74,9 @@ def send_plan(all_ghosts, bounds, rank):
         g = np.asarray(g, dtype=np.int64)
         hit = np.nonzero((g >= r0) & (g < r1))[0]
         if hit.size:
-            n_w = int(bounds[w + 1] - bounds[w])
             rows.append(g[hit] - r0)
             peers.append(np.full(hit.size, w))
-            dsts.append(n_w + hit)
+            dsts.append(hit)
             nbrs.add(w)
     # the ranks that own my ghosts are neighbours as well (symmetric for a symmetric pattern; kept general)
     mine = np.asarray(all_ghosts[rank], dtype=np.int64)
@@ -96,7 +95,7 @@ def emulate_push(x_local, n_ghost, plan, rank, world, all_gather_object):
     ext = np.concatenate([np.asarray(x_local, dtype=np.float64), np.full(n_ghost, np.nan)])
     for w, (peer, dst, val) in enumerate(out):
         sel = peer == rank
-        ext[dst[sel]] = val[sel]
+        ext[len(x_local) + dst[sel]] = val[sel]
     return ext
 
 
@@ -184,7 +183,7 @@ class DistBody:
         all_ghosts = [None] * self.world
         dist.all_gather_object(all_ghosts, ghosts.cpu().numpy())
         self.plan = send_plan(all_ghosts, self.bounds, self.rank)
-        ext = [int(self.bounds[w + 1] - self.bounds[w]) + len(all_ghosts[w]) for w in range(self.world)]
+        ext = [len(all_ghosts[w]) for w in range(self.world)]          # ghost count of every rank
         torch.cuda.synchronize(self.dev)
         self._h = _cabi.vp()
         _cabi.check(self.lib.tc_dist_create(C.byref(self._h), C.c_void_p(self.stream.cuda_stream), self.rank,
