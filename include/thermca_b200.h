@@ -187,8 +187,8 @@ int tc_bar_bench(void* cuda_stream, int32_t blocks, int32_t threads, int32_t ite
  * cooperative kernel per theta step (no NCCL call on the data path).  The reference has no
  * multi-process code; per rank this is thermca/solver.py:265-281 (right-hand side
  * of a full-order FE part) plus the implicit solve on the local rows.
- * Operator columns: < n_loc = local row, >= n_loc = ghost slot + n_loc.  Ghost values and reduction mailboxes are
- * "LL" encoded in the exported buffer (every 8-byte granule carries a sequence tag): no flags, no system fences.
+ * Ghost values and reduction mailboxes are "LL" encoded in the exported buffer (every 8-byte granule carries a
+ * sequence tag): no flags, no system fences.
  * Calls return 0, or a negative code with tc_last_error(): -3 = a wait on a peer timed out
  * (TC_DIST_TIMEOUT_S seconds, default 20), -4 = PCG iteration limit / breakdown. */
 typedef struct tc_dist tc_dist;
@@ -200,11 +200,14 @@ int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_ghos
  * send_peer[e]; nbr = ranks this rank trades ghosts with */
 int tc_dist_set_halo(tc_dist* d, int64_t n_send, const int32_t* send_row, const int32_t* send_peer,
                      const int64_t* send_dst, int32_t n_nbr, const int32_t* nbr);
-/* SELL-32 operator of the local rows (device pointers, kept by reference); col16 (optional) = column - row of
- * the interior slices; order (required when n_bnd > 0) = slice order with the n_bnd boundary slices last */
+/* SELL-32 operator of the local rows over LOCAL columns (device pointers, kept by reference; col16 optional =
+ * column - row); bidx[s] (required when n_bnd > 0) = index of slice s among the n_bnd boundary slices or -1; couplings
+ * to ghosts: side lists of the boundary slices, entry k of lane l of boundary slice b at gptr[b] + 32 k + l =
+ * (ghost slot, operator value), padded with (0, 0.0) */
 int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
                          const int16_t* col16, const double* val, const double* mass, const double* adiag,
-                         const double* b, int32_t n_bnd, const int32_t* order);
+                         const double* b, int32_t n_bnd, const int32_t* bidx, const int64_t* gptr,
+                         const int32_t* gslot, const double* gval);
 int tc_dist_set_load(tc_dist* d, const double* b_local_dev);     /* swap the load vector (time-varying loads) */
 int tc_dist_set_state(tc_dist* d, const double* y_local_dev);
 int tc_dist_get_state(tc_dist* d, double* y_local_dev);          /* fails (-3/-4) if a step since the last reset failed */
@@ -212,8 +215,9 @@ int tc_dist_copy_state_async(tc_dist* d, double* y_local_dev, int32_t dir);   /*
 int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, double h, double rtol, int32_t maxit);
 int tc_dist_check(tc_dist* d);                                   /* synchronises; 0, -3 or -4 */
 int tc_dist_reset_error(tc_dist* d);
-/* iters_last, iters_total, comm error flag, solves + 1e6 * grid, failed solves */
-int tc_dist_stats(tc_dist* d, int64_t* stats5);
+/* iters_last, iters_total, comm error flag, solves + 1e6 * grid, failed solves, ghosts that were waited for
+ * (counted only with TC_DIST_DIAG=1) */
+int tc_dist_stats(tc_dist* d, int64_t* stats6);
 int tc_dist_profile(tc_dist* d, uint64_t* out32);   /* per-phase wall time (ns) of block 0 / last block */
 /* teardown: tc_dist_close_peers on every rank, a host barrier, then tc_dist_destroy (CUDA IPC rule: the
  * exporter must not free while an importer has the buffer mapped) */

@@ -10,10 +10,10 @@
 //     also trades the local sums with all peers through per-rank mailboxes and adds them in rank
 //     order: one barrier == one global all-reduce, bit-identical scalars on all ranks ->
 //     identical convergence decisions, deterministic results;
-//   * the search direction is double buffered, so the rows a peer needs are recomputed from
-//     stable inputs by the pushing threads (no intra-phase race, no extra barrier) and the push
-//     overlaps the vector phase; the product runs interior slices first and touches ghosts only
-//     in the few boundary slices at the end of every warp's share.
+//   * the CG is the single-reduction form (Chronopoulos & Gear): ONE all-reduce and two grid
+//     barriers per iteration instead of two and three;
+//   * a product first pushes the rows the peers need, streams all slices without ghost couplings
+//     and only then does the few boundary slices, so the NVLink latency hides behind the interior.
 // Peer memory is exchanged once at setup as CUDA IPC handles (plumbing via torch.distributed in
 // thermca_b200/dist.py).  The reference has nothing comparable (no multi-process code, SURVEY.md
 // fact 1); per rank the arithmetic is the single-GPU PCG of pcg.cuh on the local rows.
@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <vector>
 #include "../../include/thermca_b200.h"
 #include "parts.cuh"
 #include "gridbar.cuh"
@@ -41,18 +42,21 @@ typedef unsigned long long u64;
 // wait for the remote acknowledgements, i.e. a full NVLink round trip on the critical path), and every ghost value is
 // usable the moment it lands.  Tags are monotonic sequence numbers (halo: hseq, reductions: rseq).
 struct TcDistK {
-    TcSell A;                             // local rows; col16 relative to the row (interior slices), col (boundary
-                                          // slices): < n local row, >= n ghost slot (col - n)
+    TcSell A;                             // local rows and LOCAL columns only (col16 relative to the row when the band
+                                          // allows it, else col); couplings to ghosts live in the side lists below
     int n, n_ghost, rank, world;
     int n_bnd;                            // boundary slices (reference at least one ghost column)
-    const int* order;                     // nslices: interior slices first, boundary slices last
+    const int* bidx;                      // nslices: -1, or the index of the slice among the boundary slices
+    const int* blist;                     // n_bnd: the boundary slices
+    const long long* gptr;                // n_bnd + 1: ghost couplings of boundary slice b (SELL-32: entry k of lane l at
+    const int* gslot; const double* gval; //   gptr[b] + 32 k + l) = (ghost slot, operator value); padding = (0, 0.0)
     const double *b, *mass, *adiag;
-    double *y, *p[2];                     // local vectors (n each); the search direction is double buffered
-    double *x, *r, *q, *dinv;
-    u64 *y_gl, *p_gl[2];                  // my ghost values, LL encoded: 2 granules per ghost slot (exported memory)
+    double *y, *u, *p, *s;                // local vectors (n each): state, D^-1 r, search direction, s = P p
+    double *x, *r, *q, *dinv;             // q doubles as w = P u
+    u64 *y_gl, *u_gl;                     // my ghost values, LL encoded: 2 granules per ghost slot (exported memory)
     long long n_send;                     // halo send list: local row -> (peer, ghost slot of the peer)
     const int* send_row; const int* send_peer; const long long* send_dst;
-    u64* peer_y_gl[TC_MAX_WORLD]; u64* peer_p_gl[2][TC_MAX_WORLD];
+    u64* peer_y_gl[TC_MAX_WORLD]; u64* peer_u_gl[TC_MAX_WORLD];
     int n_nbr;                            // ranks I trade ghosts with (only its being non-zero matters to the kernel)
     u64* peer_mb[TC_MAX_WORLD]; u64* my_mb;      // mailboxes [2 parities][TC_MAX_WORLD senders][TC_MB_SLOT]
     TcGridBar bar;
@@ -61,6 +65,7 @@ struct TcDistK {
     double theta, h, rtol;
     int maxit;
     long long spin_limit;                 // clock64 ticks
+    int push_fence;                       // experiment switch (TC_DIST_PUSH_FENCE=1): system fence after ghost pushes
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
 };
 
@@ -82,16 +87,23 @@ __device__ __forceinline__ u64 ll_wait(const u64* g, unsigned int tag, int* err,
     u64 v = ld_relaxed_sys_u64(g);
     if ((unsigned int)(v >> 32) == tag) return v;
     const long long t0 = clock64();
-    for (;;) {
+    for (unsigned int spins = 1;; ++spins) {
         v = ld_relaxed_sys_u64(g);
         if ((unsigned int)(v >> 32) == tag) return v;
-        if (*((volatile int*)err)) return v;
-        if (clock64() - t0 > limit) { *((volatile int*)err) = 1; __threadfence(); return v; }
+        if ((spins & 63u) == 0u) {                         // the bookkeeping loads stay off the polling path
+            if (*((volatile int*)err)) return v;
+            if (clock64() - t0 > limit) { *((volatile int*)err) = 1; __threadfence(); return v; }
+        }
     }
 }
 __device__ __forceinline__ double ll_load(const u64* g, unsigned int tag, int* err, long long limit) {
     const u64 lo = ll_wait(g, tag, err, limit), hi = ll_wait(g + 1, tag, err, limit);
     return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffULL)));
+}
+// both granules of one value with ONE 16-byte load (each 8-byte half is single-copy atomic on its own); the caller
+// checks the tags and falls back on ll_load for a value that has not landed yet
+__device__ __forceinline__ void ll_peek(const u64* g, u64& lo, u64& hi) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(g) : "memory");
 }
 
 // All-reduce of the local totals, run by the last block to reach the grid barrier (gridbar.cuh hook): thread w < world
@@ -129,9 +141,86 @@ struct TcDistExchange {
 
 #define TC_DIST_THREADS 1024
 
-// Local rows times [local vector | ghosts], interior slices first (16-bit relative or 32-bit local columns) and the
-// boundary slices LAST in every warp's grid-stride sequence, so the ghost values have had the whole interior pass to
-// cross NVLink; a ghost that is still missing is waited for individually (LL tag), there is no halo flag.
+// Couplings of one row of boundary slice `bi` to rows of other ranks: a short side list (<= ~6 entries per row on a
+// slab cut), four ghost values requested at a time (16-byte LL peeks).  Kept out of line: it runs for ~1 % of the
+// slices and must not cost the streaming loop registers.
+__device__ __noinline__ double ghost_part(const long long* gptr, const int* gslot, const double* gval, const u64* xg,
+                                          int bi, int lane, unsigned int hseq, int* state, long long limit) {
+    const long long gb = gptr[bi];
+    const int gw = (int)((gptr[bi + 1] - gb) >> 5);
+    double sum = 0.0;
+    for (int k0 = 0; k0 < gw; k0 += 4) {
+        u64 lo[4], hi[4]; int sl[4]; double gv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (k0 + j < gw) {
+                sl[j] = gslot[gb + 32 * (k0 + j) + lane];
+                gv[j] = gval[gb + 32 * (k0 + j) + lane];
+                ll_peek(xg + 2 * (size_t)sl[j], lo[j], hi[j]);
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (k0 + j < gw) {
+                double xv;
+                if ((unsigned int)(lo[j] >> 32) == hseq && (unsigned int)(hi[j] >> 32) == hseq) {
+                    xv = __longlong_as_double((long long)((hi[j] << 32) | (lo[j] & 0xffffffffULL)));
+                } else {
+                    if (state[11]) atomicAdd(state + 10, 1);              // diagnostic: ghosts that had not landed
+                    xv = ll_load(xg + 2 * (size_t)sl[j], hseq, state + 4, limit);
+                }
+                sum = __dadd_rn(sum, __dmul_rn(gv[j], xv));
+            }
+    }
+    return sum;
+}
+
+// sum_k A[row][k] x[col] over the LOCAL columns of one slice (one row per lane), entries in stored order, no FMA
+__device__ __forceinline__ double slice_local_sum(const TcSell& A, const double* xl, int s, int lane) {
+    const long long base = A.slice_ptr[s];
+    const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+    const double* v = A.val + base + lane;
+    double sum = 0.0;
+    if (A.col16) {
+        const short* c = A.col16 + base + lane;
+        const double* xr0 = xl + (s * 32 + lane);
+        int k = 0;
+        for (; k + 4 <= width; k += 4) {
+            const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
+            const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
+            const int c0 = ld_stream_s16(c + 32 * (k + 0)), c1 = ld_stream_s16(c + 32 * (k + 1));
+            const int c2 = ld_stream_s16(c + 32 * (k + 2)), c3 = ld_stream_s16(c + 32 * (k + 3));
+            const double x0 = tc_ld_x<0>(xr0 + c0), x1 = tc_ld_x<0>(xr0 + c1), x2 = tc_ld_x<0>(xr0 + c2), x3 = tc_ld_x<0>(xr0 + c3);
+            sum = __dadd_rn(sum, __dmul_rn(v0, x0));
+            sum = __dadd_rn(sum, __dmul_rn(v1, x1));
+            sum = __dadd_rn(sum, __dmul_rn(v2, x2));
+            sum = __dadd_rn(sum, __dmul_rn(v3, x3));
+        }
+        for (; k < width; ++k)
+            sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xr0 + ld_stream_s16(c + 32 * k))));
+    } else {
+        const int* c = A.col + base + lane;
+        int k = 0;
+        for (; k + 4 <= width; k += 4) {
+            const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
+            const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
+            const int c0 = ld_stream_s32(c + 32 * (k + 0)), c1 = ld_stream_s32(c + 32 * (k + 1));
+            const int c2 = ld_stream_s32(c + 32 * (k + 2)), c3 = ld_stream_s32(c + 32 * (k + 3));
+            const double x0 = tc_ld_x<0>(xl + c0), x1 = tc_ld_x<0>(xl + c1), x2 = tc_ld_x<0>(xl + c2), x3 = tc_ld_x<0>(xl + c3);
+            sum = __dadd_rn(sum, __dmul_rn(v0, x0));
+            sum = __dadd_rn(sum, __dmul_rn(v1, x1));
+            sum = __dadd_rn(sum, __dmul_rn(v2, x2));
+            sum = __dadd_rn(sum, __dmul_rn(v3, x3));
+        }
+        for (; k < width; ++k)
+            sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xl + ld_stream_s32(c + 32 * k))));
+    }
+    return sum;
+}
+
+// Local rows times [local vector | ghosts].  The caller has just pushed the rows its peers need (LL encoded) from
+// the SAME, complete vector.  Pass 1 streams every slice without ghost couplings; pass 2 then does the few boundary
+// slices (local part + side list), by which time the peers' pushes have had the whole first pass (tens of
+// microseconds) to cross NVLink; a ghost that is still missing is waited for individually (LL tag).  No halo flags.
 template <int MODE>
 __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, const u64* xg, double* y,
                                             const double* b, double shift, unsigned int hseq) {
@@ -140,66 +229,30 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, 
     const int warps_per_block = blockDim.x >> 5;
     const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * warps_per_block;
-    const int nsl = A.nslices, n_int = nsl - S.n_bnd, n = S.n;
+    const int nsl = A.nslices;
     double dot = 0.0;
-    for (int idx = warp; idx < nsl; idx += nwarps) {
-        const bool boundary = idx >= n_int;
-        const int s = S.order ? S.order[idx] : idx;
-        const long long base = A.slice_ptr[s];
-        const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
-        const double* v = A.val + base + lane;
-        double sum = 0.0;
-        if (boundary) {
-            const int* c = A.col + base + lane;
-            for (int k = 0; k < width; ++k) {
-                const int cc = ld_stream_s32(c + 32 * k);
-                const double xv = cc < n ? tc_ld_x<0>(xl + cc)
-                                         : ll_load(xg + 2 * (size_t)(cc - n), hseq, S.state + 4, S.spin_limit);
-                sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), xv));
-            }
-        } else if (A.col16) {
-            const short* c = A.col16 + base + lane;
-            const double* xr0 = xl + (s * 32 + lane);
-            int k = 0;
-            for (; k + 4 <= width; k += 4) {
-                const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
-                const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
-                const int c0 = ld_stream_s16(c + 32 * (k + 0)), c1 = ld_stream_s16(c + 32 * (k + 1));
-                const int c2 = ld_stream_s16(c + 32 * (k + 2)), c3 = ld_stream_s16(c + 32 * (k + 3));
-                const double x0 = tc_ld_x<0>(xr0 + c0), x1 = tc_ld_x<0>(xr0 + c1), x2 = tc_ld_x<0>(xr0 + c2), x3 = tc_ld_x<0>(xr0 + c3);
-                sum = __dadd_rn(sum, __dmul_rn(v0, x0));
-                sum = __dadd_rn(sum, __dmul_rn(v1, x1));
-                sum = __dadd_rn(sum, __dmul_rn(v2, x2));
-                sum = __dadd_rn(sum, __dmul_rn(v3, x3));
-            }
-            for (; k < width; ++k)
-                sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xr0 + ld_stream_s16(c + 32 * k))));
-        } else {
-            const int* c = A.col + base + lane;
-            int k = 0;
-            for (; k + 4 <= width; k += 4) {
-                const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
-                const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
-                const int c0 = ld_stream_s32(c + 32 * (k + 0)), c1 = ld_stream_s32(c + 32 * (k + 1));
-                const int c2 = ld_stream_s32(c + 32 * (k + 2)), c3 = ld_stream_s32(c + 32 * (k + 3));
-                const double x0 = tc_ld_x<0>(xl + c0), x1 = tc_ld_x<0>(xl + c1), x2 = tc_ld_x<0>(xl + c2), x3 = tc_ld_x<0>(xl + c3);
-                sum = __dadd_rn(sum, __dmul_rn(v0, x0));
-                sum = __dadd_rn(sum, __dmul_rn(v1, x1));
-                sum = __dadd_rn(sum, __dmul_rn(v2, x2));
-                sum = __dadd_rn(sum, __dmul_rn(v3, x3));
-            }
-            for (; k < width; ++k)
-                sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xl + ld_stream_s32(c + 32 * k))));
-        }
-        const int row = s * 32 + lane;
-        if (row < A.n) {
-            if (MODE == SPMV_B) {
-                y[row] = __dsub_rn(b[row], sum);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int count = pass == 0 ? nsl : S.n_bnd;
+        for (int idx = warp; idx < count; idx += nwarps) {
+            int s = idx, bi = -1;
+            if (pass == 0) {
+                if (S.n_bnd && S.bidx[s] >= 0) continue;             // boundary slice: second pass
             } else {
-                const double xr = tc_ld_x<0>(xl + row);
-                const double q = S.mass[row] * (xr + shift * sum);
-                y[row] = q;
-                dot += xr * q;
+                bi = idx; s = S.blist[idx];
+            }
+            double sum = slice_local_sum(A, xl, s, lane);
+            if (bi >= 0)
+                sum = __dadd_rn(sum, ghost_part(S.gptr, S.gslot, S.gval, xg, bi, lane, hseq, S.state, S.spin_limit));
+            const int row = s * 32 + lane;
+            if (row < A.n) {
+                if (MODE == SPMV_B) {
+                    y[row] = __dsub_rn(b[row], sum);
+                } else {
+                    const double xr = tc_ld_x<0>(xl + row);
+                    const double q = S.mass[row] * (xr + shift * sum);
+                    y[row] = q;
+                    dot += xr * q;
+                }
             }
         }
     }
@@ -217,14 +270,21 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define PROF(k) do { if (prof_row >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
     S.prof[prof_row * 16 + (k)] += t_ - prof_t; prof_t = t_; } } while (0)
 
-// scaled right-hand side and Jacobi factor of one row (explicit roundings: the owner's loop and the halo push
-// must produce the same bits)
-__device__ __forceinline__ void init_row(const TcDistK& S, int i, double shift, double& bsc, double& d) {
-    const double m = S.mass[i];
-    bsc = __dmul_rn(m, S.q[i]);
-    d = __ddiv_rn(1.0, __dmul_rn(m, __fma_rn(shift, S.adiag[i], 1.0)));
+// rows my peers need, straight from the (complete, stable) local vector into their LL ghost arrays
+__device__ __forceinline__ void push_ghosts(const TcDistK& S, const double* xl, u64* const* peer_gl, unsigned int hseq,
+                                            int gtid, int gsz) {
+    for (long long e = gtid; e < S.n_send; e += gsz)
+        ll_store(peer_gl[S.send_peer[e]] + 2 * S.send_dst[e], xl[S.send_row[e]], hseq);
 }
 
+// ONE cooperative launch per theta step: right-hand side, preconditioned CG, update.
+// The CG is the single-reduction form of Chronopoulos & Gear (1989): with u = D^-1 r, w = P u and the recurrences
+//   beta = gamma/gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old),   gamma = r.u, delta = w.u
+//   p = u + beta p,  s = w + beta s (= P p),  x += alpha p,  r -= alpha s,  u = D^-1 r
+// one iteration needs ONE all-reduce (gamma, delta, r.r together) and two grid barriers; classic PCG (pcg.cuh) needs
+// two all-reduces and three barriers.  Across GPUs an all-reduce is ~10 us of NVLink round trip and rank skew
+// (measured, profiles/README.md), which at 1-2.5 M rows per GPU is 10-15 % of an iteration; the extra 8 B/row of vector
+// traffic is 3 %.  Mathematically the same iterates; the convergence test lags one product behind.
 template <int MB, int THREADS = TC_DIST_THREADS>
 __global__ void __launch_bounds__(THREADS, MB)
 tc_dist_theta_kernel(TcDistK S) {
@@ -236,83 +296,78 @@ tc_dist_theta_kernel(TcDistK S) {
     unsigned int hseq = (unsigned int)S.state[1];
     PROF_INIT();
     const double shift = S.theta * S.h;
-    int pb = 0;
+    double* w = S.q;
 
     // ---- right-hand side f = b - A y (thermca/solver.py:281) on the local rows -----------------
     ++hseq;
-    for (long long e = gtid; e < S.n_send; e += gsz)
-        ll_store(S.peer_y_gl[S.send_peer[e]] + 2 * S.send_dst[e], S.y[S.send_row[e]], hseq);
+    push_ghosts(S, S.y, S.peer_y_gl, hseq, gtid, gsz);
     slab_spmv<SPMV_B>(S, S.y, S.y_gl, S.q, S.b, 0.0, hseq);
     tc_grid_barrier(S.bar, gen);
     double red[TC_DIST_K];
-    ++hseq;
     {
-        double* p0 = S.p[0];
-        double rho_l = 0.0, bb_l = 0.0;
-        // rows a peer needs first: recomputed from the same stable inputs (bit-identical), pushed over NVLink
-        for (long long e = gtid; e < S.n_send; e += gsz) {
-            double bsc, d;
-            init_row(S, S.send_row[e], shift, bsc, d);
-            ll_store(S.peer_p_gl[0][S.send_peer[e]] + 2 * S.send_dst[e], __dmul_rn(d, bsc), hseq);
-        }
+        double g_l = 0.0, bb_l = 0.0;
         for (int i = gtid; i < n; i += gsz) {
-            double bsc, d;
-            init_row(S, i, shift, bsc, d);
-            const double z = __dmul_rn(d, bsc);
-            S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; p0[i] = z;
-            rho_l += bsc * z; bb_l += bsc * bsc;
+            const double m = S.mass[i];
+            const double bsc = m * S.q[i];
+            const double d = 1.0 / (m * (1.0 + shift * S.adiag[i]));
+            const double u = d * bsc;
+            S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; S.u[i] = u; S.p[i] = 0.0; S.s[i] = 0.0;
+            g_l += bsc * u; bb_l += bsc * bsc;
         }
-        red[0] = block_sum(rho_l, sh); red[1] = block_sum(bb_l, sh); red[2] = 0.0;
+        red[0] = block_sum(g_l, sh); red[2] = block_sum(bb_l, sh); red[1] = 0.0;
     }
-    tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
-    double rho = red[0];
-    const double bb = red[1];
-    const double tol2 = S.rtol * S.rtol * bb;
+    tc_grid_barrier(S.bar, gen);
+    double gamma_old = 1.0, alpha_old = 1.0, tol2 = 0.0;
     int it = 0, status = 0;
-    if (bb > 0.0) {
-        status = 1;
-        for (; it < S.maxit;) {
-            PROF(0);
-            const double* pe = S.p[pb];
-            const double dot = slab_spmv<SPMV_SHIFT>(S, pe, S.p_gl[pb], S.q, nullptr, shift, hseq);
-            PROF(1);
-            red[0] = block_sum(dot, sh);
-            PROF(2);
-            tc_grid_reduce_last<1>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
-            PROF(3);
-            const double pq = red[0];
-            if (!(pq > 0.0) || !isfinite(pq)) { status = 2; break; }       // uniform over the grid AND over the ranks
-            const double alpha = rho / pq;
-            double rn = 0.0, rr = 0.0;
-            for (int i = gtid; i < n; i += gsz) {
-                S.x[i] += alpha * pe[i];
-                const double ri = S.r[i] - alpha * S.q[i];
-                S.r[i] = ri;
-                rn += ri * (S.dinv[i] * ri);
-                rr += ri * ri;
-            }
-            red[0] = block_sum(rn, sh); red[1] = block_sum(rr, sh);
-            PROF(4);
-            tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
-            PROF(5);
-            ++it;
-            if (!(red[1] > tol2)) { status = isfinite(red[1]) ? 0 : 2; break; }
-            const double beta = red[0] / rho;
-            double* pn = S.p[pb ^ 1];
-            ++hseq;
-            // ghost rows first, so they are in flight while the local rows are updated
-            for (long long e = gtid; e < S.n_send; e += gsz) {
-                const int i = S.send_row[e];
-                ll_store(S.peer_p_gl[pb ^ 1][S.send_peer[e]] + 2 * S.send_dst[e],
-                         __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i])), hseq);
-            }
-            for (int i = gtid; i < n; i += gsz) pn[i] = __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i]));
-            rho = red[0];
-            pb ^= 1;
-            PROF(6);
-            tc_grid_barrier(S.bar, gen);
-            PROF(7);
+    bool first = true;
+    for (;;) {
+        PROF(0);
+        // ---- w = P u: push my boundary rows of u, stream the interior, then the boundary slices --------------
+        ++hseq;
+        push_ghosts(S, S.u, S.peer_u_gl, hseq, gtid, gsz);
+        const double dot = slab_spmv<SPMV_SHIFT>(S, S.u, S.u_gl, w, nullptr, shift, hseq);
+        PROF(1);
+        red[1] = block_sum(dot, sh);
+        PROF(2);
+        tc_grid_reduce_last<3>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
+        PROF(3);
+        const double gamma = red[0], delta = red[1], rr = red[2];
+        double alpha, beta;
+        // every decision below is uniform over the grid AND over the ranks (bit-identical totals everywhere)
+        if (first) {
+            tol2 = S.rtol * S.rtol * rr;
+            if (!(rr > 0.0)) { status = isfinite(rr) ? 0 : 2; break; }
+            beta = 0.0; alpha = gamma / delta;
+            first = false;
+        } else {
+            if (!(rr > tol2)) { status = isfinite(rr) ? 0 : 2; break; }
+            if (it >= S.maxit) { status = 1; break; }
+            beta = gamma / gamma_old;
+            alpha = gamma / (delta - beta * gamma / alpha_old);
         }
+        if (!(alpha > 0.0) || !isfinite(alpha)) { status = 2; break; }
+        // ---- vector phase, two row-local sweeps (5 and 7 streams) ------------------------------------------
+        for (int i = gtid; i < n; i += gsz) {
+            const double pn = S.u[i] + beta * S.p[i];
+            S.p[i] = pn;
+            S.x[i] += alpha * pn;
+        }
+        double g_l = 0.0, rr_l = 0.0;
+        for (int i = gtid; i < n; i += gsz) {
+            const double sn = w[i] + beta * S.s[i];
+            S.s[i] = sn;
+            const double ri = S.r[i] - alpha * sn;
+            S.r[i] = ri;
+            const double un = S.dinv[i] * ri;
+            S.u[i] = un;
+            g_l += ri * un; rr_l += ri * ri;
+        }
+        red[0] = block_sum(g_l, sh); red[2] = block_sum(rr_l, sh);
+        gamma_old = gamma; alpha_old = alpha;
+        ++it;
+        PROF(4);
+        tc_grid_barrier(S.bar, gen);
+        PROF(5);
     }
     // ---- y += h * z (not committed after a communication failure / breakdown) ------------------
     if (status != 2)
@@ -348,7 +403,8 @@ struct tc_dist {
     size_t comm_bytes = 0;
     char* peer[TC_MAX_WORLD];
     long long peer_ghost[TC_MAX_WORLD];   // ghost count of every rank (fixes the layout of its buffer)
-    double *y = nullptr, *p0 = nullptr, *p1 = nullptr;
+    double *y = nullptr, *u = nullptr, *p0 = nullptr, *p1 = nullptr;
+    int* blist = nullptr;
     double *x = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr;
     int* state = nullptr;
     unsigned long long* prof = nullptr;
@@ -359,10 +415,10 @@ struct tc_dist {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-// layout of a rank's exported buffer: [y ghosts | p ghosts 0 | p ghosts 1 | mailboxes], ghosts LL encoded (16 B each)
+// layout of a rank's exported buffer: [y ghosts | u ghosts | mailboxes], ghosts LL encoded (16 B each)
 static size_t gl_bytes(long long n_ghost) { return align_up((size_t)(n_ghost > 0 ? n_ghost : 1) * 2 * sizeof(u64), 256); }
 static size_t off_gl(long long n_ghost, int k) { return (size_t)k * gl_bytes(n_ghost); }
-static size_t off_mb(long long n_ghost) { return 3 * gl_bytes(n_ghost); }
+static size_t off_mb(long long n_ghost) { return 2 * gl_bytes(n_ghost); }
 static size_t mb_bytes() { return align_up(sizeof(u64) * 2 * TC_MAX_WORLD * TC_MB_SLOT, 256); }
 
 extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t world, int64_t n_loc,
@@ -378,7 +434,7 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     TC_CUDA(cudaMalloc(&d->comm, d->comm_bytes));
     TC_CUDA(cudaMemset(d->comm, 0, d->comm_bytes));          // tag 0 everywhere: sequence numbers start at 1
     const size_t nb = sizeof(double) * (size_t)n_loc;
-    TC_CUDA(cudaMalloc(&d->y, nb)); TC_CUDA(cudaMalloc(&d->p0, nb)); TC_CUDA(cudaMalloc(&d->p1, nb));
+    TC_CUDA(cudaMalloc(&d->y, nb)); TC_CUDA(cudaMalloc(&d->u, nb)); TC_CUDA(cudaMalloc(&d->p0, nb)); TC_CUDA(cudaMalloc(&d->p1, nb));
     TC_CUDA(cudaMalloc(&d->x, nb)); TC_CUDA(cudaMalloc(&d->r, nb));
     TC_CUDA(cudaMalloc(&d->q, nb)); TC_CUDA(cudaMalloc(&d->dinv, nb));
     TC_CUDA(cudaMalloc(&d->state, sizeof(int) * 16));
@@ -448,31 +504,45 @@ extern "C" int tc_dist_set_halo(tc_dist* d, int64_t n_send, const int32_t* send_
     return 0;
 }
 
-// Operator of the local rows (device pointers, kept by reference).  col: < n_loc local row, >= n_loc ghost slot + n_loc
-// (read in boundary slices, and in all slices when col16 is absent); col16 (optional): column - row for the interior
-// slices; order (required when n_bnd > 0): slice permutation with the n_bnd boundary slices last.
+// Operator of the local rows (device pointers, kept by reference): SELL-32 over LOCAL columns (col, and optionally
+// col16 = column - row); couplings to ghosts as side lists of the n_bnd boundary slices (gptr/gslot/gval, SELL-32 per
+// boundary slice; bidx[s] = index of slice s among the boundary slices, or -1).
 extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
                                     const int16_t* col16, const double* val, const double* mass,
-                                    const double* adiag, const double* b, int32_t n_bnd, const int32_t* order) {
-    TC_CHECK(n_bnd >= 0 && n_bnd <= nslices && (n_bnd == 0 || order), "boundary slices need the slice order");
+                                    const double* adiag, const double* b, int32_t n_bnd, const int32_t* bidx,
+                                    const int64_t* gptr, const int32_t* gslot, const double* gval) {
+    TC_CHECK(n_bnd >= 0 && n_bnd <= nslices && (n_bnd == 0 || (bidx && gptr && gslot && gval)),
+             "boundary slices need their index map and the ghost coupling lists");
     TcDistK& K = d->K;
     K.A = TcSell{(int)d->n, nslices, (const long long*)slice_ptr, col, val, (const short*)col16};
     K.n = (int)d->n; K.n_ghost = (int)d->n_ghost; K.rank = d->rank; K.world = d->world;
-    K.n_bnd = n_bnd; K.order = order;
+    K.n_bnd = n_bnd; K.bidx = bidx;
+    cudaFree(d->blist); d->blist = nullptr;
+    if (n_bnd > 0) {                                         // list of the boundary slices (inverse of bidx)
+        std::vector<int> hb(nslices), hl(n_bnd, -1);
+        TC_CUDA(cudaMemcpy(hb.data(), bidx, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
+        for (int sl = 0; sl < nslices; ++sl)
+            if (hb[sl] >= 0) { TC_CHECK(hb[sl] < n_bnd, "bidx out of range"); hl[hb[sl]] = sl; }
+        for (int k = 0; k < n_bnd; ++k) TC_CHECK(hl[k] >= 0, "bidx does not cover every boundary slice");
+        TC_CUDA(cudaMalloc(&d->blist, sizeof(int) * n_bnd));
+        TC_CUDA(cudaMemcpy(d->blist, hl.data(), sizeof(int) * n_bnd, cudaMemcpyHostToDevice));
+    }
+    K.blist = d->blist;
+    K.gptr = (const long long*)gptr; K.gslot = gslot; K.gval = gval;
     K.b = b; K.mass = mass; K.adiag = adiag;
-    K.y = d->y; K.p[0] = d->p0; K.p[1] = d->p1;
+    K.y = d->y; K.u = d->u; K.p = d->p0; K.s = d->p1;
     K.x = d->x; K.r = d->r; K.q = d->q; K.dinv = d->dinv;
     K.y_gl = (u64*)(d->comm + off_gl(d->n_ghost, 0));
-    K.p_gl[0] = (u64*)(d->comm + off_gl(d->n_ghost, 1)); K.p_gl[1] = (u64*)(d->comm + off_gl(d->n_ghost, 2));
+    K.u_gl = (u64*)(d->comm + off_gl(d->n_ghost, 1));
     K.my_mb = (u64*)(d->comm + off_mb(d->n_ghost));
     for (int w = 0; w < TC_MAX_WORLD; ++w) {
-        K.peer_y_gl[w] = nullptr; K.peer_p_gl[0][w] = nullptr; K.peer_p_gl[1][w] = nullptr; K.peer_mb[w] = nullptr;
+        K.peer_y_gl[w] = nullptr; K.peer_u_gl[w] = nullptr; K.peer_mb[w] = nullptr;
     }
     for (int w = 0; w < d->world; ++w) {
         if (!d->peer[w]) continue;
         const long long g = d->peer_ghost[w];
         K.peer_y_gl[w] = (u64*)(d->peer[w] + off_gl(g, 0));
-        K.peer_p_gl[0][w] = (u64*)(d->peer[w] + off_gl(g, 1)); K.peer_p_gl[1][w] = (u64*)(d->peer[w] + off_gl(g, 2));
+        K.peer_u_gl[w] = (u64*)(d->peer[w] + off_gl(g, 1));
         K.peer_mb[w] = (u64*)(d->peer[w] + off_mb(g));
     }
     K.state = d->state;
@@ -485,13 +555,16 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     double secs = to ? atof(to) : 20.0;
     if (!(secs > 0.0)) secs = 20.0;
     K.spin_limit = (long long)(secs * 1e3 * (double)khz);
+    const char* pf = getenv("TC_DIST_PUSH_FENCE");
+    K.push_fence = pf && pf[0] == '1';
+    const char* dg = getenv("TC_DIST_DIAG");            // 1: count late ghosts in state[10]; 2: also do not wait for them
+    if (dg) { const int v = atoi(dg); cudaMemcpy(d->state + 11, &v, sizeof(int), cudaMemcpyHostToDevice); }
     TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)dist_fn(), dist_threads(), 0));
     if (occ > 2048 / dist_threads()) occ = 2048 / dist_threads();
     if (occ < 1) occ = 1;
     d->grid = occ * sms;
     if (d->grid > TC_MAX_PARTIALS) d->grid = TC_MAX_PARTIALS;
-    const int need = (nslices + dist_threads() / 32 - 1) / (dist_threads() / 32);
-    if (need < d->grid) d->grid = need > 0 ? need : 1;
+    d->grid = tc_balanced_grid(nslices, dist_threads() / 32, d->grid);
     return 0;
 }
 
@@ -556,11 +629,12 @@ extern "C" int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, dou
     return 0;
 }
 
-// stats: iters_last, iters_total, comm error flag, solves (+ grid * 1e6), failed solves
+// stats: iters_last, iters_total, comm error flag, solves (+ grid * 1e6), failed solves, late ghosts (TC_DIST_DIAG)
 extern "C" int tc_dist_stats(tc_dist* d, int64_t* stats5) {
     int st[16];
     if (dist_read_state(d, st)) return -1;
     stats5[0] = st[2]; stats5[1] = st[3]; stats5[2] = st[4]; stats5[3] = st[5] + 1000000LL * d->grid; stats5[4] = st[8];
+    stats5[5] = st[10];
     return 0;
 }
 
@@ -586,7 +660,7 @@ extern "C" int tc_dist_close_peers(tc_dist* d) {
 extern "C" int tc_dist_destroy(tc_dist* d) {
     if (!d) return 0;
     tc_dist_close_peers(d);
-    cudaFree(d->comm); cudaFree(d->y); cudaFree(d->p0); cudaFree(d->p1); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
+    cudaFree(d->comm); cudaFree(d->y); cudaFree(d->u); cudaFree(d->blist); cudaFree(d->p0); cudaFree(d->p1); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
     cudaFree(d->state); cudaFree(d->prof);
     cudaFree(d->K.bar.ctr); cudaFree(d->K.bar.part); cudaFree(d->K.bar.res);
     cudaFree(d->send_row); cudaFree(d->send_peer); cudaFree(d->send_dst);

@@ -814,8 +814,7 @@ static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int
         void* args[] = {(void*)&P, (void*)&done};
         int g = coop_grid;
         const int cthreads = pcg_coop_threads();
-        const int need = grid_for(P.A.nslices, cthreads / 32, g);
-        if (need < g) g = need;
+        g = tc_balanced_grid(P.A.nslices, cthreads / 32, g);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (s && s->timing) {
             TC_CUDA(cudaEventCreate(&e0)); TC_CUDA(cudaEventCreate(&e1));

@@ -8,9 +8,9 @@ The reference has no multi-process code; per rank the 
 the single-GPU path (thermca/solver.py:265-281 + the implicit solve) on the local rows.
 
 Layout: every rank owns the contiguous global rows [bounds[rank], bounds[rank+1]) of a (bandwidth
-reducing) ordering.  Vectors are *extended*: ``[n_loc local | n_ghost ghosts]``, ghosts = the sorted
-global columns outside the own range that the local rows reference.  Operator columns are remapped to
-that vector; slices that reference a ghost are *boundary slices* and are processed last.
+reducing) ordering.  Ghosts = the sorted global columns outside the own range that the local rows
+reference.  The SELL operator of a rank keeps its LOCAL columns; slices with couplings to ghosts are
+*boundary slices* and carry those couplings in a short side list (ghost slot, value).
 """
 from __future__ import annotations
 
@@ -159,24 +159,52 @@ class DistBody:
         self.op, self.b = op, b
         nsl = int(op["nslices"])
         col = op["col"]
-        # ---- ghosts, column remap, boundary slices (on the device: 10^8 entries at 10 M rows) ----------
+        # ---- ghosts, boundary slices, ghost side lists (on the device: 10^8 entries at 10 M rows) -------------
         outside = (col < r0) | (col >= r1)
-        ghosts = torch.unique(col[outside]).to(torch.int64)                 # sorted
+        gpos = torch.nonzero(outside).ravel()                                # entry positions of ghost couplings
+        gcol = col[gpos].to(torch.int64)
+        ghosts = torch.unique(gcol)                                          # sorted global columns
         self.n_ghost = int(ghosts.numel())
-        widths = (op["slice_ptr"][1:] - op["slice_ptr"][:-1])
-        slice_of = torch.repeat_interleave(torch.arange(nsl, device=self.dev), widths)
+        sl_of = torch.searchsorted(op["slice_ptr"], gpos, right=True) - 1    # slice of every ghost coupling
+        lane_of = (gpos - op["slice_ptr"][sl_of]) & 31
         bnd_mask = torch.zeros(nsl, dtype=torch.bool, device=self.dev)
-        if self.n_ghost:
-            bnd_mask[slice_of[outside]] = True
+        bnd_mask[sl_of] = True
+        ids = torch.arange(nsl, device=self.dev, dtype=torch.int32)
+        bnd_ids = ids[bnd_mask]
+        self.n_bnd = int(bnd_ids.numel())
+        # side lists: SELL-32 per boundary slice, entry k of lane l = k-th ghost coupling of that row (stored order)
+        b_of_slice = torch.full((nsl,), -1, dtype=torch.int64, device=self.dev)
+        b_of_slice[bnd_ids.to(torch.int64)] = torch.arange(self.n_bnd, device=self.dev)
+        self.bidx = b_of_slice.to(torch.int32)
+        key = sl_of * 32 + lane_of                                           # gpos ascending -> ascending k within a row
+        skey, perm = torch.sort(key, stable=True)
+        uniq, counts = torch.unique_consecutive(skey, return_counts=True)
+        first = torch.cumsum(counts, 0) - counts
+        k_idx = torch.arange(skey.numel(), device=self.dev) - torch.repeat_interleave(first, counts)
+        gwidth = torch.zeros(max(self.n_bnd, 1), dtype=torch.int64, device=self.dev)
+        if self.n_bnd:
+            gwidth.scatter_reduce_(0, b_of_slice[uniq // 32], counts, reduce="amax", include_self=True)
+        gptr = torch.zeros(self.n_bnd + 1, dtype=torch.int64, device=self.dev)
+        gptr[1:] = torch.cumsum(gwidth[: self.n_bnd] * 32, 0)
+        total = int(gptr[-1].item()) if self.n_bnd else 0
+        self.gslot = torch.zeros(max(total, 1), dtype=torch.int32, device=self.dev)
+        self.gval = torch.zeros(max(total, 1), dtype=torch.float64, device=self.dev)
+        if total:
+            sp_pos, sp_sl, sp_lane = gpos[perm], sl_of[perm], lane_of[perm]
+            dst = gptr[b_of_slice[sp_sl]] + 32 * k_idx + sp_lane
+            self.gslot[dst] = torch.searchsorted(ghosts, gcol[perm]).to(torch.int32)
+            self.gval[dst] = op["val"][sp_pos]
+        self.gptr = gptr
+        # the main SELL keeps LOCAL columns only: ghost couplings become padding (0, own row)
+        row_of = (sl_of * 32 + lane_of).clamp(max=self.n - 1)
         col_loc = col.to(torch.int64) - r0
-        if self.n_ghost:
-            col_loc[outside] = self.n + torch.searchsorted(ghosts, col[outside].to(torch.int64))
+        col_loc[gpos] = row_of
+        op["val"][gpos] = 0.0
+        if op.get("col16") is not None:
+            op["col16"][gpos] = (row_of - (sl_of * 32 + lane_of)).to(torch.int16)
         self.col_loc = col_loc.to(torch.int32)
         op["col"] = self.col_loc                 # the global columns are not needed any more (0.6 GB at 10 M rows)
-        del col_loc, slice_of, outside, col
-        ids = torch.arange(nsl, device=self.dev, dtype=torch.int32)
-        self.order = torch.cat([ids[~bnd_mask], ids[bnd_mask]]).contiguous()
-        self.n_bnd = int(bnd_mask.sum().item())
+        del col_loc, outside, col, gpos, gcol, sl_of, lane_of, key, skey, perm
         self.stream = torch.cuda.Stream(self.dev)
         self.nnz = int(torch.count_nonzero(op["val"]).item())
         # ---- halo plan (setup-time collectives) --------------------------------------------------------
@@ -205,7 +233,7 @@ class DistBody:
         _cabi.check(self.lib.tc_dist_set_operator(self._h, nsl, p(op["slice_ptr"]), p(self.col_loc),
                                                   p(c16) if c16 is not None else C.c_void_p(0),
                                                   p(op["val"]), p(op["mass"]), p(op["adiag"]), p(self.b),
-                                                  self.n_bnd, p(self.order)))
+                                                  self.n_bnd, p(self.bidx), p(self.gptr), p(self.gslot), p(self.gval)))
         self.set_state(torch.full((self.n,), float(init_temp), dtype=torch.float64, device=self.dev))
         dist.barrier()
 
@@ -354,13 +382,14 @@ class DistBody:
 
     def stats(self):
         from . import _cabi
-        st = (_cabi.i64 * 5)()
+        st = (_cabi.i64 * 6)()
         _cabi.check(self.lib.tc_dist_stats(self._h, st))
         return {"iters_last": int(st[0]), "iters_total": int(st[1]), "error": int(st[2]),
-                "solves": int(st[3]) % 1000000, "grid": int(st[3]) // 1000000, "failed_solves": int(st[4])}
+                "solves": int(st[3]) % 1000000, "grid": int(st[3]) // 1000000, "failed_solves": int(st[4]),
+                "late_ghosts": int(st[5])}
 
-    PHASES = ["loop top", "spmv", "dot", "reduce-barrier p.q (+allreduce)", "update x,r",
-              "reduce-barrier r.z,r.r (+allreduce)", "direction + halo push", "barrier"]
+    PHASES = ["loop top", "push + spmv", "dot", "reduce-barrier gamma,delta,r.r (+allreduce)", "vector phase",
+              "barrier"]
 
     def profile(self):
         """Accumulated per-phase wall time (ms) seen by block 0 and by the last block; cleared on read."""
