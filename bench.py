@@ -456,8 +456,8 @@ def fe_partitioned(dims, ly, heat, steps, warmup, local_rank, parity_steps=0, wa
     dist.all_reduce(nnz)
     n_tot = dc.n_global
     pl = prof["last"]
-    busy = pl["push + spmv"] + pl["vector phase"] + pl["dot"]
-    wait = pl["reduce-barrier gamma,delta,r.r (+allreduce)"] + pl["barrier"]
+    busy = pl["spmv"] + pl["update x,r"] + pl["direction + halo push"] + pl["dot"]
+    wait = pl["reduce-barrier p.q (+allreduce)"] + pl["reduce-barrier r.z,r.r (+allreduce)"] + pl["barrier"]
     mine = torch.tensor([busy, wait], dtype=torch.float64, device="cuda")
     allp = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
     dist.all_gather(allp, mine)
@@ -505,8 +505,8 @@ def run_ours_partitioned(args, world, rank, local_rank):
         "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"full FE cuboid {nx}x{ny}x{nz} cells = {main['dof']} DOF (the metric's 10M-DOF mesh, "
-                               f"FIXED size) row-partitioned into {world} y-slabs, theta=0.5 Jacobi-PCG step (single-"
-                               "reduction CG), ghosts + reductions by peer stores inside one cooperative kernel per step",
+                               f"FIXED size) row-partitioned into {world} y-slabs, theta=0.5 Jacobi-PCG step, ghosts + "
+                               "reductions by peer stores inside one cooperative kernel per step",
                    "dof": main["dof"], "dof_per_gpu": main["dof_per_gpu"], "nnz": main["nnz"], "pcg_rtol": PCG_RTOL,
                    "h_step_s": H_STEP, "iters_per_step": main["iters_per_step"], "ghost_rows": main["ghost_rows"],
                    "l2": "per-GPU inputs exceed the 126 MB L2", "grid": main["grid"], "late_ghosts": main.get("late_ghosts"),

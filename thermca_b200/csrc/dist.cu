@@ -10,10 +10,10 @@
 //     also trades the local sums with all peers through per-rank mailboxes and adds them in rank
 //     order: one barrier == one global all-reduce, bit-identical scalars on all ranks ->
 //     identical convergence decisions, deterministic results;
-//   * the CG is the single-reduction form (Chronopoulos & Gear): ONE all-reduce and two grid
-//     barriers per iteration instead of two and three;
-//   * a product first pushes the rows the peers need, streams all slices without ghost couplings
-//     and only then does the few boundary slices, so the NVLink latency hides behind the interior.
+//   * the search direction is double buffered, so the rows a peer needs are recomputed from
+//     stable inputs by the pushing threads at the START of the vector phase (no intra-phase race,
+//     no extra barrier): they cross NVLink while the local rows are updated and are in place a
+//     phase and a barrier before the product needs them.
 // Peer memory is exchanged once at setup as CUDA IPC handles (plumbing via torch.distributed in
 // thermca_b200/dist.py).  The reference has nothing comparable (no multi-process code, SURVEY.md
 // fact 1); per rank the arithmetic is the single-GPU PCG of pcg.cuh on the local rows.
@@ -47,16 +47,15 @@ struct TcDistK {
     int n, n_ghost, rank, world;
     int n_bnd;                            // boundary slices (reference at least one ghost column)
     const int* bidx;                      // nslices: -1, or the index of the slice among the boundary slices
-    const int* blist;                     // n_bnd: the boundary slices
     const long long* gptr;                // n_bnd + 1: ghost couplings of boundary slice b (SELL-32: entry k of lane l at
     const int* gslot; const double* gval; //   gptr[b] + 32 k + l) = (ghost slot, operator value); padding = (0, 0.0)
     const double *b, *mass, *adiag;
-    double *y, *u, *p, *s;                // local vectors (n each): state, D^-1 r, search direction, s = P p
-    double *x, *r, *q, *dinv;             // q doubles as w = P u
-    u64 *y_gl, *u_gl;                     // my ghost values, LL encoded: 2 granules per ghost slot (exported memory)
+    double *y, *p[2];                     // local vectors (n each); the search direction is double buffered
+    double *x, *r, *q, *dinv;
+    u64 *y_gl, *p_gl[2];                  // my ghost values, LL encoded: 2 granules per ghost slot (exported memory)
     long long n_send;                     // halo send list: local row -> (peer, ghost slot of the peer)
     const int* send_row; const int* send_peer; const long long* send_dst;
-    u64* peer_y_gl[TC_MAX_WORLD]; u64* peer_u_gl[TC_MAX_WORLD];
+    u64* peer_y_gl[TC_MAX_WORLD]; u64* peer_p_gl[2][TC_MAX_WORLD];
     int n_nbr;                            // ranks I trade ghosts with (only its being non-zero matters to the kernel)
     u64* peer_mb[TC_MAX_WORLD]; u64* my_mb;      // mailboxes [2 parities][TC_MAX_WORLD senders][TC_MB_SLOT]
     TcGridBar bar;
@@ -217,10 +216,11 @@ __device__ __forceinline__ double slice_local_sum(const TcSell& A, const double*
     return sum;
 }
 
-// Local rows times [local vector | ghosts].  The caller has just pushed the rows its peers need (LL encoded) from
-// the SAME, complete vector.  Pass 1 streams every slice without ghost couplings; pass 2 then does the few boundary
-// slices (local part + side list), by which time the peers' pushes have had the whole first pass (tens of
-// microseconds) to cross NVLink; a ghost that is still missing is waited for individually (LL tag).  No halo flags.
+// Local rows times [local vector | ghosts].  Every slice runs the same streaming loop over its LOCAL columns, in the
+// natural slice order (no permutation: an index load ahead of slice_ptr would add a dependent round trip per slice);
+// a slice with ghost couplings (looked up next to slice_ptr) then adds them from its side list.  The ghosts were
+// pushed at the start of the previous vector phase, a whole phase and a barrier earlier (measured: practically never
+// late); one that is still missing is waited for individually (LL tag).  No halo flags.
 template <int MODE>
 __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, const u64* xg, double* y,
                                             const double* b, double shift, unsigned int hseq) {
@@ -231,28 +231,20 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, 
     const int nwarps = gridDim.x * warps_per_block;
     const int nsl = A.nslices;
     double dot = 0.0;
-    for (int pass = 0; pass < 2; ++pass) {
-        const int count = pass == 0 ? nsl : S.n_bnd;
-        for (int idx = warp; idx < count; idx += nwarps) {
-            int s = idx, bi = -1;
-            if (pass == 0) {
-                if (S.n_bnd && S.bidx[s] >= 0) continue;             // boundary slice: second pass
+    for (int s = warp; s < nsl; s += nwarps) {
+        const int bi = S.n_bnd ? S.bidx[s] : -1;
+        double sum = slice_local_sum(A, xl, s, lane);
+        if (bi >= 0)
+            sum = __dadd_rn(sum, ghost_part(S.gptr, S.gslot, S.gval, xg, bi, lane, hseq, S.state, S.spin_limit));
+        const int row = s * 32 + lane;
+        if (row < A.n) {
+            if (MODE == SPMV_B) {
+                y[row] = __dsub_rn(b[row], sum);
             } else {
-                bi = idx; s = S.blist[idx];
-            }
-            double sum = slice_local_sum(A, xl, s, lane);
-            if (bi >= 0)
-                sum = __dadd_rn(sum, ghost_part(S.gptr, S.gslot, S.gval, xg, bi, lane, hseq, S.state, S.spin_limit));
-            const int row = s * 32 + lane;
-            if (row < A.n) {
-                if (MODE == SPMV_B) {
-                    y[row] = __dsub_rn(b[row], sum);
-                } else {
-                    const double xr = tc_ld_x<0>(xl + row);
-                    const double q = S.mass[row] * (xr + shift * sum);
-                    y[row] = q;
-                    dot += xr * q;
-                }
+                const double xr = tc_ld_x<0>(xl + row);
+                const double q = S.mass[row] * (xr + shift * sum);
+                y[row] = q;
+                dot += xr * q;
             }
         }
     }
@@ -270,21 +262,18 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define PROF(k) do { if (prof_row >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
     S.prof[prof_row * 16 + (k)] += t_ - prof_t; prof_t = t_; } } while (0)
 
-// rows my peers need, straight from the (complete, stable) local vector into their LL ghost arrays
-__device__ __forceinline__ void push_ghosts(const TcDistK& S, const double* xl, u64* const* peer_gl, unsigned int hseq,
-                                            int gtid, int gsz) {
-    for (long long e = gtid; e < S.n_send; e += gsz)
-        ll_store(peer_gl[S.send_peer[e]] + 2 * S.send_dst[e], xl[S.send_row[e]], hseq);
+// scaled right-hand side and Jacobi factor of one row (explicit roundings: the owner's loop and the halo push
+// must produce the same bits)
+__device__ __forceinline__ void init_row(const TcDistK& S, int i, double shift, double& bsc, double& d) {
+    const double m = S.mass[i];
+    bsc = __dmul_rn(m, S.q[i]);
+    d = __ddiv_rn(1.0, __dmul_rn(m, __fma_rn(shift, S.adiag[i], 1.0)));
 }
 
-// ONE cooperative launch per theta step: right-hand side, preconditioned CG, update.
-// The CG is the single-reduction form of Chronopoulos & Gear (1989): with u = D^-1 r, w = P u and the recurrences
-//   beta = gamma/gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old),   gamma = r.u, delta = w.u
-//   p = u + beta p,  s = w + beta s (= P p),  x += alpha p,  r -= alpha s,  u = D^-1 r
-// one iteration needs ONE all-reduce (gamma, delta, r.r together) and two grid barriers; classic PCG (pcg.cuh) needs
-// two all-reduces and three barriers.  Across GPUs an all-reduce is ~10 us of NVLink round trip and rank skew
-// (measured, profiles/README.md), which at 1-2.5 M rows per GPU is 10-15 % of an iteration; the extra 8 B/row of vector
-// traffic is 3 %.  Mathematically the same iterates; the convergence test lags one product behind.
+// ONE cooperative launch per theta step: right-hand side, Jacobi-PCG (the iteration of pcg.cuh), update.
+// A single-reduction CG (Chronopoulos & Gear) was measured too: it saves one all-reduce per iteration (~10 us) but its
+// vector phase streams 12 arrays and loses the L2 residency of the 8-array form (23 vs 13 us at 1.25 M rows per GPU):
+// 789 vs 957 M DOF*steps/s at N = 2 (profiles/README.md), so the classic two-reduction form stays.
 template <int MB, int THREADS = TC_DIST_THREADS>
 __global__ void __launch_bounds__(THREADS, MB)
 tc_dist_theta_kernel(TcDistK S) {
@@ -296,78 +285,83 @@ tc_dist_theta_kernel(TcDistK S) {
     unsigned int hseq = (unsigned int)S.state[1];
     PROF_INIT();
     const double shift = S.theta * S.h;
-    double* w = S.q;
+    int pb = 0;
 
     // ---- right-hand side f = b - A y (thermca/solver.py:281) on the local rows -----------------
     ++hseq;
-    push_ghosts(S, S.y, S.peer_y_gl, hseq, gtid, gsz);
+    for (long long e = gtid; e < S.n_send; e += gsz)
+        ll_store(S.peer_y_gl[S.send_peer[e]] + 2 * S.send_dst[e], S.y[S.send_row[e]], hseq);
     slab_spmv<SPMV_B>(S, S.y, S.y_gl, S.q, S.b, 0.0, hseq);
     tc_grid_barrier(S.bar, gen);
     double red[TC_DIST_K];
+    ++hseq;
     {
-        double g_l = 0.0, bb_l = 0.0;
-        for (int i = gtid; i < n; i += gsz) {
-            const double m = S.mass[i];
-            const double bsc = m * S.q[i];
-            const double d = 1.0 / (m * (1.0 + shift * S.adiag[i]));
-            const double u = d * bsc;
-            S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; S.u[i] = u; S.p[i] = 0.0; S.s[i] = 0.0;
-            g_l += bsc * u; bb_l += bsc * bsc;
+        double* p0 = S.p[0];
+        double rho_l = 0.0, bb_l = 0.0;
+        // rows a peer needs first: recomputed from the same stable inputs (bit-identical), pushed over NVLink
+        for (long long e = gtid; e < S.n_send; e += gsz) {
+            double bsc, d;
+            init_row(S, S.send_row[e], shift, bsc, d);
+            ll_store(S.peer_p_gl[0][S.send_peer[e]] + 2 * S.send_dst[e], __dmul_rn(d, bsc), hseq);
         }
-        red[0] = block_sum(g_l, sh); red[2] = block_sum(bb_l, sh); red[1] = 0.0;
+        for (int i = gtid; i < n; i += gsz) {
+            double bsc, d;
+            init_row(S, i, shift, bsc, d);
+            const double z = __dmul_rn(d, bsc);
+            S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; p0[i] = z;
+            rho_l += bsc * z; bb_l += bsc * bsc;
+        }
+        red[0] = block_sum(rho_l, sh); red[1] = block_sum(bb_l, sh); red[2] = 0.0;
     }
-    tc_grid_barrier(S.bar, gen);
-    double gamma_old = 1.0, alpha_old = 1.0, tol2 = 0.0;
+    tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
+    double rho = red[0];
+    const double bb = red[1];
+    const double tol2 = S.rtol * S.rtol * bb;
     int it = 0, status = 0;
-    bool first = true;
-    for (;;) {
-        PROF(0);
-        // ---- w = P u: push my boundary rows of u, stream the interior, then the boundary slices --------------
-        ++hseq;
-        push_ghosts(S, S.u, S.peer_u_gl, hseq, gtid, gsz);
-        const double dot = slab_spmv<SPMV_SHIFT>(S, S.u, S.u_gl, w, nullptr, shift, hseq);
-        PROF(1);
-        red[1] = block_sum(dot, sh);
-        PROF(2);
-        tc_grid_reduce_last<3>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
-        PROF(3);
-        const double gamma = red[0], delta = red[1], rr = red[2];
-        double alpha, beta;
-        // every decision below is uniform over the grid AND over the ranks (bit-identical totals everywhere)
-        if (first) {
-            tol2 = S.rtol * S.rtol * rr;
-            if (!(rr > 0.0)) { status = isfinite(rr) ? 0 : 2; break; }
-            beta = 0.0; alpha = gamma / delta;
-            first = false;
-        } else {
-            if (!(rr > tol2)) { status = isfinite(rr) ? 0 : 2; break; }
-            if (it >= S.maxit) { status = 1; break; }
-            beta = gamma / gamma_old;
-            alpha = gamma / (delta - beta * gamma / alpha_old);
+    if (bb > 0.0) {
+        status = 1;
+        for (; it < S.maxit;) {
+            PROF(0);
+            const double* pe = S.p[pb];
+            const double dot = slab_spmv<SPMV_SHIFT>(S, pe, S.p_gl[pb], S.q, nullptr, shift, hseq);
+            PROF(1);
+            red[0] = block_sum(dot, sh);
+            PROF(2);
+            tc_grid_reduce_last<1>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
+            PROF(3);
+            const double pq = red[0];
+            if (!(pq > 0.0) || !isfinite(pq)) { status = 2; break; }       // uniform over the grid AND over the ranks
+            const double alpha = rho / pq;
+            double rn = 0.0, rr = 0.0;
+            for (int i = gtid; i < n; i += gsz) {
+                S.x[i] += alpha * pe[i];
+                const double ri = S.r[i] - alpha * S.q[i];
+                S.r[i] = ri;
+                rn += ri * (S.dinv[i] * ri);
+                rr += ri * ri;
+            }
+            red[0] = block_sum(rn, sh); red[1] = block_sum(rr, sh);
+            PROF(4);
+            tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
+            PROF(5);
+            ++it;
+            if (!(red[1] > tol2)) { status = isfinite(red[1]) ? 0 : 2; break; }
+            const double beta = red[0] / rho;
+            double* pn = S.p[pb ^ 1];
+            ++hseq;
+            // ghost rows first, so they are in flight while the local rows are updated
+            for (long long e = gtid; e < S.n_send; e += gsz) {
+                const int i = S.send_row[e];
+                ll_store(S.peer_p_gl[pb ^ 1][S.send_peer[e]] + 2 * S.send_dst[e],
+                         __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i])), hseq);
+            }
+            for (int i = gtid; i < n; i += gsz) pn[i] = __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i]));
+            rho = red[0];
+            pb ^= 1;
+            PROF(6);
+            tc_grid_barrier(S.bar, gen);
+            PROF(7);
         }
-        if (!(alpha > 0.0) || !isfinite(alpha)) { status = 2; break; }
-        // ---- vector phase, two row-local sweeps (5 and 7 streams) ------------------------------------------
-        for (int i = gtid; i < n; i += gsz) {
-            const double pn = S.u[i] + beta * S.p[i];
-            S.p[i] = pn;
-            S.x[i] += alpha * pn;
-        }
-        double g_l = 0.0, rr_l = 0.0;
-        for (int i = gtid; i < n; i += gsz) {
-            const double sn = w[i] + beta * S.s[i];
-            S.s[i] = sn;
-            const double ri = S.r[i] - alpha * sn;
-            S.r[i] = ri;
-            const double un = S.dinv[i] * ri;
-            S.u[i] = un;
-            g_l += ri * un; rr_l += ri * ri;
-        }
-        red[0] = block_sum(g_l, sh); red[2] = block_sum(rr_l, sh);
-        gamma_old = gamma; alpha_old = alpha;
-        ++it;
-        PROF(4);
-        tc_grid_barrier(S.bar, gen);
-        PROF(5);
     }
     // ---- y += h * z (not committed after a communication failure / breakdown) ------------------
     if (status != 2)
@@ -403,8 +397,7 @@ struct tc_dist {
     size_t comm_bytes = 0;
     char* peer[TC_MAX_WORLD];
     long long peer_ghost[TC_MAX_WORLD];   // ghost count of every rank (fixes the layout of its buffer)
-    double *y = nullptr, *u = nullptr, *p0 = nullptr, *p1 = nullptr;
-    int* blist = nullptr;
+    double *y = nullptr, *p0 = nullptr, *p1 = nullptr;
     double *x = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr;
     int* state = nullptr;
     unsigned long long* prof = nullptr;
@@ -415,10 +408,10 @@ struct tc_dist {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-// layout of a rank's exported buffer: [y ghosts | u ghosts | mailboxes], ghosts LL encoded (16 B each)
+// layout of a rank's exported buffer: [y ghosts | p ghosts 0 | p ghosts 1 | mailboxes], ghosts LL encoded (16 B each)
 static size_t gl_bytes(long long n_ghost) { return align_up((size_t)(n_ghost > 0 ? n_ghost : 1) * 2 * sizeof(u64), 256); }
 static size_t off_gl(long long n_ghost, int k) { return (size_t)k * gl_bytes(n_ghost); }
-static size_t off_mb(long long n_ghost) { return 2 * gl_bytes(n_ghost); }
+static size_t off_mb(long long n_ghost) { return 3 * gl_bytes(n_ghost); }
 static size_t mb_bytes() { return align_up(sizeof(u64) * 2 * TC_MAX_WORLD * TC_MB_SLOT, 256); }
 
 extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t world, int64_t n_loc,
@@ -434,7 +427,7 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     TC_CUDA(cudaMalloc(&d->comm, d->comm_bytes));
     TC_CUDA(cudaMemset(d->comm, 0, d->comm_bytes));          // tag 0 everywhere: sequence numbers start at 1
     const size_t nb = sizeof(double) * (size_t)n_loc;
-    TC_CUDA(cudaMalloc(&d->y, nb)); TC_CUDA(cudaMalloc(&d->u, nb)); TC_CUDA(cudaMalloc(&d->p0, nb)); TC_CUDA(cudaMalloc(&d->p1, nb));
+    TC_CUDA(cudaMalloc(&d->y, nb)); TC_CUDA(cudaMalloc(&d->p0, nb)); TC_CUDA(cudaMalloc(&d->p1, nb));
     TC_CUDA(cudaMalloc(&d->x, nb)); TC_CUDA(cudaMalloc(&d->r, nb));
     TC_CUDA(cudaMalloc(&d->q, nb)); TC_CUDA(cudaMalloc(&d->dinv, nb));
     TC_CUDA(cudaMalloc(&d->state, sizeof(int) * 16));
@@ -517,32 +510,21 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     K.A = TcSell{(int)d->n, nslices, (const long long*)slice_ptr, col, val, (const short*)col16};
     K.n = (int)d->n; K.n_ghost = (int)d->n_ghost; K.rank = d->rank; K.world = d->world;
     K.n_bnd = n_bnd; K.bidx = bidx;
-    cudaFree(d->blist); d->blist = nullptr;
-    if (n_bnd > 0) {                                         // list of the boundary slices (inverse of bidx)
-        std::vector<int> hb(nslices), hl(n_bnd, -1);
-        TC_CUDA(cudaMemcpy(hb.data(), bidx, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
-        for (int sl = 0; sl < nslices; ++sl)
-            if (hb[sl] >= 0) { TC_CHECK(hb[sl] < n_bnd, "bidx out of range"); hl[hb[sl]] = sl; }
-        for (int k = 0; k < n_bnd; ++k) TC_CHECK(hl[k] >= 0, "bidx does not cover every boundary slice");
-        TC_CUDA(cudaMalloc(&d->blist, sizeof(int) * n_bnd));
-        TC_CUDA(cudaMemcpy(d->blist, hl.data(), sizeof(int) * n_bnd, cudaMemcpyHostToDevice));
-    }
-    K.blist = d->blist;
     K.gptr = (const long long*)gptr; K.gslot = gslot; K.gval = gval;
     K.b = b; K.mass = mass; K.adiag = adiag;
-    K.y = d->y; K.u = d->u; K.p = d->p0; K.s = d->p1;
+    K.y = d->y; K.p[0] = d->p0; K.p[1] = d->p1;
     K.x = d->x; K.r = d->r; K.q = d->q; K.dinv = d->dinv;
     K.y_gl = (u64*)(d->comm + off_gl(d->n_ghost, 0));
-    K.u_gl = (u64*)(d->comm + off_gl(d->n_ghost, 1));
+    K.p_gl[0] = (u64*)(d->comm + off_gl(d->n_ghost, 1)); K.p_gl[1] = (u64*)(d->comm + off_gl(d->n_ghost, 2));
     K.my_mb = (u64*)(d->comm + off_mb(d->n_ghost));
     for (int w = 0; w < TC_MAX_WORLD; ++w) {
-        K.peer_y_gl[w] = nullptr; K.peer_u_gl[w] = nullptr; K.peer_mb[w] = nullptr;
+        K.peer_y_gl[w] = nullptr; K.peer_p_gl[0][w] = nullptr; K.peer_p_gl[1][w] = nullptr; K.peer_mb[w] = nullptr;
     }
     for (int w = 0; w < d->world; ++w) {
         if (!d->peer[w]) continue;
         const long long g = d->peer_ghost[w];
         K.peer_y_gl[w] = (u64*)(d->peer[w] + off_gl(g, 0));
-        K.peer_u_gl[w] = (u64*)(d->peer[w] + off_gl(g, 1));
+        K.peer_p_gl[0][w] = (u64*)(d->peer[w] + off_gl(g, 1)); K.peer_p_gl[1][w] = (u64*)(d->peer[w] + off_gl(g, 2));
         K.peer_mb[w] = (u64*)(d->peer[w] + off_mb(g));
     }
     K.state = d->state;
@@ -660,7 +642,7 @@ extern "C" int tc_dist_close_peers(tc_dist* d) {
 extern "C" int tc_dist_destroy(tc_dist* d) {
     if (!d) return 0;
     tc_dist_close_peers(d);
-    cudaFree(d->comm); cudaFree(d->y); cudaFree(d->u); cudaFree(d->blist); cudaFree(d->p0); cudaFree(d->p1); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
+    cudaFree(d->comm); cudaFree(d->y); cudaFree(d->p0); cudaFree(d->p1); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
     cudaFree(d->state); cudaFree(d->prof);
     cudaFree(d->K.bar.ctr); cudaFree(d->K.bar.part); cudaFree(d->K.bar.res);
     cudaFree(d->send_row); cudaFree(d->send_peer); cudaFree(d->send_dst);

@@ -388,8 +388,8 @@ class DistBody:
                 "solves": int(st[3]) % 1000000, "grid": int(st[3]) // 1000000, "failed_solves": int(st[4]),
                 "late_ghosts": int(st[5])}
 
-    PHASES = ["loop top", "push + spmv", "dot", "reduce-barrier gamma,delta,r.r (+allreduce)", "vector phase",
-              "barrier"]
+    PHASES = ["loop top", "spmv", "dot", "reduce-barrier p.q (+allreduce)", "update x,r",
+              "reduce-barrier r.z,r.r (+allreduce)", "direction + halo push", "barrier"]
 
     def profile(self):
         """Accumulated per-phase wall time (ms) seen by block 0 and by the last block; cleared on read."""
