@@ -145,7 +145,17 @@ def guarded(fn, *a, **k):
 
 
 # ---- CPU legs (oracle) ---------------------------------------------------------------------------
+_CPU_PROBLEM = {}
+
+
 def _cpu_problem(target_dof):
+    if target_dof not in _CPU_PROBLEM:
+        _CPU_PROBLEM.clear()
+        _CPU_PROBLEM[target_dof] = _build_cpu_problem(target_dof)
+    return _CPU_PROBLEM[target_dof]
+
+
+def _build_cpu_problem(target_dof):
     from thermca_b200.synth import cuboid_spec
     from thermca_b200.workloads import cuboid_dims
     import scipy.sparse as sp
@@ -232,8 +242,9 @@ def run_reference(args):
 
 
 def parity_vs_omp(target_dof, steps, threads):
-    """Device theta steps against the CPU oracle (oracle/c/theta_cg_omp.c) on the bounded sample mesh, both at the
-    BENCHMARKED pcg_rtol, from the same initial state; bar 1e-9 relative (north_star, fixed step)."""
+    """Device theta steps against the CPU oracle (oracle/c/theta_cg_omp.c) on the bounded sample mesh (default: the
+    ~1 M-DOF cuboid of BASELINE config #2), both at the BENCHMARKED pcg_rtol, from the same initial state; bar 1e-9
+    relative (north_star, fixed step)."""
     import torch
     from theta_oracle import theta_cg_steps
     from thermca_b200.device import DeviceSolver
@@ -677,7 +688,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dof", type=float, default=10.0e6, help="target DOF of the headline mesh")
     ap.add_argument("--dof20", type=float, default=20.0e6, help="target DOF of the cfg#5 mesh (extra)")
-    ap.add_argument("--cpu-dof", type=float, default=0.5e6, help="DOF of the bounded CPU sample")
+    ap.add_argument("--cpu-dof", type=float, default=1.0e6,
+                    help="DOF of the bounded CPU sample (default: BASELINE config #2's ~1 M-DOF cuboid)")
     ap.add_argument("--pcg-mode", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline only (profiling runs)")
