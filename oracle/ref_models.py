@@ -261,3 +261,54 @@ def steel_sheet():
 
 
 MODELS["steel_sheet"] = steel_sheet
+
+
+def _cuboid_mesh_named(nx, ny, nz, lx, ly, lz):
+    """Kuhn cuboid through the reference Mesh API with the surfaces top / bottom / left (x=0) / rest."""
+    from thermca_b200.synth import kuhn_cuboid_mesh
+    pts, tets, tri_bottom, tri_upper = kuhn_cuboid_mesh(nx, ny, nz, lx, ly, lz, jitter=0.15)
+    z, x = pts[:, 2], pts[:, 0]
+    top = np.all(np.isclose(z[tri_upper], lz), axis=1)
+    left = np.all(np.isclose(x[tri_upper], 0.0), axis=1) & ~top
+    return Mesh(pts, [tets, tri_upper[top], tri_bottom, tri_upper[left], tri_upper[~top & ~left]],
+                ["tetra"] + ["triangle"] * 4, ["body", "top", "bottom", "left", "rest"])
+
+
+def assembly_large(frame_cells=(36, 72, 8), table_cells=(24, 48, 6)):
+    """BASELINE config #4 at its stated size: FE bodies of 10^4..10^5 DOF (one temperature dependent full-order
+    body, one MOR body), two linked LP blocks, temperature dependent fluid nodes with flow links, a stationary node,
+    nonlinear films, an Input driven heat loss — the pattern of ``assembly`` (docs/examples/bearing.ipynb with FE
+    bodies substituted) on meshes from the synthetic generator."""
+    frame_mesh = _cuboid_mesh_named(*frame_cells, 0.5, 1.0, 0.05)
+    table_mesh = _cuboid_mesh_named(*table_cells, 0.4, 0.8, 0.04)
+    with Model() as model:
+        frame = FEPart(frame_mesh, solids.steel, init_temp=22.0, temp_dependent=True, lump_cond_meth=None,
+                       name="frame")
+        table = FEPart(table_mesh, test_steel, init_temp=21.0, mor_dof=8, lump_cond_meth=None, name="table")
+        blk1 = lp_parts.block(matl=solids.steel, init_temp=23.0, width=0.2, hgt=0.1, depth=0.1,
+                              width_div=4, hgt_div=2, depth_div=2, name="blk1")
+        blk2 = lp_parts.block(matl=solids.al, init_temp=20.0, width=0.1, hgt=0.1, depth=0.1,
+                              width_div=2, hgt_div=2, depth_div=2, name="blk2")
+        env = BoundNode(temp=20.0, name="env")
+        inlet = BoundNode(temp=30.0, name="inlet")
+        oil1 = MatlNode(vol=2e-4, matl=fluids.water, init_temp=25.0, name="oil1")
+        oil2 = MatlNode(vol=3e-4, matl=fluids.water, init_temp=24.0, name="oil2")
+        oil1.temp_dependent = True
+        oil2.temp_dependent = True
+        FlowLink(oil1, inlet, vol_flow=1.0e-5)
+        FlowLink(oil2, oil1, vol_flow=lambda t_dest, t_src, fluid: 1.0e-5 * (1.0 + 0.01 * (t_src - 20.0)),
+                 matl=fluids.water)
+        FilmLink(frame.surf.top, oil1, forced_conv.plate(vel=0.5, length=0.5), matl=fluids.water)
+        FilmLink(table.surf.top, oil2, 200.0)
+        FilmLink(blk1.surf.top, frame.surf.bottom, 500.0)
+        FilmLink(blk1.surf.right, blk2.surf.left, film=lambda t0, t1, matl: 300.0 + 0.5 * (t0 + t1))
+        FilmLink(blk2.surf.right, env, combd_film.conv_radn_room(), matl=fluids.air)
+        FilmLink(frame.surf.left, env, free_conv.vert_surf(surf_hgt=0.05), matl=fluids.air)
+        FilmLink(table.surf.left, env, radiation.therm_radn(res_emis=0.7))
+        hub = StatNode(name="hub")
+        CondLink(hub, oil2, 4.0)
+        CondLink(hub, env, 1.5)
+        speed = Input([[0, 100.0], [20, 250.0], [40, 150.0]], name="speed")
+        HeatSource(table.surf.bottom, heat=lambda temp: 0.5 * speed.value * (1.0 - 0.002 * (temp - 20.0)))
+        HeatSource(hub, 12.0)
+    return Network(model), dict(time_span=[0.0, 20.0], method="RK45", rel_tol=1e-4)

@@ -150,3 +150,51 @@ def test_install_everything_full_model_build_on_device(seam):
     part, part_ref = net._fe_parts[0], net_ref._fe_parts[0]
     assert np.allclose(res[part.surf.top].temp(t_end), ref[part_ref.surf.top].temp(t_end), rtol=1e-5)
     assert np.allclose(res[part].temp(t_end), ref[part_ref].temp(t_end), rtol=1e-4, atol=1e-6)
+
+
+def test_config4_sized_assembly_on_device(seam):
+    """BASELINE config #4 at its stated size (oracle/ref_models.py:assembly_large): a 24 k-DOF temperature dependent
+    full-order FE body, an 8.6 k-DOF body reduced to MOR, two linked LP blocks, temperature dependent fluid nodes with
+    flow links, a stationary node, nonlinear films and an Input driven heat loss — built by the reference, solved on
+    the device, against the reference's own RK45."""
+    import ref_models
+    seam.install(stationary=False, assembly=False, mor_basis=False)
+    net, kw = ref_models.assembly_large()
+    res = _sim(net, kw)
+    seam.uninstall()
+    net_ref, _ = ref_models.assembly_large()
+    ref = _sim(net_ref, kw)
+    d, r = res._data, ref._data
+    assert [io.fe_sys.dof for io in net._ffe_ios] == [24309] and [io.fe_sys.dof for io in net._mor_ios] == [8575]
+    assert len(d.times) == len(r.times), "accepted-step sequences differ"
+    assert np.allclose(d.times, r.times, rtol=1e-9, atol=0.0)
+    scale = np.max(np.abs(r.net_temps))
+    assert np.max(np.abs(d.net_temps - r.net_temps)) <= 1e-9 * scale
+    assert np.max(np.abs(d.io_temps - r.io_temps)) <= 1e-9 * np.max(np.abs(r.io_temps))
+    frame, frame_ref = net._fe_parts[0], net_ref._fe_parts[0]
+    assert np.allclose(res[frame.surf.top].temp(20.0), ref[frame_ref.surf.top].temp(20.0), rtol=1e-9)
+
+
+def test_theta_pcg_method_through_the_seam(seam):
+    """``Network.sim(..., method='THETA_PCG', step=h)``: the fixed-step implicit scheme (new method name, passes
+    through the reference's ``sim`` untouched) against a CPU restatement with a sparse direct solver on the
+    reference's own operators (``FFEIO.A``), 1e-9 relative (north_star: fixed step)."""
+    import scipy.sparse as sp
+    import ref_models
+    from theta_oracle import theta_step_direct
+    seam.install(stationary=False, assembly=False, mor_basis=False)
+    net, kw = ref_models.kuhn_cuboid()
+    h, nsteps = 0.5, 8
+    res = net.sim([0.0, h * nsteps], method="THETA_PCG", step=h, pcg_rtol=1e-13, progress_bar=False, num_res_skip=1)
+    d = res._data
+    assert np.allclose(d.times, [0.0, 1.0, 2.0, 3.0, 4.0])
+    io = net._ffe_ios[0]
+    A = sp.csr_matrix(io.A)
+    n = A.shape[0]
+    flux = np.array([1000.0 / io.fe_sys.surf_areas[0], 10.0 * 20.0])          # heat on `bottom`, film * T_env on `upper_faces`
+    b = np.asarray(io.B @ flux).ravel()
+    y = np.full(n, 20.0)
+    for _ in range(nsteps):
+        y = theta_step_direct(A, b - A @ y, y, h, 0.5)
+    got = d.io_temps[-1]
+    assert np.max(np.abs(got - y)) <= 1e-9 * np.max(np.abs(y))

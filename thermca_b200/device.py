@@ -721,6 +721,38 @@ class DeviceSolver:
                 raise RuntimeError(f"PCG did not converge in {bad['failed_solves']} of {nsteps} theta steps "
                                    f"({bad['reason']}, pcg_maxit={pcg_maxit}, pcg_rtol={pcg_rtol})")
 
+    def run_theta(self, t0, t1, h, theta=0.5, num_skip=0, pcg_rtol=1e-8, pcg_maxit=2000, progress=None):
+        """Fixed-step theta scheme from t0 to t1 (new method; the reference has no implicit scheme).  Returns the same
+        dictionary as ``run_rk``: the state is stored at t0, after every ``num_skip + 1``-th step and at t1; the
+        network rows of a stored state (surface means, conductances, sources) come from one extra right-hand side at
+        that state, as after the FSAL stage of the explicit pairs."""
+        nsteps = int(round((t1 - t0) / h))
+        if nsteps < 0 or abs(t0 + nsteps * h - t1) > 1e-9 * max(abs(t1), abs(h)):
+            raise ValueError("THETA_PCG needs time_span[1] - time_span[0] to be a whole number of steps")
+        u = self.u
+        rows = {k: [] for k in ("times", "net_temps", "net_capys", "net_heat_srcs", "cond_data", "clean_data", "io_temps")}
+
+        def store(t):
+            y = self.get_state()
+            self.rhs(t, y)                                   # network arrays at (t, y)
+            ns = self.network_state()
+            T = ns["T"].copy()
+            T[:u] = y[:u]                                    # thermca/solver.py:314
+            rows["times"].append(t); rows["net_temps"].append(T); rows["net_capys"].append(ns["capy"])
+            rows["net_heat_srcs"].append(ns["heat_src"]); rows["cond_data"].append(ns["cond"])
+            rows["clean_data"].append(ns["clean"]); rows["io_temps"].append(y[u:].copy())
+        _cabi.check(self.lib.tc_set_time(self._handle, float(t0)))
+        store(t0)
+        for k in range(nsteps):
+            self.theta_steps(1, h, theta, t0=t0 + k * h, pcg_rtol=pcg_rtol, pcg_maxit=pcg_maxit)
+            if (k + 1) % (num_skip + 1) == 0 or k + 1 == nsteps:
+                store(t0 + (k + 1) * h if k + 1 < nsteps else t1)
+                if progress is not None:
+                    progress({"t": rows["times"][-1]})
+        res = {k: np.asarray(v) for k, v in rows.items()}
+        res.update({"status": 0, "accepted": nsteps, "rejected": 0, "pcg": self.pcg_stats()})
+        return res
+
     def theta_stream(self, host_in, host_out, h, theta=0.5, pcg_rtol=1e-8, pcg_maxit=2000, pcg_mode=0):
         """Host-buffer throughput API: one theta step for every pinned host state in ``host_in`` (list of 1-D float64
         tensors), results into the pinned tensors ``host_out``.  Double buffered: the upload of job j+1 and the

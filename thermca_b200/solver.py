@@ -8,6 +8,11 @@ the same side effects on the ``Network`` the reference's post-processing relies 
 Methods
 * ``'RK45'`` / ``'RK23'`` — scipy's adaptive explicit Runge-Kutta pairs restated on the
   device (step controller included); these are what the reference runs by default.
+* ``'THETA_PCG'`` — fixed-step theta scheme (``step=`` seconds, ``theta=0.5``, ``pcg_rtol=1e-8``): FE / LP parts
+  implicit by Jacobi-PCG (new method; new method names pass through ``Network.sim`` untouched, thermca/solver.py:359-362).
+  Under ``torchrun`` (world size > 1) a network that consists of one full-order FE body with constant boundary data
+  (BASELINE configs #2 / #5: heat sources, films to bound nodes) is row-partitioned over the GPUs
+  (``thermca_b200.dist.DistBody``); every rank returns the full result.
 * ``'ROS2_PCG'`` — adaptive linearly implicit 2-stage Rosenbrock-W method; FE and LP parts solved by
   Jacobi-PCG, unknown network nodes by a small CG (new method; the reference has no implicit scheme).  ``'LSODA'`` requests
   are served by it as well (LSODA's dense Jacobian is unusable beyond ~30k DOF); results
@@ -21,16 +26,17 @@ from .device import DeviceSolver
 from .lowering import lower_network
 
 IMPLICIT_METHODS = ("ROS2_PCG", "LSODA")
+FIXED_STEP_METHODS = ("THETA_PCG",)
 
 
 def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **options):
-    from thermca.resultdata import _ResultCollector      # the reference's own container
-    from sparse import DOK
-
     t0, t1 = float(time_span[0]), float(time_span[1])
     if not isinstance(method, str):
         method = getattr(method, "__name__", str(method))
     spec = lower_network(net)
+    if method in FIXED_STEP_METHODS and _world_size() > 1 and options.get("partition", True):
+        res = _theta_partitioned(spec, t0, t1, num_skip, options)
+        return _collector_from(net, spec, res, t0)
     dev = DeviceSolver(spec)
 
     # the progress thread of Network.sim reads these two attributes every 2 s (network.py:960-985, solver.py:321-325)
@@ -53,11 +59,107 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
                                max_step=options.get("max_step", np.inf),
                                first_step=options.get("first_step"),
                                pcg_rtol=options.get("pcg_rtol", 1e-8), progress=progress)
+        elif method in FIXED_STEP_METHODS:
+            if "step" not in options:
+                raise ValueError("method 'THETA_PCG' needs the step size: sim(..., method='THETA_PCG', step=seconds)")
+            res = dev.run_theta(t0, t1, float(options["step"]), theta=float(options.get("theta", 0.5)),
+                                num_skip=num_skip, pcg_rtol=options.get("pcg_rtol", 1e-8), progress=progress)
         else:
             raise ValueError(f"unknown integration method {method!r}")
         final_net = dev.network_state()
     finally:
         dev.close()
+    res["final_net"] = final_net
+    return _collector_from(net, spec, res, t0)
+
+
+def _world_size():
+    try:
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    except Exception:
+        return 1
+
+
+def _theta_partitioned(spec, t0, t1, num_skip, options):
+    """``THETA_PCG`` under torchrun: ONE full-order FE body with constant boundary data, row-partitioned over the
+    ranks (csrc/dist.cu).  The operator is the lowered part's own ``FFEIO.A`` (films folded into the diagonal,
+    thermca/fem/ffe_io.py:57-60) in a reverse Cuthill-McKee order; the load vector is the device right-hand side at
+    y = 0 (thermca/solver.py:265-281).  Constancy is CHECKED, not assumed: the right-hand side at y = 0 must not
+    depend on time and the conductances must not depend on the temperatures."""
+    import scipy.sparse as sp
+    import torch
+    from .dist import DistBody
+    if "step" not in options:
+        raise ValueError("method 'THETA_PCG' needs the step size: sim(..., method='THETA_PCG', step=seconds)")
+    h, theta = float(options["step"]), float(options.get("theta", 0.5))
+    pcg_rtol = float(options.get("pcg_rtol", 1e-8))
+    u = int(spec["u"])
+    if u != 0 or len(spec["ffe"]) != 1 or spec["lp"] or spec["mor"] or spec["ffe"][0].get("tdep") is not None:
+        raise NotImplementedError("the row-partitioned THETA_PCG path handles one full-order FE body with constant "
+                                  "boundary data (no unknown network nodes, LP / MOR parts or temperature dependent "
+                                  "materials); run this model on one GPU or pass partition=False")
+    part = spec["ffe"][0]
+    n = int(part["dof"])
+    nsteps = int(round((t1 - t0) / h))
+    if abs(t0 + nsteps * h - t1) > 1e-9 * max(abs(t1), abs(h)):
+        raise ValueError("THETA_PCG needs time_span[1] - time_span[0] to be a whole number of steps")
+    # ---- boundary data from the single-GPU pipeline (every rank: the body fits one GPU, the partition is for speed) ----
+    dev = DeviceSolver(spec)
+    try:
+        y0 = dev.initial_state()
+        zero = np.zeros_like(y0)
+        b0 = dev.rhs(t0, zero)
+        net0 = dev.network_state()
+        b1 = dev.rhs(t1, zero)
+        dev.rhs(t0, y0 + 7.0)
+        net1 = dev.network_state()
+        dev.rhs(t0, y0)
+        net_at_y0 = dev.network_state()
+    finally:
+        dev.close()
+    if not (np.array_equal(b0, b1) and np.array_equal(net0["cond"], net1["cond"])
+            and np.array_equal(net0["heat_src"], net1["heat_src"])):
+        raise NotImplementedError("the row-partitioned THETA_PCG path needs constant boundary data (loads or films of "
+                                  "this model depend on time or temperature); run it on one GPU or pass partition=False")
+    A = sp.csr_matrix((part["A_data"], part["A_body"]["indices"], part["A_body"]["indptr"]), shape=(n, n))
+    body = DistBody.from_csr(A, 1.0 / np.asarray(part["M_inv"]), b0, init_temp=0.0)
+    try:
+        body.set_global_state(y0)
+        rows = {k: [] for k in ("times", "net_temps", "net_capys", "net_heat_srcs", "cond_data", "clean_data", "io_temps")}
+        surf_nodes = np.asarray(part["surf_net_idxs"], dtype=np.int64)
+
+        def store(t):
+            y = body.gather_state().cpu().numpy()
+            T = net_at_y0["T"].copy()
+            for s_, node in enumerate(surf_nodes):               # surface mean temperatures, thermca/solver.py:211-220
+                T[node] = float(np.dot(part["C_val"][s_], y[part["C_idx"][s_]]))
+            rows["times"].append(t); rows["net_temps"].append(T); rows["net_capys"].append(net_at_y0["capy"])
+            rows["net_heat_srcs"].append(net_at_y0["heat_src"]); rows["cond_data"].append(net_at_y0["cond"])
+            rows["clean_data"].append(net_at_y0["clean"]); rows["io_temps"].append(y)
+        store(t0)
+        for k in range(nsteps):
+            body.theta_steps(1, h, theta, rtol=pcg_rtol, sync=((k + 1) % 16 == 0))
+            if (k + 1) % (num_skip + 1) == 0 or k + 1 == nsteps:
+                body.check()
+                store(t0 + (k + 1) * h if k + 1 < nsteps else t1)
+        st = body.stats()
+    finally:
+        body.close()
+    torch.cuda.synchronize()
+    res = {k: np.asarray(v) for k, v in rows.items()}
+    res.update({"status": 0, "accepted": nsteps, "rejected": 0, "pcg": st,
+                "final_net": {"T": res["net_temps"][-1], "heat_src": net_at_y0["heat_src"], "capy": net_at_y0["capy"],
+                              "cond": net_at_y0["cond"], "clean": net_at_y0["clean"]}})
+    return res
+
+
+def _collector_from(net, spec, res, t0):
+    """The reference's ``_ResultCollector`` (thermca/resultdata.py:48-65) from the device history, plus the side effects
+    the reference leaves on the ``Network``."""
+    from thermca.resultdata import _ResultCollector      # the reference's own container
+    from sparse import DOK
+    final_net = res["final_net"]
 
     # io_temp structured dtype, thermca/solver.py:154-191
     f64 = np.float64
