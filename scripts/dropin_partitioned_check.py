@@ -21,6 +21,7 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    json_path = os.path.abspath(sys.argv[sys.argv.index("--json") + 1]) if "--json" in sys.argv else None
     os.chdir(tempfile.mkdtemp())                   # the reference's disk_cache writes ./.thermca_cache
     import refenv
     refenv.activate()
@@ -66,8 +67,8 @@ def main():
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
-    if rank == 0 and "--json" in sys.argv:
-        with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
+    if rank == 0 and json_path:
+        with open(json_path, "w") as f:
             json.dump({"world": world, "dof": n, "steps": nsteps, "max_rel_vs_single_gpu": e_single,
                        "max_rel_vs_direct_solver": e_direct, "max_rel_network_rows": e_net, "ok": not bool(flag.item())}, f)
     if flag.item():
