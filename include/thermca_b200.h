@@ -135,7 +135,7 @@ int tc_reset_history(tc_handle h);
 
 /* ---- implicit steps: solve (M + c h K) per FE part with Jacobi-PCG (new numerical method;
  *      the reference has no implicit scheme) ------------------------------ */
-enum { TC_PCG_COOP = 0, TC_PCG_MULTI = 1 };
+enum { TC_PCG_COOP = 0, TC_PCG_MULTI = 1, TC_PCG_COOP_BJ = 2 };   /* 2: block-Jacobi (tc_set_block_precond first) */
 /* one fixed theta step of size h_step: (I + theta h A) d = h f(t + theta h, y); y += d */
 int tc_theta_steps(tc_handle h, int32_t nsteps, double theta, double h_step, double pcg_rtol,
                    int32_t pcg_maxit, int32_t pcg_mode);
@@ -155,6 +155,9 @@ int tc_timing(tc_handle h, int32_t enable, double* pcg_ms, int64_t* pcg_launches
 int tc_pcg_profile(tc_handle h, uint64_t* out16);   /* per-phase ns of block 0 while timing is on */
 /* PCG statistics of the implicit path: total iterations, solves, last iteration count */
 int tc_pcg_stats(tc_handle h, int64_t* stats4);
+/* block-Jacobi preconditioner of full-order FE part `part` (pcg_mode TC_PCG_COOP_BJ): inverses of the 32x32 diagonal
+ * blocks of M + shift*K that belong to the SELL slices, FP32, [slice][j][i], symmetric; device pointer kept by reference */
+int tc_set_block_precond(tc_handle h, int32_t part, const float* binv_dev, double shift);
 /* status2[0]: status of the last FAILED PCG solve since the previous call (0 none, 1 iteration limit reached with
  * the residual above the tolerance, 2 breakdown: non-finite / non-positive curvature); status2[1]: number of
  * failed solves.  Cleared on read.  The host drivers raise on it (there is no silent degradation). */
@@ -180,6 +183,11 @@ int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices, co
  * carrying K in {0,1,2} values, 1 = cooperative_groups grid.sync(), 2 = last-arriver variant (K in {1,2}) */
 int tc_bar_bench(void* cuda_stream, int32_t blocks, int32_t threads, int32_t iters, int32_t K, int32_t mode,
                  double* ns_per_barrier);
+
+/* tc_pcg_solve with the block-Jacobi preconditioner (binv as in tc_set_block_precond) */
+int tc_pcg_solve_bj(void* cuda_stream, int32_t n, int32_t nslices, const int64_t* slice_ptr, const int32_t* col,
+                    const double* val, const double* mass, const double* adiag, const double* rhs, double* x,
+                    double shift, double rtol, int32_t maxit, int32_t* iters, const float* binv);
 
 /* ---- row-partitioned implicit step across GPUs (BASELINE config #5), csrc/dist.cu ------------
  * One process per GPU; the comm buffer of every rank is exported as a CUDA IPC handle and opened

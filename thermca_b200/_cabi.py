@@ -74,9 +74,11 @@ EXPORTS = {
     "tc_pcg_profile": (i32, [vp, C.POINTER(C.c_uint64)]),
     "tc_pcg_status": (i32, [vp, C.POINTER(i64)]),
     "tc_pcg_stats": (i32, [vp, C.POINTER(i64)]),
+    "tc_set_block_precond": (i32, [vp, i32, vp, f64]),
     "tc_sell_spmv": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32]),
     "tc_vm_eval": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "tc_pcg_solve": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32, C.POINTER(i32)]),
+    "tc_pcg_solve_bj": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32, C.POINTER(i32), vp]),
     "tc_bar_bench": (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(f64)]),
     "tc_dist_create": (i32, [C.POINTER(vp), vp, i32, i32, i64, i64]),
     "tc_dist_ipc_handle": (i32, [vp, vp]),

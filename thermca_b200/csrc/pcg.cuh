@@ -182,6 +182,94 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     }
 }
 
+// ---- block-Jacobi variant (north_star (b): "Jacobi / block-Jacobi preconditioned CG") ---------------------------
+// Preconditioner: the 32 x 32 diagonal blocks of M + shift*K that belong to the SELL slices (one warp = one block),
+// inverted once per (h, films) on the host side and stored symmetric in FP32, [slice][j][i]: a preconditioner does not
+// need FP64 (the residual and all recurrences stay FP64) and the application is bandwidth: 4 KB per slice = 128 B/row
+// on top of the ~266 B/row of a point-Jacobi iteration.  Application: lane i holds r_i, z_i = sum_j Binv[j][i] r_j with
+// r_j broadcast by shuffle.  The vector phases therefore run warp-per-slice; z is stored (the direction phase reuses it).
+// Measured (profiles/README.md): fewer iterations (about -25..-35 %) but +48 % bytes per iteration: it only pays for
+// stiff shifts (large h, steady state); point Jacobi stays the default.
+__device__ __forceinline__ double tc_block_apply(const float* __restrict__ binv, int slice, int lane, double rv) {
+    const float* B = binv + (size_t)slice * 1024 + lane;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) acc += (double)__ldg(B + 32 * j) * __shfl_sync(0xffffffffu, rv, j);
+    return acc;
+}
+
+template <int MB, int THREADS = TC_PCG_THREADS>
+__global__ void __launch_bounds__(THREADS, MB)
+tc_pcg_coop_bj_kernel(TcPcg S, const float* __restrict__ binv, double* __restrict__ z, const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    if (S.skip && *S.skip) return;
+    __shared__ double sh[32];
+    unsigned int gen = 0u;
+    const double shift = S.coef * S.ctrl[1];
+    const int n = S.A.n, nsl = S.A.nslices;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    double red[2];
+    {
+        double rho = 0.0, bb = 0.0;
+        for (int sl = warp; sl < nsl; sl += nwarps) {
+            const int i = sl * 32 + lane;
+            const bool live = i < n;
+            const double b = live ? S.mass[i] * S.rhs[i] : 0.0;
+            const double zi = tc_block_apply(binv, sl, lane, b);
+            if (live) { S.r[i] = b; S.x[i] = 0.0; z[i] = zi; S.p[i] = zi; rho += b * zi; bb += b * b; }
+        }
+        red[0] = block_sum(rho, sh);
+        red[1] = block_sum(bb, sh);
+    }
+    tc_grid_reduce<2>(S.bar, gen, red);
+    double rho = red[0];
+    const double bb = red[1];
+    const double tol2 = S.rtol * S.rtol * bb;
+    int it = 0, status = 0;
+    if (bb > 0.0) {
+        status = 1;
+        for (; it < S.maxit;) {
+            const double dot = tc_sell_spmv_body<SPMV_SHIFT, 0>(S.A, S.p, S.q, nullptr, S.mass, shift);
+            red[0] = block_sum(dot, sh);
+            tc_grid_reduce<1>(S.bar, gen, red);
+            const double pq = red[0];
+            if (!(pq > 0.0) || !isfinite(pq)) { status = 2; break; }
+            const double alpha = rho / pq;
+            {
+                double rn = 0.0, rr = 0.0;
+                for (int sl = warp; sl < nsl; sl += nwarps) {
+                    const int i = sl * 32 + lane;
+                    const bool live = i < n;
+                    double ri = 0.0;
+                    if (live) {
+                        S.x[i] += alpha * S.p[i];
+                        ri = S.r[i] - alpha * S.q[i];
+                        S.r[i] = ri;
+                    }
+                    const double zi = tc_block_apply(binv, sl, lane, ri);
+                    if (live) { z[i] = zi; rn += ri * zi; rr += ri * ri; }
+                }
+                red[0] = block_sum(rn, sh);
+                red[1] = block_sum(rr, sh);
+            }
+            tc_grid_reduce<2>(S.bar, gen, red);
+            const double rho_new = red[0], rr = red[1];
+            ++it;
+            if (!(rr > tol2)) { status = isfinite(rr) ? 0 : 2; break; }
+            const double beta = rho_new / rho;
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+                S.p[i] = z[i] + beta * S.p[i];
+            rho = rho_new;
+            tc_grid_barrier(S.bar, gen);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.isc[1] = it; S.isc[2] += it; S.isc[3] += 1;
+        if (status) { S.isc[4] = status; S.isc[5] += 1; }
+    }
+}
+
 // ---- one-launch-per-phase variant ------------------------------------------------------
 __global__ void __launch_bounds__(TC_PCG_THREADS)
 tc_pcg_init_kernel(TcPcg S, const int* __restrict__ done_flag) {

@@ -271,6 +271,8 @@ struct FfePart {
     TcFilmDiag fdiag;
     double *r, *p, *q, *dinv;          // PCG workspace
     TcPcg pcg;
+    const float* binv = nullptr;       // block-Jacobi: inverted 32x32 slice blocks of M + shift K (tc_set_block_precond)
+    double bj_shift = 0.0;             // the shift they were built for
 };
 struct LpPart { tc_lp_desc d; TcSell A; const double* b; double *r, *p, *q, *dinv; TcPcg pcg; };
 struct MorPart { tc_mor_desc d; TcMor M; };
@@ -805,11 +807,29 @@ static int pcg_coop_grid(int sm_count) {
     return g;
 }
 
-static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int* done) {
+static int launch_pcg(tc_solver* s, TcPcg& P, int mode, int coop_grid, const int* done, const float* binv = nullptr) {
     cudaStream_t st = s ? s->stream : nullptr;
     // CG terminates in at most n steps in exact arithmetic: never spin on a tolerance below the
     // attainable residual of a tiny system
     if ((long long)P.maxit > 2LL * P.A.n + 50) P.maxit = 2 * P.A.n + 50;
+    if (mode == TC_PCG_COOP_BJ) {
+        TC_CHECK(binv, "block-Jacobi PCG needs the inverted blocks (tc_set_block_precond)");
+        double* zvec = P.dinv;                      // the point-Jacobi factor array is free in this variant: holds z
+        void* args[] = {(void*)&P, (void*)&binv, (void*)&zvec, (void*)&done};
+        const int cthreads = pcg_coop_threads();
+        int g = tc_balanced_grid(P.A.nslices, cthreads / 32, coop_grid);
+        void* fn = cthreads == 1024 ? (void*)tc_pcg_coop_bj_kernel<2, 1024>
+                   : cthreads == 512 ? (void*)tc_pcg_coop_bj_kernel<4, 512> : (void*)tc_pcg_coop_bj_kernel<8, 256>;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (s && s->timing) {
+            TC_CUDA(cudaEventCreate(&e0)); TC_CUDA(cudaEventCreate(&e1));
+            TC_CUDA(cudaEventRecord(e0, st));
+        }
+        TC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(g), dim3(cthreads), args, 0, st));
+        if (e0) { TC_CUDA(cudaEventRecord(e1, st)); s->ev.push_back(e0); s->ev.push_back(e1); }
+        if (s) s->launches += 1;
+        return 0;
+    }
     if (mode == TC_PCG_COOP) {
         void* args[] = {(void*)&P, (void*)&done};
         int g = coop_grid;
@@ -1075,7 +1095,7 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
                                                                           s->gate_partial, s->gate_counter, flag, done);
             P.skip = flag;
         }
-        if (launch_pcg(s, P, s->pcg_mode, s->coop_grid, done)) return -1;
+        if (launch_pcg(s, P, s->pcg_mode == TC_PCG_COOP_BJ ? TC_PCG_COOP : s->pcg_mode, s->coop_grid, done)) return -1;
     }
     for (auto& p : s->ffe) {
         const bool frozen = p.d.tdep != 0;
@@ -1095,8 +1115,22 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
                                                                           s->gate_partial, s->gate_counter, flag, done);
             P.skip = flag;
         }
-        if (launch_pcg(s, P, s->pcg_mode, s->coop_grid, done)) return -1;
+        if (s->pcg_mode == TC_PCG_COOP_BJ && !frozen) {
+            TC_CHECK(p.binv, "pcg_mode TC_PCG_COOP_BJ: call tc_set_block_precond for every full-order FE part first");
+            if (launch_pcg(s, P, TC_PCG_COOP_BJ, s->coop_grid, done, p.binv)) return -1;
+        } else if (launch_pcg(s, P, s->pcg_mode == TC_PCG_COOP_BJ ? TC_PCG_COOP : s->pcg_mode, s->coop_grid, done)) {
+            return -1;
+        }
     }
+    return 0;
+}
+
+// Inverted diagonal blocks for the block-Jacobi variant of FE part `part`: nslices x 32 x 32 floats, [slice][j][i],
+// symmetric, built for M + shift*K (device pointer, kept by reference; the caller rebuilds them when h or a film changes)
+extern "C" int tc_set_block_precond(tc_handle s, int32_t part, const float* binv_dev, double shift) {
+    TC_CHECK(s && part >= 0 && part < (int)s->ffe.size(), "part index");
+    s->ffe[part].binv = binv_dev;
+    s->ffe[part].bj_shift = shift;
     return 0;
 }
 
@@ -1305,10 +1339,32 @@ extern "C" int tc_sell_spmv(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     return 0;
 }
 
+static int pcg_solve_impl(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
+                          const int64_t* slice_ptr, const int32_t* col, const double* val,
+                          const double* mass, const double* adiag, const double* rhs, double* x,
+                          double shift, double rtol, int32_t maxit, int32_t* iters, const float* binv);
+
 extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
                             const int64_t* slice_ptr, const int32_t* col, const double* val,
                             const double* mass, const double* adiag, const double* rhs, double* x,
                             double shift, double rtol, int32_t maxit, int32_t* iters) {
+    return pcg_solve_impl(cuda_stream, mode, n, nslices, slice_ptr, col, val, mass, adiag, rhs, x, shift, rtol, maxit,
+                          iters, nullptr);
+}
+// same with the block-Jacobi preconditioner (binv: nslices x 32 x 32 floats, see tc_set_block_precond)
+extern "C" int tc_pcg_solve_bj(void* cuda_stream, int32_t n, int32_t nslices, const int64_t* slice_ptr,
+                               const int32_t* col, const double* val, const double* mass, const double* adiag,
+                               const double* rhs, double* x, double shift, double rtol, int32_t maxit,
+                               int32_t* iters, const float* binv) {
+    TC_CHECK(binv, "tc_pcg_solve_bj needs the inverted blocks");
+    return pcg_solve_impl(cuda_stream, TC_PCG_COOP_BJ, n, nslices, slice_ptr, col, val, mass, adiag, rhs, x, shift, rtol,
+                          maxit, iters, binv);
+}
+
+static int pcg_solve_impl(void* cuda_stream, int32_t mode, int32_t n, int32_t nslices,
+                          const int64_t* slice_ptr, const int32_t* col, const double* val,
+                          const double* mass, const double* adiag, const double* rhs, double* x,
+                          double shift, double rtol, int32_t maxit, int32_t* iters, const float* binv) {
     tc_solver tmp;
     tmp.stream = (cudaStream_t)cuda_stream;
     TcPcg P{};
@@ -1337,7 +1393,7 @@ extern "C" int tc_pcg_solve(void* cuda_stream, int32_t mode, int32_t n, int32_t 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cgp = pcg_coop_grid(sms);
-    int rc = launch_pcg(&tmp, P, mode, cgp, nullptr);
+    int rc = launch_pcg(&tmp, P, mode, cgp, nullptr, binv);
     if (rc == 0) {
         cudaError_t e = cudaStreamSynchronize(tmp.stream);
         if (e != cudaSuccess) { tc_set_error(__FILE__, __LINE__, cudaGetErrorString(e)); rc = -1; }

@@ -721,6 +721,22 @@ class DeviceSolver:
                 raise RuntimeError(f"PCG did not converge in {bad['failed_solves']} of {nsteps} theta steps "
                                    f"({bad['reason']}, pcg_maxit={pcg_maxit}, pcg_rtol={pcg_rtol})")
 
+    def set_block_jacobi(self, h, theta=0.5):
+        """Build the block-Jacobi preconditioner (32 x 32 slice blocks of M + theta*h*K, csrc/pcg.cuh) of every
+        full-order FE part for the CURRENT operator values (films folded in) and hand it to the solver; use with
+        ``theta_steps(..., pcg_mode=2)``.  Rebuild after changing h or a film coefficient."""
+        from .linsolve import slice_block_inverses
+        self._binv = []
+        self.stream.synchronize()
+        for k, sell in enumerate(self.ffe_sell):
+            if self.spec["ffe"][k].get("tdep") is not None:
+                continue
+            binv = slice_block_inverses(sell["slice_ptr"], sell["col"], sell["val"], sell["mass"], int(sell["n"]),
+                                        float(theta) * float(h))
+            self._binv.append(binv)
+            _cabi.check(self.lib.tc_set_block_precond(self._handle, k, self._p(binv), float(theta) * float(h)))
+        self.torch.cuda.synchronize(self.dev)
+
     def run_theta(self, t0, t1, h, theta=0.5, num_skip=0, pcg_rtol=1e-8, pcg_maxit=2000, progress=None):
         """Fixed-step theta scheme from t0 to t1 (new method; the reference has no implicit scheme).  Returns the same
         dictionary as ``run_rk``: the state is stored at t0, after every ``num_skip + 1``-th step and at t1; the

@@ -25,7 +25,7 @@ class NotConvergedError(RuntimeError):
     pass
 
 
-def spd_solve(A, b, rtol=1e-12, maxit=None, device=None, return_info=False):
+def spd_solve(A, b, rtol=1e-12, maxit=None, device=None, return_info=False, precond="jacobi"):
     """Solve ``A x = b`` for a symmetric positive definite scipy-sparse ``A`` on the GPU.
 
     Same call shape as ``scipy.sparse.linalg.spsolve(A, b)``.  Raises ``NotConvergedError`` when the
@@ -51,7 +51,7 @@ def spd_solve(A, b, rtol=1e-12, maxit=None, device=None, return_info=False):
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     op = DeviceOperator(A, dev)
     t_b = torch.from_numpy(b).to(dev)
-    t_x = op.solve(t_b, rtol, maxit)
+    t_x = op.solve(t_b, rtol, maxit, precond=precond)
     # independent residual check: r = b - A x
     t_r = op.residual_into(t_x, t_b, torch.empty(n, dtype=torch.float64, device=dev))
     torch.cuda.synchronize(dev)
