@@ -6,9 +6,9 @@
 //     partition works (contiguous slabs of a banded ordering give rank +-1 neighbours, a general
 //     partition any neighbour set); every value carries its own sequence tag ("LL" encoding), so
 //     there are no halo flags and no system-scope fences on the critical path;
-//   * every PCG reduction is folded into a grid barrier (gridbar.cuh) whose last-arriving block
-//     also trades the local sums with all peers through per-rank mailboxes and adds them in rank
-//     order: one barrier == one global all-reduce, bit-identical scalars on all ranks ->
+//   * every PCG reduction is a local reduce-barrier (gridbar.cuh) followed by a one-way mailbox
+//     exchange: block 0 writes the local sums into every rank's mailbox, every block polls its own
+//     rank's mailbox and adds the values in rank order: bit-identical scalars on all ranks ->
 //     identical convergence decisions, deterministic results;
 //   * the search direction is double buffered, so the rows a peer needs are recomputed from
 //     stable inputs by the pushing threads at the START of the vector phase (no intra-phase race,
@@ -105,38 +105,44 @@ __device__ __forceinline__ void ll_peek(const u64* g, u64& lo, u64& hi) {
     asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(g) : "memory");
 }
 
-// All-reduce of the local totals, run by the last block to reach the grid barrier (gridbar.cuh hook): thread w < world
-// writes my values into rank w's mailbox and waits for rank w's values in mine; thread 0 adds them in rank order, so
-// every rank gets bit-identical totals.  A rank whose error flag is up contributes NaN: every rank then leaves the
-// iteration in this very reduction.
-struct TcDistExchange {
-    const TcDistK& S;
-    int seq;
-    __device__ __forceinline__ void operator()(double* tot, int K) const {
-        if (S.world == 1) return;
-        __shared__ double s_in[TC_MAX_WORLD][TC_DIST_K];
-        const int par = seq & 1;
-        int* err = S.state + 4;
-        if ((int)threadIdx.x < S.world) {
-            const int peer = threadIdx.x;
+// Global reduction = local reduce-barrier (gridbar.cuh: flip barrier, every block sums the G partials itself) followed by
+// a mailbox exchange: block 0 writes the local totals into every rank's mailbox (LL encoded, sequence tagged, parity
+// double buffered) and EVERY block polls its own rank's mailbox for the W values and adds them in rank order — the
+// values cross NVLink once, one way, and nobody waits for a second local hop; all ranks and blocks get bit-identical
+// totals.  A rank whose error flag is up contributes NaN: every rank then leaves the iteration in this very reduction.
+// (The variant in which the last-arriving block exchanges and then publishes measured ~5 us more per reduction.)
+// Every wait is bounded; once the error flag is up all waits of this rank return at once, so a failure drains fast.
+template <int K>
+__device__ __forceinline__ void dist_reduce(const TcDistK& S, unsigned int& gen, double* red, int seq) {
+    int* err = S.state + 4;
+    if (S.world == 1) { tc_grid_reduce<K>(S.bar, gen, red); return; }
+    tc_grid_reduce<K>(S.bar, gen, red, err, S.spin_limit);
+    __shared__ double s_in[TC_MAX_WORLD][TC_DIST_K];
+    __shared__ double s_out[TC_DIST_K];
+    const int par = seq & 1;
+    if ((int)threadIdx.x < S.world) {
+        const int peer = threadIdx.x;
+        if (blockIdx.x == 0) {
             const bool bad = *((volatile int*)err) != 0;
             u64* out = S.peer_mb[peer] + ((size_t)par * TC_MAX_WORLD + S.rank) * TC_MB_SLOT;
-            for (int k = 0; k < K; ++k) ll_store(out + 2 * k, bad ? nan("") : tot[k], (unsigned int)seq);
-            const u64* in = S.my_mb + ((size_t)par * TC_MAX_WORLD + peer) * TC_MB_SLOT;
-            for (int k = 0; k < K; ++k) s_in[peer][k] = ll_load(in + 2 * k, (unsigned int)seq, err, S.spin_limit);
+#pragma unroll
+            for (int k = 0; k < K; ++k) ll_store(out + 2 * k, bad ? nan("") : red[k], (unsigned int)seq);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const bool bad = *((volatile int*)err) != 0;
-            for (int k = 0; k < K; ++k) {
-                double s = 0.0;
-                for (int w = 0; w < S.world; ++w) s += s_in[w][k];
-                tot[k] = bad ? nan("") : s;
-            }
-        }
-        __syncthreads();
+        const u64* in = S.my_mb + ((size_t)par * TC_MAX_WORLD + peer) * TC_MB_SLOT;
+#pragma unroll
+        for (int k = 0; k < K; ++k) s_in[peer][k] = ll_load(in + 2 * k, (unsigned int)seq, err, S.spin_limit);
     }
-};
+    __syncthreads();
+    if ((int)threadIdx.x < K) {
+        double s = 0.0;
+        for (int w = 0; w < S.world; ++w) s += s_in[w][threadIdx.x];
+        s_out[threadIdx.x] = *((volatile int*)err) ? nan("") : s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) red[k] = s_out[k];
+    __syncthreads();
+}
 
 #define TC_DIST_THREADS 1024
 
@@ -280,7 +286,7 @@ tc_dist_theta_kernel(TcDistK S) {
     __shared__ double sh[32];
     const int n = S.n;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    unsigned int gen = 0u, tgen = tc_bar_generation(S.bar);
+    unsigned int gen = 0u;
     int rseq = S.state[0];
     unsigned int hseq = (unsigned int)S.state[1];
     PROF_INIT();
@@ -292,7 +298,7 @@ tc_dist_theta_kernel(TcDistK S) {
     for (long long e = gtid; e < S.n_send; e += gsz)
         ll_store(S.peer_y_gl[S.send_peer[e]] + 2 * S.send_dst[e], S.y[S.send_row[e]], hseq);
     slab_spmv<SPMV_B>(S, S.y, S.y_gl, S.q, S.b, 0.0, hseq);
-    tc_grid_barrier(S.bar, gen);
+    tc_grid_barrier(S.bar, gen, S.world > 1 ? S.state + 4 : nullptr, S.spin_limit);
     double red[TC_DIST_K];
     ++hseq;
     {
@@ -313,7 +319,7 @@ tc_dist_theta_kernel(TcDistK S) {
         }
         red[0] = block_sum(rho_l, sh); red[1] = block_sum(bb_l, sh); red[2] = 0.0;
     }
-    tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
+    dist_reduce<2>(S, gen, red, ++rseq);
     double rho = red[0];
     const double bb = red[1];
     const double tol2 = S.rtol * S.rtol * bb;
@@ -327,7 +333,7 @@ tc_dist_theta_kernel(TcDistK S) {
             PROF(1);
             red[0] = block_sum(dot, sh);
             PROF(2);
-            tc_grid_reduce_last<1>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
+            dist_reduce<1>(S, gen, red, ++rseq);
             PROF(3);
             const double pq = red[0];
             if (!(pq > 0.0) || !isfinite(pq)) { status = 2; break; }       // uniform over the grid AND over the ranks
@@ -342,7 +348,7 @@ tc_dist_theta_kernel(TcDistK S) {
             }
             red[0] = block_sum(rn, sh); red[1] = block_sum(rr, sh);
             PROF(4);
-            tc_grid_reduce_last<2>(S.bar, tgen, red, TcDistExchange{S, ++rseq});
+            dist_reduce<2>(S, gen, red, ++rseq);
             PROF(5);
             ++it;
             if (!(red[1] > tol2)) { status = isfinite(red[1]) ? 0 : 2; break; }
@@ -359,7 +365,7 @@ tc_dist_theta_kernel(TcDistK S) {
             rho = red[0];
             pb ^= 1;
             PROF(6);
-            tc_grid_barrier(S.bar, gen);
+            tc_grid_barrier(S.bar, gen, S.world > 1 ? S.state + 4 : nullptr, S.spin_limit);
             PROF(7);
         }
     }

@@ -72,8 +72,11 @@ __device__ __forceinline__ void tc_block_sum_k(double* v) {
 
 // v[k]: this block's contribution, valid in thread 0.  On return every thread of every block holds the grid totals
 // in v[k].  `gen` counts the barriers of this launch (start at 0; only its parity is used).
+// err / limit (optional): bound the wait — after `limit` clock64 ticks (or as soon as *err is non-zero) the block
+// raises *err and carries on with whatever it has (the row-partitioned kernel: a lost peer must not hang the GPU).
 template <int K>
-__device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int& gen, double* v) {
+__device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int& gen, double* v, int* err = nullptr,
+                                               long long limit = 0) {
     const int G = gridDim.x;
     double* bank = B.part + (size_t)(gen & 1u) * TC_BAR_MAXK * TC_MAX_PARTIALS;
     __syncthreads();                                       // every thread's earlier stores are ordered before thread 0's release
@@ -82,7 +85,16 @@ __device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int&
         for (int k = 0; k < K; ++k) bank[k * TC_MAX_PARTIALS + blockIdx.x] = v[k];
         const unsigned int nb = blockIdx.x == 0 ? 0x80000000u - (unsigned int)(G - 1) : 1u;
         const unsigned int old = tc_atom_add_release_gpu_u32(B.ctr, nb);
-        while (((old ^ tc_ld_relaxed_gpu_u32(B.ctr)) & 0x80000000u) == 0u) { }
+        if (err) {
+            const long long t0 = clock64();
+            for (unsigned int spins = 1; ((old ^ tc_ld_relaxed_gpu_u32(B.ctr)) & 0x80000000u) == 0u; ++spins)
+                if ((spins & 255u) == 0u) {
+                    if (*((volatile int*)err)) break;
+                    if (clock64() - t0 > limit) { *((volatile int*)err) = 1; break; }
+                }
+        } else {
+            while (((old ^ tc_ld_relaxed_gpu_u32(B.ctr)) & 0x80000000u) == 0u) { }
+        }
         tc_fence_acq_rel_gpu();                            // acquire; stale L1 lines of this SM are dropped
     }
     __syncthreads();
@@ -112,9 +124,10 @@ __device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int&
     }
     gen += 1u;
 }
-__device__ __forceinline__ void tc_grid_barrier(const TcGridBar& B, unsigned int& gen) {
+__device__ __forceinline__ void tc_grid_barrier(const TcGridBar& B, unsigned int& gen, int* err = nullptr,
+                                                long long limit = 0) {
     double dummy[1];
-    tc_grid_reduce<0>(B, gen, dummy);
+    tc_grid_reduce<0>(B, gen, dummy, err, limit);
 }
 
 
