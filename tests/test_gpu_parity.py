@@ -343,6 +343,11 @@ def test_probe_history_matches_full_history(torch_cuda, golden):
     assert res2["probe_temps"].shape[1] == 2 and len(res2["times"]) == res2["probe_temps"].shape[0]
     with pytest.raises(IndexError):
         simulate(spec, (0.0, 1.0), probe_dofs=[10 ** 6])
+    # an EMPTY probe list is a zero-width probe mode (no part DOFs per step), not full rows
+    res0 = simulate(spec, args[:2], args[2], args[3], args[4], probe_dofs=())
+    assert res0["probes"] and res0["probe_temps"].shape == (len(full["times"]), 0)
+    assert np.array_equal(res0["net_temps"], full["net_temps"])
+    assert np.array_equal(res0["final_io_temps"], full["io_temps"][-1])
 
 
 @pytest.mark.parametrize("name", ["tdep_rod", "assembly"])

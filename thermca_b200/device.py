@@ -596,12 +596,15 @@ class DeviceSolver:
         state; network temperatures (which include every surface mean) are always stored.  ``None`` restores full
         rows.  The full field stays on the device and is fetched on demand with ``get_state()``."""
         if probe_dofs is None:
-            self._probe_idx = None
+            self._probe_idx, self._probe_mode = None, False
             _cabi.check(self.lib.tc_set_probes(self._handle, C.c_void_p(0), 0))
             return
         idx = np.ascontiguousarray(probe_dofs, dtype=np.int64).ravel()
         if idx.size and (idx.min() < 0 or idx.max() >= self.n_io):
             raise IndexError("probe DOF outside the part block of the state")
+        # an EMPTY list is a real zero-width probe mode (no part DOFs per step: the history ring gets no part buffer),
+        # not a request for full rows
+        self._probe_mode = True
         self._probe_idx = self._up(idx) if idx.size else None
         self._n_probe = int(idx.size)
         _cabi.check(self.lib.tc_set_probes(self._handle, self._p(self._probe_idx), int(idx.size)))
@@ -609,7 +612,7 @@ class DeviceSolver:
     def _alloc_history(self, num_skip):
         torch = self.torch
         w_net = 1 + 3 * self.N + 2 * self.nnz
-        self._io_width = self._n_probe if getattr(self, "_probe_idx", None) is not None else self.n_io
+        self._io_width = self._n_probe if getattr(self, "_probe_mode", False) else self.n_io
         per = 8 * (self._io_width + w_net)
         cap = int(max(8, min(8192, self.history_bytes // max(per, 1))))
         self.capacity = cap
@@ -644,7 +647,7 @@ class DeviceSolver:
         return {"times": net[:, 0].copy(), "net_temps": net[:, 1:1 + N].copy(),
                 "net_capys": net[:, 1 + N:1 + 2 * N].copy(), "net_heat_srcs": net[:, 1 + 2 * N:1 + 3 * N].copy(),
                 "cond_data": net[:, 1 + 3 * N:1 + 3 * N + nnz].copy(), "clean_data": net[:, 1 + 3 * N + nnz:].copy(),
-                "io_temps": io, "probes": getattr(self, "_probe_idx", None) is not None}
+                "io_temps": io, "probes": getattr(self, "_probe_mode", False)}
 
     # -- integrators -----------------------------------------------------------------------------------------
     def run_rk(self, t0, t1, rtol=1e-3, atol=1e-6, method="RK45", num_skip=0, max_step=np.inf,
