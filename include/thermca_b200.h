@@ -148,6 +148,12 @@ int tc_theta_steps(tc_handle h, int32_t nsteps, double theta, double h_step, dou
 int tc_ros2_begin(tc_handle h, double t0, double t_end, double rtol, double atol, double max_step,
                   double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode);
 int tc_ros2_advance(tc_handle h, int32_t max_attempts, int32_t poll_every);
+/* adaptive third-order W-method "ROW3w" (4 stages, 3 right-hand sides per attempt; same block structure, history and
+ * controller as tc_ros2_*, error exponent -1/3); serves the reference's method='LSODA' requests (thermca/solver.py:359-362,
+ * thermca/tests/test_fe_part.py:13-99,230-303) */
+int tc_row3_begin(tc_handle h, double t0, double t_end, double rtol, double atol, double max_step,
+                  double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode);
+int tc_row3_advance(tc_handle h, int32_t max_attempts, int32_t poll_every);
 int tc_set_time(tc_handle h, double t);
 /* Switch CUDA-event timing of the PCG launches on/off; returns (and clears) the time and launch
  * counts accumulated since the previous call. */

@@ -466,6 +466,54 @@ def test_ros2_matches_cpu_restatement(torch_cuda, golden, name, t1, bound):
         assert out["pcg"]["solves"] > 0
 
 
+@pytest.mark.parametrize("name,t1,bound", [("coffeecup", 100.0, 0.5), ("coffeecup", 100.0, 0.0), ("plate_ffe", 30.0, 0.0),
+                                           ("plate_mor", 100.0, 0.0), ("assembly", 30.0, 0.5), ("assembly", 30.0, 0.0),
+                                           ("plate_ffe_var", 20.0, 0.0), ("tdep_rod", 0.5, 0.5), ("lp_tdep", 0.5, 0.0)])
+def test_row3_matches_cpu_restatement(torch_cuda, golden, name, t1, bound):
+    """The adaptive third-order W-method on the device against its CPU restatement (oracle/row3_oracle.py: same four
+    stages, block structure, explicit/implicit switch and controller, direct solves instead of PCG): identical
+    accept/reject sequence, temperatures to solver tolerance.  bound = 0 forces every block onto its implicit branch."""
+    from thermca_b200.device import DeviceSolver
+    from row3_oracle import row3_integrate
+    spec, ex = golden(name)
+    t0 = float(ex["sim"]["t0"])
+    ref = row3_integrate(spec, t0, t1, 1e-4, 1e-7, bound=bound)
+    os.environ["TC_W_EXPLICIT_BOUND"] = repr(bound)
+    try:
+        dev = DeviceSolver(spec)
+        out = dev.run_ros2(t0, t1, rtol=1e-4, atol=1e-7, pcg_rtol=1e-13, pcg_maxit=5000, scheme="ROW3")
+        dev.close()
+    finally:
+        del os.environ["TC_W_EXPLICIT_BOUND"]
+    assert (out["accepted"], out["rejected"]) == (ref["accepted"], ref["rejected"])
+    assert np.allclose(out["times"], ref["times"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(out["net_temps"], ref["net_temps"], rtol=1e-7, atol=1e-9)
+    if ref["io_temps"].shape[1]:
+        assert np.abs(out["io_temps"] - ref["io_temps"]).max() <= 1e-7 * np.abs(ref["io_temps"]).max()
+    if bound == 0.0 and (spec["lp"] or spec["ffe"]):
+        assert out["pcg"]["solves"] > 0
+
+
+def test_row3_needs_fewer_attempts_than_ros2_at_equal_tolerance(torch_cuda, golden):
+    """What the third order buys (the LSODA substitute): attempts and linear solves for the plate body at rtol 1e-5,
+    both schemes within 10 * rtol of a tight RK45 run."""
+    from thermca_b200.device import DeviceSolver
+    spec, ex = golden("plate_ffe")
+    t0, t1 = float(ex["sim"]["t0"]), float(ex["sim"]["t1"])
+    dev = DeviceSolver(spec)
+    tight = dev.run_rk(t0, t1, 1e-10, 1e-12, "RK45")
+    dev.close()
+    res = {}
+    for scheme in ("ROS2", "ROW3"):
+        dev = DeviceSolver(spec)
+        out = dev.run_ros2(t0, t1, rtol=1e-5, atol=1e-9, pcg_rtol=1e-11, scheme=scheme)
+        dev.close()
+        err = np.abs(out["io_temps"][-1] - tight["io_temps"][-1]).max() / np.abs(tight["io_temps"][-1]).max()
+        res[scheme] = (out["accepted"] + out["rejected"], err)
+        assert err < 1e-4
+    assert 2 * res["ROW3"][0] < res["ROS2"][0], res          # 4 vs 2 solves per attempt: fewer solves in total
+
+
 # ---- block-Jacobi preconditioner (north_star (b)) ------------------------------------------------------------------
 def test_block_jacobi_pcg_matches_point_jacobi_and_needs_fewer_iterations():
     """theta steps with the block-Jacobi variant (32 x 32 slice blocks of M + theta*h*K, FP32-stored inverses) give the

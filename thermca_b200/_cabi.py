@@ -69,6 +69,8 @@ EXPORTS = {
     "tc_theta_steps": (i32, [vp, i32, f64, f64, f64, i32, i32]),
     "tc_ros2_begin": (i32, [vp, f64, f64, f64, f64, f64, f64, f64, i32, i32]),
     "tc_ros2_advance": (i32, [vp, i32, i32]),
+    "tc_row3_begin": (i32, [vp, f64, f64, f64, f64, f64, f64, f64, i32, i32]),
+    "tc_row3_advance": (i32, [vp, i32, i32]),
     "tc_set_time": (i32, [vp, f64]),
     "tc_timing": (i32, [vp, i32, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
     "tc_pcg_profile": (i32, [vp, C.POINTER(C.c_uint64)]),

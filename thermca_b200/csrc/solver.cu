@@ -1158,6 +1158,7 @@ extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, 
                              double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
+    s->w_bound = TC_W_EXPLICIT_BOUND;
     if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);
     if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / 2.0)) return -1;
     s->evals_per_attempt = 2;
@@ -1225,6 +1226,113 @@ extern "C" int tc_ros2_advance(tc_handle s, int32_t max_attempts, int32_t poll_e
         int burst = poll_every < max_attempts - launched ? poll_every : max_attempts - launched;
         for (int i = 0; i < burst; ++i)
             if (enqueue_ros2_attempt(s)) return -1;
+        launched += burst;
+        if (fetch_flags(s)) return -1;
+        if (s->pin_flags[FL_DONE]) break;
+    }
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- third-order W-method "ROW3w" (4 stages, 3 right-hand sides; derivation: DESIGN.md section 3, CPU restatement:
+// oracle/row3_oracle.py).  Order 3 for ANY Jacobian approximation, so the block structure of the ROS2 path carries
+// over unchanged: FE / LP parts by Jacobi-PCG, unknown network nodes and MOR blocks by their small CG kernels, frozen
+// operators for temperature dependent bodies, blocks left explicit while gamma*h*rho is inside the stability interval
+// of the explicit limit (a third-order explicit Runge-Kutta method, real interval 2.51; bound 0.5 on gamma*h*2 max A_ii).
+//   W u_i = g (F_i + sum_{j<i} c_ij u_j),  F_i = f(t + alpha_i h, y + h sum_j at_ij u_j),  F_4 = F_3,  W = I + g h A
+//   y+ = y + h sum m_i u_i,  err = h sum e_i u_i
+#define TC_ROW3_GAMMA 0.435866521508459
+#define TC_ROW3_BOUND 0.5
+__global__ void tc_stage_rhs_kernel(long long n, const double* __restrict__ F, TcLin L, double g, double* __restrict__ out,
+                                    const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = F[i];
+        for (int j = 0; j < L.nk; ++j) v += L.c[j] * L.k[j][i];
+        out[i] = g * v;
+    }
+}
+
+extern "C" int tc_row3_begin(tc_handle s, double t0, double t_end, double rtol, double atol, double max_step,
+                             double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
+    s->w_bound = TC_ROW3_BOUND;
+    if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);
+    if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / 3.0)) return -1;
+    s->evals_per_attempt = 3;
+    s->nfev_base = 1;
+    if (enqueue_rhs(s, 0.0, s->y, s->K[0])) return -1;
+    tc_copy_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->n_state, s->K[0], s->K[5], nullptr);   // "previous f(t+h, y+)"
+    if (store_initial(s)) return -1;
+    double h0 = first_step;
+    if (!(h0 > 0)) h0 = 1e-3 * fabs(t_end - t0);
+    if (set_ctrl(s, CT_HABS, h0)) return -1;
+    if (!(t_end > t0)) {
+        int one = 1;
+        TC_CUDA(cudaMemcpyAsync(s->flags + FL_DONE, &one, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        TC_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return 0;
+}
+
+static int enqueue_row3_attempt(tc_solver* s) {
+    cudaStream_t st = s->stream;
+    const int* done = s->flags + FL_DONE;
+    const long long n = s->n_state;
+    const int G = s->vec_grid;
+    const double g = TC_ROW3_GAMMA;
+    double *F1 = s->K[0], *u1 = s->K[1], *Fs = s->K[2], *rhs = s->K[3], *u2 = s->K[4], *fend = s->K[5], *u3 = s->K[6];
+    double* u4 = s->K[2];                          // F_3 is consumed before u_4 is written
+    tc_ros2_reuse_kernel<<<G, 256, 0, st>>>(n, fend, F1, s->flags);
+    tc_prepare_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
+    TcLin L{};
+    // stage 1
+    L.nk = 0;
+    tc_stage_rhs_kernel<<<G, 256, 0, st>>>(n, F1, L, g, rhs, done);
+    if (enqueue_block_solve(s, g, rhs, u1, true)) return -1;
+    // stage 2
+    L.nk = 1; L.k[0] = u1; L.c[0] = 1.1021597568860195;
+    tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L, s->ctrl, s->ystage, done);
+    if (enqueue_rhs(s, 0.48039453938051824, s->ystage, Fs)) return -1;
+    L.c[0] = -3.3064792706580586;
+    tc_stage_rhs_kernel<<<G, 256, 0, st>>>(n, Fs, L, g, rhs, done);
+    if (enqueue_block_solve(s, g, rhs, u2, true)) return -1;
+    // stage 3
+    L.nk = 2; L.k[0] = u1; L.c[0] = 2.0458152611220233; L.k[1] = u2; L.c[1] = 1.1251523859013772;
+    tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L, s->ctrl, s->ystage, done);
+    if (enqueue_rhs(s, 0.6753387630276377, s->ystage, Fs)) return -1;
+    L.c[0] = -3.1394810593440803; L.c[1] = -2.5814150212946312;
+    tc_stage_rhs_kernel<<<G, 256, 0, st>>>(n, Fs, L, g, rhs, done);
+    if (enqueue_block_solve(s, g, rhs, u3, true)) return -1;
+    // stage 4 (same right-hand side F_3)
+    L.nk = 3; L.k[0] = u1; L.c[0] = -4.6371650178370949; L.k[1] = u2; L.c[1] = -3.1668182208148394;
+    L.k[2] = u3; L.c[2] = -2.0579924311095659;
+    tc_stage_rhs_kernel<<<G, 256, 0, st>>>(n, Fs, L, g, rhs, done);
+    if (enqueue_block_solve(s, g, rhs, u4, true)) return -1;
+    // new state, f(t + h, y+), error estimate, accept / reject, snapshot
+    TcLin Ly{};
+    Ly.nk = 4; Ly.k[0] = u1; Ly.k[1] = u2; Ly.k[2] = u3; Ly.k[3] = u4;
+    Ly.c[0] = 3.6624707580663167; Ly.c[1] = 2.2151642855284215; Ly.c[2] = 1.5089213118874722; Ly.c[3] = 1.1081682922152405;
+    tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, Ly, s->ctrl, s->ynew, done);
+    if (enqueue_rhs(s, 1.0, s->ynew, fend)) return -1;
+    TcLin Le = Ly;
+    Le.c[0] = 0.25290167107671513; Le.c[1] = 0.04754813669718994; Le.c[2] = 0.23046773281334043; Le.c[3] = 0.4960290010539171;
+    tc_error_control_kernel<<<G, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    tc_accept_kernel<<<G, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, nullptr, nullptr, s->flags, s->hist_io, s->probe_idx,
+                                        s->n_probe);
+    tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net, s->y);
+    return 0;
+}
+
+extern "C" int tc_row3_advance(tc_handle s, int32_t max_attempts, int32_t poll_every) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    if (poll_every <= 0) poll_every = 4;
+    int launched = 0;
+    while (launched < max_attempts) {
+        int burst = poll_every < max_attempts - launched ? poll_every : max_attempts - launched;
+        for (int i = 0; i < burst; ++i)
+            if (enqueue_row3_attempt(s)) return -1;
         launched += burst;
         if (fetch_flags(s)) return -1;
         if (s->pin_flags[FL_DONE]) break;

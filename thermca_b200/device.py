@@ -679,11 +679,14 @@ class DeviceSolver:
         return res
 
     def run_ros2(self, t0, t1, rtol=1e-3, atol=1e-6, num_skip=0, max_step=np.inf, first_step=None,
-                 pcg_rtol=1e-8, pcg_maxit=2000, pcg_mode=0, attempts_per_poll=4, progress=None):
-        """Adaptive linearly implicit ROS2 (new method; FE parts implicit via Jacobi-PCG)."""
+                 pcg_rtol=1e-8, pcg_maxit=2000, pcg_mode=0, attempts_per_poll=4, progress=None, scheme="ROS2"):
+        """Adaptive linearly implicit W-methods (new methods; FE / LP parts implicit via Jacobi-PCG): ``scheme="ROS2"``
+        (2 stages, order 2) or ``"ROW3"`` (4 stages, 3 right-hand sides, order 3 for any Jacobian approximation)."""
+        begin, advance = {"ROS2": (self.lib.tc_ros2_begin, self.lib.tc_ros2_advance),
+                          "ROW3": (self.lib.tc_row3_begin, self.lib.tc_row3_advance)}[scheme]
         self._alloc_history(num_skip)
         ms = 0.0 if not np.isfinite(max_step) else float(max_step)
-        _cabi.check(self.lib.tc_ros2_begin(self._handle, float(t0), float(t1), float(rtol), float(atol), ms,
+        _cabi.check(begin(self._handle, float(t0), float(t1), float(rtol), float(atol), ms,
                                            float(first_step or 0.0), float(pcg_rtol), int(pcg_maxit), int(pcg_mode)))
         out = {"net": [], "io": []}
         while True:
@@ -692,7 +695,7 @@ class DeviceSolver:
                 break
             if info["status"] == 2 or info["stored"] + attempts_per_poll > self.capacity:
                 self._drain(out)
-            _cabi.check(self.lib.tc_ros2_advance(self._handle, int(attempts_per_poll), int(attempts_per_poll)))
+            _cabi.check(advance(self._handle, int(attempts_per_poll), int(attempts_per_poll)))
             if progress is not None:
                 progress(self.info())
         info = self.info()

@@ -13,10 +13,11 @@ Methods
   Under ``torchrun`` (world size > 1) a network that consists of one full-order FE body with constant boundary data
   (BASELINE configs #2 / #5: heat sources, films to bound nodes) is row-partitioned over the GPUs
   (``thermca_b200.dist.DistBody``); every rank returns the full result.
-* ``'ROS2_PCG'`` — adaptive linearly implicit 2-stage Rosenbrock-W method; FE and LP parts solved by
-  Jacobi-PCG, unknown network nodes by a small CG (new method; the reference has no implicit scheme).  ``'LSODA'`` requests
-  are served by it as well (LSODA's dense Jacobian is unusable beyond ~30k DOF); results
-  agree within the requested tolerances at output times.
+* ``'ROS2_PCG'`` / ``'ROW3_PCG'`` — adaptive linearly implicit Rosenbrock-W methods of order 2 (2 stages) and order 3
+  (4 stages, 3 right-hand sides; order 3 for any Jacobian approximation); FE and LP parts solved by Jacobi-PCG, unknown
+  network nodes and stiff MOR blocks by small CG kernels (new methods; the reference has no implicit scheme).
+  ``'LSODA'`` requests are served by ``ROW3`` (LSODA's dense Jacobian is unusable beyond ~30k DOF); results agree within
+  the requested tolerances at output times.
 """
 from __future__ import annotations
 
@@ -25,7 +26,8 @@ import numpy as np
 from .device import DeviceSolver
 from .lowering import lower_network
 
-IMPLICIT_METHODS = ("ROS2_PCG", "LSODA")
+IMPLICIT_METHODS = ("ROS2_PCG", "ROW3_PCG", "LSODA")
+_SCHEME = {"ROS2_PCG": "ROS2", "ROW3_PCG": "ROW3", "LSODA": "ROW3"}
 FIXED_STEP_METHODS = ("THETA_PCG",)
 
 
@@ -58,7 +60,7 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
             res = dev.run_ros2(t0, t1, rel_tol, abs_tol, num_skip,
                                max_step=options.get("max_step", np.inf),
                                first_step=options.get("first_step"),
-                               pcg_rtol=options.get("pcg_rtol", 1e-8), progress=progress)
+                               pcg_rtol=options.get("pcg_rtol", 1e-8), progress=progress, scheme=_SCHEME[method])
         elif method in FIXED_STEP_METHODS:
             if "step" not in options:
                 raise ValueError("method 'THETA_PCG' needs the step size: sim(..., method='THETA_PCG', step=seconds)")
@@ -277,7 +279,8 @@ def simulate(net, time_span, rel_tol=1e-3, abs_tol=1e-6, method="RK45", num_res_
                              first_step=options.get("first_step"))
         elif method in IMPLICIT_METHODS:
             res = dev.run_ros2(t0, t1, rel_tol, abs_tol, num_res_skip, max_step=options.get("max_step", np.inf),
-                               first_step=options.get("first_step"), pcg_rtol=options.get("pcg_rtol", 1e-8))
+                               first_step=options.get("first_step"), pcg_rtol=options.get("pcg_rtol", 1e-8),
+                               scheme=_SCHEME[method])
         else:
             raise ValueError(f"unknown integration method {method!r}")
         u = int(spec["u"])
