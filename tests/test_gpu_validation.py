@@ -1,7 +1,8 @@
 """Physical validation the reference ships: the steel plate against ANSYS
 (thermca/tests/test_fe_part.py:230-303, 'cuboid flat ansys.csv'; sample points in tests/golden/plate_ansys.npz,
 oracle/make_golden_ansys.py), with the reference test's own tolerances.  The reference runs this case with
-LSODA; the drop-in serves LSODA requests with the adaptive ROS2-PCG scheme, and RK45 is checked too."""
+LSODA; the drop-in serves LSODA requests with the adaptive third-order W-method (ROW3), the second-order ROS2-PCG and
+RK45 are checked too."""
 import os
 
 import numpy as np
@@ -33,7 +34,7 @@ def _probe(spec, out, a):
     return bottom, bv, tv
 
 
-@pytest.mark.parametrize("method", ["ROS2_PCG", "RK45"])
+@pytest.mark.parametrize("method", ["ROW3_PCG", "ROS2_PCG", "RK45"])
 def test_full_order_plate_against_ansys(golden, method):
     from thermca_b200.device import DeviceSolver
     a = _ansys()
@@ -47,7 +48,8 @@ def test_full_order_plate_against_ansys(golden, method):
     else:
         # second-order ROS2 with linear interpolation between its (long) steps needs 1e-4 for the 0.3 % the
         # reference reaches with LSODA at 1e-3
-        out = dev.run_ros2(0.0, t_end, 1e-4, 1e-6)
+        out = dev.run_ros2(0.0, t_end, 1e-4, 1e-6, scheme="ROW3" if method == "ROW3_PCG" else "ROS2")
+        print(method, "on the full-order plate: accepted", out["accepted"], "rejected", out["rejected"])
     dev.close()
     bottom, bv, tv = _probe(spec, out, a)
     init = 20.0
@@ -56,7 +58,7 @@ def test_full_order_plate_against_ansys(golden, method):
     assert np.allclose(a["bottom_vertex"] - init, bv - init, rtol=0.006)
 
 
-@pytest.mark.parametrize("method", ["RK45", "ROS2_PCG"])
+@pytest.mark.parametrize("method", ["RK45", "ROS2_PCG", "ROW3_PCG"])
 def test_reduced_plate_against_ansys(golden, method):
     """MOR body (golden plate_mor, mor_dof = 10; the reference test uses 30): mean bottom temperature within the
     reference test's 0.3 % (test_fe_part.py:301).  With ROS2 the long steps of this 9 h simulation put the reduced
@@ -68,8 +70,8 @@ def test_reduced_plate_against_ansys(golden, method):
     if method == "RK45":
         out = dev.run_rk(0.0, float(a["time"][-1]), 1e-3, 1e-6, "RK45", num_skip=20)
     else:
-        out = dev.run_ros2(0.0, float(a["time"][-1]), 1e-4, 1e-6)
-        print("ROS2 on the reduced plate: accepted", out["accepted"], "rejected", out["rejected"])
+        out = dev.run_ros2(0.0, float(a["time"][-1]), 1e-4, 1e-6, scheme="ROW3" if method == "ROW3_PCG" else "ROS2")
+        print(method, "on the reduced plate: accepted", out["accepted"], "rejected", out["rejected"])
     dev.close()
     bottom, _, _ = _probe(spec, out, a)
     assert np.allclose(a["bottom"] - 20.0, bottom - 20.0, rtol=0.003)

@@ -236,3 +236,27 @@ def test_package_level_install_and_uninstall():
     finally:
         thermca_b200.uninstall()
     assert (rs.transient_solution, fes.spsolve, fes.FESystem.__dict__["fem_matrices_from_skfem"], mio.transform) == before
+
+
+def test_row3w_coefficients_satisfy_the_w_order_conditions():
+    """The constants of the third-order W-method (oracle/row3_oracle.py == csrc/solver.cu:enqueue_row3_attempt), mapped
+    back from the implementation form, satisfy all eight order conditions of a W-method of order 3 (Hairer & Wanner,
+    Solving ODE II, sec. IV.7), R(inf) = 0 for the exact Jacobian, and the embedded result is of order 2."""
+    import row3_oracle as R
+    g = R.GAMMA
+    C = np.zeros((4, 4)); C[1, 0] = R.C21; C[2, 0], C[2, 1] = R.C31, R.C32; C[3, 0], C[3, 1], C[3, 2] = R.C41, R.C42, R.C43
+    At = np.zeros((4, 4)); At[1, 0] = R.AT21; At[2, 0], At[2, 1] = R.AT31, R.AT32; At[3] = At[2]
+    Gam = np.linalg.inv(np.eye(4) / g - C)                    # Gamma^-1 = diag(1/gamma) - C
+    A = At @ Gam
+    b = np.array(R.M) @ Gam
+    bh = (np.array(R.M) - np.array(R.E)) @ Gam
+    al, gp = A.sum(1), Gam.sum(1)
+    assert np.allclose(np.diag(Gam), g) and np.allclose(np.triu(Gam, 1), 0) and np.allclose(np.triu(A), 0, atol=1e-14)
+    assert np.allclose(al, R.ALPHA, atol=1e-14)
+    conds = [b.sum() - 1, b @ al - 0.5, b @ gp, b @ al ** 2 - 1 / 3, b @ (A @ al) - 1 / 6, b @ (A @ gp), b @ (Gam @ al),
+             b @ (Gam @ gp)]
+    assert np.max(np.abs(conds)) < 1e-13
+    assert abs(1 - b @ np.linalg.solve(A + Gam, np.ones(4))) < 1e-12          # R(inf) = 0
+    assert np.max(np.abs([bh.sum() - 1, bh @ al - 0.5, bh @ gp])) < 1e-13      # embedded: order 2
+    for z in list(1j * np.logspace(-2, 4, 60)) + list(-np.logspace(-2, 6, 60)):
+        assert abs(1 + z * b @ np.linalg.solve(np.eye(4) - z * (A + Gam), np.ones(4))) <= 1 + 1e-9
