@@ -8,6 +8,7 @@ import numpy as np
 from thermca_b200.device import DeviceSolver
 from thermca_b200.spec import load_spec
 
+out_path = os.path.abspath(sys.argv[1]) if len(sys.argv) > 1 else None
 rows = []
 cases = [("plate_ffe", None, None), ("plate_ffe", 0.0, 32428.0), ("plate_mor", 0.0, 32428.0), ("coffeecup", 0.0, 300.0),
          ("assembly", 0.0, 45.0), ("lp_tdep", 0.01, 3.0)]
@@ -56,5 +57,5 @@ try:
             print(json.dumps(rec), flush=True)
 except Exception as e:
     print("reference LSODA leg skipped:", type(e).__name__, str(e)[:200])
-if len(sys.argv) > 1:
-    json.dump(rows, open(sys.argv[1], "w"), indent=1)
+if out_path:
+    json.dump(rows, open(out_path, "w"), indent=1)

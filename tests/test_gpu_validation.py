@@ -70,7 +70,10 @@ def test_reduced_plate_against_ansys(golden, method):
     if method == "RK45":
         out = dev.run_rk(0.0, float(a["time"][-1]), 1e-3, 1e-6, "RK45", num_skip=20)
     else:
-        out = dev.run_ros2(0.0, float(a["time"][-1]), 1e-4, 1e-6, scheme="ROW3" if method == "ROW3_PCG" else "ROS2")
+        # the third-order scheme takes ~130 steps over these 9 h at 1e-4: the linear interpolation between stored
+        # steps (what Result.temp does) then dominates the 0.3 %, so it runs at 1e-5 (~290 steps; ROS2: 1630 at 1e-4)
+        out = dev.run_ros2(0.0, float(a["time"][-1]), 1e-5 if method == "ROW3_PCG" else 1e-4, 1e-6,
+                           scheme="ROW3" if method == "ROW3_PCG" else "ROS2")
         print(method, "on the reduced plate: accepted", out["accepted"], "rejected", out["rejected"])
     dev.close()
     bottom, _, _ = _probe(spec, out, a)
