@@ -47,6 +47,7 @@ struct TcDistK {
     int n, n_ghost, rank, world;
     int n_bnd;                            // boundary slices (reference at least one ghost column)
     const int* bidx;                      // nslices: -1, or the index of the slice among the boundary slices
+    int rot;                              // cyclic rotation of the slice order (see tc_dist_set_operator)
     const long long* gptr;                // n_bnd + 1: ghost couplings of boundary slice b (SELL-32: entry k of lane l at
     const int* gslot; const double* gval; //   gptr[b] + 32 k + l) = (ghost slot, operator value); padding = (0, 0.0)
     const double *b, *mass, *adiag;
@@ -223,7 +224,10 @@ __device__ __forceinline__ double slice_local_sum(const TcSell& A, const double*
 }
 
 // Local rows times [local vector | ghosts].  Every slice runs the same streaming loop over its LOCAL columns, in the
-// natural slice order (no permutation: an index load ahead of slice_ptr would add a dependent round trip per slice);
+// natural slice order up to a cyclic rotation (no permutation array: an index load ahead of slice_ptr would add a
+// dependent round trip per slice).  The rotation puts the boundary slices (the leading and trailing runs of a block of
+// contiguous rows) into the FIRST round of the grid-stride loop, on the highest-numbered warps: those are the warps
+// without a slice in the remainder round, so the ~4 dependent loads of the ghost side list are absorbed by their slack;
 // a slice with ghost couplings (looked up next to slice_ptr) then adds them from its side list.  The ghosts were
 // pushed at the start of the previous vector phase, a whole phase and a barrier earlier (measured: practically never
 // late); one that is still missing is waited for individually (LL tag).  No halo flags.
@@ -237,7 +241,9 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, 
     const int nwarps = gridDim.x * warps_per_block;
     const int nsl = A.nslices;
     double dot = 0.0;
-    for (int s = warp; s < nsl; s += nwarps) {
+    for (int idx = warp; idx < nsl; idx += nwarps) {
+        int s = idx + S.rot;
+        if (s >= nsl) s -= nsl;
         const int bi = S.n_bnd ? S.bidx[s] : -1;
         double sum = slice_local_sum(A, xl, s, lane);
         if (bi >= 0)
@@ -553,6 +559,21 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     d->grid = occ * sms;
     if (d->grid > TC_MAX_PARTIALS) d->grid = TC_MAX_PARTIALS;
     d->grid = tc_balanced_grid(nslices, dist_threads() / 32, d->grid);
+    K.rot = 0;
+    if (n_bnd > 0) {
+        std::vector<int> hb(nslices);
+        TC_CUDA(cudaMemcpy(hb.data(), bidx, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
+        int nl = 0, nu = 0;
+        while (nl < nslices && hb[nl] >= 0) ++nl;
+        while (nu < nslices - nl && hb[nslices - 1 - nu] >= 0) ++nu;
+        const long long nwarps = (long long)d->grid * (dist_threads() / 32);
+        if (nl + nu > 0 && nl + nu <= nwarps && nwarps <= nslices) {
+            // first-round index range [nwarps - (nl + nu), nwarps) <-> cyclic slice run starting at nslices - nu
+            long long rot = ((long long)(nslices - nu) - (nwarps - (nl + nu))) % nslices;
+            if (rot < 0) rot += nslices;
+            K.rot = (int)rot;
+        }
+    }
     return 0;
 }
 
