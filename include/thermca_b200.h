@@ -223,6 +223,16 @@ int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* slice_ptr, 
                          const double* b, int32_t n_bnd, const int32_t* bidx, const int64_t* gptr,
                          const int32_t* gslot, const double* gval);
 int tc_dist_set_load(tc_dist* d, const double* b_local_dev);     /* swap the load vector (time-varying loads) */
+int tc_dist_set_state_ptr(tc_dist* d, double* y_local_dev);      /* work on a caller-owned state block (NULL: own) */
+/* surface means of a partitioned body: sum the per-rank partial sums of jobs [job0, job0 + njobs) over all ranks in
+ * rank order (thermca/solver.py:211-220); partials / first_block / nblk: the job tables of tc_set_network */
+int tc_dist_mean_exchange(tc_dist* d, double* partials_dev, const int32_t* first_block_dev, const int32_t* nblk_dev,
+                          int32_t job0, int32_t njobs);
+int64_t tc_dist_local_rows(tc_dist* d);
+void* tc_dist_stream(tc_dist* d);
+/* general networks on several GPUs: FE part `part` of solver h holds the LOCAL rows of a row-partitioned body; tc_rhs and
+ * tc_theta_steps then add the peers' rows to its surface means and run its product / solve in the fused kernel */
+int tc_attach_dist(tc_handle h, int32_t part, tc_dist* d, int32_t first_job, int32_t n_jobs);
 int tc_dist_set_state(tc_dist* d, const double* y_local_dev);
 int tc_dist_get_state(tc_dist* d, double* y_local_dev);          /* fails (-3/-4) if a step since the last reset failed */
 int tc_dist_copy_state_async(tc_dist* d, double* y_local_dev, int32_t dir);   /* enqueue only: 0 set, 1 get */

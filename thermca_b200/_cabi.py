@@ -88,6 +88,11 @@ EXPORTS = {
     "tc_dist_set_halo": (i32, [vp, i64, vp, vp, vp, i32, vp]),
     "tc_dist_set_operator": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "tc_dist_set_load": (i32, [vp, vp]),
+    "tc_dist_set_state_ptr": (i32, [vp, vp]),
+    "tc_dist_mean_exchange": (i32, [vp, vp, vp, vp, i32, i32]),
+    "tc_dist_local_rows": (i64, [vp]),
+    "tc_dist_stream": (vp, [vp]),
+    "tc_attach_dist": (i32, [vp, i32, vp, i32, i32]),
     "tc_dist_set_state": (i32, [vp, vp]),
     "tc_dist_get_state": (i32, [vp, vp]),
     "tc_dist_copy_state_async": (i32, [vp, vp, i32]),

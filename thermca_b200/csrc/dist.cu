@@ -33,6 +33,8 @@
 #define TC_MAX_WORLD 16
 #define TC_DIST_K 3                     // values per all-reduce
 #define TC_MB_SLOT 8                    // u64 granules per (parity, sender) mailbox slot (2 per value, padded to 64 B)
+#define TC_MB2_VALUES 64                // surface means of a partitioned body per exchange (second mailbox region)
+#define TC_MB2_SLOT (2 * TC_MB2_VALUES)
 
 typedef unsigned long long u64;
 
@@ -59,6 +61,7 @@ struct TcDistK {
     u64* peer_y_gl[TC_MAX_WORLD]; u64* peer_p_gl[2][TC_MAX_WORLD];
     int n_nbr;                            // ranks I trade ghosts with (only its being non-zero matters to the kernel)
     u64* peer_mb[TC_MAX_WORLD]; u64* my_mb;      // mailboxes [2 parities][TC_MAX_WORLD senders][TC_MB_SLOT]
+    u64* peer_mb2[TC_MAX_WORLD]; u64* my_mb2;    // surface-mean mailboxes [2][TC_MAX_WORLD][TC_MB2_SLOT]
     TcGridBar bar;
     int* state;                           // [0] reduction seq, [1] halo seq, [2] iters last, [3] iters total,
                                           // [4] comm error, [5] solves, [7] status of the last failed solve, [8] failed solves
@@ -420,11 +423,14 @@ struct tc_dist {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-// layout of a rank's exported buffer: [y ghosts | p ghosts 0 | p ghosts 1 | mailboxes], ghosts LL encoded (16 B each)
+// layout of a rank's exported buffer: [y ghosts | p ghosts 0 | p ghosts 1 | reduction mailboxes | surface-mean
+// mailboxes], ghosts LL encoded (16 B each)
 static size_t gl_bytes(long long n_ghost) { return align_up((size_t)(n_ghost > 0 ? n_ghost : 1) * 2 * sizeof(u64), 256); }
 static size_t off_gl(long long n_ghost, int k) { return (size_t)k * gl_bytes(n_ghost); }
 static size_t off_mb(long long n_ghost) { return 3 * gl_bytes(n_ghost); }
 static size_t mb_bytes() { return align_up(sizeof(u64) * 2 * TC_MAX_WORLD * TC_MB_SLOT, 256); }
+static size_t off_mb2(long long n_ghost) { return off_mb(n_ghost) + mb_bytes(); }
+static size_t mb2_bytes() { return align_up(sizeof(u64) * 2 * TC_MAX_WORLD * TC_MB2_SLOT, 256); }
 
 extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t world, int64_t n_loc,
                               int64_t n_ghost) {
@@ -435,7 +441,7 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     memset(&d->K, 0, sizeof d->K);
     d->stream = (cudaStream_t)stream; d->rank = rank; d->world = world;
     d->n = n_loc; d->n_ghost = n_ghost;
-    d->comm_bytes = off_mb(n_ghost) + mb_bytes();
+    d->comm_bytes = off_mb2(n_ghost) + mb2_bytes();
     TC_CUDA(cudaMalloc(&d->comm, d->comm_bytes));
     TC_CUDA(cudaMemset(d->comm, 0, d->comm_bytes));          // tag 0 everywhere: sequence numbers start at 1
     const size_t nb = sizeof(double) * (size_t)n_loc;
@@ -529,8 +535,10 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     K.y_gl = (u64*)(d->comm + off_gl(d->n_ghost, 0));
     K.p_gl[0] = (u64*)(d->comm + off_gl(d->n_ghost, 1)); K.p_gl[1] = (u64*)(d->comm + off_gl(d->n_ghost, 2));
     K.my_mb = (u64*)(d->comm + off_mb(d->n_ghost));
+    K.my_mb2 = (u64*)(d->comm + off_mb2(d->n_ghost));
     for (int w = 0; w < TC_MAX_WORLD; ++w) {
         K.peer_y_gl[w] = nullptr; K.peer_p_gl[0][w] = nullptr; K.peer_p_gl[1][w] = nullptr; K.peer_mb[w] = nullptr;
+        K.peer_mb2[w] = nullptr;
     }
     for (int w = 0; w < d->world; ++w) {
         if (!d->peer[w]) continue;
@@ -538,6 +546,7 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
         K.peer_y_gl[w] = (u64*)(d->peer[w] + off_gl(g, 0));
         K.peer_p_gl[0][w] = (u64*)(d->peer[w] + off_gl(g, 1)); K.peer_p_gl[1][w] = (u64*)(d->peer[w] + off_gl(g, 2));
         K.peer_mb[w] = (u64*)(d->peer[w] + off_mb(g));
+        K.peer_mb2[w] = (u64*)(d->peer[w] + off_mb2(g));
     }
     K.state = d->state;
     K.prof = d->prof;
@@ -604,23 +613,75 @@ extern "C" int tc_dist_reset_error(tc_dist* d) {
     return 0;
 }
 
+// Let the kernel work on a caller-owned state block (the FE block of a tc_solver state vector: tc_attach_dist)
+extern "C" int tc_dist_set_state_ptr(tc_dist* d, double* y_local_dev) {
+    d->K.y = y_local_dev ? y_local_dev : d->y;
+    return 0;
+}
 extern "C" int tc_dist_set_state(tc_dist* d, const double* y_local_dev) {
-    TC_CUDA(cudaMemcpyAsync(d->y, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+    TC_CUDA(cudaMemcpyAsync(d->K.y, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     TC_CUDA(cudaStreamSynchronize(d->stream));
     return 0;
 }
 extern "C" int tc_dist_get_state(tc_dist* d, double* y_local_dev) {
-    TC_CUDA(cudaMemcpyAsync(y_local_dev, d->y, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+    TC_CUDA(cudaMemcpyAsync(y_local_dev, d->K.y, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     return tc_dist_check(d);
 }
 // enqueue-only copies for pipelined host<->device streaming: dir 0 = set (caller -> state), 1 = get
 extern "C" int tc_dist_copy_state_async(tc_dist* d, double* y_local_dev, int32_t dir) {
     if (dir == 0)
-        TC_CUDA(cudaMemcpyAsync(d->y, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+        TC_CUDA(cudaMemcpyAsync(d->K.y, y_local_dev, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     else
-        TC_CUDA(cudaMemcpyAsync(y_local_dev, d->y, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
+        TC_CUDA(cudaMemcpyAsync(y_local_dev, d->K.y, sizeof(double) * d->n, cudaMemcpyDeviceToDevice, d->stream));
     return 0;
 }
+// Surface means of a partitioned body (thermca/solver.py:211-220: mean = C_surf^T x is a sum over ALL rows of the
+// body): every rank has the partial sums of its local rows (tc_surf_mean_kernel, one partial per block of a job);
+// this one-CTA kernel adds them up per job in block order, trades the per-rank sums through the LL mailboxes and
+// leaves the rank-ordered total in the job's first partial (the others zeroed), so the network kernel's C_SURF_MEAN
+// command reads the global mean — bit-identical on every rank, which keeps the replicated network kernels in lockstep.
+__global__ void tc_dist_mean_exchange_kernel(TcDistK S, double* __restrict__ partials, const int* __restrict__ first_block,
+                                             const int* __restrict__ nblk, int job0, int njobs) {
+    __shared__ double s_loc[TC_MB2_VALUES];
+    int* err = S.state + 4;
+    const int seq = S.state[12] + 1;
+    const int par = seq & 1;
+    for (int j = threadIdx.x; j < njobs; j += blockDim.x) {
+        double loc = 0.0;
+        const int fb = first_block[job0 + j];
+        for (int b = 0; b < nblk[job0 + j]; ++b) loc += partials[fb + b];
+        s_loc[j] = loc;
+    }
+    __syncthreads();
+    const bool bad = *((volatile int*)err) != 0;
+    for (int it = threadIdx.x; it < S.world * njobs; it += blockDim.x) {
+        const int w = it / njobs, j = it - w * njobs;
+        ll_store(S.peer_mb2[w] + ((size_t)par * TC_MAX_WORLD + S.rank) * TC_MB2_SLOT + 2 * j, bad ? nan("") : s_loc[j],
+                 (unsigned int)seq);
+    }
+    for (int j = threadIdx.x; j < njobs; j += blockDim.x) {
+        double tot = 0.0;
+        for (int w = 0; w < S.world; ++w)
+            tot += ll_load(S.my_mb2 + ((size_t)par * TC_MAX_WORLD + w) * TC_MB2_SLOT + 2 * j, (unsigned int)seq, err,
+                           S.spin_limit);
+        const int fb = first_block[job0 + j];
+        partials[fb] = tot;
+        for (int b = 1; b < nblk[job0 + j]; ++b) partials[fb + b] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) S.state[12] = seq;
+}
+extern "C" int tc_dist_mean_exchange(tc_dist* d, double* partials_dev, const int32_t* first_block_dev,
+                                     const int32_t* nblk_dev, int32_t job0, int32_t njobs) {
+    TC_CHECK(njobs >= 0 && njobs <= TC_MB2_VALUES, "too many surface means in one exchange");
+    if (njobs == 0 || d->world == 1) return 0;
+    TC_CHECK(d->peers_open, "peers not open");
+    tc_dist_mean_exchange_kernel<<<1, 256, 0, d->stream>>>(d->K, partials_dev, first_block_dev, nblk_dev, job0, njobs);
+    return 0;
+}
+extern "C" int64_t tc_dist_local_rows(tc_dist* d) { return d->n; }
+extern "C" void* tc_dist_stream(tc_dist* d) { return (void*)d->stream; }
+
 // load vector of the local rows (device pointer, kept by reference): time-varying boundary data
 extern "C" int tc_dist_set_load(tc_dist* d, const double* b_local_dev) {
     d->K.b = b_local_dev;

@@ -273,6 +273,8 @@ struct FfePart {
     TcPcg pcg;
     const float* binv = nullptr;       // block-Jacobi: inverted 32x32 slice blocks of M + shift K (tc_set_block_precond)
     double bj_shift = 0.0;             // the shift they were built for
+    tc_dist* dist = nullptr;           // row-partitioned body (tc_attach_dist): this part holds the LOCAL rows only
+    int job0 = 0, njobs = 0;           // its surface-mean jobs
 };
 struct LpPart { tc_lp_desc d; TcSell A; const double* b; double *r, *p, *q, *dinv; TcPcg pcg; };
 struct MorPart { tc_mor_desc d; TcMor M; };
@@ -318,6 +320,7 @@ struct tc_solver {
     // implicit
     double pcg_rtol = 1e-10; int pcg_maxit = 1000; int pcg_mode = TC_PCG_COOP; int coop_grid = 0;
     double ros_gamma = 1.0 + 0.70710678118654752440;
+    bool has_dist = false;             // a part is row-partitioned (tc_attach_dist)
 };
 
 static int grid_for(long long n, int threads, int cap) {
@@ -463,6 +466,9 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
     const int* done = s->flags + FL_DONE;
     if (s->mean_grid > 0)
         tc_surf_mean_kernel<<<s->mean_grid, TC_MEAN_THREADS, 0, st>>>(s->jobs, yin, s->mean_partials, done);
+    for (auto& p : s->ffe)               // row-partitioned bodies: add the other ranks' rows to the surface means
+        if (p.dist && tc_dist_mean_exchange(p.dist, s->mean_partials, s->jobs.first_block, s->jobs.nblk, p.job0, p.njobs))
+            return -1;
     tc_network_kernel<<<1, TC_NET_THREADS, 0, st>>>(s->net, s->ctrl, c_stage, yin, out, s->mean_partials, done);
     for (auto& p : s->lp) {
         const int g = grid_for(p.A.nslices, TC_SPMV_THREADS / 32, s->sm_count * 8);
@@ -486,6 +492,15 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
         if (p.fdiag.nrows > 0)
             tc_ffe_film_diag_kernel<<<grid_for(p.fdiag.nrows, 256, s->sm_count * 4), 256, 0, st>>>(
                 p.fdiag, s->net.darena + p.d.films_doff, p.d.val, p.d.adiag, done);
+        if (p.dist) {
+            // row-partitioned body: the product needs the peers' ghost rows and happens inside the fused kernel of
+            // dist.cu (tc_theta_steps); here only the load vector b = B flux of the local rows is formed
+            TC_CUDA(cudaMemsetAsync(out + p.d.y_off, 0, sizeof(double) * p.d.n, st));
+            if (p.load.nrows > 0)
+                tc_ffe_surf_load_kernel<<<grid_for(p.load.nrows, 256, s->sm_count * 4), 256, 0, st>>>(
+                    p.load, s->net.darena + p.d.flux_doff, out + p.d.y_off, done);
+            continue;
+        }
         const int g = grid_for(p.A.nslices, TC_SPMV_THREADS / 32, s->sm_count * 8);
         TcSell Ar = p.A;
         Ar.col16 = nullptr;      // measured: 16-bit columns pay off in the PCG kernel (+2.7 %) but not here (-3.6 %)
@@ -674,9 +689,11 @@ static int store_initial(tc_solver* s) {
     return 0;
 }
 
+#define TC_NO_DIST(s) TC_CHECK(!(s)->has_dist, "this scheme is not available for a row-partitioned body (use tc_theta_steps)")
 extern "C" int tc_rk_begin(tc_handle s, int32_t method, double t0, double t_end, double rtol, double atol,
                            double max_step, double first_step) {
     TC_CHECK(s && s->finalized, "solver not finalized");
+    TC_NO_DIST(s);
     TC_CHECK(method == TC_RK45 || method == TC_RK23, "unknown method");
     if (s->rk_graph && s->method != method) { cudaGraphExecDestroy(s->rk_graph); s->rk_graph = nullptr; }
     s->method = method;
@@ -1098,6 +1115,7 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         if (launch_pcg(s, P, s->pcg_mode == TC_PCG_COOP_BJ ? TC_PCG_COOP : s->pcg_mode, s->coop_grid, done)) return -1;
     }
     for (auto& p : s->ffe) {
+        if (p.dist) continue;                                  // row-partitioned: solved by the fused kernel of dist.cu
         const bool frozen = p.d.tdep != 0;
         if (frozen && !(w_method && p.J.n > 0)) continue;      // operator depends on T: explicit (copy above)
         TcPcg& P = p.pcg;
@@ -1134,6 +1152,21 @@ extern "C" int tc_set_block_precond(tc_handle s, int32_t part, const float* binv
     return 0;
 }
 
+// Mark full-order FE part `part` as row-partitioned: the part of this solver holds the LOCAL rows of the body (local
+// surface lists, local film-diagonal lists; its SELL arrays are the ones given to tc_dist_set_operator), `d` owns the
+// halo plan.  first_job / n_jobs: the part's surface-mean jobs.  Supported by tc_rhs (network rows and load vector),
+// tc_theta_steps; the explicit and W-method paths refuse such a solver.
+extern "C" int tc_attach_dist(tc_handle s, int32_t part, tc_dist* d, int32_t first_job, int32_t n_jobs) {
+    TC_CHECK(s && part >= 0 && part < (int)s->ffe.size() && d, "part index");
+    TC_CHECK(!s->ffe[part].d.tdep, "temperature dependent bodies cannot be row-partitioned");
+    TC_CHECK(tc_dist_local_rows(d) == s->ffe[part].d.n, "local row count of the part and of the partition differ");
+    TC_CHECK(tc_dist_stream(d) == (void*)s->stream, "the partition must use the solver's stream");
+    s->ffe[part].dist = d;
+    s->ffe[part].job0 = first_job; s->ffe[part].njobs = n_jobs;
+    s->has_dist = true;
+    return 0;
+}
+
 extern "C" int tc_theta_steps(tc_handle s, int32_t nsteps, double theta, double h_step, double pcg_rtol,
                               int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
@@ -1144,9 +1177,20 @@ extern "C" int tc_theta_steps(tc_handle s, int32_t nsteps, double theta, double 
     for (int k = 0; k < nsteps; ++k) {
         if (enqueue_rhs(s, theta, s->y, s->K[0])) return -1;                 // f(t + theta h, y)
         if (enqueue_block_solve(s, theta, s->K[0], s->K[1])) return -1;      // (I + theta h A) z = f
+        for (auto& p : s->ffe)           // row-partitioned bodies are advanced by their own kernel below
+            if (p.dist) TC_CUDA(cudaMemsetAsync(s->K[1] + p.d.y_off, 0, sizeof(double) * p.d.n, st));
         TcLin L{};
         L.nk = 1; L.k[0] = s->K[1]; L.c[0] = 1.0;
         tc_lin_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, s->y, L, s->ctrl, s->y, done);  // y += h z
+        for (auto& p : s->ffe)
+            if (p.dist) {
+                // K[0] holds the load vector b(t + theta h) of the local rows; the fused kernel forms f = b - A y with the
+                // peers' ghost rows, solves (I + theta h A) z = f across the GPUs and commits y += h z in place
+                if (tc_dist_set_load(p.dist, s->K[0] + p.d.y_off)) return -1;
+                if (tc_dist_set_state_ptr(p.dist, s->y + p.d.y_off)) return -1;
+                if (tc_dist_theta_steps(p.dist, 1, theta, h_step, pcg_rtol, pcg_maxit)) return -1;
+                s->launches += 1;
+            }
         tc_advance_time_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
         s->launches += 3;   // block-solve copy, y update, time advance (+ rhs and pcg counted inside)
     }
@@ -1157,6 +1201,7 @@ extern "C" int tc_theta_steps(tc_handle s, int32_t nsteps, double theta, double 
 extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, double atol, double max_step,
                              double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
+    TC_NO_DIST(s);
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
     s->w_bound = TC_W_EXPLICIT_BOUND;
     if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);
@@ -1256,6 +1301,7 @@ __global__ void tc_stage_rhs_kernel(long long n, const double* __restrict__ F, T
 extern "C" int tc_row3_begin(tc_handle s, double t0, double t_end, double rtol, double atol, double max_step,
                              double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
+    TC_NO_DIST(s);
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
     s->w_bound = TC_ROW3_BOUND;
     if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);

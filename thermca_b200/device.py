@@ -218,7 +218,9 @@ class DeviceSolver:
             for sidx, tgt in enumerate(p["surf_net_idxs"]):
                 nz = np.nonzero(Cm[:, sidx])[0]
                 jobs.append((nz + self.lp_off[k], Cm[nz, sidx], int(tgt), -1))
+        self._ffe_job_range = []           # (first job, number of jobs) of every FE part: tc_attach_dist
         for k, p in enumerate(s["ffe"]):
+            self._ffe_job_range.append((len(jobs), len(p["surf_net_idxs"])))
             for sidx, tgt in enumerate(p["surf_net_idxs"]):
                 jobs.append((np.asarray(p["C_idx"][sidx]) + self.ffe_off[k], p["C_val"][sidx], int(tgt), -1))
         self._mor_dev = []
@@ -505,7 +507,7 @@ class DeviceSolver:
             nslices = sell["nslices"]
             pos = sell["pos"]
         self.ffe_sell.append({"slice_ptr": t_sp, "col": t_col, "val": t_val, "mass": t_mass, "adiag": t_adiag,
-                              "n": n, "nslices": nslices})
+                              "n": n, "nslices": nslices, "col16": t_col16 if self.use_col16 else None})
         # surface loads grouped by row
         rows = np.concatenate([np.asarray(ix, dtype=np.int64) for ix in p["B_idx"]]) if p["B_idx"] else np.zeros(0, np.int64)
         surf = np.concatenate([np.full(len(ix), sidx, dtype=np.int32) for sidx, ix in enumerate(p["B_idx"])]) \
@@ -726,6 +728,13 @@ class DeviceSolver:
             if bad["failed_solves"]:       # fixed steps have no error estimator behind them: a bad solve is an error
                 raise RuntimeError(f"PCG did not converge in {bad['failed_solves']} of {nsteps} theta steps "
                                    f"({bad['reason']}, pcg_maxit={pcg_maxit}, pcg_rtol={pcg_rtol})")
+
+    def attach_partition(self, k, body):
+        """FE part ``k`` of this (localised) network holds the local rows of a row-partitioned body: ``body`` is the
+        ``thermca_b200.dist.DistBody`` built on this solver's SELL tensors and stream (thermca_b200/partition.py)."""
+        j0, nj = self._ffe_job_range[k]
+        _cabi.check(self.lib.tc_attach_dist(self._handle, int(k), body._h, int(j0), int(nj)))
+        self._bodies = getattr(self, "_bodies", []) + [body]
 
     def set_block_jacobi(self, h, theta=0.5):
         """Build the block-Jacobi preconditioner (32 x 32 slice blocks of M + theta*h*K, csrc/pcg.cuh) of every

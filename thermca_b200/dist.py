@@ -145,7 +145,10 @@ class DistBody:
     (int32, GLOBAL columns), ``val``, optional ``col16`` (column - row), ``mass``, ``adiag`` (diagonal of
     A = M^-1 K incl. films), ``nslices``.  ``b``: load vector of the local rows (device)."""
 
-    def __init__(self, op, b, bounds, init_temp=20.0):
+    def __init__(self, op, b, bounds, init_temp=20.0, stream=None, presplit=None):
+        """``presplit`` (host-side split done by ``split_local_rows``): dict with ``ghosts`` (sorted global columns),
+        ``bidx`` / ``gptr`` / ``gslot`` / ``gval`` (numpy); then ``op`` already holds LOCAL columns only.
+        ``stream``: run on this torch stream (a solver's) instead of an own one."""
         import torch
         import torch.distributed as dist
         from . import _cabi
@@ -159,7 +162,25 @@ class DistBody:
         self.op, self.b = op, b
         nsl = int(op["nslices"])
         col = op["col"]
-        # ---- ghosts, boundary slices, ghost side lists (on the device: 10^8 entries at 10 M rows) -------------
+        if presplit is not None:
+            up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev).to(dt)
+            ghosts = up(presplit["ghosts"], torch.int64)
+            self.n_ghost = int(ghosts.numel())
+            self.bidx = up(presplit["bidx"], torch.int32)
+            self.n_bnd = int((presplit["bidx"] >= 0).sum())
+            self.gptr = up(presplit["gptr"], torch.int64)
+            self.gslot = up(presplit["gslot"] if len(presplit["gslot"]) else np.zeros(1), torch.int32)
+            self.gval = up(presplit["gval"] if len(presplit["gval"]) else np.zeros(1), torch.float64)
+            self.col_loc = op["col"]
+        else:
+            ghosts = self._split_on_device(op, col, r0, r1, nsl)
+        self.stream = torch.cuda.Stream(self.dev) if stream is None else stream
+        self._finish_setup(op, ghosts, nsl, init_temp)
+
+    def _split_on_device(self, op, col, r0, r1, nsl):
+        """Ghosts, boundary slices and ghost side lists of an operator with GLOBAL columns (on the device: 10^8
+        entries at 10 M rows); leaves LOCAL columns in ``op``."""
+        torch = self.torch
         outside = (col < r0) | (col >= r1)
         gpos = torch.nonzero(outside).ravel()                                # entry positions of ghost couplings
         gcol = col[gpos].to(torch.int64)
@@ -205,7 +226,12 @@ class DistBody:
         self.col_loc = col_loc.to(torch.int32)
         op["col"] = self.col_loc                 # the global columns are not needed any more (0.6 GB at 10 M rows)
         del col_loc, outside, col, gpos, gcol, sl_of, lane_of, key, skey, perm
-        self.stream = torch.cuda.Stream(self.dev)
+        return ghosts
+
+    def _finish_setup(self, op, ghosts, nsl, init_temp):
+        import ctypes as C
+        from . import _cabi
+        torch, dist = self.torch, self.dist
         self.nnz = int(torch.count_nonzero(op["val"]).item())
         # ---- halo plan (setup-time collectives) --------------------------------------------------------
         all_ghosts = [None] * self.world
@@ -232,9 +258,11 @@ class DistBody:
         c16 = op.get("col16") if os.environ.get("TC_COL16", "1") != "0" else None
         _cabi.check(self.lib.tc_dist_set_operator(self._h, nsl, p(op["slice_ptr"]), p(self.col_loc),
                                                   p(c16) if c16 is not None else C.c_void_p(0),
-                                                  p(op["val"]), p(op["mass"]), p(op["adiag"]), p(self.b),
+                                                  p(op["val"]), p(op["mass"]), p(op["adiag"]),
+                                                  p(self.b) if self.b is not None else C.c_void_p(0),
                                                   self.n_bnd, p(self.bidx), p(self.gptr), p(self.gslot), p(self.gval)))
-        self.set_state(torch.full((self.n,), float(init_temp), dtype=torch.float64, device=self.dev))
+        if init_temp is not None:
+            self.set_state(torch.full((self.n,), float(init_temp), dtype=torch.float64, device=self.dev))
         dist.barrier()
 
     # ---- construction from a replicated host operator (a real, lowered FE body) -------------------------

@@ -10,9 +10,9 @@ Methods
   device (step controller included); these are what the reference runs by default.
 * ``'THETA_PCG'`` — fixed-step theta scheme (``step=`` seconds, ``theta=0.5``, ``pcg_rtol=1e-8``): FE / LP parts
   implicit by Jacobi-PCG (new method; new method names pass through ``Network.sim`` untouched, thermca/solver.py:359-362).
-  Under ``torchrun`` (world size > 1) a network that consists of one full-order FE body with constant boundary data
-  (BASELINE configs #2 / #5: heat sources, films to bound nodes) is row-partitioned over the GPUs
-  (``thermca_b200.dist.DistBody``); every rank returns the full result.
+  Under ``torchrun`` (world size > 1) the largest full-order FE body of the network is row-partitioned over the GPUs
+  (``thermca_b200.partition`` / ``thermca_b200.dist.DistBody``), the rest of the network is replicated; every rank
+  returns the full result.
 * ``'ROS2_PCG'`` / ``'ROW3_PCG'`` — adaptive linearly implicit Rosenbrock-W methods of order 2 (2 stages) and order 3
   (4 stages, 3 right-hand sides; order 3 for any Jacobian approximation); FE and LP parts solved by Jacobi-PCG, unknown
   network nodes and stiff MOR blocks by small CG kernels (new methods; the reference has no implicit scheme).
@@ -84,75 +84,80 @@ def _world_size():
 
 
 def _theta_partitioned(spec, t0, t1, num_skip, options):
-    """``THETA_PCG`` under torchrun: ONE full-order FE body with constant boundary data, row-partitioned over the
-    ranks (csrc/dist.cu).  The operator is the lowered part's own ``FFEIO.A`` (films folded into the diagonal,
-    thermca/fem/ffe_io.py:57-60) in a reverse Cuthill-McKee order; the load vector is the device right-hand side at
-    y = 0 (thermca/solver.py:265-281).  Constancy is CHECKED, not assumed: the right-hand side at y = 0 must not
-    depend on time and the conductances must not depend on the temperatures."""
-    import scipy.sparse as sp
+    """``THETA_PCG`` under torchrun for a general network: the largest full-order FE body is row-partitioned over the
+    ranks (thermca_b200/partition.py: reverse Cuthill-McKee order, even row blocks, caller's DOF order kept), the
+    network itself — nodes, link programs, inputs, LP / MOR parts, other FE bodies — is replicated on every rank.
+    Per step every rank evaluates the surface means of its rows, the means are completed across the ranks inside the
+    right-hand side pipeline (csrc/dist.cu:tc_dist_mean_exchange_kernel) so that the replicated network kernels see
+    identical inputs, and the body's product / implicit solve runs in the fused peer-memory kernel.  Every rank returns
+    the full result."""
     import torch
+    import torch.distributed as dist
     from .dist import DistBody
+    from .partition import choose_partitioned_part, localize_ffe_part
     if "step" not in options:
         raise ValueError("method 'THETA_PCG' needs the step size: sim(..., method='THETA_PCG', step=seconds)")
     h, theta = float(options["step"]), float(options.get("theta", 0.5))
     pcg_rtol = float(options.get("pcg_rtol", 1e-8))
-    u = int(spec["u"])
-    if u != 0 or len(spec["ffe"]) != 1 or spec["lp"] or spec["mor"] or spec["ffe"][0].get("tdep") is not None:
-        raise NotImplementedError("the row-partitioned THETA_PCG path handles one full-order FE body with constant "
-                                  "boundary data (no unknown network nodes, LP / MOR parts or temperature dependent "
-                                  "materials); run this model on one GPU or pass partition=False")
-    part = spec["ffe"][0]
-    n = int(part["dof"])
     nsteps = int(round((t1 - t0) / h))
-    if abs(t0 + nsteps * h - t1) > 1e-9 * max(abs(t1), abs(h)):
+    if nsteps < 0 or abs(t0 + nsteps * h - t1) > 1e-9 * max(abs(t1), abs(h)):
         raise ValueError("THETA_PCG needs time_span[1] - time_span[0] to be a whole number of steps")
-    # ---- boundary data from the single-GPU pipeline (every rank: the body fits one GPU, the partition is for speed) ----
-    dev = DeviceSolver(spec)
+    k = choose_partitioned_part(spec)
+    if k < 0:
+        raise NotImplementedError("the row-partitioned THETA_PCG path needs a full-order FE body without temperature "
+                                  "dependent material; run this model on one GPU or pass partition=False")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    part = spec["ffe"][k]
+    n_glob = int(part["dof"])
+    local, presplit, info = localize_ffe_part(part, rank, world)
+    spec_loc = dict(spec)
+    spec_loc["ffe"] = list(spec["ffe"])
+    spec_loc["ffe"][k] = local
+    dev = DeviceSolver(spec_loc)
+    body = None
+    u = int(spec["u"])
     try:
-        y0 = dev.initial_state()
-        zero = np.zeros_like(y0)
-        b0 = dev.rhs(t0, zero)
-        net0 = dev.network_state()
-        b1 = dev.rhs(t1, zero)
-        dev.rhs(t0, y0 + 7.0)
-        net1 = dev.network_state()
-        dev.rhs(t0, y0)
-        net_at_y0 = dev.network_state()
-    finally:
-        dev.close()
-    if not (np.array_equal(b0, b1) and np.array_equal(net0["cond"], net1["cond"])
-            and np.array_equal(net0["heat_src"], net1["heat_src"])):
-        raise NotImplementedError("the row-partitioned THETA_PCG path needs constant boundary data (loads or films of "
-                                  "this model depend on time or temperature); run it on one GPU or pass partition=False")
-    A = sp.csr_matrix((part["A_data"], part["A_body"]["indices"], part["A_body"]["indptr"]), shape=(n, n))
-    body = DistBody.from_csr(A, 1.0 / np.asarray(part["M_inv"]), b0, init_temp=0.0)
-    try:
-        body.set_global_state(y0)
-        rows = {k: [] for k in ("times", "net_temps", "net_capys", "net_heat_srcs", "cond_data", "clean_data", "io_temps")}
-        surf_nodes = np.asarray(part["surf_net_idxs"], dtype=np.int64)
+        body = DistBody(dev.ffe_sell[k], None, info["bounds"], init_temp=None, stream=dev.stream, presplit=presplit)
+        dev.attach_partition(k, body)
+        off_loc, n_loc = dev.ffe_off[k], int(local["dof"])
+        sizes = [int(info["bounds"][w + 1] - info["bounds"][w]) for w in range(world)]
+        inv = torch.from_numpy(info["inv"]).to(dev.dev)
+        rows = {kk: [] for kk in ("times", "net_temps", "net_capys", "net_heat_srcs", "cond_data", "clean_data", "io_temps")}
 
         def store(t):
-            y = body.gather_state().cpu().numpy()
-            T = net_at_y0["T"].copy()
-            for s_, node in enumerate(surf_nodes):               # surface mean temperatures, thermca/solver.py:211-220
-                T[node] = float(np.dot(part["C_val"][s_], y[part["C_idx"][s_]]))
-            rows["times"].append(t); rows["net_temps"].append(T); rows["net_capys"].append(net_at_y0["capy"])
-            rows["net_heat_srcs"].append(net_at_y0["heat_src"]); rows["cond_data"].append(net_at_y0["cond"])
-            rows["clean_data"].append(net_at_y0["clean"]); rows["io_temps"].append(y)
+            y_loc = dev.get_state()                                   # [T_u | lp | ffe (local rows of part k) | mor]
+            dev.rhs(t, y_loc)                                         # network arrays at (t, y); collective
+            ns = dev.network_state()
+            T = ns["T"].copy()
+            T[:u] = y_loc[:u]
+            mine = torch.from_numpy(np.ascontiguousarray(y_loc[off_loc: off_loc + n_loc])).to(dev.dev)
+            parts = [torch.empty(sz, dtype=torch.float64, device=dev.dev) for sz in sizes]
+            dist.all_gather(parts, mine)
+            y_part = torch.cat(parts)[inv].cpu().numpy()              # caller's DOF order
+            io = np.concatenate([y_loc[u: off_loc], y_part, y_loc[off_loc + n_loc:]])
+            rows["times"].append(t); rows["net_temps"].append(T); rows["net_capys"].append(ns["capy"])
+            rows["net_heat_srcs"].append(ns["heat_src"]); rows["cond_data"].append(ns["cond"])
+            rows["clean_data"].append(ns["clean"]); rows["io_temps"].append(io)
+        from . import _cabi
+        _cabi.check(dev.lib.tc_set_time(dev._handle, float(t0)))
         store(t0)
-        for k in range(nsteps):
-            body.theta_steps(1, h, theta, rtol=pcg_rtol, sync=((k + 1) % 16 == 0))
-            if (k + 1) % (num_skip + 1) == 0 or k + 1 == nsteps:
+        for i in range(nsteps):
+            dev.theta_steps(1, h, theta, t0=t0 + i * h, pcg_rtol=pcg_rtol)
+            if (i + 1) % 8 == 0 or i + 1 == nsteps:
                 body.check()
-                store(t0 + (k + 1) * h if k + 1 < nsteps else t1)
+            if (i + 1) % (num_skip + 1) == 0 or i + 1 == nsteps:
+                store(t0 + (i + 1) * h if i + 1 < nsteps else t1)
         st = body.stats()
+        final_net = dev.network_state()
+        final_net["T"] = rows["net_temps"][-1]
     finally:
-        body.close()
-    torch.cuda.synchronize()
-    res = {k: np.asarray(v) for k, v in rows.items()}
-    res.update({"status": 0, "accepted": nsteps, "rejected": 0, "pcg": st,
-                "final_net": {"T": res["net_temps"][-1], "heat_src": net_at_y0["heat_src"], "capy": net_at_y0["capy"],
-                              "cond": net_at_y0["cond"], "clean": net_at_y0["clean"]}})
+        torch.cuda.synchronize()
+        if body is not None:
+            body.close()
+        dev.close()
+    res = {kk: np.asarray(v) for kk, v in rows.items()}
+    res.update({"status": 0, "accepted": nsteps, "rejected": 0, "pcg": st, "final_net": final_net,
+                "partition": {"part": k, "dof": n_glob, "rows_per_rank": sizes}})
     return res
 
 
