@@ -260,3 +260,52 @@ def test_row3w_coefficients_satisfy_the_w_order_conditions():
     assert np.max(np.abs([bh.sum() - 1, bh @ al - 0.5, bh @ gp])) < 1e-13      # embedded: order 2
     for z in list(1j * np.logspace(-2, 4, 60)) + list(-np.logspace(-2, 6, 60)):
         assert abs(1 + z * b @ np.linalg.solve(np.eye(4) - z * (A + Gam), np.ones(4))) <= 1 + 1e-9
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_localised_part_reassembles_the_global_operator(golden, world):
+    """thermca_b200/partition.py: the rows every rank owns of a lowered FE body (RCM order, even blocks) — local CSR +
+    ghost side lists — give back the global product; film-diagonal lists point at diagonal entries of the local CSR;
+    surface load / mean lists are the global ones restricted to the owned rows (golden with variable films)."""
+    import scipy.sparse as sp
+    from thermca_b200.partition import localize_ffe_part
+    spec, _ = golden("plate_ffe_var")
+    part = spec["ffe"][0]
+    n = int(part["dof"])
+    A = sp.csr_matrix((part["A_data"], part["A_body"]["indices"], part["A_body"]["indptr"]), shape=(n, n))
+    x = np.random.default_rng(0).standard_normal(n)
+    y = np.zeros(n)
+    seen_rows = 0
+    n_film_entries = 0
+    for rank in range(world):
+        loc, pre, info = localize_ffe_part(part, rank, world)
+        r0, r1, perm = info["r0"], info["r1"], info["perm"]
+        xp = x[perm]
+        Al = sp.csr_matrix((loc["A_data"], loc["A_body"]["indices"], loc["A_body"]["indptr"]), shape=(r1 - r0, r1 - r0))
+        yl = Al @ xp[r0:r1]
+        g = xp[pre["ghosts"]]
+        assert np.all((pre["ghosts"] < r0) | (pre["ghosts"] >= r1))
+        for sl in np.nonzero(pre["bidx"] >= 0)[0]:
+            b = pre["bidx"][sl]
+            w = (pre["gptr"][b + 1] - pre["gptr"][b]) // 32
+            for lane in range(32):
+                row = 32 * sl + lane
+                if row < r1 - r0:
+                    for k in range(w):
+                        q = pre["gptr"][b] + 32 * k + lane
+                        yl[row] += pre["gval"][q] * g[pre["gslot"][q]]
+        y[perm[r0:r1]] = yl
+        seen_rows += r1 - r0
+        for ix, a in zip(loc["film_didx"], loc["film_adata"]):
+            rows = np.searchsorted(loc["A_body"]["indptr"], ix, side="right") - 1
+            assert np.array_equal(loc["A_body"]["indices"][ix], rows) and len(ix) == len(a)
+            n_film_entries += len(ix)
+        for s_, (ix, v) in enumerate(zip(loc["B_idx"], loc["B_val"])):
+            full = dict(zip(np.asarray(part["B_idx"][s_]).tolist(), np.asarray(part["B_val"][s_]).tolist()))
+            assert all(full[int(gi)] == bv for gi, bv in zip(perm[r0:r1][ix], v))
+        for s_, (ix, v) in enumerate(zip(loc["C_idx"], loc["C_val"])):
+            full = dict(zip(np.asarray(part["C_idx"][s_]).tolist(), np.asarray(part["C_val"][s_]).tolist()))
+            assert all(full[int(gi)] == cv for gi, cv in zip(perm[r0:r1][ix], v))
+    assert seen_rows == n
+    assert n_film_entries == sum(len(ix) for ix in part["film_didx"])
+    assert np.max(np.abs(y - A @ x)) <= 1e-13 * np.max(np.abs(A @ x))
