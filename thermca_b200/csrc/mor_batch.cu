@@ -438,10 +438,13 @@ static int launch_stage_pipe(int S, int r, int B, cudaStream_t st, const MorBatc
                              const double* Xbase, double* Xout, double* Xacc, double t, double h, double c_out,
                              double c_acc, int first) {
     const size_t smem = sizeof(double) * mor_pipe_smem_total(NOPS);
-    static bool configured = false;
-    if (!configured) {
+    // per device (function attributes are per device; a process may drive several GPUs)
+    static unsigned long long configured = 0ULL;
+    int devid = 0;
+    TC_CUDA(cudaGetDevice(&devid));
+    if (devid >= 64 || !(configured >> devid & 1ULL)) {
         TC_CUDA(cudaFuncSetAttribute(tc_mor_stage_pipe_kernel<NOPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (devid < 64) configured |= 1ULL << devid;
     }
     dim3 grid((B + MP_TN - 1) / MP_TN, mor_fold_rows(r) ? r / MB_TM : (r + MB_TM - 1) / MB_TM, S);
     cudaLaunchConfig_t cfg{};

@@ -1455,10 +1455,12 @@ extern "C" int tc_vm_eval(void* cuda_stream, const int32_t* code, int32_t n_inst
     TC_CHECK(n_instr > 0 && n_instr <= TC_VM_MAX && result >= 0 && result < n_instr, "program length out of range");
     if (m <= 0) return 0;
     const size_t smem = sizeof(double) * 64 * (size_t)n_instr;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0ULL;        // per device (a process may drive several GPUs)
+    int devid = 0;
+    TC_CUDA(cudaGetDevice(&devid));
+    if (devid >= 64 || !(configured >> devid & 1ULL)) {
         TC_CUDA(cudaFuncSetAttribute(tc_vm_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 400));
-        configured = true;
+        if (devid < 64) configured |= 1ULL << devid;
     }
     TC_CHECK(n_instr <= 400, "program too long for the stand-alone evaluator");
     tc_vm_eval_kernel<<<(m + 63) / 64, 64, smem, (cudaStream_t)cuda_stream>>>(code, n_instr, result, consts, tab_dir, tab_arena,

@@ -576,11 +576,10 @@ class DeviceSolver:
     def network_state(self):
         """Host copies of the mutable network arrays (T, heat_src, capy, cond, clean_cond)."""
         self.stream.synchronize()
-        d = self.darena.cpu().numpy()
         o, N, nnz = self.off, self.N, self.nnz
-        return {"T": d[o["T"]: o["T"] + N].copy(), "heat_src": d[o["heat"]: o["heat"] + N].copy(),
-                "capy": d[o["capy"]: o["capy"] + N].copy(), "cond": d[o["cond"]: o["cond"] + nnz].copy(),
-                "clean": d[o["clean"]: o["clean"] + nnz].copy()}
+        get = lambda key, n: self.darena[o[key]: o[key] + n].cpu().numpy()       # only the five ranges, not the arena
+        return {"T": get("T", N), "heat_src": get("heat", N), "capy": get("capy", N), "cond": get("cond", nnz),
+                "clean": get("clean", nnz)}
 
     # -- right-hand side (parity hook) ------------------------------------------------------------------
     def rhs(self, t, y):
