@@ -1090,7 +1090,6 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         tc_net_block_solve_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, coef, rhs, z, s->net_vec, 1e-12, done);
     if (w_method)
         for (auto& p : s->mor) {
-            if (p.M.r > 1024) continue;                      // vectors would not fit the default shared memory: explicit
             tc_mor_block_solve_kernel<<<p.M.S, 256, sizeof(double) * 5 * p.M.r, st>>>(
                 p.M, s->net.darena + p.d.films_doff, s->ctrl, coef, s->w_bound, rhs + p.d.y_off, z + p.d.y_off, 1e-12,
                 done);
@@ -1202,6 +1201,9 @@ extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, 
                              double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
     TC_NO_DIST(s);
+    for (auto& p : s->mor)
+        TC_CHECK(p.M.r <= 1024, "a MOR block with r > 1024 cannot be solved implicitly (its CG vectors do not fit shared "
+                                "memory); use an explicit pair for this model");
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
     s->w_bound = TC_W_EXPLICIT_BOUND;
     if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);
@@ -1302,6 +1304,9 @@ extern "C" int tc_row3_begin(tc_handle s, double t0, double t_end, double rtol, 
                              double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
     TC_NO_DIST(s);
+    for (auto& p : s->mor)
+        TC_CHECK(p.M.r <= 1024, "a MOR block with r > 1024 cannot be solved implicitly (its CG vectors do not fit shared "
+                                "memory); use an explicit pair for this model");
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
     s->w_bound = TC_ROW3_BOUND;
     if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);

@@ -759,6 +759,11 @@ class DeviceSolver:
         nsteps = int(round((t1 - t0) / h))
         if nsteps < 0 or abs(t0 + nsteps * h - t1) > 1e-9 * max(abs(t1), abs(h)):
             raise ValueError("THETA_PCG needs time_span[1] - time_span[0] to be a whole number of steps")
+        if self.u > 0 or self.spec["mor"]:
+            import warnings
+            warnings.warn("THETA_PCG advances FE and LP parts implicitly; the unknown network nodes and MOR parts of this "
+                          "model take the explicit Euler update with the same step (stable only while step * their "
+                          "fastest rate < 2): prefer method='ROW3_PCG' for stiff lumped nodes", RuntimeWarning)
         u = self.u
         rows = {k: [] for k in ("times", "net_temps", "net_capys", "net_heat_srcs", "cond_data", "clean_data", "io_temps")}
 
