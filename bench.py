@@ -635,7 +635,7 @@ def mor_ensemble(args, world, rank, local_rank):
                                 f"({red['build']['pcg_solves']} PCG solves, {t_build:.1f} s)",
                    "l2": "operators (8.6 MB) are L2-resident by design; state 3x19.7 MB/GPU streams",
                    "state_finite": finite, "lambda_max_h": lam * h},
-        "clocks": clocks.summary(), "gpu_launches": nsteps * ens.launches_per_step(),
+        "clocks": clocks.summary(), "gpu_launches": ens.launches(nsteps),
         "roofline": {"bound": "tensor", "achieved": tflops, "peak": dgemm_tflops, "unit": "TFLOP/s",
                      "frac": tflops / dgemm_tflops, "traffic": None, "kernel": ens.kernel_name(),
                      "peak_kind": "torch.matmul fp64 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"},

@@ -257,6 +257,20 @@ int tc_mor_batch_steps(void* cuda_stream, int32_t S, int32_t r, int32_t F, int32
                        const double* t_link, const double* q_surf, double* X, double* work,
                        double t0, double h, int32_t nsteps, int32_t use_dmma);
 int64_t tc_mor_batch_work_doubles(int32_t S, int32_t r, int32_t F, int32_t B);
+/* Fused persistent form of the same step (csrc/mor_fused.cu): one launch integrates nsteps RK4 steps; a CTA keeps a
+ * (surface, 32 scenario columns) unit in shared memory over all stages and streams the operators, pre-packed once
+ * into DMMA fragment order by tc_mor_fused_pack, through a bulk-copy ring.  Same reference arithmetic
+ * (thermca/solver.py:282-299, thermca/fem/mor_io.py:90-92).  Supported: F <= 2, r <= 200 (tc_mor_fused_supported);
+ * work = tc_mor_fused_work_bytes bytes of device memory (hand-over flags). */
+int32_t tc_mor_fused_supported(int32_t S, int32_t r, int32_t F, int32_t B);
+int64_t tc_mor_fused_packed_doubles(int32_t S, int32_t r, int32_t F);
+int64_t tc_mor_fused_work_bytes(int32_t S, int32_t r, int32_t F, int32_t B);
+int tc_mor_fused_pack(void* cuda_stream, int32_t S, int32_t r, int32_t F, const double* A_body,
+                      const double* A_films, double* packed);
+int tc_mor_fused_steps(void* cuda_stream, int32_t S, int32_t r, int32_t F, int32_t B, const double* packed,
+                       const double* B_T, const int32_t* film_surf, const double* film_h0,
+                       const double* film_tau, const double* t_link, const double* q_surf, double* X,
+                       void* work, double t0, double h, int32_t nsteps);
 
 /* ---- device-side generator of the synthetic Kuhn cuboid operator (BASELINE configs #2/#5) */
 int tc_synth_cuboid_counts(int32_t nx, int32_t ny, int32_t nz, int64_t* n_rows, int64_t* n_slices,

@@ -46,7 +46,7 @@ def _random_case(S, r, F, B, seed):
 
 @pytest.mark.parametrize("S,r,F,B", [(3, 40, 2, 96), (2, 200, 1, 130), (1, 17, 0, 64), (2, 64, 3, 64), (2, 33, 5, 50),
                                      (3, 200, 2, 192), (2, 198, 2, 70), (1, 136, 0, 66), (2, 150, 3, 64), (1, 128, 2, 64)])
-@pytest.mark.parametrize("dmma", [2, 1, 0])
+@pytest.mark.parametrize("dmma", [3, 2, 1, 0])
 def test_mor_batch_matches_numpy(S, r, F, B, dmma):
     from thermca_b200.mor_batch import MorEnsemble
     A_body, A_films, B_T, film_surf, h0, tau, t_link, q_surf, X0 = _random_case(S, r, F, B, 7)
@@ -56,6 +56,31 @@ def test_mor_batch_matches_numpy(S, r, F, B, dmma):
     X = ens.state()
     Xref = _numpy_rk4(A_body, A_films, B_T, film_surf, h0, tau, t_link, q_surf, X0, 3.0, 0.7, 3)
     assert np.max(np.abs(X - Xref)) <= 1e-11 * np.max(np.abs(Xref))
+
+
+@pytest.mark.parametrize("S,r,F,B,nsteps", [(3, 200, 2, 2000, 5), (1, 200, 2, 64, 8), (2, 96, 1, 1000, 3),
+                                            (3, 200, 2, 4096, 2), (2, 200, 0, 70, 1), (1, 8, 2, 33, 4)])
+def test_fused_kernel_equals_per_stage_kernels(S, r, F, B, nsteps):
+    """The fused persistent kernel (mode 3) against the per-stage DMMA kernels (mode 2) at sizes a numpy loop does
+    not finish quickly.  The shapes make units straddle CTAs in every way the schedule allows: more units than SMs
+    (a unit starts on one CTA and ends on its neighbour), fewer units than SMs (one unit passes through up to 8
+    CTAs), ragged last column tile, a single step."""
+    from thermca_b200.mor_batch import MorEnsemble
+    case = _random_case(S, r, F, B, 11)
+    a = MorEnsemble(*case)
+    b = MorEnsemble(*case)
+    assert a.fused
+    a.time = b.time = 1.5
+    a.steps(nsteps, 0.3, use_dmma=3)
+    b.steps(nsteps, 0.3, use_dmma=2)
+    assert a.last_mode == 3 and b.last_mode == 2
+    Xa, Xb = a.state(), b.state()
+    assert np.isfinite(Xa).all()
+    assert np.max(np.abs(Xa - Xb)) <= 1e-13 * np.max(np.abs(Xb))
+    # a second call continues from the stored state and time
+    a.steps(2, 0.3, use_dmma=3)
+    b.steps(2, 0.3, use_dmma=2)
+    assert np.max(np.abs(a.state() - b.state())) <= 1e-13 * np.max(np.abs(Xb))
 
 
 def test_mor_batch_reproduces_reference_rhs_per_scenario(golden):

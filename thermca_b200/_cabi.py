@@ -106,6 +106,11 @@ EXPORTS = {
     "tc_mor_batch_steps": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  f64, f64, i32, i32]),
     "tc_mor_batch_work_doubles": (i64, [i32, i32, i32, i32]),
+    "tc_mor_fused_supported": (i32, [i32, i32, i32, i32]),
+    "tc_mor_fused_packed_doubles": (i64, [i32, i32, i32]),
+    "tc_mor_fused_work_bytes": (i64, [i32, i32, i32, i32]),
+    "tc_mor_fused_pack": (i32, [vp, i32, i32, i32, vp, vp, vp]),
+    "tc_mor_fused_steps": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, f64, i32]),
     "tc_synth_cuboid_counts": (i32, [i32, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "tc_synth_cuboid": (i32, [vp, i32, i32, i32, f64, f64, f64, f64, f64, f64, i64, i64, vp, vp, vp, vp, vp,
                               vp, vp, vp]),

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libthermca_b200.so")
-SOURCES = ["solver.cu", "mor_batch.cu", "synth.cu", "dist.cu", "assembly.cu", "krylov.cu", "pcg_multi.cu", "barbench.cu"]
+SOURCES = ["solver.cu", "mor_batch.cu", "mor_fused.cu", "synth.cu", "dist.cu", "assembly.cu", "krylov.cu", "pcg_multi.cu", "barbench.cu"]
 HEADERS = ["common.cuh", "vm.cuh", "network.cuh", "parts.cuh", "pcg.cuh", "gridbar.cuh",
            os.path.join("..", "..", "include", "thermca_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

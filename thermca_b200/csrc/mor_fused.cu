@@ -1,0 +1,448 @@
+// Batched MOR ensemble, fused persistent form (BASELINE config #3; round 2).
+//
+// Same arithmetic as tc_mor_stage_pipe_kernel (mor_batch.cu) — per scenario what the reference evaluates for one
+// MOR part and right-hand side (thermca/solver.py:282-299, thermca/fem/mor_io.py:90-92), advanced by classical RK4 —
+// but organised around one observation: the S per-surface subsystems of a MOR body and the B scenarios never couple
+// (films here are prescribed functions of time), so a (surface, 32 scenario columns) UNIT can be integrated over
+// every stage and every step without talking to anybody.  One persistent CTA per SM owns whole units:
+//   * the unit's state lives in shared memory for the whole run: U (the stage input, the B operand of the DMMAs,
+//     r x 32, XOR-swizzled), x_n and the RK4 accumulator in a thread-private "owner" layout (every thread updates
+//     the same 2 columns of the same rows in every stage) — no state round trip through L2 between stages, no
+//     per-stage launch, no prologue / epilogue latency, no wave tail;
+//   * the operators (3 x r x r per surface, L2 resident) stream through a TMA bulk-copy ring (cp.async.bulk +
+//     mbarrier full/empty pairs) fed by a dedicated producer warp from a PRE-PACKED copy that already has DMMA
+//     fragment order: one 128-bit shared load per lane yields the A fragments of two k4-steps, conflict free, no
+//     predicates, no address arithmetic in the loop.  The ring keeps running across stage and step boundaries
+//     (operators do not depend on the state), so the tensor pipe only idles during the short epilogue;
+//   * 20 consumer warps = 5 row groups x 4 column blocks: every SM sub-partition gets the same number of DMMAs
+//     (r = 200: 5 row blocks x 3 operators = 15 accumulator tiles per warp);
+//   * the producer warp also tabulates the per-scenario film values of the NEXT stage (one sin per lane and film);
+//   * load balance: units x steps is cut into equal contiguous ranges, one per CTA (McNaughton's wrap-around rule).
+//     A unit that straddles two ranges is integrated for its first steps by one CTA (at the START of its time line)
+//     and for the rest by its neighbour (at the END of its time line); the hand-over goes through X + a step flag.
+#include "common.cuh"
+#include "../../include/thermca_b200.h"
+
+#define MF_TN 32             // scenario columns per unit
+#define MF_GROUPS 5          // row groups
+#define MF_CWARPS 20         // consumer warps = MF_GROUPS x 4 column blocks
+#define MF_CTHREADS (MF_CWARPS * 32)
+#define MF_THREADS MF_CTHREADS
+#define MF_KC 8              // k per ring chunk (two k4-steps)
+#define MF_RBW 5             // max 8-row blocks per warp  -> r <= 200
+#define MF_SMEM_MAX 232448   // 227 KB
+
+struct MorFused {
+    int S, r, F, B;
+    int nrb, rbw, nchunks, ns, ups, L;
+    long long total, T;
+    const double* packed; const double* B_T; const int* film_surf; const double* film_h0; const double* film_tau;
+    const double* t_link; const double* q_surf;
+    double* X; int* flags;
+    double t0, h;
+    int stage_bytes, off_U, off_xb, off_xacc, off_film, off_bar;
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned mf_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mf_mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mf_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mf_mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mf_mbar_try(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mf_mbar_wait(unsigned bar, unsigned parity) {
+    while (!mf_mbar_try(bar, parity)) {}
+}
+__device__ __forceinline__ void mf_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mf_bar(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mf_dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 mf_lds128(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double mf_lds64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// Walks the (unit, step, stage) sequence of one CTA: units in DESCENDING order (the unit shared with the next CTA
+// first, the one shared with the previous CTA last), steps and stages ascending.
+struct MfIter {
+    long long lo, hi;
+    int L, c, step, step_end, stage;
+    bool valid;
+    __device__ void set_unit() {
+        const long long base = (long long)c * L;
+        step = (int)((lo > base ? lo : base) - base);
+        const long long e = base + L;
+        step_end = (int)((hi < e ? hi : e) - base);
+    }
+    __device__ void init(long long lo_, long long hi_, int L_) {
+        lo = lo_; hi = hi_; L = L_; stage = 0;
+        valid = hi > lo;
+        if (valid) { c = (int)((hi - 1) / L); set_unit(); }
+    }
+    __device__ bool unit_begins() const {
+        const long long base = (long long)c * L;
+        return stage == 0 && step == (int)((lo > base ? lo : base) - base);
+    }
+    __device__ bool unit_ends() const { return stage == 3 && step == step_end - 1; }
+    __device__ void next() {
+        if (++stage < 4) return;
+        stage = 0;
+        if (++step < step_end) return;
+        --c;
+        if (c < 0 || (long long)c * L + L <= lo) { valid = false; return; }
+        set_unit();
+    }
+};
+
+__device__ __forceinline__ double mf_film_at(const MorFused& P, int f, int b, double t) {
+    const double TWO_PI = 6.283185307179586476925;
+    return P.film_h0[(size_t)f * P.B + b] * (1.0 + 0.5 * sin(TWO_PI * t / P.film_tau[(size_t)f * P.B + b]));
+}
+
+// operators -> fragment order: packed[s][chunk][op][rb][lane][2] = W_op,s[rb*8 + lane/4][chunk*8 + 4*j + lane%4], zero padded
+__global__ void tc_mor_fused_pack_kernel(int S, int r, int nops, int nrb, int nchunks, const double* __restrict__ A_body,
+                                         const double* __restrict__ A_films, double* __restrict__ packed) {
+    const size_t n = (size_t)S * nchunks * nops * nrb * 64;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e & 1), lane = (int)((e >> 1) & 31);
+        size_t q = e >> 6;
+        const int rb = (int)(q % nrb); q /= nrb;
+        const int o = (int)(q % nops); q /= nops;
+        const int ch = (int)(q % nchunks);
+        const int s = (int)(q / nchunks);
+        const int row = rb * 8 + (lane >> 2), k = ch * MF_KC + 4 * j + (lane & 3);
+        double v = 0.0;
+        if (row < r && k < r) {
+            const double* W = o == 0 ? A_body + (size_t)s * r * r : A_films + ((size_t)(o - 1) * S + s) * r * r;
+            v = W[(size_t)row * r + k];
+        }
+        packed[e] = v;
+    }
+}
+
+template <int NOPS, bool FULL>
+__global__ void __launch_bounds__(MF_THREADS, 1)
+tc_mor_fused_kernel(const MorFused P) {
+    extern __shared__ __align__(128) unsigned char mf_smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned ring = mf_smem(mf_smem_raw);
+    double* U = reinterpret_cast<double*>(mf_smem_raw + P.off_U);
+    double2* xb = reinterpret_cast<double2*>(mf_smem_raw + P.off_xb);
+    double2* xacc = reinterpret_cast<double2*>(mf_smem_raw + P.off_xacc);
+    double* film = reinterpret_cast<double*>(mf_smem_raw + P.off_film);      // [max(F,1)][32]
+    const unsigned bars = mf_smem(mf_smem_raw + P.off_bar);                  // full[ns] mbarriers
+    unsigned* cnt = reinterpret_cast<unsigned*>(mf_smem_raw + P.off_bar + 64);   // released[ns] counters
+    const int ns = P.ns, nchunks = P.nchunks;
+    const long long lo = (long long)blockIdx.x * P.T;
+    const long long hi = lo + P.T < P.total ? lo + P.T : P.total;
+    if (hi <= lo) return;
+    const size_t stage_doubles = (size_t)P.stage_bytes / 8;
+    MfIter it;
+    it.init(lo, hi, P.L);
+    if (tid == 0) {
+        for (int s = 0; s < ns; ++s) { mf_mbar_init(bars + 8u * s, 1); cnt[s] = 0u; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // prime the ring: the first ns chunks (ns <= nchunks: all of the first stage)
+        const double* src = P.packed + (size_t)(it.c / P.ups) * nchunks * stage_doubles;
+        for (int s = 0; s < ns; ++s) {
+            mf_mbar_expect_tx(bars + 8u * s, (unsigned)P.stage_bytes);
+            mf_bulk_g2s(ring + (unsigned)s * P.stage_bytes, src + (size_t)s * stage_doubles, (unsigned)P.stage_bytes,
+                        bars + 8u * s);
+        }
+    }
+    __syncthreads();
+
+    const int g = warp >> 2, cb = warp & 3;
+    const int rb0 = g * P.rbw;
+    const int nj = FULL ? MF_RBW : max(0, min(P.rbw, P.nrb - rb0));      // row blocks of this warp (warp-uniform)
+    const int r = P.r, B = P.B;
+    // swizzle of U: column ^ sw(k), sw(k) = ((k&3)<<2) ^ ((k&1)<<3): B-fragment loads (4 k x 8 n per warp) and the
+    // epilogue's double2 stores (8 rows x 4 column pairs) are both conflict free
+    const int kq = lane & 3, nq = lane >> 2;
+    const int sw_b = (kq << 2) ^ ((kq & 1) << 3);
+    const unsigned u_b = mf_smem(U) + 8u * (unsigned)(kq * MF_TN + ((cb * 8 + nq) ^ sw_b));   // + k0*256 bytes
+    const int sw_e = ((nq & 3) << 2) ^ ((nq & 1) << 3);
+    const int col = cb * 8 + 2 * kq;                     // local column pair of the C fragment
+    const int u_e = nq * MF_TN + (col ^ sw_e);           // + rb*8*32 doubles
+    const unsigned a_lane = 16u * lane;
+    const unsigned a_op = 512u * P.nrb;                  // bytes per operator within a ring stage
+    const double h = P.h;
+
+    int slot = 0;
+    unsigned phase = 0;
+    int s = 0, b0 = 0;
+    double q_s = 0.0, tl[NOPS > 1 ? NOPS - 1 : 1];
+    bool on[NOPS > 1 ? NOPS - 1 : 1];
+    for (; it.valid; it.next()) {
+        if (it.unit_begins()) {
+            s = it.c / P.ups; b0 = (it.c % P.ups) * MF_TN;
+            q_s = P.q_surf[s];
+#pragma unroll
+            for (int f = 0; f < NOPS - 1; ++f) { on[f] = P.film_surf[f] == s; tl[f] = P.t_link[f]; }
+            if (it.step > 0) {                           // first steps were integrated by the neighbour CTA
+                if (tid == 0) {
+                    const volatile int* fl = P.flags + it.c;
+                    while (*fl < it.step) {}
+                    __threadfence();
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int j = 0; j < MF_RBW; ++j) {
+                if (!FULL && j >= nj) break;
+                const int i = (rb0 + j) * 8 + nq;
+                double2 v = make_double2(0.0, 0.0);
+                if (i < r) {
+                    const double* src = P.X + ((size_t)s * r + i) * B + b0 + col;
+                    if (b0 + col < B) v.x = __ldcg(src);
+                    if (b0 + col + 1 < B) v.y = __ldcg(src + 1);
+                }
+                xb[j * MF_CTHREADS + tid] = v;
+                *reinterpret_cast<double2*>(U + (rb0 + j) * 8 * MF_TN + u_e) = v;
+            }
+            __syncthreads();
+        }
+        // surface of the stage after this one (-1: none): its first chunks are requested from inside this stage
+        int s_next;
+        {
+            MfIter nx = it;
+            nx.next();
+            s_next = nx.valid ? nx.c / P.ups : -1;
+        }
+        // film values of this stage's time for the unit's 32 columns (warp f -> film f); read after the k loop
+        if (warp < NOPS - 1) {
+            const int kidx = it.stage == 0 ? 0 : (it.stage == 3 ? 2 : 1);
+            const double t = __dadd_rn(P.t0, __dmul_rn((double)it.step, P.h)) + 0.5 * P.h * kidx;   // host: t0 + k*h
+            film[warp * MF_TN + lane] = b0 + lane < B ? mf_film_at(P, warp, b0 + lane, t) : 0.0;
+        }
+        // ---- k loop of one stage: Z_o = W_o,s . U for the NOPS operators ----
+        double acc[NOPS][MF_RBW][2];
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+            for (int j = 0; j < MF_RBW; ++j) acc[o][j][0] = acc[o][j][1] = 0.0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            mf_mbar_wait(bars + 8u * slot, phase);
+            const unsigned abase = ring + (unsigned)slot * P.stage_bytes + 512u * rb0 + a_lane;
+            const double bf0 = mf_lds64(u_b + 2048u * ch);
+            const double bf1 = mf_lds64(u_b + 2048u * ch + 1024u);
+#pragma unroll
+            for (int o = 0; o < NOPS; ++o) {
+                double2 a[MF_RBW];
+#pragma unroll
+                for (int j = 0; j < MF_RBW; ++j)
+                    if (FULL || j < nj) a[j] = mf_lds128(abase + o * a_op + 512u * j);
+#pragma unroll
+                for (int j = 0; j < MF_RBW; ++j)
+                    if (FULL || j < nj) mf_dmma(acc[o][j][0], acc[o][j][1], a[j].x, bf0);
+#pragma unroll
+                for (int j = 0; j < MF_RBW; ++j)
+                    if (FULL || j < nj) mf_dmma(acc[o][j][0], acc[o][j][1], a[j].y, bf1);
+            }
+            __syncwarp();
+            // the LAST warp to release a ring slot refills it (nobody ever waits for an empty slot)
+            if (lane == 0 && atomicAdd(cnt + slot, 1u) == MF_CWARPS - 1) {
+                *((volatile unsigned*)(cnt + slot)) = 0u;
+                int nch = ch + ns, sn = s;
+                if (nch >= nchunks) { nch -= nchunks; sn = s_next; }
+                if (sn >= 0) {
+                    mf_mbar_expect_tx(bars + 8u * slot, (unsigned)P.stage_bytes);
+                    mf_bulk_g2s(ring + (unsigned)slot * P.stage_bytes,
+                                P.packed + ((size_t)sn * nchunks + nch) * stage_doubles, (unsigned)P.stage_bytes,
+                                bars + 8u * slot);
+                }
+            }
+            if (++slot == ns) { slot = 0; phase ^= 1u; }
+        }
+        __syncthreads();                                 // everybody is done reading U; film values are in place
+        // ---- epilogue: film weighting, input term, RK4 stage update; all operands in shared memory ----
+        {
+            double fvv[NOPS > 1 ? NOPS - 1 : 1][2];
+            double flux[2] = {q_s, q_s};
+#pragma unroll
+            for (int f = 0; f < NOPS - 1; ++f) {
+                const double2 v = *reinterpret_cast<const double2*>(film + f * MF_TN + col);
+                fvv[f][0] = v.x; fvv[f][1] = v.y;
+                if (on[f]) { flux[0] += v.x * tl[f]; flux[1] += v.y * tl[f]; }
+            }
+            const int stage = it.stage;
+            const double c_out = stage == 2 ? 1.0 : 0.5;
+            const double c_acc = (stage == 0 || stage == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
+            const double ho = c_out * h, ha = c_acc * h;
+#pragma unroll
+            for (int j = 0; j < MF_RBW; ++j) {
+                if (!FULL && j >= nj) break;
+                const int i = (rb0 + j) * 8 + nq;
+                if (i >= r) continue;                   // padding rows stay zero
+                const double bt = __ldg(P.B_T + (size_t)s * r + i);
+                double kv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double z = acc[0][j][e];
+#pragma unroll
+                    for (int f = 0; f < NOPS - 1; ++f) z += fvv[f][e] * acc[f + 1][j][e];
+                    kv[e] = -z + bt * flux[e];
+                }
+                const int own = j * MF_CTHREADS + tid;
+                const double2 x0 = xb[own];
+                const double2 base = stage == 0 ? x0 : xacc[own];
+                const double2 na = make_double2(base.x + ha * kv[0], base.y + ha * kv[1]);
+                double2 u;
+                if (stage < 3) {
+                    xacc[own] = na;
+                    u = make_double2(x0.x + ho * kv[0], x0.y + ho * kv[1]);
+                } else {
+                    xb[own] = na;                        // x_{n+1}
+                    u = na;
+                }
+                *reinterpret_cast<double2*>(U + (rb0 + j) * 8 * MF_TN + u_e) = u;
+            }
+        }
+        if (it.unit_ends()) {
+            // hand the unit back (or over to the neighbour CTA that integrates its remaining steps)
+#pragma unroll
+            for (int j = 0; j < MF_RBW; ++j) {
+                if (!FULL && j >= nj) break;
+                const int i = (rb0 + j) * 8 + nq;
+                if (i < r) {
+                    const double2 v = xb[j * MF_CTHREADS + tid];
+                    double* dst = P.X + ((size_t)s * r + i) * B + b0 + col;
+                    if (b0 + col < B) __stcg(dst, v.x);
+                    if (b0 + col + 1 < B) __stcg(dst + 1, v.y);
+                }
+            }
+            if (it.step_end < P.L) {
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence();
+                    *((volatile int*)(P.flags + it.c)) = it.step_end;
+                }
+            }
+        }
+        __syncthreads();                                 // U complete before the next stage reads it
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+static bool mf_layout(int S, int r, int F, int B, MorFused& P) {
+    if (F < 0 || F > 2 || r < 1 || r > 8 * MF_RBW * MF_GROUPS || S < 1 || B < 1) return false;
+    const int nops = F + 1;
+    P.S = S; P.r = r; P.F = F; P.B = B;
+    P.nrb = (r + 7) / 8;
+    P.rbw = (P.nrb + MF_GROUPS - 1) / MF_GROUPS;
+    P.nchunks = (r + MF_KC - 1) / MF_KC;
+    P.ups = (B + MF_TN - 1) / MF_TN;
+    P.stage_bytes = nops * P.nrb * 512;
+    const int u_bytes = P.nrb * 8 * MF_TN * 8;
+    const int own_bytes = P.rbw * MF_CTHREADS * 16;
+    const int film_bytes = (F > 0 ? F : 1) * MF_TN * 8;
+    const int bar_bytes = 128;
+    const int fixed = u_bytes + 2 * own_bytes + film_bytes + bar_bytes;
+    int ns = (MF_SMEM_MAX - fixed) / P.stage_bytes;
+    if (ns > 4) ns = 4;
+    if (ns > P.nchunks) ns = P.nchunks;
+    if (ns < 1 || (ns < 2 && P.nchunks > 1)) return false;
+    P.ns = ns;
+    P.off_U = ns * P.stage_bytes;
+    P.off_xb = P.off_U + u_bytes;
+    P.off_xacc = P.off_xb + own_bytes;
+    P.off_film = P.off_xacc + own_bytes;
+    P.off_bar = P.off_film + film_bytes;
+    return true;
+}
+
+extern "C" int32_t tc_mor_fused_supported(int32_t S, int32_t r, int32_t F, int32_t B) {
+    MorFused P{};
+    return mf_layout(S, r, F, B, P) ? 1 : 0;
+}
+
+extern "C" int64_t tc_mor_fused_packed_doubles(int32_t S, int32_t r, int32_t F) {
+    const int64_t nrb = (r + 7) / 8, nchunks = (r + MF_KC - 1) / MF_KC;
+    return (int64_t)S * nchunks * (F + 1) * nrb * 64;
+}
+
+extern "C" int64_t tc_mor_fused_work_bytes(int32_t S, int32_t r, int32_t F, int32_t B) {
+    return 4LL * S * ((B + MF_TN - 1) / MF_TN) + 64;
+}
+
+extern "C" int tc_mor_fused_pack(void* cuda_stream, int32_t S, int32_t r, int32_t F, const double* A_body,
+                                 const double* A_films, double* packed) {
+    MorFused P{};
+    TC_CHECK(mf_layout(S, r, F, 32, P), "shape not supported by the fused MOR kernel");
+    const int64_t n = tc_mor_fused_packed_doubles(S, r, F);
+    const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+    tc_mor_fused_pack_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(S, r, F + 1, P.nrb, P.nchunks, A_body, A_films,
+                                                                           packed);
+    TC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NOPS, bool FULL>
+static int mf_launch(const MorFused& P, int grid, size_t smem, cudaStream_t st) {
+    static unsigned long long configured = 0ULL;
+    int devid = 0;
+    TC_CUDA(cudaGetDevice(&devid));
+    if (devid >= 64 || !(configured >> devid & 1ULL)) {
+        TC_CUDA(cudaFuncSetAttribute(tc_mor_fused_kernel<NOPS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     MF_SMEM_MAX));
+        if (devid < 64) configured |= 1ULL << devid;
+    }
+    MorFused Pc = P;
+    void* args[] = {(void*)&Pc};
+    // co-residency of all CTAs is required by the hand-over flags: cooperative launch guarantees it (or fails)
+    TC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_mor_fused_kernel<NOPS, FULL>, dim3(grid), dim3(MF_THREADS), args,
+                                        smem, st));
+    return 0;
+}
+
+extern "C" int tc_mor_fused_steps(void* cuda_stream, int32_t S, int32_t r, int32_t F, int32_t B, const double* packed,
+                                  const double* B_T, const int32_t* film_surf, const double* film_h0,
+                                  const double* film_tau, const double* t_link, const double* q_surf, double* X,
+                                  void* work, double t0, double h, int32_t nsteps) {
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    MorFused P{};
+    TC_CHECK(mf_layout(S, r, F, B, P), "shape not supported by the fused MOR kernel");
+    if (nsteps <= 0) return 0;
+    int devid = 0, sms = 0;
+    TC_CUDA(cudaGetDevice(&devid));
+    TC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid));
+    P.L = nsteps;
+    P.total = (long long)S * P.ups * nsteps;
+    const int grid = (int)(P.total < sms ? P.total : sms);
+    P.T = (P.total + grid - 1) / grid;
+    P.packed = packed; P.B_T = B_T; P.film_surf = film_surf; P.film_h0 = film_h0; P.film_tau = film_tau;
+    P.t_link = t_link; P.q_surf = q_surf; P.X = X; P.flags = (int*)work; P.t0 = t0; P.h = h;
+    TC_CUDA(cudaMemsetAsync(work, 0, 4 * (size_t)S * P.ups, st));
+    const size_t smem = (size_t)P.off_bar + 128;
+    const bool full = P.nrb == MF_RBW * MF_GROUPS;
+    int rc;
+    switch (F) {
+        case 0: rc = full ? mf_launch<1, true>(P, grid, smem, st) : mf_launch<1, false>(P, grid, smem, st); break;
+        case 1: rc = full ? mf_launch<2, true>(P, grid, smem, st) : mf_launch<2, false>(P, grid, smem, st); break;
+        default: rc = full ? mf_launch<3, true>(P, grid, smem, st) : mf_launch<3, false>(P, grid, smem, st); break;
+    }
+    return rc;
+}

@@ -44,6 +44,18 @@ class MorEnsemble:
         nwork = int(self.lib.tc_mor_batch_work_doubles(self.S, self.r, self.F, self.B))
         self.work = torch.empty(nwork, dtype=torch.float64, device=self.dev)
         self.time = 0.0
+        # fused persistent kernel (csrc/mor_fused.cu): operators packed once into DMMA fragment order
+        self.fused = bool(self.lib.tc_mor_fused_supported(self.S, self.r, self.F, self.B))
+        if self.fused:
+            st = torch.cuda.current_stream(self.dev)
+            self.packed = torch.empty(int(self.lib.tc_mor_fused_packed_doubles(self.S, self.r, self.F)),
+                                      dtype=torch.float64, device=self.dev)
+            self.fwork = torch.empty(int(self.lib.tc_mor_fused_work_bytes(self.S, self.r, self.F, self.B)),
+                                     dtype=torch.uint8, device=self.dev)
+            _cabi.check(self.lib.tc_mor_fused_pack(C.c_void_p(st.cuda_stream), self.S, self.r, self.F,
+                                                   C.c_void_p(self.t["A_body"].data_ptr()),
+                                                   C.c_void_p(self.t["A_films"].data_ptr()),
+                                                   C.c_void_p(self.packed.data_ptr())))
         torch.cuda.synchronize(self.dev)
 
     @classmethod
@@ -68,12 +80,23 @@ class MorEnsemble:
         X = self.state()                                       # (S, r, B)
         return np.einsum("srq,srb->qb", self.C_surfs, X) + self.ref_temp
 
-    def steps(self, nsteps, h, use_dmma=2, stream=None):
-        """use_dmma: 2 = pipelined DMMA kernel (default), 1 = simple DMMA kernel, 0 = FMA cross-check."""
+    def steps(self, nsteps, h, use_dmma=3, stream=None):
+        """use_dmma: 3 = fused persistent DMMA kernel (default; shapes it does not cover — F > 2 or r > 200 — run
+        mode 2), 2 = one pipelined DMMA kernel per RK4 stage, 1 = simple DMMA kernel, 0 = FMA cross-check."""
         torch = self.torch
         st = torch.cuda.current_stream(self.dev) if stream is None else stream
         p = lambda a: C.c_void_p(a.data_ptr())
         t = self.t
+        self.last_mode = use_dmma
+        if use_dmma == 3 and not self.fused:
+            use_dmma = self.last_mode = 2
+        if use_dmma == 3:
+            _cabi.check(self.lib.tc_mor_fused_steps(
+                C.c_void_p(st.cuda_stream), self.S, self.r, self.F, self.B, p(self.packed), p(t["B_T"]),
+                p(t["film_surf"]), p(t["film_h0"]), p(t["film_tau"]), p(t["t_link"]), p(t["q_surf"]), p(self.X),
+                p(self.fwork), float(self.time), float(h), int(nsteps)))
+            self.time += nsteps * h
+            return
         _cabi.check(self.lib.tc_mor_batch_steps(
             C.c_void_p(st.cuda_stream), self.S, self.r, self.F, self.B, p(t["A_body"]), p(t["A_films"]), p(t["B_T"]),
             p(t["film_surf"]), p(t["film_h0"]), p(t["film_tau"]), p(t["t_link"]), p(t["q_surf"]), p(self.X),
@@ -85,11 +108,16 @@ class MorEnsemble:
         return self.X.cpu().numpy()
 
     def launches_per_step(self):
-        """Kernels per RK4 step of the default path: film table + four stage kernels."""
+        """Kernels per RK4 step of the per-stage path (mode 2): film table + four stage kernels.  The fused path
+        (mode 3) is ONE launch per ``steps`` call, whatever the number of steps."""
         return 5
 
+    def launches(self, nsteps):
+        """Kernel launches of one ``steps(nsteps, ...)`` call on the default path."""
+        return 1 if self.fused else nsteps * self.launches_per_step()
+
     def kernel_name(self):
-        return "tc_mor_stage_pipe_kernel<3>"
+        return f"tc_mor_fused_kernel<{self.F + 1}>" if self.fused else f"tc_mor_stage_pipe_kernel<{self.F + 1}>"
 
     def flops_per_step(self):
         return 4 * 2.0 * (1 + self.F) * self.r * self.r * self.S * self.B
