@@ -22,19 +22,20 @@
 //     and for the rest by its neighbour (at the END of its time line); the hand-over goes through X + a step flag.
 #include "common.cuh"
 #include "../../include/thermca_b200.h"
+#include <stdlib.h>
 
 #define MF_TN 32             // scenario columns per unit
 #define MF_GROUPS 5          // row groups
 #define MF_CWARPS 20         // consumer warps = MF_GROUPS x 4 column blocks
 #define MF_CTHREADS (MF_CWARPS * 32)
 #define MF_THREADS MF_CTHREADS
-#define MF_KC 8              // k per ring chunk (two k4-steps)
+// k per ring chunk: KC = 4 * KF, KF = 1 or 2 k4-steps (template parameter)
 #define MF_RBW 5             // max 8-row blocks per warp  -> r <= 200
 #define MF_SMEM_MAX 232448   // 227 KB
 
 struct MorFused {
     int S, r, F, B;
-    int nrb, rbw, nchunks, ns, ups, L;
+    int nrb, rbw, nchunks, ns, ups, L, kf, zero;
     long long total, T;
     const double* packed; const double* B_T; const int* film_surf; const double* film_h0; const double* film_tau;
     const double* t_link; const double* q_surf;
@@ -122,18 +123,20 @@ __device__ __forceinline__ double mf_film_at(const MorFused& P, int f, int b, do
     return P.film_h0[(size_t)f * P.B + b] * (1.0 + 0.5 * sin(TWO_PI * t / P.film_tau[(size_t)f * P.B + b]));
 }
 
-// operators -> fragment order: packed[s][chunk][op][rb][lane][2] = W_op,s[rb*8 + lane/4][chunk*8 + 4*j + lane%4], zero padded
-__global__ void tc_mor_fused_pack_kernel(int S, int r, int nops, int nrb, int nchunks, const double* __restrict__ A_body,
-                                         const double* __restrict__ A_films, double* __restrict__ packed) {
-    const size_t n = (size_t)S * nchunks * nops * nrb * 64;
+// operators -> fragment order: packed[s][chunk][op][rb][lane][kf] = W_op,s[rb*8 + lane/4][chunk*4*kf + 4*j + lane%4],
+// zero padded
+__global__ void tc_mor_fused_pack_kernel(int S, int r, int nops, int nrb, int nchunks, int kf,
+                                         const double* __restrict__ A_body, const double* __restrict__ A_films,
+                                         double* __restrict__ packed) {
+    const size_t n = (size_t)S * nchunks * nops * nrb * 32 * kf;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(e & 1), lane = (int)((e >> 1) & 31);
-        size_t q = e >> 6;
+        const int j = (int)(e % kf), lane = (int)((e / kf) & 31);
+        size_t q = e / (32 * kf);
         const int rb = (int)(q % nrb); q /= nrb;
         const int o = (int)(q % nops); q /= nops;
         const int ch = (int)(q % nchunks);
         const int s = (int)(q / nchunks);
-        const int row = rb * 8 + (lane >> 2), k = ch * MF_KC + 4 * j + (lane & 3);
+        const int row = rb * 8 + (lane >> 2), k = ch * 4 * kf + 4 * j + (lane & 3);
         double v = 0.0;
         if (row < r && k < r) {
             const double* W = o == 0 ? A_body + (size_t)s * r * r : A_films + ((size_t)(o - 1) * S + s) * r * r;
@@ -143,7 +146,7 @@ __global__ void tc_mor_fused_pack_kernel(int S, int r, int nops, int nrb, int nc
     }
 }
 
-template <int NOPS, bool FULL>
+template <int NOPS, bool FULL, int KF>
 __global__ void __launch_bounds__(MF_THREADS, 1)
 tc_mor_fused_kernel(const MorFused P) {
     extern __shared__ __align__(128) unsigned char mf_smem_raw[];
@@ -187,8 +190,10 @@ tc_mor_fused_kernel(const MorFused P) {
     const int sw_e = ((nq & 3) << 2) ^ ((nq & 1) << 3);
     const int col = cb * 8 + 2 * kq;                     // local column pair of the C fragment
     const int u_e = nq * MF_TN + (col ^ sw_e);           // + rb*8*32 doubles
-    const unsigned a_lane = 16u * lane;
-    const unsigned a_op = 512u * P.nrb;                  // bytes per operator within a ring stage
+    constexpr unsigned RB_BYTES = 256u * KF;             // one 8-row block of one operator within a ring chunk
+    const unsigned a_lane = 8u * KF * lane;
+    const unsigned a_op = RB_BYTES * P.nrb;              // bytes per operator within a ring stage
+    const unsigned cnt0 = mf_smem(cnt);
     const double h = P.h;
 
     int slot = 0;
@@ -245,26 +250,45 @@ tc_mor_fused_kernel(const MorFused P) {
 #pragma unroll
             for (int j = 0; j < MF_RBW; ++j) acc[o][j][0] = acc[o][j][1] = 0.0;
         for (int ch = 0; ch < nchunks; ++ch) {
+            const double bf0 = mf_lds64(u_b + 1024u * KF * ch);       // U does not depend on the ring
+            double bf1 = 0.0;
+            if (KF == 2) bf1 = mf_lds64(u_b + 2048u * ch + 1024u);
             mf_mbar_wait(bars + 8u * slot, phase);
-            const unsigned abase = ring + (unsigned)slot * P.stage_bytes + 512u * rb0 + a_lane;
-            const double bf0 = mf_lds64(u_b + 2048u * ch);
-            const double bf1 = mf_lds64(u_b + 2048u * ch + 1024u);
+            const unsigned abase = ring + (unsigned)slot * P.stage_bytes + RB_BYTES * rb0 + a_lane;
+            unsigned old = 0u;
 #pragma unroll
             for (int o = 0; o < NOPS; ++o) {
                 double2 a[MF_RBW];
 #pragma unroll
                 for (int j = 0; j < MF_RBW; ++j)
-                    if (FULL || j < nj) a[j] = mf_lds128(abase + o * a_op + 512u * j);
+                    if (FULL || j < nj) {
+                        if (KF == 2) a[j] = mf_lds128(abase + o * a_op + RB_BYTES * j);
+                        else a[j].x = mf_lds64(abase + o * a_op + RB_BYTES * j);
+                    }
+                if (o == NOPS - 1) {
+                    // Release the slot as soon as this warp's last fragment loads have RETURNED (the integer ops
+                    // below consume them), not after its last DMMA: the round trip of the shared-memory atomic
+                    // overlaps the remaining DMMAs.  The LAST warp to release a slot refills it, so nobody ever
+                    // waits for an empty slot.  P.zero is a run-time 0 the compiler cannot fold.
+                    int dep = __double2hiint(bf0) | __double2hiint(bf1);
+#pragma unroll
+                    for (int j = 0; j < MF_RBW; ++j)
+                        if (FULL || j < nj) dep |= __double2hiint(a[j].x);
+                    dep = min((unsigned)dep, (unsigned)P.zero);
+                    if (lane == 0)
+                        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(cnt0 + 4u * slot), "r"(1u + dep)
+                                     : "memory");
+                }
 #pragma unroll
                 for (int j = 0; j < MF_RBW; ++j)
                     if (FULL || j < nj) mf_dmma(acc[o][j][0], acc[o][j][1], a[j].x, bf0);
+                if (KF == 2) {
 #pragma unroll
-                for (int j = 0; j < MF_RBW; ++j)
-                    if (FULL || j < nj) mf_dmma(acc[o][j][0], acc[o][j][1], a[j].y, bf1);
+                    for (int j = 0; j < MF_RBW; ++j)
+                        if (FULL || j < nj) mf_dmma(acc[o][j][0], acc[o][j][1], a[j].y, bf1);
+                }
             }
-            __syncwarp();
-            // the LAST warp to release a ring slot refills it (nobody ever waits for an empty slot)
-            if (lane == 0 && atomicAdd(cnt + slot, 1u) == MF_CWARPS - 1) {
+            if (lane == 0 && old == MF_CWARPS - 1) {
                 *((volatile unsigned*)(cnt + slot)) = 0u;
                 int nch = ch + ns, sn = s;
                 if (nch >= nchunks) { nch -= nchunks; sn = s_next; }
@@ -347,22 +371,23 @@ tc_mor_fused_kernel(const MorFused P) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
-static bool mf_layout(int S, int r, int F, int B, MorFused& P) {
+static bool mf_layout(int S, int r, int F, int B, int kf, MorFused& P) {
     if (F < 0 || F > 2 || r < 1 || r > 8 * MF_RBW * MF_GROUPS || S < 1 || B < 1) return false;
     const int nops = F + 1;
     P.S = S; P.r = r; P.F = F; P.B = B;
     P.nrb = (r + 7) / 8;
     P.rbw = (P.nrb + MF_GROUPS - 1) / MF_GROUPS;
-    P.nchunks = (r + MF_KC - 1) / MF_KC;
+    P.kf = kf; P.zero = 0;
+    P.nchunks = (r + 4 * kf - 1) / (4 * kf);
     P.ups = (B + MF_TN - 1) / MF_TN;
-    P.stage_bytes = nops * P.nrb * 512;
+    P.stage_bytes = nops * P.nrb * 256 * kf;
     const int u_bytes = P.nrb * 8 * MF_TN * 8;
     const int own_bytes = P.rbw * MF_CTHREADS * 16;
     const int film_bytes = (F > 0 ? F : 1) * MF_TN * 8;
     const int bar_bytes = 128;
     const int fixed = u_bytes + 2 * own_bytes + film_bytes + bar_bytes;
     int ns = (MF_SMEM_MAX - fixed) / P.stage_bytes;
-    if (ns > 4) ns = 4;
+    if (ns > 6) ns = 6;
     if (ns > P.nchunks) ns = P.nchunks;
     if (ns < 1 || (ns < 2 && P.nchunks > 1)) return false;
     P.ns = ns;
@@ -374,14 +399,28 @@ static bool mf_layout(int S, int r, int F, int B, MorFused& P) {
     return true;
 }
 
+// k4-steps per ring chunk: 2 (default: a 200 x 200 x 3 operator set in 25 chunks of 38 KB, 2 ring slots) or 1 (50 chunks
+// of 19 KB, 4 slots).  Measured on the B200 (S=3, r=200, F=2, B=4096): 11.24 vs 10.39 M scenarios*steps/s — the
+// per-chunk cost (barrier wait, release, fragment-load start-up) outweighs the deeper ring.  TC_MOR_KF overrides
+// (read once; pack and step must agree)
+static int mf_kf() {
+    static int kf = 0;
+    if (kf == 0) {
+        const char* e = getenv("TC_MOR_KF");
+        kf = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return kf;
+}
+
 extern "C" int32_t tc_mor_fused_supported(int32_t S, int32_t r, int32_t F, int32_t B) {
     MorFused P{};
-    return mf_layout(S, r, F, B, P) ? 1 : 0;
+    return mf_layout(S, r, F, B, mf_kf(), P) ? 1 : 0;
 }
 
 extern "C" int64_t tc_mor_fused_packed_doubles(int32_t S, int32_t r, int32_t F) {
-    const int64_t nrb = (r + 7) / 8, nchunks = (r + MF_KC - 1) / MF_KC;
-    return (int64_t)S * nchunks * (F + 1) * nrb * 64;
+    const int kf = mf_kf();
+    const int64_t nrb = (r + 7) / 8, nchunks = (r + 4 * kf - 1) / (4 * kf);
+    return (int64_t)S * nchunks * (F + 1) * nrb * 32 * kf;
 }
 
 extern "C" int64_t tc_mor_fused_work_bytes(int32_t S, int32_t r, int32_t F, int32_t B) {
@@ -391,31 +430,38 @@ extern "C" int64_t tc_mor_fused_work_bytes(int32_t S, int32_t r, int32_t F, int3
 extern "C" int tc_mor_fused_pack(void* cuda_stream, int32_t S, int32_t r, int32_t F, const double* A_body,
                                  const double* A_films, double* packed) {
     MorFused P{};
-    TC_CHECK(mf_layout(S, r, F, 32, P), "shape not supported by the fused MOR kernel");
+    TC_CHECK(mf_layout(S, r, F, 32, mf_kf(), P), "shape not supported by the fused MOR kernel");
     const int64_t n = tc_mor_fused_packed_doubles(S, r, F);
     const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-    tc_mor_fused_pack_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(S, r, F + 1, P.nrb, P.nchunks, A_body, A_films,
-                                                                           packed);
+    tc_mor_fused_pack_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(S, r, F + 1, P.nrb, P.nchunks, P.kf, A_body,
+                                                                           A_films, packed);
     TC_CUDA(cudaGetLastError());
     return 0;
 }
 
-template <int NOPS, bool FULL>
+template <int NOPS, bool FULL, int KF>
 static int mf_launch(const MorFused& P, int grid, size_t smem, cudaStream_t st) {
     static unsigned long long configured = 0ULL;
     int devid = 0;
     TC_CUDA(cudaGetDevice(&devid));
     if (devid >= 64 || !(configured >> devid & 1ULL)) {
-        TC_CUDA(cudaFuncSetAttribute(tc_mor_fused_kernel<NOPS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TC_CUDA(cudaFuncSetAttribute(tc_mor_fused_kernel<NOPS, FULL, KF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      MF_SMEM_MAX));
         if (devid < 64) configured |= 1ULL << devid;
     }
     MorFused Pc = P;
     void* args[] = {(void*)&Pc};
     // co-residency of all CTAs is required by the hand-over flags: cooperative launch guarantees it (or fails)
-    TC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_mor_fused_kernel<NOPS, FULL>, dim3(grid), dim3(MF_THREADS), args,
-                                        smem, st));
+    TC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_mor_fused_kernel<NOPS, FULL, KF>, dim3(grid), dim3(MF_THREADS),
+                                        args, smem, st));
     return 0;
+}
+
+template <int NOPS>
+static int mf_dispatch(const MorFused& P, int grid, size_t smem, cudaStream_t st) {
+    const bool full = P.nrb == MF_RBW * MF_GROUPS;
+    if (P.kf == 2) return full ? mf_launch<NOPS, true, 2>(P, grid, smem, st) : mf_launch<NOPS, false, 2>(P, grid, smem, st);
+    return full ? mf_launch<NOPS, true, 1>(P, grid, smem, st) : mf_launch<NOPS, false, 1>(P, grid, smem, st);
 }
 
 extern "C" int tc_mor_fused_steps(void* cuda_stream, int32_t S, int32_t r, int32_t F, int32_t B, const double* packed,
@@ -424,7 +470,7 @@ extern "C" int tc_mor_fused_steps(void* cuda_stream, int32_t S, int32_t r, int32
                                   void* work, double t0, double h, int32_t nsteps) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     MorFused P{};
-    TC_CHECK(mf_layout(S, r, F, B, P), "shape not supported by the fused MOR kernel");
+    TC_CHECK(mf_layout(S, r, F, B, mf_kf(), P), "shape not supported by the fused MOR kernel");
     if (nsteps <= 0) return 0;
     int devid = 0, sms = 0;
     TC_CUDA(cudaGetDevice(&devid));
@@ -437,12 +483,9 @@ extern "C" int tc_mor_fused_steps(void* cuda_stream, int32_t S, int32_t r, int32
     P.t_link = t_link; P.q_surf = q_surf; P.X = X; P.flags = (int*)work; P.t0 = t0; P.h = h;
     TC_CUDA(cudaMemsetAsync(work, 0, 4 * (size_t)S * P.ups, st));
     const size_t smem = (size_t)P.off_bar + 128;
-    const bool full = P.nrb == MF_RBW * MF_GROUPS;
-    int rc;
     switch (F) {
-        case 0: rc = full ? mf_launch<1, true>(P, grid, smem, st) : mf_launch<1, false>(P, grid, smem, st); break;
-        case 1: rc = full ? mf_launch<2, true>(P, grid, smem, st) : mf_launch<2, false>(P, grid, smem, st); break;
-        default: rc = full ? mf_launch<3, true>(P, grid, smem, st) : mf_launch<3, false>(P, grid, smem, st); break;
+        case 0: return mf_dispatch<1>(P, grid, smem, st);
+        case 1: return mf_dispatch<2>(P, grid, smem, st);
+        default: return mf_dispatch<3>(P, grid, smem, st);
     }
-    return rc;
 }
