@@ -74,6 +74,9 @@ typedef struct {
      * is stepped explicitly inside the implicit scheme */
     int32_t j_nslices;
     const int64_t* j_slice_ptr; const int32_t* j_col; const double* j_val; const double* j_mass; const double* j_adiag;
+    /* fd_rhs != 0: films vary and every right-hand side refreshes the diagonal from the fd_* lists (the reference's
+     * per-call copy, ffe_io.py:76-82); 0 with fd_nrows > 0: the lists only serve tc_set_jac_films */
+    int32_t fd_rhs;
 } tc_ffe_desc;
 
 /* ---- LP part (replaces LPIO at run time, thermca/lpm/lp_io.py:8-80); operator and load
@@ -87,6 +90,7 @@ typedef struct {
     int32_t b_doff;                 /* dense load vector M_inv*(Qs flux + L_film_margs T_link) */
     int32_t mass_doff;
     int32_t adiag_doff;             /* dense diag(A), kept current by the network kernel */
+    int32_t F, lfm_doff, minv_doff; /* L_film_margs[n][F] and M_inv[n] (lp_io.py:83-103), read by tc_set_jac_films */
 } tc_lp_desc;
 
 /* ---- MOR part (replaces MORIO at run time, thermca/fem/mor_io.py:78-92) ------------------ */
@@ -106,6 +110,15 @@ int tc_add_ffe_part(tc_handle h, const tc_ffe_desc* d);
 int tc_add_lp_part(tc_handle h, const tc_lp_desc* d);
 int tc_add_mor_part(tc_handle h, const tc_mor_desc* d);
 int tc_finalize(tc_handle h, int64_t n_state);
+/* Films between a part surface and a STATIONARY node (thermca/solver.py:30-42; the reference's idiom for a
+ * prescribed surface heat flow is StatNode + HeatSource + a stiff film, thermca/tests/test_lp_part.py:655-660).
+ * The node follows the surface instantly, so inside the Jacobian of the implicit W-methods (tc_ros2_*, tc_row3_*)
+ * such a film is the rank-one term u c^T (u: the film's load vector times theta = g_film / sum of the node's
+ * conductances, kept by the network kernel at theta_doff; c: the surface-mean weights = mean job `job`), applied
+ * through the Woodbury identity around the block solves.  The right-hand side is not affected.
+ * rec7[n][7] = {kind (0 LP, 1 FE, 2 MOR), part, film, surface of the film, mean job, theta_doff, film_doff};
+ * n <= 4; call after tc_finalize. */
+int tc_set_jac_films(tc_handle h, int32_t n, const int32_t* rec7);
 
 /* Right-hand side f(t, y) = update_time_derivative (solver.py:193-302). Stateful like the
  * reference: node temperatures, heat sources and conductances persist between calls. */

@@ -32,7 +32,7 @@ from thermca_b200.lowering import lower_network, initial_state  # noqa: E402
 from thermca_b200.spec import save_spec  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
-MAX_RHS = {"default": 48, "plate_ffe": 14, "plate_ffe_var": 14, "kuhn_cuboid": 20, "tdep_rod": 20, "assembly": 16}
+MAX_RHS = {"default": 48, "plate_ffe": 14, "plate_ffe_var": 14, "plate_ffe_stat": 8, "plate_ffe_statc": 8, "kuhn_cuboid": 20, "tdep_rod": 20, "assembly": 16}
 MAX_IO_SNAPSHOTS = 8
 
 

@@ -243,6 +243,44 @@ def lp_tdep():
 MODELS["lp_tdep"] = lp_tdep
 
 
+def _plate_stat(mor_dof, variable):
+    """Plate fed and cooled through stationary nodes (the reference's idiom for a prescribed surface heat flow:
+    StatNode + HeatSource + a stiff film, thermca/tests/test_lp_part.py:655-660 — here on an FE / MOR body).
+    Exercises the W-methods' Jacobian model for films that lead to stationary nodes (csrc/network.cuh C_JFAC)."""
+    mesh = Mesh.read(PLATE_MSH, file_format="gmsh")
+    with Model() as model:
+        plate = FEPart(mesh, test_steel, init_temp=20.0, mor_dof=mor_dof, lump_cond_meth=None, name="plate")
+        env = BoundNode(temp=20.0, name="environment")
+        feed = StatNode(name="feed")
+        FilmLink(plate.surf.bottom, feed, 1.0e5)                # the node only carries the source: flux condition
+        HeatSource(feed, heat=1000.0)
+        mid = StatNode(name="mid")                              # film in series with a conductance
+        if variable:
+            FilmLink(plate.surf.top, mid, free_conv.vert_surf(surf_hgt=0.5), matl=fluids.air)
+        else:
+            FilmLink(plate.surf.top, mid, 2000.0)
+        CondLink(mid, env, 2.0)
+        FilmLink.multi([plate.surf.left, plate.surf.right], env, 10.0)
+    return Network(model)
+
+
+def plate_ffe_stat():
+    return _plate_stat(None, True), dict(time_span=[0.0, 30.0], method="RK45")
+
+
+def plate_ffe_statc():
+    return _plate_stat(None, False), dict(time_span=[0.0, 30.0], method="RK45")
+
+
+def plate_mor_stat():
+    return _plate_stat(10, True), dict(time_span=[0.0, 300.0], method="RK45")
+
+
+MODELS["plate_ffe_stat"] = plate_ffe_stat
+MODELS["plate_ffe_statc"] = plate_ffe_statc
+MODELS["plate_mor_stat"] = plate_mor_stat
+
+
 def steel_sheet():
     """The LPPart steel sheet of the ``Result`` doctest (thermca/resultdata.py:81-131): its printed
     temperature table is a known answer of the reference for an LP transient."""

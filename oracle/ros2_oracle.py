@@ -52,8 +52,81 @@ class Ros2Oracle:
             self.ffe_gate.append(_diag_first(A0))
             self.ffe_frozen.append(A0 if p.get("tdep") is not None else None)
         self.solves = 0
+        # films that lead to a STATIONARY node: rank-one Jacobian terms (csrc/solver.cu enqueue_jac_prepare)
+        stat = set(int(i) for i in spec["stat_idx"])
+        self.jac_films = []                              # (kind, part, film, C column)
+        offs = {"lp": r.lp_off, "ffe": r.ffe_off, "mor": r.mor_off}
+        for kind in ("lp", "ffe", "mor"):
+            for k, p in enumerate(spec[kind]):
+                for f in range(len(p["films"])):
+                    if int(p["link_elem_net_idxs"][f]) not in stat:
+                        continue
+                    sidx = int(p["film_surf_idxs"][f])
+                    c = np.zeros(self.n)
+                    o = offs[kind][k]
+                    if kind == "lp":
+                        c[o:o + int(p["dof"])] = np.asarray(p["C_marg"])[:, sidx]
+                    elif kind == "ffe":
+                        c[o + np.asarray(p["C_idx"][sidx])] = np.asarray(p["C_val"][sidx])
+                    else:
+                        S, rr = int(p["S"]), int(p["r"])
+                        c[o:o + S * rr] = np.asarray(p["C_surfs"]).reshape(S * rr, S)[:, sidx]
+                    self.jac_films.append((kind, k, f, c))
+        self._jac = None
+        # a block with such a film is always solved implicitly: the rank-one term alone (without the film's own
+        # diagonal term inside B) would be a destabilising Jacobian
+        self.jac_parts = set((kind, k) for kind, k, _, _ in self.jac_films)
+
+    def _jac_prepare(self, s):
+        """Once per attempt.  The temperature of a stationary node n follows its neighbours instantly
+        (thermca/solver.py:30-42): T_n = (q + sum_k g_k T_k) / G, so a film f between a part surface and n adds the
+        rank-one term  u_f c_f^T  to the part's Jacobian (u_f: the film's load vector times theta = g_f / G, c_f:
+        the surface-mean weights).  W = B - s sum_f u_f c_f^T is applied through the Woodbury identity around the
+        block solves B^-1 the scheme already has:  W^-1 r = z + Y (I - s C^T Y)^-1 s C^T z,  z = B^-1 r,
+        Y = B^-1 U."""
+        self._jac = None
+        if not self.jac_films:
+            return
+        r, spec = self.rhs, self.s
+        ip, ix, cd = r.indptr, r.indices, r.cond_data
+        K = len(self.jac_films)
+        U = np.zeros((self.n, K))
+        C = np.zeros((self.n, K))
+        for j, (kind, k, f, c) in enumerate(self.jac_films):
+            p = spec[kind][k]
+            st = getattr(r, kind)[k]
+            n = int(p["link_elem_net_idxs"][f])
+            sn = int(np.asarray(p["surf_net_idxs"])[int(p["film_surf_idxs"][f])])
+            G = g = 0.0
+            for kk in range(ip[n], ip[n + 1]):
+                G += cd[kk]
+                if ix[kk] == sn:
+                    g += cd[kk]
+            theta = g / G if G > 0.0 else 0.0
+            C[:, j] = c
+            if kind == "lp":
+                o, dof = r.lp_off[k], int(p["dof"])
+                U[o:o + dof, j] = theta * st["M_inv"] * np.asarray(st["L_film_margs"]).reshape(dof, -1)[:, f]
+            elif kind == "ffe":
+                o = r.ffe_off[k]
+                rows = np.searchsorted(np.asarray(p["A_body"]["indptr"]), np.asarray(p["film_didx"][f]), side="right") - 1
+                np.add.at(U[:, j], o + rows, (theta * st["films"][f]) * np.asarray(p["film_adata"][f]))
+            else:
+                rr, q = int(p["r"]), int(p["film_surf_idxs"][f])
+                o = r.mor_off[k] + q * rr
+                U[o:o + rr, j] = (theta * st["films"][f]) * np.asarray(p["B_T"][q])
+        Y = np.column_stack([self._block_solve_raw(s, U[:, j]) for j in range(K)])
+        Ginv = np.linalg.inv(np.eye(K) - s * (C.T @ Y))
+        self._jac = (C, Y, Ginv)
 
     def _block_solve(self, s, rhs):
+        z = self._block_solve_raw(s, rhs)
+        if self._jac is not None:
+            C, Y, Ginv = self._jac
+            z = z + Y @ (Ginv @ (s * (C.T @ z)))
+        return z
+
+    def _block_solve_raw(self, s, rhs):
         r, spec, u = self.rhs, self.s, self.u
         z = rhs.copy()
         if u > 0:                                    # unknown network nodes: (C + s L_uu) z = C rhs, always implicit
@@ -68,14 +141,14 @@ class Ros2Oracle:
         for k, (p, st) in enumerate(zip(spec["lp"], r.lp)):
             o, n = r.lp_off[k], int(p["dof"])
             A = sp.csr_matrix(st["A"])
-            if s * 2.0 * A.diagonal().max() < self.bound:
+            if s * 2.0 * A.diagonal().max() < self.bound and ("lp", k) not in self.jac_parts:
                 continue
             z[o:o + n] = spla.spsolve((sp.identity(n, format="csc") + s * A.tocsc()), rhs[o:o + n])
             self.solves += 1
         for k, (p, st) in enumerate(zip(spec["ffe"], r.ffe)):
             o, n = r.ffe_off[k], int(p["dof"])
             A = self.ffe_frozen[k] if self.ffe_frozen[k] is not None else sp.csr_matrix(st["A"])
-            if s * 2.0 * self.ffe_gate[k].max() < self.bound:
+            if s * 2.0 * self.ffe_gate[k].max() < self.bound and ("ffe", k) not in self.jac_parts:
                 continue
             z[o:o + n] = spla.spsolve((sp.identity(n, format="csc") + s * A.tocsc()), rhs[o:o + n])
             self.solves += 1
@@ -84,7 +157,7 @@ class Ros2Oracle:
             o = r.mor_off[k]
             for q in range(S):
                 Aq = np.asarray(st["A"][q])
-                if s * np.abs(Aq).sum(axis=1).max() < self.bound:
+                if s * np.abs(Aq).sum(axis=1).max() < self.bound and ("mor", k) not in self.jac_parts:
                     continue
                 sl = slice(o + q * rr, o + (q + 1) * rr)
                 z[sl] = np.linalg.solve(np.eye(rr) + s * Aq, rhs[sl])
@@ -118,6 +191,7 @@ class Ros2Oracle:
                 t_new = t1
             h = t_new - t
             h_abs = abs(h)
+            self._jac_prepare(GAMMA * h)
             k1 = self._block_solve(GAMMA * h, f1)
             ystage = y + h * k1
             f2 = rhs(t + 1.0 * h, ystage)

@@ -40,6 +40,7 @@ class Row3Oracle(Ros2Oracle):
 
     def attempt(self, t, y, h, f1):
         rhs, g = self.rhs, GAMMA
+        self._jac_prepare(g * h)
         u1 = self._block_solve(g * h, g * f1)
         f2 = rhs(t + ALPHA[1] * h, y + h * (AT21 * u1))
         u2 = self._block_solve(g * h, g * (f2 + C21 * u1))

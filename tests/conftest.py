@@ -10,7 +10,8 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_MODELS = ["getting_started", "coffeecup", "cutting_disc", "plate_ffe", "plate_mor", "plate_ffe_var",
-                 "plate_mor_var", "kuhn_cuboid", "tdep_rod", "assembly", "lp_tdep", "steel_sheet"]
+                 "plate_mor_var", "kuhn_cuboid", "tdep_rod", "assembly", "lp_tdep", "steel_sheet",
+                 "plate_ffe_stat", "plate_ffe_statc", "plate_mor_stat"]
 
 
 def pytest_configure(config):

@@ -21,7 +21,8 @@ import refenv  # noqa: E402
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refenv.available(), reason="reference copy oracle/_ref not staged")]
 
 MODELS = ["getting_started", "coffeecup", "cutting_disc", "plate_ffe", "plate_mor", "plate_ffe_var", "plate_mor_var",
-          "kuhn_cuboid", "tdep_rod", "assembly", "lp_tdep", "steel_sheet"]
+          "kuhn_cuboid", "tdep_rod", "assembly", "lp_tdep", "steel_sheet", "plate_ffe_stat", "plate_ffe_statc",
+          "plate_mor_stat"]
 
 
 @pytest.fixture()
@@ -133,6 +134,22 @@ def test_lsoda_request_served_by_implicit_path_within_tolerance(seam):
     assert np.max(np.abs(a - b)) <= 20 * rtol * np.max(np.abs(b))
     fa, fb = res._data.io_temps[-1], ref._data.io_temps[-1]
     assert np.max(np.abs(fa - fb)) <= 20 * rtol * np.max(np.abs(fb))
+
+
+@pytest.mark.parametrize("name", ["lp_tdep", "plate_ffe_stat", "plate_ffe_statc", "plate_mor_stat"])
+def test_lsoda_request_on_models_fed_through_stationary_nodes(seam, name):
+    """Surfaces fed through StatNode + HeatSource + a stiff film (the reference's idiom for a prescribed heat flow,
+    thermca/tests/test_lp_part.py:655-660) or cooled through a film in series with a stationary node: an LSODA request
+    through the unmodified ``Network.sim`` on the device against the reference's own LSODA run.  These are the models
+    the rank-one Jacobian terms of tc_set_jac_films exist for."""
+    rtol = 1e-5
+    net, res, net_ref, ref, kw = _both(seam, name, method="LSODA", rel_tol=rtol, abs_tol=1e-8)
+    a, b = res._data.net_temps[-1], ref._data.net_temps[-1]
+    assert res._data.times[-1] == pytest.approx(ref._data.times[-1], rel=1e-12)
+    assert np.max(np.abs(a - b)) <= 20 * rtol * np.max(np.abs(b))
+    fa, fb = res._data.io_temps[-1], ref._data.io_temps[-1]
+    assert np.max(np.abs(fa - fb)) <= 20 * rtol * np.max(np.abs(fb))
+    assert len(res._data.times) <= 2 * len(ref._data.times) + 20        # step count of LSODA's order
 
 
 def test_install_everything_full_model_build_on_device(seam):

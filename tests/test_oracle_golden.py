@@ -30,10 +30,13 @@ def test_trajectory_matches_reference(golden, name):
     out = integrate(spec, [float(sim["t0"]), float(sim["t1"])], float(sim["rel_tol"]), float(sim["abs_tol"]),
                     str(sim["method"]))
     assert len(out["times"]) == len(ref["times"])
-    assert np.allclose(out["times"], ref["times"], rtol=1e-12, atol=1e-12)
-    assert np.allclose(out["net_temps"], ref["net_temps"], rtol=1e-10, atol=1e-12)
+    # "*_stat*": a 1e5 W/m2K film between a surface and a stationary node that follows it - the right-hand side is a
+    # difference of large terms, so the summation order of the reference's BLAS calls shows at 1e-12
+    tt, tx = (1e-9, 1e-9) if "_stat" in name else (1e-12, 1e-10)
+    assert np.allclose(out["times"], ref["times"], rtol=tt, atol=1e-12)
+    assert np.allclose(out["net_temps"], ref["net_temps"], rtol=tx, atol=1e-12)
     if ref["io_temps"].size:
-        assert np.allclose(out["io_temps"][ref["io_snap_idx"]], ref["io_temps"], rtol=1e-10, atol=1e-12)
+        assert np.allclose(out["io_temps"][ref["io_snap_idx"]], ref["io_temps"], rtol=tx, atol=1e-12)
     assert out["nfev"] == int(ref["nfev"]) + 1
 
 
@@ -105,3 +108,26 @@ def test_ros2_restatement_converges_to_the_explicit_solution(golden):
             errs.append(np.abs(out["net_temps"][-1] - tight["net_temps"][-1]).max())
             assert bound != 0.0 or out["solves"] > 0
         assert errs[1] < 5e-4 and errs[1] < 0.05 * errs[0]          # measured: 9.8e-5 (gated), 3.4e-4 (always implicit)
+
+
+@pytest.mark.parametrize("name,t0,t1,max_steps", [("lp_tdep", 0.01, 3.0, 120), ("plate_ffe_stat", 0.0, 30.0, 20),
+                                                  ("plate_mor_stat", 0.0, 300.0, 200)])
+def test_row3_restatement_with_films_to_stationary_nodes(golden, name, t0, t1, max_steps):
+    """Rank-one Jacobian model for films that lead to stationary nodes (oracle/ros2_oracle.py _jac_prepare == csrc/solver.cu
+    enqueue_jac_prepare).  Without it the restatement answers these models 7e-4 .. 3e-3 off at rtol 1e-5 (measured:
+    lp_tdep 9.8e-4 in 423 steps, plate 6.9e-4 in 84, reduced plate 3.1e-3 in 501); with it the error is of the size
+    of the tolerance in 99 / 13 / 113 steps."""
+    from row3_oracle import Row3Oracle
+    from rhs_oracle import integrate
+    spec, ex = golden(name)
+    tight = integrate(spec, [t0, t1], 1e-10, 1e-12, "RK45")
+    orc = Row3Oracle(spec)
+    assert orc.jac_films
+    out = orc.integrate(t0, t1, 1e-5, 1e-8)
+    assert out["accepted"] <= max_steps
+    for key in ("net_temps", "io_temps"):
+        assert np.abs(out[key][-1] - tight[key][-1]).max() <= 5e-5 * np.abs(tight[key][-1]).max()
+    raw = Row3Oracle(spec)
+    raw.jac_films, raw.jac_parts = [], set()
+    bad = raw.integrate(t0, t1, 1e-5, 1e-8)
+    assert np.abs(bad["net_temps"][-1] - tight["net_temps"][-1]).max() > 5e-4 * np.abs(tight["net_temps"][-1]).max()

@@ -33,12 +33,14 @@ class FfeDesc(C.Structure):
                 ("tdep", i32), ("condy_tab", i32), ("volcapy_tab", i32), ("ts_nrows", i32),
                 ("ts_row", vp), ("ts_start", vp), ("ts_surf", vp), ("ts_qval", vp),
                 ("ts_fstart", vp), ("ts_film", vp), ("ts_adata", vp),
-                ("j_nslices", i32), ("j_slice_ptr", vp), ("j_col", vp), ("j_val", vp), ("j_mass", vp), ("j_adiag", vp)]
+                ("j_nslices", i32), ("j_slice_ptr", vp), ("j_col", vp), ("j_val", vp), ("j_mass", vp), ("j_adiag", vp),
+                ("fd_rhs", i32)]
 
 
 class LpDesc(C.Structure):
     _fields_ = [("n", i32), ("nslices", i32), ("y_off", i64), ("slice_ptr_ioff64", i32), ("col_ioff", i32),
-                ("val_doff", i32), ("b_doff", i32), ("mass_doff", i32), ("adiag_doff", i32)]
+                ("val_doff", i32), ("b_doff", i32), ("mass_doff", i32), ("adiag_doff", i32),
+                ("F", i32), ("lfm_doff", i32), ("minv_doff", i32)]
 
 
 class MorDesc(C.Structure):
@@ -56,6 +58,7 @@ EXPORTS = {
     "tc_add_lp_part": (i32, [vp, C.POINTER(LpDesc)]),
     "tc_add_mor_part": (i32, [vp, C.POINTER(MorDesc)]),
     "tc_finalize": (i32, [vp, i64]),
+    "tc_set_jac_films": (i32, [vp, i32, vp]),
     "tc_rhs": (i32, [vp, f64, vp, vp]),
     "tc_set_state": (i32, [vp, vp]),
     "tc_get_state": (i32, [vp, vp]),

@@ -20,7 +20,7 @@
 enum TcCmd {
     C_END = 0, C_SET_TU, C_SURF_MEAN, C_INPUTS, C_MATL_GROUP, C_CAPY, C_FLOW_CONST, C_FLOW_FUNC,
     C_FILM_FUNC, C_HEAT_FUNC, C_FLUX_FUNC, C_BOUND_FUNC, C_PART_FILMS, C_LP_UPDATE, C_LP2LP,
-    C_LP_LEAK, C_STAT, C_DIAG, C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D, C_LP_TDEP, C_FUNCS
+    C_LP_LEAK, C_STAT, C_DIAG, C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D, C_LP_TDEP, C_FUNCS, C_JTHETA
 };
 
 struct TcNetParams {
@@ -351,6 +351,27 @@ tc_network_kernel(TcNetParams P, const double* __restrict__ ctrl, double c_stage
             for (int k = tid; k < a[18]; k += nt) D[a[22] + sp[k]] = __dmul_rn(D[a[11] + abr[k]], Ld[fl[k]]);
             for (int i = tid; i < dof; i += nt) D[a[23] + i] = __dmul_rn(D[a[11] + i], Ld[dg[i]]);
             (void)n_rows;
+        } break;
+        case C_JTHETA: {
+            // For the Jacobian of the implicit W-methods only (tc_set_jac_films; the right-hand side is untouched):
+            // film f of a part leads to the stationary node n = link[f].  T_n = (q_n + sum_k g_k T_k) / G
+            // (C_STAT above), so dT_n / dT_surface = theta = g_f / G with g_f the entry of the part's surface
+            // node in row n and G the row sum.  A node that only carries a heat source (the reference's idiom
+            // for a prescribed surface heat flow) has theta = 1: the flux does not depend on the surface.
+            // a: F, theta_doff, link_ioff, surfnode_ioff, statflag_ioff
+            const int *lk = I + a[2], *sn = I + a[3], *sf = I + a[4];
+            for (int f = tid; f < a[0]; f += nt) {
+                double theta = 0.0;
+                if (sf[f]) {
+                    double G = 0.0, g = 0.0;
+                    for (int j = indptr[lk[f]]; j < indptr[lk[f] + 1]; ++j) {
+                        G = __dadd_rn(G, cond[j]);
+                        if (indices[j] == sn[f]) g = __dadd_rn(g, cond[j]);
+                    }
+                    if (G > 0.0) theta = __ddiv_rn(g, G);
+                }
+                D[a[1] + f] = theta;
+            }
         } break;
         case C_COPY_D: {                // n, src_doff, dst_doff
             for (int i = tid; i < a[0]; i += nt) D[a[2] + i] = D[a[1] + i];

@@ -275,9 +275,11 @@ struct FfePart {
     double bj_shift = 0.0;             // the shift they were built for
     tc_dist* dist = nullptr;           // row-partitioned body (tc_attach_dist): this part holds the LOCAL rows only
     int job0 = 0, njobs = 0;           // its surface-mean jobs
+    bool has_jac = false;              // a film leads to a stationary node (tc_set_jac_films): always implicit in the W-methods
 };
-struct LpPart { tc_lp_desc d; TcSell A; const double* b; double *r, *p, *q, *dinv; TcPcg pcg; };
-struct MorPart { tc_mor_desc d; TcMor M; };
+struct LpPart { tc_lp_desc d; TcSell A; const double* b; double *r, *p, *q, *dinv; TcPcg pcg; bool has_jac = false; };
+struct MorPart { tc_mor_desc d; TcMor M; bool has_jac = false; };
+#define TC_JAC_MAX 4
 
 struct tc_solver {
     cudaStream_t stream = nullptr;
@@ -321,6 +323,13 @@ struct tc_solver {
     double pcg_rtol = 1e-10; int pcg_maxit = 1000; int pcg_mode = TC_PCG_COOP; int coop_grid = 0;
     double ros_gamma = 1.0 + 0.70710678118654752440;
     bool has_dist = false;             // a part is row-partitioned (tc_attach_dist)
+    // rank-one Jacobian terms of films that lead to stationary nodes (tc_set_jac_films)
+    int jac_n = 0;
+    int jac_rec[TC_JAC_MAX][8] = {};
+    double* jac_Y[TC_JAC_MAX] = {nullptr, nullptr, nullptr, nullptr};   // B^-1 u_j (state length)
+    double* jac_U = nullptr;           // u_j (state length)
+    double* jac_part = nullptr;        // (TC_JAC_MAX + 1) x mean_grid partial sums of c^T Y_j and c^T z
+    double* jac_ginv = nullptr;        // (I - s C^T Y)^-1, K x K
 };
 
 static int grid_for(long long n, int threads, int cap) {
@@ -366,6 +375,8 @@ extern "C" int tc_destroy(tc_handle s) {
     cudaFree(s->bar.ctr); cudaFree(s->bar.part); cudaFree(s->bar.res);
     cudaFree(s->y); cudaFree(s->ynew); cudaFree(s->ystage);
     for (int i = 0; i < 7; ++i) cudaFree(s->K[i]);
+    for (int j = 0; j < TC_JAC_MAX; ++j) cudaFree(s->jac_Y[j]);
+    cudaFree(s->jac_U); cudaFree(s->jac_part); cudaFree(s->jac_ginv);
     cudaFree(s->net_vec); cudaFree(s->gate_flags); cudaFree(s->gate_partial); cudaFree(s->gate_counter);
     for (auto& p : s->ffe) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
     for (auto& p : s->lp) { cudaFree(p.r); cudaFree(p.p); cudaFree(p.q); cudaFree(p.dinv); }
@@ -489,7 +500,7 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
             }
             continue;
         }
-        if (p.fdiag.nrows > 0)
+        if (p.fdiag.nrows > 0 && p.d.fd_rhs)
             tc_ffe_film_diag_kernel<<<grid_for(p.fdiag.nrows, 256, s->sm_count * 4), 256, 0, st>>>(
                 p.fdiag, s->net.darena + p.d.films_doff, p.d.val, p.d.adiag, done);
         if (p.dist) {
@@ -519,7 +530,7 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
     s->nfev += 1;
     s->launches += (s->mean_grid > 0 ? 1 : 0) + 1 + (long long)s->lp.size() + (long long)s->mor.size();
     for (auto& p : s->ffe)
-        s->launches += p.d.tdep ? 1 + (p.d.ts_nrows > 0 ? 1 : 0) : 1 + (p.fdiag.nrows > 0 ? 1 : 0) + (p.load.nrows > 0 ? 1 : 0);
+        s->launches += p.d.tdep ? 1 + (p.d.ts_nrows > 0 ? 1 : 0) : 1 + (p.fdiag.nrows > 0 && p.d.fd_rhs ? 1 : 0) + (p.load.nrows > 0 ? 1 : 0);
     return 0;
 }
 
@@ -1091,8 +1102,8 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
     if (w_method)
         for (auto& p : s->mor) {
             tc_mor_block_solve_kernel<<<p.M.S, 256, sizeof(double) * 5 * p.M.r, st>>>(
-                p.M, s->net.darena + p.d.films_doff, s->ctrl, coef, s->w_bound, rhs + p.d.y_off, z + p.d.y_off, 1e-12,
-                done);
+                p.M, s->net.darena + p.d.films_doff, s->ctrl, coef, p.has_jac ? 0.0 : s->w_bound, rhs + p.d.y_off,
+                z + p.d.y_off, 1e-12, done);
         }
     // LP parts: same SPD structure (M A = L_body + film/margin diagonal, thermca/lpm/lp_io.py:106-128)
     for (auto& p : s->lp) {
@@ -1105,7 +1116,7 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         P.prof = nullptr;
         P.skip = nullptr;
         P.bar = s->bar;
-        if (w_method && s->pcg_mode == TC_PCG_COOP) {
+        if (w_method && s->pcg_mode == TC_PCG_COOP && !p.has_jac) {
             int* flag = s->gate_flags + gate_ix++;
             tc_pcg_gate_kernel<<<grid_for(p.d.n, 256, 256), 256, 0, st>>>(p.d.n, P.adiag, s->ctrl, coef, s->w_bound,
                                                                           s->gate_partial, s->gate_counter, flag, done);
@@ -1126,7 +1137,7 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         P.prof = s->timing ? s->pcg_prof : nullptr;
         P.skip = nullptr;
         P.bar = s->bar;
-        if (w_method && s->pcg_mode == TC_PCG_COOP) {
+        if (w_method && s->pcg_mode == TC_PCG_COOP && !p.has_jac) {
             int* flag = s->gate_flags + gate_ix++;
             tc_pcg_gate_kernel<<<grid_for(p.d.n, 256, 256), 256, 0, st>>>(p.d.n, P.adiag, s->ctrl, coef, s->w_bound,
                                                                           s->gate_partial, s->gate_counter, flag, done);
@@ -1139,6 +1150,179 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
             return -1;
         }
     }
+    return 0;
+}
+
+// ---- rank-one Jacobian terms of films that lead to stationary nodes (tc_set_jac_films) ------------------------------
+// W = B - s sum_j u_j c_j^T with B = blockdiag(I + s A_p) (what enqueue_block_solve inverts), u_j the load vector of
+// film j times theta_j (network.cuh C_JTHETA), c_j the surface-mean weights of the film's surface.  Woodbury:
+//   W^-1 r = z + Y (I - s C^T Y)^-1 s C^T z,   z = B^-1 r,   Y = B^-1 U.
+// Y and the K x K inverse are formed once per attempt (enqueue_jac_prepare); every block solve of the attempt is
+// followed by the correction (enqueue_jac_correct).  c^T x is the surface-mean kernel of the right-hand side applied
+// to x.  CPU restatement: oracle/ros2_oracle.py _jac_prepare.
+struct TcJacRanges { int K; int first[TC_JAC_MAX]; int nblk[TC_JAC_MAX]; };
+struct TcJacY { const double* p[TC_JAC_MAX]; };
+__global__ void tc_jac_u_lp_kernel(int dof, int F, int f, const double* __restrict__ lfm, const double* __restrict__ minv,
+                                   const double* __restrict__ theta, double* __restrict__ U,
+                                   const int* __restrict__ done) {
+    if (done && *done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dof; i += gridDim.x * blockDim.x)
+        U[i] = theta[0] * minv[i] * lfm[i * F + f];
+}
+__global__ void tc_jac_u_ffe_kernel(TcFilmDiag Fd, int f, const double* __restrict__ theta, const double* __restrict__ film,
+                                    double* __restrict__ U, const int* __restrict__ done) {
+    if (done && *done) return;
+    const double tf = theta[0] * film[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Fd.nrows; i += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int k = Fd.start[i]; k < Fd.start[i + 1]; ++k)
+            if (Fd.film[k] == f) acc += tf * Fd.adata[k];
+        U[Fd.row[i]] = acc;
+    }
+}
+__global__ void tc_jac_u_vec_kernel(int n, const double* __restrict__ v, const double* __restrict__ theta,
+                                    const double* __restrict__ film, double* __restrict__ U, const int* __restrict__ done) {
+    if (done && *done) return;
+    const double tf = theta[0] * film[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) U[i] = tf * v[i];
+}
+__global__ void tc_jac_gram_kernel(TcJacRanges R, const double* __restrict__ partY, int stride, const double* __restrict__ ctrl,
+                                   double coef, double* __restrict__ ginv, const int* __restrict__ done) {
+    if (done && *done) return;
+    if (threadIdx.x != 0) return;
+    const int K = R.K;
+    const double sft = coef * ctrl[CT_H];
+    double G[TC_JAC_MAX][2 * TC_JAC_MAX];
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+            double cy = 0.0;
+            for (int b = 0; b < R.nblk[i]; ++b) cy += partY[(size_t)j * stride + R.first[i] + b];
+            G[i][j] = (i == j ? 1.0 : 0.0) - sft * cy;
+            G[i][K + j] = i == j ? 1.0 : 0.0;
+        }
+    for (int c = 0; c < K; ++c) {                       // Gauss-Jordan with partial pivoting
+        int piv = c;
+        for (int i = c + 1; i < K; ++i) if (fabs(G[i][c]) > fabs(G[piv][c])) piv = i;
+        for (int j = 0; j < 2 * K; ++j) { const double t = G[c][j]; G[c][j] = G[piv][j]; G[piv][j] = t; }
+        const double d = 1.0 / G[c][c];
+        for (int j = 0; j < 2 * K; ++j) G[c][j] *= d;
+        for (int i = 0; i < K; ++i) {
+            if (i == c) continue;
+            const double m = G[i][c];
+            for (int j = 0; j < 2 * K; ++j) G[i][j] -= m * G[c][j];
+        }
+    }
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) ginv[i * K + j] = G[i][K + j];
+}
+__global__ void tc_jac_apply_kernel(long long n, double* __restrict__ z, TcJacY Y, TcJacRanges R,
+                                    const double* __restrict__ partZ, const double* __restrict__ ginv,
+                                    const double* __restrict__ ctrl, double coef, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double m[TC_JAC_MAX];
+    const int K = R.K;
+    if (threadIdx.x == 0) {
+        const double sft = coef * ctrl[CT_H];
+        double t[TC_JAC_MAX];
+        for (int i = 0; i < K; ++i) {
+            double a = 0.0;
+            for (int b = 0; b < R.nblk[i]; ++b) a += partZ[R.first[i] + b];
+            t[i] = sft * a;
+        }
+        for (int i = 0; i < K; ++i) {
+            double a = 0.0;
+            for (int j = 0; j < K; ++j) a += ginv[i * K + j] * t[j];
+            m[i] = a;
+        }
+    }
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = z[i];
+        for (int j = 0; j < K; ++j) v += m[j] * Y.p[j][i];
+        z[i] = v;
+    }
+}
+
+static TcJacRanges jac_ranges(const tc_solver* s) {
+    TcJacRanges R{};
+    R.K = s->jac_n;
+    for (int j = 0; j < s->jac_n; ++j) { R.first[j] = s->jac_rec[j][6]; R.nblk[j] = s->jac_rec[j][7]; }
+    return R;
+}
+
+static int enqueue_jac_prepare(tc_solver* s, double coef) {
+    if (s->jac_n == 0) return 0;
+    cudaStream_t st = s->stream;
+    const int* done = s->flags + FL_DONE;
+    double* D = s->net.darena;
+    for (int j = 0; j < s->jac_n; ++j) {
+        const int* q = s->jac_rec[j];       // kind, part, film, surface, theta_doff, film_doff, first_block, nblk
+        TC_CUDA(cudaMemsetAsync(s->jac_U, 0, sizeof(double) * (size_t)s->n_state, st));
+        if (q[0] == 0) {
+            LpPart& p = s->lp[q[1]];
+            tc_jac_u_lp_kernel<<<grid_for(p.d.n, 256, 64), 256, 0, st>>>(p.d.n, p.d.F, q[2], D + p.d.lfm_doff, D + p.d.minv_doff,
+                                                                         D + q[4], s->jac_U + p.d.y_off, done);
+        } else if (q[0] == 1) {
+            FfePart& p = s->ffe[q[1]];
+            tc_jac_u_ffe_kernel<<<grid_for(p.fdiag.nrows, 256, s->sm_count * 4), 256, 0, st>>>(
+                p.fdiag, q[2], D + q[4], D + q[5], s->jac_U + p.d.y_off, done);
+        } else {
+            MorPart& p = s->mor[q[1]];
+            tc_jac_u_vec_kernel<<<grid_for(p.M.r, 256, 8), 256, 0, st>>>(
+                p.M.r, p.M.B_T + (size_t)q[3] * p.M.r, D + q[4], D + q[5], s->jac_U + p.d.y_off + (size_t)q[3] * p.M.r, done);
+        }
+        if (enqueue_block_solve(s, coef, s->jac_U, s->jac_Y[j], true)) return -1;
+        tc_surf_mean_kernel<<<s->mean_grid, TC_MEAN_THREADS, 0, st>>>(s->jobs, s->jac_Y[j],
+                                                                      s->jac_part + (size_t)j * s->mean_grid, done);
+    }
+    tc_jac_gram_kernel<<<1, 32, 0, st>>>(jac_ranges(s), s->jac_part, s->mean_grid, s->ctrl, coef, s->jac_ginv, done);
+    return 0;
+}
+
+// z = B^-1 r  ->  z = W^-1 r
+static int enqueue_jac_correct(tc_solver* s, double coef, double* z) {
+    if (s->jac_n == 0) return 0;
+    cudaStream_t st = s->stream;
+    const int* done = s->flags + FL_DONE;
+    double* partZ = s->jac_part + (size_t)TC_JAC_MAX * s->mean_grid;
+    tc_surf_mean_kernel<<<s->mean_grid, TC_MEAN_THREADS, 0, st>>>(s->jobs, z, partZ, done);
+    TcJacY Y{};
+    for (int j = 0; j < s->jac_n; ++j) Y.p[j] = s->jac_Y[j];
+    tc_jac_apply_kernel<<<s->vec_grid, 256, 0, st>>>(s->n_state, z, Y, jac_ranges(s), partZ, s->jac_ginv, s->ctrl, coef, done);
+    return 0;
+}
+
+extern "C" int tc_set_jac_films(tc_handle s, int32_t n, const int32_t* rec) {
+    TC_CHECK(s && s->finalized, "solver not finalized");
+    TC_CHECK(n >= 0 && n <= TC_JAC_MAX, "at most 4 films between part surfaces and stationary nodes are supported");
+    TC_CHECK(n == 0 || s->mean_grid > 0, "no surface-mean jobs");
+    for (int j = 0; j < n; ++j) {
+        const int32_t* q = rec + 8 * j;
+        for (int k = 0; k < 8; ++k) s->jac_rec[j][k] = q[k];
+        if (q[0] == 0) {
+            TC_CHECK(q[1] >= 0 && q[1] < (int)s->lp.size() && q[2] >= 0 && q[2] < s->lp[q[1]].d.F, "LP film index");
+            s->lp[q[1]].has_jac = true;
+        } else if (q[0] == 1) {
+            TC_CHECK(q[1] >= 0 && q[1] < (int)s->ffe.size(), "FE part index");
+            FfePart& p = s->ffe[q[1]];
+            TC_CHECK(p.fdiag.nrows > 0 && !p.d.tdep && !p.dist, "FE part without film lists (fd_*), temperature dependent "
+                                                                "or row-partitioned");
+            p.has_jac = true;
+        } else {
+            TC_CHECK(q[0] == 2 && q[1] >= 0 && q[1] < (int)s->mor.size() && q[3] >= 0 && q[3] < s->mor[q[1]].M.S,
+                     "MOR film index");
+            s->mor[q[1]].has_jac = true;
+        }
+        TC_CHECK(q[6] >= 0 && q[7] >= 1 && q[6] + q[7] <= s->mean_grid, "mean job range");
+    }
+    if (n > 0 && !s->jac_U) {
+        const size_t bytes = sizeof(double) * (size_t)(s->n_state > 0 ? s->n_state : 1);
+        TC_CUDA(cudaMalloc(&s->jac_U, bytes));
+        for (int j = 0; j < TC_JAC_MAX; ++j) TC_CUDA(cudaMalloc(&s->jac_Y[j], bytes));
+        TC_CUDA(cudaMalloc(&s->jac_part, sizeof(double) * (size_t)(TC_JAC_MAX + 1) * s->mean_grid));
+        TC_CUDA(cudaMalloc(&s->jac_ginv, sizeof(double) * TC_JAC_MAX * TC_JAC_MAX));
+    }
+    s->jac_n = n;
     return 0;
 }
 
@@ -1243,13 +1427,16 @@ static int enqueue_ros2_attempt(tc_solver* s) {
     const int G = s->vec_grid;
     tc_ros2_reuse_kernel<<<G, 256, 0, st>>>(n, s->K[5], s->K[0], s->flags);        // before prepare clears nothing it needs
     tc_prepare_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
+    if (enqueue_jac_prepare(s, s->ros_gamma)) return -1;
     if (enqueue_block_solve(s, s->ros_gamma, s->K[0], s->K[1], true)) return -1;    // k1
+    if (enqueue_jac_correct(s, s->ros_gamma, s->K[1])) return -1;
     TcLin L1{};
     L1.nk = 1; L1.k[0] = s->K[1]; L1.c[0] = 1.0;
     tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L1, s->ctrl, s->ystage, done);       // y + h k1
     if (enqueue_rhs(s, 1.0, s->ystage, s->K[2])) return -1;
     tc_axpby_kernel<<<G, 256, 0, st>>>(n, s->K[2], -2.0, s->K[1], s->K[3], done);  // f2 - 2 k1
     if (enqueue_block_solve(s, s->ros_gamma, s->K[3], s->K[4], true)) return -1;    // k2
+    if (enqueue_jac_correct(s, s->ros_gamma, s->K[4])) return -1;
     TcLin L2{};
     L2.nk = 2; L2.k[0] = s->K[1]; L2.c[0] = 1.5; L2.k[1] = s->K[4]; L2.c[1] = 0.5;
     tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L2, s->ctrl, s->ynew, done);
@@ -1337,11 +1524,13 @@ static int enqueue_row3_attempt(tc_solver* s) {
     double* u4 = s->K[2];                          // F_3 is consumed before u_4 is written
     tc_ros2_reuse_kernel<<<G, 256, 0, st>>>(n, fend, F1, s->flags);
     tc_prepare_kernel<<<1, 1, 0, st>>>(s->ctrl, s->flags);
+    if (enqueue_jac_prepare(s, g)) return -1;
     TcLin L{};
     // stage 1
     L.nk = 0;
     tc_stage_rhs_kernel<<<G, 256, 0, st>>>(n, F1, L, g, rhs, done);
     if (enqueue_block_solve(s, g, rhs, u1, true)) return -1;
+    if (enqueue_jac_correct(s, g, u1)) return -1;
     // stage 2
     L.nk = 1; L.k[0] = u1; L.c[0] = 1.1021597568860195;
     tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L, s->ctrl, s->ystage, done);
@@ -1349,6 +1538,7 @@ static int enqueue_row3_attempt(tc_solver* s) {
     L.c[0] = -3.3064792706580586;
     tc_stage_rhs_kernel<<<G, 256, 0, st>>>(n, Fs, L, g, rhs, done);
     if (enqueue_block_solve(s, g, rhs, u2, true)) return -1;
+    if (enqueue_jac_correct(s, g, u2)) return -1;
     // stage 3
     L.nk = 2; L.k[0] = u1; L.c[0] = 2.0458152611220233; L.k[1] = u2; L.c[1] = 1.1251523859013772;
     tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L, s->ctrl, s->ystage, done);
@@ -1356,11 +1546,13 @@ static int enqueue_row3_attempt(tc_solver* s) {
     L.c[0] = -3.1394810593440803; L.c[1] = -2.5814150212946312;
     tc_stage_rhs_kernel<<<G, 256, 0, st>>>(n, Fs, L, g, rhs, done);
     if (enqueue_block_solve(s, g, rhs, u3, true)) return -1;
+    if (enqueue_jac_correct(s, g, u3)) return -1;
     // stage 4 (same right-hand side F_3)
     L.nk = 3; L.k[0] = u1; L.c[0] = -4.6371650178370949; L.k[1] = u2; L.c[1] = -3.1668182208148394;
     L.k[2] = u3; L.c[2] = -2.0579924311095659;
     tc_stage_rhs_kernel<<<G, 256, 0, st>>>(n, Fs, L, g, rhs, done);
     if (enqueue_block_solve(s, g, rhs, u4, true)) return -1;
+    if (enqueue_jac_correct(s, g, u4)) return -1;
     // new state, f(t + h, y+), error estimate, accept / reject, snapshot
     TcLin Ly{};
     Ly.nk = 4; Ly.k[0] = u1; Ly.k[1] = u2; Ly.k[2] = u3; Ly.k[3] = u4;

@@ -18,7 +18,7 @@ from .spec import state_offsets
 # command opcodes, keep in sync with csrc/network.cuh
 (C_END, C_SET_TU, C_SURF_MEAN, C_INPUTS, C_MATL_GROUP, C_CAPY, C_FLOW_CONST, C_FLOW_FUNC, C_FILM_FUNC,
  C_HEAT_FUNC, C_FLUX_FUNC, C_BOUND_FUNC, C_PART_FILMS, C_LP_UPDATE, C_LP2LP, C_LP_LEAK, C_STAT, C_DIAG,
- C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D, C_LP_TDEP, C_FUNCS) = range(24)
+ C_NET_DERIV, C_PART_FLUX, C_LP_LOAD, C_COPY_D, C_LP_TDEP, C_FUNCS, C_JTHETA) = range(25)
 
 MEAN_ENTRIES_PER_BLOCK = 4096
 MEAN_MAX_BLOCKS_PER_JOB = 64
@@ -213,15 +213,18 @@ class DeviceSolver:
 
         # ---- surface-mean jobs (thermca/solver.py:211-220) -----------------------------------
         jobs = []          # (entry idx array, weights, target net idx, ref_doff)
+        job_of = {}        # (kind, part, surface) -> job index
         for k, p in enumerate(s["lp"]):
             Cm = np.asarray(p["C_marg"])
             for sidx, tgt in enumerate(p["surf_net_idxs"]):
                 nz = np.nonzero(Cm[:, sidx])[0]
+                job_of[(0, k, sidx)] = len(jobs)
                 jobs.append((nz + self.lp_off[k], Cm[nz, sidx], int(tgt), -1))
         self._ffe_job_range = []           # (first job, number of jobs) of every FE part: tc_attach_dist
         for k, p in enumerate(s["ffe"]):
             self._ffe_job_range.append((len(jobs), len(p["surf_net_idxs"])))
             for sidx, tgt in enumerate(p["surf_net_idxs"]):
+                job_of[(1, k, sidx)] = len(jobs)
                 jobs.append((np.asarray(p["C_idx"][sidx]) + self.ffe_off[k], p["C_val"][sidx], int(tgt), -1))
         self._mor_dev = []
         for k, p in enumerate(s["mor"]):
@@ -229,6 +232,7 @@ class DeviceSolver:
             ref_doff = A.add_d([float(p["ref_temp"])])
             Cs = np.asarray(p["C_surfs"]).reshape(S * r, S)
             for sidx, tgt in enumerate(p["surf_net_idxs"]):
+                job_of[(2, k, sidx)] = len(jobs)
                 jobs.append((np.arange(S * r) + self.mor_off[k], Cs[:, sidx], int(tgt), ref_doff))
             self._mor_dev.append({"ref_doff": ref_doff})
         job_of_block, first_block, nblk, ent_start = [], [], [], [0]
@@ -338,6 +342,29 @@ class DeviceSolver:
                                      "link": A.add_i(p["link_elem_net_idxs"] if F else [0]),
                                      "dock": A.add_d(p["dock_areas"] if F else np.zeros(1)), "F": F, "S": S})
 
+        # ---- films between part surfaces and stationary nodes: rank-one terms of the W-method Jacobian
+        #      (csrc/network.cuh C_JTHETA, csrc/solver.cu tc_set_jac_films); the right-hand side does not use them ----
+        stat_nodes = set(int(i) for i in s["stat_idx"])
+        self._jac_films = []
+        for kind, (parts, devs) in enumerate(((s["lp"], lp_dev), (s["ffe"], ffe_dev), (s["mor"], self._mor_dev))):
+            for k, (p, d) in enumerate(zip(parts, devs)):
+                F = d["F"]
+                flags = [1 if int(n) in stat_nodes else 0 for n in p["link_elem_net_idxs"]] if F else []
+                d["jac_on"] = bool(any(flags)) and not (kind == 1 and (p.get("tdep") is not None or "sell" in p))
+                if not d["jac_on"]:
+                    continue
+                fsurf = np.asarray(p["film_surf_idxs"], dtype=np.int64)
+                d["theta"] = A.add_d(np.zeros(F))
+                d["statflag"] = A.add_i(flags)
+                d["surfnode"] = A.add_i(np.asarray(p["surf_net_idxs"])[fsurf])
+                for f in range(F):
+                    if flags[f]:
+                        j = job_of[(kind, k, int(fsurf[f]))]
+                        self._jac_films.append([kind, k, f, int(fsurf[f]), d["theta"] + f, d["films"] + f,
+                                                first_block[j], nblk[j]])
+        if len(self._jac_films) > 4:
+            raise NotImplementedError("more than 4 films between part surfaces and stationary nodes")
+
         # ---- films of variable parts (network.py:803-817) -------------------------------------------
         for p, d in list(zip(s["lp"], lp_dev)) + list(zip(s["ffe"], ffe_dev)) + list(zip(s["mor"], self._mor_dev)):
             if p["var_film_rc_idx"] is not None:
@@ -366,6 +393,9 @@ class DeviceSolver:
         # ---- stationary nodes, differential form, network derivative (solver.py:224-255) --------------
         if len(s["stat_idx"]):
             cmd(C_STAT, len(s["stat_idx"]), A.add_i(s["stat_idx"]))
+        for d in lp_dev + ffe_dev + list(self._mor_dev):
+            if d.get("jac_on"):
+                cmd(C_JTHETA, d["F"], d["theta"], d["link"], d["surfnode"], d["statflag"])
         cmd(C_DIAG)
         if u:
             cmd(C_NET_DERIV)
@@ -411,6 +441,7 @@ class DeviceSolver:
             ld.n, ld.nslices, ld.y_off = d["dof"], d["sell"]["nslices"], self.lp_off[k]
             ld.slice_ptr_ioff64, ld.col_ioff, ld.val_doff = d["slice_ptr"], d["col"], d["val"]
             ld.b_doff, ld.mass_doff, ld.adiag_doff = d["b"], d["mass"], d["adiag"]
+            ld.F, ld.lfm_doff, ld.minv_doff = d["F"], d["lfm"], d["minv"]
             _cabi.check(self.lib.tc_add_lp_part(self._handle, C.byref(ld)))
         self.ffe_sell = []
         for k, (p, d) in enumerate(zip(s["ffe"], ffe_dev)):
@@ -425,6 +456,9 @@ class DeviceSolver:
             md.films_doff, md.flux_doff = d["films"], d["flux"]
             _cabi.check(self.lib.tc_add_mor_part(self._handle, C.byref(md)))
         _cabi.check(self.lib.tc_finalize(self._handle, self.n_state))
+        if self._jac_films:
+            rec = np.ascontiguousarray(self._jac_films, dtype=np.int32)
+            _cabi.check(self.lib.tc_set_jac_films(self._handle, len(self._jac_films), rec.ctypes.data_as(C.c_void_p)))
 
     def _add_ffe_tdep(self, k, p, d):
         """Temperature dependent body: ship Lx_base (geometry) + tables; the operator is formed edge
@@ -530,7 +564,8 @@ class DeviceSolver:
         else:
             fd.load_nrows = 0
         # variable films -> diagonal update lists (thermca/fem/ffe_io.py:76-82)
-        if p["var_film_rc_idx"] is not None and len(p["films"]):
+        var_films = p["var_film_rc_idx"] is not None and len(p["films"]) > 0
+        if var_films or d.get("jac_on"):
             if pos is None:
                 raise NotImplementedError("variable films on a device-generated operator")
             cpos = np.concatenate([np.asarray(ix, dtype=np.int64) for ix in p["film_didx"]])
@@ -549,6 +584,7 @@ class DeviceSolver:
         else:
             fd.fd_nrows = 0
         fd.films_doff, fd.flux_doff = d["films"], d["flux"]
+        fd.fd_rhs = int(var_films)
         fd.tdep, fd.ts_nrows = 0, 0
         _cabi.check(self.lib.tc_add_ffe_part(self._handle, C.byref(fd)))
 
