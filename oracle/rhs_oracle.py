@@ -31,9 +31,8 @@ from bisect import bisect_right
 import numpy as np
 import scipy.sparse as sp
 
-from thermca_b200.trace import run_program
-from thermca_b200.spec import state_offsets
-from thermca_b200.lowering import initial_state  # noqa: F401  (re-export for tests)
+from program_oracle import eval_program, state_offsets, initial_state  # noqa: F401  (own evaluator: nothing is
+#                                                     imported from the product package; initial_state re-exported)
 
 
 class OracleRHS:
@@ -83,7 +82,7 @@ class OracleRHS:
     # -- helpers -------------------------------------------------------------------
     def _prog(self, k, args):
         p = self.s["programs"][int(k)]
-        return run_program(p["code"], p["consts"], int(p["result"]), args, self.input_vals, self.tables)
+        return eval_program(p["code"], p["consts"], int(p["result"]), args, self.input_vals, self.tables)
 
     def _interp(self, tab, x):
         xp, fp = self.tables[int(tab)]

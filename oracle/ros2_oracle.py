@@ -19,7 +19,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from rhs_oracle import OracleRHS
-from thermca_b200.lowering import initial_state
+from program_oracle import initial_state
 
 GAMMA = 1.0 + 1.0 / np.sqrt(2.0)
 

@@ -18,7 +18,7 @@ Step control: scipy's RK controller (scipy/integrate/_ivp/rk.py:111-165) with er
 import numpy as np
 
 from ros2_oracle import Ros2Oracle
-from thermca_b200.lowering import initial_state
+from program_oracle import initial_state
 
 GAMMA = 0.435866521508459
 ALPHA = (0.0, 0.48039453938051824, 0.6753387630276377, 0.6753387630276377)

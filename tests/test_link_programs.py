@@ -33,6 +33,22 @@ def test_host_interpreter_reproduces_reference_closures_bit_exactly():
             assert abs(got[0] - KAT[name]) <= 4e-16 * KAT[name]     # from a scalar call (libm pow vs numpy's array pow)
 
 
+def test_oracle_evaluator_is_independent_and_reproduces_reference_closures():
+    """The oracle evaluates link programs with its own table-driven evaluator (oracle/program_oracle.py); it
+    shares only the storage format (opcode numbering) with the product and is pinned against the values of the
+    unmodified reference closures, bit for bit."""
+    import program_oracle
+    from thermca_b200.trace import OPS
+    assert list(program_oracle.OPCODES) == list(OPS)
+    src = open(program_oracle.__file__).read() + open(os.path.join(os.path.dirname(program_oracle.__file__),
+                                                                   "rhs_oracle.py")).read()
+    assert "import thermca_b200" not in src and "from thermca_b200" not in src
+    progs, tables, t0, t1 = _load()
+    for name, code, consts, result, expect in progs:
+        got = program_oracle.eval_program(code, consts, result, [t0, t1], [], tables)
+        assert np.array_equal(got, expect, equal_nan=True), name
+
+
 @pytest.mark.gpu
 def test_device_interpreter_matches_reference_closures():
     import torch
