@@ -145,6 +145,10 @@ int tc_rk_begin(tc_handle h, int32_t method, double t0, double t_end, double rto
 int tc_rk_advance(tc_handle h, int32_t max_attempts, int32_t poll_every);
 int tc_get_info(tc_handle h, int64_t* info8, double* t_now, double* h_next);
 int tc_reset_history(tc_handle h);
+/* Diagnostic: out2[0] = 1 if the explicit attempt graph is instantiated; out2[1] = 2 / 3 if a ROS2 / ROW3w attempt
+ * graph is instantiated, -1 if the runtime refused the capture (attempts are then launched kernel by kernel), 0 if none
+ * has been captured since the last begin. */
+int tc_graph_info(tc_handle h, int32_t* out2);
 
 /* ---- implicit steps: solve (M + c h K) per FE part with Jacobi-PCG (new numerical method;
  *      the reference has no implicit scheme) ------------------------------ */

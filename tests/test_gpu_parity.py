@@ -466,6 +466,37 @@ def test_ros2_matches_cpu_restatement(torch_cuda, golden, name, t1, bound):
         assert out["pcg"]["solves"] > 0
 
 
+@pytest.mark.parametrize("scheme,kind", [("ROS2", 2), ("ROW3", 3)])
+def test_w_method_attempt_graph_is_used_and_changes_nothing(torch_cuda, golden, scheme, kind):
+    """A W-method attempt is replayed as ONE CUDA graph (cooperative PCG launches included); the trajectory is
+    bit-identical to launching the same kernels one by one (TC_W_GRAPH=0), and a second simulation on the same solver
+    re-captures (tolerances and history pointers are baked into the graph)."""
+    from thermca_b200.device import DeviceSolver
+    spec, ex = golden("assembly")
+    t0 = float(ex["sim"]["t0"])
+    runs = {}
+    for mode in ("1", "0"):
+        os.environ["TC_W_GRAPH"] = mode
+        try:
+            dev = DeviceSolver(spec)
+            out = dev.run_ros2(t0, t0 + 20.0, rtol=1e-4, atol=1e-7, scheme=scheme)
+            info = dev.graph_info()
+            if mode == "1":
+                assert info["w"] == kind, info
+                again = dev.run_ros2(t0, t0 + 20.0, rtol=1e-3, atol=1e-6, scheme=scheme)    # other tolerances: new graph
+                assert dev.graph_info()["w"] == kind and again["accepted"] > 0 and np.isfinite(again["net_temps"]).all()
+            else:
+                assert info["w"] == 0, info
+            dev.close()
+        finally:
+            del os.environ["TC_W_GRAPH"]
+        runs[mode] = out
+    a, b = runs["1"], runs["0"]
+    assert (a["accepted"], a["rejected"]) == (b["accepted"], b["rejected"])
+    assert np.array_equal(a["times"], b["times"]) and np.array_equal(a["net_temps"], b["net_temps"])
+    assert np.array_equal(a["io_temps"], b["io_temps"])
+
+
 @pytest.mark.parametrize("name,t1,bound", [("coffeecup", 100.0, 0.5), ("coffeecup", 100.0, 0.0), ("plate_ffe", 30.0, 0.0),
                                            ("plate_mor", 100.0, 0.0), ("assembly", 30.0, 0.5), ("assembly", 30.0, 0.0),
                                            ("plate_ffe_var", 20.0, 0.0), ("tdep_rod", 0.5, 0.5), ("lp_tdep", 0.5, 0.0),

@@ -69,6 +69,7 @@ EXPORTS = {
     "tc_rk_advance": (i32, [vp, i32, i32]),
     "tc_get_info": (i32, [vp, C.POINTER(i64), C.POINTER(f64), C.POINTER(f64)]),
     "tc_reset_history": (i32, [vp]),
+    "tc_graph_info": (i32, [vp, vp]),
     "tc_theta_steps": (i32, [vp, i32, f64, f64, f64, i32, i32]),
     "tc_ros2_begin": (i32, [vp, f64, f64, f64, f64, f64, f64, f64, i32, i32]),
     "tc_ros2_advance": (i32, [vp, i32, i32]),

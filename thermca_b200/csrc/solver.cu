@@ -311,6 +311,12 @@ struct tc_solver {
     // RK
     int method = TC_RK45; int n_stages = 6;
     cudaGraphExec_t rk_graph = nullptr;
+    // one W-method attempt (ROS2 / ROW3w) as a CUDA graph: captured at the first advance after a begin, dropped whenever
+    // something baked into its kernel arguments changes (history, probes, Jacobian terms, preconditioner, tolerances)
+    cudaGraphExec_t w_graph = nullptr;
+    int w_graph_kind = 0;              // 2: ROS2, 3: ROW3w
+    bool w_graph_off = false;          // capture refused by the runtime (or TC_W_GRAPH=0): direct launches
+    long long w_attempt_kernels = 0, w_attempt_nfev = 0;
     long long nfev = 0;            // host-side count of enqueued RHS pipelines (diagnostic)
     long long nfev_base = 0;       // evaluations outside step attempts (initial snapshot, f0, step probe)
     int evals_per_attempt = 0;
@@ -331,6 +337,11 @@ struct tc_solver {
     double* jac_part = nullptr;        // (TC_JAC_MAX + 1) x mean_grid partial sums of c^T Y_j and c^T z
     double* jac_ginv = nullptr;        // (I - s C^T Y)^-1, K x K
 };
+
+static void drop_graphs(tc_solver* s) {
+    if (s->rk_graph) { cudaGraphExecDestroy(s->rk_graph); s->rk_graph = nullptr; }
+    if (s->w_graph) { cudaGraphExecDestroy(s->w_graph); s->w_graph = nullptr; }
+}
 
 static int grid_for(long long n, int threads, int cap) {
     long long g = (n + threads - 1) / threads;
@@ -369,7 +380,7 @@ extern "C" int tc_create(tc_handle* out, void* cuda_stream) {
 
 extern "C" int tc_destroy(tc_handle s) {
     if (!s) return 0;
-    if (s->rk_graph) cudaGraphExecDestroy(s->rk_graph);
+    drop_graphs(s);
     cudaFree(s->ctrl); cudaFree(s->flags); cudaFree(s->red_partial); cudaFree(s->pcg_sc);
     cudaFree(s->pcg_isc); cudaFree(s->pcg_prof); cudaFree(s->mean_partials);
     cudaFree(s->bar.ctr); cudaFree(s->bar.part); cudaFree(s->bar.res);
@@ -575,13 +586,14 @@ extern "C" int tc_set_probes(tc_handle s, const int64_t* probe_idx_dev, int32_t 
     TC_CHECK(n_probe >= 0, "negative probe count");
     s->probe_idx = n_probe > 0 ? (const long long*)probe_idx_dev : nullptr;
     s->n_probe = n_probe > 0 ? n_probe : 0;
+    drop_graphs(s);
     return 0;
 }
 
 extern "C" int tc_set_history(tc_handle s, double* hist_io, double* hist_net, int32_t capacity, int32_t num_skip) {
     TC_CHECK(s, "null");
     s->hist_io = hist_io; s->hist_net = hist_net; s->capacity = capacity; s->num_skip = num_skip;
-    if (s->rk_graph) { cudaGraphExecDestroy(s->rk_graph); s->rk_graph = nullptr; }
+    drop_graphs(s);
     return 0;
 }
 extern "C" int tc_reset_history(tc_handle s) {
@@ -789,6 +801,13 @@ extern "C" int tc_get_info(tc_handle s, int64_t* info8, double* t_now, double* h
     info8[6] = s->pin_flags[FL_RESULT_STEP]; info8[7] = s->launches;
     if (t_now) *t_now = s->pin_ctrl[CT_T];
     if (h_next) *h_next = s->pin_ctrl[CT_HABS];
+    return 0;
+}
+
+extern "C" int tc_graph_info(tc_handle s, int32_t* out2) {
+    TC_CHECK(s && out2, "null");
+    out2[0] = s->rk_graph ? 1 : 0;
+    out2[1] = s->w_graph ? s->w_graph_kind : (s->w_graph_off ? -1 : 0);
     return 0;
 }
 
@@ -1296,6 +1315,7 @@ extern "C" int tc_set_jac_films(tc_handle s, int32_t n, const int32_t* rec) {
     TC_CHECK(s && s->finalized, "solver not finalized");
     TC_CHECK(n >= 0 && n <= TC_JAC_MAX, "at most 4 films between part surfaces and stationary nodes are supported");
     TC_CHECK(n == 0 || s->mean_grid > 0, "no surface-mean jobs");
+    drop_graphs(s);
     for (int j = 0; j < n; ++j) {
         const int32_t* q = rec + 8 * j;
         for (int k = 0; k < 8; ++k) s->jac_rec[j][k] = q[k];
@@ -1332,6 +1352,7 @@ extern "C" int tc_set_block_precond(tc_handle s, int32_t part, const float* binv
     TC_CHECK(s && part >= 0 && part < (int)s->ffe.size(), "part index");
     s->ffe[part].binv = binv_dev;
     s->ffe[part].bj_shift = shift;
+    drop_graphs(s);
     return 0;
 }
 
@@ -1389,6 +1410,7 @@ extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, 
         TC_CHECK(p.M.r <= 1024, "a MOR block with r > 1024 cannot be solved implicitly (its CG vectors do not fit shared "
                                 "memory); use an explicit pair for this model");
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
+    drop_graphs(s);
     s->w_bound = TC_W_EXPLICIT_BOUND;
     if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);
     if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / 2.0)) return -1;
@@ -1452,20 +1474,56 @@ static int enqueue_ros2_attempt(tc_solver* s) {
     return 0;
 }
 
-extern "C" int tc_ros2_advance(tc_handle s, int32_t max_attempts, int32_t poll_every) {
+// W-method attempts are launch bound on small models (ROS2: ~25, ROW3w: ~45 kernels of a few microseconds each, several
+// of them cooperative launches): one attempt is captured once per begin and replayed as a CUDA graph.  Not captured:
+// the phase-per-launch PCG mode (it polls a device flag from the host), PCG timing (events per launch), and runtimes
+// that refuse a cooperative launch inside a capture - those fall back to direct launches, same kernels, same order.
+static int w_advance(tc_solver* s, int kind, int (*enqueue)(tc_solver*), int max_attempts, int poll_every) {
     TC_CHECK(s && s->finalized, "solver not finalized");
+    cudaStream_t st = s->stream;
     if (poll_every <= 0) poll_every = 4;
+    bool use_graph = !s->w_graph_off && !s->timing && s->pcg_mode != TC_PCG_MULTI;
+    if (const char* e = getenv("TC_W_GRAPH")) use_graph = use_graph && atoi(e) != 0;   // A/B switch (scripts, tests)
+    if (use_graph && s->w_graph && s->w_graph_kind != kind) { cudaGraphExecDestroy(s->w_graph); s->w_graph = nullptr; }
+    if (use_graph && !s->w_graph) {
+        cudaGraph_t graph = nullptr;
+        const long long nfev0 = s->nfev, l0 = s->launches;
+        TC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue(s);
+        const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+        s->w_attempt_nfev = s->nfev - nfev0; s->w_attempt_kernels = s->launches - l0;
+        s->nfev = nfev0; s->launches = l0;
+        cudaError_t ei = cudaErrorUnknown;
+        if (rc == 0 && ec == cudaSuccess && graph) ei = cudaGraphInstantiate(&s->w_graph, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) {
+            cudaGetLastError();                                 // capture refused: nothing ran, fall back for good
+            s->w_graph = nullptr; s->w_graph_off = true; use_graph = false;
+        } else {
+            s->w_graph_kind = kind;
+        }
+    }
     int launched = 0;
     while (launched < max_attempts) {
         int burst = poll_every < max_attempts - launched ? poll_every : max_attempts - launched;
-        for (int i = 0; i < burst; ++i)
-            if (enqueue_ros2_attempt(s)) return -1;
+        for (int i = 0; i < burst; ++i) {
+            if (use_graph) {
+                TC_CUDA(cudaGraphLaunch(s->w_graph, st));
+                s->nfev += s->w_attempt_nfev; s->launches += s->w_attempt_kernels;
+            } else if (enqueue(s)) {
+                return -1;
+            }
+        }
         launched += burst;
         if (fetch_flags(s)) return -1;
         if (s->pin_flags[FL_DONE]) break;
     }
     TC_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int tc_ros2_advance(tc_handle s, int32_t max_attempts, int32_t poll_every) {
+    return w_advance(s, 2, enqueue_ros2_attempt, max_attempts, poll_every);
 }
 
 // ---- third-order W-method "ROW3w" (4 stages, 3 right-hand sides; derivation: DESIGN.md section 3, CPU restatement:
@@ -1495,6 +1553,7 @@ extern "C" int tc_row3_begin(tc_handle s, double t0, double t_end, double rtol, 
         TC_CHECK(p.M.r <= 1024, "a MOR block with r > 1024 cannot be solved implicitly (its CG vectors do not fit shared "
                                 "memory); use an explicit pair for this model");
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
+    drop_graphs(s);
     s->w_bound = TC_ROW3_BOUND;
     if (const char* e = getenv("TC_W_EXPLICIT_BOUND")) s->w_bound = atof(e);
     if (begin_common(s, t0, t_end, rtol, atol, max_step, -1.0 / 3.0)) return -1;
@@ -1569,19 +1628,7 @@ static int enqueue_row3_attempt(tc_solver* s) {
 }
 
 extern "C" int tc_row3_advance(tc_handle s, int32_t max_attempts, int32_t poll_every) {
-    TC_CHECK(s && s->finalized, "solver not finalized");
-    if (poll_every <= 0) poll_every = 4;
-    int launched = 0;
-    while (launched < max_attempts) {
-        int burst = poll_every < max_attempts - launched ? poll_every : max_attempts - launched;
-        for (int i = 0; i < burst; ++i)
-            if (enqueue_row3_attempt(s)) return -1;
-        launched += burst;
-        if (fetch_flags(s)) return -1;
-        if (s->pin_flags[FL_DONE]) break;
-    }
-    TC_CUDA(cudaGetLastError());
-    return 0;
+    return w_advance(s, 3, enqueue_row3_attempt, max_attempts, poll_every);
 }
 
 extern "C" int tc_timing(tc_handle s, int32_t enable, double* pcg_ms, int64_t* pcg_launches, int64_t* launches) {

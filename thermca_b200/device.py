@@ -667,6 +667,12 @@ class DeviceSolver:
                 "stored": int(info[4]), "nfev": int(info[5]), "result_step": int(info[6]), "t": t.value,
                 "h_next": h.value}
 
+    def graph_info(self):
+        """Which attempt graphs are instantiated: ``{"rk": bool, "w": 0 | 2 (ROS2) | 3 (ROW3w) | -1 (capture refused)}``."""
+        out = (C.c_int32 * 2)()
+        _cabi.check(self.lib.tc_graph_info(self._handle, out))
+        return {"rk": bool(out[0]), "w": int(out[1])}
+
     def _drain(self, out):
         n = self.info()["stored"]
         self.stream.synchronize()
@@ -716,7 +722,7 @@ class DeviceSolver:
         return res
 
     def run_ros2(self, t0, t1, rtol=1e-3, atol=1e-6, num_skip=0, max_step=np.inf, first_step=None,
-                 pcg_rtol=1e-8, pcg_maxit=2000, pcg_mode=0, attempts_per_poll=4, progress=None, scheme="ROS2"):
+                 pcg_rtol=1e-8, pcg_maxit=2000, pcg_mode=0, attempts_per_poll=8, progress=None, scheme="ROS2"):
         """Adaptive linearly implicit W-methods (new methods; FE / LP parts implicit via Jacobi-PCG): ``scheme="ROS2"``
         (2 stages, order 2) or ``"ROW3"`` (4 stages, 3 right-hand sides, order 3 for any Jacobian approximation)."""
         begin, advance = {"ROS2": (self.lib.tc_ros2_begin, self.lib.tc_ros2_advance),
