@@ -245,11 +245,20 @@ int tc_dist_set_state_ptr(tc_dist* d, double* y_local_dev);      /* work on a ca
  * rank order (thermca/solver.py:211-220); partials / first_block / nblk: the job tables of tc_set_network */
 int tc_dist_mean_exchange(tc_dist* d, double* partials_dev, const int32_t* first_block_dev, const int32_t* nblk_dev,
                           int32_t job0, int32_t njobs);
+/* explicit stages of a partitioned body: out = out - A v on the local rows (out holds the load vector b on entry), the
+ * ghost rows of v exchanged by peer stores inside the kernel; done_flag_dev (may be NULL): skip when *flag != 0 */
+int tc_dist_residual(tc_dist* d, const double* v_local_dev, double* out_local_dev, const int32_t* done_flag_dev);
+/* vals[j] <- sum over the ranks (rank order, bit-identical everywhere) for k <= 64 doubles on the device */
+int tc_dist_sum_exchange(tc_dist* d, double* vals_dev, int32_t k, const int32_t* done_flag_dev);
+int32_t tc_dist_rank(tc_dist* d);
 int64_t tc_dist_local_rows(tc_dist* d);
 void* tc_dist_stream(tc_dist* d);
 /* general networks on several GPUs: FE part `part` of solver h holds the LOCAL rows of a row-partitioned body; tc_rhs and
  * tc_theta_steps then add the peers' rows to its surface means and run its product / solve in the fused kernel */
 int tc_attach_dist(tc_handle h, int32_t part, tc_dist* d, int32_t first_job, int32_t n_jobs);
+/* rows of the partitioned body over ALL ranks: lets tc_rk_begin / tc_rk_advance run the adaptive explicit pairs on the
+ * partitioned network (error and initial-step norms are means over the global state, thermca/solver.py:348-390) */
+int tc_set_dist_global_rows(tc_handle h, int64_t n_rows_global);
 int tc_dist_set_state(tc_dist* d, const double* y_local_dev);
 int tc_dist_get_state(tc_dist* d, double* y_local_dev);          /* fails (-3/-4) if a step since the last reset failed */
 int tc_dist_copy_state_async(tc_dist* d, double* y_local_dev, int32_t dir);   /* enqueue only: 0 set, 1 get */

@@ -23,3 +23,18 @@ def test_dist_kernel_world1_matches_single_gpu_solver():
                        text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "dist_check ok" in r.stdout
+
+
+def test_partitioned_rk_world1_matches_single_gpu_run():
+    """The adaptive explicit pairs on a partitioned body (tc_dist_residual, class-split norms, the attempt graph with
+    cooperative launches) through the unmodified reference's Network.sim at world size 1."""
+    if not (os.path.isdir(os.path.join(ROOT, "oracle", "_ref")) or os.path.isdir("/root/reference")):
+        pytest.skip("reference tree not staged")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dropin_partitioned_rk_check.py")], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "dropin_partitioned_rk_check ok" in r.stdout

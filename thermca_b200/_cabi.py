@@ -95,6 +95,10 @@ EXPORTS = {
     "tc_dist_set_state_ptr": (i32, [vp, vp]),
     "tc_dist_mean_exchange": (i32, [vp, vp, vp, vp, i32, i32]),
     "tc_dist_local_rows": (i64, [vp]),
+    "tc_dist_residual": (i32, [vp, vp, vp, vp]),
+    "tc_dist_sum_exchange": (i32, [vp, vp, i32, vp]),
+    "tc_dist_rank": (i32, [vp]),
+    "tc_set_dist_global_rows": (i32, [vp, i64]),
     "tc_dist_stream": (vp, [vp]),
     "tc_attach_dist": (i32, [vp, i32, vp, i32, i32]),
     "tc_dist_set_state": (i32, [vp, vp]),

@@ -679,6 +679,75 @@ extern "C" int tc_dist_mean_exchange(tc_dist* d, double* partials_dev, const int
     tc_dist_mean_exchange_kernel<<<1, 256, 0, d->stream>>>(d->K, partials_dev, first_block_dev, nblk_dev, job0, njobs);
     return 0;
 }
+// ---- explicit stages of a partitioned body (the adaptive pairs RK45 / RK23 under torchrun) ---------------------------
+// f = b - A v on the local rows for ANY stage vector v (thermca/solver.py:281).  The ghost rows of v travel LL encoded
+// as in the fused theta kernel; the two p ghost buffers alternate with the halo sequence number: a rank can run at most
+// one product ahead of a neighbour (its next product needs that neighbour's next push, which is stream-ordered behind
+// the neighbour's current product), so two buffers are enough and no flow control is needed.  `out` holds b on entry.
+// The sequence number is advanced by a one-thread kernel ahead of the product (stream / graph ordered), so a replayed
+// CUDA graph needs no host argument.  Cooperative launch: all blocks must be resident, a block that waits for a ghost
+// pushed by a not yet scheduled block of the peer (which waits for this rank's unscheduled blocks) would deadlock.
+__global__ void tc_dist_seq_kernel(int* state, const int* __restrict__ done) {
+    if (done && *done) return;
+    state[1] += 1;
+}
+template <int MB, int THREADS>
+__global__ void __launch_bounds__(THREADS, MB)
+tc_dist_residual_kernel(TcDistK S, const double* __restrict__ v, double* out, const int* __restrict__ done) {
+    if (done && *done) return;
+    const unsigned int hseq = (unsigned int)S.state[1];
+    const int pb = (int)(hseq & 1u);
+    const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+    for (long long e = gtid; e < S.n_send; e += gsz)
+        ll_store(S.peer_p_gl[pb][S.send_peer[e]] + 2 * S.send_dst[e], v[S.send_row[e]], hseq);
+    slab_spmv<SPMV_B>(S, v, S.p_gl[pb], out, out, 0.0, hseq);
+}
+extern "C" int tc_dist_residual(tc_dist* d, const double* v_local_dev, double* out_local_dev, const int32_t* done_flag_dev) {
+    TC_CHECK(d->K.A.val && d->grid > 0, "operator not set");
+    TC_CHECK(d->world == 1 || d->peers_open, "peers not open");
+    tc_dist_seq_kernel<<<1, 1, 0, d->stream>>>(d->state, done_flag_dev);
+    void* fn = dist_threads() == 512 ? (void*)tc_dist_residual_kernel<4, 512>
+               : dist_threads() == 256 ? (void*)tc_dist_residual_kernel<8, 256> : (void*)tc_dist_residual_kernel<2, 1024>;
+    void* args[] = {(void*)&d->K, (void*)&v_local_dev, (void*)&out_local_dev, (void*)&done_flag_dev};
+    TC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(dist_threads()), args, 0, d->stream));
+    return 0;
+}
+
+// vals[j] <- sum over the ranks of vals[j], added in rank order (bit-identical on every rank): the error norm and the
+// initial-step norms of the adaptive pairs (scipy rk.py:145-165, common.py:63-134 are means over ALL rows).  Shares the
+// mailbox and the sequence counter of the surface-mean exchange.
+__global__ void tc_dist_sum_exchange_kernel(TcDistK S, double* __restrict__ vals, int k, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double s_loc[TC_MB2_VALUES];
+    int* err = S.state + 4;
+    const int seq = S.state[12] + 1;
+    const int par = seq & 1;
+    const bool bad = *((volatile int*)err) != 0;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) s_loc[j] = vals[j];
+    __syncthreads();
+    for (int it = threadIdx.x; it < S.world * k; it += blockDim.x) {
+        const int w = it / k, j = it - w * k;
+        ll_store(S.peer_mb2[w] + ((size_t)par * TC_MAX_WORLD + S.rank) * TC_MB2_SLOT + 2 * j, bad ? nan("") : s_loc[j],
+                 (unsigned int)seq);
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        double tot = 0.0;
+        for (int w = 0; w < S.world; ++w)
+            tot += ll_load(S.my_mb2 + ((size_t)par * TC_MAX_WORLD + w) * TC_MB2_SLOT + 2 * j, (unsigned int)seq, err,
+                           S.spin_limit);
+        vals[j] = tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) S.state[12] = seq;
+}
+extern "C" int tc_dist_sum_exchange(tc_dist* d, double* vals_dev, int32_t k, const int32_t* done_flag_dev) {
+    TC_CHECK(k >= 0 && k <= TC_MB2_VALUES, "too many values in one exchange");
+    if (k == 0 || d->world == 1) return 0;
+    TC_CHECK(d->peers_open, "peers not open");
+    tc_dist_sum_exchange_kernel<<<1, 64, 0, d->stream>>>(d->K, vals_dev, k, done_flag_dev);
+    return 0;
+}
+extern "C" int32_t tc_dist_rank(tc_dist* d) { return d->rank; }
 extern "C" int64_t tc_dist_local_rows(tc_dist* d) { return d->n; }
 extern "C" void* tc_dist_stream(tc_dist* d) { return (void*)d->stream; }
 

@@ -128,31 +128,9 @@ __global__ void tc_prepare_kernel(double* ctrl, int* fl) {
     ctrl[CT_H] = h; ctrl[CT_HABS] = fabs(h); ctrl[CT_TNEW] = t_new;
 }
 
-// error norm + accept / reject + next step size   (scipy rk.py:145-165, common.py:63-65)
-// err_i = h * sum_j E_j K_j[i]; scale = atol + max(|y|,|ynew|) rtol
-__global__ void tc_error_control_kernel(long long n, const double* __restrict__ y,
-                                        const double* __restrict__ ynew, TcLin E, double* ctrl,
-                                        int* fl, double* __restrict__ partial) {
-    if (fl[FL_DONE]) return;
-    __shared__ double sh[32];
-    const double h = ctrl[CT_H], rtol = ctrl[CT_RTOL], atol = ctrl[CT_ATOL];
-    double s = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 7; ++j)
-            if (j < E.nk) acc += E.k[j][i] * E.c[j];
-        const double sc = atol + fmax(fabs(y[i]), fabs(ynew[i])) * rtol;
-        const double e = acc * h / sc;
-        s += e * e;
-    }
-    const double bs = block_sum(s, sh);
-    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
-    if (!last_block_arrives(reinterpret_cast<unsigned int*>(fl + FL_COUNTER))) return;
-    const double tot = ordered_partial_sum(partial, gridDim.x, sh);
-    if (threadIdx.x != 0) return;
-    const double err = sqrt(tot) / sqrt((double)n);
+// accept / reject + next step size from the squared error sum `tot` over n entries (scipy rk.py:145-165); one thread
+__device__ void tc_rk_control(double tot, double n, double* ctrl, int* fl) {
+    const double err = sqrt(tot) / sqrt(n);
     ctrl[CT_ERR] = err;
     double h_abs = ctrl[CT_HABS];
     const double ex = ctrl[CT_EXP];
@@ -183,6 +161,33 @@ __global__ void tc_error_control_kernel(long long n, const double* __restrict__ 
     }
 }
 
+// error norm + accept / reject + next step size   (scipy rk.py:145-165, common.py:63-65)
+// err_i = h * sum_j E_j K_j[i]; scale = atol + max(|y|,|ynew|) rtol
+__global__ void tc_error_control_kernel(long long n, const double* __restrict__ y,
+                                        const double* __restrict__ ynew, TcLin E, double* ctrl,
+                                        int* fl, double* __restrict__ partial) {
+    if (fl[FL_DONE]) return;
+    __shared__ double sh[32];
+    const double h = ctrl[CT_H], rtol = ctrl[CT_RTOL], atol = ctrl[CT_ATOL];
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (j < E.nk) acc += E.k[j][i] * E.c[j];
+        const double sc = atol + fmax(fabs(y[i]), fabs(ynew[i])) * rtol;
+        const double e = acc * h / sc;
+        s += e * e;
+    }
+    const double bs = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+    if (!last_block_arrives(reinterpret_cast<unsigned int*>(fl + FL_COUNTER))) return;
+    const double tot = ordered_partial_sum(partial, gridDim.x, sh);
+    if (threadIdx.x != 0) return;
+    tc_rk_control(tot, (double)n, ctrl, fl);
+}
+
 // on accept: y <- ynew, K0 <- K_last (FSAL), history snapshot
 __global__ void tc_accept_kernel(long long n, long long u, double* __restrict__ y,
                                  const double* __restrict__ ynew, double* __restrict__ k0,
@@ -206,6 +211,70 @@ __global__ void tc_accept_kernel(long long n, long long u, double* __restrict__ 
              i += (long long)gridDim.x * blockDim.x)
             hist_io[(long long)slot * n_probe + i] = ynew[u + probe_idx[i]];
 }
+// ---- the same norms on a row-partitioned network (explicit pairs under torchrun) -------------------------------------
+// The state of a rank is [replicated entries | LOCAL rows of the partitioned body [lo, hi) | replicated entries]; the
+// reference's norms are means over the GLOBAL state.  Partial sums are kept per class; rank 0 alone contributes the
+// replicated class (its grouping of those entries differs between ranks because hi does), the sums are traded with
+// tc_dist_sum_exchange (rank order), so every rank takes bit-identical accept / reject and step-size decisions.
+//   MODE 0: error norm, bank 0/1 = replicated/body;  MODE 1: the two select_initial_step norms, banks 0/1 and 2/3
+template <int MODE>
+__global__ void tc_dist_norm_partial_kernel(long long n, long long lo, long long hi, const double* __restrict__ y,
+                                            const double* __restrict__ ynew, TcLin E, const double* __restrict__ a,
+                                            const double* __restrict__ b, const double* __restrict__ bsub,
+                                            const double* __restrict__ ctrl, double* __restrict__ partial,
+                                            const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sh[32];
+    const double h = ctrl[CT_H], rtol = ctrl[CT_RTOL], atol = ctrl[CT_ATOL];
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int cls = (i >= lo && i < hi) ? 1 : 0;
+        if (MODE == 0) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 7; ++j)
+                if (j < E.nk) acc += E.k[j][i] * E.c[j];
+            const double sc = atol + fmax(fabs(y[i]), fabs(ynew[i])) * rtol;
+            const double e = acc * h / sc;
+            s[cls] += e * e;
+        } else {
+            const double sc = atol + fabs(y[i]) * rtol;
+            const double va = a[i] / sc;
+            s[cls] += va * va;
+            const double vb = (bsub ? b[i] - bsub[i] : b[i]) / sc;
+            s[2 + cls] += vb * vb;
+        }
+    }
+    for (int q = 0; q < (MODE == 0 ? 2 : 4); ++q) {
+        const double r = block_sum(s[q], sh);
+        if (threadIdx.x == 0) partial[q * TC_MAX_PARTIALS + blockIdx.x] = r;
+        __syncthreads();
+    }
+}
+// ex[j] = body sum j (+ replicated sum j on rank 0), ex[nv] = local body rows (+ replicated entries on rank 0)
+__global__ void tc_dist_norm_fold_kernel(int G, const double* __restrict__ partial, int nv, int rank, long long n_repl,
+                                         long long n_body, double* __restrict__ ex, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sh[32];
+    for (int j = 0; j < nv; ++j) {
+        const double rep = ordered_partial_sum(partial + (2 * j) * TC_MAX_PARTIALS, G, sh);
+        __syncthreads();
+        const double bod = ordered_partial_sum(partial + (2 * j + 1) * TC_MAX_PARTIALS, G, sh);
+        __syncthreads();
+        if (threadIdx.x == 0) ex[j] = rank == 0 ? rep + bod : bod;
+    }
+    if (threadIdx.x == 0) ex[nv] = (double)(rank == 0 ? n_repl + n_body : n_body);
+}
+__global__ void tc_dist_control_kernel(const double* __restrict__ ex, double* ctrl, int* fl) {
+    if (fl[FL_DONE]) return;
+    tc_rk_control(ex[0], ex[1], ctrl, fl);
+}
+// totals -> the layout tc_init_h0_kernel / tc_init_h1_kernel read with G = 1
+__global__ void tc_dist_norm_unfold_kernel(const double* __restrict__ ex, double* __restrict__ partial) {
+    partial[0] = ex[0];
+    partial[TC_MAX_PARTIALS] = ex[1];
+}
+
 // network snapshot + flag finalisation (single block)
 __global__ void tc_snapshot_kernel(TcNetParams P, const double* __restrict__ ctrl, int* fl,
                                    double* __restrict__ hist_net, const double* __restrict__ y = nullptr) {
@@ -329,6 +398,10 @@ struct tc_solver {
     double pcg_rtol = 1e-10; int pcg_maxit = 1000; int pcg_mode = TC_PCG_COOP; int coop_grid = 0;
     double ros_gamma = 1.0 + 0.70710678118654752440;
     bool has_dist = false;             // a part is row-partitioned (tc_attach_dist)
+    long long dist_rows_global = 0;    // rows of that body over all ranks (tc_set_dist_global_rows): enables the explicit pairs
+    bool dist_full_rhs = false;        // enqueue_rhs forms f = b - A y for the partitioned body (explicit pairs); false:
+                                       // only b (the fused theta kernel of dist.cu does the product itself)
+    double* dist_ex = nullptr;         // 4 doubles traded by tc_dist_sum_exchange (norm sums + row count)
     // rank-one Jacobian terms of films that lead to stationary nodes (tc_set_jac_films)
     int jac_n = 0;
     int jac_rec[TC_JAC_MAX][8] = {};
@@ -361,6 +434,7 @@ extern "C" int tc_create(tc_handle* out, void* cuda_stream) {
     TC_CUDA(cudaMemset(s->ctrl, 0, sizeof(double) * 32));
     TC_CUDA(cudaMemset(s->flags, 0, sizeof(int) * 32));
     TC_CUDA(cudaMalloc(&s->red_partial, sizeof(double) * 4 * TC_MAX_PARTIALS));
+    TC_CUDA(cudaMalloc(&s->dist_ex, sizeof(double) * 8));
     TC_CUDA(cudaMalloc(&s->pcg_sc, sizeof(double) * 16));
     TC_CUDA(cudaMalloc(&s->pcg_isc, sizeof(int) * 16));
     TC_CUDA(cudaMemset(s->pcg_sc, 0, sizeof(double) * 16));
@@ -381,7 +455,7 @@ extern "C" int tc_create(tc_handle* out, void* cuda_stream) {
 extern "C" int tc_destroy(tc_handle s) {
     if (!s) return 0;
     drop_graphs(s);
-    cudaFree(s->ctrl); cudaFree(s->flags); cudaFree(s->red_partial); cudaFree(s->pcg_sc);
+    cudaFree(s->ctrl); cudaFree(s->flags); cudaFree(s->red_partial); cudaFree(s->dist_ex); cudaFree(s->pcg_sc);
     cudaFree(s->pcg_isc); cudaFree(s->pcg_prof); cudaFree(s->mean_partials);
     cudaFree(s->bar.ctr); cudaFree(s->bar.part); cudaFree(s->bar.res);
     cudaFree(s->y); cudaFree(s->ynew); cudaFree(s->ystage);
@@ -521,6 +595,11 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
             if (p.load.nrows > 0)
                 tc_ffe_surf_load_kernel<<<grid_for(p.load.nrows, 256, s->sm_count * 4), 256, 0, st>>>(
                     p.load, s->net.darena + p.d.flux_doff, out + p.d.y_off, done);
+            // explicit pairs: f = b - A y with the peers' ghost rows of THIS stage vector (halo inside the kernel)
+            if (s->dist_full_rhs) {
+                if (tc_dist_residual(p.dist, yin + p.d.y_off, out + p.d.y_off, done)) return -1;
+                s->launches += 2;
+            }
             continue;
         }
         const int g = grid_for(p.A.nslices, TC_SPMV_THREADS / 32, s->sm_count * 8);
@@ -558,7 +637,13 @@ extern "C" int tc_rhs(tc_handle s, double t, const double* y_dev, double* ydot_d
     double c2[2] = {t, 0.0};
     TC_CUDA(cudaMemcpyAsync(s->ctrl + CT_T, c2, sizeof c2, cudaMemcpyHostToDevice, s->stream));
     TC_CUDA(cudaStreamSynchronize(s->stream));
-    if (enqueue_rhs(s, 0.0, y_dev, ydot_dev)) return -1;
+    // row-partitioned body: the complete f = b - A y of the local rows once the explicit pairs are enabled
+    // (tc_set_dist_global_rows), otherwise only the load vector b (what the fused theta kernel consumes); collective
+    const bool keep = s->dist_full_rhs;
+    s->dist_full_rhs = s->has_dist && s->dist_rows_global > 0;
+    const int rc = enqueue_rhs(s, 0.0, y_dev, ydot_dev);
+    s->dist_full_rhs = keep;
+    if (rc) return -1;
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
@@ -640,6 +725,25 @@ static Tableau tableau(int method) {
     return T;
 }
 
+// norms of the adaptive pairs on a row-partitioned network: class-split partial sums -> fold -> exchange (dist.cu)
+static const FfePart* dist_part(const tc_solver* s) {
+    for (auto& p : s->ffe) if (p.dist) return &p;
+    return nullptr;
+}
+template <int MODE>
+static int enqueue_dist_norm(tc_solver* s, const double* ynew, const TcLin& E, const double* a, const double* b,
+                             const double* bsub, const int* done) {
+    const FfePart* p = dist_part(s);
+    const long long n = s->n_state, lo = p->d.y_off, hi = p->d.y_off + p->d.n;
+    const int G = s->vec_grid, nv = MODE == 0 ? 1 : 2;
+    tc_dist_norm_partial_kernel<MODE><<<G, 256, 0, s->stream>>>(n, lo, hi, s->y, ynew, E, a, b, bsub, s->ctrl, s->red_partial, done);
+    tc_dist_norm_fold_kernel<<<1, 256, 0, s->stream>>>(G, s->red_partial, nv, tc_dist_rank(p->dist), n - p->d.n, p->d.n,
+                                                       s->dist_ex, done);
+    if (tc_dist_sum_exchange(p->dist, s->dist_ex, nv + 1, done)) return -1;
+    s->launches += 3;
+    return 0;
+}
+
 static int enqueue_rk_attempt(tc_solver* s) {
     cudaStream_t st = s->stream;
     const Tableau T = tableau(s->method);
@@ -662,7 +766,12 @@ static int enqueue_rk_attempt(tc_solver* s) {
     TcLin Le{};
     Le.nk = ns + 1;
     for (int j = 0; j <= ns; ++j) { Le.k[j] = s->K[j]; Le.c[j] = T.E[j]; }
-    tc_error_control_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    if (s->has_dist) {
+        if (enqueue_dist_norm<0>(s, s->ynew, Le, nullptr, nullptr, nullptr, done)) return -1;
+        tc_dist_control_kernel<<<1, 1, 0, st>>>(s->dist_ex, s->ctrl, s->flags);
+    } else {
+        tc_error_control_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    }
     tc_accept_kernel<<<s->vec_grid, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, s->K[0], s->K[ns], s->flags, s->hist_io, s->probe_idx, s->n_probe);
     tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net);
     s->launches += ns + 4;   // stage combinations, prepare, error control, accept, snapshot
@@ -716,8 +825,9 @@ static int store_initial(tc_solver* s) {
 extern "C" int tc_rk_begin(tc_handle s, int32_t method, double t0, double t_end, double rtol, double atol,
                            double max_step, double first_step) {
     TC_CHECK(s && s->finalized, "solver not finalized");
-    TC_NO_DIST(s);
+    TC_CHECK(!s->has_dist || s->dist_rows_global > 0, "explicit pairs on a row-partitioned body need tc_set_dist_global_rows");
     TC_CHECK(method == TC_RK45 || method == TC_RK23, "unknown method");
+    s->dist_full_rhs = s->has_dist;
     if (s->rk_graph && s->method != method) { cudaGraphExecDestroy(s->rk_graph); s->rk_graph = nullptr; }
     s->method = method;
     const Tableau T = tableau(method);
@@ -745,15 +855,29 @@ extern "C" int tc_rk_begin(tc_handle s, int32_t method, double t0, double t_end,
     } else if (n == 0) {
         if (set_ctrl(s, CT_HABS, INFINITY)) return -1;
     } else {
-        tc_norm2_kernel<<<G, 256, 0, st>>>(n, s->y, s->y, s->K[0], nullptr, s->ctrl, s->red_partial, nullptr);
-        tc_init_h0_kernel<<<1, 256, 0, st>>>(n, G, s->red_partial, s->ctrl);
+        // partitioned network: global sums through the exchange, then the same two kernels on the totals (G = 1)
+        const long long ng = s->has_dist ? n - dist_part(s)->d.n + s->dist_rows_global : n;
+        const int Gn = s->has_dist ? 1 : G;
+        const TcLin none{};
+        if (s->has_dist) {
+            if (enqueue_dist_norm<1>(s, nullptr, none, s->y, s->K[0], nullptr, nullptr)) return -1;
+            tc_dist_norm_unfold_kernel<<<1, 1, 0, st>>>(s->dist_ex, s->red_partial);
+        } else {
+            tc_norm2_kernel<<<G, 256, 0, st>>>(n, s->y, s->y, s->K[0], nullptr, s->ctrl, s->red_partial, nullptr);
+        }
+        tc_init_h0_kernel<<<1, 256, 0, st>>>(ng, Gn, s->red_partial, s->ctrl);
         TcLin L{};
         L.nk = 1; L.k[0] = s->K[0]; L.c[0] = 1.0;
         tc_lin_kernel<<<G, 256, 0, st>>>(n, s->y, L, s->ctrl, s->ystage, nullptr);   // y1 = y0 + h0 f0
         if (enqueue_rhs(s, 1.0, s->ystage, s->K[1])) return -1;                        // f1 at t0 + h0
         s->nfev_base += 1;
-        tc_norm2_kernel<<<G, 256, 0, st>>>(n, s->y, s->y, s->K[1], s->K[0], s->ctrl, s->red_partial, nullptr);
-        tc_init_h1_kernel<<<1, 256, 0, st>>>(n, G, s->red_partial, s->ctrl, T.order);
+        if (s->has_dist) {
+            if (enqueue_dist_norm<1>(s, nullptr, none, s->y, s->K[1], s->K[0], nullptr)) return -1;
+            tc_dist_norm_unfold_kernel<<<1, 1, 0, st>>>(s->dist_ex, s->red_partial);
+        } else {
+            tc_norm2_kernel<<<G, 256, 0, st>>>(n, s->y, s->y, s->K[1], s->K[0], s->ctrl, s->red_partial, nullptr);
+        }
+        tc_init_h1_kernel<<<1, 256, 0, st>>>(ng, Gn, s->red_partial, s->ctrl, T.order);
     }
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(st));
@@ -1371,10 +1495,18 @@ extern "C" int tc_attach_dist(tc_handle s, int32_t part, tc_dist* d, int32_t fir
     return 0;
 }
 
+extern "C" int tc_set_dist_global_rows(tc_handle s, int64_t n_rows_global) {
+    TC_CHECK(s && s->has_dist, "no row-partitioned part attached");
+    TC_CHECK(n_rows_global >= dist_part(s)->d.n, "global row count below the local one");
+    s->dist_rows_global = n_rows_global;
+    return 0;
+}
+
 extern "C" int tc_theta_steps(tc_handle s, int32_t nsteps, double theta, double h_step, double pcg_rtol,
                               int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
     s->pcg_rtol = pcg_rtol; s->pcg_maxit = pcg_maxit; s->pcg_mode = pcg_mode;
+    s->dist_full_rhs = false;                       // the fused kernel of dist.cu forms b - A y itself
     if (set_ctrl(s, CT_H, h_step)) return -1;
     cudaStream_t st = s->stream;
     const int* done = s->flags + FL_DONE;

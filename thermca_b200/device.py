@@ -650,7 +650,9 @@ class DeviceSolver:
         torch = self.torch
         w_net = 1 + 3 * self.N + 2 * self.nnz
         self._io_width = self._n_probe if getattr(self, "_probe_mode", False) else self.n_io
-        per = 8 * (self._io_width + w_net)
+        # a row-partitioned run needs the SAME ring capacity on every rank (a full ring pauses the device loop):
+        # partition.py sets _cap_width to the widest rank's row
+        per = 8 * (max(self._io_width, getattr(self, "_cap_width", 0)) + w_net)
         cap = int(max(8, min(8192, self.history_bytes // max(per, 1))))
         self.capacity = cap
         self.hist_io = torch.zeros((cap, max(self._io_width, 1)), dtype=torch.float64, device=self.dev)
@@ -775,6 +777,8 @@ class DeviceSolver:
         ``thermca_b200.dist.DistBody`` built on this solver's SELL tensors and stream (thermca_b200/partition.py)."""
         j0, nj = self._ffe_job_range[k]
         _cabi.check(self.lib.tc_attach_dist(self._handle, int(k), body._h, int(j0), int(nj)))
+        # global row count: the adaptive explicit pairs (run_rk) take their error / initial-step norms over ALL ranks
+        _cabi.check(self.lib.tc_set_dist_global_rows(self._handle, int(body.n_global)))
         self._bodies = getattr(self, "_bodies", []) + [body]
 
     def set_block_jacobi(self, h, theta=0.5):

@@ -39,6 +39,9 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
     if method in FIXED_STEP_METHODS and _world_size() > 1 and options.get("partition", True):
         res = _theta_partitioned(spec, t0, t1, num_skip, options)
         return _collector_from(net, spec, res, t0)
+    if method in ("RK45", "RK23") and options.get("partition", False) and _dist_ready():
+        res = _rk_partitioned(spec, t0, t1, rel_tol, abs_tol, method, num_skip, options)
+        return _collector_from(net, spec, res, t0)
     dev = DeviceSolver(spec)
 
     # the progress thread of Network.sim reads these two attributes every 2 s (network.py:960-985, solver.py:321-325)
@@ -75,12 +78,74 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
     return _collector_from(net, spec, res, t0)
 
 
+def _dist_ready():
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized()
+    except Exception:                                        # pragma: no cover
+        return False
+
+
 def _world_size():
     try:
         import torch.distributed as dist
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     except Exception:
         return 1
+
+
+def _rk_partitioned(spec, t0, t1, rel_tol, abs_tol, method, num_skip, options):
+    """The reference's own adaptive pairs (``RK45`` / ``RK23``, thermca/solver.py:348-390) under torchrun with
+    ``sim(..., partition=True)``: the largest full-order FE body is row-partitioned as for ``THETA_PCG``, everything else
+    is replicated.  Every right-hand side evaluates the body's ``b - A y`` on the local rows with the neighbours' ghost
+    rows of that stage vector pushed over NVLink inside the product kernel (csrc/dist.cu:tc_dist_residual_kernel);
+    surface means, the error norm and the initial-step norms are sums over all ranks added in rank order
+    (``tc_dist_mean_exchange`` / ``tc_dist_sum_exchange``), so every rank takes bit-identical step decisions and the
+    on-device controller, the attempt graph and the history ring work as on one GPU.  Every rank returns the full
+    result (stored part states gathered once, after the run)."""
+    import torch
+    import torch.distributed as dist
+    from .dist import DistBody
+    from .partition import choose_partitioned_part, localize_ffe_part
+    k = choose_partitioned_part(spec)
+    if k < 0:
+        raise NotImplementedError("partition=True needs a full-order FE body without temperature dependent material")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    part = spec["ffe"][k]
+    n_glob = int(part["dof"])
+    local, presplit, info = localize_ffe_part(part, rank, world)
+    spec_loc = dict(spec)
+    spec_loc["ffe"] = list(spec["ffe"])
+    spec_loc["ffe"][k] = local
+    dev = DeviceSolver(spec_loc)
+    body = None
+    u = int(spec["u"])
+    try:
+        body = DistBody(dev.ffe_sell[k], None, info["bounds"], init_temp=None, stream=dev.stream, presplit=presplit)
+        dev.attach_partition(k, body)
+        dev._cap_width = dev.n_io - int(local["dof"]) + int(np.diff(info["bounds"]).max())     # same ring capacity everywhere
+        res = dev.run_rk(t0, t1, rel_tol, abs_tol, method, num_skip, max_step=options.get("max_step", np.inf),
+                         first_step=options.get("first_step"))
+        body.check()
+        final_net = dev.network_state()
+        off_loc, n_loc = dev.ffe_off[k], int(local["dof"])
+        sizes = [int(info["bounds"][w + 1] - info["bounds"][w]) for w in range(world)]
+        io = res["io_temps"]
+        m, a = io.shape[0], off_loc - u
+        mine = torch.from_numpy(np.ascontiguousarray(io[:, a: a + n_loc].T)).to(dev.dev)        # rows of the body x steps
+        parts = [torch.empty((sz, m), dtype=torch.float64, device=dev.dev) for sz in sizes]
+        dist.all_gather(parts, mine)
+        inv = torch.from_numpy(info["inv"]).to(dev.dev)
+        body_glob = torch.cat(parts, dim=0)[inv].T.cpu().numpy()                                # caller's DOF order
+        res["io_temps"] = np.concatenate([io[:, :a], body_glob, io[:, a + n_loc:]], axis=1)
+    finally:
+        torch.cuda.synchronize()
+        if body is not None:
+            body.close()
+        dev.close()
+    res["final_net"] = final_net
+    res["partition"] = {"part": k, "dof": n_glob, "rows_per_rank": sizes}
+    return res
 
 
 def _theta_partitioned(spec, t0, t1, num_skip, options):
