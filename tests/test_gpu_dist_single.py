@@ -26,8 +26,9 @@ def test_dist_kernel_world1_matches_single_gpu_solver():
 
 
 def test_partitioned_rk_world1_matches_single_gpu_run():
-    """The adaptive explicit pairs on a partitioned body (tc_dist_residual, class-split norms, the attempt graph with
-    cooperative launches) through the unmodified reference's Network.sim at world size 1."""
+    """The adaptive schemes on a partitioned body — explicit pairs (tc_dist_residual, class-split norms, the attempt graph
+    with cooperative launches) and W-methods (stage solves in the solve-only instantiation of the fused kernel) — through
+    the unmodified reference's Network.sim at world size 1."""
     if not (os.path.isdir(os.path.join(ROOT, "oracle", "_ref")) or os.path.isdir("/root/reference")):
         pytest.skip("reference tree not staged")
     with socket.socket() as s:

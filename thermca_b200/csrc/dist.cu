@@ -67,6 +67,10 @@ struct TcDistK {
                                           // [4] comm error, [5] solves, [7] status of the last failed solve, [8] failed solves
     double theta, h, rtol;
     int maxit;
+    // solve-only instantiation (stage solves of the W-methods on a partitioned body): z = (I + theta h A)^-1 rhs
+    const double* rhs_in; double* x_out;  // local rows
+    const double* h_dev;                  // step size on the device (the controller's), overrides h when non-null
+    const int* done;                      // skip the launch when *done != 0
     long long spin_limit;                 // clock64 ticks
     int push_fence;                       // experiment switch (TC_DIST_PUSH_FENCE=1): system fence after ghost pushes
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
@@ -279,9 +283,9 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 // scaled right-hand side and Jacobi factor of one row (explicit roundings: the owner's loop and the halo push
 // must produce the same bits)
-__device__ __forceinline__ void init_row(const TcDistK& S, int i, double shift, double& bsc, double& d) {
+__device__ __forceinline__ void init_row(const TcDistK& S, const double* f, int i, double shift, double& bsc, double& d) {
     const double m = S.mass[i];
-    bsc = __dmul_rn(m, S.q[i]);
+    bsc = __dmul_rn(m, f[i]);
     d = __ddiv_rn(1.0, __dmul_rn(m, __fma_rn(shift, S.adiag[i], 1.0)));
 }
 
@@ -289,25 +293,32 @@ __device__ __forceinline__ void init_row(const TcDistK& S, int i, double shift, 
 // A single-reduction CG (Chronopoulos & Gear) was measured too: it saves one all-reduce per iteration (~10 us) but its
 // vector phase streams 12 arrays and loses the L2 residency of the 8-array form (23 vs 13 us at 1.25 M rows per GPU):
 // 789 vs 957 M DOF*steps/s at N = 2 (profiles/README.md), so the classic two-reduction form stays.
-template <int MB, int THREADS = TC_DIST_THREADS>
+// SOLVE = true: the same iteration as a stage solve of a W-method, z = (I + theta h A)^-1 rhs_in -> x_out (no product
+// with y, no commit), h read from the device.
+template <int MB, int THREADS = TC_DIST_THREADS, bool SOLVE = false>
 __global__ void __launch_bounds__(THREADS, MB)
 tc_dist_theta_kernel(TcDistK S) {
     __shared__ double sh[32];
+    if (SOLVE && S.done && *S.done) return;              // uniform over the grid and the ranks
     const int n = S.n;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     unsigned int gen = 0u;
     int rseq = S.state[0];
     unsigned int hseq = (unsigned int)S.state[1];
     PROF_INIT();
-    const double shift = S.theta * S.h;
+    const double hstep = (SOLVE && S.h_dev) ? *S.h_dev : S.h;
+    const double shift = S.theta * hstep;
     int pb = 0;
+    const double* f = SOLVE ? S.rhs_in : S.q;
 
     // ---- right-hand side f = b - A y (thermca/solver.py:281) on the local rows -----------------
-    ++hseq;
-    for (long long e = gtid; e < S.n_send; e += gsz)
-        ll_store(S.peer_y_gl[S.send_peer[e]] + 2 * S.send_dst[e], S.y[S.send_row[e]], hseq);
-    slab_spmv<SPMV_B>(S, S.y, S.y_gl, S.q, S.b, 0.0, hseq);
-    tc_grid_barrier(S.bar, gen, S.world > 1 ? S.state + 4 : nullptr, S.spin_limit);
+    if (!SOLVE) {
+        ++hseq;
+        for (long long e = gtid; e < S.n_send; e += gsz)
+            ll_store(S.peer_y_gl[S.send_peer[e]] + 2 * S.send_dst[e], S.y[S.send_row[e]], hseq);
+        slab_spmv<SPMV_B>(S, S.y, S.y_gl, S.q, S.b, 0.0, hseq);
+        tc_grid_barrier(S.bar, gen, S.world > 1 ? S.state + 4 : nullptr, S.spin_limit);
+    }
     double red[TC_DIST_K];
     ++hseq;
     {
@@ -316,12 +327,12 @@ tc_dist_theta_kernel(TcDistK S) {
         // rows a peer needs first: recomputed from the same stable inputs (bit-identical), pushed over NVLink
         for (long long e = gtid; e < S.n_send; e += gsz) {
             double bsc, d;
-            init_row(S, S.send_row[e], shift, bsc, d);
+            init_row(S, f, S.send_row[e], shift, bsc, d);
             ll_store(S.peer_p_gl[0][S.send_peer[e]] + 2 * S.send_dst[e], __dmul_rn(d, bsc), hseq);
         }
         for (int i = gtid; i < n; i += gsz) {
             double bsc, d;
-            init_row(S, i, shift, bsc, d);
+            init_row(S, f, i, shift, bsc, d);
             const double z = __dmul_rn(d, bsc);
             S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; p0[i] = z;
             rho_l += bsc * z; bb_l += bsc * bsc;
@@ -379,8 +390,12 @@ tc_dist_theta_kernel(TcDistK S) {
         }
     }
     // ---- y += h * z (not committed after a communication failure / breakdown) ------------------
-    if (status != 2)
+    if (SOLVE) {
+        // a failed stage solve leaves NaN: the controller rejects the attempt on every rank alike
+        for (int i = gtid; i < n; i += gsz) S.x_out[i] = status != 2 ? S.x[i] : nan("");
+    } else if (status != 2) {
         for (int i = gtid; i < n; i += gsz) S.y[i] += S.h * S.x[i];
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         S.state[0] = rseq; S.state[1] = (int)hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
         if (status) { S.state[7] = status; S.state[8] += 1; }
@@ -765,6 +780,21 @@ extern "C" int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, dou
         void* args[] = {(void*)&d->K};
         TC_CUDA(cudaLaunchCooperativeKernel(dist_fn(), dim3(d->grid), dim3(dist_threads()), args, 0, d->stream));
     }
+    return 0;
+}
+
+// stage solve of a W-method on the partitioned body: z = (I + coef * h A)^-1 rhs on the local rows, h from the device
+extern "C" int tc_dist_solve(tc_dist* d, double coef, const double* h_dev, const double* rhs_local_dev, double* z_local_dev,
+                             double rtol, int32_t maxit, const int32_t* done_flag_dev) {
+    TC_CHECK(d->K.A.val && d->grid > 0, "operator not set");
+    TC_CHECK(d->world == 1 || d->peers_open, "peers not open");
+    TcDistK K = d->K;
+    K.theta = coef; K.h = 0.0; K.h_dev = h_dev; K.rtol = rtol; K.maxit = maxit;
+    K.rhs_in = rhs_local_dev; K.x_out = z_local_dev; K.done = done_flag_dev;
+    void* fn = dist_threads() == 512 ? (void*)tc_dist_theta_kernel<4, 512, true>
+               : dist_threads() == 256 ? (void*)tc_dist_theta_kernel<8, 256, true> : (void*)tc_dist_theta_kernel<2, 1024, true>;
+    void* args[] = {(void*)&K};
+    TC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(dist_threads()), args, 0, d->stream));
     return 0;
 }
 

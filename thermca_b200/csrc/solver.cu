@@ -821,7 +821,6 @@ static int store_initial(tc_solver* s) {
     return 0;
 }
 
-#define TC_NO_DIST(s) TC_CHECK(!(s)->has_dist, "this scheme is not available for a row-partitioned body (use tc_theta_steps)")
 extern "C" int tc_rk_begin(tc_handle s, int32_t method, double t0, double t_end, double rtol, double atol,
                            double max_step, double first_step) {
     TC_CHECK(s && s->finalized, "solver not finalized");
@@ -1268,7 +1267,16 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
         if (launch_pcg(s, P, s->pcg_mode == TC_PCG_COOP_BJ ? TC_PCG_COOP : s->pcg_mode, s->coop_grid, done)) return -1;
     }
     for (auto& p : s->ffe) {
-        if (p.dist) continue;                                  // row-partitioned: solved by the fused kernel of dist.cu
+        if (p.dist) {
+            // row-partitioned body.  theta steps: advanced by the fused kernel of dist.cu (tc_theta_steps).  W-methods:
+            // the stage solve runs in the solve-only instantiation of that kernel across the GPUs, always implicit
+            if (w_method) {
+                if (tc_dist_solve(p.dist, coef, s->ctrl + CT_H, rhs + p.d.y_off, z + p.d.y_off, s->pcg_rtol, s->pcg_maxit, done))
+                    return -1;
+                s->launches += 1;
+            }
+            continue;
+        }
         const bool frozen = p.d.tdep != 0;
         if (frozen && !(w_method && p.J.n > 0)) continue;      // operator depends on T: explicit (copy above)
         TcPcg& P = p.pcg;
@@ -1490,6 +1498,19 @@ extern "C" int tc_attach_dist(tc_handle s, int32_t part, tc_dist* d, int32_t fir
     TC_CHECK(tc_dist_local_rows(d) == s->ffe[part].d.n, "local row count of the part and of the partition differ");
     TC_CHECK(tc_dist_stream(d) == (void*)s->stream, "the partition must use the solver's stream");
     s->ffe[part].dist = d;
+    // rank-one Jacobian terms of films between this body and stationary nodes are dropped: their Woodbury correction
+    // uses surface means of the LOCAL rows only; a W-method admits any Jacobian approximation (it costs steps, not order)
+    if (s->ffe[part].has_jac) {
+        int m = 0;
+        for (int j = 0; j < s->jac_n; ++j)
+            if (!(s->jac_rec[j][0] == 1 && s->jac_rec[j][1] == part)) {
+                if (m != j) for (int k = 0; k < 8; ++k) s->jac_rec[m][k] = s->jac_rec[j][k];
+                ++m;
+            }
+        s->jac_n = m;
+        s->ffe[part].has_jac = false;
+    }
+    drop_graphs(s);
     s->ffe[part].job0 = first_job; s->ffe[part].njobs = n_jobs;
     s->has_dist = true;
     return 0;
@@ -1537,7 +1558,9 @@ extern "C" int tc_theta_steps(tc_handle s, int32_t nsteps, double theta, double 
 extern "C" int tc_ros2_begin(tc_handle s, double t0, double t_end, double rtol, double atol, double max_step,
                              double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
-    TC_NO_DIST(s);
+    TC_CHECK(!s->has_dist || s->dist_rows_global > 0, "W-methods on a row-partitioned body need tc_set_dist_global_rows");
+    TC_CHECK(!s->has_dist || pcg_mode == TC_PCG_COOP, "a row-partitioned body needs pcg_mode TC_PCG_COOP");
+    s->dist_full_rhs = s->has_dist;
     for (auto& p : s->mor)
         TC_CHECK(p.M.r <= 1024, "a MOR block with r > 1024 cannot be solved implicitly (its CG vectors do not fit shared "
                                 "memory); use an explicit pair for this model");
@@ -1599,7 +1622,12 @@ static int enqueue_ros2_attempt(tc_solver* s) {
     if (enqueue_rhs(s, 1.0, s->ynew, s->K[5])) return -1;
     TcLin Le{};
     Le.nk = 2; Le.k[0] = s->K[1]; Le.c[0] = 0.5; Le.k[1] = s->K[4]; Le.c[1] = 0.5;
-    tc_error_control_kernel<<<G, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    if (s->has_dist) {
+        if (enqueue_dist_norm<0>(s, s->ynew, Le, nullptr, nullptr, nullptr, done)) return -1;
+        tc_dist_control_kernel<<<1, 1, 0, st>>>(s->dist_ex, s->ctrl, s->flags);
+    } else {
+        tc_error_control_kernel<<<G, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    }
     tc_accept_kernel<<<G, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, nullptr, nullptr, s->flags, s->hist_io, s->probe_idx,
                                         s->n_probe);
     tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net, s->y);
@@ -1680,7 +1708,9 @@ __global__ void tc_stage_rhs_kernel(long long n, const double* __restrict__ F, T
 extern "C" int tc_row3_begin(tc_handle s, double t0, double t_end, double rtol, double atol, double max_step,
                              double first_step, double pcg_rtol, int32_t pcg_maxit, int32_t pcg_mode) {
     TC_CHECK(s && s->finalized, "solver not finalized");
-    TC_NO_DIST(s);
+    TC_CHECK(!s->has_dist || s->dist_rows_global > 0, "W-methods on a row-partitioned body need tc_set_dist_global_rows");
+    TC_CHECK(!s->has_dist || pcg_mode == TC_PCG_COOP, "a row-partitioned body needs pcg_mode TC_PCG_COOP");
+    s->dist_full_rhs = s->has_dist;
     for (auto& p : s->mor)
         TC_CHECK(p.M.r <= 1024, "a MOR block with r > 1024 cannot be solved implicitly (its CG vectors do not fit shared "
                                 "memory); use an explicit pair for this model");
@@ -1752,7 +1782,12 @@ static int enqueue_row3_attempt(tc_solver* s) {
     if (enqueue_rhs(s, 1.0, s->ynew, fend)) return -1;
     TcLin Le = Ly;
     Le.c[0] = 0.25290167107671513; Le.c[1] = 0.04754813669718994; Le.c[2] = 0.23046773281334043; Le.c[3] = 0.4960290010539171;
-    tc_error_control_kernel<<<G, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    if (s->has_dist) {
+        if (enqueue_dist_norm<0>(s, s->ynew, Le, nullptr, nullptr, nullptr, done)) return -1;
+        tc_dist_control_kernel<<<1, 1, 0, st>>>(s->dist_ex, s->ctrl, s->flags);
+    } else {
+        tc_error_control_kernel<<<G, 256, 0, st>>>(n, s->y, s->ynew, Le, s->ctrl, s->flags, s->red_partial);
+    }
     tc_accept_kernel<<<G, 256, 0, st>>>(n, s->net.u, s->y, s->ynew, nullptr, nullptr, s->flags, s->hist_io, s->probe_idx,
                                         s->n_probe);
     tc_snapshot_kernel<<<1, 256, 0, st>>>(s->net, s->ctrl, s->flags, s->hist_net, s->y);

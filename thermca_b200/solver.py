@@ -39,8 +39,8 @@ def transient_solution(time_span, net, rel_tol, abs_tol, method, num_skip, **opt
     if method in FIXED_STEP_METHODS and _world_size() > 1 and options.get("partition", True):
         res = _theta_partitioned(spec, t0, t1, num_skip, options)
         return _collector_from(net, spec, res, t0)
-    if method in ("RK45", "RK23") and options.get("partition", False) and _dist_ready():
-        res = _rk_partitioned(spec, t0, t1, rel_tol, abs_tol, method, num_skip, options)
+    if method in ("RK45", "RK23") + IMPLICIT_METHODS and options.get("partition", False) and _dist_ready():
+        res = _adaptive_partitioned(spec, t0, t1, rel_tol, abs_tol, method, num_skip, options)
         return _collector_from(net, spec, res, t0)
     dev = DeviceSolver(spec)
 
@@ -94,15 +94,17 @@ def _world_size():
         return 1
 
 
-def _rk_partitioned(spec, t0, t1, rel_tol, abs_tol, method, num_skip, options):
-    """The reference's own adaptive pairs (``RK45`` / ``RK23``, thermca/solver.py:348-390) under torchrun with
-    ``sim(..., partition=True)``: the largest full-order FE body is row-partitioned as for ``THETA_PCG``, everything else
-    is replicated.  Every right-hand side evaluates the body's ``b - A y`` on the local rows with the neighbours' ghost
-    rows of that stage vector pushed over NVLink inside the product kernel (csrc/dist.cu:tc_dist_residual_kernel);
-    surface means, the error norm and the initial-step norms are sums over all ranks added in rank order
-    (``tc_dist_mean_exchange`` / ``tc_dist_sum_exchange``), so every rank takes bit-identical step decisions and the
-    on-device controller, the attempt graph and the history ring work as on one GPU.  Every rank returns the full
-    result (stored part states gathered once, after the run)."""
+def _adaptive_partitioned(spec, t0, t1, rel_tol, abs_tol, method, num_skip, options):
+    """The adaptive schemes under torchrun with ``sim(..., partition=True)``: the reference's own pairs (``RK45`` /
+    ``RK23``, thermca/solver.py:348-390) and the W-methods that serve ``LSODA`` / ``ROS2_PCG`` / ``ROW3_PCG``.  The
+    largest full-order FE body is row-partitioned as for ``THETA_PCG``, everything else is replicated.  Every right-hand
+    side evaluates the body's ``b - A y`` on the local rows with the neighbours' ghost rows of that stage vector pushed
+    over NVLink inside the product kernel (csrc/dist.cu:tc_dist_residual_kernel); the stage solves of the W-methods run
+    in the solve-only instantiation of the fused peer-memory PCG kernel (``tc_dist_solve``); surface means, the error
+    norm and the initial-step norms are sums over all ranks added in rank order (``tc_dist_mean_exchange`` /
+    ``tc_dist_sum_exchange``), so every rank takes bit-identical step decisions and the on-device controller, the
+    attempt graph and the history ring work as on one GPU.  Every rank returns the full result (stored part states
+    gathered once, after the run)."""
     import torch
     import torch.distributed as dist
     from .dist import DistBody
@@ -124,8 +126,13 @@ def _rk_partitioned(spec, t0, t1, rel_tol, abs_tol, method, num_skip, options):
         body = DistBody(dev.ffe_sell[k], None, info["bounds"], init_temp=None, stream=dev.stream, presplit=presplit)
         dev.attach_partition(k, body)
         dev._cap_width = dev.n_io - int(local["dof"]) + int(np.diff(info["bounds"]).max())     # same ring capacity everywhere
-        res = dev.run_rk(t0, t1, rel_tol, abs_tol, method, num_skip, max_step=options.get("max_step", np.inf),
-                         first_step=options.get("first_step"))
+        if method in IMPLICIT_METHODS:
+            res = dev.run_ros2(t0, t1, rel_tol, abs_tol, num_skip, max_step=options.get("max_step", np.inf),
+                               first_step=options.get("first_step"), pcg_rtol=options.get("pcg_rtol", 1e-8),
+                               scheme=_SCHEME[method])
+        else:
+            res = dev.run_rk(t0, t1, rel_tol, abs_tol, method, num_skip, max_step=options.get("max_step", np.inf),
+                             first_step=options.get("first_step"))
         body.check()
         final_net = dev.network_state()
         off_loc, n_loc = dev.ffe_off[k], int(local["dof"])
