@@ -249,11 +249,12 @@ int tc_dist_mean_exchange(tc_dist* d, double* partials_dev, const int32_t* first
  * ghost rows of v exchanged by peer stores inside the kernel; done_flag_dev (may be NULL): skip when *flag != 0 */
 int tc_dist_residual(tc_dist* d, const double* v_local_dev, double* out_local_dev, const int32_t* done_flag_dev);
 /* stage solve of the W-methods on the partitioned body: z = (I + coef * h A)^-1 rhs on the local rows (the fused
- * Jacobi-PCG kernel without product / commit), h read from *h_dev */
+ * Jacobi-PCG kernel without product / commit), h read from *h_dev; *skip_flag_dev != 0 (may be NULL): leave z as it is */
 int tc_dist_solve(tc_dist* d, double coef, const double* h_dev, const double* rhs_local_dev, double* z_local_dev,
-                  double rtol, int32_t maxit, const int32_t* done_flag_dev);
+                  double rtol, int32_t maxit, const int32_t* skip_flag_dev, const int32_t* done_flag_dev);
 /* vals[j] <- sum over the ranks (rank order, bit-identical everywhere) for k <= 64 doubles on the device */
 int tc_dist_sum_exchange(tc_dist* d, double* vals_dev, int32_t k, const int32_t* done_flag_dev);
+int tc_dist_max_exchange(tc_dist* d, double* vals_dev, int32_t k, const int32_t* done_flag_dev);   /* same with max */
 int32_t tc_dist_rank(tc_dist* d);
 int64_t tc_dist_local_rows(tc_dist* d);
 void* tc_dist_stream(tc_dist* d);

@@ -53,11 +53,6 @@ def main():
         kw = dict(method=method, rel_tol=rtol, abs_tol=1e-7, progress_bar=False, num_res_skip=skip)
         if method not in ("RK45", "RK23"):
             kw["pcg_rtol"] = 1e-12
-            # a partitioned body is always on the implicit branch of the W-methods; put the one-GPU run there too
-            # (otherwise its first attempts, with gamma*h*rho(A) inside the explicit stability interval, stay explicit)
-            os.environ["TC_W_EXPLICIT_BOUND"] = "0"
-        else:
-            os.environ.pop("TC_W_EXPLICIT_BOUND", None)
         # plate_ffe_var has a film towards a stationary node: its rank-one Jacobian term is dropped on a partitioned body
         # (csrc/solver.cu:tc_attach_dist), so the W-methods take other (not fewer accurate) steps than on one GPU there
         same_scheme = not (name == "plate_ffe_var" and method not in ("RK45", "RK23"))

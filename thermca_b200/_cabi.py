@@ -98,7 +98,8 @@ EXPORTS = {
     "tc_dist_residual": (i32, [vp, vp, vp, vp]),
     "tc_dist_sum_exchange": (i32, [vp, vp, i32, vp]),
     "tc_dist_rank": (i32, [vp]),
-    "tc_dist_solve": (i32, [vp, f64, vp, vp, vp, f64, i32, vp]),
+    "tc_dist_solve": (i32, [vp, f64, vp, vp, vp, f64, i32, vp, vp]),
+    "tc_dist_max_exchange": (i32, [vp, vp, i32, vp]),
     "tc_set_dist_global_rows": (i32, [vp, i64]),
     "tc_dist_stream": (vp, [vp]),
     "tc_attach_dist": (i32, [vp, i32, vp, i32, i32]),

@@ -71,6 +71,7 @@ struct TcDistK {
     const double* rhs_in; double* x_out;  // local rows
     const double* h_dev;                  // step size on the device (the controller's), overrides h when non-null
     const int* done;                      // skip the launch when *done != 0
+    const int* skip;                      // stiffness gate: *skip != 0 leaves x_out (= rhs, the explicit branch) untouched
     long long spin_limit;                 // clock64 ticks
     int push_fence;                       // experiment switch (TC_DIST_PUSH_FENCE=1): system fence after ghost pushes
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
@@ -299,7 +300,7 @@ template <int MB, int THREADS = TC_DIST_THREADS, bool SOLVE = false>
 __global__ void __launch_bounds__(THREADS, MB)
 tc_dist_theta_kernel(TcDistK S) {
     __shared__ double sh[32];
-    if (SOLVE && S.done && *S.done) return;              // uniform over the grid and the ranks
+    if (SOLVE && ((S.done && *S.done) || (S.skip && *S.skip))) return;     // uniform over the grid and the ranks
     const int n = S.n;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     unsigned int gen = 0u;
@@ -731,6 +732,7 @@ extern "C" int tc_dist_residual(tc_dist* d, const double* v_local_dev, double* o
 // vals[j] <- sum over the ranks of vals[j], added in rank order (bit-identical on every rank): the error norm and the
 // initial-step norms of the adaptive pairs (scipy rk.py:145-165, common.py:63-134 are means over ALL rows).  Shares the
 // mailbox and the sequence counter of the surface-mean exchange.
+template <int OP>      // 0: sum, 1: max
 __global__ void tc_dist_sum_exchange_kernel(TcDistK S, double* __restrict__ vals, int k, const int* __restrict__ done) {
     if (done && *done) return;
     __shared__ double s_loc[TC_MB2_VALUES];
@@ -747,9 +749,11 @@ __global__ void tc_dist_sum_exchange_kernel(TcDistK S, double* __restrict__ vals
     }
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
         double tot = 0.0;
-        for (int w = 0; w < S.world; ++w)
-            tot += ll_load(S.my_mb2 + ((size_t)par * TC_MAX_WORLD + w) * TC_MB2_SLOT + 2 * j, (unsigned int)seq, err,
-                           S.spin_limit);
+        for (int w = 0; w < S.world; ++w) {
+            const double v = ll_load(S.my_mb2 + ((size_t)par * TC_MAX_WORLD + w) * TC_MB2_SLOT + 2 * j, (unsigned int)seq,
+                                     err, S.spin_limit);
+            tot = OP == 0 ? tot + v : (w == 0 || v > tot || v != v ? v : tot);      // NaN (a failed rank) wins the max
+        }
         vals[j] = tot;
     }
     __syncthreads();
@@ -759,7 +763,14 @@ extern "C" int tc_dist_sum_exchange(tc_dist* d, double* vals_dev, int32_t k, con
     TC_CHECK(k >= 0 && k <= TC_MB2_VALUES, "too many values in one exchange");
     if (k == 0 || d->world == 1) return 0;
     TC_CHECK(d->peers_open, "peers not open");
-    tc_dist_sum_exchange_kernel<<<1, 64, 0, d->stream>>>(d->K, vals_dev, k, done_flag_dev);
+    tc_dist_sum_exchange_kernel<0><<<1, 64, 0, d->stream>>>(d->K, vals_dev, k, done_flag_dev);
+    return 0;
+}
+extern "C" int tc_dist_max_exchange(tc_dist* d, double* vals_dev, int32_t k, const int32_t* done_flag_dev) {
+    TC_CHECK(k >= 0 && k <= TC_MB2_VALUES, "too many values in one exchange");
+    if (k == 0 || d->world == 1) return 0;
+    TC_CHECK(d->peers_open, "peers not open");
+    tc_dist_sum_exchange_kernel<1><<<1, 64, 0, d->stream>>>(d->K, vals_dev, k, done_flag_dev);
     return 0;
 }
 extern "C" int32_t tc_dist_rank(tc_dist* d) { return d->rank; }
@@ -785,12 +796,12 @@ extern "C" int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, dou
 
 // stage solve of a W-method on the partitioned body: z = (I + coef * h A)^-1 rhs on the local rows, h from the device
 extern "C" int tc_dist_solve(tc_dist* d, double coef, const double* h_dev, const double* rhs_local_dev, double* z_local_dev,
-                             double rtol, int32_t maxit, const int32_t* done_flag_dev) {
+                             double rtol, int32_t maxit, const int32_t* skip_flag_dev, const int32_t* done_flag_dev) {
     TC_CHECK(d->K.A.val && d->grid > 0, "operator not set");
     TC_CHECK(d->world == 1 || d->peers_open, "peers not open");
     TcDistK K = d->K;
     K.theta = coef; K.h = 0.0; K.h_dev = h_dev; K.rtol = rtol; K.maxit = maxit;
-    K.rhs_in = rhs_local_dev; K.x_out = z_local_dev; K.done = done_flag_dev;
+    K.rhs_in = rhs_local_dev; K.x_out = z_local_dev; K.done = done_flag_dev; K.skip = skip_flag_dev;
     void* fn = dist_threads() == 512 ? (void*)tc_dist_theta_kernel<4, 512, true>
                : dist_threads() == 256 ? (void*)tc_dist_theta_kernel<8, 256, true> : (void*)tc_dist_theta_kernel<2, 1024, true>;
     void* args[] = {(void*)&K};

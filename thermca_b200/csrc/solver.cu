@@ -1210,7 +1210,7 @@ tc_mor_block_solve_kernel(TcMor M, const double* __restrict__ films, const doubl
 __global__ void __launch_bounds__(256)
 tc_pcg_gate_kernel(long long n, const double* __restrict__ adiag, const double* __restrict__ ctrl, double coef,
                    double bound, double* __restrict__ partial, unsigned int* __restrict__ counter,
-                   int* __restrict__ skip, const int* __restrict__ done) {
+                   int* __restrict__ skip, const int* __restrict__ done, double* __restrict__ gmax_out = nullptr) {
     if (done && *done) return;
     __shared__ double sh[32];
     double m = 0.0;
@@ -1227,9 +1227,15 @@ tc_pcg_gate_kernel(long long n, const double* __restrict__ adiag, const double* 
         if (threadIdx.x == 0) {
             double g = 0.0;
             for (unsigned int b = 0; b < gridDim.x; ++b) g = fmax(g, ((volatile double*)partial)[b]);
-            *skip = (coef * ctrl[1] * 2.0 * g < bound) ? 1 : 0;
+            if (gmax_out) *gmax_out = g;               // row-partitioned body: the decision needs the max over the ranks
+            else *skip = (coef * ctrl[1] * 2.0 * g < bound) ? 1 : 0;
         }
     }
+}
+__global__ void tc_gate_decide_kernel(const double* __restrict__ gmax, const double* __restrict__ ctrl, double coef,
+                                      double bound, int* __restrict__ skip, const int* __restrict__ done) {
+    if (done && *done) return;
+    *skip = (coef * ctrl[1] * 2.0 * gmax[0] < bound) ? 1 : 0;
 }
 
 // w_method: the caller tolerates an inexact Jacobian (ROS2), so temperature dependent bodies are solved with
@@ -1271,9 +1277,17 @@ static int enqueue_block_solve(tc_solver* s, double coef, const double* rhs, dou
             // row-partitioned body.  theta steps: advanced by the fused kernel of dist.cu (tc_theta_steps).  W-methods:
             // the stage solve runs in the solve-only instantiation of that kernel across the GPUs, always implicit
             if (w_method) {
-                if (tc_dist_solve(p.dist, coef, s->ctrl + CT_H, rhs + p.d.y_off, z + p.d.y_off, s->pcg_rtol, s->pcg_maxit, done))
+                // stiffness gate as for the other blocks, on the largest diagonal entry over ALL ranks (rank-uniform flag)
+                int* flag = s->gate_flags + gate_ix++;
+                tc_pcg_gate_kernel<<<grid_for(p.d.n, 256, 256), 256, 0, st>>>(p.d.n, p.d.adiag, s->ctrl, coef, s->w_bound,
+                                                                              s->gate_partial, s->gate_counter, flag, done,
+                                                                              s->dist_ex + 4);
+                if (tc_dist_max_exchange(p.dist, s->dist_ex + 4, 1, done)) return -1;
+                tc_gate_decide_kernel<<<1, 1, 0, st>>>(s->dist_ex + 4, s->ctrl, coef, s->w_bound, flag, done);
+                if (tc_dist_solve(p.dist, coef, s->ctrl + CT_H, rhs + p.d.y_off, z + p.d.y_off, s->pcg_rtol, s->pcg_maxit,
+                                  flag, done))
                     return -1;
-                s->launches += 1;
+                s->launches += 4;
             }
             continue;
         }
