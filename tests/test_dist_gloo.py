@@ -179,3 +179,55 @@ def test_even_row_bounds():
     assert b[0] == 0 and b[-1] == 1000 and all(v % 32 == 0 for v in b[:-1])
     with pytest.raises(ValueError):
         even_row_bounds(40, 4)
+
+
+def _worker_adaptive(rank, world, port, out_dir):
+    """Host-side bookkeeping of the adaptive schemes on a partitioned body (csrc/solver.cu tc_dist_norm_* +
+    csrc/dist.cu tc_dist_sum_exchange, thermca_b200.partition.gather_stored_rows): (a) the class-split, rank-ordered
+    error norm equals scipy's rms norm over the GLOBAL state (scipy rk.py:145-165) and is bit-identical on every rank;
+    (b) stored rank-local rows are completed over the ranks and returned in the caller's DOF order."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from thermca_b200.partition import gather_stored_rows
+    rng = np.random.default_rng(3)
+    n_a, n_b, n_body = 5, 7, 32 * 9 + 11                    # replicated entries before / after the body
+    bounds = even_row_bounds(n_body, world)
+    perm = rng.permutation(n_body)                           # caller's order -> partition order
+    inv = np.empty(n_body, dtype=np.int64)
+    inv[perm] = np.arange(n_body)
+    m = 4                                                    # stored steps
+    glob = rng.standard_normal((m, n_a + n_body + n_b))      # caller's layout [repl | body | repl]
+    body_part = glob[:, n_a:n_a + n_body][:, perm]           # partition order
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    io_loc = np.concatenate([glob[:, :n_a], body_part[:, r0:r1], glob[:, n_a + n_body:]], axis=1)
+    sizes = [int(bounds[w + 1] - bounds[w]) for w in range(world)]
+    back = gather_stored_rows(io_loc, n_a, r1 - r0, sizes, inv)
+    assert np.array_equal(back, glob)
+    # (a) error norm of one attempt: e = err / scale per entry
+    e_glob = glob[0]
+    e_loc = io_loc[0]
+    lo, hi = n_a, n_a + (r1 - r0)
+    cls_body = float(np.sum(e_loc[lo:hi] ** 2))
+    cls_repl = float(np.sum(e_loc[:lo] ** 2) + np.sum(e_loc[hi:] ** 2))
+    mine = torch.tensor([cls_body + (cls_repl if rank == 0 else 0.0),
+                         float((r1 - r0) + (n_a + n_b if rank == 0 else 0))], dtype=torch.float64)
+    allv = [torch.empty(2, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    tot, cnt = 0.0, 0.0
+    for w in range(world):                                   # rank order, as the device exchange adds them
+        tot += float(allv[w][0]); cnt += float(allv[w][1])
+    err = np.sqrt(tot) / np.sqrt(cnt)
+    assert cnt == e_glob.size
+    assert abs(err - np.linalg.norm(e_glob) / np.sqrt(e_glob.size)) <= 1e-15 * err
+    errs = [None] * world
+    dist.all_gather_object(errs, err.hex() if hasattr(err, "hex") else float(err).hex())
+    assert len(set(errs)) == 1                               # identical decisions on every rank
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_adaptive_bookkeeping(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_worker_adaptive, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}.npy").exists() for r in range(world))

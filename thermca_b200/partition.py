@@ -145,3 +145,25 @@ def choose_partitioned_part(spec, min_dof=0):
         if p.get("tdep") is None and int(p["dof"]) > best_n:
             best, best_n = k, int(p["dof"])
     return best
+
+
+def gather_stored_rows(io_loc, a, n_loc, sizes, inv, device=None):
+    """Stored part states of a partitioned adaptive run, rank-local -> global.  ``io_loc`` (stored steps x local part
+    state) holds this rank's rows of the partitioned body in columns ``[a, a + n_loc)`` (partition order) between the
+    replicated parts; returns the rows with the body completed over all ranks (``sizes`` rows per rank) and put back
+    into the caller's DOF order (``inv``: global partition order -> caller's order, partition.localize_ffe_part).  The
+    number of stored steps is the same on every rank (all ranks take bit-identical step decisions)."""
+    import torch
+    import torch.distributed as dist
+    m = io_loc.shape[0]
+    mine = torch.from_numpy(np.ascontiguousarray(io_loc[:, a: a + n_loc].T))          # rows of the body x steps
+    if device is not None:
+        mine = mine.to(device)
+    widest = int(max(sizes))                                    # equal-sized pieces: every backend gathers those
+    padded = torch.zeros((widest, m), dtype=torch.float64, device=mine.device)
+    padded[:n_loc] = mine
+    parts = [torch.empty((widest, m), dtype=torch.float64, device=mine.device) for _ in sizes]
+    dist.all_gather(parts, padded)
+    order = torch.from_numpy(np.asarray(inv, dtype=np.int64)).to(mine.device)
+    body = torch.cat([p[:int(sz)] for p, sz in zip(parts, sizes)], dim=0)[order].T.cpu().numpy()
+    return np.concatenate([io_loc[:, :a], body, io_loc[:, a + n_loc:]], axis=1)

@@ -137,14 +137,8 @@ def _adaptive_partitioned(spec, t0, t1, rel_tol, abs_tol, method, num_skip, opti
         final_net = dev.network_state()
         off_loc, n_loc = dev.ffe_off[k], int(local["dof"])
         sizes = [int(info["bounds"][w + 1] - info["bounds"][w]) for w in range(world)]
-        io = res["io_temps"]
-        m, a = io.shape[0], off_loc - u
-        mine = torch.from_numpy(np.ascontiguousarray(io[:, a: a + n_loc].T)).to(dev.dev)        # rows of the body x steps
-        parts = [torch.empty((sz, m), dtype=torch.float64, device=dev.dev) for sz in sizes]
-        dist.all_gather(parts, mine)
-        inv = torch.from_numpy(info["inv"]).to(dev.dev)
-        body_glob = torch.cat(parts, dim=0)[inv].T.cpu().numpy()                                # caller's DOF order
-        res["io_temps"] = np.concatenate([io[:, :a], body_glob, io[:, a + n_loc:]], axis=1)
+        from .partition import gather_stored_rows
+        res["io_temps"] = gather_stored_rows(res["io_temps"], off_loc - u, n_loc, sizes, info["inv"], dev.dev)
     finally:
         torch.cuda.synchronize()
         if body is not None:
