@@ -268,6 +268,11 @@ int tc_dist_set_state(tc_dist* d, const double* y_local_dev);
 int tc_dist_get_state(tc_dist* d, double* y_local_dev);          /* fails (-3/-4) if a step since the last reset failed */
 int tc_dist_copy_state_async(tc_dist* d, double* y_local_dev, int32_t dir);   /* enqueue only: 0 set, 1 get */
 int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, double h, double rtol, int32_t maxit);
+/* PCG formulation of tc_dist_theta_steps (the same on every rank): 0 = classic (two reductions and a barrier per
+ * iteration), 1 = pipelined (Ghysels-Vanroose recurrences fused into the product sweep: ONE sweep and ONE reduction per
+ * iteration; pays under strong scaling, few rows per GPU).  -2 when the body cannot be served by the pipelined kernel. */
+int tc_dist_set_pcg(tc_dist* d, int32_t mode);
+int32_t tc_dist_get_pcg(tc_dist* d);
 int tc_dist_check(tc_dist* d);                                   /* synchronises; 0, -3 or -4 */
 int tc_dist_reset_error(tc_dist* d);
 /* iters_last, iters_total, comm error flag, solves + 1e6 * grid, failed solves, ghosts that were waited for

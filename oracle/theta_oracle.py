@@ -98,3 +98,87 @@ def theta_cg_steps(A, mass, b, y, nsteps, h, theta=0.5, rtol=1e-8, maxit=2000, b
             rho = rho_new
         y = y + h * x
     return y, iters, time.perf_counter() - t0
+
+
+def theta_pipecg_steps(A, mass, b, y, nsteps, h, theta=0.5, rtol=1e-8, maxit=2000):
+    """CPU restatement of the PIPELINED Jacobi-PCG of csrc/dist.cu (``tc_dist_theta_pipe_kernel``): the recurrences of
+    Ghysels & Vanroose (Parallel Computing 40, 2014, Alg. 4) in Jacobi-scaled variables
+    u = D r, wh = D w, zh = D z, q = D s with B = D (M + theta h K) = c o (I + theta h A):
+    one operator sweep and ONE reduction (gamma, delta, r.r) per iteration.  Mathematically the same iterates as
+    ``theta_cg_steps``.  Returns (y, total iterations, seconds)."""
+    A = sp.csr_matrix(A)
+    shift = theta * h
+    t = 1.0 + shift * A.diagonal()
+    g = mass * t                      # 1 / d
+    c = 1.0 / t
+    iters = 0
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        f = b - A @ y
+        u = (mass * f) / g
+        x = np.zeros_like(y)
+        wh = c * (u + shift * (A @ u))
+        zh = np.zeros_like(y); q = np.zeros_like(y); p = np.zeros_like(y)
+        gu = g * u
+        gamma, delta, bb = u @ gu, wh @ gu, gu @ gu
+        tol2 = rtol * rtol * bb
+        gamma_old = alpha_old = 0.0
+        if bb > 0.0:
+            for it in range(maxit):
+                if it == 0:
+                    beta, alpha = 0.0, gamma / delta
+                else:
+                    beta = gamma / gamma_old
+                    alpha = gamma / (delta - beta * gamma / alpha_old)
+                nh = c * (wh + shift * (A @ wh))
+                zh = nh + beta * zh
+                q = wh + beta * q
+                p = u + beta * p
+                x += alpha * p
+                u = u - alpha * q
+                wh = wh - alpha * zh
+                gu = g * u
+                iters += 1
+                gamma_old, alpha_old = gamma, alpha
+                gamma, delta, rr = u @ gu, wh @ gu, gu @ gu
+                if not rr > tol2:
+                    break
+        y = y + h * x
+    return y, iters, time.perf_counter() - t0
+
+
+def theta_srcg_steps(A, mass, b, y, nsteps, h, theta=0.5, rtol=1e-8, maxit=2000):
+    """CPU restatement of the SINGLE-REDUCTION Jacobi-PCG of csrc/dist.cu (``tc_dist_theta_sr_kernel``): the classic
+    iterates, with all inner products of an iteration taken from the product sweep (p.q, r.Dr, r.Dq, q.Dq, r.r, r.q,
+    q.q) and rho', r'.r' expanded from them (D'Azevedo, Eijkhout & Romine 1993), so the iteration has one reduction.
+    Returns (y, total iterations, seconds)."""
+    A = sp.csr_matrix(A)
+    shift = theta * h
+    d = 1.0 / (mass * (1.0 + shift * A.diagonal()))
+    iters = 0
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        f = b - A @ y
+        r = mass * f
+        x = np.zeros_like(y)
+        p = d * r
+        tol2 = None
+        for it in range(maxit):
+            q = mass * (p + shift * (A @ p))
+            dr, dq = d * r, d * q
+            pq, rho, rdq, qdq, rr, rq, qq = p @ q, r @ dr, r @ dq, q @ dq, r @ r, r @ q, q @ q
+            if tol2 is None:
+                tol2 = rtol * rtol * rr
+                if not rr > 0.0:
+                    break
+            alpha = rho / pq
+            rho_new = rho - 2.0 * alpha * rdq + alpha * alpha * qdq
+            rr_new = rr - 2.0 * alpha * rq + alpha * alpha * qq
+            x += alpha * p
+            iters += 1
+            if not rr_new > tol2:
+                break
+            r -= alpha * q
+            p = d * r + (rho_new / rho) * p
+        y = y + h * x
+    return y, iters, time.perf_counter() - t0

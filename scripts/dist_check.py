@@ -27,21 +27,35 @@ def main():
     nx, ny, nz = 20, 16 * world - 1, 6
     # ---- (a) cuboid slabs ------------------------------------------------------------------------
     dc = DistCuboid(nx, ny, nz)
-    dc.theta_steps(steps, 1.0, 0.5, rtol=rtol, sync=True)
-    st = dc.stats()
-    y_loc = dc.get_state().cpu().numpy()
     spec = device_cuboid_spec(nx, ny, nz)
     ref = DeviceSolver(spec)
     ref.theta_steps(steps, 1.0, 0.5, t0=0.0, pcg_rtol=rtol)
     y_full = ref.get_state()
     pst = ref.pcg_stats()
-    y_ref = y_full[dc.row_begin: dc.row_begin + dc.n]
-    err_a = float(np.max(np.abs(y_loc - y_ref) / np.abs(y_ref)))
-    e_d, n_d = dc.global_sums()
-    ok = err_a < 1e-9 and st["error"] == 0 and st["failed_solves"] == 0 and st["iters_total"] == pst["iterations"]
-    print(f"[cuboid] rank {rank}/{world}: rows [{dc.row_begin},{dc.row_begin + dc.n}) ghosts {dc.n_ghost} "
-          f"boundary slices {dc.n_bnd} neighbours {list(dc.plan[3])} iters {st['iters_total']} (single GPU "
-          f"{pst['iterations']}) max rel err {err_a:.3e}", flush=True)
+    ok, err_by_mode, iters_by_mode = True, {}, {}
+    # the PCG formulations of the fused kernel: classic (same arithmetic as the single-GPU kernel: identical iteration
+    # counts), pipelined (one sweep + one reduction per iteration) and single-reduction (one all-reduce of seven sums +
+    # a local barrier per iteration); the latter two round differently: counts within one per step
+    for mode in ("classic", "pipe", "sr"):
+        assert dc.set_pcg(mode) == mode
+        dc.set_state(torch.full((dc.n,), 20.0, dtype=torch.float64, device="cuda"))
+        it0 = dc.stats()["iters_total"]
+        dc.theta_steps(steps, 1.0, 0.5, rtol=rtol, sync=True)
+        st = dc.stats()
+        iters = st["iters_total"] - it0
+        y_loc = dc.get_state().cpu().numpy()
+        y_ref = y_full[dc.row_begin: dc.row_begin + dc.n]
+        err_a = float(np.max(np.abs(y_loc - y_ref) / np.abs(y_ref)))
+        e_d, n_d = dc.global_sums()
+        slack = 0 if mode == "classic" else steps
+        ok = ok and err_a < 1e-9 and st["error"] == 0 and st["failed_solves"] == 0 and abs(iters - pst["iterations"]) <= slack
+        err_by_mode[mode], iters_by_mode[mode] = err_a, iters
+        if not ok:
+            print(f"[cuboid/{mode}] rank {rank}: CHECK FAILED err {err_a:.3e} stats {st} iters {iters} vs {pst['iterations']}", flush=True)
+        print(f"[cuboid/{mode}] rank {rank}/{world}: rows [{dc.row_begin},{dc.row_begin + dc.n}) ghosts {dc.n_ghost} "
+              f"boundary slices {dc.n_bnd} neighbours {list(dc.plan[3])} iters {iters} (single GPU "
+              f"{pst['iterations']}) max rel err {err_a:.3e}", flush=True)
+    err_a = max(err_by_mode.values())
     # ---- (b) a body handed over as host CSR in a scrambled order -----------------------------------
     op = spec["ffe"][0]["sell"]
     A = sell_to_csr_host(op).tocsr()
@@ -55,13 +69,21 @@ def main():
     scr = np.random.default_rng(3).permutation(n)                    # the caller's DOF order
     A_s = A[scr][:, scr].tocsr()
     body = DistBody.from_csr(A_s, mass[scr], b[scr], init_temp=20.0)
-    body.theta_steps(steps, 1.0, 0.5, rtol=rtol, sync=True)
-    y_body = body.gather_state().cpu().numpy()                       # caller's order
-    err_b = float(np.max(np.abs(y_body - y_full[scr]) / np.abs(y_full[scr])))
-    stb = body.stats()
-    ok = ok and err_b < 1e-9 and stb["error"] == 0 and stb["failed_solves"] == 0
-    print(f"[csr body] rank {rank}/{world}: rows {body.n} ghosts {body.n_ghost} boundary slices {body.n_bnd} "
-          f"neighbours {list(body.plan[3])} iters {stb['iters_total']} max rel err {err_b:.3e}", flush=True)
+    err_b = 0.0
+    for mode in ("classic", "pipe", "sr"):
+        assert body.set_pcg(mode) == mode
+        body.set_global_state(torch.full((n,), 20.0, dtype=torch.float64, device="cuda"))
+        it0 = body.stats()["iters_total"]
+        body.theta_steps(steps, 1.0, 0.5, rtol=rtol, sync=True)
+        y_body = body.gather_state().cpu().numpy()                       # caller's order
+        err_m = float(np.max(np.abs(y_body - y_full[scr]) / np.abs(y_full[scr])))
+        stb = body.stats()
+        ok = ok and err_m < 1e-9 and stb["error"] == 0 and stb["failed_solves"] == 0
+        err_b = max(err_b, err_m)
+        if not ok:
+            print(f"[csr body/{mode}] rank {rank}: CHECK FAILED err {err_m:.3e} stats {stb}", flush=True)
+        print(f"[csr body/{mode}] rank {rank}/{world}: rows {body.n} ghosts {body.n_ghost} boundary slices {body.n_bnd} "
+              f"neighbours {list(body.plan[3])} iters {stb['iters_total'] - it0} max rel err {err_m:.3e}", flush=True)
     ref.close()
     body.close()
     dc.close()
@@ -74,7 +96,8 @@ def main():
         with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
             json.dump({"world": world, "steps": steps, "pcg_rtol": rtol, "cuboid_cells": [nx, ny, nz],
                        "max_rel_err_cuboid_slabs": float(errs[0]), "max_rel_err_csr_body_rcm": float(errs[1]),
-                       "iters_dist": st["iters_total"], "iters_single_gpu": pst["iterations"],
+                       "iters_dist": iters_by_mode, "iters_single_gpu": pst["iterations"],
+                       "max_rel_err_by_pcg_mode": err_by_mode,
                        "energy_sum_M_y": e_d, "ok": not bool(flag.item())}, f)
     if flag.item():
         sys.exit(1)

@@ -92,6 +92,20 @@ def test_theta_oracle_backends_agree():
     assert it_np == it_c
     assert np.allclose(y_np, y_c, rtol=1e-13)
     assert np.allclose(y_np, y_d, rtol=1e-10)
+    # the pipelined formulation (one sweep + one reduction per iteration, csrc/dist.cu) produces the same iterates
+    from theta_oracle import theta_pipecg_steps
+    y_p, it_p, _ = theta_pipecg_steps(A, mass, b, y0, 3, 2.0, rtol=1e-13)
+    assert abs(it_p - it_np) <= 3
+    assert np.allclose(y_p, y_d, rtol=1e-10)
+    y_p8, it_p8, _ = theta_pipecg_steps(A, mass, b, y0, 3, 2.0, rtol=1e-8)
+    _, it_8, _ = theta_cg_steps(A, mass, b, y0, 3, 2.0, rtol=1e-8)
+    assert it_p8 == it_8 and np.allclose(y_p8, y_d, rtol=1e-9)
+    # the single-reduction formulation (all inner products from the product sweep): the classic iterates
+    from theta_oracle import theta_srcg_steps
+    y_s, it_s, _ = theta_srcg_steps(A, mass, b, y0, 3, 2.0, rtol=1e-13)
+    assert abs(it_s - it_np) <= 3 and np.allclose(y_s, y_d, rtol=1e-10)
+    y_s8, it_s8, _ = theta_srcg_steps(A, mass, b, y0, 3, 2.0, rtol=1e-8)
+    assert it_s8 == it_8 and np.allclose(y_s8, y_d, rtol=1e-9)
 
 
 def test_ros2_restatement_converges_to_the_explicit_solution(golden):

@@ -107,6 +107,8 @@ EXPORTS = {
     "tc_dist_get_state": (i32, [vp, vp]),
     "tc_dist_copy_state_async": (i32, [vp, vp, i32]),
     "tc_dist_theta_steps": (i32, [vp, i32, f64, f64, f64, i32]),
+    "tc_dist_set_pcg": (i32, [vp, i32]),
+    "tc_dist_get_pcg": (i32, [vp]),
     "tc_dist_check": (i32, [vp]),
     "tc_dist_reset_error": (i32, [vp]),
     "tc_dist_stats": (i32, [vp, C.POINTER(i64)]),

@@ -31,8 +31,8 @@
 #include "gridbar.cuh"
 
 #define TC_MAX_WORLD 16
-#define TC_DIST_K 3                     // values per all-reduce
-#define TC_MB_SLOT 8                    // u64 granules per (parity, sender) mailbox slot (2 per value, padded to 64 B)
+#define TC_DIST_K 7                     // values per all-reduce (single-reduction PCG: seven sums at once)
+#define TC_MB_SLOT 16                   // u64 granules per (parity, sender) mailbox slot (2 per value, padded to 128 B)
 #define TC_MB2_VALUES 64                // surface means of a partitioned body per exchange (second mailbox region)
 #define TC_MB2_SLOT (2 * TC_MB2_VALUES)
 
@@ -75,6 +75,10 @@ struct TcDistK {
     long long spin_limit;                 // clock64 ticks
     int push_fence;                       // experiment switch (TC_DIST_PUSH_FENCE=1): system fence after ghost pushes
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
+    // pipelined PCG (tc_dist_theta_pipe_kernel): extra vectors and the send lists grouped by boundary slice
+    double *zh, *pv, *cc;                 // D z, search direction, c_i = 1 / (1 + shift a_ii)
+    const int* sptr;                      // n_bnd + 1: send entries of boundary slice b (sorted by lane)
+    const int* s_lane; const int* s_peer; const long long* s_dst;
 };
 
 __device__ __forceinline__ u64 ld_relaxed_sys_u64(const u64* p) {
@@ -121,25 +125,32 @@ __device__ __forceinline__ void ll_peek(const u64* g, u64& lo, u64& hi) {
 // totals.  A rank whose error flag is up contributes NaN: every rank then leaves the iteration in this very reduction.
 // (The variant in which the last-arriving block exchanges and then publishes measured ~5 us more per reduction.)
 // Every wait is bounded; once the error flag is up all waits of this rank return at once, so a failure drains fast.
-template <int K>
-__device__ __forceinline__ void dist_reduce(const TcDistK& S, unsigned int& gen, double* red, int seq) {
+// `work` (optional): split-phase — runs on all threads after the local totals are on their way to the peers and
+// before the block polls its mailbox (one GPU: between the block's arrival and its wait, gridbar.cuh).
+template <int K, class F = TcNoWork>
+__device__ __forceinline__ void dist_reduce(const TcDistK& S, unsigned int& gen, double* red, int seq, F work = F()) {
     int* err = S.state + 4;
-    if (S.world == 1) { tc_grid_reduce<K>(S.bar, gen, red); return; }
+    if (S.world == 1) { tc_grid_reduce<K, (K > 3 ? 1 : 4)>(S.bar, gen, red, nullptr, 0, work); return; }
     tc_grid_reduce<K>(S.bar, gen, red, err, S.spin_limit);
     __shared__ double s_in[TC_MAX_WORLD][TC_DIST_K];
     __shared__ double s_out[TC_DIST_K];
     const int par = seq & 1;
-    if ((int)threadIdx.x < S.world) {
-        const int peer = threadIdx.x;
-        if (blockIdx.x == 0) {
-            const bool bad = *((volatile int*)err) != 0;
-            u64* out = S.peer_mb[peer] + ((size_t)par * TC_MAX_WORLD + S.rank) * TC_MB_SLOT;
+    if (threadIdx.x == 0) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) ll_store(out + 2 * k, bad ? nan("") : red[k], (unsigned int)seq);
-        }
+        for (int k = 0; k < K; ++k) s_out[k] = red[k];
+    }
+    __syncthreads();
+    const bool mine = (int)threadIdx.x < S.world * K;             // one thread per (peer, value): all waits run side by side
+    const int peer = threadIdx.x / K, k = threadIdx.x - peer * K;
+    if (mine && blockIdx.x == 0) {
+        const bool bad = *((volatile int*)err) != 0;
+        u64* out = S.peer_mb[peer] + ((size_t)par * TC_MAX_WORLD + S.rank) * TC_MB_SLOT;
+        ll_store(out + 2 * k, bad ? nan("") : s_out[k], (unsigned int)seq);
+    }
+    work();                                                       // hidden behind the NVLink flight and the rank skew
+    if (mine) {
         const u64* in = S.my_mb + ((size_t)par * TC_MAX_WORLD + peer) * TC_MB_SLOT;
-#pragma unroll
-        for (int k = 0; k < K; ++k) s_in[peer][k] = ll_load(in + 2 * k, (unsigned int)seq, err, S.spin_limit);
+        s_in[peer][k] = ll_load(in + 2 * k, (unsigned int)seq, err, S.spin_limit);
     }
     __syncthreads();
     if ((int)threadIdx.x < K) {
@@ -188,8 +199,35 @@ __device__ __noinline__ double ghost_part(const long long* gptr, const int* gslo
     return sum;
 }
 
+// Matrix streams with an L2 evict-first policy (EF): when the vectors of a rank fit into the 126 MB L2 (strong
+// scaling: ~1 M rows per GPU) the operator must not push them out, it is read exactly once per sweep.
+__device__ __forceinline__ u64 l2_evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <bool EF> __device__ __forceinline__ double ldm_f64(const double* p, u64 pol) {
+    if (!EF) return ld_stream_f64(p);
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <bool EF> __device__ __forceinline__ int ldm_s16(const short* p, u64 pol) {
+    if (!EF) return ld_stream_s16(p);
+    short v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return (int)v;
+}
+template <bool EF> __device__ __forceinline__ int ldm_s32(const int* p, u64 pol) {
+    if (!EF) return ld_stream_s32(p);
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 // sum_k A[row][k] x[col] over the LOCAL columns of one slice (one row per lane), entries in stored order, no FMA
-__device__ __forceinline__ double slice_local_sum(const TcSell& A, const double* xl, int s, int lane) {
+template <bool EF = false>
+__device__ __forceinline__ double slice_local_sum(const TcSell& A, const double* xl, int s, int lane, u64 pol = 0ULL) {
     const long long base = A.slice_ptr[s];
     const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
     const double* v = A.val + base + lane;
@@ -199,10 +237,10 @@ __device__ __forceinline__ double slice_local_sum(const TcSell& A, const double*
         const double* xr0 = xl + (s * 32 + lane);
         int k = 0;
         for (; k + 4 <= width; k += 4) {
-            const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
-            const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
-            const int c0 = ld_stream_s16(c + 32 * (k + 0)), c1 = ld_stream_s16(c + 32 * (k + 1));
-            const int c2 = ld_stream_s16(c + 32 * (k + 2)), c3 = ld_stream_s16(c + 32 * (k + 3));
+            const double v0 = ldm_f64<EF>(v + 32 * (k + 0), pol), v1 = ldm_f64<EF>(v + 32 * (k + 1), pol);
+            const double v2 = ldm_f64<EF>(v + 32 * (k + 2), pol), v3 = ldm_f64<EF>(v + 32 * (k + 3), pol);
+            const int c0 = ldm_s16<EF>(c + 32 * (k + 0), pol), c1 = ldm_s16<EF>(c + 32 * (k + 1), pol);
+            const int c2 = ldm_s16<EF>(c + 32 * (k + 2), pol), c3 = ldm_s16<EF>(c + 32 * (k + 3), pol);
             const double x0 = tc_ld_x<0>(xr0 + c0), x1 = tc_ld_x<0>(xr0 + c1), x2 = tc_ld_x<0>(xr0 + c2), x3 = tc_ld_x<0>(xr0 + c3);
             sum = __dadd_rn(sum, __dmul_rn(v0, x0));
             sum = __dadd_rn(sum, __dmul_rn(v1, x1));
@@ -210,15 +248,15 @@ __device__ __forceinline__ double slice_local_sum(const TcSell& A, const double*
             sum = __dadd_rn(sum, __dmul_rn(v3, x3));
         }
         for (; k < width; ++k)
-            sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xr0 + ld_stream_s16(c + 32 * k))));
+            sum = __dadd_rn(sum, __dmul_rn(ldm_f64<EF>(v + 32 * k, pol), tc_ld_x<0>(xr0 + ldm_s16<EF>(c + 32 * k, pol))));
     } else {
         const int* c = A.col + base + lane;
         int k = 0;
         for (; k + 4 <= width; k += 4) {
-            const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
-            const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
-            const int c0 = ld_stream_s32(c + 32 * (k + 0)), c1 = ld_stream_s32(c + 32 * (k + 1));
-            const int c2 = ld_stream_s32(c + 32 * (k + 2)), c3 = ld_stream_s32(c + 32 * (k + 3));
+            const double v0 = ldm_f64<EF>(v + 32 * (k + 0), pol), v1 = ldm_f64<EF>(v + 32 * (k + 1), pol);
+            const double v2 = ldm_f64<EF>(v + 32 * (k + 2), pol), v3 = ldm_f64<EF>(v + 32 * (k + 3), pol);
+            const int c0 = ldm_s32<EF>(c + 32 * (k + 0), pol), c1 = ldm_s32<EF>(c + 32 * (k + 1), pol);
+            const int c2 = ldm_s32<EF>(c + 32 * (k + 2), pol), c3 = ldm_s32<EF>(c + 32 * (k + 3), pol);
             const double x0 = tc_ld_x<0>(xl + c0), x1 = tc_ld_x<0>(xl + c1), x2 = tc_ld_x<0>(xl + c2), x3 = tc_ld_x<0>(xl + c3);
             sum = __dadd_rn(sum, __dmul_rn(v0, x0));
             sum = __dadd_rn(sum, __dmul_rn(v1, x1));
@@ -226,7 +264,7 @@ __device__ __forceinline__ double slice_local_sum(const TcSell& A, const double*
             sum = __dadd_rn(sum, __dmul_rn(v3, x3));
         }
         for (; k < width; ++k)
-            sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<0>(xl + ld_stream_s32(c + 32 * k))));
+            sum = __dadd_rn(sum, __dmul_rn(ldm_f64<EF>(v + 32 * k, pol), tc_ld_x<0>(xl + ldm_s32<EF>(c + 32 * k, pol))));
     }
     return sum;
 }
@@ -361,7 +399,6 @@ tc_dist_theta_kernel(TcDistK S) {
             const double alpha = rho / pq;
             double rn = 0.0, rr = 0.0;
             for (int i = gtid; i < n; i += gsz) {
-                S.x[i] += alpha * pe[i];
                 const double ri = S.r[i] - alpha * S.q[i];
                 S.r[i] = ri;
                 rn += ri * (S.dinv[i] * ri);
@@ -369,7 +406,11 @@ tc_dist_theta_kernel(TcDistK S) {
             }
             red[0] = block_sum(rn, sh); red[1] = block_sum(rr, sh);
             PROF(4);
-            dist_reduce<2>(S, gen, red, ++rseq);
+            // x += alpha p feeds neither this reduction nor another block: it runs while the block waits for the
+            // slowest rank's sums (split-phase barrier), 3 of the 7 streams of the update phase
+            dist_reduce<2>(S, gen, red, ++rseq, [&]() {
+                for (int i = gtid; i < n; i += gsz) S.x[i] += alpha * pe[i];
+            });
             PROF(5);
             ++it;
             if (!(red[1] > tol2)) { status = isfinite(red[1]) ? 0 : 2; break; }
@@ -396,6 +437,346 @@ tc_dist_theta_kernel(TcDistK S) {
         for (int i = gtid; i < n; i += gsz) S.x_out[i] = status != 2 ? S.x[i] : nan("");
     } else if (status != 2) {
         for (int i = gtid; i < n; i += gsz) S.y[i] += S.h * S.x[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.state[0] = rseq; S.state[1] = (int)hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
+        if (status) { S.state[7] = status; S.state[8] += 1; }
+    }
+}
+
+// ---- pipelined PCG: ONE sweep over the operator and ONE reduction per iteration -------------------------------
+// Strong scaling (10 M rows over 8 GPUs = 1.3 M rows per GPU, 40 us of streaming per iteration) is bounded by the
+// fixed costs of an iteration: the classic form has two all-reduces and a barrier (~25 us) between its three phases.
+// The pipelined conjugate gradients of Ghysels & Vanroose (Parallel Computing 40, 2014) keep, next to the residual
+// recurrences, w = A u and z = A q by recurrences of their own, so BOTH dot products of an iteration come from
+// vectors that are known before the product: they are summed in one reduction.  Here all vector recurrences are
+// fused into the product sweep (every row is updated by the thread that just formed its row sum, the gathered
+// vector is double buffered), which leaves one sweep + one reduce-barrier / all-reduce per iteration at the
+// streamed bytes of the classic form (14 vector streams instead of 13, no separately stored product).
+// Jacobi-scaled variables (D = diag(d), d_i = 1 / (M_i (1 + shift A_ii)) = 1 / g_i):
+//   u = D r,  wh = D w,  zh = D z,  q = D s;   B = D (M + shift K) = c o (I + shift A),  c_i = 1 / (1 + shift A_ii)
+//   per iteration:  nh = B wh;  zh = nh + beta zh;  q = wh + beta q;  p = u + beta p;  x += alpha p;
+//                   u -= alpha q;  wh -= alpha zh;   gamma = sum g u^2,  delta = sum g wh u,  rr = sum (g u)^2
+//   beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)   (first iteration: beta = 0)
+// Same iteration counts and accuracy as the classic form on the cuboid operators (CPU study, oracle/theta_oracle.py
+// theta_pipecg_steps: 34/34, 95/95, 434/434 iterations at h = 1, 10, 100 s; identical error against the direct solver).
+// Ghosts: the warp that forms a boundary row pushes the new wh value straight from its register (per-slice send
+// lists, LL encoded); the boundary slices run first in every warp's sequence (rot), so the values are on their
+// way a whole sweep and a reduction before a peer gathers them.
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
+template <bool FIRST, bool EF>
+__device__ __forceinline__ void pipe_sweep(const TcDistK& S, const double* wo, const u64* wo_g, double* wn, int pbw,
+                                           double alpha, double beta, double shift, unsigned int hread,
+                                           unsigned int hwrite, u64 pol, double* acc) {
+    const TcSell& A = S.A;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * warps_per_block;
+    const int nsl = A.nslices;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int idx = warp; idx < nsl; idx += nwarps) {
+        int s = idx + S.rot;
+        if (s >= nsl) s -= nsl;
+        const int bi = S.n_bnd ? S.bidx[s] : -1;
+        double sum = slice_local_sum<EF>(A, wo, s, lane, pol);
+        if (bi >= 0)
+            sum = __dadd_rn(sum, ghost_part(S.gptr, S.gslot, S.gval, wo_g, bi, lane, hread, S.state, S.spin_limit));
+        const int row = s * 32 + lane;
+        double wnew = 0.0;
+        if (row < A.n) {
+            const double g = S.dinv[row], c = S.cc[row];
+            const double woi = tc_ld_x<0>(wo + row);
+            const double nh = c * (woi + shift * sum);
+            if (FIRST) {                                   // wh_0 = B u_0 (wo holds u_0)
+                wnew = nh;
+                const double gu = g * woi;
+                a0 += woi * gu; a1 += wnew * gu; a2 += gu * gu;
+            } else {
+                const double z = nh + beta * S.zh[row];
+                const double qn = woi + beta * S.q[row];
+                const double uo = S.r[row];
+                const double pn = uo + beta * S.pv[row];
+                S.x[row] += alpha * pn;
+                const double un = uo - alpha * qn;
+                wnew = woi - alpha * z;
+                S.zh[row] = z; S.q[row] = qn; S.pv[row] = pn; S.r[row] = un;
+                const double gu = g * un;
+                a0 += un * gu; a1 += wnew * gu; a2 += gu * gu;
+            }
+            wn[row] = wnew;
+        }
+        if (bi >= 0) {                                     // rows of this slice that peers gather
+            const int e0 = S.sptr[bi], e1 = S.sptr[bi + 1];
+            for (int e = e0; e < e1; e += 32) {
+                const int ee = e + lane;
+                const bool act = ee < e1;
+                const double v = shfl_f64(wnew, act ? S.s_lane[ee] : 0);
+                if (act) ll_store(S.peer_p_gl[pbw][S.s_peer[ee]] + 2 * S.s_dst[ee], v, hwrite);
+            }
+        }
+    }
+    acc[0] = a0; acc[1] = a1; acc[2] = a2;
+}
+
+template <int MB, int THREADS, bool EF>
+__global__ void __launch_bounds__(THREADS, MB)
+tc_dist_theta_pipe_kernel(TcDistK S) {
+    const int n = S.n;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    unsigned int gen = 0u;
+    int rseq = S.state[0];
+    unsigned int hseq = (unsigned int)S.state[1];
+    PROF_INIT();
+    const double shift = S.theta * S.h;
+    const u64 pol = EF ? l2_evict_first_policy() : 0ULL;
+    int* berr = S.world > 1 ? S.state + 4 : nullptr;
+
+    // ---- right-hand side f = b - A y (thermca/solver.py:281) on the local rows -> S.q ---------------------
+    ++hseq;
+    for (long long e = gtid; e < S.n_send; e += gsz)
+        ll_store(S.peer_y_gl[S.send_peer[e]] + 2 * S.send_dst[e], S.y[S.send_row[e]], hseq);
+    slab_spmv<SPMV_B>(S, S.y, S.y_gl, S.q, S.b, 0.0, hseq);
+    tc_grid_barrier(S.bar, gen, berr, S.spin_limit);
+
+    // ---- u_0 = D M f (double-buffer slot 0 + ghosts), coefficient vectors, zeroed recurrences ------------
+    ++hseq;
+    for (long long e = gtid; e < S.n_send; e += gsz) {
+        const int i = S.send_row[e];
+        const double m = S.mass[i];
+        const double g = __dmul_rn(m, __fma_rn(shift, S.adiag[i], 1.0));
+        ll_store(S.peer_p_gl[0][S.send_peer[e]] + 2 * S.send_dst[e], __ddiv_rn(__dmul_rn(m, S.q[i]), g), hseq);
+    }
+    for (int i = gtid; i < n; i += gsz) {
+        const double m = S.mass[i];
+        const double t = __fma_rn(shift, S.adiag[i], 1.0);
+        const double g = __dmul_rn(m, t);
+        const double u0 = __ddiv_rn(__dmul_rn(m, S.q[i]), g);
+        S.r[i] = u0; S.p[0][i] = u0; S.dinv[i] = g; S.cc[i] = __ddiv_rn(1.0, t);
+        S.x[i] = 0.0; S.zh[i] = 0.0; S.q[i] = 0.0; S.pv[i] = 0.0;
+    }
+    tc_grid_barrier(S.bar, gen, berr, S.spin_limit);
+
+    // ---- wh_0 = B u_0 and the first dot products --------------------------------------------------------
+    double red[TC_DIST_K];
+    unsigned int hread = hseq;
+    ++hseq;
+    pipe_sweep<true, EF>(S, S.p[0], S.p_gl[0], S.p[1], 1, 0.0, 0.0, shift, hread, hseq, pol, red);
+    tc_block_sum_k<3>(red);
+    dist_reduce<3>(S, gen, red, ++rseq);
+    hread = hseq;
+    int pb = 1;
+    double gamma = red[0], delta = red[1], gamma_old = 0.0, alpha_old = 0.0;
+    const double bb = red[2];
+    const double tol2 = S.rtol * S.rtol * bb;
+    int it = 0, status = 0;
+    if (bb > 0.0) {
+        status = 1;
+        for (; it < S.maxit;) {
+            PROF(0);
+            double alpha, beta;
+            if (it == 0) { beta = 0.0; alpha = gamma / delta; }
+            else { beta = gamma / gamma_old; alpha = gamma / (delta - beta * gamma / alpha_old); }
+            if (!(alpha > 0.0) || !isfinite(alpha)) { status = 2; break; }     // uniform over the grid AND the ranks
+            ++hseq;
+            pipe_sweep<false, EF>(S, S.p[pb], S.p_gl[pb], S.p[pb ^ 1], pb ^ 1, alpha, beta, shift, hread, hseq, pol, red);
+            PROF(1);
+            tc_block_sum_k<3>(red);
+            PROF(2);
+            dist_reduce<3>(S, gen, red, ++rseq);
+            PROF(3);
+            hread = hseq;
+            pb ^= 1;
+            ++it;
+            if (!(red[2] > tol2)) { status = isfinite(red[2]) ? 0 : 2; break; }
+            gamma_old = gamma; alpha_old = alpha;
+            gamma = red[0]; delta = red[1];
+        }
+    }
+    // ---- y += h * z (not committed after a communication failure / breakdown) ----------------------------
+    if (status != 2)
+        for (int i = gtid; i < n; i += gsz) S.y[i] += S.h * S.x[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.state[0] = rseq; S.state[1] = (int)hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
+        if (status) { S.state[7] = status; S.state[8] += 1; }
+    }
+}
+
+// ---- single-reduction classic PCG: ONE all-reduce and one local barrier per iteration -------------------------------
+// The iterates of the classic form (same alpha, beta up to rounding) with both of its reductions taken in ONE: the sums
+//   p.q,  rho = r.Dr,  r.Dq,  q.Dq,  r.r,  r.q,  q.q
+// are all known once q = (M + shift K) p has been formed, and they give the scalars of the whole iteration:
+//   alpha = rho / p.q,   rho' = rho - 2 alpha r.Dq + alpha^2 q.Dq = r'.Dr',   r'.r' = r.r - 2 alpha r.q + alpha^2 q.q,
+//   beta = rho' / rho
+// (the recurrences for the inner products are those of D'Azevedo, Eijkhout & Romine, LAPACK working note 56, 1993; rho
+// and r.r are summed afresh from the vectors in every sweep, only beta and the stopping test use the expanded forms, so
+// nothing drifts).  The product sweep reads r and d next to the operator (2 more streams), and the update and direction
+// phases of the classic kernel merge into one vector phase (x += alpha p; r -= alpha q; p' = D r + beta p: 8 streams
+// instead of 7 + 4), run by the thread that owns the row in the sweep: the owner of a boundary row pushes p' to the
+// peers straight from its register.  Per iteration: sweep -> all-reduce of 7 -> vector phase -> local barrier, i.e. one
+// all-reduce less than the classic kernel at fewer streamed bytes.  CPU study (oracle/theta_oracle.py theta_srcg_steps):
+// identical iteration counts and errors against the direct solver for h = 1 .. 100 s, rtol 1e-8 .. 1e-12.
+template <bool EF>
+__device__ __forceinline__ void sr_sweep(const TcDistK& S, const double* pe, const u64* pe_g, unsigned int hread,
+                                         double shift, u64 pol, double* acc) {
+    const TcSell& A = S.A;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * warps_per_block;
+    const int nsl = A.nslices;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0;
+    for (int idx = warp; idx < nsl; idx += nwarps) {
+        int s = idx + S.rot;
+        if (s >= nsl) s -= nsl;
+        const int bi = S.n_bnd ? S.bidx[s] : -1;
+        double sum = slice_local_sum<EF>(A, pe, s, lane, pol);
+        if (bi >= 0)
+            sum = __dadd_rn(sum, ghost_part(S.gptr, S.gslot, S.gval, pe_g, bi, lane, hread, S.state, S.spin_limit));
+        const int row = s * 32 + lane;
+        if (row < A.n) {
+            const double pi = tc_ld_x<0>(pe + row);
+            const double q = S.mass[row] * (pi + shift * sum);
+            S.q[row] = q;
+            const double r = S.r[row], d = S.dinv[row];
+            const double dr = d * r, dq = d * q;
+            a0 += pi * q; a1 += r * dr; a2 += r * dq; a3 += q * dq; a4 += r * r; a5 += r * q; a6 += q * q;
+        }
+    }
+    acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3; acc[4] = a4; acc[5] = a5; acc[6] = a6;
+}
+
+// x += alpha p; r -= alpha q; p' = D r + beta p (written to the other buffer and pushed to the peers that gather it).
+// LAST: the iteration ends here, no new direction; !SOLVE: y += h x is committed in the same pass.
+template <bool LAST, bool SOLVE>
+__device__ __forceinline__ void sr_vector_phase(const TcDistK& S, const double* pe, double* pn, int pbw, double alpha,
+                                                double beta, unsigned int hwrite, bool commit) {
+    const TcSell& A = S.A;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * warps_per_block;
+    const int nsl = A.nslices;
+    for (int idx = warp; idx < nsl; idx += nwarps) {
+        int s = idx + S.rot;
+        if (s >= nsl) s -= nsl;
+        const int row = s * 32 + lane;
+        double pnew = 0.0;
+        if (row < A.n) {
+            const double pi = pe[row];
+            const double xn = S.x[row] + alpha * pi;
+            if (LAST) {                                   // a failed solve leaves NaN (SOLVE) / an untouched state
+                if (SOLVE) S.x_out[row] = commit ? xn : nan("");
+                else if (commit) S.y[row] += S.h * xn;
+            } else {
+                S.x[row] = xn;
+                const double rn = S.r[row] - alpha * S.q[row];
+                S.r[row] = rn;
+                pnew = __fma_rn(beta, pi, __dmul_rn(S.dinv[row], rn));
+                pn[row] = pnew;
+            }
+        }
+        if (!LAST && S.n_bnd) {
+            const int bi = S.bidx[s];
+            if (bi >= 0) {
+                const int e0 = S.sptr[bi], e1 = S.sptr[bi + 1];
+                for (int e = e0; e < e1; e += 32) {
+                    const int ee = e + lane;
+                    const bool act = ee < e1;
+                    const double v = shfl_f64(pnew, act ? S.s_lane[ee] : 0);
+                    if (act) ll_store(S.peer_p_gl[pbw][S.s_peer[ee]] + 2 * S.s_dst[ee], v, hwrite);
+                }
+            }
+        }
+    }
+}
+
+template <int MB, int THREADS, bool EF, bool SOLVE = false>
+__global__ void __launch_bounds__(THREADS, MB)
+tc_dist_theta_sr_kernel(TcDistK S) {
+    if (SOLVE && ((S.done && *S.done) || (S.skip && *S.skip))) return;     // uniform over the grid and the ranks
+    const int n = S.n;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    unsigned int gen = 0u;
+    int rseq = S.state[0];
+    unsigned int hseq = (unsigned int)S.state[1];
+    PROF_INIT();
+    const double hstep = (SOLVE && S.h_dev) ? *S.h_dev : S.h;
+    const double shift = S.theta * hstep;
+    const u64 pol = EF ? l2_evict_first_policy() : 0ULL;
+    int* berr = S.world > 1 ? S.state + 4 : nullptr;
+    const double* f = SOLVE ? S.rhs_in : S.q;
+
+    // ---- right-hand side f = b - A y (thermca/solver.py:281) on the local rows ----------------------------
+    if (!SOLVE) {
+        ++hseq;
+        for (long long e = gtid; e < S.n_send; e += gsz)
+            ll_store(S.peer_y_gl[S.send_peer[e]] + 2 * S.send_dst[e], S.y[S.send_row[e]], hseq);
+        slab_spmv<SPMV_B>(S, S.y, S.y_gl, S.q, S.b, 0.0, hseq);
+        tc_grid_barrier(S.bar, gen, berr, S.spin_limit);
+    }
+    // ---- r_0 = M f, d, p_0 = D r_0 (+ ghosts, recomputed from the same stable inputs: bit-identical) ------
+    ++hseq;
+    for (long long e = gtid; e < S.n_send; e += gsz) {
+        double bsc, d;
+        init_row(S, f, S.send_row[e], shift, bsc, d);
+        ll_store(S.peer_p_gl[0][S.send_peer[e]] + 2 * S.send_dst[e], __dmul_rn(d, bsc), hseq);
+    }
+    for (int i = gtid; i < n; i += gsz) {
+        double bsc, d;
+        init_row(S, f, i, shift, bsc, d);
+        S.r[i] = bsc; S.x[i] = 0.0; S.dinv[i] = d; S.p[0][i] = __dmul_rn(d, bsc);
+    }
+    tc_grid_barrier(S.bar, gen, berr, S.spin_limit);
+
+    double red[TC_DIST_K];
+    int pb = 0, it = 0, status = 1;
+    bool consumed = false;                           // the last vector phase has already committed x
+    double tol2 = 0.0;
+    for (;;) {
+        PROF(0);
+        sr_sweep<EF>(S, S.p[pb], S.p_gl[pb], hseq, shift, pol, red);
+        PROF(1);
+        tc_block_sum_k<7>(red);
+        PROF(2);
+        dist_reduce<7>(S, gen, red, ++rseq);
+        PROF(3);
+        const double pq = red[0], rho = red[1], rr = red[4];
+        if (it == 0) {
+            tol2 = S.rtol * S.rtol * rr;
+            if (!(rr > 0.0)) { status = isfinite(rr) ? 0 : 2; break; }           // zero right-hand side: x = 0
+        }
+        if (!(pq > 0.0) || !isfinite(pq)) { status = 2; break; }                // uniform over the grid AND the ranks
+        const double alpha = rho / pq;
+        const double rho_new = rho - 2.0 * alpha * red[2] + alpha * alpha * red[3];
+        const double rr_new = rr - 2.0 * alpha * red[5] + alpha * alpha * red[6];
+        ++it;
+        const bool conv = !(rr_new > tol2);
+        if (conv || it >= S.maxit) {
+            status = conv ? (isfinite(rr_new) ? 0 : 2) : 1;
+            sr_vector_phase<true, SOLVE>(S, S.p[pb], nullptr, 0, alpha, 0.0, 0u, status != 2);
+            PROF(4);
+            consumed = true;
+            break;
+        }
+        const double beta = rho_new / rho;
+        ++hseq;
+        sr_vector_phase<false, SOLVE>(S, S.p[pb], S.p[pb ^ 1], pb ^ 1, alpha, beta, hseq, false);
+        pb ^= 1;
+        PROF(4);
+        tc_grid_barrier(S.bar, gen, berr, S.spin_limit);
+        PROF(7);
+    }
+    if (!consumed) {
+        // left before a vector phase consumed x: zero right-hand side (x = 0) or a breakdown
+        if (SOLVE) { for (int i = gtid; i < n; i += gsz) S.x_out[i] = status != 2 ? S.x[i] : nan(""); }
+        else if (status != 2) { for (int i = gtid; i < n; i += gsz) S.y[i] += S.h * S.x[i]; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         S.state[0] = rseq; S.state[1] = (int)hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
@@ -433,6 +814,15 @@ struct tc_dist {
     int* state = nullptr;
     unsigned long long* prof = nullptr;
     int* send_row = nullptr; int* send_peer = nullptr; long long* send_dst = nullptr;
+    std::vector<int> h_send_row, h_send_peer;      // host copies: regrouped by boundary slice for the pipelined kernel
+    std::vector<long long> h_send_dst;
+    double *zh = nullptr, *pv = nullptr, *cc = nullptr;
+    int *sptr = nullptr, *s_lane = nullptr, *s_peer = nullptr; long long* s_dst = nullptr;
+    int pcg_mode = 0;                 // 0 classic (two reductions + barrier), 1 pipelined (one sweep, one reduction)
+    bool pipe_ok = false;             // every send row lies in a boundary slice (true for symmetric patterns)
+    int pipe_shape = 216, pipe_threads = 512, pipe_grid = 0, rot_pipe = 0;     // shape shared by the pipelined and the
+    int sr_grid = 0, rot_sr = 0;                                                  // single-reduction kernel (TC_PIPE_SHAPE)
+    bool l2_hint = true;
     TcDistK K;
     int grid = 0;
     bool peers_open = false;
@@ -464,6 +854,7 @@ extern "C" int tc_dist_create(tc_dist** out, void* stream, int32_t rank, int32_t
     TC_CUDA(cudaMalloc(&d->y, nb)); TC_CUDA(cudaMalloc(&d->p0, nb)); TC_CUDA(cudaMalloc(&d->p1, nb));
     TC_CUDA(cudaMalloc(&d->x, nb)); TC_CUDA(cudaMalloc(&d->r, nb));
     TC_CUDA(cudaMalloc(&d->q, nb)); TC_CUDA(cudaMalloc(&d->dinv, nb));
+    TC_CUDA(cudaMalloc(&d->zh, nb)); TC_CUDA(cudaMalloc(&d->pv, nb)); TC_CUDA(cudaMalloc(&d->cc, nb));
     TC_CUDA(cudaMalloc(&d->state, sizeof(int) * 16));
     TC_CUDA(cudaMemset(d->state, 0, sizeof(int) * 16));
     TC_CUDA(cudaMalloc(&d->prof, sizeof(unsigned long long) * 32));
@@ -525,9 +916,68 @@ extern "C" int tc_dist_set_halo(tc_dist* d, int64_t n_send, const int32_t* send_
         TC_CUDA(cudaMemcpy(d->send_peer, send_peer, sizeof(int) * n_send, cudaMemcpyHostToDevice));
         TC_CUDA(cudaMemcpy(d->send_dst, send_dst, sizeof(long long) * n_send, cudaMemcpyHostToDevice));
     }
+    d->h_send_row.assign(send_row, send_row + n_send);
+    d->h_send_peer.assign(send_peer, send_peer + n_send);
+    d->h_send_dst.assign(send_dst, send_dst + n_send);
     TcDistK& K = d->K;
     K.n_send = n_send; K.send_row = d->send_row; K.send_peer = d->send_peer; K.send_dst = d->send_dst;
     K.n_nbr = n_nbr;
+    return 0;
+}
+
+// ---- pipelined kernel: launch shape and per-slice send lists ---------------------------------------------------
+#define PIPE_FN(MB, T) (ef ? (void*)tc_dist_theta_pipe_kernel<MB, T, true> : (void*)tc_dist_theta_pipe_kernel<MB, T, false>)
+static void* dist_pipe_fn(int shape, bool ef) {          // shape = 100 * blocks per SM + threads / 32
+    switch (shape) {
+        case 132: return PIPE_FN(1, 1024);               // 64 registers, 32 warps per SM
+        case 232: return PIPE_FN(2, 1024);               // 32 registers, 64 warps per SM
+        case 316: return PIPE_FN(3, 512);                // 40 registers, 48 warps per SM
+        case 416: return PIPE_FN(4, 512);                // 32 registers
+        default:  return PIPE_FN(2, 512);                // 216: 64 registers, 32 warps per SM
+    }
+}
+static int pipe_shape_threads(int shape) { return 32 * (shape % 100); }
+#define SR_FN(MB, T) (ef ? (void*)tc_dist_theta_sr_kernel<MB, T, true> : (void*)tc_dist_theta_sr_kernel<MB, T, false>)
+static void* dist_sr_fn(int shape, bool ef) {
+    switch (shape) {
+        case 132: return SR_FN(1, 1024);
+        case 232: return SR_FN(2, 1024);
+        case 316: return SR_FN(3, 512);
+        case 416: return SR_FN(4, 512);
+        default:  return SR_FN(2, 512);
+    }
+}
+// Send entries regrouped by the boundary slice of their row (sorted by lane): the warp that forms the slice pushes.
+// A send row outside every boundary slice (possible only for a structurally non-symmetric pattern) switches the
+// pipelined kernel off for this body (pipe_ok = false); the classic kernel does not need the grouping.
+static int dist_build_slice_sends(tc_dist* d, const std::vector<int>& hb, int n_bnd) {
+    cudaFree(d->sptr); cudaFree(d->s_lane); cudaFree(d->s_peer); cudaFree(d->s_dst);
+    d->sptr = d->s_lane = d->s_peer = nullptr; d->s_dst = nullptr;
+    d->pipe_ok = true;
+    const size_t ns = d->h_send_row.size();
+    std::vector<int> cnt(n_bnd + 1, 0);
+    for (size_t e = 0; e < ns; ++e) {
+        const int b = hb[d->h_send_row[e] >> 5];
+        if (b < 0) { d->pipe_ok = false; return 0; }
+        cnt[b + 1] += 1;
+    }
+    for (int b = 0; b < n_bnd; ++b) cnt[b + 1] += cnt[b];
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1), lane(ns ? ns : 1), peer(ns ? ns : 1);
+    std::vector<long long> dst(ns ? ns : 1);
+    for (size_t e = 0; e < ns; ++e) {                 // the send list is sorted by (peer, row): lanes ascend per peer
+        const int b = hb[d->h_send_row[e] >> 5];
+        const int k = fill[b]++;
+        lane[k] = d->h_send_row[e] & 31; peer[k] = d->h_send_peer[e]; dst[k] = d->h_send_dst[e];
+    }
+    TC_CUDA(cudaMalloc(&d->sptr, sizeof(int) * (n_bnd + 1)));
+    TC_CUDA(cudaMalloc(&d->s_lane, sizeof(int) * lane.size()));
+    TC_CUDA(cudaMalloc(&d->s_peer, sizeof(int) * peer.size()));
+    TC_CUDA(cudaMalloc(&d->s_dst, sizeof(long long) * dst.size()));
+    TC_CUDA(cudaMemcpy(d->sptr, cnt.data(), sizeof(int) * (n_bnd + 1), cudaMemcpyHostToDevice));
+    TC_CUDA(cudaMemcpy(d->s_lane, lane.data(), sizeof(int) * lane.size(), cudaMemcpyHostToDevice));
+    TC_CUDA(cudaMemcpy(d->s_peer, peer.data(), sizeof(int) * peer.size(), cudaMemcpyHostToDevice));
+    TC_CUDA(cudaMemcpy(d->s_dst, dst.data(), sizeof(long long) * dst.size(), cudaMemcpyHostToDevice));
+    d->K.sptr = d->sptr; d->K.s_lane = d->s_lane; d->K.s_peer = d->s_peer; d->K.s_dst = d->s_dst;
     return 0;
 }
 
@@ -548,6 +998,7 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     K.b = b; K.mass = mass; K.adiag = adiag;
     K.y = d->y; K.p[0] = d->p0; K.p[1] = d->p1;
     K.x = d->x; K.r = d->r; K.q = d->q; K.dinv = d->dinv;
+    K.zh = d->zh; K.pv = d->pv; K.cc = d->cc;
     K.y_gl = (u64*)(d->comm + off_gl(d->n_ghost, 0));
     K.p_gl[0] = (u64*)(d->comm + off_gl(d->n_ghost, 1)); K.p_gl[1] = (u64*)(d->comm + off_gl(d->n_ghost, 2));
     K.my_mb = (u64*)(d->comm + off_mb(d->n_ghost));
@@ -583,21 +1034,59 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     if (occ < 1) occ = 1;
     d->grid = occ * sms;
     if (d->grid > TC_MAX_PARTIALS) d->grid = TC_MAX_PARTIALS;
-    d->grid = tc_balanced_grid(nslices, dist_threads() / 32, d->grid);
-    K.rot = 0;
+    // boundary slices cost about one slice more (the dependent loads of the ghost side list): leave that many warps
+    // without a slice in the remainder round — the rotation below puts the boundary slices exactly on those warps
+    const char* bs = getenv("TC_DIST_BND_SLACK");
+    const double bnd_slack = bs ? atof(bs) : 1.0;
+    const long long nsl_eff = nslices + (long long)(bnd_slack * n_bnd);
+    d->grid = tc_balanced_grid(nsl_eff, dist_threads() / 32, d->grid);
+    if (const char* fg = getenv("TC_DIST_GRID")) { const int g = atoi(fg); if (g > 0 && g <= d->grid + 64 && g <= occ * sms) d->grid = g; }
+    // pipelined kernel: 2 x 512 threads per SM by default (64 registers for the fused recurrences)
+    {
+        const char* pt = getenv("TC_PIPE_SHAPE");        // 100 * blocks per SM + warps per block
+        d->pipe_shape = pt ? atoi(pt) : 216;
+        if (d->pipe_shape != 132 && d->pipe_shape != 232 && d->pipe_shape != 316 && d->pipe_shape != 416) d->pipe_shape = 216;
+        d->pipe_threads = pipe_shape_threads(d->pipe_shape);
+        const char* lh = getenv("TC_PIPE_L2_HINT");
+        d->l2_hint = !(lh && lh[0] == '0');
+        int pocc = 0;
+        TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, (const void*)dist_pipe_fn(d->pipe_shape, d->l2_hint),
+                                                              d->pipe_threads, 0));
+        if (pocc > d->pipe_shape / 100) pocc = d->pipe_shape / 100;
+        if (pocc < 1) pocc = 1;
+        d->pipe_grid = pocc * sms;
+        if (d->pipe_grid > TC_MAX_PARTIALS) d->pipe_grid = TC_MAX_PARTIALS;
+        d->pipe_grid = tc_balanced_grid(nslices + (long long)(bnd_slack * n_bnd), d->pipe_threads / 32, d->pipe_grid);
+        int socc = 0;
+        TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, (const void*)dist_sr_fn(d->pipe_shape, d->l2_hint),
+                                                              d->pipe_threads, 0));
+        if (socc > d->pipe_shape / 100) socc = d->pipe_shape / 100;
+        if (socc < 1) socc = 1;
+        d->sr_grid = socc * sms;
+        if (d->sr_grid > TC_MAX_PARTIALS) d->sr_grid = TC_MAX_PARTIALS;
+        d->sr_grid = tc_balanced_grid(nslices + (long long)(bnd_slack * n_bnd), d->pipe_threads / 32, d->sr_grid);
+    }
+    K.rot = 0; d->rot_pipe = 0; d->rot_sr = 0;
+    d->pipe_ok = true;
+    K.sptr = nullptr; K.s_lane = nullptr; K.s_peer = nullptr; K.s_dst = nullptr;
+    if (n_bnd == 0 && !d->h_send_row.empty()) d->pipe_ok = false;
     if (n_bnd > 0) {
         std::vector<int> hb(nslices);
         TC_CUDA(cudaMemcpy(hb.data(), bidx, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
+        if (dist_build_slice_sends(d, hb, n_bnd)) return -1;
         int nl = 0, nu = 0;
         while (nl < nslices && hb[nl] >= 0) ++nl;
         while (nu < nslices - nl && hb[nslices - 1 - nu] >= 0) ++nu;
-        const long long nwarps = (long long)d->grid * (dist_threads() / 32);
-        if (nl + nu > 0 && nl + nu <= nwarps && nwarps <= nslices) {
+        auto rot_for = [&](long long nwarps) -> int {
+            if (!(nl + nu > 0 && nl + nu <= nwarps && nwarps <= nslices)) return 0;
             // first-round index range [nwarps - (nl + nu), nwarps) <-> cyclic slice run starting at nslices - nu
             long long rot = ((long long)(nslices - nu) - (nwarps - (nl + nu))) % nslices;
             if (rot < 0) rot += nslices;
-            K.rot = (int)rot;
-        }
+            return (int)rot;
+        };
+        K.rot = rot_for((long long)d->grid * (dist_threads() / 32));
+        d->rot_pipe = rot_for((long long)d->pipe_grid * (d->pipe_threads / 32));
+        d->rot_sr = rot_for((long long)d->sr_grid * (d->pipe_threads / 32));
     }
     return 0;
 }
@@ -789,10 +1278,35 @@ extern "C" int tc_dist_theta_steps(tc_dist* d, int32_t nsteps, double theta, dou
     d->K.theta = theta; d->K.h = h; d->K.rtol = rtol; d->K.maxit = maxit;
     for (int k = 0; k < nsteps; ++k) {
         void* args[] = {(void*)&d->K};
-        TC_CUDA(cudaLaunchCooperativeKernel(dist_fn(), dim3(d->grid), dim3(dist_threads()), args, 0, d->stream));
+        if (d->pcg_mode == 1) {
+            TcDistK Kp = d->K;
+            Kp.rot = d->rot_pipe;
+            void* pargs[] = {(void*)&Kp};
+            TC_CUDA(cudaLaunchCooperativeKernel(dist_pipe_fn(d->pipe_shape, d->l2_hint), dim3(d->pipe_grid),
+                                                dim3(d->pipe_threads), pargs, 0, d->stream));
+        } else if (d->pcg_mode == 2) {
+            TcDistK Kp = d->K;
+            Kp.rot = d->rot_sr;
+            void* pargs[] = {(void*)&Kp};
+            TC_CUDA(cudaLaunchCooperativeKernel(dist_sr_fn(d->pipe_shape, d->l2_hint), dim3(d->sr_grid),
+                                                dim3(d->pipe_threads), pargs, 0, d->stream));
+        } else
+            TC_CUDA(cudaLaunchCooperativeKernel(dist_fn(), dim3(d->grid), dim3(dist_threads()), args, 0, d->stream));
     }
     return 0;
 }
+
+// PCG formulation of tc_dist_theta_steps: 0 = classic (two reductions and a barrier per iteration), 1 = pipelined
+// (one fused sweep and one reduction per iteration), 2 = single-reduction classic (sweep, ONE all-reduce of seven sums,
+// merged vector phase, local barrier).
+// Must be the same on every rank.  Returns -2 when the pipelined kernel cannot serve this body.
+extern "C" int tc_dist_set_pcg(tc_dist* d, int32_t mode) {
+    TC_CHECK(mode >= 0 && mode <= 2, "pcg mode");
+    TC_CHECK(mode == 0 || (d->K.A.val && d->pipe_ok), "single-reduction / pipelined PCG: operator not set or a send row lies outside the boundary slices");
+    d->pcg_mode = mode;
+    return 0;
+}
+extern "C" int32_t tc_dist_get_pcg(tc_dist* d) { return d->pcg_mode; }
 
 // stage solve of a W-method on the partitioned body: z = (I + coef * h A)^-1 rhs on the local rows, h from the device
 extern "C" int tc_dist_solve(tc_dist* d, double coef, const double* h_dev, const double* rhs_local_dev, double* z_local_dev,
@@ -813,7 +1327,7 @@ extern "C" int tc_dist_solve(tc_dist* d, double coef, const double* h_dev, const
 extern "C" int tc_dist_stats(tc_dist* d, int64_t* stats5) {
     int st[16];
     if (dist_read_state(d, st)) return -1;
-    stats5[0] = st[2]; stats5[1] = st[3]; stats5[2] = st[4]; stats5[3] = st[5] + 1000000LL * d->grid; stats5[4] = st[8];
+    stats5[0] = st[2]; stats5[1] = st[3]; stats5[2] = st[4]; stats5[3] = st[5] + 1000000LL * (d->pcg_mode == 1 ? d->pipe_grid : d->pcg_mode == 2 ? d->sr_grid : d->grid); stats5[4] = st[8];
     stats5[5] = st[10];
     return 0;
 }
@@ -844,6 +1358,8 @@ extern "C" int tc_dist_destroy(tc_dist* d) {
     cudaFree(d->state); cudaFree(d->prof);
     cudaFree(d->K.bar.ctr); cudaFree(d->K.bar.part); cudaFree(d->K.bar.res);
     cudaFree(d->send_row); cudaFree(d->send_peer); cudaFree(d->send_dst);
+    cudaFree(d->zh); cudaFree(d->pv); cudaFree(d->cc);
+    cudaFree(d->sptr); cudaFree(d->s_lane); cudaFree(d->s_peer); cudaFree(d->s_dst);
     delete d;
     return 0;
 }

@@ -16,7 +16,7 @@
 #pragma once
 #include "common.cuh"
 
-#define TC_BAR_MAXK 4
+#define TC_BAR_MAXK 8
 
 struct TcGridBar {
     unsigned int* ctr;      // word [0]: arrival counter (top bit = barrier phase).  Last-arriver variant: word [32] =
@@ -74,17 +74,24 @@ __device__ __forceinline__ void tc_block_sum_k(double* v) {
 // in v[k].  `gen` counts the barriers of this launch (start at 0; only its parity is used).
 // err / limit (optional): bound the wait — after `limit` clock64 ticks (or as soon as *err is non-zero) the block
 // raises *err and carries on with whatever it has (the row-partitioned kernel: a lost peer must not hang the GPU).
-template <int K>
+struct TcNoWork { __device__ __forceinline__ void operator()() const {} };
+// `work` (optional) runs on ALL threads between the block's arrival and its wait: work that neither feeds this
+// reduction nor is read by other blocks before the NEXT barrier hides behind the wait (split-phase barrier).
+template <int K, int U = (K > 3 ? 1 : 4), class F = TcNoWork>       // U partial loads per value in flight
 __device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int& gen, double* v, int* err = nullptr,
-                                               long long limit = 0) {
+                                               long long limit = 0, F work = F()) {
     const int G = gridDim.x;
     double* bank = B.part + (size_t)(gen & 1u) * TC_BAR_MAXK * TC_MAX_PARTIALS;
     __syncthreads();                                       // every thread's earlier stores are ordered before thread 0's release
+    unsigned int old = 0u;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) bank[k * TC_MAX_PARTIALS + blockIdx.x] = v[k];
         const unsigned int nb = blockIdx.x == 0 ? 0x80000000u - (unsigned int)(G - 1) : 1u;
-        const unsigned int old = tc_atom_add_release_gpu_u32(B.ctr, nb);
+        old = tc_atom_add_release_gpu_u32(B.ctr, nb);
+    }
+    work();
+    if (threadIdx.x == 0) {
         if (err) {
             const long long t0 = clock64();
             for (unsigned int spins = 1; ((old ^ tc_ld_relaxed_gpu_u32(B.ctr)) & 0x80000000u) == 0u; ++spins)
@@ -103,16 +110,16 @@ __device__ __forceinline__ void tc_grid_reduce(const TcGridBar& B, unsigned int&
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.0;
         // fixed order: thread t owns partials t, t+T, t+2T, ... (ascending), then the fixed block tree
-        for (int i0 = threadIdx.x; i0 < G; i0 += 4 * blockDim.x) {
-            double buf[4][K > 0 ? K : 1];
+        for (int i0 = threadIdx.x; i0 < G; i0 += U * blockDim.x) {
+            double buf[U][K > 0 ? K : 1];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < U; ++j) {
                 const int i = i0 + j * blockDim.x;
 #pragma unroll
                 for (int k = 0; k < K; ++k) buf[j][k] = i < G ? __ldcg(bank + k * TC_MAX_PARTIALS + i) : 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < U; ++j)
                 if (i0 + j * (int)blockDim.x < G) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) acc[k] += buf[j][k];

@@ -263,7 +263,29 @@ class DistBody:
                                                   self.n_bnd, p(self.bidx), p(self.gptr), p(self.gslot), p(self.gval)))
         if init_temp is not None:
             self.set_state(torch.full((self.n,), float(init_temp), dtype=torch.float64, device=self.dev))
+        self.set_pcg(os.environ.get("TC_DIST_PCG", "auto"))
         dist.barrier()
+
+    def set_pcg(self, mode="auto"):
+        """PCG formulation of ``theta_steps`` (csrc/dist.cu), the same on every rank: 'classic' (two all-reduces and a
+        barrier per iteration: the default, fastest at every measured size), 'sr' (single-reduction: one all-reduce of
+        seven sums + a local barrier per iteration) or 'pipe' (pipelined recurrences fused into the product sweep: one
+        sweep + one all-reduce per iteration).  The alternatives are measured in DESIGN.md section 6."""
+        from . import _cabi
+        if mode == "auto":
+            mode = "classic"
+        want = {"classic": 0, "pipe": 1, "sr": 2}[mode]
+        rc = int(self.lib.tc_dist_set_pcg(self._h, want))
+        if want:
+            # a body the alternative kernels cannot serve on ANY rank falls back to the classic kernel on ALL ranks
+            flag = self.torch.tensor([rc], dtype=self.torch.int64, device=self.dev)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+            if int(flag.item()) != 0:
+                _cabi.check(self.lib.tc_dist_set_pcg(self._h, 0))
+        else:
+            _cabi.check(rc)
+        self.pcg = ("classic", "pipe", "sr")[int(self.lib.tc_dist_get_pcg(self._h))]
+        return self.pcg
 
     # ---- construction from a replicated host operator (a real, lowered FE body) -------------------------
     @classmethod
