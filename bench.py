@@ -479,6 +479,7 @@ def fe_partitioned(dims, ly, heat, steps, warmup, local_rank, parity_steps=0, wa
         "value": n_tot * steps / (ms * 1e-3), "ms_per_step": ms / steps, "dof": n_tot, "dof_per_gpu": dc.n,
         "nnz": int(nnz.item()), "iters_per_step": iters / steps, "ghost_rows": dc.n_ghost,
         "boundary_slices": dc.n_bnd, "grid": st["grid"], "late_ghosts": st.get("late_ghosts"), "clocks": clocks.summary(),
+        "pcg": dc.pcg,
         "phase_ms_rank0": prof, "busy_wait_ms_per_rank": [[round(float(v[0]), 1), round(float(v[1]), 1)] for v in allp],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "tc_dist_theta_kernel (per GPU)", "peak_kind": peak_kind},
@@ -521,6 +522,8 @@ def run_ours_partitioned(args, world, rank, local_rank):
                    "dof": main["dof"], "dof_per_gpu": main["dof_per_gpu"], "nnz": main["nnz"], "pcg_rtol": PCG_RTOL,
                    "h_step_s": H_STEP, "iters_per_step": main["iters_per_step"], "ghost_rows": main["ghost_rows"],
                    "l2": "per-GPU inputs exceed the 126 MB L2", "grid": main["grid"], "late_ghosts": main.get("late_ghosts"),
+                   "pcg": main["pcg"] + " (csrc/dist.cu: classic = two all-reduces + a barrier per iteration, x-update hidden "
+                          "behind the second one)",
                    "phase_ms_rank0": main["phase_ms_rank0"], "busy_wait_ms_per_rank": main["busy_wait_ms_per_rank"]},
         "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": args.steps * world,
         "roofline": main["roofline"], "parity": main["parity"],

@@ -279,6 +279,8 @@ int tc_dist_reset_error(tc_dist* d);
  * (counted only with TC_DIST_DIAG=1) */
 int tc_dist_stats(tc_dist* d, int64_t* stats6);
 int tc_dist_profile(tc_dist* d, uint64_t* out32);   /* per-phase wall time (ns) of block 0 / last block */
+/* diagnostic (TC_DIST_DIAG=3 at set_operator): out[block * 10 + phase] accumulated ns of EVERY block (slot 8: SM id); returns the grid */
+int tc_dist_block_profile(tc_dist* d, uint64_t* out, int32_t max_blocks);
 /* teardown: tc_dist_close_peers on every rank, a host barrier, then tc_dist_destroy (CUDA IPC rule: the
  * exporter must not free while an importer has the buffer mapped) */
 int tc_dist_close_peers(tc_dist* d);

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--variants", default="classic,pipe")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--blocks", action="store_true", help="per-block phase profile (TC_DIST_DIAG=3) of rank 0")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -44,6 +45,8 @@ def main():
             os.environ["TC_PIPE_SHAPE"] = parts[1]
         if len(parts) > 2 and parts[2]:
             os.environ["TC_PIPE_L2_HINT"] = parts[2]
+        if args.blocks:
+            os.environ["TC_DIST_DIAG"] = "3"
         dc = DistCuboid(nx, ny, nz)
         assert dc.set_pcg(mode) == mode
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -61,19 +64,30 @@ def main():
         st = dc.stats()
         iters = st["iters_total"] - it0
         prof = dc.profile()
+        blocks = None
+        if args.blocks:
+            import ctypes as C
+            import numpy as np
+            buf = (C.c_uint64 * (10 * 2048))()
+            g = int(dc.lib.tc_dist_block_profile(dc._h, buf, 2048))
+            a = np.frombuffer(buf, dtype=np.uint64).reshape(2048, 10)[:g].astype(np.float64)
+            blocks = {"grid": g, "sm": a[:, 8].astype(int).tolist(),
+                      "us_per_iter": (a[:, :8] / 1e3 / max(iters + args.warmup * iters // args.steps, 1)).round(2).tolist()}
         states[var] = dc.get_state().clone()
         r = {"variant": var, "world": world, "dof": dc.n_global, "rows_per_gpu": dc.n, "ms_per_step": float(ms) / args.steps,
              "iters_per_step": iters / args.steps, "us_per_iter": 1e3 * float(ms) / max(iters, 1),
              "mdof_steps_per_s": dc.n_global * args.steps / float(ms) / 1e3, "grid": st["grid"],
              "us_per_iter_by_phase_block0": {k: round(1e3 * v / max(iters, 1), 2) for k, v in prof["block0"].items() if v},
              "us_per_iter_by_phase_last": {k: round(1e3 * v / max(iters, 1), 2) for k, v in prof["last"].items() if v}}
+        if blocks is not None:
+            r["blocks"] = blocks
         first = next(iter(states.values()))
         d = torch.max(torch.abs(states[var] - first) / torch.abs(first)).reshape(1)
         dist.all_reduce(d, op=dist.ReduceOp.MAX)
         r["max_rel_vs_first_variant"] = float(d)
         results.append(r)
         if rank == 0:
-            print(json.dumps(r), flush=True)
+            print(json.dumps({k: v for k, v in r.items() if k != "blocks"}), flush=True)
         dc.close()
         del dc
         torch.cuda.empty_cache()

@@ -113,6 +113,7 @@ EXPORTS = {
     "tc_dist_reset_error": (i32, [vp]),
     "tc_dist_stats": (i32, [vp, C.POINTER(i64)]),
     "tc_dist_profile": (i32, [vp, C.POINTER(C.c_uint64)]),
+    "tc_dist_block_profile": (i32, [vp, C.POINTER(C.c_uint64), i32]),
     "tc_dist_close_peers": (i32, [vp]),
     "tc_dist_destroy": (i32, [vp]),
     "tc_mor_batch_steps": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,

@@ -43,6 +43,32 @@ __device__ __forceinline__ int ld_stream_s32(const int* p) {
     return v;
 }
 
+// Matrix streams with an L2 evict-first policy (EF): when the vectors of a rank fit into the 126 MB L2 (strong
+// scaling: ~1 M rows per GPU) the operator must not push them out, it is read exactly once per sweep.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <bool EF> __device__ __forceinline__ double ldm_f64(const double* p, unsigned long long pol) {
+    if (!EF) return ld_stream_f64(p);
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <bool EF> __device__ __forceinline__ int ldm_s16(const short* p, unsigned long long pol) {
+    if (!EF) return ld_stream_s16(p);
+    short v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return (int)v;
+}
+template <bool EF> __device__ __forceinline__ int ldm_s32(const int* p, unsigned long long pol) {
+    if (!EF) return ld_stream_s32(p);
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 // ---- deterministic block reduction (fixed shuffle tree, fixed warp order) -----------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

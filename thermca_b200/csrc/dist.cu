@@ -75,6 +75,7 @@ struct TcDistK {
     long long spin_limit;                 // clock64 ticks
     int push_fence;                       // experiment switch (TC_DIST_PUSH_FENCE=1): system fence after ghost pushes
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
+    unsigned long long* blkprof;          // optional (TC_DIST_DIAG=3): [block][10]: 8 phase times (ns), SM id
     // pipelined PCG (tc_dist_theta_pipe_kernel): extra vectors and the send lists grouped by boundary slice
     double *zh, *pv, *cc;                 // D z, search direction, c_i = 1 / (1 + shift a_ii)
     const int* sptr;                      // n_bnd + 1: send entries of boundary slice b (sorted by lane)
@@ -199,74 +200,11 @@ __device__ __noinline__ double ghost_part(const long long* gptr, const int* gslo
     return sum;
 }
 
-// Matrix streams with an L2 evict-first policy (EF): when the vectors of a rank fit into the 126 MB L2 (strong
-// scaling: ~1 M rows per GPU) the operator must not push them out, it is read exactly once per sweep.
-__device__ __forceinline__ u64 l2_evict_first_policy() {
-    u64 pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-template <bool EF> __device__ __forceinline__ double ldm_f64(const double* p, u64 pol) {
-    if (!EF) return ld_stream_f64(p);
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-template <bool EF> __device__ __forceinline__ int ldm_s16(const short* p, u64 pol) {
-    if (!EF) return ld_stream_s16(p);
-    short v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
-    return (int)v;
-}
-template <bool EF> __device__ __forceinline__ int ldm_s32(const int* p, u64 pol) {
-    if (!EF) return ld_stream_s32(p);
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-
-// sum_k A[row][k] x[col] over the LOCAL columns of one slice (one row per lane), entries in stored order, no FMA
+// sum_k A[row][k] x[col] over the LOCAL columns of one slice (one row per lane): parts.cuh tc_slice_row_sum (entries in
+// stored order, no FMA); EF = matrix streams with the L2 evict-first policy `pol`
 template <bool EF = false>
 __device__ __forceinline__ double slice_local_sum(const TcSell& A, const double* xl, int s, int lane, u64 pol = 0ULL) {
-    const long long base = A.slice_ptr[s];
-    const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
-    const double* v = A.val + base + lane;
-    double sum = 0.0;
-    if (A.col16) {
-        const short* c = A.col16 + base + lane;
-        const double* xr0 = xl + (s * 32 + lane);
-        int k = 0;
-        for (; k + 4 <= width; k += 4) {
-            const double v0 = ldm_f64<EF>(v + 32 * (k + 0), pol), v1 = ldm_f64<EF>(v + 32 * (k + 1), pol);
-            const double v2 = ldm_f64<EF>(v + 32 * (k + 2), pol), v3 = ldm_f64<EF>(v + 32 * (k + 3), pol);
-            const int c0 = ldm_s16<EF>(c + 32 * (k + 0), pol), c1 = ldm_s16<EF>(c + 32 * (k + 1), pol);
-            const int c2 = ldm_s16<EF>(c + 32 * (k + 2), pol), c3 = ldm_s16<EF>(c + 32 * (k + 3), pol);
-            const double x0 = tc_ld_x<0>(xr0 + c0), x1 = tc_ld_x<0>(xr0 + c1), x2 = tc_ld_x<0>(xr0 + c2), x3 = tc_ld_x<0>(xr0 + c3);
-            sum = __dadd_rn(sum, __dmul_rn(v0, x0));
-            sum = __dadd_rn(sum, __dmul_rn(v1, x1));
-            sum = __dadd_rn(sum, __dmul_rn(v2, x2));
-            sum = __dadd_rn(sum, __dmul_rn(v3, x3));
-        }
-        for (; k < width; ++k)
-            sum = __dadd_rn(sum, __dmul_rn(ldm_f64<EF>(v + 32 * k, pol), tc_ld_x<0>(xr0 + ldm_s16<EF>(c + 32 * k, pol))));
-    } else {
-        const int* c = A.col + base + lane;
-        int k = 0;
-        for (; k + 4 <= width; k += 4) {
-            const double v0 = ldm_f64<EF>(v + 32 * (k + 0), pol), v1 = ldm_f64<EF>(v + 32 * (k + 1), pol);
-            const double v2 = ldm_f64<EF>(v + 32 * (k + 2), pol), v3 = ldm_f64<EF>(v + 32 * (k + 3), pol);
-            const int c0 = ldm_s32<EF>(c + 32 * (k + 0), pol), c1 = ldm_s32<EF>(c + 32 * (k + 1), pol);
-            const int c2 = ldm_s32<EF>(c + 32 * (k + 2), pol), c3 = ldm_s32<EF>(c + 32 * (k + 3), pol);
-            const double x0 = tc_ld_x<0>(xl + c0), x1 = tc_ld_x<0>(xl + c1), x2 = tc_ld_x<0>(xl + c2), x3 = tc_ld_x<0>(xl + c3);
-            sum = __dadd_rn(sum, __dmul_rn(v0, x0));
-            sum = __dadd_rn(sum, __dmul_rn(v1, x1));
-            sum = __dadd_rn(sum, __dmul_rn(v2, x2));
-            sum = __dadd_rn(sum, __dmul_rn(v3, x3));
-        }
-        for (; k < width; ++k)
-            sum = __dadd_rn(sum, __dmul_rn(ldm_f64<EF>(v + 32 * k, pol), tc_ld_x<0>(xl + ldm_s32<EF>(c + 32 * k, pol))));
-    }
-    return sum;
+    return tc_slice_row_sum<0, EF>(A, xl, 0, s, lane, pol);
 }
 
 // Local rows times [local vector | ghosts].  Every slice runs the same streaming loop over its LOCAL columns, in the
@@ -278,6 +216,23 @@ __device__ __forceinline__ double slice_local_sum(const TcSell& A, const double*
 // pushed at the start of the previous vector phase, a whole phase and a barrier earlier (measured: practically never
 // late); one that is still missing is waited for individually (LL tag).  No halo flags.
 template <int MODE>
+__device__ __forceinline__ void slab_finish_row(const TcDistK& S, const double* xl, double* y, const double* b, double shift,
+                                                int row, double sum, double& dot) {
+    if (MODE == SPMV_B) {
+        y[row] = __dsub_rn(b[row], sum);
+    } else {
+        const double xr = tc_ld_x<0>(xl + row);
+        const double q = S.mass[row] * (xr + shift * sum);
+        y[row] = q;
+        dot += xr * q;
+    }
+}
+// Two passes per warp: the streaming pass over ALL its slices leaves the local sums of boundary slices in y and
+// remembers their rounds in a bit mask; the ghost side lists (a non-inlined call with ~4 dependent loads) are added in
+// a second pass over those rounds only — the call, its argument registers and the spills around it stay out of the
+// streaming loop (with the call inside it the row accumulator lived in local memory: 12 % slower products than the
+// single-GPU kernel at 10 M rows), and the ghosts have had the whole pass to land.
+template <int MODE>
 __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, const u64* xg, double* y,
                                             const double* b, double shift, unsigned int hseq) {
     const TcSell& A = S.A;
@@ -287,23 +242,32 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, 
     const int nwarps = gridDim.x * warps_per_block;
     const int nsl = A.nslices;
     double dot = 0.0;
+    unsigned int bmask = 0u, bit = 1u;
     for (int idx = warp; idx < nsl; idx += nwarps) {
         int s = idx + S.rot;
         if (s >= nsl) s -= nsl;
-        const int bi = S.n_bnd ? S.bidx[s] : -1;
-        double sum = slice_local_sum(A, xl, s, lane);
-        if (bi >= 0)
-            sum = __dadd_rn(sum, ghost_part(S.gptr, S.gslot, S.gval, xg, bi, lane, hseq, S.state, S.spin_limit));
+        const bool bnd = S.n_bnd && S.bidx[s] >= 0;                  // warp uniform
+        const double sum = slice_local_sum(A, xl, s, lane);
         const int row = s * 32 + lane;
-        if (row < A.n) {
-            if (MODE == SPMV_B) {
-                y[row] = __dsub_rn(b[row], sum);
-            } else {
-                const double xr = tc_ld_x<0>(xl + row);
-                const double q = S.mass[row] * (xr + shift * sum);
-                y[row] = q;
-                dot += xr * q;
-            }
+        if (bnd) {
+            bmask |= bit;
+            if (row < A.n) y[row] = sum;                             // local part, finished in the second pass
+        } else if (row < A.n) {
+            slab_finish_row<MODE>(S, xl, y, b, shift, row, sum, dot);
+        }
+        bit = (bit << 1) | (bit >> 31);                              // round mod 32
+    }
+    if (bmask) {
+        bit = 1u;
+        for (int idx = warp; idx < nsl; idx += nwarps, bit = (bit << 1) | (bit >> 31)) {
+            if (!(bmask & bit)) continue;
+            int s = idx + S.rot;
+            if (s >= nsl) s -= nsl;
+            const int bi = S.bidx[s];
+            if (bi < 0) continue;                                    // a round that shares the mask bit (> 32 rounds)
+            const double gs = ghost_part(S.gptr, S.gslot, S.gval, xg, bi, lane, hseq, S.state, S.spin_limit);
+            const int row = s * 32 + lane;
+            if (row < A.n) slab_finish_row<MODE>(S, xl, y, b, shift, row, __dadd_rn(y[row], gs), dot);
         }
     }
     return dot;
@@ -316,9 +280,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 // phase profiler: thread 0 of block 0 and of the last block accumulate wall time per phase
 #define PROF_INIT() const int prof_row = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1); \
-    unsigned long long prof_t = (prof_row >= 0 && threadIdx.x == 0) ? gtime() : 0ULL
+    unsigned long long prof_t = (prof_row >= 0 && threadIdx.x == 0) ? gtime() : 0ULL; \
+    unsigned long long blk_t = (S.blkprof && threadIdx.x == 0) ? gtime() : 0ULL; \
+    if (S.blkprof && threadIdx.x == 0) { unsigned int sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); S.blkprof[blockIdx.x * 10 + 8] = sm_; }
 #define PROF(k) do { if (prof_row >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
-    S.prof[prof_row * 16 + (k)] += t_ - prof_t; prof_t = t_; } } while (0)
+    S.prof[prof_row * 16 + (k)] += t_ - prof_t; prof_t = t_; } \
+    if (S.blkprof && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
+    S.blkprof[blockIdx.x * 10 + (k)] += t_ - blk_t; blk_t = t_; } } while (0)
 
 // scaled right-hand side and Jacobi factor of one row (explicit roundings: the owner's loop and the halo push
 // must produce the same bits)
@@ -790,12 +758,13 @@ static int dist_threads() {
     if (t < 0) {
         const char* e = getenv("TC_PCG_THREADS");
         t = e ? atoi(e) : TC_DIST_THREADS;
-        if (t != 256 && t != 512 && t != 1024) t = TC_DIST_THREADS;
+        if (t != 256 && t != 512 && t != 768 && t != 1024) t = TC_DIST_THREADS;
     }
     return t;
 }
 static void* dist_fn() {
     // 2 blocks x 1024 threads per SM by default (fewer barrier participants, profiles/README.md); TC_PCG_THREADS=512/256
+    if (dist_threads() == 768) return (void*)tc_dist_theta_kernel<2, 768>;     // 42 registers, 48 warps per SM
     if (dist_threads() == 512) return (void*)tc_dist_theta_kernel<4, 512>;
     if (dist_threads() == 256) return (void*)tc_dist_theta_kernel<8, 256>;
     return (void*)tc_dist_theta_kernel<2, 1024>;
@@ -813,6 +782,7 @@ struct tc_dist {
     double *x = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr;
     int* state = nullptr;
     unsigned long long* prof = nullptr;
+    unsigned long long* blkprof = nullptr;
     int* send_row = nullptr; int* send_peer = nullptr; long long* send_dst = nullptr;
     std::vector<int> h_send_row, h_send_peer;      // host copies: regrouped by boundary slice for the pipelined kernel
     std::vector<long long> h_send_dst;
@@ -1029,6 +999,11 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     K.push_fence = pf && pf[0] == '1';
     const char* dg = getenv("TC_DIST_DIAG");            // 1: count late ghosts in state[10]; 2: also do not wait for them
     if (dg) { const int v = atoi(dg); cudaMemcpy(d->state + 11, &v, sizeof(int), cudaMemcpyHostToDevice); }
+    if (dg && atoi(dg) == 3 && !d->blkprof) {           // per-block phase profile (scripts/pipe_bench.py --blocks)
+        TC_CUDA(cudaMalloc(&d->blkprof, sizeof(unsigned long long) * 10 * TC_MAX_PARTIALS));
+        TC_CUDA(cudaMemset(d->blkprof, 0, sizeof(unsigned long long) * 10 * TC_MAX_PARTIALS));
+    }
+    K.blkprof = d->blkprof;
     TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)dist_fn(), dist_threads(), 0));
     if (occ > 2048 / dist_threads()) occ = 2048 / dist_threads();
     if (occ < 1) occ = 1;
@@ -1332,6 +1307,17 @@ extern "C" int tc_dist_stats(tc_dist* d, int64_t* stats5) {
     return 0;
 }
 
+// per-block phase profile (TC_DIST_DIAG=3): out[block * 10 + phase] accumulated ns (slot 8: SM id), cleared on read; returns the grid
+extern "C" int tc_dist_block_profile(tc_dist* d, uint64_t* out, int32_t max_blocks) {
+    TC_CHECK(d->blkprof, "per-block profile not enabled (TC_DIST_DIAG=3)");
+    TC_CUDA(cudaStreamSynchronize(d->stream));
+    const int g = d->pcg_mode == 1 ? d->pipe_grid : d->pcg_mode == 2 ? d->sr_grid : d->grid;
+    const int nb = g < max_blocks ? g : max_blocks;
+    TC_CUDA(cudaMemcpy(out, d->blkprof, sizeof(unsigned long long) * 10 * nb, cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemset(d->blkprof, 0, sizeof(unsigned long long) * 10 * TC_MAX_PARTIALS));
+    return g;
+}
+
 // phase profile: 32 accumulated nanosecond counters (block 0: [0..15], last block: [16..31]); cleared on read
 extern "C" int tc_dist_profile(tc_dist* d, uint64_t* out32) {
     TC_CUDA(cudaStreamSynchronize(d->stream));
@@ -1355,7 +1341,7 @@ extern "C" int tc_dist_destroy(tc_dist* d) {
     if (!d) return 0;
     tc_dist_close_peers(d);
     cudaFree(d->comm); cudaFree(d->y); cudaFree(d->p0); cudaFree(d->p1); cudaFree(d->x); cudaFree(d->r); cudaFree(d->q); cudaFree(d->dinv);
-    cudaFree(d->state); cudaFree(d->prof);
+    cudaFree(d->state); cudaFree(d->prof); cudaFree(d->blkprof);
     cudaFree(d->K.bar.ctr); cudaFree(d->K.bar.part); cudaFree(d->K.bar.res);
     cudaFree(d->send_row); cudaFree(d->send_peer); cudaFree(d->send_dst);
     cudaFree(d->zh); cudaFree(d->pv); cudaFree(d->cc);

@@ -45,8 +45,59 @@ __device__ __forceinline__ double tc_ld_x(const double* p) {
     return v;
 }
 
+// One group of N stored entries of a row: N value + N index loads in flight, then N gathers, then the un-fused
+// multiply-add chain in stored order.
+__device__ __forceinline__ int tc_ld_idx(const short* p, unsigned long long pol, bool ef) {
+    return ef ? ldm_s16<true>(p, pol) : ld_stream_s16(p);
+}
+__device__ __forceinline__ int tc_ld_idx(const int* p, unsigned long long pol, bool ef) {
+    return ef ? ldm_s32<true>(p, pol) : ld_stream_s32(p);
+}
+template <int N, int NC_X, bool EF, class CT>
+__device__ __forceinline__ double tc_row_group(double sum, const double* v, const CT* c, const double* xb,
+                                               unsigned long long pol) {
+    double vv[N], xx[N];
+    int cc[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) vv[j] = ldm_f64<EF>(v + 32 * j, pol);
+#pragma unroll
+    for (int j = 0; j < N; ++j) cc[j] = tc_ld_idx(c + 32 * j, pol, EF);
+#pragma unroll
+    for (int j = 0; j < N; ++j) xx[j] = tc_ld_x<NC_X>(xb + cc[j]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) sum = __dadd_rn(sum, __dmul_rn(vv[j], xx[j]));
+    return sum;
+}
+// Row sum of one slice (one row per lane), entries in stored order.  All lanes of a slice share its width, so the
+// tail (width mod 4) is ONE group behind a warp-uniform branch: a per-entry tail loop costs two dependent memory
+// round trips per entry (load value/index -> gather), and the warps are latency bound (measured: an SM that runs one
+// block finishes its slices no sooner than an SM that runs two) — for the 15-wide rows of a tetrahedral mesh the
+// tail loop was half of the 12 round trips of a slice.
+template <int NC_X, bool EF, class CT>
+__device__ __forceinline__ double tc_row_sum_cols(const double* v, const CT* c, const double* xb, int width,
+                                                  unsigned long long pol) {
+    double sum = 0.0;
+    int k = 0;
+    for (; k + 4 <= width; k += 4) sum = tc_row_group<4, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, pol);
+    const int rem = width - k;
+    if (rem == 3) sum = tc_row_group<3, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, pol);
+    else if (rem == 2) sum = tc_row_group<2, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, pol);
+    else if (rem == 1) sum = tc_row_group<1, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, pol);
+    return sum;
+}
 // xrow_off: index of local row 0 in the gathered vector (row partition: x is addressed by
 // GLOBAL column, outputs by LOCAL row); 0 on a single GPU.
+template <int NC_X, bool EF>
+__device__ __forceinline__ double tc_slice_row_sum(const TcSell& A, const double* x, long long xrow_off, int s, int lane,
+                                                   unsigned long long pol = 0ULL) {
+    const long long base = A.slice_ptr[s];
+    const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+    const double* v = A.val + base + lane;
+    if (A.col16)                                                      // x at this thread's own row + relative column
+        return tc_row_sum_cols<NC_X, EF>(v, A.col16 + base + lane, x + (xrow_off + s * 32 + lane), width, pol);
+    return tc_row_sum_cols<NC_X, EF>(v, A.col + base + lane, x, width, pol);
+}
+
 template <int MODE, int NC_X = 1>
 __device__ __forceinline__ double tc_sell_spmv_body(const TcSell& A, const double* x,
                                                     double* y, const double* __restrict__ b,
@@ -59,46 +110,7 @@ __device__ __forceinline__ double tc_sell_spmv_body(const TcSell& A, const doubl
     double dot = 0.0;
     if (s_end < 0) s_end = A.nslices;
     for (int s = s_begin + warp; s < s_end; s += nwarps) {
-        const long long base = A.slice_ptr[s];
-        const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
-        const double* v = A.val + base + lane;
-        double sum = 0.0;
-        int k = 0;
-        if (A.col16) {
-            const short* c = A.col16 + base + lane;
-            const double* xr0 = x + (xrow_off + s * 32 + lane);       // x at this thread's own row
-            for (; k + 4 <= width; k += 4) {
-                const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
-                const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
-                const int c0 = ld_stream_s16(c + 32 * (k + 0)), c1 = ld_stream_s16(c + 32 * (k + 1));
-                const int c2 = ld_stream_s16(c + 32 * (k + 2)), c3 = ld_stream_s16(c + 32 * (k + 3));
-                const double x0 = tc_ld_x<NC_X>(xr0 + c0), x1 = tc_ld_x<NC_X>(xr0 + c1), x2 = tc_ld_x<NC_X>(xr0 + c2), x3 = tc_ld_x<NC_X>(xr0 + c3);
-                sum = __dadd_rn(sum, __dmul_rn(v0, x0));
-                sum = __dadd_rn(sum, __dmul_rn(v1, x1));
-                sum = __dadd_rn(sum, __dmul_rn(v2, x2));
-                sum = __dadd_rn(sum, __dmul_rn(v3, x3));
-            }
-            for (; k < width; ++k)
-                sum = __dadd_rn(sum, __dmul_rn(ld_stream_f64(v + 32 * k), tc_ld_x<NC_X>(xr0 + ld_stream_s16(c + 32 * k))));
-        } else {
-        const int* c = A.col + base + lane;
-        for (; k + 4 <= width; k += 4) {
-            const double v0 = ld_stream_f64(v + 32 * (k + 0)), v1 = ld_stream_f64(v + 32 * (k + 1));
-            const double v2 = ld_stream_f64(v + 32 * (k + 2)), v3 = ld_stream_f64(v + 32 * (k + 3));
-            const int c0 = ld_stream_s32(c + 32 * (k + 0)), c1 = ld_stream_s32(c + 32 * (k + 1));
-            const int c2 = ld_stream_s32(c + 32 * (k + 2)), c3 = ld_stream_s32(c + 32 * (k + 3));
-            const double x0 = tc_ld_x<NC_X>(x + c0), x1 = tc_ld_x<NC_X>(x + c1), x2 = tc_ld_x<NC_X>(x + c2), x3 = tc_ld_x<NC_X>(x + c3);
-            sum = __dadd_rn(sum, __dmul_rn(v0, x0));
-            sum = __dadd_rn(sum, __dmul_rn(v1, x1));
-            sum = __dadd_rn(sum, __dmul_rn(v2, x2));
-            sum = __dadd_rn(sum, __dmul_rn(v3, x3));
-        }
-        for (; k < width; ++k) {
-            const double v0 = ld_stream_f64(v + 32 * k);
-            const int c0 = ld_stream_s32(c + 32 * k);
-            sum = __dadd_rn(sum, __dmul_rn(v0, tc_ld_x<NC_X>(x + c0)));
-        }
-        }
+        const double sum = tc_slice_row_sum<NC_X, false>(A, x, xrow_off, s, lane);
         const int row = s * 32 + lane;
         if (row < A.n) {
             if (MODE == SPMV_NEG) {

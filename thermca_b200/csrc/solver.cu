@@ -952,13 +952,14 @@ static int pcg_coop_threads() {
     if (t < 0) {
         const char* e = getenv("TC_PCG_THREADS");
         t = e ? atoi(e) : TC_PCG_COOP_THREADS_DEFAULT;
-        if (t != 256 && t != 512 && t != 1024) t = TC_PCG_COOP_THREADS_DEFAULT;
+        if (t != 256 && t != 512 && t != 768 && t != 1024) t = TC_PCG_COOP_THREADS_DEFAULT;
     }
     return t;
 }
 static void* pcg_coop_fn() {
     const int t = pcg_coop_threads();
     if (t == 1024) return (void*)tc_pcg_coop_kernel<2, 1024>;
+    if (t == 768) return (void*)tc_pcg_coop_kernel<2, 768>;          // 42 registers, 48 warps per SM
     if (t == 512) return (void*)tc_pcg_coop_kernel<4, 512>;
     switch (pcg_occ_variant()) {
         case 5: return (void*)tc_pcg_coop_kernel<5>;
