@@ -52,8 +52,9 @@ def algorithmic_bytes_per_iteration(n_rows, nnz):
 
 
 def streamed_bytes_per_iteration(n_rows, nnz_stored, col16):
-    """What the kernel actually streams: SELL storage incl. padding, 2-byte relative columns when available."""
-    return nnz_stored * (8 + (2 if col16 else 4)) + n_rows * (24 + 56 + 32)
+    """What the kernel actually streams: SELL storage incl. padding, 2-byte relative columns when available; the
+    x update rides on the direction phase (p is read twice per iteration, not three times): 48 + 48 - 8 B/row."""
+    return nnz_stored * (8 + (2 if col16 else 4)) + n_rows * (24 + 48 + 32)
 
 
 class ClockSampler:

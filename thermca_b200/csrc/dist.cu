@@ -76,6 +76,8 @@ struct TcDistK {
     int push_fence;                       // experiment switch (TC_DIST_PUSH_FENCE=1): system fence after ghost pushes
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
     unsigned long long* blkprof;          // optional (TC_DIST_DIAG=3): [block][10]: 8 phase times (ns), SM id
+    int x_in_dir;                         // x += alpha p rides on the direction phase (many rows per GPU) instead of
+                                          // hiding behind the second all-reduce (few rows per GPU)
     // pipelined PCG (tc_dist_theta_pipe_kernel): extra vectors and the send lists grouped by boundary slice
     double *zh, *pv, *cc;                 // D z, search direction, c_i = 1 / (1 + shift a_ii)
     const int* sptr;                      // n_bnd + 1: send entries of boundary slice b (sorted by lane)
@@ -278,15 +280,19 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// phase profiler: thread 0 of block 0 and of the last block accumulate wall time per phase
+// phase profiler: thread 0 of block 0 and of the last block (every block with TC_DIST_DIAG=3) accumulate wall time per
+// phase in SHARED memory and flush once at the end of the launch — a global read-modify-write per phase put an
+// exposed memory round trip of thread 0 in front of every barrier (measured ~1.3 us per phase at 10 M rows)
 #define PROF_INIT() const int prof_row = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1); \
-    unsigned long long prof_t = (prof_row >= 0 && threadIdx.x == 0) ? gtime() : 0ULL; \
-    unsigned long long blk_t = (S.blkprof && threadIdx.x == 0) ? gtime() : 0ULL; \
-    if (S.blkprof && threadIdx.x == 0) { unsigned int sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); S.blkprof[blockIdx.x * 10 + 8] = sm_; }
-#define PROF(k) do { if (prof_row >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
-    S.prof[prof_row * 16 + (k)] += t_ - prof_t; prof_t = t_; } \
-    if (S.blkprof && threadIdx.x == 0) { const unsigned long long t_ = gtime(); \
-    S.blkprof[blockIdx.x * 10 + (k)] += t_ - blk_t; blk_t = t_; } } while (0)
+    __shared__ unsigned long long s_prof[8]; \
+    const bool prof_on = threadIdx.x == 0 && (prof_row >= 0 || S.blkprof != nullptr); \
+    if (prof_on) { for (int k_ = 0; k_ < 8; ++k_) s_prof[k_] = 0ULL; } \
+    unsigned long long prof_t = prof_on ? gtime() : 0ULL
+#define PROF(k) do { if (prof_on) { const unsigned long long t_ = gtime(); s_prof[(k)] += t_ - prof_t; prof_t = t_; } } while (0)
+#define PROF_FLUSH() do { if (prof_on) { \
+    if (prof_row >= 0) { for (int k_ = 0; k_ < 8; ++k_) S.prof[prof_row * 16 + k_] += s_prof[k_]; } \
+    if (S.blkprof) { unsigned int sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); \
+        for (int k_ = 0; k_ < 8; ++k_) S.blkprof[blockIdx.x * 10 + k_] += s_prof[k_]; S.blkprof[blockIdx.x * 10 + 8] = sm_; } } } while (0)
 
 // scaled right-hand side and Jacobi factor of one row (explicit roundings: the owner's loop and the halo push
 // must produce the same bits)
@@ -376,12 +382,20 @@ tc_dist_theta_kernel(TcDistK S) {
             PROF(4);
             // x += alpha p feeds neither this reduction nor another block: it runs while the block waits for the
             // slowest rank's sums (split-phase barrier), 3 of the 7 streams of the update phase
+            // (with many rows per GPU the phases are bandwidth bound and nothing hides: there the update rides on the
+            // direction phase, which reads p anyway — one stream less, as in the single-GPU kernel)
             dist_reduce<2>(S, gen, red, ++rseq, [&]() {
-                for (int i = gtid; i < n; i += gsz) S.x[i] += alpha * pe[i];
+                if (!S.x_in_dir)
+                    for (int i = gtid; i < n; i += gsz) S.x[i] += alpha * pe[i];
             });
             PROF(5);
             ++it;
-            if (!(red[1] > tol2)) { status = isfinite(red[1]) ? 0 : 2; break; }
+            if (!(red[1] > tol2)) {
+                status = isfinite(red[1]) ? 0 : 2;
+                if (S.x_in_dir)
+                    for (int i = gtid; i < n; i += gsz) S.x[i] += alpha * pe[i];
+                break;
+            }
             const double beta = red[0] / rho;
             double* pn = S.p[pb ^ 1];
             ++hseq;
@@ -391,7 +405,15 @@ tc_dist_theta_kernel(TcDistK S) {
                 ll_store(S.peer_p_gl[pb ^ 1][S.send_peer[e]] + 2 * S.send_dst[e],
                          __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i])), hseq);
             }
-            for (int i = gtid; i < n; i += gsz) pn[i] = __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i]));
+            if (S.x_in_dir) {
+                for (int i = gtid; i < n; i += gsz) {
+                    const double pi = pe[i];
+                    S.x[i] += alpha * pi;
+                    pn[i] = __fma_rn(beta, pi, __dmul_rn(S.dinv[i], S.r[i]));
+                }
+            } else {
+                for (int i = gtid; i < n; i += gsz) pn[i] = __fma_rn(beta, pe[i], __dmul_rn(S.dinv[i], S.r[i]));
+            }
             rho = red[0];
             pb ^= 1;
             PROF(6);
@@ -406,6 +428,7 @@ tc_dist_theta_kernel(TcDistK S) {
     } else if (status != 2) {
         for (int i = gtid; i < n; i += gsz) S.y[i] += S.h * S.x[i];
     }
+    PROF_FLUSH();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         S.state[0] = rseq; S.state[1] = (int)hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
         if (status) { S.state[7] = status; S.state[8] += 1; }
@@ -570,6 +593,7 @@ tc_dist_theta_pipe_kernel(TcDistK S) {
     // ---- y += h * z (not committed after a communication failure / breakdown) ----------------------------
     if (status != 2)
         for (int i = gtid; i < n; i += gsz) S.y[i] += S.h * S.x[i];
+    PROF_FLUSH();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         S.state[0] = rseq; S.state[1] = (int)hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
         if (status) { S.state[7] = status; S.state[8] += 1; }
@@ -746,6 +770,7 @@ tc_dist_theta_sr_kernel(TcDistK S) {
         if (SOLVE) { for (int i = gtid; i < n; i += gsz) S.x_out[i] = status != 2 ? S.x[i] : nan(""); }
         else if (status != 2) { for (int i = gtid; i < n; i += gsz) S.y[i] += S.h * S.x[i]; }
     }
+    PROF_FLUSH();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         S.state[0] = rseq; S.state[1] = (int)hseq; S.state[2] = it; S.state[3] += it; S.state[5] += 1;
         if (status) { S.state[7] = status; S.state[8] += 1; }
@@ -987,6 +1012,11 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     }
     K.state = d->state;
     K.prof = d->prof;
+    {
+        const char* xe = getenv("TC_DIST_X_IN_DIR");                 // rows per GPU from which the x update is merged
+        const long long thr = xe ? atoll(xe) : 4000000LL;
+        K.x_in_dir = d->n >= thr ? 1 : 0;
+    }
     int dev = 0, sms = 148, occ = 0, khz = 1965000;
     TC_CUDA(cudaGetDevice(&dev));
     TC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

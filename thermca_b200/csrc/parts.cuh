@@ -68,21 +68,71 @@ __device__ __forceinline__ double tc_row_group(double sum, const double* v, cons
     for (int j = 0; j < N; ++j) sum = __dadd_rn(sum, __dmul_rn(vv[j], xx[j]));
     return sum;
 }
-// Row sum of one slice (one row per lane), entries in stored order.  All lanes of a slice share its width, so the
-// tail (width mod 4) is ONE group behind a warp-uniform branch: a per-entry tail loop costs two dependent memory
-// round trips per entry (load value/index -> gather), and the warps are latency bound (measured: an SM that runs one
-// block finishes its slices no sooner than an SM that runs two) — for the 15-wide rows of a tetrahedral mesh the
-// tail loop was half of the 12 round trips of a slice.
+// Last full group (its indices `cc` are already here) and the R-entry tail of a row: the tail indices travel with the
+// group's values, the tail values with the group's gathers.
+template <int R, int NC_X, bool EF, class CT>
+__device__ __forceinline__ double tc_row_finish(double sum, const double* v, const CT* c, const double* xb, const int* cc,
+                                                unsigned long long pol) {
+    double vv[4], xx[4];
+    int tc[R > 0 ? R : 1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) vv[j] = ldm_f64<EF>(v + 32 * j, pol);
+#pragma unroll
+    for (int j = 0; j < R; ++j) tc[j] = tc_ld_idx(c + 32 * (4 + j), pol, EF);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xx[j] = tc_ld_x<NC_X>(xb + cc[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sum = __dadd_rn(sum, __dmul_rn(vv[j], xx[j]));
+    if (R > 0) {
+        double tv[R > 0 ? R : 1], tx[R > 0 ? R : 1];
+#pragma unroll
+        for (int j = 0; j < R; ++j) tv[j] = ldm_f64<EF>(v + 32 * (4 + j), pol);
+#pragma unroll
+        for (int j = 0; j < R; ++j) tx[j] = tc_ld_x<NC_X>(xb + tc[j]);
+#pragma unroll
+        for (int j = 0; j < R; ++j) sum = __dadd_rn(sum, __dmul_rn(tv[j], tx[j]));
+    }
+    return sum;
+}
+// Row sum of one slice (one row per lane), entries in stored order (bit-identical to the sequential CSR product).
+// The warps are LATENCY bound (measured: an SM that runs one block finishes its slices no sooner than an SM that runs
+// two; 48 warps per SM with 40 registers are slower than 64 with 32), so what counts is the number of dependent
+// memory round trips per slice.  A group of four entries needs values, indices -> gathers -> sum: two round trips; here
+// the indices run ONE GROUP AHEAD (4 more registers), so a group's values, its gathers and the next group's indices
+// are in flight together: one round trip per group.  All lanes of a slice share its width, so the tail (width mod 4)
+// is handled behind warp-uniform branches, its indices prefetched with the last full group (a per-entry tail loop cost
+// two round trips per entry).  15-wide rows of a tetrahedral mesh: 13 -> 6 round trips per slice.
 template <int NC_X, bool EF, class CT>
 __device__ __forceinline__ double tc_row_sum_cols(const double* v, const CT* c, const double* xb, int width,
                                                   unsigned long long pol) {
     double sum = 0.0;
-    int k = 0;
-    for (; k + 4 <= width; k += 4) sum = tc_row_group<4, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, pol);
-    const int rem = width - k;
-    if (rem == 3) sum = tc_row_group<3, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, pol);
-    else if (rem == 2) sum = tc_row_group<2, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, pol);
-    else if (rem == 1) sum = tc_row_group<1, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, pol);
+    if (width >= 4) {
+        int cc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cc[j] = tc_ld_idx(c + 32 * j, pol, EF);
+        int k = 0;
+        for (; k + 8 <= width; k += 4) {                               // another full group follows
+            double vv[4], xx[4];
+            int nc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vv[j] = ldm_f64<EF>(v + 32 * (k + j), pol);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nc[j] = tc_ld_idx(c + 32 * (k + 4 + j), pol, EF);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xx[j] = tc_ld_x<NC_X>(xb + cc[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sum = __dadd_rn(sum, __dmul_rn(vv[j], xx[j]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cc[j] = nc[j];
+        }
+        const int rem = width - k - 4;                                 // 0 .. 3, warp uniform
+        if (rem == 3) sum = tc_row_finish<3, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, cc, pol);
+        else if (rem == 2) sum = tc_row_finish<2, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, cc, pol);
+        else if (rem == 1) sum = tc_row_finish<1, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, cc, pol);
+        else sum = tc_row_finish<0, NC_X, EF>(sum, v + 32 * k, c + 32 * k, xb, cc, pol);
+    } else if (width == 3) sum = tc_row_group<3, NC_X, EF>(sum, v, c, xb, pol);
+    else if (width == 2) sum = tc_row_group<2, NC_X, EF>(sum, v, c, xb, pol);
+    else if (width == 1) sum = tc_row_group<1, NC_X, EF>(sum, v, c, xb, pol);
     return sum;
 }
 // xrow_off: index of local row 0 in the gathered vector (row partition: x is addressed by

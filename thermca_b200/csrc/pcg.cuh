@@ -98,8 +98,9 @@ __device__ __forceinline__ unsigned long long tc_gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define PCG_PROF(k) do { if (S.prof && blockIdx.x == 0 && threadIdx.x == 0) { const unsigned long long t_ = tc_gtime(); \
-    S.prof[(k)] += t_ - prof_t; prof_t = t_; } } while (0)
+// accumulated in shared memory, flushed once per launch: a global read-modify-write per phase is an exposed memory
+// round trip of thread 0 in front of every barrier
+#define PCG_PROF(k) do { if (prof_on) { const unsigned long long t_ = tc_gtime(); s_prof[(k)] += t_ - prof_t; prof_t = t_; } } while (0)
 
 // MB = resident blocks per SM the register allocation is tuned for (occupancy matters: the kernel
 // is latency/bandwidth bound; measured on B200, see profiles/).
@@ -116,7 +117,10 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
     __shared__ double sh[32];
     unsigned int gen = 0u;
     const double shift = S.coef * S.ctrl[1];
-    unsigned long long prof_t = (S.prof && blockIdx.x == 0 && threadIdx.x == 0) ? tc_gtime() : 0ULL;
+    __shared__ unsigned long long s_prof[8];
+    const bool prof_on = S.prof && blockIdx.x == 0 && threadIdx.x == 0;
+    if (prof_on) { for (int k = 0; k < 8; ++k) s_prof[k] = 0ULL; }
+    unsigned long long prof_t = prof_on ? tc_gtime() : 0ULL;
     double red[2];
     {
         const int n = S.A.n;
@@ -152,9 +156,9 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
             {
                 const int n = S.A.n;
                 double rn = 0.0, rr = 0.0;
+                // x += alpha p is taken in the direction phase below, which reads p anyway (one stream less per
+                // iteration; same operations per element, so x is bit-identical)
                 for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-                    const double pi = S.p[i];
-                    S.x[i] += alpha * pi;
                     const double ri = S.r[i] - alpha * S.q[i];
                     S.r[i] = ri;
                     rn += ri * (S.dinv[i] * ri);
@@ -168,14 +172,29 @@ tc_pcg_coop_kernel(TcPcg S, const int* __restrict__ done_flag) {
             PCG_PROF(4);
             const double rho_new = red[0], rr = red[1];
             ++it;
-            if (!(rr > tol2)) { status = isfinite(rr) ? 0 : 2; break; }   // uniform
-            tc_pcg_dir_phase(S, rho_new / rho);
+            if (!(rr > tol2)) {                                           // uniform
+                status = isfinite(rr) ? 0 : 2;
+                const int n = S.A.n;                                      // the last x update
+                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+                    S.x[i] += alpha * S.p[i];
+                break;
+            }
+            {
+                const double beta = rho_new / rho;
+                const int n = S.A.n;
+                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+                    const double pi = S.p[i];
+                    S.x[i] += alpha * pi;
+                    S.p[i] = S.dinv[i] * S.r[i] + beta * pi;
+                }
+            }
             rho = rho_new;
             PCG_PROF(5);
             tc_grid_barrier(S.bar, gen);
             PCG_PROF(6);
         }
     }
+    if (prof_on) { for (int k = 0; k < 8; ++k) S.prof[k] += s_prof[k]; }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         S.isc[1] = it; S.isc[2] += it; S.isc[3] += 1;
         if (status) { S.isc[4] = status; S.isc[5] += 1; }
