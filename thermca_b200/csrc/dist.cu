@@ -76,6 +76,7 @@ struct TcDistK {
     int push_fence;                       // experiment switch (TC_DIST_PUSH_FENCE=1): system fence after ghost pushes
     unsigned long long* prof;             // [2][16] phase times in ns: block 0 and the last block
     unsigned long long* blkprof;          // optional (TC_DIST_DIAG=3): [block][10]: 8 phase times (ns), SM id
+    double* bstash;                       // n_bnd * 32: local row sums of the boundary slices between the two passes
     int x_in_dir;                         // x += alpha p rides on the direction phase (many rows per GPU) instead of
                                           // hiding behind the second all-reduce (few rows per GPU)
     // pipelined PCG (tc_dist_theta_pipe_kernel): extra vectors and the send lists grouped by boundary slice
@@ -231,7 +232,7 @@ __device__ __forceinline__ void slab_finish_row(const TcDistK& S, const double* 
 }
 // Two passes per warp: the streaming pass over ALL its slices leaves the local sums of boundary slices in y and
 // remembers their rounds in a bit mask; the ghost side lists (a non-inlined call with ~4 dependent loads) are added in
-// a second pass over those rounds only — the call, its argument registers and the spills around it stay out of the
+// a second pass over those rounds only (the local sums wait in a small scratch array) — the call, its argument registers and the spills around it stay out of the
 // streaming loop (with the call inside it the row accumulator lived in local memory: 12 % slower products than the
 // single-GPU kernel at 10 M rows), and the ghosts have had the whole pass to land.
 template <int MODE>
@@ -248,12 +249,13 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, 
     for (int idx = warp; idx < nsl; idx += nwarps) {
         int s = idx + S.rot;
         if (s >= nsl) s -= nsl;
-        const bool bnd = S.n_bnd && S.bidx[s] >= 0;                  // warp uniform
+        const int bi = S.n_bnd ? S.bidx[s] : -1;                     // warp uniform
         const double sum = slice_local_sum(A, xl, s, lane);
         const int row = s * 32 + lane;
-        if (bnd) {
+        if (bi >= 0) {
             bmask |= bit;
-            if (row < A.n) y[row] = sum;                             // local part, finished in the second pass
+            S.bstash[bi * 32 + lane] = sum;                          // local part, finished in the second pass (its own
+                                                                     // scratch: y may alias b, tc_dist_residual_kernel)
         } else if (row < A.n) {
             slab_finish_row<MODE>(S, xl, y, b, shift, row, sum, dot);
         }
@@ -269,7 +271,7 @@ __device__ __forceinline__ double slab_spmv(const TcDistK& S, const double* xl, 
             if (bi < 0) continue;                                    // a round that shares the mask bit (> 32 rounds)
             const double gs = ghost_part(S.gptr, S.gslot, S.gval, xg, bi, lane, hseq, S.state, S.spin_limit);
             const int row = s * 32 + lane;
-            if (row < A.n) slab_finish_row<MODE>(S, xl, y, b, shift, row, __dadd_rn(y[row], gs), dot);
+            if (row < A.n) slab_finish_row<MODE>(S, xl, y, b, shift, row, __dadd_rn(S.bstash[bi * 32 + lane], gs), dot);
         }
     }
     return dot;
@@ -812,6 +814,7 @@ struct tc_dist {
     std::vector<int> h_send_row, h_send_peer;      // host copies: regrouped by boundary slice for the pipelined kernel
     std::vector<long long> h_send_dst;
     double *zh = nullptr, *pv = nullptr, *cc = nullptr;
+    double* bstash = nullptr;
     int *sptr = nullptr, *s_lane = nullptr, *s_peer = nullptr; long long* s_dst = nullptr;
     int pcg_mode = 0;                 // 0 classic (two reductions + barrier), 1 pipelined (one sweep, one reduction)
     bool pipe_ok = false;             // every send row lies in a boundary slice (true for symmetric patterns)
@@ -1012,6 +1015,9 @@ extern "C" int tc_dist_set_operator(tc_dist* d, int32_t nslices, const int64_t* 
     }
     K.state = d->state;
     K.prof = d->prof;
+    cudaFree(d->bstash); d->bstash = nullptr;
+    TC_CUDA(cudaMalloc(&d->bstash, sizeof(double) * 32 * (size_t)(n_bnd > 0 ? n_bnd : 1)));
+    K.bstash = d->bstash;
     {
         const char* xe = getenv("TC_DIST_X_IN_DIR");                 // rows per GPU from which the x update is merged
         const long long thr = xe ? atoll(xe) : 4000000LL;
@@ -1374,7 +1380,7 @@ extern "C" int tc_dist_destroy(tc_dist* d) {
     cudaFree(d->state); cudaFree(d->prof); cudaFree(d->blkprof);
     cudaFree(d->K.bar.ctr); cudaFree(d->K.bar.part); cudaFree(d->K.bar.res);
     cudaFree(d->send_row); cudaFree(d->send_peer); cudaFree(d->send_dst);
-    cudaFree(d->zh); cudaFree(d->pv); cudaFree(d->cc);
+    cudaFree(d->zh); cudaFree(d->pv); cudaFree(d->cc); cudaFree(d->bstash);
     cudaFree(d->sptr); cudaFree(d->s_lane); cudaFree(d->s_peer); cudaFree(d->s_dst);
     delete d;
     return 0;
