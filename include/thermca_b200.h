@@ -227,6 +227,8 @@ int tc_dist_create(tc_dist** out, void* cuda_stream, int32_t rank, int32_t world
 int tc_dist_ipc_handle(tc_dist* d, void* handle64);
 /* handles: world x 64 bytes; peer_ghost[w] = ghost count of rank w */
 int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t* peer_ghost);
+/* test harness: the "ranks" are sibling handles of ONE process on one GPU (own streams); all[w] = handle of rank w */
+int tc_dist_open_peers_local(tc_dist* d, tc_dist* const* all, const int64_t* peer_ghost);
 /* halo plan (host arrays, copied): entry e sends local row send_row[e] to ghost slot send_dst[e] of rank
  * send_peer[e]; nbr = ranks this rank trades ghosts with */
 int tc_dist_set_halo(tc_dist* d, int64_t n_send, const int32_t* send_row, const int32_t* send_peer,

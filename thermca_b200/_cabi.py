@@ -89,6 +89,7 @@ EXPORTS = {
     "tc_dist_create": (i32, [C.POINTER(vp), vp, i32, i32, i64, i64]),
     "tc_dist_ipc_handle": (i32, [vp, vp]),
     "tc_dist_open_peers": (i32, [vp, vp, C.POINTER(i64)]),
+    "tc_dist_open_peers_local": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
     "tc_dist_set_halo": (i32, [vp, i64, vp, vp, vp, i32, vp]),
     "tc_dist_set_operator": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "tc_dist_set_load": (i32, [vp, vp]),

@@ -824,6 +824,7 @@ struct tc_dist {
     TcDistK K;
     int grid = 0;
     bool peers_open = false;
+    bool peers_local = false;         // peers are sibling handles of this process (tc_dist_open_peers_local): no IPC mappings
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -889,6 +890,22 @@ extern "C" int tc_dist_open_peers(tc_dist* d, const void* handles, const int64_t
         d->peer[w] = (char*)p;
     }
     d->peers_open = true;
+    return 0;
+}
+
+// Same-process variant (test harness: several "ranks" as sibling handles on ONE GPU, each on its own stream, so that a
+// single-GPU box reaches the ghost side lists, send lists and mailboxes): the peers' buffers are plain device pointers.
+// The kernels of the sibling ranks must be able to run concurrently (small grids); a rank that never sees its peer
+// times out (TC_DIST_TIMEOUT_S) and reports -3 as usual.
+extern "C" int tc_dist_open_peers_local(tc_dist* d, tc_dist* const* all, const int64_t* peer_ghost) {
+    for (int w = 0; w < d->world; ++w) {
+        d->peer_ghost[w] = peer_ghost[w];
+        if (w == d->rank) continue;
+        TC_CHECK(all[w] && all[w]->rank == w && all[w]->world == d->world && all[w]->comm, "sibling handle");
+        d->peer[w] = all[w]->comm;
+    }
+    d->peers_open = true;
+    d->peers_local = true;
     return 0;
 }
 
@@ -1369,7 +1386,7 @@ extern "C" int tc_dist_close_peers(tc_dist* d) {
     if (!d) return 0;
     cudaStreamSynchronize(d->stream);
     for (int w = 0; w < d->world; ++w)
-        if (w != d->rank && d->peer[w]) { cudaIpcCloseMemHandle(d->peer[w]); d->peer[w] = nullptr; }
+        if (w != d->rank && d->peer[w]) { if (!d->peers_local) cudaIpcCloseMemHandle(d->peer[w]); d->peer[w] = nullptr; }
     d->peers_open = false;
     return 0;
 }
