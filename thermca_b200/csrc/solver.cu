@@ -557,6 +557,9 @@ extern "C" int tc_finalize(tc_handle s, int64_t n_state) {
 }
 
 // ---- right-hand side pipeline (thermca/solver.py:193-302) ---------------------------------
+#ifndef TC_RHS_COL16_DEFAULT
+#define TC_RHS_COL16_DEFAULT 1
+#endif
 static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* out) {
     cudaStream_t st = s->stream;
     const int* done = s->flags + FL_DONE;
@@ -604,7 +607,11 @@ static int enqueue_rhs(tc_solver* s, double c_stage, const double* yin, double* 
         }
         const int g = grid_for(p.A.nslices, TC_SPMV_THREADS / 32, s->sm_count * 8);
         TcSell Ar = p.A;
-        Ar.col16 = nullptr;      // measured: 16-bit columns pay off in the PCG kernel (+2.7 %) but not here (-3.6 %)
+        // 16-bit relative columns in the right-hand side product too (TC_RHS_COL16=0 switches back): with the per-entry
+        // tail loop of round 1 they lost 3.6 %, with the grouped tail and the indices one group ahead (parts.cuh) an
+        // explicit RK45 attempt on the 10 M mesh takes 2.56 instead of 2.74 ms (same bits: the columns are the same)
+        static const int rhs_col16 = [] { const char* e = getenv("TC_RHS_COL16"); return e ? atoi(e) : TC_RHS_COL16_DEFAULT; }();
+        if (!rhs_col16) Ar.col16 = nullptr;
         tc_sell_spmv_kernel<SPMV_NEG><<<g, TC_SPMV_THREADS, 0, st>>>(
             Ar, yin + p.d.y_off, out + p.d.y_off, nullptr, nullptr, s->ctrl, 0.0, nullptr, done);
         if (p.load.nrows > 0)
