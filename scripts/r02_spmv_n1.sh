@@ -1,4 +1,5 @@
-# single GPU: dist kernel (world 1) at three sizes + the bench line of the solver path
+# single GPU: dist kernel (world 1) at two sizes + the bench line of the solver path; the development series of the
+# product (row tail, indices ahead, profiler, block shape via TC_PCG_THREADS=768) in profiles/README.md came from this script
 export TC_DIST_TIMEOUT_S=10 RANK=0 WORLD_SIZE=1 LOCAL_RANK=0 MASTER_ADDR=127.0.0.1 MASTER_PORT=29571
 timeout 300 python scripts/dist_check.py 2>&1 | grep "FAILED\|dist_check ok" | cut -c1-200
 for r in 1300000 10350000; do
