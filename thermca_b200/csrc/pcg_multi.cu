@@ -44,6 +44,23 @@ __device__ __forceinline__ void pm_bank_sums(const double* bank, int G, int K, d
     __syncthreads();
 }
 
+// N stored entries of one row against the KT interleaved vectors: N value + N column loads in flight, then the gathers
+#define PM_GROUP 4
+template <int N, int KT>
+__device__ __forceinline__ void pm_row_group(const TcPcgMulti& S, long long pos, double* sum) {
+    double v[N];
+    long long c[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) v[t] = ld_stream_f64(S.val + pos + 32LL * t);
+#pragma unroll
+    for (int t = 0; t < N; ++t) c[t] = ld_stream_s32(S.col + pos + 32LL * t);
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) sum[k] += v[t] * S.p[c[t] * KT + k];
+    }
+}
+
 // KT = number of right-hand sides (compile time: exact unrolling, registers and occupancy scale with it)
 template <int KT>
 __global__ void __launch_bounds__(PM_THREADS, (KT <= 2 ? 6 : (KT <= 4 ? 4 : 2)))
@@ -105,12 +122,17 @@ tc_pcg_multi_kernel(TcPcgMulti S) {
             double sum[KT];
 #pragma unroll
             for (int k = 0; k < KT; ++k) sum[k] = 0.0;
-            for (int j = 0; j < width; ++j) {
-                const double v = ld_stream_f64(S.val + base + 32LL * j + lane);
-                const long long c = ld_stream_s32(S.col + base + 32LL * j + lane);
-#pragma unroll
-                for (int k = 0; k < KT; ++k)
-                    if (k < K) sum[k] += v * S.p[c * K + k];
+            // values and columns of a group of entries travel together (one round trip per group instead of one per
+            // entry: the warps are latency bound, parts.cuh); the tail is one group behind a warp-uniform branch;
+            // the sums keep the stored entry order
+            int j = 0;
+            for (; j + PM_GROUP <= width; j += PM_GROUP)
+                pm_row_group<PM_GROUP, KT>(S, base + 32LL * j + lane, sum);
+            switch (width - j) {                                   // warp uniform (all lanes share the width)
+                case 3: pm_row_group<3, KT>(S, base + 32LL * j + lane, sum); break;
+                case 2: pm_row_group<2, KT>(S, base + 32LL * j + lane, sum); break;
+                case 1: pm_row_group<1, KT>(S, base + 32LL * j + lane, sum); break;
+                default: break;
             }
             if (row < n) {
 #pragma unroll
